@@ -1,0 +1,83 @@
+// Shared declarations for libcns_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/cns_b200.h"
+
+namespace cns {
+
+constexpr int H = CNS_HIDDEN_DIM;  // 128
+
+void set_error(const char* fmt, ...);
+
+#define CNS_CUDA_CHECK(expr)                                                            \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      cns::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return CNS_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+#define CNS_LAUNCH_CHECK() CNS_CUDA_CHECK(cudaGetLastError())
+
+#define CNS_REQUIRE(cond, msg)                                   \
+  do {                                                           \
+    if (!(cond)) {                                               \
+      cns::set_error("%s:%d %s", __FILE__, __LINE__, msg);       \
+      return CNS_ERR_INVALID_ARGUMENT;                           \
+    }                                                            \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- canonical parameter table (state-dict order of checkpoints/cns_state_dict.pth) ----
+enum ParamId {
+  P_IN_W = 0, P_IN_B, P_POS0_W, P_POS0_B, P_POS1_W, P_POS1_B, P_ATT0_W, P_ATT0_B, P_ATT1_W, P_ATT1_B,
+  P_LIN_W, P_LINSRC_W, P_LINDST_W, P_OUT_W, P_OUT_B,
+  P_C0_MSG_W, P_C0_MSG_B, P_C0_BN_W, P_C0_BN_B, P_C0_BN_MS, P_C0_FC_W, P_C0_FC_B,
+  P_G_MSG_W, P_G_MSG_B, P_K_MSG_W, P_K_MSG_B,
+  P_C1_MSG_W, P_C1_MSG_B, P_C1_BN_W, P_C1_BN_B, P_C1_BN_MS, P_C1_FC_W, P_C1_FC_B,
+  P_POOL_W, P_POOL_B, P_VEC0_W, P_VEC0_B, P_VEC1_W, P_VEC1_B, P_NRM0_W, P_NRM0_B, P_NRM1_W, P_NRM1_B,
+  P_COUNT
+};
+static_assert(P_COUNT == CNS_NUM_PARAM_TENSORS, "param table");
+
+struct ParamInfo { const char* name; int rows; int cols; };
+extern const ParamInfo kParams[P_COUNT];
+
+// Packed, device-resident GEMM operands derived from the raw parameters.
+struct Packed {
+  // encoder edge chain: 5 (k=128, o=128) matrices, k-major rows ("transposed" weights):
+  //   0: pos_nn.fcs.1^T   1: -lin_src^T   2: lin^T   3: attn_nn.fcs.0^T   4: attn_nn.fcs.1^T
+  float* enc_chain;      // [5][128][128]
+  float* lin_dst_t;      // [128][128]
+  float* out_t;          // [256][128]
+  // PointEdgeConv factorisation  PQ = X @ wt + pos @ wp + b ; columns [P (f) | Q (f)]
+  float* c0_wt; float* c0_wp; float* c0_b;      // [128][256], [2][256], [256]
+  float* g_wt;  float* g_wp;  float* g_b;       // [256][512], [2][512], [512]
+  float* k_wt;  float* k_wp;  float* k_b;       // [256][256], [2][256], [256]
+  float* c1_wt; float* c1_wp; float* c1_b;      // [128][256], [2][256], [256]
+  float* c0_fc_t; float* c1_fc_t;               // [128][128]
+  float* vec0_t; float* nrm0_t;                 // [128][128]
+};
+
+}  // namespace cns
+
+struct cns_handle {
+  int device;
+  int precision;
+  int sm_count;
+  float* raw;                       // all 43 tensors, concatenated, fp32 (device)
+  size_t raw_off[cns::P_COUNT + 1]; // element offsets into raw
+  float* packed_base;
+  cns::Packed pk;
+  bool weights_loaded;
+  // pinned / device staging for the *_host entry point
+  void* stage_host; size_t stage_host_bytes;
+  void* stage_dev;  size_t stage_dev_bytes;
+  const float* P(int id) const { return raw + raw_off[id]; }
+};

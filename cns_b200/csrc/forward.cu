@@ -1,0 +1,294 @@
+// GraphVS.forward + postprocess as one enqueue of kernels on the caller's stream
+// (cns/models/graph_vs.py:284-322, cns/models/functions.py:26-38).
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace cns {
+
+// Bump allocator over the caller's workspace; first pass (base == nullptr) only measures.
+struct Arena {
+  char* base; size_t off;
+  explicit Arena(void* b) : base((char*)b), off(0) {}
+  template <typename T> T* take(size_t n) {
+    size_t o = off;
+    off += align_up(n * sizeof(T));
+    return base ? reinterpret_cast<T*>(base + o) : nullptr;
+  }
+};
+
+struct FwdBuffers {
+  int* err; int* clu_rowptr; int* clu_graph; int* graph_ptr; int* gp_tmp; int* scan_scratch;
+  int* cur_rowptr; int* cur_src; int* tar_rowptr; int* tar_src; void* csr_ws;
+  float* a_dst; float* pos_clu; float* clu_feat; float* partial; float* x_clu;
+  float* pq; float* conv; float* gn; float* x1; float* u; float* hr; float* x2; float* gate;
+  int64_t n_slots;
+};
+
+static void carve(Arena& ar, const cns_batch* b, FwdBuffers& f) {
+  const int64_t C = b->n_clusters, B = b->n_graphs;
+  const int64_t tiles = (b->n_e01 + ENC_TILE_E - 1) / ENC_TILE_E;
+  f.n_slots = C + 2 * tiles + 2;
+  f.err = ar.take<int>(64);
+  f.clu_rowptr = ar.take<int>(C + 1);
+  f.clu_graph = ar.take<int>(C + 1);
+  f.graph_ptr = ar.take<int>(B + 1);
+  f.gp_tmp = ar.take<int>(B + 1);
+  f.scan_scratch = (int*)ar.take<char>(scan_scratch_bytes(B + 1));
+  f.cur_rowptr = ar.take<int>(C + 1);
+  f.cur_src = ar.take<int>(b->n_e11_cur + 1);
+  f.tar_rowptr = ar.take<int>(C + 1);
+  f.tar_src = ar.take<int>(b->n_e11_tar + 1);
+  f.csr_ws = ar.take<char>(csr_workspace_bytes(C));
+  f.a_dst = ar.take<float>(C * H);
+  f.pos_clu = ar.take<float>(C * 2 + 2);
+  f.clu_feat = ar.take<float>(2 * C * H);
+  f.partial = ar.take<float>((size_t)2 * f.n_slots * 3 * H);
+  f.x_clu = ar.take<float>(C * H);
+  f.pq = ar.take<float>(C * 4 * H);
+  f.conv = ar.take<float>(C * H);
+  f.gn = ar.take<float>(C * H);
+  f.x1 = ar.take<float>(C * H);
+  f.u = ar.take<float>(C * H);
+  f.hr = ar.take<float>(C * H);
+  f.x2 = ar.take<float>(C * H);
+  f.gate = ar.take<float>(C + 1);
+}
+
+static int validate(const cns_batch* b) {
+  CNS_REQUIRE(b != nullptr, "batch is NULL");
+  CNS_REQUIRE(b->n_nodes >= 0 && b->n_clusters >= 0 && b->n_graphs >= 0 && b->n_e01 >= 0 &&
+              b->n_e11_cur >= 0 && b->n_e11_tar >= 0, "negative size in cns_batch");
+  CNS_REQUIRE(b->n_nodes < (1ll << 31) && b->n_clusters < (1ll << 31) && b->n_e01 < (1ll << 31) &&
+              b->n_e11_cur < (1ll << 31) && b->n_e11_tar < (1ll << 31), "sizes must fit int32");
+  if (b->n_nodes > 0) CNS_REQUIRE(b->x_cur && b->x_tar && b->pos_cur && b->pos_tar, "NULL keypoint tensor");
+  if (b->n_e01 > 0) CNS_REQUIRE(b->l0_to_l1_j && b->l0_to_l1_i, "NULL l0_to_l1 edge list");
+  if (b->n_e11_cur > 0) CNS_REQUIRE(b->l1_edge_cur, "NULL l1_dense_edge_index_cur");
+  if (b->n_e11_tar > 0) CNS_REQUIRE(b->l1_edge_tar, "NULL l1_dense_edge_index_tar");
+  if (b->n_clusters > 0) CNS_REQUIRE(b->cluster_mask && b->cluster_centers, "NULL cluster tensor");
+  if (b->n_graphs > 0) CNS_REQUIRE(b->num_clusters, "NULL num_clusters");
+  return CNS_OK;
+}
+
+int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, float* vel_si_vec,
+                 float* vel_si_norm, float* hidden_out, float* vel, void* workspace, cudaStream_t s) {
+  Arena ar(workspace);
+  FwdBuffers f;
+  carve(ar, b, f);
+  const int64_t C = b->n_clusters, B = b->n_graphs;
+  const Packed& pk = h->pk;
+  int rc;
+#define RUN(expr) if ((rc = (expr)) != CNS_OK) return rc;
+
+  CNS_CUDA_CHECK(cudaMemsetAsync(f.err, 0, 64 * sizeof(int), s));
+  // ---- index preparation ------------------------------------------------------------------
+  RUN(sorted_rowptr(b->l0_to_l1_i, b->n_e01, C, f.clu_rowptr, f.err, s));
+  RUN(graph_ptr_from_counts(b->num_clusters, B, f.graph_ptr, f.gp_tmp, f.scan_scratch, s));
+  const int64_t cur_stride = b->l1_cur_stride ? b->l1_cur_stride : b->n_e11_cur;
+  const int64_t tar_stride = b->l1_tar_stride ? b->l1_tar_stride : b->n_e11_tar;
+  RUN(csr_by_dst(b->l1_edge_cur, b->l1_edge_cur + cur_stride, b->n_e11_cur, C, f.cur_rowptr, f.cur_src, f.csr_ws, f.err, s));
+  RUN(csr_by_dst(b->l1_edge_tar, b->l1_edge_tar + tar_stride, b->n_e11_tar, C, f.tar_rowptr, f.tar_src, f.csr_ws, f.err, s));
+
+  // ---- encoder ----------------------------------------------------------------------------
+  EncPreArgs pre{};
+  pre.n_clusters = C; pre.x_tar = b->x_tar; pre.pos_tar = b->pos_tar; pre.centers = b->cluster_centers;
+  pre.node_graph = b->node_graph; pre.w_in = h->P(P_IN_W); pre.b_in = h->P(P_IN_B); pre.lin_dst_t = pk.lin_dst_t;
+  pre.a_dst = f.a_dst; pre.pos_clu = f.pos_clu; pre.clu_graph = f.clu_graph;
+  RUN(enc_cluster_pre(pre, s));
+
+  EncEdgeArgs ee{};
+  ee.n_e01 = b->n_e01; ee.n_clusters = C; ee.n_slots = f.n_slots;
+  ee.x_cur = b->x_cur; ee.x_tar = b->x_tar; ee.pos_cur = b->pos_cur; ee.pos_tar = b->pos_tar;
+  ee.ej = b->l0_to_l1_j; ee.ei = b->l0_to_l1_i;
+  ee.pos_clu = f.pos_clu; ee.a_dst = f.a_dst; ee.clu_rowptr = f.clu_rowptr;
+  ee.w_in = h->P(P_IN_W); ee.b_in = h->P(P_IN_B); ee.w_p0 = h->P(P_POS0_W); ee.b_p0 = h->P(P_POS0_B);
+  ee.enc_chain = pk.enc_chain; ee.b_p1 = h->P(P_POS1_B); ee.b_a0 = h->P(P_ATT0_B); ee.b_a1 = h->P(P_ATT1_B);
+  ee.clu_feat = f.clu_feat; ee.partial = f.partial;
+  if (h->precision == CNS_PREC_FP32) {
+    RUN(enc_edge_fp32(ee, s));
+  } else {
+    RUN(enc_edge_tc(ee, h->precision, nullptr, h->sm_count, s));
+  }
+
+  EncFinishArgs ef{};
+  ef.n_clusters = C; ef.n_slots = f.n_slots; ef.clu_rowptr = f.clu_rowptr; ef.partial = f.partial;
+  ef.clu_feat = f.clu_feat; ef.out_t = pk.out_t; ef.b_out = h->P(P_OUT_B); ef.cluster_mask = b->cluster_mask;
+  ef.x_clu = f.x_clu;
+  RUN(enc_finish(ef, s));
+
+  // ---- backbone ---------------------------------------------------------------------------
+  auto pq_linear = [&](const float* x1, const float* x2, const float* wt, const float* wp, const float* bias,
+                       int n_out) {
+    LinearArgs la{};
+    la.m = C; la.k1 = H; la.k2 = x2 ? H : 0; la.n_out = n_out;
+    la.x1 = x1; la.x2 = x2; la.wt = wt; la.bias = bias; la.pos = f.pos_clu; la.wp = wp;
+    la.residual = nullptr; la.relu = 0; la.y = f.pq;
+    return linear(la, s);
+  };
+  auto perconv = [&](const float* x, const float* wt, const float* wp, const float* bias, int bn_w, int bn_b,
+                     int bn_ms, const float* fc_t, int fc_b, float* y) {
+    int r;
+    if ((r = pq_linear(x, nullptr, wt, wp, bias, 2 * H)) != CNS_OK) return r;
+    EdgeConvArgs ec{};
+    ec.n_rows = C; ec.f_out = H; ec.mode = EC_PLAIN; ec.pq = f.pq; ec.rowptr = f.cur_rowptr; ec.src = f.cur_src;
+    ec.out = f.conv;
+    if ((r = edgeconv_max(ec, s)) != CNS_OK) return r;
+    GraphNormArgs gn{};
+    gn.n_graphs = B; gn.graph_ptr = f.graph_ptr; gn.x = f.conv; gn.weight = h->P(bn_w); gn.bias = h->P(bn_b);
+    gn.mean_scale = h->P(bn_ms); gn.y = f.gn; gn.stats = nullptr;
+    if ((r = graphnorm_relu(gn, s)) != CNS_OK) return r;
+    LinearArgs la{};
+    la.m = C; la.k1 = H; la.k2 = 0; la.n_out = H; la.x1 = f.gn; la.wt = fc_t; la.bias = h->P(fc_b);
+    la.residual = x; la.relu = 1; la.y = y;   // F.relu(l1_conv(x)) of Backbone.forward folded in
+    return linear(la, s);
+  };
+
+  RUN(perconv(f.x_clu, pk.c0_wt, pk.c0_wp, pk.c0_b, P_C0_BN_W, P_C0_BN_B, P_C0_BN_MS, pk.c0_fc_t, P_C0_FC_B, f.x1));
+
+  // GRU gates on the TARGET cluster graph, candidate on the CURRENT one (graph_vs.py:246-249)
+  RUN(pq_linear(f.x1, hidden_in, pk.g_wt, pk.g_wp, pk.g_b, 4 * H));
+  {
+    EdgeConvArgs ec{};
+    ec.n_rows = C; ec.f_out = 2 * H; ec.mode = EC_GATES; ec.pq = f.pq; ec.rowptr = f.tar_rowptr; ec.src = f.tar_src;
+    ec.h = hidden_in; ec.hr = f.hr; ec.u = f.u;
+    RUN(edgeconv_max(ec, s));
+  }
+  RUN(pq_linear(f.x1, hidden_in ? f.hr : nullptr, pk.k_wt, pk.k_wp, pk.k_b, 2 * H));
+  {
+    EdgeConvArgs ec{};
+    ec.n_rows = C; ec.f_out = H; ec.mode = EC_CANDIDATE; ec.pq = f.pq; ec.rowptr = f.cur_rowptr; ec.src = f.cur_src;
+    ec.h = hidden_in; ec.u_in = f.u; ec.h_out = hidden_out;
+    RUN(edgeconv_max(ec, s));
+  }
+  RUN(perconv(hidden_out, pk.c1_wt, pk.c1_wp, pk.c1_b, P_C1_BN_W, P_C1_BN_B, P_C1_BN_MS, pk.c1_fc_t, P_C1_FC_B, f.x2));
+
+  // ---- decoder ----------------------------------------------------------------------------
+  PoolHeadArgs ph{};
+  ph.n_graphs = B; ph.graph_ptr = f.graph_ptr; ph.x = f.x2; ph.cluster_mask = b->cluster_mask;
+  ph.pool_w = h->P(P_POOL_W); ph.pool_b = h->P(P_POOL_B);
+  ph.vec0_t = pk.vec0_t; ph.vec0_b = h->P(P_VEC0_B); ph.vec1_w = h->P(P_VEC1_W); ph.vec1_b = h->P(P_VEC1_B);
+  ph.nrm0_t = pk.nrm0_t; ph.nrm0_b = h->P(P_NRM0_B); ph.nrm1_w = h->P(P_NRM1_W); ph.nrm1_b = h->P(P_NRM1_B);
+  ph.tPo_norm = b->tPo_norm; ph.gate = f.gate;
+  ph.vel_si_vec = vel_si_vec; ph.vel_si_norm = vel_si_norm; ph.vel = vel;
+  RUN(pool_head(ph, s));
+#undef RUN
+  return CNS_OK;
+}
+
+}  // namespace cns
+
+using namespace cns;
+
+extern "C" {
+
+size_t cns_forward_workspace_bytes(const cns_batch* b) {
+  if (!b) return 0;
+  Arena ar(nullptr);
+  FwdBuffers f;
+  carve(ar, b, f);
+  return ar.off + 256;
+}
+
+size_t cns_forward_save_bytes(const cns_batch* b) {
+  (void)b;
+  return 0;  // training saves: see cns_graphvs_backward (not part of the inference library yet)
+}
+
+int cns_graphvs_forward(cns_handle* h, const cns_batch* b, const float* hidden_in, float* vel_si_vec,
+                        float* vel_si_norm, float* hidden_out, float* vel, void* workspace,
+                        size_t workspace_bytes, void* save, size_t save_bytes, void* stream) {
+  (void)save; (void)save_bytes;
+  CNS_REQUIRE(h != nullptr, "NULL handle");
+  CNS_REQUIRE(h->weights_loaded, "weights not loaded (cns_load_weights)");
+  int rc = validate(b);
+  if (rc != CNS_OK) return rc;
+  if (b->n_graphs == 0) return CNS_OK;
+  CNS_REQUIRE(vel_si_vec && vel_si_norm && (hidden_out || b->n_clusters == 0), "NULL output");
+  CNS_REQUIRE(workspace != nullptr, "NULL workspace");
+  size_t need = cns_forward_workspace_bytes(b);
+  if (workspace_bytes < need) {
+    set_error("cns_graphvs_forward: workspace %zu < %zu bytes", workspace_bytes, need);
+    return CNS_ERR_WORKSPACE_TOO_SMALL;
+  }
+  CNS_CUDA_CHECK(cudaSetDevice(h->device));
+  return forward_impl(h, b, hidden_in, vel_si_vec, vel_si_norm, hidden_out, vel, workspace, (cudaStream_t)stream);
+}
+
+// Error word written by the index-preparation kernels (0 = fine).  Synchronises `stream`.
+int cns_forward_status(const void* workspace, void* stream) {
+  CNS_REQUIRE(workspace != nullptr, "NULL workspace");
+  int flag = 0;
+  CNS_CUDA_CHECK(cudaMemcpyAsync(&flag, workspace, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CNS_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  if (flag == 1) { set_error("l0_to_l1_edge_index_i is not sorted by cluster / out of range"); return CNS_ERR_UNSORTED_EDGES; }
+  if (flag != 0) { set_error("edge index out of range"); return CNS_ERR_INVALID_ARGUMENT; }
+  return CNS_OK;
+}
+
+int cns_graphvs_forward_host(cns_handle* h, const cns_batch* bh, const float* hidden_in_host,
+                             float* vel_si_vec_host, float* vel_si_norm_host, float* hidden_out_host,
+                             float* vel_host) {
+  CNS_REQUIRE(h != nullptr, "NULL handle");
+  int rc = validate(bh);
+  if (rc != CNS_OK) return rc;
+  if (bh->n_graphs == 0) return CNS_OK;
+  CNS_CUDA_CHECK(cudaSetDevice(h->device));
+  const int64_t N = bh->n_nodes, C = bh->n_clusters, B = bh->n_graphs;
+  // device staging layout: inputs | hidden_in | outputs | workspace
+  Arena ar(nullptr);
+  auto plan = [&](Arena& a, cns_batch& d, float*& hin, float*& vec, float*& nrm, float*& hout, float*& vel, void*& ws) {
+    d = *bh;
+    d.l1_cur_stride = 0; d.l1_tar_stride = 0;
+    d.x_cur = a.take<float>(N * 2); d.x_tar = a.take<float>(N * 2);
+    d.pos_cur = a.take<float>(N * 2); d.pos_tar = a.take<float>(N * 2);
+    d.l0_to_l1_j = a.take<int64_t>(bh->n_e01); d.l0_to_l1_i = a.take<int64_t>(bh->n_e01);
+    d.l1_edge_cur = a.take<int64_t>(2 * bh->n_e11_cur); d.l1_edge_tar = a.take<int64_t>(2 * bh->n_e11_tar);
+    d.cluster_mask = a.take<uint8_t>(C); d.cluster_centers = a.take<int64_t>(C);
+    d.node_graph = bh->node_graph ? a.take<int64_t>(N) : nullptr;
+    d.num_clusters = a.take<int64_t>(B);
+    d.tPo_norm = bh->tPo_norm ? a.take<float>(B) : nullptr;
+    hin = hidden_in_host ? a.take<float>(C * H) : nullptr;
+    vec = a.take<float>(B * 6); nrm = a.take<float>(B); hout = a.take<float>(C * H); vel = a.take<float>(B * 6);
+    ws = a.take<char>(cns_forward_workspace_bytes(bh));
+  };
+  cns_batch d; float *hin, *vec, *nrm, *hout, *vel; void* ws;
+  plan(ar, d, hin, vec, nrm, hout, vel, ws);
+  if (ar.off > h->stage_dev_bytes) {
+    if (h->stage_dev) CNS_CUDA_CHECK(cudaFree(h->stage_dev));
+    h->stage_dev = nullptr; h->stage_dev_bytes = 0;
+    size_t want = ar.off + ar.off / 4;
+    CNS_CUDA_CHECK(cudaMalloc(&h->stage_dev, want));
+    h->stage_dev_bytes = want;
+  }
+  Arena ad(h->stage_dev);
+  plan(ad, d, hin, vec, nrm, hout, vel, ws);
+  cudaStream_t s = 0;
+#define H2D(dst, src, bytes) \
+  if ((bytes) > 0) CNS_CUDA_CHECK(cudaMemcpyAsync((void*)(dst), (src), (bytes), cudaMemcpyHostToDevice, s));
+  H2D(d.x_cur, bh->x_cur, N * 2 * sizeof(float)); H2D(d.x_tar, bh->x_tar, N * 2 * sizeof(float));
+  H2D(d.pos_cur, bh->pos_cur, N * 2 * sizeof(float)); H2D(d.pos_tar, bh->pos_tar, N * 2 * sizeof(float));
+  H2D(d.l0_to_l1_j, bh->l0_to_l1_j, bh->n_e01 * sizeof(int64_t)); H2D(d.l0_to_l1_i, bh->l0_to_l1_i, bh->n_e01 * sizeof(int64_t));
+  {
+    const int64_t cs = bh->l1_cur_stride ? bh->l1_cur_stride : bh->n_e11_cur;
+    const int64_t ts = bh->l1_tar_stride ? bh->l1_tar_stride : bh->n_e11_tar;
+    H2D(d.l1_edge_cur, bh->l1_edge_cur, bh->n_e11_cur * sizeof(int64_t));
+    H2D(d.l1_edge_cur + bh->n_e11_cur, bh->l1_edge_cur + cs, bh->n_e11_cur * sizeof(int64_t));
+    H2D(d.l1_edge_tar, bh->l1_edge_tar, bh->n_e11_tar * sizeof(int64_t));
+    H2D(d.l1_edge_tar + bh->n_e11_tar, bh->l1_edge_tar + ts, bh->n_e11_tar * sizeof(int64_t));
+  }
+  H2D(d.cluster_mask, bh->cluster_mask, C); H2D(d.cluster_centers, bh->cluster_centers, C * sizeof(int64_t));
+  if (bh->node_graph) H2D(d.node_graph, bh->node_graph, N * sizeof(int64_t));
+  H2D(d.num_clusters, bh->num_clusters, B * sizeof(int64_t));
+  if (bh->tPo_norm) H2D(d.tPo_norm, bh->tPo_norm, B * sizeof(float));
+  if (hidden_in_host) H2D(hin, hidden_in_host, C * H * sizeof(float));
+#undef H2D
+  rc = cns_graphvs_forward(h, &d, hin, vec, nrm, hout, vel, ws, cns_forward_workspace_bytes(bh), nullptr, 0, s);
+  if (rc != CNS_OK) return rc;
+#define D2H(dst, src, bytes) \
+  if ((dst) && (bytes) > 0) CNS_CUDA_CHECK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, s));
+  D2H(vel_si_vec_host, vec, B * 6 * sizeof(float)); D2H(vel_si_norm_host, nrm, B * sizeof(float));
+  D2H(hidden_out_host, hout, C * H * sizeof(float)); D2H(vel_host, vel, B * 6 * sizeof(float));
+#undef D2H
+  return cns_forward_status(ws, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+// Internal launch interfaces shared between the translation units of libcns_sm100.so.
+#pragma once
+#include "common.cuh"
+
+namespace cns {
+
+constexpr int ENC_TILE_E = 128;   // edges per encoder tile
+constexpr int ENC_PIECE_E = 64;   // softmax piece granularity (partials are indexed per piece)
+
+// ---- prep.cu ------------------------------------------------------------------------------
+int exclusive_scan_i32(const int* in, int64_t n, int* out, int* scratch, cudaStream_t s);
+size_t scan_scratch_bytes(int64_t n);
+int sorted_rowptr(const int64_t* dst, int64_t n_edges, int64_t n_rows, int* rowptr, int* err_flag,
+                  cudaStream_t s);
+size_t csr_workspace_bytes(int64_t n_rows);
+int csr_by_dst(const int64_t* ej, const int64_t* ei, int64_t n_edges, int64_t n_rows, int* rowptr, int* src,
+               void* workspace, int* err_flag, cudaStream_t s);
+int graph_ptr_from_counts(const int64_t* num_clusters, int64_t n_graphs, int* graph_ptr, int* tmp,
+                          int* scratch, cudaStream_t s);
+
+// ---- encoder.cu ---------------------------------------------------------------------------
+struct EncPreArgs {
+  int64_t n_clusters;
+  const float* x_tar; const float* pos_tar; const int64_t* centers; const int64_t* node_graph;
+  const float* w_in; const float* b_in; const float* lin_dst_t;
+  float* a_dst;      // (C,128)
+  float* pos_clu;    // (C,2)
+  int* clu_graph;    // (C,)
+};
+int enc_cluster_pre(const EncPreArgs& a, cudaStream_t s);
+
+struct EncEdgeArgs {
+  int64_t n_e01, n_clusters, n_slots;
+  const float* x_cur; const float* x_tar; const float* pos_cur; const float* pos_tar;
+  const int64_t* ej; const int64_t* ei;
+  const float* pos_clu; const float* a_dst; const int* clu_rowptr;
+  const float* w_in; const float* b_in; const float* w_p0; const float* b_p0;
+  const float* enc_chain; const float* b_p1; const float* b_a0; const float* b_a1;
+  float* clu_feat;   // (2, C, 128): relu(ptconv) for cur / tar
+  float* partial;    // (2, n_slots, 3, 128)
+};
+int enc_edge_fp32(const EncEdgeArgs& a, cudaStream_t s);
+int enc_edge_tc(const EncEdgeArgs& a, int precision, const void* tc_weights, int sm_count, cudaStream_t s);
+
+struct EncFinishArgs {
+  int64_t n_clusters, n_slots;
+  const int* clu_rowptr; const float* partial; float* clu_feat;
+  const float* out_t; const float* b_out; const uint8_t* cluster_mask;
+  float* x_clu;      // (C,128)
+};
+int enc_finish(const EncFinishArgs& a, cudaStream_t s);
+
+// ---- backbone.cu --------------------------------------------------------------------------
+// Y = act([X1 | X2] @ wt + pos @ wp + bias + residual);  wt (k1+k2, n_out) row-major
+struct LinearArgs {
+  int64_t m; int k1, k2, n_out;
+  const float* x1; const float* x2; const float* wt; const float* bias;
+  const float* pos; const float* wp;       // optional (m,2) / (2,n_out)
+  const float* residual;                   // optional (m,n_out)
+  int relu;
+  float* y;
+};
+int linear(const LinearArgs& a, cudaStream_t s);
+
+enum EdgeConvMode { EC_PLAIN = 0, EC_GATES = 1, EC_CANDIDATE = 2 };
+struct EdgeConvArgs {
+  int64_t n_rows; int f_out; int mode;
+  const float* pq; const int* rowptr; const int* src;
+  float* out;              // EC_PLAIN: (n, f)
+  const float* h;          // EC_GATES / EC_CANDIDATE: previous hidden (n,128) or NULL (zeros)
+  float* hr; float* u;     // EC_GATES: h * r (n,128), update gate (n,128)
+  const float* u_in;       // EC_CANDIDATE
+  float* h_out;            // EC_CANDIDATE: (1-u) h + u tanh(.)
+  int* argmax;             // optional (n, f): winning source per channel (training)
+  float* act;              // optional: post-activation values kept for backward
+};
+int edgeconv_max(const EdgeConvArgs& a, cudaStream_t s);
+
+struct GraphNormArgs {
+  int64_t n_graphs; const int* graph_ptr; const float* x;
+  const float* weight; const float* bias; const float* mean_scale;
+  float* y; float* stats;  // stats optional (B, 2, 128): mean, rstd (training)
+};
+int graphnorm_relu(const GraphNormArgs& a, cudaStream_t s);
+
+struct PoolHeadArgs {
+  int64_t n_graphs; const int* graph_ptr; const float* x; const uint8_t* cluster_mask;
+  const float* pool_w; const float* pool_b;
+  const float* vec0_t; const float* vec0_b; const float* vec1_w; const float* vec1_b;
+  const float* nrm0_t; const float* nrm0_b; const float* nrm1_w; const float* nrm1_b;
+  const float* tPo_norm;
+  float* gate;      // scratch (C,)
+  float* vel_si_vec; float* vel_si_norm; float* vel;  // vel optional
+  float* x_scene; float* hid;  // optional saves (B,128), (B,2,128)
+};
+int pool_head(const PoolHeadArgs& a, cudaStream_t s);
+
+}  // namespace cns

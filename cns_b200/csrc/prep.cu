@@ -1,0 +1,203 @@
+// Index preparation: segment pointers and destination-sorted CSR from the reference's int64 edge
+// lists (PyG convention edge_index[0] = source j, edge_index[1] = destination i,
+// cns/models/graph_vs.py:41-43).  Integer work only; int32 on device.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace cns {
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan of int32 (n up to 2^31), three phases, 1024 elements per block
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_BLOCK = 1024;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+  __shared__ int warp_sums[32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = warp_sums[lane];
+    int winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += t;
+    }
+    warp_sums[lane] = winc - w;  // exclusive
+    if (lane == 31 && total) *total = winc;
+  }
+  __syncthreads();
+  int res = inc - v + warp_sums[wid];
+  __syncthreads();
+  return res;
+}
+
+__global__ void scan_block_sums_kernel(const int* __restrict__ in, int64_t n, int* __restrict__ sums) {
+  __shared__ int total;
+  int64_t i = (int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+  int v = (i < n) ? in[i] : 0;
+  block_exclusive_scan(v, &total);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of up to 1024*1024 block sums, in place
+__global__ void scan_sums_kernel(int* sums, int n_blocks) {
+  __shared__ int total;
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_blocks; base += SCAN_BLOCK) {
+    int i = base + threadIdx.x;
+    int v = (i < n_blocks) ? sums[i] : 0;
+    int ex = block_exclusive_scan(v, &total);
+    if (i < n_blocks) sums[i] = ex + carry;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += total;
+    __syncthreads();
+  }
+}
+
+// out[i] = exclusive prefix; out has n+1 entries when `write_total`
+__global__ void scan_apply_kernel(const int* __restrict__ in, int64_t n, const int* __restrict__ sums,
+                                  int* __restrict__ out) {
+  __shared__ int total;
+  int64_t i = (int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+  int v = (i < n) ? in[i] : 0;
+  int ex = block_exclusive_scan(v, &total) + sums[blockIdx.x];
+  if (i < n) out[i] = ex;
+  if (i == n - 1) out[n] = ex + v;
+}
+
+// in-place safe (in may alias out).  scratch: ceil(n/1024) ints.
+int exclusive_scan_i32(const int* in, int64_t n, int* out, int* scratch, cudaStream_t s) {
+  if (n == 0) {
+    CNS_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(int), s));
+    return CNS_OK;
+  }
+  int nb = ceil_div(n, SCAN_BLOCK);
+  CNS_REQUIRE(nb <= SCAN_BLOCK * SCAN_BLOCK, "scan too large");
+  scan_block_sums_kernel<<<nb, SCAN_BLOCK, 0, s>>>(in, n, scratch);
+  CNS_LAUNCH_CHECK();
+  scan_sums_kernel<<<1, SCAN_BLOCK, 0, s>>>(scratch, nb);
+  CNS_LAUNCH_CHECK();
+  scan_apply_kernel<<<nb, SCAN_BLOCK, 0, s>>>(in, n, scratch, out);
+  CNS_LAUNCH_CHECK();
+  return CNS_OK;
+}
+
+size_t scan_scratch_bytes(int64_t n) { return align_up((size_t)(ceil_div(n, SCAN_BLOCK) + 1) * sizeof(int)); }
+
+// ---------------------------------------------------------------------------------------------
+// rowptr of a sorted destination list (l0_to_l1_edge_index_i): boundary detection, no atomics
+// ---------------------------------------------------------------------------------------------
+__global__ void sorted_rowptr_kernel(const int64_t* __restrict__ dst, int64_t n_edges, int64_t n_rows,
+                                     int* __restrict__ rowptr, int* __restrict__ err) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e > n_edges) return;
+  int64_t prev = (e == 0) ? -1 : dst[e - 1];
+  int64_t cur = (e == n_edges) ? n_rows : dst[e];
+  if (cur < prev || cur < 0 || cur > n_rows || (e < n_edges && cur >= n_rows)) {
+    atomicExch(err, 1);
+    return;
+  }
+  for (int64_t r = prev + 1; r <= cur; ++r) rowptr[r] = (int)e;
+}
+
+int sorted_rowptr(const int64_t* dst, int64_t n_edges, int64_t n_rows, int* rowptr, int* err_flag,
+                  cudaStream_t s) {
+  sorted_rowptr_kernel<<<ceil_div(n_edges + 1, 256), 256, 0, s>>>(dst, n_edges, n_rows, rowptr, err_flag);
+  CNS_LAUNCH_CHECK();
+  return CNS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic CSR by destination: count (int atomics) -> scan -> slot fill
+// ---------------------------------------------------------------------------------------------
+__global__ void csr_count_kernel(const int64_t* __restrict__ dst, int64_t n_edges, int64_t n_rows,
+                                 int* __restrict__ deg, int* __restrict__ err) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  int64_t i = dst[e];
+  if (i < 0 || i >= n_rows) { atomicExch(err, 2); return; }
+  atomicAdd(&deg[i], 1);
+}
+
+__global__ void csr_fill_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                int64_t n_edges, int64_t n_rows, const int* __restrict__ rowptr,
+                                int* __restrict__ cursor, int* __restrict__ out_src) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  int64_t i = dst[e];
+  if (i < 0 || i >= n_rows) return;
+  int slot = rowptr[i] + atomicAdd(&cursor[i], 1);
+  out_src[slot] = (int)src[e];
+}
+
+// workspace: cursor (n_rows+1 ints) + scan scratch
+size_t csr_workspace_bytes(int64_t n_rows) {
+  return align_up((size_t)(n_rows + 1) * sizeof(int)) + scan_scratch_bytes(n_rows + 1);
+}
+
+int csr_by_dst(const int64_t* ej, const int64_t* ei, int64_t n_edges, int64_t n_rows, int* rowptr, int* src,
+               void* workspace, int* err_flag, cudaStream_t s) {
+  int* cursor = (int*)workspace;
+  int* scratch = (int*)((char*)workspace + align_up((size_t)(n_rows + 1) * sizeof(int)));
+  CNS_CUDA_CHECK(cudaMemsetAsync(cursor, 0, (size_t)(n_rows + 1) * sizeof(int), s));
+  if (n_edges > 0) {
+    csr_count_kernel<<<ceil_div(n_edges, 256), 256, 0, s>>>(ei, n_edges, n_rows, cursor, err_flag);
+    CNS_LAUNCH_CHECK();
+  }
+  // scan over n_rows degrees, writes rowptr[0..n_rows]
+  int rc = exclusive_scan_i32(cursor, n_rows, rowptr, scratch, s);
+  if (rc != CNS_OK) return rc;
+  if (n_rows == 0) return CNS_OK;
+  CNS_CUDA_CHECK(cudaMemsetAsync(cursor, 0, (size_t)(n_rows + 1) * sizeof(int), s));
+  if (n_edges > 0) {
+    csr_fill_kernel<<<ceil_div(n_edges, 256), 256, 0, s>>>(ej, ei, n_edges, n_rows, rowptr, cursor, src);
+    CNS_LAUNCH_CHECK();
+  }
+  return CNS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-cluster metadata: centre position, graph id; graph_ptr from num_clusters
+// ---------------------------------------------------------------------------------------------
+__global__ void i64_to_i32_kernel(const int64_t* __restrict__ in, int64_t n, int* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int)in[i];
+}
+
+int graph_ptr_from_counts(const int64_t* num_clusters, int64_t n_graphs, int* graph_ptr, int* tmp,
+                          int* scratch, cudaStream_t s) {
+  if (n_graphs > 0) {
+    i64_to_i32_kernel<<<ceil_div(n_graphs, 256), 256, 0, s>>>(num_clusters, n_graphs, tmp);
+    CNS_LAUNCH_CHECK();
+  }
+  return exclusive_scan_i32(tmp, n_graphs, graph_ptr, scratch, s);
+}
+
+}  // namespace cns
+
+using namespace cns;
+
+extern "C" int cns_csr_by_dst(const int64_t* edge_index, int64_t n_edges, int64_t n_dst, int32_t* rowptr,
+                              int32_t* src, void* workspace, size_t workspace_bytes, void* stream) {
+  CNS_REQUIRE(n_edges >= 0 && n_dst >= 0, "negative size");
+  CNS_REQUIRE(rowptr && (src || n_edges == 0) && workspace, "NULL pointer");
+  size_t need = csr_workspace_bytes(n_dst) + 256;
+  if (workspace_bytes < need) {
+    set_error("cns_csr_by_dst: workspace %zu < %zu", workspace_bytes, need);
+    return CNS_ERR_WORKSPACE_TOO_SMALL;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  int* err = (int*)workspace;
+  CNS_CUDA_CHECK(cudaMemsetAsync(err, 0, sizeof(int), s));
+  return csr_by_dst(edge_index, edge_index + n_edges, n_edges, n_dst, rowptr, src, (char*)workspace + 256, err, s);
+}

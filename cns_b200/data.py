@@ -1,0 +1,173 @@
+"""PyG-free `GraphData` / `Batch` containers with the reference's field names.
+
+Drop-in for `cns.midend.graph_gen.GraphData` (reference graph_gen.py:68-101) and for
+`torch_geometric.data.Batch.from_data_list` as the reference uses it
+(sim/dataset.py:208).  Only the behaviour the hot path relies on is kept:
+
+* attribute / item access, `hasattr(data, "batch")`, `.to(device)`, tolerating
+  non-tensor extras (`intrinsic`, `cur_img`, ...) that the servo pipeline attaches
+  (benchmark/pipeline.py:150-166);
+* defaults `new_scene=False`, `tPo_norm=1.0` (graph_gen.py:71-74);
+* collation offsets (graph_gen.py:78-95): keys containing `l0_dense_edge_index`,
+  `l0_to_l1_edge_index_j`, `cluster_centers_index` advance by `num_nodes`; keys
+  containing `l1_dense_edge_index`, `l0_to_l1_edge_index_i`, `belong_cluster_index`
+  advance by `num_clusters`; any other key containing "index" advances by
+  `num_nodes` (PyG default); keys containing "index" concatenate on the last dim,
+  everything else on dim 0; 0-d tensors become (B,) vectors.
+
+Unlike PyG the collation is vectorised: one `torch.cat` per field plus one
+`repeat_interleave` for the offsets instead of B python-level additions.
+"""
+import copy
+from typing import Any, Dict, Iterable, List
+
+import torch
+
+_INC_BY_NODES = ("l0_dense_edge_index", "l0_to_l1_edge_index_j", "cluster_centers_index")
+_INC_BY_CLUSTERS = ("l1_dense_edge_index", "l0_to_l1_edge_index_i", "belong_cluster_index")
+
+
+class GraphData(object):
+    """One servo frame: target/current keypoints plus the two-level graph."""
+
+    def __init__(self, **fields):
+        object.__setattr__(self, "_f", {})
+        if "new_scene" not in fields:
+            fields["new_scene"] = torch.tensor(False)
+        if "tPo_norm" not in fields:
+            fields["tPo_norm"] = torch.tensor(1.0, dtype=torch.float32)
+        for k, v in fields.items():
+            if v is not None:
+                self._f[k] = v
+
+    # -- attribute plumbing ---------------------------------------------------
+    def __getattr__(self, key):
+        try:
+            return object.__getattribute__(self, "_f")[key]
+        except KeyError:
+            raise AttributeError(key) from None
+
+    def __setattr__(self, key, value):
+        self._f[key] = value
+
+    def __getitem__(self, key):
+        return self._f[key]
+
+    def __setitem__(self, key, value):
+        self._f[key] = value
+
+    def __contains__(self, key):
+        return key in self._f
+
+    @property
+    def keys(self) -> List[str]:
+        return list(self._f.keys())
+
+    def items(self):
+        return self._f.items()
+
+    def __repr__(self):
+        body = ", ".join(
+            "%s=%s" % (k, list(v.shape) if isinstance(v, torch.Tensor) else type(v).__name__)
+            for k, v in self._f.items())
+        return "%s(%s)" % (type(self).__name__, body)
+
+    # -- reference API --------------------------------------------------------
+    def start_new_scene(self, is_new: bool = True):
+        self._f["new_scene"] = torch.tensor(bool(is_new))
+
+    def set_distance_scale(self, dist_scale):
+        self._f["tPo_norm"] = torch.tensor(float(dist_scale), dtype=torch.float32)
+
+    def to(self, device, non_blocking: bool = False):
+        out = copy.copy(self)
+        object.__setattr__(out, "_f", {
+            k: (v.to(device, non_blocking=non_blocking) if isinstance(v, torch.Tensor) else v)
+            for k, v in self._f.items()})
+        return out
+
+    def pin_memory(self):
+        out = copy.copy(self)
+        object.__setattr__(out, "_f", {
+            k: (v.pin_memory() if isinstance(v, torch.Tensor) else v)
+            for k, v in self._f.items()})
+        return out
+
+    def clone(self):
+        out = copy.copy(self)
+        object.__setattr__(out, "_f", {
+            k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in self._f.items()})
+        return out
+
+    # -- collation rules ------------------------------------------------------
+    def __cat_dim__(self, key: str, value=None) -> int:
+        return -1 if "index" in key else 0
+
+    def __inc__(self, key: str, value=None):
+        for cand in _INC_BY_NODES:
+            if cand in key:
+                return int(self.num_nodes)
+        for cand in _INC_BY_CLUSTERS:
+            if cand in key:
+                return int(self.num_clusters)
+        return int(self.num_nodes) if "index" in key else 0
+
+
+def _inc_kind(key: str) -> int:
+    """0: no offset, 1: by num_nodes, 2: by num_clusters."""
+    for cand in _INC_BY_NODES:
+        if cand in key:
+            return 1
+    for cand in _INC_BY_CLUSTERS:
+        if cand in key:
+            return 2
+    return 1 if "index" in key else 0
+
+
+class Batch(GraphData):
+    """B graphs concatenated with index offsets; adds `batch`, `ptr`, `cluster_ptr`."""
+
+    def __init__(self, **fields):
+        object.__setattr__(self, "_f", {})
+        for k, v in fields.items():
+            self._f[k] = v
+
+    @property
+    def num_graphs(self) -> int:
+        return int(self._f["num_clusters"].numel())
+
+    @classmethod
+    def from_data_list(cls, data_list: Iterable[GraphData]) -> "Batch":
+        data_list = list(data_list)
+        assert len(data_list) > 0
+        nb = len(data_list)
+        n_nodes = torch.tensor([int(d.num_nodes) for d in data_list], dtype=torch.long)
+        n_clu = torch.tensor([int(d.num_clusters) for d in data_list], dtype=torch.long)
+        node_off = torch.cumsum(n_nodes, 0) - n_nodes
+        clu_off = torch.cumsum(n_clu, 0) - n_clu
+
+        out: Dict[str, Any] = {}
+        for key in data_list[0].keys:
+            if key == "num_nodes":
+                continue
+            vals = [d[key] for d in data_list]
+            v0 = vals[0]
+            if isinstance(v0, torch.Tensor):
+                vals = [v.unsqueeze(0) if v.dim() == 0 else v for v in vals]
+                cat = torch.cat(vals, dim=-1 if "index" in key else 0)
+                kind = _inc_kind(key)
+                if kind:
+                    lens = torch.tensor([v.shape[-1] for v in vals], dtype=torch.long)
+                    off = torch.repeat_interleave(node_off if kind == 1 else clu_off, lens)
+                    cat = cat + off  # broadcasts over the leading 2 of (2, E) edge lists
+                out[key] = cat
+            elif isinstance(v0, (int, float)) and not isinstance(v0, bool):
+                out[key] = torch.tensor(vals)
+            else:
+                out[key] = vals
+        out["num_nodes"] = int(n_nodes.sum())
+        out["batch"] = torch.repeat_interleave(torch.arange(nb), n_nodes)
+        ptr = torch.zeros(nb + 1, dtype=torch.long)
+        ptr[1:] = torch.cumsum(n_nodes, 0)
+        out["ptr"] = ptr
+        return cls(**out)

@@ -1,0 +1,299 @@
+"""`GraphVS`: drop-in for `cns.models.graph_vs.GraphVS` whose forward runs on libcns_sm100.
+
+Same constructor, `forward(data, hidden=None) -> (vel_si_vec, vel_si_norm, hidden)`,
+`init_hidden`, classmethods `preprocess / postprocess / objectives`,
+`get_parameter_groups()` and - because the parameter containers below reuse the
+reference's attribute names - the same 43 state-dict keys (graph_vs.py:273-350), so
+`load_state_dict(torch.load("checkpoints/cns_state_dict.pth"))` works unchanged.
+
+The modules here only OWN parameters; no torch op computes anything on the hot path.
+`forward` hands raw device pointers to `cns_graphvs_forward` (include/cns_b200.h).
+There is no CPU implementation: calling it with CPU tensors raises.
+"""
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import functions as F_
+
+
+class MLP(nn.Module):
+    """Parameter container with the reference's layout `fcs.{l}.{weight,bias}` (graph_vs.py:16-24)."""
+
+    def __init__(self, channels, bias=True):
+        super().__init__()
+        assert len(channels) >= 2
+        self.fcs = nn.ModuleList(
+            nn.Linear(channels[i - 1], channels[i], bias=bias) for i in range(1, len(channels)))
+
+
+class _PointTransformer(nn.Module):   # encoder.att_clu_conv
+    def __init__(self, dim, pos_dim):
+        super().__init__()
+        self.pos_nn = MLP([pos_dim * 2, dim, dim])
+        self.attn_nn = MLP([dim, dim, dim])
+        self.lin = nn.Linear(dim, dim, bias=False)
+        self.lin_src = nn.Linear(dim, dim, bias=False)
+        self.lin_dst = nn.Linear(dim, dim, bias=False)
+
+
+class _Encoder(nn.Module):
+    def __init__(self, input_dim, dim, pos_dim):
+        super().__init__()
+        self.in_enc = MLP([input_dim, dim])
+        self.att_clu_conv = _PointTransformer(dim, pos_dim)
+        self.out_enc = MLP([dim * 2, dim])
+
+
+class _PointEdgeConv(nn.Module):
+    def __init__(self, in_dim, out_dim, pos_dim):
+        super().__init__()
+        self.msg_nn = MLP([in_dim * 2 + pos_dim, out_dim])
+
+
+class GraphNormParams(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.bias = nn.Parameter(torch.zeros(dim))
+        self.mean_scale = nn.Parameter(torch.ones(dim))
+
+
+class _PERConv(nn.Module):
+    def __init__(self, dim, pos_dim):
+        super().__init__()
+        self.conv = _PointEdgeConv(dim, dim, pos_dim)
+        self.bn = GraphNormParams(dim)
+        self.fc = nn.Linear(dim, dim)
+
+
+class _GRUCell(nn.Module):
+    def __init__(self, dim, pos_dim):
+        super().__init__()
+        self.out_channels = dim
+        self.conv_gates = _PointEdgeConv(2 * dim, 2 * dim, pos_dim)
+        self.conv_candi = _PointEdgeConv(2 * dim, dim, pos_dim)
+
+
+class _Backbone(nn.Module):
+    def __init__(self, dim, pos_dim):
+        super().__init__()
+        self.l1_conv0 = _PERConv(dim, pos_dim)
+        self.temporal_aggr = _GRUCell(dim, pos_dim)
+        self.l1_conv1 = _PERConv(dim, pos_dim)
+
+
+class _Pool(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.gate_nn = nn.Linear(dim, 1)
+
+
+class _Decoder(nn.Module):
+    def __init__(self, dim, regress_norm):
+        super().__init__()
+        self.pool = _Pool(dim)
+        self.vel_si_vec = MLP([dim, dim, 6])
+        if regress_norm:
+            self.vel_si_norm = MLP([dim, dim, 1])
+
+
+class RawPred(tuple):
+    """(vel_si_vec, vel_si_norm, hidden) that also carries the fused post-processed velocity."""
+    vel = None
+    tpo_ptr = None
+
+
+def _field(data, key, default=None):
+    try:
+        return data[key] if isinstance(data, dict) else getattr(data, key)
+    except (KeyError, AttributeError):
+        return default
+
+
+class GraphVS(nn.Module):
+    def __init__(self, input_dim, pos_dim, hidden_dim=128, regress_norm=True, precision="fp32"):
+        super().__init__()
+        if (input_dim, pos_dim, hidden_dim) != (2, 2, 128) or not regress_norm:
+            raise NotImplementedError(
+                "libcns_sm100 is specialised for the shipped configuration "
+                "GraphVS(2, 2, 128, regress_norm=True) (checkpoints/cns.pth, train_cns.py:56-61)")
+        self.regress_norm = regress_norm
+        self.encoder = _Encoder(input_dim, hidden_dim, pos_dim)
+        self.backbone = _Backbone(hidden_dim, pos_dim)
+        self.decoder = _Decoder(hidden_dim, regress_norm)
+        self.hidden_dim = hidden_dim
+        self.precision = precision
+        self._handles = {}       # device index -> (_lib.Handle, weight version)
+        self._workspaces = {}    # device index -> uint8 tensor
+        self._names = None
+
+    # ------------------------------------------------------------------ reference API
+    def init_hidden(self, size0):
+        return torch.zeros(int(size0), self.hidden_dim)
+
+    @classmethod
+    def preprocess(cls, data):
+        return data
+
+    @classmethod
+    def postprocess(cls, raw_pred, data):
+        vel = getattr(raw_pred, "vel", None)
+        tpo = _field(data, "tPo_norm")
+        if vel is not None and tpo is not None and raw_pred.tpo_ptr == tpo.data_ptr():
+            return vel.clone()
+        return F_.postprocess(raw_pred, data, post_scale=True)
+
+    @classmethod
+    def objectives(cls, raw_pred, data):
+        return F_.objectives(raw_pred, data, gt_si=True, weight=1)
+
+    def get_parameter_groups(self):
+        """(decay, no_decay) as graph_vs.py:340-350: Linear weights decay; biases and the
+        GraphNorm weight / mean_scale do not."""
+        decay, no_decay = [], []
+        for m in self.modules():
+            if isinstance(getattr(m, "bias", None), nn.Parameter):
+                no_decay.append(m.bias)
+            if isinstance(m, GraphNormParams):
+                no_decay += [m.weight, m.mean_scale]
+            elif isinstance(getattr(m, "weight", None), nn.Parameter):
+                decay.append(m.weight)
+        return decay, no_decay
+
+    # ------------------------------------------------------------------ library plumbing
+    def set_precision(self, precision: str):
+        assert precision in _lib.PRECISIONS
+        self.precision = precision
+        for h, _ in self._handles.values():
+            h.set_precision(precision)
+
+    def _ordered_params(self):
+        if self._names is None:
+            self._names = _lib.param_names()
+        sd = dict(self.named_parameters())
+        return [sd[n] for n in self._names]
+
+    def _handle(self, device: torch.device) -> "_lib.Handle":
+        params = self._ordered_params()
+        version = tuple((p.data_ptr(), p._version) for p in params)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        ent = self._handles.get(idx)
+        if ent is None:
+            h = _lib.Handle(torch.device("cuda", idx))
+            h.set_precision(self.precision)
+            ent = [h, None]
+            self._handles[idx] = ent
+        if ent[1] != version:
+            on_dev = all(p.is_cuda for p in params)
+            if not on_dev and any(p.is_cuda for p in params):
+                raise _lib.CnsError("parameters are split between CPU and CUDA")
+            ent[0].load_weights(params, on_device=on_dev)
+            ent[1] = version
+        return ent[0]
+
+    def _workspace(self, idx: int, nbytes: int) -> torch.Tensor:
+        ws = self._workspaces.get(idx)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=torch.device("cuda", idx))
+            self._workspaces[idx] = ws
+        return ws
+
+    @staticmethod
+    def make_batch_struct(data) -> Tuple["_lib.cns_batch", list]:
+        """cns_batch view of a GraphData/Batch whose tensors live on one CUDA device."""
+        keep = []
+
+        def t(key, dtype, required=True):
+            v = _field(data, key)
+            if v is None:
+                if required:
+                    raise KeyError("GraphData is missing field %r" % key)
+                return None
+            if v.dtype != dtype:
+                v = v.to(dtype)
+            if not v.is_contiguous():
+                v = v.contiguous()
+            keep.append(v)
+            return v
+
+        x_cur, x_tar = t("x_cur", torch.float32), t("x_tar", torch.float32)
+        pos_cur, pos_tar = t("pos_cur", torch.float32), t("pos_tar", torch.float32)
+        ej, ei = t("l0_to_l1_edge_index_j_cur", torch.int64), t("l0_to_l1_edge_index_i_cur", torch.int64)
+        ec, et = t("l1_dense_edge_index_cur", torch.int64), t("l1_dense_edge_index_tar", torch.int64)
+        cmask = _field(data, "cluster_mask")
+        if cmask.dtype == torch.bool:
+            cmask = cmask.view(torch.uint8)
+        elif cmask.dtype != torch.uint8:
+            cmask = (cmask != 0).view(torch.uint8)
+        keep.append(cmask)
+        ctr = t("cluster_centers_index", torch.int64)
+        batch = t("batch", torch.int64, required=False)
+        ncl = _field(data, "num_clusters")
+        ncl = ncl.reshape(-1).to(torch.int64).contiguous()
+        keep.append(ncl)
+        tpo = _field(data, "tPo_norm")
+        if tpo is not None:
+            tpo = tpo.reshape(-1).to(torch.float32).contiguous()
+            keep.append(tpo)
+        if x_cur.shape[-1] != 2 or pos_cur.shape[-1] != 2:
+            raise _lib.CnsError("libcns_sm100 expects 2-D features and positions")
+        dev = x_cur.device
+        for v in keep:
+            if v.device != dev:
+                raise _lib.CnsError("all GraphData tensors must live on one device (%s vs %s)" % (v.device, dev))
+        b = _lib.cns_batch()
+        b.n_nodes, b.n_clusters, b.n_graphs = x_cur.shape[0], ctr.shape[0], ncl.shape[0]
+        b.n_e01, b.n_e11_cur, b.n_e11_tar = ej.shape[0], ec.shape[1], et.shape[1]
+        p = lambda v: None if v is None else v.data_ptr()
+        b.x_cur, b.x_tar, b.pos_cur, b.pos_tar = p(x_cur), p(x_tar), p(pos_cur), p(pos_tar)
+        b.l0_to_l1_j, b.l0_to_l1_i = p(ej), p(ei)
+        b.l1_edge_cur, b.l1_edge_tar = p(ec), p(et)
+        b.l1_cur_stride, b.l1_tar_stride = 0, 0
+        b.cluster_mask, b.cluster_centers = p(cmask), p(ctr)
+        b.node_graph, b.num_clusters, b.tPo_norm = p(batch), p(ncl), p(tpo)
+        return b, keep
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, data, hidden: Optional[torch.Tensor] = None, check: bool = False):
+        x_cur = _field(data, "x_cur")
+        if not x_cur.is_cuda:
+            raise _lib.CnsError(
+                "cns_b200.GraphVS runs only on CUDA (sm_100a); move the GraphData with .to('cuda') "
+                "- there is no CPU fallback")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .autograd import graphvs_autograd
+            return graphvs_autograd(self, data, hidden)
+        return self._forward_inference(data, hidden, check)
+
+    def _forward_inference(self, data, hidden, check=False):
+        lib = _lib.load()
+        b, keep = self.make_batch_struct(data)
+        dev = keep[0].device
+        h = self._handle(dev)
+        nb, nc = b.n_graphs, b.n_clusters
+        out = torch.empty(nb * 13 + nc * 128, dtype=torch.float32, device=dev)
+        vec = out[:nb * 6].view(nb, 6)
+        vel = out[nb * 6:nb * 12].view(nb, 6)
+        nrm = out[nb * 12:nb * 13].view(nb, 1)
+        hid = out[nb * 13:].view(nc, 128)
+        if hidden is not None:
+            hidden = hidden.detach().to(dev, torch.float32).contiguous()
+            if hidden.shape != (nc, 128):
+                raise _lib.CnsError("hidden has shape %s, expected (%d, 128)" % (tuple(hidden.shape), nc))
+        nbytes = lib.cns_forward_workspace_bytes(C.byref(b))
+        ws = self._workspace(dev.index, nbytes)
+        stream = _lib.stream_ptr(dev)
+        _lib.check(lib.cns_graphvs_forward(
+            h.raw, C.byref(b), _lib.ptr(hidden), _lib.ptr(vec), _lib.ptr(nrm), _lib.ptr(hid), _lib.ptr(vel),
+            _lib.ptr(ws), ws.numel(), None, 0, stream), "cns_graphvs_forward")
+        if check:
+            _lib.check(lib.cns_forward_status(_lib.ptr(ws), stream), "cns_forward_status")
+        pred = RawPred((vec, nrm, hid))
+        pred.vel = vel
+        tpo = _field(data, "tPo_norm")
+        pred.tpo_ptr = None if tpo is None else tpo.data_ptr()
+        return pred

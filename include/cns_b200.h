@@ -1,0 +1,186 @@
+/*
+ * cns_b200.h - C ABI of libcns_sm100.so: the B200 (sm_100a) implementation of the
+ * CNS hot path (hhcaz/CNS: cns/midend graph construction + cns/models GraphVS).
+ *
+ * The reference is 100 % Python and has no FFI of its own, so
+ * every entry point below names the reference *Python* interface it replaces
+ * (file:line relative to hhcaz/CNS).  A reference maintainer binds these with ctypes;
+ * the stub is shown in INTEGRATION.md and implemented in cns_b200/_lib.py.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes only, no torch / C++ types.
+ *  - every pointer is a DEVICE pointer owned by the caller unless the name ends in
+ *    `_host`.  fp32 tensors are row-major and contiguous; index tensors are int64
+ *    exactly as the reference's GraphData stores them; masks are 1 byte per element.
+ *  - every function returns 0 (CNS_OK) or a negative cns_status.  Nothing throws,
+ *    exits or allocates device memory behind the caller's back: scratch comes from a
+ *    caller-provided workspace whose size a `*_workspace_bytes` query returns.
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All work
+ *    is enqueued asynchronously on it; a handle is used by one host thread at a time.
+ *  - kernels are deterministic: segment-sorted aggregation, no floating-point atomics.
+ */
+#ifndef CNS_B200_H
+#define CNS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cns_status {
+  CNS_OK = 0,
+  CNS_ERR_INVALID_ARGUMENT = -1,
+  CNS_ERR_WORKSPACE_TOO_SMALL = -2,
+  CNS_ERR_CUDA = -3,
+  CNS_ERR_UNSORTED_EDGES = -4,   /* l0_to_l1 edges must be sorted by cluster (reference order) */
+  CNS_ERR_NO_DEVICE = -5,
+  CNS_ERR_UNSUPPORTED = -6
+} cns_status;
+
+#define CNS_HIDDEN_DIM 128        /* hidden_dim of checkpoints/cns.pth (graph_vs.py:274) */
+#define CNS_FEAT_DIM 2            /* input_dim  (train_cns.py:56-61)                      */
+#define CNS_POS_DIM 2             /* pos_dim                                              */
+#define CNS_NUM_PARAM_TENSORS 43  /* state-dict entries, SURVEY.md section 8b             */
+
+/* arithmetic mode of the batched MLP (GEMM) kernels */
+typedef enum cns_precision {
+  CNS_PREC_FP32 = 0,     /* fp32 FFMA everywhere (rel 1e-4 vs the fp64 oracle)         */
+  CNS_PREC_TF32X3 = 1,   /* tcgen05 kind::tf32, 3-pass split (fp32-class accuracy)      */
+  CNS_PREC_BF16 = 2      /* tcgen05 kind::f16 bf16 inputs, fp32 accumulate (rel 2e-2)   */
+} cns_precision;
+
+typedef struct cns_handle cns_handle;   /* packed weights + per-device constants */
+
+/* ---- library / handle ------------------------------------------------------------ */
+const char* cns_version(void);
+const char* cns_last_error_string(void);            /* thread-local, never NULL */
+int cns_device_count(void);
+
+/* Replaces GraphVS.__init__ + load_state_dict (graph_vs.py:273-279, controller.py:18-19).
+ * `params_host` : 43 host pointers to fp32 tensors in the canonical state-dict order
+ *                 returned by cns_param_name(k); `numels[k]` must equal cns_param_numel(k).
+ * Packs (transposes / folds) the weights into device-resident GEMM operands. */
+int cns_create(cns_handle** out, int device);
+int cns_destroy(cns_handle* h);
+int cns_load_weights(cns_handle* h, const float* const* params_host, const int64_t* numels,
+                     int n_tensors, void* stream);
+/* Same, from device-resident parameters (training: re-pack after every optimizer step). */
+int cns_load_weights_device(cns_handle* h, const float* const* params_dev, const int64_t* numels,
+                            int n_tensors, void* stream);
+const char* cns_param_name(int k);      /* e.g. "encoder.in_enc.fcs.0.weight" */
+int64_t cns_param_numel(int k);
+int cns_set_precision(cns_handle* h, int precision /* cns_precision */);
+
+/* ---- one batch of servo graphs ------------------------------------------------------
+ * Field-for-field the tensors GraphVS.forward unpacks from a GraphData/Batch
+ * (graph_vs.py:285-307; field list graph_gen.py:257-275). */
+typedef struct cns_batch {
+  int64_t n_nodes;       /* sum N  : keypoints                                    */
+  int64_t n_clusters;    /* sum C  : clusters (rows of hidden)                    */
+  int64_t n_graphs;      /* B                                                     */
+  int64_t n_e01;         /* len(l0_to_l1_edge_index_*_cur)                        */
+  int64_t n_e11_cur;     /* l1_dense_edge_index_cur.shape[1]                      */
+  int64_t n_e11_tar;     /* l1_dense_edge_index_tar.shape[1]                      */
+  const float* x_cur;    /* (N,2) */
+  const float* x_tar;    /* (N,2) */
+  const float* pos_cur;  /* (N,2) */
+  const float* pos_tar;  /* (N,2) */
+  const int64_t* l0_to_l1_j;      /* (E01,) source keypoint                       */
+  const int64_t* l0_to_l1_i;      /* (E01,) destination cluster, non-decreasing   */
+  const int64_t* l1_edge_cur;     /* (2,E11c) row 0 = source j, row 1 = dest i    */
+  const int64_t* l1_edge_tar;     /* (2,E11t)                                     */
+  int64_t l1_cur_stride;          /* elements between the two rows; 0 => n_e11_cur */
+  int64_t l1_tar_stride;          /* 0 => n_e11_tar                                */
+  const uint8_t* cluster_mask;    /* (C,)  bool                                   */
+  const int64_t* cluster_centers; /* (C,)  keypoint index of each cluster centre  */
+  const int64_t* node_graph;      /* (N,)  `batch` vector, or NULL => all zero    */
+  const int64_t* num_clusters;    /* (B,)  clusters per graph                     */
+  const float* tPo_norm;          /* (B,)  distance scale, or NULL => 1           */
+} cns_batch;
+
+/* Replaces GraphVS.forward (graph_vs.py:284-322) + GraphVS.postprocess
+ * (functions.py:26-38).  hidden_in may be NULL (== init_hidden zeros, graph_vs.py:315).
+ * Outputs: vel_si_vec (B,6), vel_si_norm (B,1), hidden_out (C,128), vel (B,6) or NULL.
+ * `save` != NULL (training) keeps the activations the backward pass needs in
+ * `save` (size cns_forward_save_bytes). */
+size_t cns_forward_workspace_bytes(const cns_batch* b);
+size_t cns_forward_save_bytes(const cns_batch* b);
+int cns_graphvs_forward(cns_handle* h, const cns_batch* b, const float* hidden_in,
+                        float* vel_si_vec, float* vel_si_norm, float* hidden_out, float* vel,
+                        void* workspace, size_t workspace_bytes,
+                        void* save, size_t save_bytes, void* stream);
+
+/* Error word left in `workspace` by the index-preparation kernels of the last forward on
+ * `stream` (unsorted l0_to_l1 edges, out-of-range indices).  Synchronises `stream`. */
+int cns_forward_status(const void* workspace, void* stream);
+
+/* Same call with every cns_batch pointer (and hidden_in / outputs) in HOST memory: the
+ * library stages inputs through its own pinned buffers, runs the forward and copies the
+ * results back before returning (synchronous).  This is what a caller without device
+ * tensors binds - GraphVSController.__call__ incl. data.to(device) and .cpu()
+ * (controller.py:23-38). */
+int cns_graphvs_forward_host(cns_handle* h, const cns_batch* b_host, const float* hidden_in_host,
+                             float* vel_si_vec_host, float* vel_si_norm_host,
+                             float* hidden_out_host, float* vel_host);
+
+/* ---- per-op entry points (each is one stage of the forward; parity-tested alone) ---- */
+
+/* CSR by destination of an int64 (2,E) edge list (PyG flow source->target,
+ * graph_vs.py:41-43): rowptr (n_dst+1) int32, src (E) int32.  Needs (n_dst+1)*4 bytes
+ * of workspace.  Row order inside a row is unspecified (max/sum of a set). */
+int cns_csr_by_dst(const int64_t* edge_index, int64_t n_edges, int64_t n_dst,
+                   int32_t* rowptr, int32_t* src, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* PointEdgeConv aggregation in factorised form (graph_vs.py:46-111):
+ * out[i,:] = deg(i) ? P[i,:] + max_{j in N(i)} Q[j,:] : 0, PQ = (n, 2*f) rows [P | Q]. */
+int cns_edgeconv_max(const float* pq, const int32_t* rowptr, const int32_t* src,
+                     int64_t n_rows, int f_out, float* out, void* stream);
+
+/* PyG GraphNorm + ReLU (graph_vs.py:132,142-143): per graph g over rows
+ * [graph_ptr[g], graph_ptr[g+1]) ; y = relu(w * (x - mean*ms) / sqrt(var + 1e-5) + b). */
+int cns_graphnorm_relu(const float* x, const int32_t* graph_ptr, int64_t n_graphs,
+                       const float* weight, const float* bias, const float* mean_scale,
+                       float* y, void* stream);
+
+/* Y = act(X1 @ W[:, :k1].T + X2 @ W[:, k1:].T + bias (+ residual)); W given TRANSPOSED
+ * (k, n_out) row-major.  Batched node MLP (graph_vs.py:16-31). */
+int cns_linear(const float* x1, int k1, const float* x2, int k2, const float* wt,
+               const float* bias, const float* residual, int relu, int64_t m, int n_out,
+               float* y, void* stream);
+
+/* ---- graph construction (cns/midend/graph_gen.py) ----------------------------------- */
+
+/* Per-frame sub-graph masking for a batch of scenes (graph_gen.py:199-228): given the
+ * static two-level graph of every scene and a per-keypoint visibility mask, emits the
+ * filtered, order-preserving edge lists and masks of GraphGenerator._get_graph.
+ *   in : belong (N,) int64 global cluster id of each keypoint (batched offsets applied),
+ *        member_order (N,) int64 keypoints in cluster-major order (= static l0_to_l1 j),
+ *        cluster_size (C,) int64, cluster_graph_ptr (B+1,) int64, visible (N,) u8
+ *   out: e01_j, e01_i (<=N) ; e11_cur (2, <= sum C_g^2) written as two rows of stride
+ *        e11_capacity (pass it as cns_batch.l1_cur_stride) ; cluster_mask (C,) ;
+ *        counts_out[0]=E01, [1]=E11cur (device int64).
+ */
+size_t cns_graph_mask_workspace_bytes(int64_t n_nodes, int64_t n_clusters, int64_t n_graphs);
+int cns_graph_mask(const int64_t* belong, const int64_t* member_order, const int64_t* cluster_size,
+                   const int64_t* cluster_graph_ptr, const uint8_t* visible,
+                   int64_t n_nodes, int64_t n_clusters, int64_t n_graphs,
+                   int64_t* e01_j, int64_t* e01_i, int64_t* e11_cur, int64_t e11_capacity,
+                   uint8_t* cluster_mask, int64_t* counts_out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* 1-NN keypoint -> exemplar labelling, the only nearest-neighbour search of the
+ * reference's clustering (sklearn AffinityPropagation final assignment,
+ * argmax_k -||x - e_k||^2 ).  points (N,2) f64 ; point_graph (N,) graph id of
+ * each point or NULL (one graph) ; exemplars (sum K,2) f64 with per-graph ranges
+ * exemplar_ptr (B+1,) ; labels (N,) int32 = rank of the nearest exemplar inside its graph. */
+int cns_label_nearest(const double* points, const int64_t* point_graph, int64_t n_points,
+                      const double* exemplars, const int64_t* exemplar_ptr, int32_t* labels,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNS_B200_H */
