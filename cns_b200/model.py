@@ -275,11 +275,12 @@ class GraphVS(nn.Module):
         dev = keep[0].device
         h = self._handle(dev)
         nb, nc = b.n_graphs, b.n_clusters
-        out = torch.empty(nb * 13 + nc * 128, dtype=torch.float32, device=dev)
-        vec = out[:nb * 6].view(nb, 6)
-        vel = out[nb * 6:nb * 12].view(nb, 6)
-        nrm = out[nb * 12:nb * 13].view(nb, 1)
-        hid = out[nb * 13:].view(nc, 128)
+        # one allocation; the (C,128) block first so its rows stay 16-byte aligned
+        out = torch.empty(nc * 128 + nb * 13, dtype=torch.float32, device=dev)
+        hid = out[:nc * 128].view(nc, 128)
+        vec = out[nc * 128:nc * 128 + nb * 6].view(nb, 6)
+        vel = out[nc * 128 + nb * 6:nc * 128 + nb * 12].view(nb, 6)
+        nrm = out[nc * 128 + nb * 12:].view(nb, 1)
         if hidden is not None:
             hidden = hidden.detach().to(dev, torch.float32).contiguous()
             if hidden.shape != (nc, 128):
