@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""bench.py - servo graphs/s of the CNS hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision fp32|tf32x3|bf16]
+
+Workload (BASELINE.json configs[1]): pretrained checkpoints/cns.pth, batched inference,
+1024 synthetic servo graphs x 512 keypoints per GPU (weak scaling: every rank owns its own 1024
+graphs; inference needs no collective).  One "step" = one GraphVS forward (+ fused postprocess)
+over one 1024-graph batch.
+
+  value : graphs/s with the batches already resident in HBM (CUDA events, max over ranks).
+  e2e   : the same through the public API with HOST (pinned) GraphData: Batch.to(device) every
+          step + the forward + a device->host read of the (B,6) velocities.
+  roofline     : the dominant kernel (encoder edge kernel), timed live with CUDA events on its
+                 launching stream (cns_profile_begin/end).
+  cpu_baseline : the oracle (CPU port of the reference forward) on a bounded sample of the same
+                 workload, on this box's host cores.
+`--impl reference` times that CPU implementation alone (the reference itself is Python on PyG,
+which cannot be installed here; the port in oracle/ is the stand-in, kind "port").
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GRAPHS, N_POINTS, MISSING = 1024, 512, 0.1
+N_ROTATE = 4          # distinct input batches cycled through so the inputs exceed L2 (126 MB)
+# algorithmic FLOPs of the encoder edge kernel per (edge, side): 5 GEMMs 128x128 + in_enc + pos_nn.0
+FLOP_PER_EDGE_SIDE = 2 * (5 * 128 * 128 + 2 * 128 + 4 * 128)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("CNS_PRECISION", "fp32"))
+    ap.add_argument("--graphs", type=int, default=N_GRAPHS)
+    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--cpu-sample", type=int, default=64, help="graphs per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def build_batches(n_graphs, n_points, seed, n_batches):
+    """`n_batches` host batches: the same scenes (clustered once) observed at successive frames."""
+    from cns_b200 import synth
+    from cns_b200.data import Batch
+    scenes = synth.make_scenes(n_graphs, n_points, seed=seed, n_layouts=64)
+    out = []
+    for _ in range(n_batches):
+        out.append(Batch.from_data_list([s.frame(MISSING) for s in scenes]))
+        for s in scenes:    # move every camera a little so each batch holds different coordinates
+            s.step(synth.pbvs_straight(s.cur_wcT, s.tar_wcT) * 2)
+    return out
+
+
+def tensor_bytes(batch):
+    import torch
+    return sum(v.numel() * v.element_size() for _, v in batch.items() if isinstance(v, torch.Tensor))
+
+
+def cpu_reference_rate(n_graphs, n_points, steps, warmup, budget_s=25.0):
+    """graphs/s of the CPU port of the reference forward (oracle/cns_oracle.py), all host threads."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cns_oracle
+    from cns_b200 import ckpt
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = ckpt.read_state_dict(os.path.join(ROOT, "checkpoints", "cns.pth"))
+    batch = build_batches(n_graphs, n_points, 2022, 1)[0]
+    with torch.no_grad():
+        for _ in range(max(1, warmup)):
+            cns_oracle.forward(sd, batch, None)
+        t0, done = time.perf_counter(), 0
+        for _ in range(steps):
+            cns_oracle.forward(sd, batch, None)
+            done += 1
+            if time.perf_counter() - t0 > budget_s:
+                break
+        dt = time.perf_counter() - t0
+    return n_graphs * done / dt, dt / done * 1e3, done, torch.get_num_threads()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = "cns.pth batched inference, %d synthetic servo graphs x %d keypoints per GPU" % (args.graphs, args.points)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        rate, ms, done, cores = cpu_reference_rate(args.cpu_sample, args.points, args.steps, args.warmup, 120.0)
+        sample = "%d of the %d graphs per step (N=%d keypoints, 10%% missing), fp32 torch CPU" % (
+            args.cpu_sample, args.graphs, args.points)
+        print(json.dumps({
+            "impl": "reference", "metric": "servo graphs/sec (fwd)", "value": rate, "unit": "graphs/s",
+            "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from cns_b200 import _lib, ckpt
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    net = ckpt.load_model(os.path.join(ROOT, "checkpoints", "cns.pth"), dev, precision=args.precision)
+
+    host = [b.pin_memory() for b in build_batches(args.graphs, args.points, 2022 + rank, N_ROTATE)]
+    resident = [b.to(dev) for b in host]
+    n_edges = [int(b.l0_to_l1_edge_index_j_cur.numel()) for b in host]
+    h2d = tensor_bytes(host[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    handle = net._handle(dev)
+    with torch.no_grad():
+        # ---------------- device-resident throughput ("value") + live kernel timing ----------------
+        for i in range(args.warmup):
+            net(resident[i % N_ROTATE], None)
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        _lib.check(lib.cns_profile_begin(handle.raw), "profile_begin")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            net(resident[i % N_ROTATE], None)
+        e1.record()
+        barrier()
+        kms, kn, launches = C.c_float(), C.c_int(), C.c_longlong()
+        _lib.check(lib.cns_profile_end(handle.raw, C.byref(kms), C.byref(kn), C.byref(launches)), "profile_end")
+        sampler.stop_flag = True
+        total_ms = max_over_ranks(e0.elapsed_time(e1))
+        value = args.graphs * world * args.steps / (total_ms * 1e-3)
+
+        # ---------------- end to end: pinned host GraphData in, velocities out ----------------------
+        for i in range(args.warmup):
+            net(host[i % N_ROTATE].to(dev, non_blocking=True), None).vel.cpu()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(args.steps):
+            data = host[i % N_ROTATE].to(dev, non_blocking=True)       # host -> device, every step
+            pred = net(data, None)
+            vel = net.postprocess(pred, data).cpu()                    # device -> host read of the result
+        f1.record()
+        barrier()
+        e2e_ms = max_over_ranks(f0.elapsed_time(f1))
+        e2e = args.graphs * world * args.steps / (e2e_ms * 1e-3)
+        d2h = vel.numel() * vel.element_size()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_src = peaks()
+    kernel_ms = kms.value / max(kn.value, 1)
+    flops_per_launch = FLOP_PER_EDGE_SIDE * 2 * (sum(n_edges[i % N_ROTATE] for i in range(args.steps)) / args.steps)
+    achieved = flops_per_launch / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else 0.0
+    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "enc_edge_traffic.json")) as f:
+            traffic = json.load(f).get(args.precision, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    line = {
+        "metric": "servo graphs/sec (fwd)", "value": value, "unit": "graphs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "bf16": "bf16"}[args.precision], "data": "synthetic",
+        "config": {"workload": workload, "missing_keypoints": MISSING, "weights": "checkpoints/cns.pth",
+                   "hidden": "None (first frame)", "l2": "inputs rotate over %d distinct batches (%.0f MB) > L2" % (
+                       N_ROTATE, N_ROTATE * h2d / 1e6), "graphs_per_gpu": args.graphs},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e, "unit": "graphs/s", "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches.value),
+        "roofline": {"kernel": "enc_edge (%s)" % args.precision, "bound": "tensor", "achieved": achieved,
+                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": pk_src + " bf16 sustained", "kernel_ms": kernel_ms,
+                     "kernel_share_of_step": kernel_ms / (total_ms / args.steps),
+                     "flops_per_launch": flops_per_launch},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        rate, ms, done, cores = cpu_reference_rate(args.cpu_sample, args.points, 50, 1, 20.0)
+        line["cpu_baseline"] = {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port",
+                                "sample": "%d graphs x %d keypoints per step, %d steps (%.1f ms/step)" % (
+                                    args.cpu_sample, args.points, done, ms)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

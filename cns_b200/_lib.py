@@ -51,6 +51,8 @@ def _declare(lib):
         "cns_param_name": (C.c_char_p, [i32]),
         "cns_param_numel": (i64, [i32]),
         "cns_set_precision": (i32, [vp, i32]),
+        "cns_profile_begin": (i32, [vp]),
+        "cns_profile_end": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
         "cns_forward_workspace_bytes": (sz, [C.POINTER(cns_batch)]),
         "cns_forward_save_bytes": (sz, [C.POINTER(cns_batch)]),
         "cns_graphvs_forward": (i32, [vp, C.POINTER(cns_batch), vp, vp, vp, vp, vp, vp, sz, vp, sz, vp]),

@@ -21,7 +21,12 @@ void set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
-#define CNS_LAUNCH_CHECK() CNS_CUDA_CHECK(cudaGetLastError())
+extern long long g_launch_count;   // kernels launched by this library (host-side counter)
+#define CNS_LAUNCH_CHECK()        \
+  do {                            \
+    ++cns::g_launch_count;        \
+    CNS_CUDA_CHECK(cudaGetLastError()); \
+  } while (0)
 
 #define CNS_REQUIRE(cond, msg)                                   \
   do {                                                           \
@@ -76,6 +81,8 @@ struct cns_handle {
   float* packed_base;
   cns::Packed pk;
   bool weights_loaded;
+  // optional CUDA-event timing of the dominant kernel (encoder edge kernel), see cns_profile_*
+  int timing; int ev_n; cudaEvent_t ev[2 * 256];
   // pinned / device staging for the *_host entry point
   void* stage_host; size_t stage_host_bytes;
   void* stage_dev;  size_t stage_dev_bytes;

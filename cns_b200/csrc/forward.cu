@@ -103,11 +103,14 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   ee.w_in = h->P(P_IN_W); ee.b_in = h->P(P_IN_B); ee.w_p0 = h->P(P_POS0_W); ee.b_p0 = h->P(P_POS0_B);
   ee.enc_chain = pk.enc_chain; ee.b_p1 = h->P(P_POS1_B); ee.b_a0 = h->P(P_ATT0_B); ee.b_a1 = h->P(P_ATT1_B);
   ee.clu_feat = f.clu_feat; ee.partial = f.partial;
+  const bool timed = h->timing && h->ev_n < 256;
+  if (timed) CNS_CUDA_CHECK(cudaEventRecord(h->ev[2 * h->ev_n], s));
   if (h->precision == CNS_PREC_FP32) {
     RUN(enc_edge_fp32(ee, s));
   } else {
     RUN(enc_edge_tc(ee, h->precision, nullptr, h->sm_count, s));
   }
+  if (timed) { CNS_CUDA_CHECK(cudaEventRecord(h->ev[2 * h->ev_n + 1], s)); ++h->ev_n; }
 
   EncFinishArgs ef{};
   ef.n_clusters = C; ef.n_slots = f.n_slots; ef.clu_rowptr = f.clu_rowptr; ef.partial = f.partial;

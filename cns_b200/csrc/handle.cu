@@ -6,6 +6,7 @@
 namespace cns {
 
 static thread_local char g_err[512] = "";
+long long g_launch_count = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -217,6 +218,7 @@ int cns_create(cns_handle** out, int device) {
 int cns_destroy(cns_handle* h) {
   if (!h) return CNS_OK;
   cudaSetDevice(h->device);
+  if (h->ev[0]) for (int i = 0; i < 2 * 256; ++i) cudaEventDestroy(h->ev[i]);
   cudaFree(h->raw);
   cudaFree(h->packed_base);
   if (h->stage_host) cudaFreeHost(h->stage_host);
@@ -252,6 +254,33 @@ int cns_load_weights(cns_handle* h, const float* const* params_host, const int64
 int cns_load_weights_device(cns_handle* h, const float* const* params_dev, const int64_t* numels,
                             int n_tensors, void* stream) {
   return load_common(h, params_dev, numels, n_tensors, stream, cudaMemcpyDeviceToDevice);
+}
+
+// CUDA-event timing of the encoder edge kernel on the launching stream + kernel-launch counter.
+int cns_profile_begin(cns_handle* h) {
+  CNS_REQUIRE(h != nullptr, "NULL handle");
+  CNS_CUDA_CHECK(cudaSetDevice(h->device));
+  if (!h->ev[0]) for (int i = 0; i < 2 * 256; ++i) CNS_CUDA_CHECK(cudaEventCreate(&h->ev[i]));
+  h->ev_n = 0;
+  h->timing = 1;
+  g_launch_count = 0;
+  return CNS_OK;
+}
+
+int cns_profile_end(cns_handle* h, float* enc_edge_ms_total, int* n_timed, long long* launches) {
+  CNS_REQUIRE(h != nullptr, "NULL handle");
+  h->timing = 0;
+  float total = 0.f;
+  for (int i = 0; i < h->ev_n; ++i) {
+    float ms = 0.f;
+    CNS_CUDA_CHECK(cudaEventSynchronize(h->ev[2 * i + 1]));
+    CNS_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]));
+    total += ms;
+  }
+  if (enc_edge_ms_total) *enc_edge_ms_total = total;
+  if (n_timed) *n_timed = h->ev_n;
+  if (launches) *launches = g_launch_count;
+  return CNS_OK;
 }
 
 int cns_set_precision(cns_handle* h, int precision) {

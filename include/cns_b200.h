@@ -73,6 +73,12 @@ const char* cns_param_name(int k);      /* e.g. "encoder.in_enc.fcs.0.weight" */
 int64_t cns_param_numel(int k);
 int cns_set_precision(cns_handle* h, int precision /* cns_precision */);
 
+/* Measurement hooks: between begin and end every cns_graphvs_forward brackets its dominant
+ * kernel (the encoder edge kernel) with CUDA events on the launching stream (first 256
+ * forwards) and the library counts the kernels it launches.  end() waits for the events. */
+int cns_profile_begin(cns_handle* h);
+int cns_profile_end(cns_handle* h, float* enc_edge_ms_total, int* n_timed, long long* kernel_launches);
+
 /* ---- one batch of servo graphs ------------------------------------------------------
  * Field-for-field the tensors GraphVS.forward unpacks from a GraphData/Batch
  * (graph_vs.py:285-307; field list graph_gen.py:257-275). */

@@ -1,0 +1,157 @@
+"""GPU (-m gpu): GraphVS.forward through the C ABI vs the CPU oracle and the golden fixtures.
+
+Tolerance: velocities / hidden features within rel 1e-4 (fp32 path) of the fp64 oracle, where
+"rel" is max|got - ref| / max|ref| per tensor (north_star: "rel 1e-4 in fp32")."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cns_oracle
+from cns_b200 import Batch, GraphGenerator, GraphVS, _lib, ckpt, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+TOL = {"fp32": 1e-4, "tf32x3": 1e-4, "bf16": 2e-2}
+
+
+def rel(got, ref):
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    return float((got - ref).abs().max() / ref.abs().max().clamp(min=1e-12))
+
+
+@pytest.fixture(scope="module")
+def net():
+    return ckpt.load_model(os.path.join(ROOT, "checkpoints", "cns.pth"), "cuda:0")
+
+
+def _check(net, batch, hid_g, hid_o, sd, tol=1e-4):
+    ov, on, oh = cns_oracle.forward(sd, batch, hid_o, dtype=torch.float64)
+    with torch.no_grad():
+        pred = net(batch.to("cuda:0"), hid_g, check=True)
+    assert rel(pred[0], ov) < tol and rel(pred[1], on) < tol and rel(pred[2], oh) < tol
+    ovel = cns_oracle.postprocess((ov, on), batch.tPo_norm.reshape(-1))
+    assert rel(pred.vel, ovel) < tol
+    assert rel(net.postprocess(pred, batch.to("cuda:0")), ovel) < tol
+    return pred, oh
+
+
+@pytest.mark.parametrize("name", ["forward_single.pt", "forward_ragged.pt"])
+def test_golden_fixtures(net, name):
+    """Inputs and outputs recorded from the unmodified reference (tests/golden/make_golden.py)."""
+    case = torch.load(os.path.join(GOLD, name), weights_only=False)
+    hidden = None
+    for st in case["steps"]:
+        data = {k: v.to("cuda:0") for k, v in st["fields"].items()}
+        with torch.no_grad():
+            pred = net(data, hidden, check=True)
+        hidden = pred[2]
+        assert rel(pred[0], st["vel_si_vec"]) < 1e-4
+        assert rel(pred[1], st["vel_si_norm"]) < 1e-4
+        assert rel(pred[2], st["hidden"]) < 1e-4
+        assert rel(pred.vel, st["vel"]) < 1e-4
+
+
+@pytest.mark.parametrize("sizes,missing", [([40], 0.0), ([5, 16, 17, 64], 0.2), ([512] * 6, 0.1),
+                                           ([24, 100, 300, 512, 33], 0.3), ([2000], 0.05)])
+def test_forward_matches_oracle_recurrent(net, state_dict, sizes, missing):
+    """Ragged batches, missing keypoints, clusters larger than a 64-edge softmax piece (N=2000),
+    hidden state carried over 3 frames with the camera moved by the predicted velocity."""
+    rng = np.random.default_rng(len(sizes))
+    np.random.seed(len(sizes))
+    scenes = [synth.Scene(rng, n) for n in sizes]
+    hid_g = hid_o = None
+    for _ in range(3):
+        frames = [s.frame(missing) for s in scenes]
+        batch = Batch.from_data_list(frames) if len(frames) > 1 else frames[0]
+        pred, hid_o = _check(net, batch, hid_g, hid_o, state_dict)
+        hid_g = pred[2]
+        for s, v in zip(scenes, pred.vel.cpu().numpy()):
+            s.step(v * 2)
+
+
+def test_all_clusters_of_one_graph_masked(net, state_dict):
+    """A graph whose every keypoint is missing: empty segments must give zeros, not NaNs."""
+    rng = np.random.default_rng(9)
+    np.random.seed(9)
+    a, b = synth.Scene(rng, 30), synth.Scene(rng, 50)
+    fa = a.generator.get_data(synth.project_norm(a.cur_wcT, a.points), missing_node_indices=np.arange(30))
+    fb = b.frame(0.5)
+    batch = Batch.from_data_list([fb, fa])      # the fully masked graph is last (PyG would drop its row)
+    with torch.no_grad():
+        pred = net(batch.to("cuda:0"), None, check=True)
+    assert torch.isfinite(pred[0]).all() and torch.isfinite(pred[2]).all()
+    ov, on, oh = cns_oracle.forward(state_dict, Batch.from_data_list([fb]), None, dtype=torch.float64)
+    assert rel(pred[0][:1], ov) < 1e-4 and rel(pred[2][:oh.shape[0]], oh) < 1e-4
+
+
+def test_deterministic_and_batch_invariant(net):
+    """Same input twice -> bit-identical output (no fp atomics); a graph's result does not depend on
+    its neighbours in the batch beyond fp32 re-association of the softmax pieces."""
+    batch = synth.make_batch(16, 200, seed=5, n_layouts=4)
+    dev = batch.to("cuda:0")
+    with torch.no_grad():
+        p1 = net(dev, None)
+        p2 = net(dev, None)
+    assert torch.equal(p1[0], p2[0]) and torch.equal(p1[2], p2[2])
+    scenes = synth.make_scenes(16, 200, seed=5, n_layouts=4)
+    frames = [s.frame(0.1) for s in scenes]
+    with torch.no_grad():
+        full = net(Batch.from_data_list(frames).to("cuda:0"), None)
+        solo = net(Batch.from_data_list(frames[5:6]).to("cuda:0"), None)
+    assert rel(solo[0], full[0][5:6]) < 1e-5
+
+
+def test_unsorted_cluster_edges_are_reported(net):
+    d = synth.Scene(np.random.default_rng(1), 40).frame().to("cuda:0")
+    d.l0_to_l1_edge_index_i_cur = d.l0_to_l1_edge_index_i_cur.flip(0).contiguous()
+    with pytest.raises(_lib.CnsError):
+        with torch.no_grad():
+            net(d, None, check=True)
+
+
+def test_cpu_tensors_rejected(net):
+    d = synth.Scene(np.random.default_rng(1), 40).frame()
+    with pytest.raises(_lib.CnsError):
+        net(d, None)
+
+
+def test_host_pointer_entry_matches_device_entry(net):
+    """cns_graphvs_forward_host (host buffers in, host buffers out) == device-pointer call."""
+    lib = _lib.load()
+    batch = synth.make_batch(8, 128, seed=7, n_layouts=4)
+    with torch.no_grad():
+        ref = net(batch.to("cuda:0"), None)
+    torch.cuda.synchronize()
+    b, keep = GraphVS.make_batch_struct(batch)      # CPU tensors -> host pointers
+    nb, nc = b.n_graphs, b.n_clusters
+    vec, nrm = torch.empty(nb, 6), torch.empty(nb, 1)
+    hid, vel = torch.empty(nc, 128), torch.empty(nb, 6)
+    h = net._handle(torch.device("cuda:0"))
+    _lib.check(lib.cns_graphvs_forward_host(h.raw, C.byref(b), None, _lib.ptr(vec), _lib.ptr(nrm),
+                                            _lib.ptr(hid), _lib.ptr(vel)), "forward_host")
+    assert torch.equal(vec, ref[0].cpu()) and torch.equal(hid, ref[2].cpu()) and torch.equal(vel, ref.vel.cpu())
+
+
+def test_full_size_batch_properties(net, state_dict):
+    """BASELINE config: 1024 graphs x 512 keypoints.  The oracle is too slow for all of it, so:
+    (1) spot-check 8 graphs against the oracle, (2) permuting the graphs of the batch permutes the
+    outputs, (3) finiteness and hidden-state shape."""
+    scenes = synth.make_scenes(1024, 512, seed=2022, n_layouts=16)
+    frames = [s.frame(0.1) for s in scenes]
+    batch = Batch.from_data_list(frames)
+    with torch.no_grad():
+        pred = net(batch.to("cuda:0"), None, check=True)
+    assert pred[0].shape == (1024, 6) and pred[2].shape == (int(batch.num_clusters.sum()), 128)
+    assert torch.isfinite(pred[0]).all() and torch.isfinite(pred[2]).all()
+    pick = [0, 1, 17, 255, 256, 700, 1022, 1023]
+    ov, on, oh = cns_oracle.forward(state_dict, Batch.from_data_list([frames[i] for i in pick]), None,
+                                    dtype=torch.float64)
+    assert rel(pred[0][pick], ov) < 1e-4 and rel(pred[1][pick], on) < 1e-4
+    perm = np.random.default_rng(0).permutation(1024)
+    with torch.no_grad():
+        pp = net(Batch.from_data_list([frames[i] for i in perm]).to("cuda:0"), None)
+    assert rel(pp[0], pred[0][torch.as_tensor(perm, device="cuda")]) < 1e-5

@@ -1,0 +1,165 @@
+"""GPU (-m gpu): per-op C-ABI entry points vs the oracle's segment primitives / numpy."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cns_oracle
+from cns_b200 import Batch, GraphGenerator, _lib, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _sp():
+    return _lib.stream_ptr(torch.device(DEV))
+
+
+def _csr(edge_index, n_dst):
+    lib = _lib.load()
+    e = edge_index.shape[1]
+    rowptr = torch.empty(n_dst + 1, dtype=torch.int32, device=DEV)
+    src = torch.empty(max(e, 1), dtype=torch.int32, device=DEV)
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
+    ei = edge_index.to(DEV).contiguous()
+    _lib.check(lib.cns_csr_by_dst(_lib.ptr(ei), e, n_dst, _lib.ptr(rowptr), _lib.ptr(src), _lib.ptr(ws),
+                                  ws.numel(), _sp()), "csr")
+    return rowptr, src[:e]
+
+
+def test_csr_by_dst_is_a_permutation_grouped_by_destination():
+    g = torch.Generator().manual_seed(0)
+    n, e = 300, 5000
+    ei = torch.stack([torch.randint(0, n, (e,), generator=g), torch.randint(0, n - 10, (e,), generator=g)])
+    rowptr, src = _csr(ei, n)
+    rowptr, src = rowptr.cpu().long(), src.cpu().long()
+    deg = torch.bincount(ei[1], minlength=n)
+    assert torch.equal(rowptr[1:] - rowptr[:-1], deg) and int(rowptr[0]) == 0
+    for i in (0, 5, 123, 289, 299):      # rows hold exactly the sources of that destination (as multisets)
+        mine = sorted(src[rowptr[i]:rowptr[i + 1]].tolist())
+        assert mine == sorted(ei[0][ei[1] == i].tolist())
+    r0, s0 = _csr(torch.zeros(2, 0, dtype=torch.long), 7)       # empty edge list
+    assert r0.cpu().tolist() == [0] * 8
+
+
+@pytest.mark.parametrize("f", [128, 256])
+def test_edgeconv_max_factorised_equals_literal_message_passing(f):
+    """out_i = P_i + max_j Q_j equals max_j Linear([x_i, x_j - x_i, pos_j - pos_i]) of the oracle
+    (graph_vs.py:107-111), including destinations with no in-edge (-> 0)."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(1)
+    n, fin = 200, f
+    x = torch.randn(n, fin, generator=g, dtype=torch.float64)
+    pos = torch.randn(n, 2, generator=g, dtype=torch.float64)
+    W = torch.randn(f, 2 * fin + 2, generator=g, dtype=torch.float64) / (fin ** 0.5)
+    b = torch.randn(f, generator=g, dtype=torch.float64)
+    ei = torch.stack([torch.randint(0, n, (3000,), generator=g), torch.randint(0, n - 20, (3000,), generator=g)])
+    ref = cns_oracle.peconv({"c.msg_nn.fcs.0.weight": W, "c.msg_nn.fcs.0.bias": b}, "c", x, pos, ei)
+    W1, W2, W3 = W[:, :fin], W[:, fin:2 * fin], W[:, 2 * fin:]
+    P = x @ (W1 - W2).T - pos @ W3.T + b
+    Q = x @ W2.T + pos @ W3.T
+    pq = torch.cat([P, Q], 1).float().to(DEV).contiguous()
+    rowptr, src = _csr(ei, n)
+    out = torch.empty(n, f, device=DEV)
+    _lib.check(lib.cns_edgeconv_max(_lib.ptr(pq), _lib.ptr(rowptr), _lib.ptr(src), n, f, _lib.ptr(out), _sp()), "ec")
+    assert float((out.double().cpu() - ref).abs().max() / ref.abs().max()) < 1e-5
+    assert float(out[n - 20:].abs().max()) == 0.0
+
+
+def test_graphnorm_relu_matches_oracle():
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(2)
+    sizes = [1, 7, 18, 40, 3]
+    n = sum(sizes)
+    x = torch.randn(n, 128, generator=g) * 3 + 1
+    x[5] = 0                                   # masked cluster rows are all-zero but counted
+    w, b, ms = torch.rand(128, generator=g) + .5, torch.randn(128, generator=g), torch.rand(128, generator=g)
+    batch = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+    ref = torch.relu(cns_oracle.graph_norm({"p.weight": w.double(), "p.bias": b.double(), "p.mean_scale": ms.double()},
+                                           "p", x.double(), batch, len(sizes)))
+    gp = torch.tensor(np.cumsum([0] + sizes), dtype=torch.int32, device=DEV)
+    y = torch.empty(n, 128, device=DEV)
+    xd, wd, bd, msd = x.to(DEV), w.to(DEV), b.to(DEV), ms.to(DEV)
+    _lib.check(lib.cns_graphnorm_relu(_lib.ptr(xd), _lib.ptr(gp), len(sizes), _lib.ptr(wd), _lib.ptr(bd),
+                                      _lib.ptr(msd), _lib.ptr(y), _sp()), "gn")
+    assert float((y.double().cpu() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("m,k1,k2,n", [(1, 128, 0, 128), (77, 128, 128, 256), (1000, 128, 128, 512)])
+def test_linear_matches_fp64(m, k1, k2, n):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    x1, x2 = torch.randn(m, k1, generator=g), torch.randn(m, max(k2, 1), generator=g)
+    wt, bias, res = torch.randn(k1 + k2, n, generator=g) / 16, torch.randn(n, generator=g), torch.randn(m, n, generator=g)
+    ref = x1.double() @ wt[:k1].double()
+    if k2:
+        ref = ref + x2.double() @ wt[k1:].double()
+    ref = torch.relu(ref + bias.double() + res.double())
+    y = torch.empty(m, n, device=DEV)
+    a = [t.to(DEV).contiguous() for t in (x1, x2, wt, bias, res)]
+    _lib.check(lib.cns_linear(_lib.ptr(a[0]), k1, _lib.ptr(a[1]) if k2 else None, k2, _lib.ptr(a[2]), _lib.ptr(a[3]),
+                              _lib.ptr(a[4]), 1, m, n, _lib.ptr(y), _sp()), "linear")
+    assert float((y.double().cpu() - ref).abs().max()) < 1e-5 * float(ref.abs().max())
+
+
+def test_graph_mask_bit_exact_vs_graph_generator():
+    """Batched per-frame masking on device == GraphGenerator._get_graph + Batch collation (bit-exact,
+    edge order included): reference graph_gen.py:199-228."""
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    np.random.seed(3)
+    gens, vis, frames = [], [], []
+    for n in (12, 40, 130, 16, 300):
+        pts = synth.project_norm(synth.sample_target_pose(rng), synth.sample_points(rng, n))
+        g = GraphGenerator(pts)
+        frac = rng.choice([0.0, 0.3, 0.8, 1.0])
+        missing = np.sort(rng.choice(len(pts), size=int(len(pts) * frac), replace=False))
+        v = np.ones(len(pts), bool); v[missing] = False
+        gens.append(g); vis.append(v); frames.append(g.get_data(pts, missing_node_indices=missing))
+    ref = Batch.from_data_list(frames)
+    n_nodes = np.array([g.num_points for g in gens]); n_clu = np.array([g.num_clusters for g in gens])
+    noff, coff = np.cumsum(n_nodes) - n_nodes, np.cumsum(n_clu) - n_clu
+    belong = np.concatenate([g.belong_cluster_index + c for g, c in zip(gens, coff)])
+    order = np.concatenate([g.l0_to_l1_edge_index[0] + o for g, o in zip(gens, noff)])
+    csize = np.concatenate([g.cluster_points_count for g in gens]).astype(np.int64)
+    gptr = np.concatenate([[0], np.cumsum(n_clu)]).astype(np.int64)
+    N, Cn, B = int(n_nodes.sum()), int(n_clu.sum()), len(gens)
+    cap = int((n_clu ** 2).sum())
+    d = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=DEV)
+    t_belong, t_order, t_csize, t_gptr = d(belong, torch.int64), d(order, torch.int64), d(csize, torch.int64), d(gptr, torch.int64)
+    t_vis = d(np.concatenate(vis), torch.uint8)
+    e01_j, e01_i = torch.empty(N, dtype=torch.int64, device=DEV), torch.empty(N, dtype=torch.int64, device=DEV)
+    e11 = torch.empty(2, cap, dtype=torch.int64, device=DEV)
+    cmask = torch.empty(Cn, dtype=torch.uint8, device=DEV)
+    counts = torch.zeros(2, dtype=torch.int64, device=DEV)
+    ws = torch.empty(lib.cns_graph_mask_workspace_bytes(N, Cn, B), dtype=torch.uint8, device=DEV)
+    _lib.check(lib.cns_graph_mask(_lib.ptr(t_belong), _lib.ptr(t_order), _lib.ptr(t_csize), _lib.ptr(t_gptr),
+                                  _lib.ptr(t_vis), N, Cn, B, _lib.ptr(e01_j), _lib.ptr(e01_i), _lib.ptr(e11), cap,
+                                  _lib.ptr(cmask), _lib.ptr(counts), _lib.ptr(ws), ws.numel(), _sp()), "graph_mask")
+    n01, n11 = counts.cpu().tolist()
+    assert n01 == ref.l0_to_l1_edge_index_j_cur.numel() and n11 == ref.l1_dense_edge_index_cur.shape[1]
+    assert torch.equal(e01_j[:n01].cpu(), ref.l0_to_l1_edge_index_j_cur)
+    assert torch.equal(e01_i[:n01].cpu(), ref.l0_to_l1_edge_index_i_cur)
+    assert torch.equal(e11[:, :n11].cpu(), ref.l1_dense_edge_index_cur)
+    assert torch.equal(cmask.bool().cpu(), ref.cluster_mask)
+
+
+def test_label_nearest_matches_numpy_argmax():
+    lib = _lib.load()
+    rng = np.random.default_rng(4)
+    sizes, ks = [50, 700, 9], [4, 23, 9]
+    pts = [rng.random((n, 2)) for n in sizes]
+    ex = [p[rng.choice(len(p), k, replace=False)] for p, k in zip(pts, ks)]
+    want = []
+    for p, e in zip(pts, ex):
+        d2 = (-2 * (p @ e.T) + (p * p).sum(1)[:, None]) + (e * e).sum(1)[None, :]
+        want.append(np.argmax(-np.maximum(d2, 0), axis=1))
+    P = torch.as_tensor(np.concatenate(pts), device=DEV)
+    E = torch.as_tensor(np.concatenate(ex), device=DEV)
+    pg = torch.as_tensor(np.repeat(np.arange(3), sizes), device=DEV)
+    xp = torch.as_tensor(np.concatenate([[0], np.cumsum(ks)]), device=DEV)
+    lab = torch.empty(sum(sizes), dtype=torch.int32, device=DEV)
+    _lib.check(lib.cns_label_nearest(_lib.ptr(P), _lib.ptr(pg), sum(sizes), _lib.ptr(E), _lib.ptr(xp), _lib.ptr(lab), _sp()), "label")
+    assert np.array_equal(lab.cpu().numpy(), np.concatenate(want))
