@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - servo graphs/s of the CNS hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision fp32|tf32x3|bf16]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision fp32|f16|bf16]
 
 Workload (BASELINE.json configs[1]): pretrained checkpoints/cns.pth, batched inference,
 1024 synthetic servo graphs x 512 keypoints per GPU (weak scaling: every rank owns its own 1024
@@ -239,7 +239,7 @@ def main():
         "metric": "servo graphs/sec (fwd)", "value": value, "unit": "graphs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "bf16": "bf16"}[args.precision], "data": "synthetic",
+        "dtype": {"fp32": "f32", "f16": "f16", "bf16": "bf16"}[args.precision], "data": "synthetic",
         "config": {"workload": workload, "missing_keypoints": MISSING, "weights": "checkpoints/cns.pth",
                    "hidden": "None (first frame)", "l2": "inputs rotate over %d distinct batches (%.0f MB) > L2" % (
                        N_ROTATE, N_ROTATE * h2d / 1e6), "graphs_per_gpu": args.graphs},

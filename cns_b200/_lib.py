@@ -14,8 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcns_sm100.so")
 
 CNS_OK = 0
-PREC_FP32, PREC_TF32X3, PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "bf16": PREC_BF16}
+PREC_FP32, PREC_F16, PREC_BF16 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "f16": PREC_F16, "bf16": PREC_BF16}
 
 
 class CnsError(RuntimeError):
@@ -51,6 +51,7 @@ def _declare(lib):
         "cns_param_name": (C.c_char_p, [i32]),
         "cns_param_numel": (i64, [i32]),
         "cns_set_precision": (i32, [vp, i32]),
+        "cns_set_tc_tile": (i32, [vp, i32]),
         "cns_profile_begin": (i32, [vp]),
         "cns_profile_end": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
         "cns_forward_workspace_bytes": (sz, [C.POINTER(cns_batch)]),
@@ -119,6 +120,9 @@ class Handle(object):
         check(lib.cns_create(C.byref(h), self.device.index or 0), "cns_create")
         self._h = h
         self.precision = "fp32"
+        tile = os.environ.get("CNS_TC_TILE")
+        if tile:
+            check(lib.cns_set_tc_tile(h, int(tile)), "cns_set_tc_tile")
 
     def __del__(self):
         try:

@@ -81,6 +81,10 @@ struct cns_handle {
   float* packed_base;
   cns::Packed pk;
   bool weights_loaded;
+  // tensor-core (tcgen05) encoder operands: bf16 image then f16 image, 5 swizzled 32 KB tiles each
+  unsigned char* tc_w_img;
+  float tc_small_host[128 * 2 + 128 + 128 * 4 + 128];   // in_enc / pos_nn.0 weights passed as kernel params
+  int tc_tile_n;                                        // edges per tensor-core tile (32 or 64)
   // optional CUDA-event timing of the dominant kernel (encoder edge kernel), see cns_profile_*
   int timing; int ev_n; cudaEvent_t ev[2 * 256];
   // pinned / device staging for the *_host entry point

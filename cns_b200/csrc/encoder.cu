@@ -311,7 +311,7 @@ enc_finish_kernel(EncFinishArgs p) {
     if (c < p.n_clusters) {
       int beg = p.clu_rowptr[c], end = p.clu_rowptr[c + 1];
       if (end > beg) {
-        int p0 = beg / ENC_PIECE_E, p1 = (end - 1) / ENC_PIECE_E;
+        int p0 = beg / p.piece_e, p1 = (end - 1) / p.piece_e;
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
           float* feat = p.clu_feat + ((size_t)side * p.n_clusters + c) * H;

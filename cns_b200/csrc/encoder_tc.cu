@@ -1,11 +1,497 @@
-// tcgen05 (5th-gen tensor core) version of the encoder edge kernel - placeholder until the
-// UMMA pipeline lands; selecting CNS_PREC_TF32X3 / CNS_PREC_BF16 reports UNSUPPORTED loudly.
+// tcgen05 (5th-gen tensor core) version of the encoder edge kernel (CNS_PREC_BF16 / CNS_PREC_F16).
+//
+// One persistent CTA per SM.  The five 128x128 weight matrices of the keypoint->cluster attention
+// chain (cns/models/graph_vs.py:195-214) stay resident in shared memory for the whole kernel
+// (160 KB of 16-bit operands, fetched once per CTA with 1-D TMA bulk copies).  Edges are processed
+// in tiles of TN edges; each tile is a "slot" owned by 4 warps (thread == output channel == TMEM
+// lane) and SLOTS = 128/TN tiles are in flight per CTA so that the SIMT epilogues of one tile
+// overlap the tensor-core work of the others.  Accumulators are transposed (D[channel][edge]): the
+// per-channel segment softmax over the edges of a cluster is then a sequential walk along TMEM
+// columns inside one thread, with warp-uniform segment boundaries - no shuffles, no atomics.
+//
+//   round A :  T = x (-lin_src)^T + hp pos_nn.1^T        V = x lin^T + hp pos_nn.1^T      (K = 256 each)
+//   epi   A :  t = T + a_dst[cluster] + b_p1  -> 16-bit -> smem (B operand of round B)
+//   round B :  U = t attn_nn.0^T                epi B : u = relu(U + b_a0) -> smem
+//   round C :  L = u attn_nn.1^T                final : online segment softmax of (L + b_a1) weighting (V + b_p1)
+//
+// x = relu(in_enc(feat)) and hp = relu(pos_nn.0(dpos)) have K = 2 / 4 and are produced by FFMA straight
+// into the swizzled B-operand layout.  Shared-memory operand tiles use the canonical K-major
+// SWIZZLE_128B layout ([k/64][row][128 B], 16-byte chunk index XOR (row & 7)).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace cns {
-int enc_edge_tc(const EncEdgeArgs&, int, const void*, int, cudaStream_t) {
-  set_error("tensor-core encoder not built into this library");
+
+constexpr int TC_W_BYTES = 128 * 128 * 2;         // one weight matrix, 16-bit
+constexpr int TC_NW = 5;                          // pos_nn.1, -lin_src, lin, attn_nn.0, attn_nn.1
+constexpr int TC_ACT_BYTES = 64 * 1024;           // all activation buffers of all slots
+
+// byte offset of element (row, col) in a K-major SWIZZLE_128B tile with `rows` rows, 16-bit elements
+__host__ __device__ __forceinline__ uint32_t sw128_off(int rows, int row, int col) {
+  int kc = col >> 6, c = (col & 63) >> 3;
+  return (uint32_t)(kc * rows * 128 + row * 128 + (((c ^ (row & 7)) << 4)) + (col & 7) * 2);
+}
+
+// ---- weight image: fp32 (k-major "chain" [5][k][o]) -> 16-bit swizzled A-operand tiles ----------
+template <bool BF16>
+__global__ void tc_pack_weights_kernel(const float* __restrict__ enc_chain, unsigned char* __restrict__ img) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= TC_NW * 128 * 128) return;
+  int w = idx / 16384, rem = idx % 16384;
+  int k = rem / 128, o = rem % 128;               // enc_chain[w][k][o] = W_w[o][k]
+  float v = enc_chain[idx];
+  unsigned short bits;
+  if (BF16) bits = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  else bits = __half_as_ushort(__float2half_rn(v));
+  *reinterpret_cast<unsigned short*>(img + (size_t)w * TC_W_BYTES + sw128_off(128, o, k)) = bits;
+}
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, 16-bit inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc),
+      "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive columns -> 32 registers per thread (thread i of the warp reads lane base+i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+        "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+        "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start>>4 | SBO(1024 B)>>4 at
+// bit 32 | version 1 at bit 46 | layout SWIZZLE_128B (2) at bit 61.  LBO is unused for this layout.
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  if (BF16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+
+struct TcSmallW {          // passed by value in the kernel parameter space (constant bank)
+  float w_in[128 * 2];
+  float b_in[128];
+  float w_p0[128 * 4];
+  float b_p0[128];
+};
+
+struct TcArgs {
+  EncEdgeArgs e;
+  const unsigned char* w_img;   // 5 swizzled 16-bit weight tiles
+  int n_tiles;                  // edge tiles of TN edges
+};
+
+// =================================================================================================
+template <int TN, bool BF16>
+__global__ void __launch_bounds__(128 * (128 / TN) + 32, 1)
+enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ TcSmallW sw) {
+  constexpr int SLOTS = 128 / TN;
+  constexpr int ACT_TILE = TN * 256;                 // one [TN x 128] 16-bit operand tile
+  constexpr int TMEM_COLS = 256;                     // SLOTS * 2 regions * TN columns
+  constexpr int EPI_THREADS = 128 * SLOTS;
+  extern __shared__ unsigned char smem_raw[];
+  // SWIZZLE_128B operand tiles need 1024-byte alignment: align by hand (1 KB of slack is allocated)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* w_s = smem;                                     // 5 x 32 KB
+  unsigned char* act_s = smem + TC_NW * TC_W_BYTES;              // SLOTS x 2 x ACT_TILE = 64 KB
+  unsigned char* tail = act_s + TC_ACT_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);            // [0]=weights, [1+2s]=ready[s], [2+2s]=done[s]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tail + 128);
+  int* ci_s = reinterpret_cast<int*>(tail + 256);                // [SLOTS][TN] cluster id per edge (-1: padding)
+
+  const EncEdgeArgs& p = args.e;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int total_tiles = args.n_tiles * 2;                      // x 2 sides
+  const bool is_mma_warp = (warp == EPI_THREADS / 32);
+
+  if (is_mma_warp) {
+    if (lane == 0) {
+      mbar_init(smem_u32(&bars[0]), 1);
+      for (int s = 0; s < SLOTS; ++s) {
+        mbar_init(smem_u32(&bars[1 + 2 * s]), 128);
+        mbar_init(smem_u32(&bars[2 + 2 * s]), 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_ptr_s), TMEM_COLS);
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(&bars[0]), TC_NW * TC_W_BYTES);
+      for (int w = 0; w < TC_NW; ++w)
+        bulk_g2s(smem_u32(w_s + w * TC_W_BYTES), args.w_img + (size_t)w * TC_W_BYTES, TC_W_BYTES, smem_u32(&bars[0]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (is_mma_warp) {
+    // ============================== MMA issuer ==============================================
+    // instruction descriptor: D=f32 (bit 4), A/B format at bits 7/10 (0 f16, 1 bf16), K-major both,
+    // N>>3 at bit 17, M>>4 at bit 24
+    const uint32_t fmt = BF16 ? 1u : 0u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TN >> 3) << 17) | ((128u >> 4) << 24);
+    mbar_wait(smem_u32(&bars[0]), 0);                            // weights landed
+    uint32_t ready_parity[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) ready_parity[s] = 0;
+    const uint32_t w_base = smem_u32(w_s);
+    for (int it = 0;; ++it) {
+      if ((it * SLOTS) * (int)gridDim.x + (int)blockIdx.x >= total_tiles) break;
+#pragma unroll 1
+      for (int round = 0; round < 3; ++round) {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          const int g = (it * SLOTS + s) * (int)gridDim.x + (int)blockIdx.x;
+          if (g >= total_tiles) continue;
+          mbar_wait(smem_u32(&bars[1 + 2 * s]), ready_parity[s]);
+          ready_parity[s] ^= 1;
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t b0 = smem_u32(act_s + (s * 2 + 0) * ACT_TILE);
+            const uint32_t b1 = smem_u32(act_s + (s * 2 + 1) * ACT_TILE);
+            const uint32_t d0 = tmem_base + (uint32_t)((s * 2 + 0) * TN);
+            const uint32_t d1 = tmem_base + (uint32_t)((s * 2 + 1) * TN);
+            // one K=128 product: 2 swizzle blocks of 64 k, 4 MMAs (K=16 = 32 B) per block
+            auto gemm128 = [&](uint32_t d, int w, uint32_t b, uint32_t acc_first) {
+              const uint32_t a = w_base + (uint32_t)w * TC_W_BYTES;
+#pragma unroll
+              for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  uint64_t ad = sw128_desc(a + kc * (128 * 128) + ks * 32);
+                  uint64_t bd = sw128_desc(b + kc * (TN * 128) + ks * 32);
+                  umma_f16(d, ad, bd, idesc, (kc | ks) ? 1u : acc_first);
+                }
+            };
+            if (round == 0) {
+              gemm128(d0, 1, b0, 0);   // T  = x  (-lin_src)^T
+              gemm128(d0, 0, b1, 1);   //    + hp pos_nn.1^T
+              gemm128(d1, 2, b0, 0);   // V  = x  lin^T
+              gemm128(d1, 0, b1, 1);   //    + hp pos_nn.1^T
+            } else if (round == 1) {
+              gemm128(d0, 3, b0, 0);   // U = t attn_nn.0^T     (t lives in buffer 0)
+            } else {
+              gemm128(d0, 4, b1, 0);   // L = u attn_nn.1^T     (u lives in buffer 1)
+            }
+            umma_commit(smem_u32(&bars[2 + 2 * s]));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ============================== producer / epilogue warps ===============================
+    const int s = warp >> 2;                       // slot
+    const int t = tid & 127;                       // thread in slot == output channel == TMEM lane
+    const int wq = warp & 3;                       // TMEM lane quarter of this warp
+    unsigned char* buf0 = act_s + (s * 2 + 0) * ACT_TILE;
+    unsigned char* buf1 = act_s + (s * 2 + 1) * ACT_TILE;
+    int* ci = ci_s + s * TN;
+    const uint32_t ready = smem_u32(&bars[1 + 2 * s]), done = smem_u32(&bars[2 + 2 * s]);
+    const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((s * 2 + 0) * TN);
+    const uint32_t t1 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((s * 2 + 1) * TN);
+    const float b_p1 = p.b_p1[t], b_a0 = p.b_a0[t], b_a1 = p.b_a1[t];
+    uint32_t done_parity = 0;
+    constexpr float LOG2E = 1.4426950408889634f;
+
+    // store a [channel t][edge e] fp32 column pair as 16-bit into the B-operand tile (row e, col t)
+    auto store_pair = [&](unsigned char* buf, int e, float v0, float v1) {
+      // even lane keeps row e (cols t, t+1), odd lane keeps row e+1 (cols t-1, t)
+      const bool odd = lane & 1;
+      float send = odd ? v0 : v1;
+      float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+      uint32_t packed = odd ? pack2<BF16>(recv, v1) : pack2<BF16>(v0, recv);
+      int row = odd ? e + 1 : e, col = odd ? t - 1 : t;
+      *reinterpret_cast<uint32_t*>(buf + sw128_off(TN, row, col)) = packed;
+    };
+
+    for (int it = 0;; ++it) {
+      const int g = (it * SLOTS + s) * (int)gridDim.x + (int)blockIdx.x;
+      if (g >= total_tiles) break;
+      const int side = g & 1;
+      const int64_t e0 = (int64_t)(g >> 1) * TN;
+      const int n_valid = (int)min((int64_t)TN, p.n_e01 - e0);
+      const float* __restrict__ feat_src = side == 0 ? p.x_cur : p.x_tar;
+      const float* __restrict__ pos_src = side == 0 ? p.pos_cur : p.pos_tar;
+
+      // ---- producer: x -> buf0, hp -> buf1 (thread = edge e, channel block kp) -----------------
+      {
+        const int e = t % TN, kp = t / TN;           // channels [kp*TN, kp*TN + TN)
+        float f0 = 0.f, f1 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+        int cid = -1;
+        if (e < n_valid) {
+          const int64_t j = p.ej[e0 + e];
+          cid = (int)p.ei[e0 + e];
+          const float2 f = reinterpret_cast<const float2*>(feat_src)[j];
+          const float2 ps = reinterpret_cast<const float2*>(pos_src)[j];
+          const float2 pt = reinterpret_cast<const float2*>(p.pos_tar)[j];
+          const float2 pc = reinterpret_cast<const float2*>(p.pos_clu)[cid];
+          f0 = f.x; f1 = f.y;
+          d0 = pc.x - ps.x; d1 = pc.y - ps.y; d2 = pc.x - pt.x; d3 = pc.y - pt.y;
+        }
+        if (kp == 0) ci[e] = cid;
+        const bool live = e < n_valid;
+#pragma unroll
+        for (int gq = 0; gq < TN / 8; ++gq) {
+          const int k0 = kp * TN + gq * 8;
+          uint32_t xo[4], ho[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float xv[2], hv[2];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int k = k0 + q * 2 + h2;
+              float x = fmaf(sw.w_in[k * 2 + 1], f1, fmaf(sw.w_in[k * 2], f0, sw.b_in[k]));
+              float hp = sw.b_p0[k];
+              hp = fmaf(sw.w_p0[k * 4], d0, hp);
+              hp = fmaf(sw.w_p0[k * 4 + 1], d1, hp);
+              hp = fmaf(sw.w_p0[k * 4 + 2], d2, hp);
+              hp = fmaf(sw.w_p0[k * 4 + 3], d3, hp);
+              xv[h2] = live ? fmaxf(x, 0.f) : 0.f;
+              hv[h2] = live ? fmaxf(hp, 0.f) : 0.f;
+            }
+            xo[q] = pack2<BF16>(xv[0], xv[1]);
+            ho[q] = pack2<BF16>(hv[0], hv[1]);
+          }
+          const uint32_t off = sw128_off(TN, e, k0);
+          *reinterpret_cast<uint4*>(buf0 + off) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
+          *reinterpret_cast<uint4*>(buf1 + off) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+        }
+      }
+      tc_fence_before();          // orders the previous tile's TMEM loads before the next MMAs
+      fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor core
+      mbar_arrive(ready);
+      named_bar(1 + s, 128);      // ci[] visible to the whole slot
+
+      // ---- epilogue A: t = T + a_dst[cluster] + b_p1 -> buf0 ------------------------------------
+      mbar_wait(done, done_parity); done_parity ^= 1;
+      tc_fence_after();
+      {
+        int prev = -2;
+        float ad = 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+          float acc[32];
+          tmem_ld32(t0 + c0, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) {
+            float v[2];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int e = c0 + q + h2;
+              const int c = ci[e];
+              if (c != prev) { prev = c; ad = (c >= 0) ? p.a_dst[(size_t)c * H + t] : 0.f; }
+              v[h2] = (c >= 0) ? acc[q + h2] + ad + b_p1 : 0.f;
+            }
+            store_pair(buf0, c0 + q, v[0], v[1]);
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(ready);
+
+      // ---- epilogue B: u = relu(U + b_a0) -> buf1 ------------------------------------------------
+      mbar_wait(done, done_parity); done_parity ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        float acc[32];
+        tmem_ld32(t0 + c0, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; q += 2)
+          store_pair(buf1, c0 + q, fmaxf(acc[q] + b_a0, 0.f), fmaxf(acc[q + 1] + b_a0, 0.f));
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(ready);
+
+      // ---- final: per-channel online segment softmax of L weighting V ---------------------------
+      mbar_wait(done, done_parity); done_parity ^= 1;
+      tc_fence_after();
+      {
+        float* out = p.clu_feat + (size_t)side * p.n_clusters * H;
+        float* part = p.partial + (size_t)side * p.n_slots * 3 * H;
+        const int64_t piece = g >> 1;
+        float m = -INFINITY, ssum = 0.f, a = 0.f;
+        int cur = ci[0], seg_beg = 0;
+        auto flush = [&](int seg, int e_beg, int e_end) {
+          const bool complete = (p.clu_rowptr[seg] == (int)(e0 + e_beg)) && (p.clu_rowptr[seg + 1] == (int)(e0 + e_end));
+          if (complete) {
+            out[(size_t)seg * H + t] = fmaxf(a / (ssum + 1e-16f), 0.f);
+          } else {
+            float* slot = part + ((size_t)seg + piece) * 3 * H;
+            slot[t] = m; slot[H + t] = ssum; slot[2 * H + t] = a;
+          }
+        };
+#pragma unroll
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+          float lg[32], vv[32];
+          tmem_ld32(t0 + c0, lg);
+          tmem_ld32(t1 + c0, vv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const int e = c0 + q;
+            if (e < n_valid) {
+              const int c = ci[e];
+              if (c != cur) {
+                flush(cur, seg_beg, e);
+                m = -INFINITY; ssum = 0.f; a = 0.f; cur = c; seg_beg = e;
+              }
+              const float l = lg[q] + b_a1;
+              const float v = vv[q] + b_p1;
+              const float mn = fmaxf(m, l);
+              const float sc = exp2f((m - mn) * LOG2E);
+              const float pr = exp2f((l - mn) * LOG2E);
+              ssum = fmaf(ssum, sc, pr);
+              a = fmaf(a, sc, pr * v);
+              m = mn;
+            }
+          }
+        }
+        if (n_valid > 0) flush(cur, seg_beg, n_valid);
+      }
+      named_bar(1 + s, 128);      // everyone is done with ci[] before the next tile overwrites it
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (is_mma_warp) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// =================================================================================================
+constexpr size_t TC_SMEM_BYTES = TC_NW * TC_W_BYTES + TC_ACT_BYTES + 256 + 128 * sizeof(int) + 1024;
+
+template <int TN, bool BF16>
+static int launch_tc(const EncEdgeArgs& a, const unsigned char* w_img, const cns_handle* h, cudaStream_t s) {
+  static bool configured = false;
+  auto kern = enc_edge_tc_kernel<TN, BF16>;
+  if (!configured) {
+    CNS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    configured = true;
+  }
+  TcArgs ta;
+  ta.e = a;
+  ta.w_img = w_img;
+  ta.n_tiles = ceil_div(a.n_e01, TN);
+  const int total = ta.n_tiles * 2;
+  const int slots = 128 / TN;
+  int grid = h->sm_count;
+  if (grid * slots > total) grid = (total + slots - 1) / slots;
+  kern<<<grid, 128 * slots + 32, TC_SMEM_BYTES, s>>>(ta, *reinterpret_cast<const TcSmallW*>(h->tc_small_host));
+  CNS_LAUNCH_CHECK();
+  return CNS_OK;
+}
+
+int tc_pack_weights(cns_handle* h, cudaStream_t s) {
+  if (!h->tc_w_img) CNS_CUDA_CHECK(cudaMalloc(&h->tc_w_img, 2 * TC_NW * TC_W_BYTES));
+  const int total = TC_NW * 128 * 128;
+  tc_pack_weights_kernel<true><<<ceil_div(total, 256), 256, 0, s>>>(h->pk.enc_chain, h->tc_w_img);
+  CNS_LAUNCH_CHECK();
+  tc_pack_weights_kernel<false><<<ceil_div(total, 256), 256, 0, s>>>(h->pk.enc_chain, h->tc_w_img + TC_NW * TC_W_BYTES);
+  CNS_LAUNCH_CHECK();
+  // small first-layer weights travel in the kernel parameter space: keep a host copy
+  static_assert(sizeof(TcSmallW) == sizeof(h->tc_small_host), "TcSmallW size");
+  TcSmallW* sw = reinterpret_cast<TcSmallW*>(h->tc_small_host);
+  CNS_CUDA_CHECK(cudaMemcpyAsync(sw->w_in, h->P(P_IN_W), sizeof(sw->w_in), cudaMemcpyDeviceToHost, s));
+  CNS_CUDA_CHECK(cudaMemcpyAsync(sw->b_in, h->P(P_IN_B), sizeof(sw->b_in), cudaMemcpyDeviceToHost, s));
+  CNS_CUDA_CHECK(cudaMemcpyAsync(sw->w_p0, h->P(P_POS0_W), sizeof(sw->w_p0), cudaMemcpyDeviceToHost, s));
+  CNS_CUDA_CHECK(cudaMemcpyAsync(sw->b_p0, h->P(P_POS0_B), sizeof(sw->b_p0), cudaMemcpyDeviceToHost, s));
+  CNS_CUDA_CHECK(cudaStreamSynchronize(s));
+  return CNS_OK;
+}
+
+int enc_edge_tc(const EncEdgeArgs& a, int precision, const cns_handle* h, cudaStream_t s) {
+  if (a.n_e01 == 0) return CNS_OK;
+  CNS_REQUIRE(h->tc_w_img != nullptr, "tensor-core weight image missing");
+  const int tn = h->tc_tile_n;
+  if (precision == CNS_PREC_BF16) {
+    if (tn == 32) return launch_tc<32, true>(a, h->tc_w_img, h, s);
+    return launch_tc<64, true>(a, h->tc_w_img, h, s);
+  }
+  if (precision == CNS_PREC_F16) {
+    const unsigned char* img = h->tc_w_img + TC_NW * TC_W_BYTES;
+    if (tn == 32) return launch_tc<32, false>(a, img, h, s);
+    return launch_tc<64, false>(a, img, h, s);
+  }
+  set_error("enc_edge_tc: unsupported precision %d", precision);
   return CNS_ERR_UNSUPPORTED;
 }
+
 }  // namespace cns

@@ -26,8 +26,7 @@ struct FwdBuffers {
 
 static void carve(Arena& ar, const cns_batch* b, FwdBuffers& f) {
   const int64_t C = b->n_clusters, B = b->n_graphs;
-  const int64_t tiles = (b->n_e01 + ENC_TILE_E - 1) / ENC_TILE_E;
-  f.n_slots = C + 2 * tiles + 2;
+  f.n_slots = C + (b->n_e01 + 31) / 32 + 2;   // one partial slot per (cluster, softmax piece) pair; pieces >= 32 edges
   f.err = ar.take<int>(64);
   f.clu_rowptr = ar.take<int>(C + 1);
   f.clu_graph = ar.take<int>(C + 1);
@@ -108,12 +107,13 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   if (h->precision == CNS_PREC_FP32) {
     RUN(enc_edge_fp32(ee, s));
   } else {
-    RUN(enc_edge_tc(ee, h->precision, nullptr, h->sm_count, s));
+    RUN(enc_edge_tc(ee, h->precision, h, s));
   }
   if (timed) { CNS_CUDA_CHECK(cudaEventRecord(h->ev[2 * h->ev_n + 1], s)); ++h->ev_n; }
 
   EncFinishArgs ef{};
-  ef.n_clusters = C; ef.n_slots = f.n_slots; ef.clu_rowptr = f.clu_rowptr; ef.partial = f.partial;
+  ef.n_clusters = C; ef.n_slots = f.n_slots;
+  ef.piece_e = (h->precision == CNS_PREC_FP32) ? ENC_PIECE_E : h->tc_tile_n; ef.clu_rowptr = f.clu_rowptr; ef.partial = f.partial;
   ef.clu_feat = f.clu_feat; ef.out_t = pk.out_t; ef.b_out = h->P(P_OUT_B); ef.cluster_mask = b->cluster_mask;
   ef.x_clu = f.x_clu;
   RUN(enc_finish(ef, s));

@@ -2,6 +2,7 @@
 // Replaces GraphVS.__init__ / load_state_dict of the reference (cns/models/graph_vs.py:273-279).
 #include <stdarg.h>
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace cns {
 
@@ -149,6 +150,7 @@ int repack(cns_handle* h, cudaStream_t s) {
   if ((rc = launch_edgeconv_pack(h->P(P_G_MSG_W), h->P(P_G_MSG_B), 256, 256, pk.g_wt, pk.g_wp, pk.g_b, s))) return rc;
   if ((rc = launch_edgeconv_pack(h->P(P_K_MSG_W), h->P(P_K_MSG_B), 256, 128, pk.k_wt, pk.k_wp, pk.k_b, s))) return rc;
   if ((rc = launch_edgeconv_pack(h->P(P_C1_MSG_W), h->P(P_C1_MSG_B), 128, 128, pk.c1_wt, pk.c1_wp, pk.c1_b, s))) return rc;
+  if ((rc = tc_pack_weights(h, s)) != CNS_OK) return rc;
   h->weights_loaded = true;
   return CNS_OK;
 }
@@ -189,6 +191,7 @@ int cns_create(cns_handle** out, int device) {
   memset(h, 0, sizeof(*h));
   h->device = device;
   h->precision = CNS_PREC_FP32;
+  h->tc_tile_n = 32;
   h->sm_count = prop.multiProcessorCount;
   size_t off = 0;
   for (int k = 0; k < P_COUNT; ++k) {
@@ -221,6 +224,7 @@ int cns_destroy(cns_handle* h) {
   if (h->ev[0]) for (int i = 0; i < 2 * 256; ++i) cudaEventDestroy(h->ev[i]);
   cudaFree(h->raw);
   cudaFree(h->packed_base);
+  if (h->tc_w_img) cudaFree(h->tc_w_img);
   if (h->stage_host) cudaFreeHost(h->stage_host);
   if (h->stage_dev) cudaFree(h->stage_dev);
   delete h;
@@ -280,6 +284,15 @@ int cns_profile_end(cns_handle* h, float* enc_edge_ms_total, int* n_timed, long 
   if (enc_edge_ms_total) *enc_edge_ms_total = total;
   if (n_timed) *n_timed = h->ev_n;
   if (launches) *launches = g_launch_count;
+  return CNS_OK;
+}
+
+// Tuning knob of the tensor-core encoder kernel: edges per tile (32 -> 4 tiles in flight per SM,
+// 64 -> 2).  Also the granularity of the softmax partials.
+int cns_set_tc_tile(cns_handle* h, int tile_n) {
+  CNS_REQUIRE(h != nullptr, "NULL handle");
+  CNS_REQUIRE(tile_n == 32 || tile_n == 64, "tile_n must be 32 or 64");
+  h->tc_tile_n = tile_n;
   return CNS_OK;
 }
 

@@ -40,10 +40,12 @@ struct EncEdgeArgs {
   float* partial;    // (2, n_slots, 3, 128)
 };
 int enc_edge_fp32(const EncEdgeArgs& a, cudaStream_t s);
-int enc_edge_tc(const EncEdgeArgs& a, int precision, const void* tc_weights, int sm_count, cudaStream_t s);
+int enc_edge_tc(const EncEdgeArgs& a, int precision, const cns_handle* h, cudaStream_t s);
+int tc_pack_weights(cns_handle* h, cudaStream_t s);
 
 struct EncFinishArgs {
   int64_t n_clusters, n_slots;
+  int piece_e;       // edges per softmax piece used by the edge kernel that ran
   const int* clu_rowptr; const float* partial; float* clu_feat;
   const float* out_t; const float* b_out; const uint8_t* cluster_mask;
   float* x_clu;      // (C,128)

@@ -47,7 +47,7 @@ typedef enum cns_status {
 /* arithmetic mode of the batched MLP (GEMM) kernels */
 typedef enum cns_precision {
   CNS_PREC_FP32 = 0,     /* fp32 FFMA everywhere (rel 1e-4 vs the fp64 oracle)         */
-  CNS_PREC_TF32X3 = 1,   /* tcgen05 kind::tf32, 3-pass split (fp32-class accuracy)      */
+  CNS_PREC_F16 = 1,      /* tcgen05 kind::f16 fp16 inputs, fp32 accumulate (rel ~2e-3)   */
   CNS_PREC_BF16 = 2      /* tcgen05 kind::f16 bf16 inputs, fp32 accumulate (rel 2e-2)   */
 } cns_precision;
 
@@ -72,6 +72,7 @@ int cns_load_weights_device(cns_handle* h, const float* const* params_dev, const
 const char* cns_param_name(int k);      /* e.g. "encoder.in_enc.fcs.0.weight" */
 int64_t cns_param_numel(int k);
 int cns_set_precision(cns_handle* h, int precision /* cns_precision */);
+int cns_set_tc_tile(cns_handle* h, int tile_n /* 32 or 64: edges per tensor-core tile */);
 
 /* Measurement hooks: between begin and end every cns_graphvs_forward brackets its dominant
  * kernel (the encoder edge kernel) with CUDA events on the launching stream (first 256
