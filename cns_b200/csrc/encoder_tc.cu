@@ -70,6 +70,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -152,7 +166,7 @@ struct TcArgs {
 
 // =================================================================================================
 template <int TN, bool BF16>
-__global__ void __launch_bounds__(128 * (128 / TN) + 32, 1)
+__global__ void __launch_bounds__(128 * (128 / TN), 1)
 enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ TcSmallW sw) {
   constexpr int SLOTS = 128 / TN;
   constexpr int ACT_TILE = TN * 256;                 // one [TN x 128] 16-bit operand tile
@@ -164,22 +178,17 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
   unsigned char* w_s = smem;                                     // 5 x 32 KB
   unsigned char* act_s = smem + TC_NW * TC_W_BYTES;              // SLOTS x 2 x ACT_TILE = 64 KB
   unsigned char* tail = act_s + TC_ACT_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);            // [0]=weights, [1+2s]=ready[s], [2+2s]=done[s]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);            // [0] = weights landed, [1+s] = MMAs of slot s done
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tail + 128);
   int* ci_s = reinterpret_cast<int*>(tail + 256);                // [SLOTS][TN] cluster id per edge (-1: padding)
 
   const EncEdgeArgs& p = args.e;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int total_tiles = args.n_tiles * 2;                      // x 2 sides
-  const bool is_mma_warp = (warp == EPI_THREADS / 32);
-
-  if (is_mma_warp) {
+  if (warp == 0) {
     if (lane == 0) {
       mbar_init(smem_u32(&bars[0]), 1);
-      for (int s = 0; s < SLOTS; ++s) {
-        mbar_init(smem_u32(&bars[1 + 2 * s]), 128);
-        mbar_init(smem_u32(&bars[2 + 2 * s]), 1);
-      }
+      for (int s = 0; s < SLOTS; ++s) mbar_init(smem_u32(&bars[1 + s]), 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -195,62 +204,13 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  if (is_mma_warp) {
-    // ============================== MMA issuer ==============================================
-    // instruction descriptor: D=f32 (bit 4), A/B format at bits 7/10 (0 f16, 1 bf16), K-major both,
-    // N>>3 at bit 17, M>>4 at bit 24
-    const uint32_t fmt = BF16 ? 1u : 0u;
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TN >> 3) << 17) | ((128u >> 4) << 24);
-    mbar_wait(smem_u32(&bars[0]), 0);                            // weights landed
-    uint32_t ready_parity[SLOTS];
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) ready_parity[s] = 0;
-    const uint32_t w_base = smem_u32(w_s);
-    for (int it = 0;; ++it) {
-      if ((it * SLOTS) * (int)gridDim.x + (int)blockIdx.x >= total_tiles) break;
-#pragma unroll 1
-      for (int round = 0; round < 3; ++round) {
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-          const int g = (it * SLOTS + s) * (int)gridDim.x + (int)blockIdx.x;
-          if (g >= total_tiles) continue;
-          mbar_wait(smem_u32(&bars[1 + 2 * s]), ready_parity[s]);
-          ready_parity[s] ^= 1;
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t b0 = smem_u32(act_s + (s * 2 + 0) * ACT_TILE);
-            const uint32_t b1 = smem_u32(act_s + (s * 2 + 1) * ACT_TILE);
-            const uint32_t d0 = tmem_base + (uint32_t)((s * 2 + 0) * TN);
-            const uint32_t d1 = tmem_base + (uint32_t)((s * 2 + 1) * TN);
-            // one K=128 product: 2 swizzle blocks of 64 k, 4 MMAs (K=16 = 32 B) per block
-            auto gemm128 = [&](uint32_t d, int w, uint32_t b, uint32_t acc_first) {
-              const uint32_t a = w_base + (uint32_t)w * TC_W_BYTES;
-#pragma unroll
-              for (int kc = 0; kc < 2; ++kc)
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  uint64_t ad = sw128_desc(a + kc * (128 * 128) + ks * 32);
-                  uint64_t bd = sw128_desc(b + kc * (TN * 128) + ks * 32);
-                  umma_f16(d, ad, bd, idesc, (kc | ks) ? 1u : acc_first);
-                }
-            };
-            if (round == 0) {
-              gemm128(d0, 1, b0, 0);   // T  = x  (-lin_src)^T
-              gemm128(d0, 0, b1, 1);   //    + hp pos_nn.1^T
-              gemm128(d1, 2, b0, 0);   // V  = x  lin^T
-              gemm128(d1, 0, b1, 1);   //    + hp pos_nn.1^T
-            } else if (round == 1) {
-              gemm128(d0, 3, b0, 0);   // U = t attn_nn.0^T     (t lives in buffer 0)
-            } else {
-              gemm128(d0, 4, b1, 0);   // L = u attn_nn.1^T     (u lives in buffer 1)
-            }
-            umma_commit(smem_u32(&bars[2 + 2 * s]));
-          }
-          __syncwarp();
-        }
-      }
-    }
-  } else {
+  // instruction descriptor: D=f32 (bit 4), A/B format at bits 7/10 (0 f16, 1 bf16), K-major both,
+  // N>>3 at bit 17, M>>4 at bit 24
+  const uint32_t fmt = BF16 ? 1u : 0u;
+  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TN >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t w_base = smem_u32(w_s);
+
+  {
     // ============================== producer / epilogue warps ===============================
     const int s = warp >> 2;                       // slot
     const int t = tid & 127;                       // thread in slot == output channel == TMEM lane
@@ -258,12 +218,51 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     unsigned char* buf0 = act_s + (s * 2 + 0) * ACT_TILE;
     unsigned char* buf1 = act_s + (s * 2 + 1) * ACT_TILE;
     int* ci = ci_s + s * TN;
-    const uint32_t ready = smem_u32(&bars[1 + 2 * s]), done = smem_u32(&bars[2 + 2 * s]);
+    const uint32_t done = smem_u32(&bars[1 + s]);
     const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((s * 2 + 0) * TN);
     const uint32_t t1 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((s * 2 + 1) * TN);
     const float b_p1 = p.b_p1[t], b_a0 = p.b_a0[t], b_a1 = p.b_a1[t];
     uint32_t done_parity = 0;
     constexpr float LOG2E = 1.4426950408889634f;
+
+    // The slot's thread 0 issues the slot's tensor-core work itself (tcgen05.mma is a single-thread
+    // instruction): after the slot barrier every operand byte written by the 128 threads is visible
+    // to the async proxy, so no dedicated MMA warp / "ready" mbarrier is needed.
+    // One K=128 product = 2 swizzle blocks of 64 k x 4 MMAs (K = 16 = 32 B).
+    auto gemm128 = [&](uint32_t d, int w, uint32_t b, uint32_t acc_first) {
+      const uint32_t a = w_base + (uint32_t)w * TC_W_BYTES;
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint64_t ad = sw128_desc(a + kc * (128 * 128) + ks * 32);
+          uint64_t bd = sw128_desc(b + kc * (TN * 128) + ks * 32);
+          umma_f16(d, ad, bd, idesc, (kc | ks) ? 1u : acc_first);
+        }
+    };
+    auto publish_and_issue = [&](int round) {
+      tc_fence_before();          // this thread's earlier TMEM loads are ordered before the next MMAs
+      fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor core
+      named_bar(1 + s, 128);
+      if (t == 0) {
+        tc_fence_after();
+        const uint32_t b0 = smem_u32(buf0), b1 = smem_u32(buf1);
+        const uint32_t d0 = tmem_base + (uint32_t)((s * 2 + 0) * TN);
+        const uint32_t d1 = tmem_base + (uint32_t)((s * 2 + 1) * TN);
+        if (round == 0) {
+          gemm128(d0, 1, b0, 0);   // T  = x  (-lin_src)^T
+          gemm128(d0, 0, b1, 1);   //    + hp pos_nn.1^T
+          gemm128(d1, 2, b0, 0);   // V  = x  lin^T
+          gemm128(d1, 0, b1, 1);   //    + hp pos_nn.1^T
+        } else if (round == 1) {
+          gemm128(d0, 3, b0, 0);   // U = t attn_nn.0^T     (t lives in buffer 0)
+        } else {
+          gemm128(d0, 4, b1, 0);   // L = u attn_nn.1^T     (u lives in buffer 1)
+        }
+        umma_commit(done);
+      }
+    };
+    if (t == 0) mbar_wait(smem_u32(&bars[0]), 0);      // weights landed (only the issuing thread cares)
 
     // store a [channel t][edge e] fp32 column pair as 16-bit into the B-operand tile (row e, col t)
     auto store_pair = [&](unsigned char* buf, int e, float v0, float v1) {
@@ -276,32 +275,50 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
       *reinterpret_cast<uint32_t*>(buf + sw128_off(TN, row, col)) = packed;
     };
 
+    // Per-edge inputs of the producer (thread = edge pe, channel block kp) are fetched one tile ahead:
+    // the index loads are issued before the producer math of the current tile and the dependent
+    // coordinate gathers right after it, so both latencies hide behind the epilogues.
+    const int pe = t % TN, kp = t / TN;            // channels [kp*TN, kp*TN + TN)
+    auto tile_of = [&](int it) { return (it * SLOTS + s) * (int)gridDim.x + (int)blockIdx.x; };
+    int n_j = 0, n_cid = -1;                       // next tile: source keypoint / cluster of edge pe
+    float2 n_f = make_float2(0.f, 0.f), n_ps = n_f, n_pt = n_f, n_pc = n_f;
+    auto fetch_index = [&](int g) {
+      n_cid = -1; n_j = 0;
+      if (g < total_tiles) {
+        const int64_t e = (int64_t)(g >> 1) * TN + pe;
+        if (e < p.n_e01) { n_j = (int)p.ej[e]; n_cid = (int)p.ei[e]; }
+      }
+    };
+    auto fetch_coords = [&](int g) {
+      if (n_cid >= 0) {
+        const float* __restrict__ fsrc = (g & 1) ? p.x_tar : p.x_cur;
+        const float* __restrict__ psrc = (g & 1) ? p.pos_tar : p.pos_cur;
+        n_f = reinterpret_cast<const float2*>(fsrc)[n_j];
+        n_ps = reinterpret_cast<const float2*>(psrc)[n_j];
+        n_pt = reinterpret_cast<const float2*>(p.pos_tar)[n_j];
+        n_pc = reinterpret_cast<const float2*>(p.pos_clu)[n_cid];
+      }
+    };
+    fetch_index(tile_of(0));
+    fetch_coords(tile_of(0));
+
     for (int it = 0;; ++it) {
-      const int g = (it * SLOTS + s) * (int)gridDim.x + (int)blockIdx.x;
+      const int g = tile_of(it);
       if (g >= total_tiles) break;
       const int side = g & 1;
       const int64_t e0 = (int64_t)(g >> 1) * TN;
       const int n_valid = (int)min((int64_t)TN, p.n_e01 - e0);
-      const float* __restrict__ feat_src = side == 0 ? p.x_cur : p.x_tar;
-      const float* __restrict__ pos_src = side == 0 ? p.pos_cur : p.pos_tar;
 
-      // ---- producer: x -> buf0, hp -> buf1 (thread = edge e, channel block kp) -----------------
+      // ---- producer: x -> buf0, hp -> buf1 ---------------------------------------------------------
       {
-        const int e = t % TN, kp = t / TN;           // channels [kp*TN, kp*TN + TN)
-        float f0 = 0.f, f1 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-        int cid = -1;
-        if (e < n_valid) {
-          const int64_t j = p.ej[e0 + e];
-          cid = (int)p.ei[e0 + e];
-          const float2 f = reinterpret_cast<const float2*>(feat_src)[j];
-          const float2 ps = reinterpret_cast<const float2*>(pos_src)[j];
-          const float2 pt = reinterpret_cast<const float2*>(p.pos_tar)[j];
-          const float2 pc = reinterpret_cast<const float2*>(p.pos_clu)[cid];
-          f0 = f.x; f1 = f.y;
-          d0 = pc.x - ps.x; d1 = pc.y - ps.y; d2 = pc.x - pt.x; d3 = pc.y - pt.y;
-        }
+        const int e = pe;
+        const int cid = n_cid;
+        const bool live = cid >= 0;
+        const float f0 = live ? n_f.x : 0.f, f1 = live ? n_f.y : 0.f;
+        const float d0 = live ? n_pc.x - n_ps.x : 0.f, d1 = live ? n_pc.y - n_ps.y : 0.f;   // pos_i - pos_j
+        const float d2 = live ? n_pc.x - n_pt.x : 0.f, d3 = live ? n_pc.y - n_pt.y : 0.f;
         if (kp == 0) ci[e] = cid;
-        const bool live = e < n_valid;
+        fetch_index(tile_of(it + 1));              // in flight during the producer math below
 #pragma unroll
         for (int gq = 0; gq < TN / 8; ++gq) {
           const int k0 = kp * TN + gq * 8;
@@ -329,10 +346,8 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
           *reinterpret_cast<uint4*>(buf1 + off) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
         }
       }
-      tc_fence_before();          // orders the previous tile's TMEM loads before the next MMAs
-      fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor core
-      mbar_arrive(ready);
-      named_bar(1 + s, 128);      // ci[] visible to the whole slot
+      publish_and_issue(0);            // also makes ci[] visible to the whole slot
+      fetch_coords(tile_of(it + 1));   // dependent gathers of the next tile fly during the epilogues
 
       // ---- epilogue A: t = T + a_dst[cluster] + b_p1 -> buf0 ------------------------------------
       mbar_wait(done, done_parity); done_parity ^= 1;
@@ -359,9 +374,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
           }
         }
       }
-      tc_fence_before();
-      fence_proxy_async();
-      mbar_arrive(ready);
+      publish_and_issue(1);
 
       // ---- epilogue B: u = relu(U + b_a0) -> buf1 ------------------------------------------------
       mbar_wait(done, done_parity); done_parity ^= 1;
@@ -375,9 +388,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         for (int q = 0; q < 32; q += 2)
           store_pair(buf1, c0 + q, fmaxf(acc[q] + b_a0, 0.f), fmaxf(acc[q + 1] + b_a0, 0.f));
       }
-      tc_fence_before();
-      fence_proxy_async();
-      mbar_arrive(ready);
+      publish_and_issue(2);
 
       // ---- final: per-channel online segment softmax of L weighting V ---------------------------
       mbar_wait(done, done_parity); done_parity ^= 1;
@@ -415,8 +426,8 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
               const float l = lg[q] + b_a1;
               const float v = vv[q] + b_p1;
               const float mn = fmaxf(m, l);
-              const float sc = exp2f((m - mn) * LOG2E);
-              const float pr = exp2f((l - mn) * LOG2E);
+              const float sc = ex2_approx((m - mn) * LOG2E);
+              const float pr = ex2_approx((l - mn) * LOG2E);
               ssum = fmaf(ssum, sc, pr);
               a = fmaf(a, sc, pr * v);
               m = mn;
@@ -432,7 +443,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (is_mma_warp) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // =================================================================================================
@@ -454,7 +465,7 @@ static int launch_tc(const EncEdgeArgs& a, const unsigned char* w_img, const cns
   const int slots = 128 / TN;
   int grid = h->sm_count;
   if (grid * slots > total) grid = (total + slots - 1) / slots;
-  kern<<<grid, 128 * slots + 32, TC_SMEM_BYTES, s>>>(ta, *reinterpret_cast<const TcSmallW*>(h->tc_small_host));
+  kern<<<grid, 128 * slots, TC_SMEM_BYTES, s>>>(ta, *reinterpret_cast<const TcSmallW*>(h->tc_small_host));
   CNS_LAUNCH_CHECK();
   return CNS_OK;
 }
