@@ -40,10 +40,10 @@ FLOP_PER_EDGE_SIDE = 2 * (5 * 128 * 128 + 2 * 128 + 4 * 128)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("CNS_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("CNS_PRECISION", "bf16"), choices=["fp32", "f16", "bf16"])
     ap.add_argument("--graphs", type=int, default=N_GRAPHS)
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--cpu-sample", type=int, default=64, help="graphs per CPU-baseline step")
@@ -61,34 +61,55 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, ~2 ms period;
+    falls back to polling nvidia-smi when pynvml is unavailable)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.stop_flag = index, False
+        self.sm, self.sm_max, self.reasons, self.source = [], None, set(), "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv, self.source = None, "nvidia-smi"
+
+    def _sample(self):
+        if self.nv is not None:
+            self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            bits = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            self.reasons |= {n for n, b in self.BITS.items() if bits & b}
+            time.sleep(0.002)
+            return
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [x.strip() for x in out.strip().split(",")]
+        if len(parts) >= 6:
+            self.sm.append(float(parts[0]))
+            self.sm_max = float(parts[1])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            self.reasons |= {n for i, n in enumerate(names) if parts[2 + i].lower().startswith("active")}
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.rows.append(parts)
+                self._sample()
             except Exception:
-                pass
-            time.sleep(0.05)
+                time.sleep(0.01)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]),
-                "reasons": reasons, "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"], "samples": 0}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": self.source}
 
 
 def build_batches(n_graphs, n_points, seed, n_batches):

@@ -19,6 +19,7 @@
 // SWIZZLE_128B layout ([k/64][row][128 B], 16-byte chunk index XOR (row & 7)).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <type_traits>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -311,64 +312,84 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
 
       // ---- producer: x -> buf0, hp -> buf1 ---------------------------------------------------------
       {
-        const int e = pe;
         const int cid = n_cid;
         const bool live = cid >= 0;
         const float f0 = live ? n_f.x : 0.f, f1 = live ? n_f.y : 0.f;
         const float d0 = live ? n_pc.x - n_ps.x : 0.f, d1 = live ? n_pc.y - n_ps.y : 0.f;   // pos_i - pos_j
         const float d2 = live ? n_pc.x - n_pt.x : 0.f, d3 = live ? n_pc.y - n_pt.y : 0.f;
-        if (kp == 0) ci[e] = cid;
+        if (kp == 0) ci[pe] = cid;
         fetch_index(tile_of(it + 1));              // in flight during the producer math below
+        // kp is warp-uniform; dispatching on it makes every channel index a compile-time constant so
+        // the first-layer weights are read as immediate constant-bank operands of the FFMAs.
+        auto produce = [&](auto kp_c) {
+          constexpr int KP = decltype(kp_c)::value;
 #pragma unroll
-        for (int gq = 0; gq < TN / 8; ++gq) {
-          const int k0 = kp * TN + gq * 8;
-          uint32_t xo[4], ho[4];
+          for (int gq = 0; gq < TN / 8; ++gq) {
+            constexpr int kbase = KP * TN;
+            const int k0 = kbase + gq * 8;
+            uint32_t xo[4], ho[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float xv[2], hv[2];
+            for (int q = 0; q < 4; ++q) {
+              float xv[2], hv[2];
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              const int k = k0 + q * 2 + h2;
-              float x = fmaf(sw.w_in[k * 2 + 1], f1, fmaf(sw.w_in[k * 2], f0, sw.b_in[k]));
-              float hp = sw.b_p0[k];
-              hp = fmaf(sw.w_p0[k * 4], d0, hp);
-              hp = fmaf(sw.w_p0[k * 4 + 1], d1, hp);
-              hp = fmaf(sw.w_p0[k * 4 + 2], d2, hp);
-              hp = fmaf(sw.w_p0[k * 4 + 3], d3, hp);
-              xv[h2] = live ? fmaxf(x, 0.f) : 0.f;
-              hv[h2] = live ? fmaxf(hp, 0.f) : 0.f;
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const int k = k0 + q * 2 + h2;
+                float x = fmaf(sw.w_in[k * 2 + 1], f1, fmaf(sw.w_in[k * 2], f0, sw.b_in[k]));
+                float hp = sw.b_p0[k];
+                hp = fmaf(sw.w_p0[k * 4], d0, hp);
+                hp = fmaf(sw.w_p0[k * 4 + 1], d1, hp);
+                hp = fmaf(sw.w_p0[k * 4 + 2], d2, hp);
+                hp = fmaf(sw.w_p0[k * 4 + 3], d3, hp);
+                xv[h2] = fmaxf(x, 0.f);
+                hv[h2] = fmaxf(hp, 0.f);
+              }
+              xo[q] = pack2<BF16>(xv[0], xv[1]);
+              ho[q] = pack2<BF16>(hv[0], hv[1]);
             }
-            xo[q] = pack2<BF16>(xv[0], xv[1]);
-            ho[q] = pack2<BF16>(hv[0], hv[1]);
+            const uint32_t off = sw128_off(TN, pe, k0);
+            *reinterpret_cast<uint4*>(buf0 + off) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
+            *reinterpret_cast<uint4*>(buf1 + off) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
           }
-          const uint32_t off = sw128_off(TN, e, k0);
-          *reinterpret_cast<uint4*>(buf0 + off) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
-          *reinterpret_cast<uint4*>(buf1 + off) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
-        }
+        };
+        if (kp == 0) produce(std::integral_constant<int, 0>{});
+        else if (kp == 1) produce(std::integral_constant<int, 1>{});
+        else if (SLOTS > 2 && kp == 2) produce(std::integral_constant<int, 2 % (128 / TN)>{});
+        else produce(std::integral_constant<int, 3 % (128 / TN)>{});
       }
       publish_and_issue(0);            // also makes ci[] visible to the whole slot
       fetch_coords(tile_of(it + 1));   // dependent gathers of the next tile fly during the epilogues
 
+      // segment-start bit per edge (bit e: ci[e] != ci[e-1]); warp-uniform registers, no per-element LDS
+      uint32_t seg_mask[TN / 32];
+#pragma unroll
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        const int e = c0 + lane;
+        const int cprev = (e == 0) ? -2 : ci[e - 1];
+        seg_mask[c0 / 32] = __ballot_sync(0xffffffffu, ci[e] != cprev);
+      }
+
       // ---- epilogue A: t = T + a_dst[cluster] + b_p1 -> buf0 ------------------------------------
+      // (padding rows of the last tile keep finite garbage; their columns are never read back)
       mbar_wait(done, done_parity); done_parity ^= 1;
       tc_fence_after();
       {
-        int prev = -2;
-        float ad = 0.f;
+        float adb = 0.f;
 #pragma unroll
         for (int c0 = 0; c0 < TN; c0 += 32) {
           float acc[32];
           tmem_ld32(t0 + c0, acc);
           tmem_ld_wait();
+          const uint32_t mask = seg_mask[c0 / 32];
 #pragma unroll
           for (int q = 0; q < 32; q += 2) {
             float v[2];
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
-              const int e = c0 + q + h2;
-              const int c = ci[e];
-              if (c != prev) { prev = c; ad = (c >= 0) ? p.a_dst[(size_t)c * H + t] : 0.f; }
-              v[h2] = (c >= 0) ? acc[q + h2] + ad + b_p1 : 0.f;
+              if (mask & (1u << (q + h2))) {
+                const int c = ci[c0 + q + h2];
+                if (c >= 0) adb = p.a_dst[(size_t)c * H + t] + b_p1;
+              }
+              v[h2] = acc[q + h2] + adb;
             }
             store_pair(buf0, c0 + q, v[0], v[1]);
           }
@@ -391,21 +412,26 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
       publish_and_issue(2);
 
       // ---- final: per-channel online segment softmax of L weighting V ---------------------------
+      // softmax is shift-invariant per channel, so the attn_nn.1 bias drops out; the value bias b_p1
+      // is added once per segment (sum p (v + b) = sum p v + b sum p).  One ex2 per element: of the
+      // two rescale factors exp(m_old - m_new), exp(l - m_new) one is always 1.
       mbar_wait(done, done_parity); done_parity ^= 1;
       tc_fence_after();
       {
         float* out = p.clu_feat + (size_t)side * p.n_clusters * H;
         float* part = p.partial + (size_t)side * p.n_slots * 3 * H;
         const int64_t piece = g >> 1;
-        float m = -INFINITY, ssum = 0.f, a = 0.f;
-        int cur = ci[0], seg_beg = 0;
-        auto flush = [&](int seg, int e_beg, int e_end) {
+        float m = 0.f, ssum = 0.f, a = 0.f;
+        int seg_beg = 0;
+        auto flush = [&](int e_beg, int e_end) {
+          const int seg = ci[e_beg];
+          const float ab = fmaf(b_p1, ssum, a);
           const bool complete = (p.clu_rowptr[seg] == (int)(e0 + e_beg)) && (p.clu_rowptr[seg + 1] == (int)(e0 + e_end));
           if (complete) {
-            out[(size_t)seg * H + t] = fmaxf(a / (ssum + 1e-16f), 0.f);
+            out[(size_t)seg * H + t] = fmaxf(ab / (ssum + 1e-16f), 0.f);
           } else {
             float* slot = part + ((size_t)seg + piece) * 3 * H;
-            slot[t] = m; slot[H + t] = ssum; slot[2 * H + t] = a;
+            slot[t] = m + b_a1; slot[H + t] = ssum; slot[2 * H + t] = ab;
           }
         };
 #pragma unroll
@@ -414,27 +440,28 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
           tmem_ld32(t0 + c0, lg);
           tmem_ld32(t1 + c0, vv);
           tmem_ld_wait();
+          const uint32_t mask = seg_mask[c0 / 32];
 #pragma unroll
           for (int q = 0; q < 32; ++q) {
             const int e = c0 + q;
             if (e < n_valid) {
-              const int c = ci[e];
-              if (c != cur) {
-                flush(cur, seg_beg, e);
-                m = -INFINITY; ssum = 0.f; a = 0.f; cur = c; seg_beg = e;
+              const float l = lg[q], v = vv[q];
+              if (mask & (1u << q)) {
+                if (e > 0) flush(seg_beg, e);
+                seg_beg = e; m = l; ssum = 1.f; a = v;
+              } else {
+                const float d = l - m;
+                const float ex = ex2_approx(-fabsf(d) * LOG2E);
+                const bool up = d > 0.f;
+                const float sc = up ? ex : 1.f, pr = up ? 1.f : ex;
+                ssum = fmaf(ssum, sc, pr);
+                a = fmaf(a, sc, pr * v);
+                m = fmaxf(m, l);
               }
-              const float l = lg[q] + b_a1;
-              const float v = vv[q] + b_p1;
-              const float mn = fmaxf(m, l);
-              const float sc = ex2_approx((m - mn) * LOG2E);
-              const float pr = ex2_approx((l - mn) * LOG2E);
-              ssum = fmaf(ssum, sc, pr);
-              a = fmaf(a, sc, pr * v);
-              m = mn;
             }
           }
         }
-        if (n_valid > 0) flush(cur, seg_beg, n_valid);
+        if (n_valid > 0) flush(seg_beg, n_valid);
       }
       named_bar(1 + s, 128);      // everyone is done with ci[] before the next tile overwrites it
     }
