@@ -68,6 +68,10 @@ struct Packed {
   float* c1_wt; float* c1_wp; float* c1_b;      // [128][256], [2][256], [256]
   float* c0_fc_t; float* c1_fc_t;               // [128][128]
   float* vec0_t; float* nrm0_t;                 // [128][128]
+  // 16-bit swizzled B-operand images for gemm_tc: index 0 = bf16, 1 = f16
+  unsigned char* tc_c0[2]; unsigned char* tc_c0_fc[2]; unsigned char* tc_g[2]; unsigned char* tc_k[2];
+  unsigned char* tc_c1[2]; unsigned char* tc_c1_fc[2]; unsigned char* tc_out[2];
+  unsigned char* tc_node_base;
 };
 
 }  // namespace cns

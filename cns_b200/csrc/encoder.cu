@@ -339,7 +339,12 @@ enc_finish_kernel(EncFinishArgs p) {
     }
     cat[r][o] = f[0];
     cat[r][H + o] = f[1] - f[0];
+    if (p.cat_out && c < p.n_clusters) {
+      p.cat_out[c * 2 * H + o] = f[0];
+      p.cat_out[c * 2 * H + H + o] = f[1] - f[0];
+    }
   }
+  if (p.cat_out) return;
   __syncthreads();
   float acc[CLU_ROWS];
   float b = p.b_out[o];

@@ -116,11 +116,27 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   ef.piece_e = (h->precision == CNS_PREC_FP32) ? ENC_PIECE_E : h->tc_tile_n; ef.clu_rowptr = f.clu_rowptr; ef.partial = f.partial;
   ef.clu_feat = f.clu_feat; ef.out_t = pk.out_t; ef.b_out = h->P(P_OUT_B); ef.cluster_mask = b->cluster_mask;
   ef.x_clu = f.x_clu;
+  const bool tc = h->precision != CNS_PREC_FP32;
+  const int tci = (h->precision == CNS_PREC_BF16) ? 0 : 1;
+  ef.cat_out = tc ? f.pq : nullptr;       // (C,256) scratch; pq is free until the first [P|Q] projection
   RUN(enc_finish(ef, s));
+  if (tc) {
+    GemmTcArgs ga{};
+    ga.m = C; ga.k1 = 2 * H; ga.k2 = 0; ga.n_out = H; ga.x1 = f.pq; ga.w_img = pk.tc_out[tci];
+    ga.bias = h->P(P_OUT_B); ga.row_mask = b->cluster_mask; ga.relu = 1; ga.y = f.x_clu;
+    RUN(gemm_tc(ga, tci == 0, s));
+  }
 
   // ---- backbone ---------------------------------------------------------------------------
   auto pq_linear = [&](const float* x1, const float* x2, const float* wt, const float* wp, const float* bias,
-                       int n_out) {
+                       int n_out, unsigned char* const* img, int k_img) {
+    if (tc) {
+      GemmTcArgs ga{};
+      ga.m = C; ga.k1 = H; ga.k2 = x2 ? H : 0; ga.n_out = n_out; ga.x1 = x1; ga.x2 = x2; ga.w_img = img[tci];
+      ga.k_img = k_img;
+      ga.bias = bias; ga.pos = f.pos_clu; ga.wp = wp; ga.relu = 0; ga.y = f.pq;
+      return gemm_tc(ga, tci == 0, s);
+    }
     LinearArgs la{};
     la.m = C; la.k1 = H; la.k2 = x2 ? H : 0; la.n_out = n_out;
     la.x1 = x1; la.x2 = x2; la.wt = wt; la.bias = bias; la.pos = f.pos_clu; la.wp = wp;
@@ -128,9 +144,10 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     return linear(la, s);
   };
   auto perconv = [&](const float* x, const float* wt, const float* wp, const float* bias, int bn_w, int bn_b,
-                     int bn_ms, const float* fc_t, int fc_b, float* y) {
+                     int bn_ms, const float* fc_t, int fc_b, float* y, unsigned char* const* img,
+                     unsigned char* const* fc_img) {
     int r;
-    if ((r = pq_linear(x, nullptr, wt, wp, bias, 2 * H)) != CNS_OK) return r;
+    if ((r = pq_linear(x, nullptr, wt, wp, bias, 2 * H, img, H)) != CNS_OK) return r;
     EdgeConvArgs ec{};
     ec.n_rows = C; ec.f_out = H; ec.mode = EC_PLAIN; ec.pq = f.pq; ec.rowptr = f.cur_rowptr; ec.src = f.cur_src;
     ec.out = f.conv;
@@ -139,30 +156,36 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     gn.n_graphs = B; gn.graph_ptr = f.graph_ptr; gn.x = f.conv; gn.weight = h->P(bn_w); gn.bias = h->P(bn_b);
     gn.mean_scale = h->P(bn_ms); gn.y = f.gn; gn.stats = nullptr;
     if ((r = graphnorm_relu(gn, s)) != CNS_OK) return r;
+    if (tc) {
+      GemmTcArgs ga{};
+      ga.m = C; ga.k1 = H; ga.k2 = 0; ga.n_out = H; ga.x1 = f.gn; ga.w_img = fc_img[tci]; ga.bias = h->P(fc_b);
+      ga.residual = x; ga.relu = 1; ga.y = y;
+      return gemm_tc(ga, tci == 0, s);
+    }
     LinearArgs la{};
     la.m = C; la.k1 = H; la.k2 = 0; la.n_out = H; la.x1 = f.gn; la.wt = fc_t; la.bias = h->P(fc_b);
     la.residual = x; la.relu = 1; la.y = y;   // F.relu(l1_conv(x)) of Backbone.forward folded in
     return linear(la, s);
   };
 
-  RUN(perconv(f.x_clu, pk.c0_wt, pk.c0_wp, pk.c0_b, P_C0_BN_W, P_C0_BN_B, P_C0_BN_MS, pk.c0_fc_t, P_C0_FC_B, f.x1));
+  RUN(perconv(f.x_clu, pk.c0_wt, pk.c0_wp, pk.c0_b, P_C0_BN_W, P_C0_BN_B, P_C0_BN_MS, pk.c0_fc_t, P_C0_FC_B, f.x1, pk.tc_c0, pk.tc_c0_fc));
 
   // GRU gates on the TARGET cluster graph, candidate on the CURRENT one (graph_vs.py:246-249)
-  RUN(pq_linear(f.x1, hidden_in, pk.g_wt, pk.g_wp, pk.g_b, 4 * H));
+  RUN(pq_linear(f.x1, hidden_in, pk.g_wt, pk.g_wp, pk.g_b, 4 * H, pk.tc_g, 2 * H));
   {
     EdgeConvArgs ec{};
     ec.n_rows = C; ec.f_out = 2 * H; ec.mode = EC_GATES; ec.pq = f.pq; ec.rowptr = f.tar_rowptr; ec.src = f.tar_src;
     ec.h = hidden_in; ec.hr = f.hr; ec.u = f.u;
     RUN(edgeconv_max(ec, s));
   }
-  RUN(pq_linear(f.x1, hidden_in ? f.hr : nullptr, pk.k_wt, pk.k_wp, pk.k_b, 2 * H));
+  RUN(pq_linear(f.x1, hidden_in ? f.hr : nullptr, pk.k_wt, pk.k_wp, pk.k_b, 2 * H, pk.tc_k, 2 * H));
   {
     EdgeConvArgs ec{};
     ec.n_rows = C; ec.f_out = H; ec.mode = EC_CANDIDATE; ec.pq = f.pq; ec.rowptr = f.cur_rowptr; ec.src = f.cur_src;
     ec.h = hidden_in; ec.u_in = f.u; ec.h_out = hidden_out;
     RUN(edgeconv_max(ec, s));
   }
-  RUN(perconv(hidden_out, pk.c1_wt, pk.c1_wp, pk.c1_b, P_C1_BN_W, P_C1_BN_B, P_C1_BN_MS, pk.c1_fc_t, P_C1_FC_B, f.x2));
+  RUN(perconv(hidden_out, pk.c1_wt, pk.c1_wp, pk.c1_b, P_C1_BN_W, P_C1_BN_B, P_C1_BN_MS, pk.c1_fc_t, P_C1_FC_B, f.x2, pk.tc_c1, pk.tc_c1_fc));
 
   // ---- decoder ----------------------------------------------------------------------------
   PoolHeadArgs ph{};

@@ -151,6 +151,22 @@ int repack(cns_handle* h, cudaStream_t s) {
   if ((rc = launch_edgeconv_pack(h->P(P_K_MSG_W), h->P(P_K_MSG_B), 256, 128, pk.k_wt, pk.k_wp, pk.k_b, s))) return rc;
   if ((rc = launch_edgeconv_pack(h->P(P_C1_MSG_W), h->P(P_C1_MSG_B), 128, 128, pk.c1_wt, pk.c1_wp, pk.c1_b, s))) return rc;
   if ((rc = tc_pack_weights(h, s)) != CNS_OK) return rc;
+  {
+    // node-GEMM weight images (bf16 + f16), 2 bytes per element
+    struct Item { const float* wt; int k, n; unsigned char** dst; };
+    Item items[] = {{pk.c0_wt, 128, 256, pk.tc_c0}, {pk.c0_fc_t, 128, 128, pk.tc_c0_fc}, {pk.g_wt, 256, 512, pk.tc_g},
+                    {pk.k_wt, 256, 256, pk.tc_k},   {pk.c1_wt, 128, 256, pk.tc_c1},   {pk.c1_fc_t, 128, 128, pk.tc_c1_fc},
+                    {pk.out_t, 256, 128, pk.tc_out}};
+    if (!pk.tc_node_base) {
+      size_t total = 0;
+      for (auto& it : items) total += (size_t)it.k * it.n * 2 * 2;
+      CNS_CUDA_CHECK(cudaMalloc(&pk.tc_node_base, total));
+      unsigned char* q = pk.tc_node_base;
+      for (auto& it : items) { it.dst[0] = q; q += (size_t)it.k * it.n * 2; it.dst[1] = q; q += (size_t)it.k * it.n * 2; }
+    }
+    for (auto& it : items)
+      if ((rc = gemm_tc_pack(it.wt, it.k, it.n, it.dst[0], it.dst[1], s)) != CNS_OK) return rc;
+  }
   h->weights_loaded = true;
   return CNS_OK;
 }
@@ -225,6 +241,7 @@ int cns_destroy(cns_handle* h) {
   cudaFree(h->raw);
   cudaFree(h->packed_base);
   if (h->tc_w_img) cudaFree(h->tc_w_img);
+  if (h->pk.tc_node_base) cudaFree(h->pk.tc_node_base);
   if (h->stage_host) cudaFreeHost(h->stage_host);
   if (h->stage_dev) cudaFree(h->stage_dev);
   delete h;

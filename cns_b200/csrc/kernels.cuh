@@ -49,6 +49,7 @@ struct EncFinishArgs {
   const int* clu_rowptr; const float* partial; float* clu_feat;
   const float* out_t; const float* b_out; const uint8_t* cluster_mask;
   float* x_clu;      // (C,128)
+  float* cat_out;    // optional (C,256): write [cur | tar - cur] and skip out_enc (done by gemm_tc)
 };
 int enc_finish(const EncFinishArgs& a, cudaStream_t s);
 
@@ -63,6 +64,21 @@ struct LinearArgs {
   float* y;
 };
 int linear(const LinearArgs& a, cudaStream_t s);
+
+// ---- gemm_tc.cu: same contract as `linear` on tcgen05 (16-bit operands), plus an optional row mask
+struct GemmTcArgs {
+  int64_t m; int k1, k2, n_out;
+  const float* x1; const float* x2;
+  const unsigned char* w_img;              // swizzled 16-bit weight image (gemm_tc_pack)
+  int k_img;                               // K the image was packed with (>= k1+k2; 0 => k1+k2): a GEMM over
+                                           // the first k1+k2 input columns only reads a prefix of each chunk
+  const float* bias; const float* pos; const float* wp; const float* residual;
+  const uint8_t* row_mask;                 // optional (m,): rows with 0 are written as zeros
+  int relu;
+  float* y;
+};
+int gemm_tc(const GemmTcArgs& a, bool bf16, cudaStream_t s);
+int gemm_tc_pack(const float* wt, int k_dim, int n_out, unsigned char* img_bf16, unsigned char* img_f16, cudaStream_t s);
 
 enum EdgeConvMode { EC_PLAIN = 0, EC_GATES = 1, EC_CANDIDATE = 2 };
 struct EdgeConvArgs {
