@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("CNS_PRECISION", "bf16"), choices=["fp32", "f16", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("CNS_PRECISION", "f16"), choices=["fp32", "f16", "bf16"])
     ap.add_argument("--graphs", type=int, default=N_GRAPHS)
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--cpu-sample", type=int, default=64, help="graphs per CPU-baseline step")

@@ -73,6 +73,25 @@ def test_forward_matches_oracle_recurrent(net, state_dict, sizes, missing):
             s.step(v * 2)
 
 
+@pytest.mark.parametrize("prec", ["f16", "bf16"])
+@pytest.mark.parametrize("sizes,missing", [([24, 100, 300, 512, 33], 0.3), ([512] * 6, 0.1), ([7], 0.0), ([2000], 0.05)])
+def test_tensor_core_modes_match_oracle(state_dict, prec, sizes, missing):
+    """tcgen05 paths (encoder edge kernel + node GEMMs with 16-bit operands, fp32 accumulation in
+    TMEM): 5 recurrent frames, hidden carried, within the per-dtype tolerance of the fp64 oracle."""
+    net = ckpt.load_model(os.path.join(ROOT, "checkpoints", "cns.pth"), "cuda:0", precision=prec)
+    rng = np.random.default_rng(len(sizes) + 100)
+    np.random.seed(len(sizes) + 100)
+    scenes = [synth.Scene(rng, n) for n in sizes]
+    hid_g = hid_o = None
+    for _ in range(5):
+        frames = [s.frame(missing) for s in scenes]
+        batch = Batch.from_data_list(frames) if len(frames) > 1 else frames[0]
+        pred, hid_o = _check(net, batch, hid_g, hid_o, state_dict, tol=TOL[prec])
+        hid_g = pred[2]
+        for s, v in zip(scenes, pred.vel.cpu().numpy()):
+            s.step(v * 2)
+
+
 def test_all_clusters_of_one_graph_masked(net, state_dict):
     """A graph whose every keypoint is missing: empty segments must give zeros, not NaNs."""
     rng = np.random.default_rng(9)
