@@ -85,6 +85,8 @@ struct cns_handle {
   float* packed_base;
   cns::Packed pk;
   bool weights_loaded;
+  long long weights_version;        // bumped by every (re)pack of the weights
+  void* bwd_pack; long long bwd_pack_version;   // transposed operands of the backward pass (backward.cu)
   // tensor-core (tcgen05) encoder operands: bf16 image then f16 image, 5 swizzled 32 KB tiles each
   unsigned char* tc_w_img;
   float tc_small_host[128 * 2 + 128 + 128 * 4 + 128];   // in_enc / pos_nn.0 weights passed as kernel params

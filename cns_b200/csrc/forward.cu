@@ -2,55 +2,61 @@
 // (cns/models/graph_vs.py:284-322, cns/models/functions.py:26-38).
 #include "common.cuh"
 #include "kernels.cuh"
+#include "save.cuh"
 
 namespace cns {
-
-// Bump allocator over the caller's workspace; first pass (base == nullptr) only measures.
-struct Arena {
-  char* base; size_t off;
-  explicit Arena(void* b) : base((char*)b), off(0) {}
-  template <typename T> T* take(size_t n) {
-    size_t o = off;
-    off += align_up(n * sizeof(T));
-    return base ? reinterpret_cast<T*>(base + o) : nullptr;
-  }
-};
 
 struct FwdBuffers {
   int* err; int* clu_rowptr; int* clu_graph; int* graph_ptr; int* gp_tmp; int* scan_scratch;
   int* cur_rowptr; int* cur_src; int* tar_rowptr; int* tar_src; void* csr_ws;
   float* a_dst; float* pos_clu; float* clu_feat; float* partial; float* x_clu;
-  float* pq; float* conv; float* gn; float* x1; float* u; float* hr; float* x2; float* gate;
+  float* pq; float* conv0; float* conv1; float* gn0; float* gn1; float* stats0; float* stats1;
+  float* x1; float* u; float* hr; float* x2; float* gate;
+  float* g; float* ht; float* x_scene; float* hid;          // training only
+  int* arg0; int* argg; int* argk; int* arg1;               // training only
   int64_t n_slots;
 };
 
-static void carve(Arena& ar, const cns_batch* b, FwdBuffers& f) {
+// Scratch always comes from the workspace; activations the backward pass needs come from the
+// caller's save buffer when one is given (training), else they alias workspace scratch.
+static void carve(Arena& ar, const cns_batch* b, FwdBuffers& f, const SaveBuffers* sv) {
   const int64_t C = b->n_clusters, B = b->n_graphs;
+  memset(&f, 0, sizeof(f));
   f.n_slots = C + (b->n_e01 + 31) / 32 + 2;   // one partial slot per (cluster, softmax piece) pair; pieces >= 32 edges
   f.err = ar.take<int>(64);
-  f.clu_rowptr = ar.take<int>(C + 1);
   f.clu_graph = ar.take<int>(C + 1);
-  f.graph_ptr = ar.take<int>(B + 1);
   f.gp_tmp = ar.take<int>(B + 1);
   f.scan_scratch = (int*)ar.take<char>(scan_scratch_bytes(B + 1));
-  f.cur_rowptr = ar.take<int>(C + 1);
-  f.cur_src = ar.take<int>(b->n_e11_cur + 1);
-  f.tar_rowptr = ar.take<int>(C + 1);
-  f.tar_src = ar.take<int>(b->n_e11_tar + 1);
   f.csr_ws = ar.take<char>(csr_workspace_bytes(C));
   f.a_dst = ar.take<float>(C * H);
-  f.pos_clu = ar.take<float>(C * 2 + 2);
-  f.clu_feat = ar.take<float>(2 * C * H);
   f.partial = ar.take<float>((size_t)2 * f.n_slots * 3 * H);
-  f.x_clu = ar.take<float>(C * H);
   f.pq = ar.take<float>(C * 4 * H);
-  f.conv = ar.take<float>(C * H);
-  f.gn = ar.take<float>(C * H);
-  f.x1 = ar.take<float>(C * H);
-  f.u = ar.take<float>(C * H);
-  f.hr = ar.take<float>(C * H);
-  f.x2 = ar.take<float>(C * H);
-  f.gate = ar.take<float>(C + 1);
+  if (sv) {
+    f.clu_rowptr = sv->clu_rowptr; f.graph_ptr = sv->graph_ptr;
+    f.cur_rowptr = sv->cur_rowptr; f.cur_src = sv->cur_src; f.tar_rowptr = sv->tar_rowptr; f.tar_src = sv->tar_src;
+    f.pos_clu = sv->pos_clu; f.clu_feat = sv->clu_feat; f.x_clu = sv->x_clu;
+    f.conv0 = sv->conv0; f.conv1 = sv->conv1; f.gn0 = sv->gn0; f.gn1 = sv->gn1; f.stats0 = sv->stats0; f.stats1 = sv->stats1;
+    f.x1 = sv->x1; f.u = sv->u; f.hr = sv->hr; f.x2 = sv->x2; f.gate = sv->gate;
+    f.g = sv->g; f.ht = sv->ht; f.x_scene = sv->x_scene; f.hid = sv->hid;
+    f.arg0 = sv->arg0; f.argg = sv->argg; f.argk = sv->argk; f.arg1 = sv->arg1;
+  } else {
+    f.clu_rowptr = ar.take<int>(C + 1);
+    f.graph_ptr = ar.take<int>(B + 1);
+    f.cur_rowptr = ar.take<int>(C + 1);
+    f.cur_src = ar.take<int>(b->n_e11_cur + 1);
+    f.tar_rowptr = ar.take<int>(C + 1);
+    f.tar_src = ar.take<int>(b->n_e11_tar + 1);
+    f.pos_clu = ar.take<float>(C * 2 + 2);
+    f.clu_feat = ar.take<float>(2 * C * H);
+    f.x_clu = ar.take<float>(C * H);
+    f.conv0 = f.conv1 = ar.take<float>(C * H);
+    f.gn0 = f.gn1 = ar.take<float>(C * H);
+    f.x1 = ar.take<float>(C * H);
+    f.u = ar.take<float>(C * H);
+    f.hr = ar.take<float>(C * H);
+    f.x2 = ar.take<float>(C * H);
+    f.gate = ar.take<float>(C + 1);
+  }
 }
 
 static int validate(const cns_batch* b) {
@@ -69,10 +75,17 @@ static int validate(const cns_batch* b) {
 }
 
 int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, float* vel_si_vec,
-                 float* vel_si_norm, float* hidden_out, float* vel, void* workspace, cudaStream_t s) {
+                 float* vel_si_norm, float* hidden_out, float* vel, void* workspace, void* save, cudaStream_t s) {
   Arena ar(workspace);
   FwdBuffers f;
-  carve(ar, b, f);
+  SaveBuffers sv_store;
+  const SaveBuffers* sv = nullptr;
+  if (save) {
+    Arena sa(save);
+    carve_save(sa, b, sv_store);
+    sv = &sv_store;
+  }
+  carve(ar, b, f, sv);
   const int64_t C = b->n_clusters, B = b->n_graphs;
   const Packed& pk = h->pk;
   int rc;
@@ -145,47 +158,47 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   };
   auto perconv = [&](const float* x, const float* wt, const float* wp, const float* bias, int bn_w, int bn_b,
                      int bn_ms, const float* fc_t, int fc_b, float* y, unsigned char* const* img,
-                     unsigned char* const* fc_img) {
+                     unsigned char* const* fc_img, float* conv, float* gnb, float* stats, int* arg) {
     int r;
     if ((r = pq_linear(x, nullptr, wt, wp, bias, 2 * H, img, H)) != CNS_OK) return r;
     EdgeConvArgs ec{};
     ec.n_rows = C; ec.f_out = H; ec.mode = EC_PLAIN; ec.pq = f.pq; ec.rowptr = f.cur_rowptr; ec.src = f.cur_src;
-    ec.out = f.conv;
+    ec.out = conv; ec.argmax = arg;
     if ((r = edgeconv_max(ec, s)) != CNS_OK) return r;
     GraphNormArgs gn{};
-    gn.n_graphs = B; gn.graph_ptr = f.graph_ptr; gn.x = f.conv; gn.weight = h->P(bn_w); gn.bias = h->P(bn_b);
-    gn.mean_scale = h->P(bn_ms); gn.y = f.gn; gn.stats = nullptr;
+    gn.n_graphs = B; gn.graph_ptr = f.graph_ptr; gn.x = conv; gn.weight = h->P(bn_w); gn.bias = h->P(bn_b);
+    gn.mean_scale = h->P(bn_ms); gn.y = gnb; gn.stats = stats;
     if ((r = graphnorm_relu(gn, s)) != CNS_OK) return r;
     if (tc) {
       GemmTcArgs ga{};
-      ga.m = C; ga.k1 = H; ga.k2 = 0; ga.n_out = H; ga.x1 = f.gn; ga.w_img = fc_img[tci]; ga.bias = h->P(fc_b);
+      ga.m = C; ga.k1 = H; ga.k2 = 0; ga.n_out = H; ga.x1 = gnb; ga.w_img = fc_img[tci]; ga.bias = h->P(fc_b);
       ga.residual = x; ga.relu = 1; ga.y = y;
       return gemm_tc(ga, tci == 0, s);
     }
     LinearArgs la{};
-    la.m = C; la.k1 = H; la.k2 = 0; la.n_out = H; la.x1 = f.gn; la.wt = fc_t; la.bias = h->P(fc_b);
+    la.m = C; la.k1 = H; la.k2 = 0; la.n_out = H; la.x1 = gnb; la.wt = fc_t; la.bias = h->P(fc_b);
     la.residual = x; la.relu = 1; la.y = y;   // F.relu(l1_conv(x)) of Backbone.forward folded in
     return linear(la, s);
   };
 
-  RUN(perconv(f.x_clu, pk.c0_wt, pk.c0_wp, pk.c0_b, P_C0_BN_W, P_C0_BN_B, P_C0_BN_MS, pk.c0_fc_t, P_C0_FC_B, f.x1, pk.tc_c0, pk.tc_c0_fc));
+  RUN(perconv(f.x_clu, pk.c0_wt, pk.c0_wp, pk.c0_b, P_C0_BN_W, P_C0_BN_B, P_C0_BN_MS, pk.c0_fc_t, P_C0_FC_B, f.x1, pk.tc_c0, pk.tc_c0_fc, f.conv0, f.gn0, f.stats0, f.arg0));
 
   // GRU gates on the TARGET cluster graph, candidate on the CURRENT one (graph_vs.py:246-249)
   RUN(pq_linear(f.x1, hidden_in, pk.g_wt, pk.g_wp, pk.g_b, 4 * H, pk.tc_g, 2 * H));
   {
     EdgeConvArgs ec{};
     ec.n_rows = C; ec.f_out = 2 * H; ec.mode = EC_GATES; ec.pq = f.pq; ec.rowptr = f.tar_rowptr; ec.src = f.tar_src;
-    ec.h = hidden_in; ec.hr = f.hr; ec.u = f.u;
+    ec.h = hidden_in; ec.hr = f.hr; ec.u = f.u; ec.argmax = f.argg; ec.act = f.g;
     RUN(edgeconv_max(ec, s));
   }
   RUN(pq_linear(f.x1, hidden_in ? f.hr : nullptr, pk.k_wt, pk.k_wp, pk.k_b, 2 * H, pk.tc_k, 2 * H));
   {
     EdgeConvArgs ec{};
     ec.n_rows = C; ec.f_out = H; ec.mode = EC_CANDIDATE; ec.pq = f.pq; ec.rowptr = f.cur_rowptr; ec.src = f.cur_src;
-    ec.h = hidden_in; ec.u_in = f.u; ec.h_out = hidden_out;
+    ec.h = hidden_in; ec.u_in = f.u; ec.h_out = hidden_out; ec.argmax = f.argk; ec.act = f.ht;
     RUN(edgeconv_max(ec, s));
   }
-  RUN(perconv(hidden_out, pk.c1_wt, pk.c1_wp, pk.c1_b, P_C1_BN_W, P_C1_BN_B, P_C1_BN_MS, pk.c1_fc_t, P_C1_FC_B, f.x2, pk.tc_c1, pk.tc_c1_fc));
+  RUN(perconv(hidden_out, pk.c1_wt, pk.c1_wp, pk.c1_b, P_C1_BN_W, P_C1_BN_B, P_C1_BN_MS, pk.c1_fc_t, P_C1_FC_B, f.x2, pk.tc_c1, pk.tc_c1_fc, f.conv1, f.gn1, f.stats1, f.arg1));
 
   // ---- decoder ----------------------------------------------------------------------------
   PoolHeadArgs ph{};
@@ -195,6 +208,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   ph.nrm0_t = pk.nrm0_t; ph.nrm0_b = h->P(P_NRM0_B); ph.nrm1_w = h->P(P_NRM1_W); ph.nrm1_b = h->P(P_NRM1_B);
   ph.tPo_norm = b->tPo_norm; ph.gate = f.gate;
   ph.vel_si_vec = vel_si_vec; ph.vel_si_norm = vel_si_norm; ph.vel = vel;
+  ph.x_scene = f.x_scene; ph.hid = f.hid;
   RUN(pool_head(ph, s));
 #undef RUN
   return CNS_OK;
@@ -210,20 +224,26 @@ size_t cns_forward_workspace_bytes(const cns_batch* b) {
   if (!b) return 0;
   Arena ar(nullptr);
   FwdBuffers f;
-  carve(ar, b, f);
+  carve(ar, b, f, nullptr);
   return ar.off + 256;
 }
 
 size_t cns_forward_save_bytes(const cns_batch* b) {
-  (void)b;
-  return 0;  // training saves: see cns_graphvs_backward (not part of the inference library yet)
+  if (!b) return 0;
+  Arena ar(nullptr);
+  SaveBuffers sv;
+  carve_save(ar, b, sv);
+  return ar.off + 256;
 }
 
 int cns_graphvs_forward(cns_handle* h, const cns_batch* b, const float* hidden_in, float* vel_si_vec,
                         float* vel_si_norm, float* hidden_out, float* vel, void* workspace,
                         size_t workspace_bytes, void* save, size_t save_bytes, void* stream) {
-  (void)save; (void)save_bytes;
   CNS_REQUIRE(h != nullptr, "NULL handle");
+  if (save && save_bytes < cns_forward_save_bytes(b)) {
+    set_error("cns_graphvs_forward: save buffer %zu < %zu bytes", save_bytes, cns_forward_save_bytes(b));
+    return CNS_ERR_WORKSPACE_TOO_SMALL;
+  }
   CNS_REQUIRE(h->weights_loaded, "weights not loaded (cns_load_weights)");
   int rc = validate(b);
   if (rc != CNS_OK) return rc;
@@ -236,7 +256,7 @@ int cns_graphvs_forward(cns_handle* h, const cns_batch* b, const float* hidden_i
     return CNS_ERR_WORKSPACE_TOO_SMALL;
   }
   CNS_CUDA_CHECK(cudaSetDevice(h->device));
-  return forward_impl(h, b, hidden_in, vel_si_vec, vel_si_norm, hidden_out, vel, workspace, (cudaStream_t)stream);
+  return forward_impl(h, b, hidden_in, vel_si_vec, vel_si_norm, hidden_out, vel, workspace, save, (cudaStream_t)stream);
 }
 
 // Error word written by the index-preparation kernels (0 = fine).  Synchronises `stream`.

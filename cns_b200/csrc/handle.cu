@@ -129,6 +129,8 @@ static int launch_edgeconv_pack(const float* w, const float* b, int f_in, int f_
   return CNS_OK;
 }
 
+void free_bwd_pack(cns_handle* h);
+
 int repack(cns_handle* h, cudaStream_t s) {
   Packed& pk = h->pk;
   int rc;
@@ -168,6 +170,7 @@ int repack(cns_handle* h, cudaStream_t s) {
       if ((rc = gemm_tc_pack(it.wt, it.k, it.n, it.dst[0], it.dst[1], s)) != CNS_OK) return rc;
   }
   h->weights_loaded = true;
+  ++h->weights_version;
   return CNS_OK;
 }
 
@@ -240,6 +243,7 @@ int cns_destroy(cns_handle* h) {
   if (h->ev[0]) for (int i = 0; i < 2 * 256; ++i) cudaEventDestroy(h->ev[i]);
   cudaFree(h->raw);
   cudaFree(h->packed_base);
+  free_bwd_pack(h);
   if (h->tc_w_img) cudaFree(h->tc_w_img);
   if (h->pk.tc_node_base) cudaFree(h->pk.tc_node_base);
   if (h->stage_host) cudaFreeHost(h->stage_host);

@@ -168,8 +168,9 @@ class GraphVS(nn.Module):
     def set_precision(self, precision: str):
         assert precision in _lib.PRECISIONS
         self.precision = precision
-        for h, _ in self._handles.values():
-            h.set_precision(precision)
+        for key, (h, _) in self._handles.items():
+            if not isinstance(key, tuple):
+                h.set_precision(precision)
 
     def _ordered_params(self):
         if self._names is None:
@@ -177,16 +178,17 @@ class GraphVS(nn.Module):
         sd = dict(self.named_parameters())
         return [sd[n] for n in self._names]
 
-    def _handle(self, device: torch.device) -> "_lib.Handle":
+    def _handle(self, device: torch.device, training: bool = False) -> "_lib.Handle":
         params = self._ordered_params()
         version = tuple((p.data_ptr(), p._version) for p in params)
         idx = device.index if device.index is not None else torch.cuda.current_device()
-        ent = self._handles.get(idx)
+        key = (idx, "train") if training else idx       # training always uses the fp32 kernels
+        ent = self._handles.get(key)
         if ent is None:
             h = _lib.Handle(torch.device("cuda", idx))
-            h.set_precision(self.precision)
+            h.set_precision("fp32" if training else self.precision)
             ent = [h, None]
-            self._handles[idx] = ent
+            self._handles[key] = ent
         if ent[1] != version:
             on_dev = all(p.is_cuda for p in params)
             if not on_dev and any(p.is_cuda for p in params):
@@ -195,11 +197,11 @@ class GraphVS(nn.Module):
             ent[1] = version
         return ent[0]
 
-    def _workspace(self, idx: int, nbytes: int) -> torch.Tensor:
-        ws = self._workspaces.get(idx)
+    def _workspace(self, idx: int, nbytes: int, key: str = "fwd") -> torch.Tensor:
+        ws = self._workspaces.get((idx, key))
         if ws is None or ws.numel() < nbytes:
             ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=torch.device("cuda", idx))
-            self._workspaces[idx] = ws
+            self._workspaces[(idx, key)] = ws
         return ws
 
     @staticmethod

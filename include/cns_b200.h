@@ -119,6 +119,19 @@ int cns_graphvs_forward(cns_handle* h, const cns_batch* b, const float* hidden_i
                         void* workspace, size_t workspace_bytes,
                         void* save, size_t save_bytes, void* stream);
 
+/* Backward of cns_graphvs_forward (training: trainer.py:75-100, train_gvs_short_seq.py:24-53).
+ * `save` is the buffer the forward filled; hidden_in / hidden_out are the forward's input / output
+ * hidden states; d_* are upstream gradients (NULL == zero).  Parameter gradients are ACCUMULATED
+ * (+=) into grad_flat, a flat fp32 buffer of cns_param_offset(h, 43) floats where parameter k
+ * starts at cns_param_offset(h, k).  d_hidden_in (C,128) is overwritten (may be NULL).
+ * fp32 arithmetic; deterministic (fixed-order reductions, no floating-point atomics). */
+size_t cns_backward_workspace_bytes(const cns_batch* b);
+int64_t cns_param_offset(const cns_handle* h, int k);
+int cns_graphvs_backward(cns_handle* h, const cns_batch* b, const float* hidden_in, const float* hidden_out,
+                         const float* d_vel_si_vec, const float* d_vel_si_norm, const float* d_hidden_out,
+                         float* d_hidden_in, float* grad_flat, const void* save, size_t save_bytes,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* Error word left in `workspace` by the index-preparation kernels of the last forward on
  * `stream` (unsorted l0_to_l1 edges, out-of-range indices).  Synchronises `stream`. */
 int cns_forward_status(const void* workspace, void* stream);
