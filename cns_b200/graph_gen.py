@@ -95,14 +95,38 @@ def _segment_median(values, order_by_label, starts, sizes):
     return med
 
 
+def label_nearest_exemplar(points, exemplar_indices, device="cuda:0") -> np.ndarray:
+    """1-NN keypoint -> exemplar assignment on the GPU (`cns_label_nearest`): the final labelling step
+    of sklearn's AffinityPropagation (argmax_k -||x - e_k||^2, first maximum wins), in fp64."""
+    import ctypes as C  # noqa: F401
+    from . import _lib
+    lib = _lib.load()
+    pts = torch.as_tensor(np.ascontiguousarray(points, dtype=np.float64), device=device)
+    ex = pts[torch.as_tensor(np.asarray(exemplar_indices, dtype=np.int64), device=device)].contiguous()
+    xptr = torch.tensor([0, ex.shape[0]], dtype=torch.int64, device=device)
+    labels = torch.empty(pts.shape[0], dtype=torch.int32, device=device)
+    _lib.check(lib.cns_label_nearest(_lib.ptr(pts), None, pts.shape[0], _lib.ptr(ex), _lib.ptr(xptr),
+                                     _lib.ptr(labels), _lib.stream_ptr(torch.device(device))), "cns_label_nearest")
+    return labels.cpu().numpy().astype(np.int64)
+
+
 class GraphGenerator(object):
-    def __init__(self, target_points):
+    @classmethod
+    def from_exemplars(cls, target_points, exemplar_indices, device="cuda:0"):
+        """Graph whose clusters are the Voronoi cells of the given exemplar keypoints (labels computed
+        on the device).  Used where host-side Affinity Propagation is impractical (N > ~1000)."""
+        return cls(target_points, labels=label_nearest_exemplar(target_points, exemplar_indices, device))
+
+    def __init__(self, target_points, labels=None):
         target_points = np.asarray(target_points)
         self.num_points = len(target_points)
         self.target_points = target_points
         n = self.num_points
 
-        if n > 16:
+        if labels is not None:
+            self.yhat = np.asarray(labels)
+            self.cluster_ids, self.cluster_points_count = np.unique(self.yhat, return_counts=True)
+        elif n > 16:
             self.yhat, self.cluster_ids, self.cluster_points_count = \
                 try_cluster_points(target_points, max_tries=3)
         else:
