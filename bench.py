@@ -229,9 +229,11 @@ def main():
             net(host[i % N_ROTATE].to(dev, non_blocking=True), None).vel.cpu()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        from cns_b200.data import DevicePrefetcher
         f0.record()
-        for i in range(args.steps):
-            data = host[i % N_ROTATE].to(dev, non_blocking=True)       # host -> device, every step
+        # every step copies its own pinned host Batch to the device (on a side stream, overlapping the
+        # previous step's kernels) and reads its velocities back to the host
+        for data in DevicePrefetcher((host[i % N_ROTATE] for i in range(args.steps)), dev):
             pred = net(data, None)
             vel = net.postprocess(pred, data).cpu()                    # device -> host read of the result
         f1.record()

@@ -62,6 +62,7 @@ def _declare(lib):
         "cns_param_offset": (i64, [vp, i32]),
         "cns_graphvs_backward": (i32, [vp, C.POINTER(cns_batch), vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, sz, vp]),
         "cns_graphvs_forward_host": (i32, [vp, C.POINTER(cns_batch), vp, vp, vp, vp, vp]),
+        "cns_servo_step_host": (i32, [vp, C.POINTER(cns_batch), i32, vp, vp, vp]),
         "cns_csr_by_dst": (i32, [vp, i64, i64, vp, vp, vp, sz, vp]),
         "cns_edgeconv_max": (i32, [vp, vp, vp, i64, i32, vp, vp]),
         "cns_graphnorm_relu": (i32, [vp, vp, i64, vp, vp, vp, vp, vp]),

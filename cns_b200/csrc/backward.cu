@@ -6,6 +6,7 @@
 #include "kernels.cuh"
 #include "save.cuh"
 #include "bwd.cuh"
+#include <algorithm>
 
 namespace cns {
 
@@ -52,10 +53,11 @@ struct BwdBuffers {
       *dclu, *d_adst, *a_dst, *d_xtc, *xtc, *fe_c, *zeros_h, *dhid, *dgate, *gn_partial, *G, *Gp, *gb, *dw_partial,
       *small_partial;
   float* E[N_EBUF]; float* FE; float* DP;
+  int small_slabs;
 };
 
 constexpr size_t DW_PARTIAL_FLOATS = (size_t)10 * 1024 * 1024;   // 40 MB of split-M partials
-constexpr int SMALL_SLABS = 128;
+// dw_small splits rows into slabs of 128; sized per batch in carve_bwd
 
 static void carve_bwd(Arena& ar, const cns_batch* b, BwdBuffers& w) {
   const int64_t C = b->n_clusters, B = b->n_graphs, E = b->n_e01;
@@ -74,7 +76,8 @@ static void carve_bwd(Arena& ar, const cns_batch* b, BwdBuffers& w) {
   w.gn_partial = ar.take<float>(B * 3 * H);
   w.G = ar.take<float>(512 * 256); w.Gp = ar.take<float>(512 * 2); w.gb = ar.take<float>(512);
   w.dw_partial = ar.take<float>(DW_PARTIAL_FLOATS);
-  w.small_partial = ar.take<float>((size_t)SMALL_SLABS * 512 * 8);
+  w.small_slabs = (int)((std::max<int64_t>(std::max<int64_t>(E, C), B) + 127) / 128) + 1;
+  w.small_partial = ar.take<float>((size_t)w.small_slabs * 512 * 4);   // n*q <= 512*2 or 128*8
   for (int i = 0; i < N_EBUF; ++i) w.E[i] = ar.take<float>((size_t)E * H + 4);
   w.FE = ar.take<float>(E * 2 + 2); w.DP = ar.take<float>(E * 4 + 4);
 }
@@ -115,7 +118,7 @@ int backward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, con
                  int transposed, int accumulate) {
     DwSmallArgs d{};
     d.m = m; d.n = n; d.q = q; d.a = a; d.lda = lda; d.s = sm; d.lds = lds; d.out = out; d.ld_out = ld_out;
-    d.transposed = transposed; d.scale = 1.f; d.accumulate = accumulate; d.partial = w.small_partial; d.max_slabs = SMALL_SLABS;
+    d.transposed = transposed; d.scale = 1.f; d.accumulate = accumulate; d.partial = w.small_partial; d.max_slabs = w.small_slabs;
     return dw_small(d, s);
   };
   auto colsum = [&](const float* a, int lda, int n, int64_t m, float* out, int accumulate) {

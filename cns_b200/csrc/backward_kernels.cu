@@ -105,19 +105,50 @@ int dw_gemm(const DwGemmArgs& a, cudaStream_t s) {
 //         transposed == 1 -> out[q*ld_out + n] (weight [tiny out][in])
 // one thread per column n, a block per row slab; stage 2 as above.
 // =============================================================================================
-__global__ void dw_small_kernel(DwSmallArgs p, int rows_per_slab) {
+constexpr int DWS_ROWS = 128;   // rows per slab: many small CTAs so that long reductions fill the GPU
+
+__global__ void __launch_bounds__(128)
+dw_small_kernel(DwSmallArgs p, int rows_per_slab) {
+  __shared__ float ss[DWS_ROWS * 8];
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int slab = blockIdx.y;
-  if (n >= p.n) return;
   const int64_t r0 = (int64_t)slab * rows_per_slab, r1 = min(p.m, r0 + rows_per_slab);
+  const int rows = (int)(r1 - r0);
+  if (p.s) {
+    for (int i = threadIdx.x; i < rows * p.q; i += blockDim.x) ss[i] = p.s[(r0 + i / p.q) * p.lds + i % p.q];
+  }
+  __syncthreads();
+  if (n >= p.n) return;
   float acc[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-  for (int64_t m = r0; m < r1; ++m) {
-    const float a = p.a[m * p.lda + n];
+  const float* __restrict__ a = p.a + r0 * p.lda + n;
+  int r = 0;
+  for (; r + 4 <= rows; r += 4) {        // 4 independent loads in flight
+    const float a0 = a[(int64_t)r * p.lda], a1 = a[(int64_t)(r + 1) * p.lda];
+    const float a2 = a[(int64_t)(r + 2) * p.lda], a3 = a[(int64_t)(r + 3) * p.lda];
+    if (p.s) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      if (q < p.q) acc[q] = fmaf(a, p.s ? p.s[m * p.lds + q] : 1.f, acc[q]);
+      for (int q = 0; q < 8; ++q)
+        if (q < p.q) {
+          acc[q] = fmaf(a0, ss[r * p.q + q], acc[q]);
+          acc[q] = fmaf(a1, ss[(r + 1) * p.q + q], acc[q]);
+          acc[q] = fmaf(a2, ss[(r + 2) * p.q + q], acc[q]);
+          acc[q] = fmaf(a3, ss[(r + 3) * p.q + q], acc[q]);
+        }
+    } else {
+      acc[0] += (a0 + a1) + (a2 + a3);
+    }
+  }
+  for (; r < rows; ++r) {
+    const float a0 = a[(int64_t)r * p.lda];
+    if (p.s) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < p.q) acc[q] = fmaf(a0, ss[r * p.q + q], acc[q]);
+    } else {
+      acc[0] += a0;
+    }
   }
   for (int q = 0; q < p.q; ++q) p.partial[((size_t)slab * p.n + n) * p.q + q] = acc[q];
 }
@@ -135,10 +166,13 @@ __global__ void reduce_small_kernel(DwSmallArgs p, int n_slabs) {
 int dw_small(const DwSmallArgs& a, cudaStream_t s) {
   CNS_REQUIRE(a.q >= 1 && a.q <= 8, "dw_small: q must be 1..8");
   const int64_t m1 = a.m > 0 ? a.m : 1;
-  int slabs = ceil_div(m1, 128);
-  if (slabs > 128) slabs = 128;
+  int slabs = ceil_div(m1, DWS_ROWS);
   if (slabs > a.max_slabs) slabs = a.max_slabs;
-  const int rows_per_slab = (int)((m1 + slabs - 1) / slabs);
+  int rows_per_slab = (int)((m1 + slabs - 1) / slabs);
+  if (rows_per_slab > DWS_ROWS) {          // more rows than the smem staging holds: use more, smaller slabs
+    set_error("dw_small: %lld rows need more than %d slabs", (long long)a.m, a.max_slabs);
+    return CNS_ERR_WORKSPACE_TOO_SMALL;
+  }
   dim3 grid(ceil_div(a.n, 128), slabs);
   dw_small_kernel<<<grid, 128, 0, s>>>(a, rows_per_slab);
   CNS_LAUNCH_CHECK();

@@ -96,5 +96,7 @@ struct cns_handle {
   // pinned / device staging for the *_host entry point
   void* stage_host; size_t stage_host_bytes;
   void* stage_dev;  size_t stage_dev_bytes;
+  // recurrent hidden state of cns_servo_step_host (two ping-pong device buffers inside stage_dev)
+  int servo_valid; int servo_cur; long long servo_nc;
   const float* P(int id) const { return raw + raw_off[id]; }
 };

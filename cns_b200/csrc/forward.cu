@@ -93,12 +93,23 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
 
   CNS_CUDA_CHECK(cudaMemsetAsync(f.err, 0, 64 * sizeof(int), s));
   // ---- index preparation ------------------------------------------------------------------
-  RUN(sorted_rowptr(b->l0_to_l1_i, b->n_e01, C, f.clu_rowptr, f.err, s));
-  RUN(graph_ptr_from_counts(b->num_clusters, B, f.graph_ptr, f.gp_tmp, f.scan_scratch, s));
   const int64_t cur_stride = b->l1_cur_stride ? b->l1_cur_stride : b->n_e11_cur;
   const int64_t tar_stride = b->l1_tar_stride ? b->l1_tar_stride : b->n_e11_tar;
-  RUN(csr_by_dst(b->l1_edge_cur, b->l1_edge_cur + cur_stride, b->n_e11_cur, C, f.cur_rowptr, f.cur_src, f.csr_ws, f.err, s));
-  RUN(csr_by_dst(b->l1_edge_tar, b->l1_edge_tar + tar_stride, b->n_e11_tar, C, f.tar_rowptr, f.tar_src, f.csr_ws, f.err, s));
+  if (C <= PREP_SMALL_MAX && B <= PREP_SMALL_MAX && b->n_e01 <= (1 << 20) && b->n_e11_cur + b->n_e11_tar <= (1 << 20)) {
+    // servo-loop sizes: one single-CTA launch instead of thirteen
+    PrepSmallArgs pa{};
+    pa.n_clusters = C; pa.n_graphs = B; pa.n_e01 = b->n_e01; pa.n_e11_cur = b->n_e11_cur; pa.n_e11_tar = b->n_e11_tar;
+    pa.num_clusters = b->num_clusters; pa.ei = b->l0_to_l1_i;
+    pa.cur_j = b->l1_edge_cur; pa.cur_i = b->l1_edge_cur + cur_stride; pa.tar_j = b->l1_edge_tar; pa.tar_i = b->l1_edge_tar + tar_stride;
+    pa.graph_ptr = f.graph_ptr; pa.clu_rowptr = f.clu_rowptr; pa.cur_rowptr = f.cur_rowptr; pa.cur_src = f.cur_src;
+    pa.tar_rowptr = f.tar_rowptr; pa.tar_src = f.tar_src; pa.err = f.err;
+    RUN(prep_small(pa, s));
+  } else {
+    RUN(sorted_rowptr(b->l0_to_l1_i, b->n_e01, C, f.clu_rowptr, f.err, s));
+    RUN(graph_ptr_from_counts(b->num_clusters, B, f.graph_ptr, f.gp_tmp, f.scan_scratch, s));
+    RUN(csr_by_dst(b->l1_edge_cur, b->l1_edge_cur + cur_stride, b->n_e11_cur, C, f.cur_rowptr, f.cur_src, f.csr_ws, f.err, s));
+    RUN(csr_by_dst(b->l1_edge_tar, b->l1_edge_tar + tar_stride, b->n_e11_tar, C, f.tar_rowptr, f.tar_src, f.csr_ws, f.err, s));
+  }
 
   // ---- encoder ----------------------------------------------------------------------------
   EncPreArgs pre{};
@@ -273,6 +284,93 @@ int cns_forward_status(const void* workspace, void* stream) {
   return CNS_OK;
 }
 
+// One servo frame from host memory with the recurrent hidden state kept ON THE DEVICE inside the handle
+// (what GraphVSController does with self.hidden, controller.py:23-38): every input array is packed into
+// one pinned staging block -> ONE host->device copy, the forward, ONE device->host copy of
+// (vel_si_vec | vel | vel_si_norm).  Meant for small batches (the staging memcpy is on the CPU).
+int cns_servo_step_host(cns_handle* h, const cns_batch* bh, int reset_hidden, float* vel_host,
+                        float* vel_si_vec_host, float* vel_si_norm_host) {
+  CNS_REQUIRE(h != nullptr && vel_host != nullptr, "NULL argument");
+  int rc = validate(bh);
+  if (rc != CNS_OK) return rc;
+  if (bh->n_graphs == 0) return CNS_OK;
+  CNS_CUDA_CHECK(cudaSetDevice(h->device));
+  const int64_t N = bh->n_nodes, C = bh->n_clusters, B = bh->n_graphs;
+  cns_batch d = *bh;
+  d.l1_cur_stride = 0; d.l1_tar_stride = 0;
+  const int64_t cs = bh->l1_cur_stride ? bh->l1_cur_stride : bh->n_e11_cur;
+  const int64_t ts = bh->l1_tar_stride ? bh->l1_tar_stride : bh->n_e11_tar;
+  // input block layout (offsets shared by the pinned host copy and the device copy)
+  size_t off[16]; size_t bytes[16]; const void* src[16]; int n_items = 0; size_t in_bytes = 0;
+  auto add = [&](const void* p, size_t nb) {
+    off[n_items] = in_bytes; bytes[n_items] = nb; src[n_items] = p; ++n_items;
+    in_bytes += align_up(nb);
+    return off[n_items - 1];
+  };
+  const size_t o_xc = add(bh->x_cur, N * 2 * sizeof(float)), o_xt = add(bh->x_tar, N * 2 * sizeof(float));
+  const size_t o_pc = add(bh->pos_cur, N * 2 * sizeof(float)), o_pt = add(bh->pos_tar, N * 2 * sizeof(float));
+  const size_t o_ej = add(bh->l0_to_l1_j, bh->n_e01 * sizeof(int64_t)), o_ei = add(bh->l0_to_l1_i, bh->n_e01 * sizeof(int64_t));
+  const size_t o_cj = add(bh->l1_edge_cur, bh->n_e11_cur * sizeof(int64_t));
+  add(bh->l1_edge_cur ? bh->l1_edge_cur + cs : nullptr, bh->n_e11_cur * sizeof(int64_t));   // row 1 right after row 0
+  const size_t o_tj = add(bh->l1_edge_tar, bh->n_e11_tar * sizeof(int64_t));
+  add(bh->l1_edge_tar ? bh->l1_edge_tar + ts : nullptr, bh->n_e11_tar * sizeof(int64_t));
+  const size_t o_cm = add(bh->cluster_mask, C), o_cc = add(bh->cluster_centers, C * sizeof(int64_t));
+  const size_t o_nc = add(bh->num_clusters, B * sizeof(int64_t));
+  const size_t o_tp = bh->tPo_norm ? add(bh->tPo_norm, B * sizeof(float)) : 0;
+  // rows of a (2,E) edge list must be contiguous on the device: row 1 sits align_up(row 0) later
+  d.l1_cur_stride = (int64_t)(align_up(bh->n_e11_cur * sizeof(int64_t)) / sizeof(int64_t));
+  d.l1_tar_stride = (int64_t)(align_up(bh->n_e11_tar * sizeof(int64_t)) / sizeof(int64_t));
+  const size_t out_bytes = align_up((size_t)B * 13 * sizeof(float));
+  const size_t hid_bytes = align_up((size_t)C * H * sizeof(float));
+  const size_t ws_bytes = cns_forward_workspace_bytes(bh);
+  const size_t dev_need = in_bytes + out_bytes + 2 * hid_bytes + ws_bytes;
+  const size_t host_need = in_bytes + out_bytes;
+  if (dev_need > h->stage_dev_bytes) {
+    if (h->stage_dev) CNS_CUDA_CHECK(cudaFree(h->stage_dev));
+    h->stage_dev = nullptr; h->stage_dev_bytes = 0;
+    CNS_CUDA_CHECK(cudaMalloc(&h->stage_dev, dev_need + dev_need / 4));
+    h->stage_dev_bytes = dev_need + dev_need / 4;
+    h->servo_valid = 0;
+  }
+  if (host_need > h->stage_host_bytes) {
+    if (h->stage_host) CNS_CUDA_CHECK(cudaFreeHost(h->stage_host));
+    h->stage_host = nullptr; h->stage_host_bytes = 0;
+    CNS_CUDA_CHECK(cudaMallocHost(&h->stage_host, host_need + host_need / 4));
+    h->stage_host_bytes = host_need + host_need / 4;
+  }
+  char* hb = (char*)h->stage_host;
+  char* db = (char*)h->stage_dev;
+  for (int i = 0; i < n_items; ++i)
+    if (bytes[i] && src[i]) memcpy(hb + off[i], src[i], bytes[i]);
+  cudaStream_t s = 0;
+  CNS_CUDA_CHECK(cudaMemcpyAsync(db, hb, in_bytes, cudaMemcpyHostToDevice, s));
+  d.x_cur = (const float*)(db + o_xc); d.x_tar = (const float*)(db + o_xt);
+  d.pos_cur = (const float*)(db + o_pc); d.pos_tar = (const float*)(db + o_pt);
+  d.l0_to_l1_j = (const int64_t*)(db + o_ej); d.l0_to_l1_i = (const int64_t*)(db + o_ei);
+  d.l1_edge_cur = (const int64_t*)(db + o_cj); d.l1_edge_tar = (const int64_t*)(db + o_tj);
+  d.cluster_mask = (const uint8_t*)(db + o_cm); d.cluster_centers = (const int64_t*)(db + o_cc);
+  d.node_graph = nullptr;
+  d.num_clusters = (const int64_t*)(db + o_nc);
+  d.tPo_norm = bh->tPo_norm ? (const float*)(db + o_tp) : nullptr;
+  float* out_d = (float*)(db + in_bytes);                 // vec (B,6) | vel (B,6) | nrm (B,1)
+  float* hid[2] = {(float*)(db + in_bytes + out_bytes), (float*)(db + in_bytes + out_bytes + hid_bytes)};
+  void* ws = db + in_bytes + out_bytes + 2 * hid_bytes;
+  const bool carry = h->servo_valid && !reset_hidden && h->servo_nc == C;
+  const float* hin = carry ? hid[h->servo_cur] : nullptr;
+  float* hout = hid[h->servo_cur ^ 1];
+  rc = cns_graphvs_forward(h, &d, hin, out_d, out_d + B * 12, hout, out_d + B * 6, ws, ws_bytes, nullptr, 0, s);
+  if (rc != CNS_OK) return rc;
+  h->servo_cur ^= 1; h->servo_valid = 1; h->servo_nc = C;
+  float* out_h = (float*)(hb + in_bytes);
+  CNS_CUDA_CHECK(cudaMemcpyAsync(out_h, out_d, (size_t)B * 13 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  rc = cns_forward_status(ws, s);                         // synchronises the stream
+  if (rc != CNS_OK) return rc;
+  if (vel_si_vec_host) memcpy(vel_si_vec_host, out_h, (size_t)B * 6 * sizeof(float));
+  memcpy(vel_host, out_h + B * 6, (size_t)B * 6 * sizeof(float));
+  if (vel_si_norm_host) memcpy(vel_si_norm_host, out_h + B * 12, (size_t)B * sizeof(float));
+  return CNS_OK;
+}
+
 int cns_graphvs_forward_host(cns_handle* h, const cns_batch* bh, const float* hidden_in_host,
                              float* vel_si_vec_host, float* vel_si_norm_host, float* hidden_out_host,
                              float* vel_host) {
@@ -299,6 +397,7 @@ int cns_graphvs_forward_host(cns_handle* h, const cns_batch* bh, const float* hi
     vec = a.take<float>(B * 6); nrm = a.take<float>(B); hout = a.take<float>(C * H); vel = a.take<float>(B * 6);
     ws = a.take<char>(cns_forward_workspace_bytes(bh));
   };
+  h->servo_valid = 0;      // this entry point reuses the staging buffer of cns_servo_step_host
   cns_batch d; float *hin, *vec, *nrm, *hout, *vel; void* ws;
   plan(ar, d, hin, vec, nrm, hout, vel, ws);
   if (ar.off > h->stage_dev_bytes) {

@@ -18,6 +18,15 @@ int csr_by_dst(const int64_t* ej, const int64_t* ei, int64_t n_edges, int64_t n_
 int graph_ptr_from_counts(const int64_t* num_clusters, int64_t n_graphs, int* graph_ptr, int* tmp,
                           int* scratch, cudaStream_t s);
 
+constexpr int PREP_SMALL_MAX = 4096;
+struct PrepSmallArgs {
+  int64_t n_clusters, n_graphs, n_e01, n_e11_cur, n_e11_tar;
+  const int64_t* num_clusters; const int64_t* ei;
+  const int64_t* cur_j; const int64_t* cur_i; const int64_t* tar_j; const int64_t* tar_i;
+  int* graph_ptr; int* clu_rowptr; int* cur_rowptr; int* cur_src; int* tar_rowptr; int* tar_src; int* err;
+};
+int prep_small(const PrepSmallArgs& a, cudaStream_t s);
+
 // ---- encoder.cu ---------------------------------------------------------------------------
 struct EncPreArgs {
   int64_t n_clusters;

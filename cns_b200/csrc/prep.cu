@@ -183,6 +183,79 @@ int graph_ptr_from_counts(const int64_t* num_clusters, int64_t n_graphs, int* gr
   return exclusive_scan_i32(tmp, n_graphs, graph_ptr, scratch, s);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small-batch fast path (servo loop, batch 1): every index structure of one forward in ONE
+// single-CTA launch instead of 13 - graph_ptr, cluster rowptr and both destination CSRs.
+// Requires n_clusters <= PREP_SMALL_MAX (degrees / cursors live in shared memory).
+// ---------------------------------------------------------------------------------------------
+__device__ void block_scan_inplace(int* v, int n, int* out /* n+1 */) {
+  // exclusive scan of v[0..n) into out[0..n], n <= PREP_SMALL_MAX, blockDim = 1024
+  __shared__ int carry_s;
+  __shared__ int tot_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int x = (i < n) ? v[i] : 0;
+    const int ex = block_exclusive_scan(x, &tot_s);
+    if (i < n) out[i] = ex + carry_s;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s += tot_s;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = carry_s;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024)
+prep_small_kernel(PrepSmallArgs p) {
+  __shared__ int deg[PREP_SMALL_MAX + 1];
+  __shared__ int cur[PREP_SMALL_MAX + 1];
+  const int tid = threadIdx.x;
+  const int C = (int)p.n_clusters, B = (int)p.n_graphs;
+  // graph_ptr = exclusive scan of num_clusters
+  for (int i = tid; i < B; i += 1024) deg[i] = (int)p.num_clusters[i];
+  __syncthreads();
+  block_scan_inplace(deg, B, p.graph_ptr);
+  // cluster rowptr from the sorted destination list
+  for (int64_t e = tid; e <= p.n_e01; e += 1024) {
+    const int64_t prev = (e == 0) ? -1 : p.ei[e - 1];
+    const int64_t cu = (e == p.n_e01) ? C : p.ei[e];
+    if (cu < prev || cu < 0 || cu > C || (e < p.n_e01 && cu >= C)) { atomicExch(p.err, 1); continue; }
+    for (int64_t r = prev + 1; r <= cu; ++r) p.clu_rowptr[r] = (int)e;
+  }
+  // the two destination CSRs
+  for (int which = 0; which < 2; ++which) {
+    const int64_t* ej = which ? p.tar_j : p.cur_j;
+    const int64_t* ei = which ? p.tar_i : p.cur_i;
+    const int64_t ne = which ? p.n_e11_tar : p.n_e11_cur;
+    int* rowptr = which ? p.tar_rowptr : p.cur_rowptr;
+    int* src = which ? p.tar_src : p.cur_src;
+    __syncthreads();
+    for (int i = tid; i <= C; i += 1024) { deg[i] = 0; cur[i] = 0; }
+    __syncthreads();
+    for (int64_t e = tid; e < ne; e += 1024) {
+      const int64_t i = ei[e];
+      if (i < 0 || i >= C) { atomicExch(p.err, 2); continue; }
+      atomicAdd(&deg[i], 1);
+    }
+    __syncthreads();
+    block_scan_inplace(deg, C, rowptr);
+    for (int64_t e = tid; e < ne; e += 1024) {
+      const int64_t i = ei[e];
+      if (i < 0 || i >= C) continue;
+      const int slot = rowptr[i] + atomicAdd(&cur[i], 1);
+      src[slot] = (int)ej[e];
+    }
+  }
+}
+
+int prep_small(const PrepSmallArgs& a, cudaStream_t s) {
+  prep_small_kernel<<<1, 1024, 0, s>>>(a);
+  CNS_LAUNCH_CHECK();
+  return CNS_OK;
+}
+
 }  // namespace cns
 
 using namespace cns;

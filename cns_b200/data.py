@@ -113,6 +113,44 @@ class GraphData(object):
         return int(self.num_nodes) if "index" in key else 0
 
 
+class DevicePrefetcher(object):
+    """Iterates host (ideally pinned) GraphData/Batch objects as device-resident ones, issuing the
+    host->device copy of item i+1 on a side stream while the caller computes on item i."""
+
+    def __init__(self, items, device, depth: int = 1):
+        self.items, self.device, self.depth = iter(items), torch.device(device), max(1, depth)
+        self.stream = torch.cuda.Stream(self.device)
+        self.queue = []
+
+    def _fill(self):
+        while len(self.queue) < self.depth + 1:
+            try:
+                host = next(self.items)
+            except StopIteration:
+                return
+            with torch.cuda.stream(self.stream):
+                dev = host.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            self.queue.append((dev, ev))
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        self._fill()
+        if not self.queue:
+            raise StopIteration
+        dev, ev = self.queue.pop(0)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for _, v in dev.items():
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                v.record_stream(cur)
+        self._fill()
+        return dev
+
+
 def _inc_kind(key: str) -> int:
     """0: no offset, 1: by num_nodes, 2: by num_clusters."""
     for cand in _INC_BY_NODES:

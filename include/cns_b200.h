@@ -145,6 +145,14 @@ int cns_graphvs_forward_host(cns_handle* h, const cns_batch* b_host, const float
                              float* vel_si_vec_host, float* vel_si_norm_host,
                              float* hidden_out_host, float* vel_host);
 
+/* One servo frame from HOST memory with the recurrent hidden state kept on the device inside the
+ * handle - GraphVSController.__call__ (controller.py:23-38) including its self.hidden bookkeeping:
+ * reset_hidden != 0 (new scene) or a changed cluster count start from the zero state.  Inputs are
+ * packed into one pinned block (one H2D copy), outputs come back in one D2H copy.  Synchronous.
+ * vel_host (B,6) is the post-processed velocity; the raw heads are optional. */
+int cns_servo_step_host(cns_handle* h, const cns_batch* b_host, int reset_hidden, float* vel_host,
+                        float* vel_si_vec_host, float* vel_si_norm_host);
+
 /* ---- per-op entry points (each is one stage of the forward; parity-tested alone) ---- */
 
 /* CSR by destination of an int64 (2,E) edge list (PyG flow source->target,

@@ -155,6 +155,28 @@ def test_host_pointer_entry_matches_device_entry(net):
     assert torch.equal(vec, ref[0].cpu()) and torch.equal(hid, ref[2].cpu()) and torch.equal(vel, ref.vel.cpu())
 
 
+def test_servo_controller_host_path(state_dict):
+    """GraphVSController on host GraphData (cns_servo_step_host: one staged copy in, hidden kept on the
+    device) reproduces the oracle's recurrent velocities, including the new-scene reset."""
+    from cns_b200.controller import GraphVSController
+    ctl = GraphVSController(os.path.join(ROOT, "checkpoints", "cns_state_dict.pth"), "cuda:0")
+    rng = np.random.default_rng(21)
+    np.random.seed(21)
+    scene = synth.Scene(rng, 150)
+    hid = None
+    for t in range(6):
+        d = scene.frame(0.1)
+        if t in (0, 4):
+            d.start_new_scene()
+            hid = None
+        vel = ctl(d)
+        ov, on, hid = cns_oracle.forward(state_dict, d, hid, dtype=torch.float64)
+        ovel = cns_oracle.postprocess((ov, on), d.tPo_norm.reshape(1))[0].numpy()
+        assert vel.shape == (6,) and vel.dtype == np.float32
+        assert np.abs(vel - ovel).max() < 1e-4 * np.abs(ovel).max()
+        scene.step(vel * 2)
+
+
 def test_full_size_batch_properties(net, state_dict):
     """BASELINE config: 1024 graphs x 512 keypoints.  The oracle is too slow for all of it, so:
     (1) spot-check 8 graphs against the oracle, (2) permuting the graphs of the batch permutes the
