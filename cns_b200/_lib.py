@@ -70,6 +70,8 @@ def _declare(lib):
         "cns_graph_mask_workspace_bytes": (sz, [i64, i64, i64]),
         "cns_graph_mask": (i32, [vp, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, i64, vp, vp, vp, sz, vp]),
         "cns_label_nearest": (i32, [vp, vp, i64, vp, vp, vp, vp]),
+        "cns_ap_workspace_bytes": (sz, [i64, i64, i64, i32]),
+        "cns_affinity_propagation": (i32, [vp, vp, vp, vp, i64, i64, i64, C.c_double, i32, i32, vp, vp, vp, vp, sz, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)   # AttributeError here == header / library mismatch: fail loudly

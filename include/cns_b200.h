@@ -199,6 +199,19 @@ int cns_graph_mask(const int64_t* belong, const int64_t* member_order, const int
                    uint8_t* cluster_mask, int64_t* counts_out,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Affinity Propagation message passing (the clustering behind cluster_points, graph_gen.py:104-106 ->
+ * sklearn AffinityPropagation(damping=0.9)) for a batch of G problems, bit-exact in fp64 with
+ * sklearn's loop.  S (sum n_g^2) is the similarity matrix as sklearn prepares it (median preference on
+ * the diagonal, noise added) - device; pt_off / mat_off (G+1) int64 prefix sums of n_g / n_g^2 - device;
+ * row_graph (sum n) int32 - device.  Outputs: E_out (sum n) u8 exemplar indicator and n_iter_out (G)
+ * on the device, converged_host (G) on the HOST (1 converged, 2 hit max_iter).  Synchronises. */
+size_t cns_ap_workspace_bytes(int64_t n_rows_total, int64_t n_mat_total, int64_t n_graphs, int conv_iter);
+int cns_affinity_propagation(const double* S, const int64_t* pt_off, const int64_t* mat_off,
+                             const int32_t* row_graph, int64_t n_graphs, int64_t n_rows_total,
+                             int64_t n_mat_total, double damping, int max_iter, int conv_iter,
+                             unsigned char* E_out, int32_t* n_iter_out, int32_t* converged_host,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* 1-NN keypoint -> exemplar labelling, the only nearest-neighbour search of the
  * reference's clustering (sklearn AffinityPropagation final assignment,
  * argmax_k -||x - e_k||^2 ).  points (N,2) f64 ; point_graph (N,) graph id of
