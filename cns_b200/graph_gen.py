@@ -111,6 +111,29 @@ def label_nearest_exemplar(points, exemplar_indices, device="cuda:0") -> np.ndar
 
 
 class GraphGenerator(object):
+    # "host": scikit-learn on the CPU exactly like the reference; "device": the same Affinity Propagation
+    # with its message passing on the GPU (cns_b200/cluster.py, label-identical to sklearn)
+    CLUSTER_BACKEND = "host"
+    CLUSTER_DEVICE = "cuda:0"
+
+    @classmethod
+    def build_many(cls, target_point_sets, device="cuda:0"):
+        """Generators for many targets with ONE batched device clustering call.  Labels equal the
+        reference's sequential construction as long as no set needs the KMeans(4) fallback (the
+        fallback draws from numpy's global RNG after, not between, the AP noise draws)."""
+        from .cluster import affinity_propagation_device
+        sets = [np.asarray(p) for p in target_point_sets]
+        big = [k for k, p in enumerate(sets) if len(p) > 16]
+        labels = dict(zip(big, affinity_propagation_device([sets[k] for k in big], device=device))) if big else {}
+        out = []
+        for k, p in enumerate(sets):
+            lab = labels.get(k)
+            if lab is not None and np.unique(lab).shape[0] < 4:
+                from sklearn.cluster import KMeans
+                lab = KMeans(n_clusters=4).fit_predict(p)
+            out.append(cls(p, labels=lab) if lab is not None else cls(p))
+        return out
+
     @classmethod
     def from_exemplars(cls, target_points, exemplar_indices, device="cuda:0"):
         """Graph whose clusters are the Voronoi cells of the given exemplar keypoints (labels computed
@@ -127,8 +150,13 @@ class GraphGenerator(object):
             self.yhat = np.asarray(labels)
             self.cluster_ids, self.cluster_points_count = np.unique(self.yhat, return_counts=True)
         elif n > 16:
-            self.yhat, self.cluster_ids, self.cluster_points_count = \
-                try_cluster_points(target_points, max_tries=3)
+            if self.CLUSTER_BACKEND == "device":
+                from .cluster import cluster_points_device
+                self.yhat, self.cluster_ids, self.cluster_points_count = \
+                    cluster_points_device(target_points, device=self.CLUSTER_DEVICE)
+            else:
+                self.yhat, self.cluster_ids, self.cluster_points_count = \
+                    try_cluster_points(target_points, max_tries=3)
         else:
             self.yhat = np.arange(n)
             self.cluster_ids = self.yhat.copy()

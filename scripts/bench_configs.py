@@ -68,6 +68,36 @@ if "c1" in which:
                          "cores": torch.get_num_threads()}
     out["C1_batch1_latency_N512"] = res
 
+if "c0" in which:
+    import warnings
+    from sklearn.cluster import AffinityPropagation
+    from cns_b200.cluster import affinity_propagation_device
+    res = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for n, reps in ((128, 5), (512, 3), (1024, 2), (2048, 1)):
+            rng = np.random.default_rng(n)
+            X = synth.project_norm(synth.sample_target_pose(rng), synth.sample_points(rng, n))
+            np.random.seed(0); t0 = time.perf_counter()
+            for _ in range(reps): ref = AffinityPropagation(damping=0.9).fit(X)
+            t_sk = (time.perf_counter() - t0) / reps
+            np.random.seed(0); affinity_propagation_device([X]); torch.cuda.synchronize()
+            np.random.seed(0); t0 = time.perf_counter()
+            for _ in range(reps): lab = affinity_propagation_device([X])[0]
+            t_dev = (time.perf_counter() - t0) / reps
+            np.random.seed(0); lab = affinity_propagation_device([X])[0]
+            np.random.seed(0); ref = AffinityPropagation(damping=0.9).fit(X)
+            res[str(n)] = {"sklearn_s": t_sk, "device_s": t_dev, "speedup": t_sk / t_dev, "n_iter": int(ref.n_iter_),
+                           "labels_identical": bool(np.array_equal(lab, ref.labels_))}
+        rng = np.random.default_rng(7)
+        sets = [synth.project_norm(synth.sample_target_pose(rng), synth.sample_points(rng, 512)) for _ in range(64)]
+        np.random.seed(1); t0 = time.perf_counter(); labs = affinity_propagation_device(sets); t_b = time.perf_counter() - t0
+        np.random.seed(1); t0 = time.perf_counter(); refs = [AffinityPropagation(damping=0.9).fit_predict(X) for X in sets[:8]]
+        t_s8 = time.perf_counter() - t0
+        res["batch_64x512"] = {"device_s_total": t_b, "sklearn_s_per_set": t_s8 / 8, "speedup": (t_s8 / 8 * 64) / t_b,
+                               "labels_identical_first8": bool(all(np.array_equal(a, b) for a, b in zip(labs[:8], refs)))}
+    out["C0_affinity_propagation"] = res
+
 if "c3" in which or "c4" in which:
     def make_windows(bs, n_frames, n_points, seed):
         rng = np.random.default_rng(seed); np.random.seed(seed)
