@@ -58,6 +58,72 @@ class GradBucket(object):
             self.flat.div_(dist.get_world_size(group))
 
 
+class _FusedObjectives(torch.autograd.Function):
+    """GraphVS.objectives as one kernel (`cns_objectives`): loss triple + gradients in a single launch."""
+
+    @staticmethod
+    def forward(ctx, vec, nrm, gt):
+        from . import _lib
+        lib = _lib.load()
+        vec_c, nrm_c, gt_c = vec.detach().contiguous().float(), nrm.detach().contiguous().float(), gt.contiguous().float()
+        out = torch.empty(3, dtype=torch.float32, device=vec.device)
+        dvec, dnrm = torch.empty_like(vec_c), torch.empty_like(nrm_c)
+        _lib.check(lib.cns_objectives(_lib.ptr(vec_c), _lib.ptr(nrm_c), _lib.ptr(gt_c), vec_c.shape[0], 1.0,
+                                      _lib.ptr(out), _lib.ptr(dvec), _lib.ptr(dnrm), _lib.stream_ptr(vec.device)),
+                   "cns_objectives")
+        ctx.save_for_backward(dvec, dnrm)
+        ctx.mark_non_differentiable(out)
+        return out[2].clone(), out
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_out):
+        dvec, dnrm = ctx.saved_tensors
+        return dvec * g_loss, dnrm * g_loss, None
+
+
+def fused_objectives(raw_pred, data):
+    """(loss, [dir, norm, total] device tensor) - same values as functions.objectives, no host sync."""
+    gt = data.vel_si if not isinstance(data, dict) else data["vel_si"]
+    return _FusedObjectives.apply(raw_pred[0], raw_pred[1], gt.to(raw_pred[0].device))
+
+
+class FusedClipAdamW(object):
+    """clip_grad_norm_(10) + the reference's two AdamW groups as one fused update (`cns_clip_adamw`) over a
+    flat parameter buffer.  Parameters of `net` are re-pointed at views of that buffer."""
+
+    def __init__(self, net, bucket: "GradBucket", lr=5e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
+                 max_norm=10.0):
+        from . import _lib
+        self.lib, self._lib = _lib.load(), _lib
+        self.net = net
+        self.params = bucket.params
+        dev = self.params[0].device
+        self.flat = torch.cat([p.detach().reshape(-1) for p in self.params]).contiguous()
+        decay_ids = {id(p) for p in net.get_parameter_groups()[0]}
+        mask = torch.cat([torch.full((p.numel(),), 1 if id(p) in decay_ids else 0, dtype=torch.uint8) for p in self.params])
+        self.decay_mask = mask.to(dev)
+        off = 0
+        for p in self.params:
+            p.data = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.bucket = bucket
+        self.m, self.v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        self.lr, self.wd, self.betas, self.eps, self.max_norm, self.t = lr, weight_decay, betas, eps, max_norm, 0
+        self.ws = torch.empty(self.lib.cns_clip_adamw_workspace_bytes(), dtype=torch.uint8, device=dev)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def step(self, grad_div: float = 1.0):
+        self.t += 1
+        L = self._lib
+        L.check(self.lib.cns_clip_adamw(L.ptr(self.flat), L.ptr(self.bucket.flat), L.ptr(self.m), L.ptr(self.v),
+                                        L.ptr(self.decay_mask), self.flat.numel(), self.max_norm, self.lr, self.betas[0],
+                                        self.betas[1], self.eps, self.wd, self.t, float(grad_div), L.ptr(self.grad_norm),
+                                        L.ptr(self.ws), self.ws.numel(), L.stream_ptr(self.flat.device)), "cns_clip_adamw")
+        # the kernel updated the parameter storage behind torch's back: make GraphVS re-pack its weights
+        for ent in self.net._handles.values():
+            ent[1] = None
+
+
 def shard_range(n_items: int, rank: int, world: int):
     """Contiguous, balanced split of `n_items` scenes over `world` ranks."""
     base, rem = divmod(n_items, world)
@@ -69,11 +135,16 @@ class TBPTTStepper(object):
     """One optimizer update from a window of recurrent frames."""
 
     def __init__(self, net, optimizers: Optional[Dict[str, torch.optim.Optimizer]] = None, clip_norm: float = 10.0,
-                 group=None):
+                 group=None, fused: bool = False, lr: float = 5e-4, weight_decay: float = 1e-4):
         self.net = net
-        self.optimizers = optimizers if optimizers is not None else make_optimizers(net)
         self.clip_norm = clip_norm
         self.bucket = GradBucket(list(net.parameters()))
+        self.fused = fused
+        if fused:       # fused loss + fused clip/AdamW kernels (no torch optimizer objects)
+            self.optimizers = {}
+            self.fused_opt = FusedClipAdamW(net, self.bucket, lr=lr, weight_decay=weight_decay, max_norm=clip_norm)
+        else:
+            self.optimizers = optimizers if optimizers is not None else make_optimizers(net, lr, weight_decay)
         self.group = group
         self.hidden = None
 
@@ -85,6 +156,11 @@ class TBPTTStepper(object):
                 self.hidden = None
             pred = self.net(data, self.hidden)
             self.hidden = pred[2]
+            if self.fused:
+                loss_t, triple = fused_objectives(pred, data)
+                losses.append(loss_t)
+                logs.append((triple[0], triple[1]))
+                continue
             vec, nrm = pred[0], pred[1]
             gt = data.vel_si.to(vec)
             dir_loss = (1 - torch.nn.functional.cosine_similarity(vec, gt, dim=-1)).mean()
@@ -101,10 +177,17 @@ class TBPTTStepper(object):
         loss, _ = self.window_loss(frames, mean=mean)
         loss.backward()
         self.bucket.rebind()
-        self.bucket.allreduce_mean(self.group)
-        torch.nn.utils.clip_grad_norm_(self.bucket.params, self.clip_norm)
-        for opt in self.optimizers.values():
-            opt.step()
+        if self.fused:
+            world = 1
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM, group=self.group)
+                world = dist.get_world_size(self.group)
+            self.fused_opt.step(grad_div=float(world))      # averages, clips and steps in one kernel
+        else:
+            self.bucket.allreduce_mean(self.group)
+            torch.nn.utils.clip_grad_norm_(self.bucket.params, self.clip_norm)
+            for opt in self.optimizers.values():
+                opt.step()
         if self.hidden is not None:
             self.hidden = self.hidden.detach()          # truncate BPTT (train_gvs_short_seq.py:48)
         return loss.detach()

@@ -132,6 +132,20 @@ int cns_graphvs_backward(cns_handle* h, const cns_batch* b, const float* hidden_
                          float* d_hidden_in, float* grad_flat, const void* save, size_t save_bytes,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Loss of GraphVS.objectives (functions.py:41-65, gt_si=True, weight=1) and, when d_vec / d_norm are given,
+ * grad_scale * d loss / d (vel_si_vec, vel_si_norm), in one launch.  loss_out3 (device): dir, norm, total. */
+int cns_objectives(const float* vel_si_vec, const float* vel_si_norm, const float* vel_si_gt, int64_t n_graphs,
+                   float grad_scale, float* loss_out3, float* d_vec, float* d_norm, void* stream);
+
+/* clip_grad_norm_(max_norm) + AdamW over flat parameter / gradient / moment buffers (trainer.py:96-100,
+ * train_cns.py:65-69); decay_mask (n) u8 selects the decayed group.  `grad_div` pre-divides the gradients
+ * (world size after a summing all-reduce).  grad_norm_out: optional device float (pre-clip norm). */
+size_t cns_clip_adamw_workspace_bytes(void);
+int cns_clip_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                   const unsigned char* decay_mask, int64_t n, float max_norm, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int64_t step, float grad_div, float* grad_norm_out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* Error word left in `workspace` by the index-preparation kernels of the last forward on
  * `stream` (unsorted l0_to_l1 edges, out-of-range indices).  Synchronises `stream`. */
 int cns_forward_status(const void* workspace, void* stream);
