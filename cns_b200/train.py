@@ -156,6 +156,7 @@ class TBPTTStepper(object):
                 self.hidden = None
             pred = self.net(data, self.hidden)
             self.hidden = pred[2]
+            self.last_pred = pred          # closed-loop callers read the prediction between frames
             if self.fused:
                 loss_t, triple = fused_objectives(pred, data)
                 losses.append(loss_t)
