@@ -79,11 +79,14 @@ class GraphData(object):
     def set_distance_scale(self, dist_scale):
         self._f["tPo_norm"] = torch.tensor(float(dist_scale), dtype=torch.float32)
 
-    def to(self, device, non_blocking: bool = False):
+    def to(self, device, non_blocking: bool = False, fields=None):
+        """Like PyG's Data.to.  `fields` (optional) restricts the copy to the named tensor fields - e.g.
+        `GraphVS.INPUT_FIELDS`, the tensors the policy reads; other tensor fields are dropped."""
         out = copy.copy(self)
         object.__setattr__(out, "_f", {
             k: (v.to(device, non_blocking=non_blocking) if isinstance(v, torch.Tensor) else v)
-            for k, v in self._f.items()})
+            for k, v in self._f.items()
+            if fields is None or k in fields or not isinstance(v, torch.Tensor)})
         return out
 
     def pin_memory(self):
@@ -117,8 +120,9 @@ class DevicePrefetcher(object):
     """Iterates host (ideally pinned) GraphData/Batch objects as device-resident ones, issuing the
     host->device copy of item i+1 on a side stream while the caller computes on item i."""
 
-    def __init__(self, items, device, depth: int = 1):
+    def __init__(self, items, device, depth: int = 1, fields=None):
         self.items, self.device, self.depth = iter(items), torch.device(device), max(1, depth)
+        self.fields = fields
         self.stream = torch.cuda.Stream(self.device)
         self.queue = []
 
@@ -129,7 +133,7 @@ class DevicePrefetcher(object):
             except StopIteration:
                 return
             with torch.cuda.stream(self.stream):
-                dev = host.to(self.device, non_blocking=True)
+                dev = host.to(self.device, non_blocking=True, fields=self.fields)
             ev = torch.cuda.Event()
             ev.record(self.stream)
             self.queue.append((dev, ev))

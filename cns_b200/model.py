@@ -115,6 +115,11 @@ def _field(data, key, default=None):
 
 
 class GraphVS(nn.Module):
+    # the GraphData / Batch tensors forward() reads (graph_vs.py:285-307); `vel_si` / `vel` ride along for the loss
+    INPUT_FIELDS = ("x_cur", "x_tar", "pos_cur", "pos_tar", "l0_to_l1_edge_index_j_cur", "l0_to_l1_edge_index_i_cur",
+                    "l1_dense_edge_index_cur", "l1_dense_edge_index_tar", "cluster_mask", "cluster_centers_index",
+                    "num_clusters", "tPo_norm", "new_scene", "vel_si", "vel")
+
     def __init__(self, input_dim, pos_dim, hidden_dim=128, regress_norm=True, precision="fp32"):
         super().__init__()
         if (input_dim, pos_dim, hidden_dim) != (2, 2, 128) or not regress_norm:
@@ -233,7 +238,7 @@ class GraphVS(nn.Module):
             cmask = (cmask != 0).view(torch.uint8)
         keep.append(cmask)
         ctr = t("cluster_centers_index", torch.int64)
-        batch = t("batch", torch.int64, required=False)
+        batch = None      # the node->graph vector is not needed: graph segments come from num_clusters
         ncl = _field(data, "num_clusters")
         ncl = ncl.reshape(-1).to(torch.int64).contiguous()
         keep.append(ncl)
