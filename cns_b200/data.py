@@ -125,6 +125,31 @@ class DevicePrefetcher(object):
         self.fields = fields
         self.stream = torch.cuda.Stream(self.device)
         self.queue = []
+        # persistent staging slots (no allocator traffic in steady state): slot -> {field: byte buffer}
+        self.n_slots = self.depth + 2
+        self.slots = [dict() for _ in range(self.n_slots)]
+        self.slot_free = [None] * self.n_slots          # event: the consumer is done with this slot
+        self.next_slot = 0
+        self.last = None                                # (slot index) handed out most recently
+
+    def _stage(self, host, slot):
+        bufs = self.slots[slot]
+        out = {}
+        for k, v in host.items():
+            if not isinstance(v, torch.Tensor):
+                out[k] = v
+                continue
+            if self.fields is not None and k not in self.fields:
+                continue
+            nbytes = v.numel() * v.element_size()
+            buf = bufs.get(k)
+            if buf is None or buf.numel() < nbytes:
+                buf = torch.empty(max(int(nbytes * 1.25), 16), dtype=torch.uint8, device=self.device)
+                bufs[k] = buf
+            dst = buf[:nbytes].view(v.dtype).view(v.shape)
+            dst.copy_(v, non_blocking=True)
+            out[k] = dst
+        return type(host)(**out)
 
     def _fill(self):
         while len(self.queue) < self.depth + 1:
@@ -132,25 +157,31 @@ class DevicePrefetcher(object):
                 host = next(self.items)
             except StopIteration:
                 return
+            slot = self.next_slot
+            self.next_slot = (self.next_slot + 1) % self.n_slots
             with torch.cuda.stream(self.stream):
-                dev = host.to(self.device, non_blocking=True, fields=self.fields)
+                if self.slot_free[slot] is not None:
+                    self.stream.wait_event(self.slot_free[slot])     # its previous consumer has finished
+                dev = self._stage(host, slot)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-            self.queue.append((dev, ev))
+            self.queue.append((dev, ev, slot))
 
     def __iter__(self):
         return self
 
     def __next__(self):
+        cur = torch.cuda.current_stream(self.device)
+        if self.last is not None:          # everything the caller enqueued on the previous item is ordered before this
+            done = torch.cuda.Event()
+            done.record(cur)
+            self.slot_free[self.last] = done
         self._fill()
         if not self.queue:
             raise StopIteration
-        dev, ev = self.queue.pop(0)
-        cur = torch.cuda.current_stream(self.device)
+        dev, ev, slot = self.queue.pop(0)
         cur.wait_event(ev)
-        for _, v in dev.items():
-            if isinstance(v, torch.Tensor) and v.is_cuda:
-                v.record_stream(cur)
+        self.last = slot
         self._fill()
         return dev
 
