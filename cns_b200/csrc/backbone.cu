@@ -101,11 +101,12 @@ int linear(const LinearArgs& a, cudaStream_t s) {
 // =============================================================================================
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// One destination row, one warp.  Q rows of sources inside [q_row0, q_row1) are read from the staged
-// shared-memory copy `sq` (row-major, F floats per row); any other source falls back to global memory.
 template <int VPL>
-__device__ __forceinline__ void edgeconv_row(const EdgeConvArgs& p, int64_t row, int lane, const float* sq, int q_row0,
-                                             int q_row1) {
+__global__ void __launch_bounds__(256)
+edgeconv_max_kernel(EdgeConvArgs p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.n_rows) return;
   constexpr int F = VPL * 128;
   const int beg = p.rowptr[row], end = p.rowptr[row + 1];
   float4 best[VPL];
@@ -120,9 +121,7 @@ __device__ __forceinline__ void edgeconv_row(const EdgeConvArgs& p, int64_t row,
     int cnt = min(32, end - base);
     for (int t = 0; t < cnt; ++t) {
       int j = __shfl_sync(0xffffffffu, my, t);
-      const float4* q = (j >= q_row0 && j < q_row1)
-                            ? reinterpret_cast<const float4*>(sq + (size_t)(j - q_row0) * F)
-                            : reinterpret_cast<const float4*>(p.pq + (size_t)j * 2 * F + F);
+      const float4* q = reinterpret_cast<const float4*>(p.pq + (size_t)j * 2 * F + F);
 #pragma unroll
       for (int v = 0; v < VPL; ++v) {
         float4 x = q[v * 32 + lane];
@@ -172,60 +171,11 @@ __device__ __forceinline__ void edgeconv_row(const EdgeConvArgs& p, int64_t row,
   }
 }
 
-// generic path: any CSR, sources read through L2
-template <int VPL>
-__global__ void __launch_bounds__(256)
-edgeconv_max_kernel(EdgeConvArgs p) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= p.n_rows) return;
-  edgeconv_row<VPL>(p, row, lane, nullptr, 0, 0);
-}
-
-// graph-staged path: one CTA per graph copies the graph's Q rows into shared memory once (coalesced
-// float4), so the deg x F gather of every destination row is served on-chip and HBM sees each PQ row
-// exactly once.  Graphs whose Q block exceeds the shared-memory budget run the generic gather.
-constexpr int EC_STAGE_BYTES = 48 * 1024;   // per CTA: C_g <= 96 rows (F=128) / 48 rows (F=256), 4 CTAs per SM
-
-template <int VPL>
-__global__ void __launch_bounds__(256)
-edgeconv_max_graph_kernel(EdgeConvArgs p) {
-  extern __shared__ __align__(16) float sq[];
-  constexpr int F = VPL * 128;
-  const int g = blockIdx.x;
-  const int r0 = p.graph_ptr[g], r1 = p.graph_ptr[g + 1];
-  const int n = r1 - r0;
-  if (n <= 0) return;
-  const bool staged = (size_t)n * F * sizeof(float) <= (size_t)EC_STAGE_BYTES;
-  if (staged) {
-    const int total = n * (F / 4);
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-      const int r = idx / (F / 4), c4 = idx % (F / 4);
-      reinterpret_cast<float4*>(sq)[idx] = reinterpret_cast<const float4*>(p.pq + (size_t)(r0 + r) * 2 * F + F)[c4];
-    }
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int row = r0 + warp; row < r1; row += nw) edgeconv_row<VPL>(p, row, lane, sq, staged ? r0 : 0, staged ? r1 : 0);
-}
-
 int edgeconv_max(const EdgeConvArgs& a, cudaStream_t s) {
   if (a.n_rows == 0) return CNS_OK;
   CNS_REQUIRE(a.f_out == 128 || a.f_out == 256, "edgeconv_max: f_out must be 128 or 256");
   CNS_REQUIRE(a.mode != EC_GATES || a.f_out == 256, "gates need f_out = 256");
   CNS_REQUIRE(a.mode != EC_CANDIDATE || a.f_out == 128, "candidate needs f_out = 128");
-  if (a.graph_ptr && a.n_graphs > 0) {
-    static bool configured = false;
-    if (!configured) {
-      CNS_CUDA_CHECK(cudaFuncSetAttribute(edgeconv_max_graph_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, EC_STAGE_BYTES));
-      CNS_CUDA_CHECK(cudaFuncSetAttribute(edgeconv_max_graph_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, EC_STAGE_BYTES));
-      configured = true;
-    }
-    if (a.f_out == 128) edgeconv_max_graph_kernel<1><<<(unsigned)a.n_graphs, 256, EC_STAGE_BYTES, s>>>(a);
-    else edgeconv_max_graph_kernel<2><<<(unsigned)a.n_graphs, 256, EC_STAGE_BYTES, s>>>(a);
-    CNS_LAUNCH_CHECK();
-    return CNS_OK;
-  }
   const int warps = 8;
   int grid = ceil_div(a.n_rows, warps);
   if (a.f_out == 128) edgeconv_max_kernel<1><<<grid, warps * 32, 0, s>>>(a);

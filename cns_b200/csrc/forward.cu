@@ -177,7 +177,6 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     if ((r = pq_linear(x, nullptr, wt, wp, bias, 2 * H, img, H)) != CNS_OK) return r;
     EdgeConvArgs ec{};
     ec.n_rows = C; ec.f_out = H; ec.mode = EC_PLAIN; ec.pq = f.pq; ec.rowptr = f.cur_rowptr; ec.src = f.cur_src;
-    ec.graph_ptr = f.graph_ptr; ec.n_graphs = B;
     ec.out = conv; ec.argmax = arg;
     if ((r = edgeconv_max(ec, s)) != CNS_OK) return r;
     GraphNormArgs gn{};
@@ -203,7 +202,6 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   {
     EdgeConvArgs ec{};
     ec.n_rows = C; ec.f_out = 2 * H; ec.mode = EC_GATES; ec.pq = f.pq; ec.rowptr = f.tar_rowptr; ec.src = f.tar_src;
-    ec.graph_ptr = f.graph_ptr; ec.n_graphs = B;
     ec.h = hidden_in; ec.hr = f.hr; ec.u = f.u; ec.argmax = f.argg; ec.act = f.g;
     RUN(edgeconv_max(ec, s));
   }
@@ -211,7 +209,6 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   {
     EdgeConvArgs ec{};
     ec.n_rows = C; ec.f_out = H; ec.mode = EC_CANDIDATE; ec.pq = f.pq; ec.rowptr = f.cur_rowptr; ec.src = f.cur_src;
-    ec.graph_ptr = f.graph_ptr; ec.n_graphs = B;
     ec.h = hidden_in; ec.u_in = f.u; ec.h_out = hidden_out; ec.argmax = f.argk; ec.act = f.ht;
     RUN(edgeconv_max(ec, s));
   }

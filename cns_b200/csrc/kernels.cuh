@@ -98,7 +98,6 @@ struct EdgeConvArgs {
   float* hr; float* u;     // EC_GATES: h * r (n,128), update gate (n,128)
   const float* u_in;       // EC_CANDIDATE
   float* h_out;            // EC_CANDIDATE: (1-u) h + u tanh(.)
-  const int* graph_ptr; int64_t n_graphs;   // optional: row ranges of the graphs -> shared-memory staged path
   int* argmax;             // optional (n, f): winning source per channel (training)
   float* act;              // optional: post-activation values kept for backward
 };
