@@ -55,6 +55,7 @@ struct TcArgs {
   EncEdgeArgs e;
   const unsigned char* w_img;   // 5 swizzled 16-bit weight tiles
   int n_tiles;                  // edge tiles of TN edges
+  int tiles_per_chunk;          // consecutive tiles handled by one slot (per side)
 };
 
 // =================================================================================================
@@ -77,7 +78,6 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
 
   const EncEdgeArgs& p = args.e;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int total_tiles = args.n_tiles * 2;                      // x 2 sides
   if (warp == 0) {
     if (lane == 0) {
       mbar_init(smem_u32(&bars[0]), 1);
@@ -172,20 +172,30 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     // the index loads are issued before the producer math of the current tile and the dependent
     // coordinate gathers right after it, so both latencies hide behind the epilogues.
     const int pe = t % TN, kp = t / TN;            // channels [kp*TN, kp*TN + TN)
-    auto tile_of = [&](int it) { return (it * SLOTS + s) * (int)gridDim.x + (int)blockIdx.x; };
+    // Work assignment: the 2 * n_tiles (side, edge tile) items are cut into gridDim.x * SLOTS contiguous
+    // chunks, one per slot, the first half of the chunks on the current-frame side, the second half on
+    // the target side.  Consecutive tiles in one slot let a cluster cut by a tile boundary carry its
+    // running (max, sum, acc) in registers; only chunk boundaries leave partials for enc_finish.
+    const int n_chunks_side = ((int)gridDim.x * SLOTS) / 2;
+    const int chunk_q = (int)blockIdx.x * SLOTS + s;
+    const int side = chunk_q / n_chunks_side;
+    const int chunk = chunk_q - side * n_chunks_side;
+    const int tpc = args.tiles_per_chunk;
+    const int t_begin = chunk * tpc, t_end = min(t_begin + tpc, args.n_tiles);
+    auto tile_of = [&](int it) { return t_begin + it; };
     int n_j = 0, n_cid = -1;                       // next tile: source keypoint / cluster of edge pe
     float2 n_f = make_float2(0.f, 0.f), n_ps = n_f, n_pt = n_f, n_pc = n_f;
     auto fetch_index = [&](int g) {
       n_cid = -1; n_j = 0;
-      if (g < total_tiles) {
-        const int64_t e = (int64_t)(g >> 1) * TN + pe;
+      if (g < t_end) {
+        const int64_t e = (int64_t)g * TN + pe;
         if (e < p.n_e01) { n_j = (int)p.ej[e]; n_cid = (int)p.ei[e]; }
       }
     };
     auto fetch_coords = [&](int g) {
       if (n_cid >= 0) {
-        const float* __restrict__ fsrc = (g & 1) ? p.x_tar : p.x_cur;
-        const float* __restrict__ psrc = (g & 1) ? p.pos_tar : p.pos_cur;
+        const float* __restrict__ fsrc = side ? p.x_tar : p.x_cur;
+        const float* __restrict__ psrc = side ? p.pos_tar : p.pos_cur;
         n_f = reinterpret_cast<const float2*>(fsrc)[n_j];
         n_ps = reinterpret_cast<const float2*>(psrc)[n_j];
         n_pt = reinterpret_cast<const float2*>(p.pos_tar)[n_j];
@@ -195,11 +205,27 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     fetch_index(tile_of(0));
     fetch_coords(tile_of(0));
 
+    // running softmax state of the cluster that is open at the end of a tile (carried to the next tile)
+    float run_m = 0.f, run_s = 0.f, run_a = 0.f;
+    int run_seg = -1;
+    int64_t run_beg = 0;                           // global edge index where the open segment started (in this chunk)
+    float* const out_side = p.clu_feat + (size_t)side * p.n_clusters * H;
+    float* const part_side = p.partial + (size_t)side * p.n_slots * 3 * H;
+    auto flush_run = [&](int64_t g_end) {
+      const float ab = fmaf(b_p1, run_s, run_a);
+      const bool complete = (p.clu_rowptr[run_seg] == (int)run_beg) && (p.clu_rowptr[run_seg + 1] == (int)g_end);
+      if (complete) {
+        out_side[(size_t)run_seg * H + t] = fmaxf(ab / (run_s + 1e-16f), 0.f);
+      } else {
+        float* slot = part_side + ((size_t)run_seg + chunk) * 3 * H;
+        slot[t] = run_m + b_a1; slot[H + t] = run_s; slot[2 * H + t] = ab;
+      }
+    };
+
     for (int it = 0;; ++it) {
       const int g = tile_of(it);
-      if (g >= total_tiles) break;
-      const int side = g & 1;
-      const int64_t e0 = (int64_t)(g >> 1) * TN;
+      if (g >= t_end) break;
+      const int64_t e0 = (int64_t)g * TN;
       const int n_valid = (int)min((int64_t)TN, p.n_e01 - e0);
 
       // ---- producer: x -> buf0, hp -> buf1 ---------------------------------------------------------
@@ -310,22 +336,6 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
       mbar_wait(done, done_parity); done_parity ^= 1;
       tc_fence_after();
       {
-        float* out = p.clu_feat + (size_t)side * p.n_clusters * H;
-        float* part = p.partial + (size_t)side * p.n_slots * 3 * H;
-        const int64_t piece = g >> 1;
-        float m = 0.f, ssum = 0.f, a = 0.f;
-        int seg_beg = 0;
-        auto flush = [&](int e_beg, int e_end) {
-          const int seg = ci[e_beg];
-          const float ab = fmaf(b_p1, ssum, a);
-          const bool complete = (p.clu_rowptr[seg] == (int)(e0 + e_beg)) && (p.clu_rowptr[seg + 1] == (int)(e0 + e_end));
-          if (complete) {
-            out[(size_t)seg * H + t] = fmaxf(ab / (ssum + 1e-16f), 0.f);
-          } else {
-            float* slot = part + ((size_t)seg + piece) * 3 * H;
-            slot[t] = m + b_a1; slot[H + t] = ssum; slot[2 * H + t] = ab;
-          }
-        };
 #pragma unroll
         for (int c0 = 0; c0 < TN; c0 += 32) {
           float lg[32], vv[32];
@@ -338,22 +348,24 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
             const int e = c0 + q;
             if (e < n_valid) {
               const float l = lg[q], v = vv[q];
-              if (mask & (1u << q)) {
-                if (e > 0) flush(seg_beg, e);
-                seg_beg = e; m = l; ssum = 1.f; a = v;
+              // edge 0 of a tile opens a new segment only if its cluster differs from the carried one
+              const bool start = (e == 0) ? (ci[0] != run_seg) : ((mask >> q) & 1u);
+              if (start) {
+                if (run_seg >= 0) flush_run(e0 + e);
+                run_seg = ci[e]; run_beg = e0 + e; run_m = l; run_s = 1.f; run_a = v;
               } else {
-                const float d = l - m;
+                const float d = l - run_m;
                 const float ex = ex2_approx(-fabsf(d) * LOG2E);
                 const bool up = d > 0.f;
                 const float sc = up ? ex : 1.f, pr = up ? 1.f : ex;
-                ssum = fmaf(ssum, sc, pr);
-                a = fmaf(a, sc, pr * v);
-                m = fmaxf(m, l);
+                run_s = fmaf(run_s, sc, pr);
+                run_a = fmaf(run_a, sc, pr * v);
+                run_m = fmaxf(run_m, l);
               }
             }
           }
         }
-        if (n_valid > 0) flush(seg_beg, n_valid);
+        if (g + 1 >= t_end && run_seg >= 0) { flush_run(e0 + n_valid); run_seg = -1; }   // chunk end
       }
       named_bar(1 + s, 128);      // everyone is done with ci[] before the next tile overwrites it
     }
@@ -380,13 +392,31 @@ static int launch_tc(const EncEdgeArgs& a, const unsigned char* w_img, const cns
   ta.e = a;
   ta.w_img = w_img;
   ta.n_tiles = ceil_div(a.n_e01, TN);
-  const int total = ta.n_tiles * 2;
+  int grid, tpc;
+  tc_chunking(a.n_e01, TN, h->sm_count, &grid, &tpc);
+  ta.tiles_per_chunk = tpc;
   const int slots = 128 / TN;
-  int grid = h->sm_count;
-  if (grid * slots > total) grid = (total + slots - 1) / slots;
   kern<<<grid, 128 * slots, TC_SMEM_BYTES, s>>>(ta, *reinterpret_cast<const TcSmallW*>(h->tc_small_host));
   CNS_LAUNCH_CHECK();
   return CNS_OK;
+}
+
+// grid size and tiles per slot-chunk for n_e01 edges: (grid * slots) / 2 contiguous chunks per side
+void tc_chunking(int64_t n_e01, int tile_n, int sm_count, int* grid, int* tiles_per_chunk) {
+  const int slots = 128 / tile_n;
+  const int n_tiles = ceil_div(n_e01, tile_n);
+  int g = sm_count;
+  const int want = ceil_div(2 * (int64_t)n_tiles, slots);
+  if (g > want) g = want > 0 ? want : 1;
+  const int chunks_side = (g * slots) / 2;
+  *grid = g;
+  *tiles_per_chunk = ceil_div(n_tiles > 0 ? n_tiles : 1, chunks_side);
+}
+
+int tc_piece_edges(int64_t n_e01, const cns_handle* h) {
+  int grid, tpc;
+  tc_chunking(n_e01, h->tc_tile_n, h->sm_count, &grid, &tpc);
+  return tpc * h->tc_tile_n;
 }
 
 int tc_pack_weights(cns_handle* h, cudaStream_t s) {

@@ -137,7 +137,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
 
   EncFinishArgs ef{};
   ef.n_clusters = C; ef.n_slots = f.n_slots;
-  ef.piece_e = (h->precision == CNS_PREC_FP32) ? ENC_PIECE_E : h->tc_tile_n; ef.clu_rowptr = f.clu_rowptr; ef.partial = f.partial;
+  ef.piece_e = (h->precision == CNS_PREC_FP32) ? ENC_PIECE_E : tc_piece_edges(b->n_e01, h); ef.clu_rowptr = f.clu_rowptr; ef.partial = f.partial;
   ef.clu_feat = f.clu_feat; ef.out_t = pk.out_t; ef.b_out = h->P(P_OUT_B); ef.cluster_mask = b->cluster_mask;
   ef.x_clu = f.x_clu;
   // Cluster-level GEMMs (7 % of the FLOPs) go to the tensor cores only in f16 mode: with bf16's 8-bit

@@ -51,6 +51,8 @@ struct EncEdgeArgs {
 int enc_edge_fp32(const EncEdgeArgs& a, cudaStream_t s);
 int enc_edge_tc(const EncEdgeArgs& a, int precision, const cns_handle* h, cudaStream_t s);
 int tc_pack_weights(cns_handle* h, cudaStream_t s);
+void tc_chunking(int64_t n_e01, int tile_n, int sm_count, int* grid, int* tiles_per_chunk);
+int tc_piece_edges(int64_t n_e01, const cns_handle* h);   // edges per softmax piece (= slot chunk) of enc_edge_tc
 
 struct EncFinishArgs {
   int64_t n_clusters, n_slots;
