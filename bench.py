@@ -9,8 +9,11 @@ graphs; inference needs no collective).  One "step" = one GraphVS forward (+ fus
 over one 1024-graph batch.
 
   value : graphs/s with the batches already resident in HBM (CUDA events, max over ranks).
-  e2e   : the same through the public API with HOST (pinned) GraphData: Batch.to(device) every
-          step + the forward + a device->host read of the (B,6) velocities.
+  e2e   : the same through the public API from HOST (pinned) memory, servo form (BatchedServo.step):
+          the target-side graphs are per-scene state resident on the device (the reference's Midend
+          builds them once per target), a step copies the current keypoint coordinates + visibility
+          in, masks the graphs on the device, runs the forward and reads the (B,6) velocities back.
+          e2e.full_graph: GraphVS.forward on a prebuilt host Batch copied whole every step.
   roofline     : the dominant kernel (encoder edge kernel), timed live with CUDA events on its
                  launching stream (cns_profile_begin/end).
   cpu_baseline : the oracle (CPU port of the reference forward) on a bounded sample of the same
@@ -112,7 +115,7 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.sm), "source": self.source}
 
 
-def build_batches(n_graphs, n_points, seed, n_batches):
+def build_batches(n_graphs, n_points, seed, n_batches, with_scenes=False):
     """`n_batches` host batches: the same scenes (clustered once) observed at successive frames."""
     from cns_b200 import synth
     from cns_b200.data import Batch
@@ -122,7 +125,7 @@ def build_batches(n_graphs, n_points, seed, n_batches):
         out.append(Batch.from_data_list([s.frame(MISSING) for s in scenes]))
         for s in scenes:    # move every camera a little so each batch holds different coordinates
             s.step(synth.pbvs_straight(s.cur_wcT, s.tar_wcT) * 2)
-    return out
+    return (out, scenes) if with_scenes else out
 
 
 def tensor_bytes(batch):
@@ -186,7 +189,8 @@ def main():
     lib = _lib.load()
     net = ckpt.load_model(os.path.join(ROOT, "checkpoints", "cns.pth"), dev, precision=args.precision)
 
-    host = [b.pin_memory() for b in build_batches(args.graphs, args.points, 2022 + rank, N_ROTATE)]
+    host, scenes = build_batches(args.graphs, args.points, 2022 + rank, N_ROTATE, with_scenes=True)
+    host = [b.pin_memory() for b in host]
     resident = [b.to(dev) for b in host]
     n_edges = [int(b.l0_to_l1_edge_index_j_cur.numel()) for b in host]
     h2d = sum(v.numel() * v.element_size() for k, v in host[0].items()
@@ -245,9 +249,32 @@ def main():
         vel = pending.cpu()
         f1.record()
         barrier()
-        e2e_ms = max_over_ranks(f0.elapsed_time(f1))
+        full_ms = max_over_ranks(f0.elapsed_time(f1))
+        e2e_full = args.graphs * world * args.steps / (full_ms * 1e-3)
+        d2h_full = vel.numel() * vel.element_size()
+
+        # ---------------- end to end, servo form: target graphs resident, a frame ships keypoints ---
+        # BatchedServo = the reference's Midend split (graph built once per target, masked per frame):
+        # per step H2D of the current keypoint coordinates + visibility, per-frame graph masking on the
+        # device, forward, D2H of the velocities; each step waits for its own result (closed loop).
+        from cns_b200.servo import BatchedServo
+        servo = BatchedServo(net, [s.generator for s in scenes], [s.tPo_norm for s in scenes], dev)
+        frames = [(b.pos_cur, b.node_mask.view(torch.uint8)) for b in host]     # pinned host tensors
+        for i in range(args.warmup):
+            servo.reset()
+            vel = servo.step(*frames[i % N_ROTATE])
+        ref = net(resident[(args.warmup - 1) % N_ROTATE], None).vel.cpu()
+        assert torch.equal(vel, ref), "servo path and batch path disagree"
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(args.steps):
+            servo.reset()                                 # hidden=None, the workload `value` is quoted on
+            vel = servo.step(*frames[i % N_ROTATE])
+        g1.record()
+        barrier()
+        e2e_ms = max_over_ranks(g0.elapsed_time(g1))
         e2e = args.graphs * world * args.steps / (e2e_ms * 1e-3)
-        d2h = vel.numel() * vel.element_size()
 
     if rank != 0:
         if world > 1:
@@ -275,7 +302,13 @@ def main():
                        N_ROTATE, N_ROTATE * h2d / 1e6), "graphs_per_gpu": args.graphs},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e, "unit": "graphs/s", "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "h2d_bytes_per_step": servo.h2d_bytes, "d2h_bytes_per_step": servo.d2h_bytes,
+                "api": "BatchedServo.step(cur_xy, visible): target graphs resident on the device, per-frame graph "
+                       "masking on the device, every step waits for its velocities",
+                "full_graph": {"value": e2e_full, "ms_per_step": full_ms / args.steps, "h2d_bytes_per_step": h2d,
+                               "d2h_bytes_per_step": d2h_full,
+                               "api": "GraphVS.forward(Batch.to(device)): the whole prebuilt host Batch is copied "
+                                      "every step (DevicePrefetcher), read-back one step behind"}},
         "gpu_launches": int(launches.value),
         "roofline": {"kernel": "enc_edge (%s)" % args.precision, "bound": "tensor", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,

@@ -1,0 +1,104 @@
+"""Device-resident batched servo loop: the target-side graph of every scene lives on the GPU, a frame
+only ships what changes per frame.
+
+The reference builds the two-level graph once per target image and, every frame, only masks out the
+keypoints that were not matched (`Midend.get_graph_data`, cns/midend/corr2graph.py:11-22 ->
+`GraphGenerator.get_data`, graph_gen.py:236-277) before collating B python objects with
+`Batch.from_data_list` (sim/dataset.py:206-209).  `BatchedServo` keeps that split for B scenes at once
+(SURVEY 8f2): constructor = "target changed" (static tensors uploaded once: target keypoints, cluster
+membership, centres, the full cluster graph); `step(cur_xy, visible)` = one frame: H2D of the current
+keypoint coordinates + visibility mask, `cns_graph_mask` (per-frame sub-graph, bit-exact with
+`_get_graph` + collation), `cns_graphvs_forward` with the hidden state carried on the device, D2H of the
+(B,6) velocities.
+"""
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .graph_gen import GraphGenerator
+
+
+class BatchedServo(object):
+    def __init__(self, net, generators: Sequence[GraphGenerator], dist_scale, device="cuda:0"):
+        self.net, self.dev = net, torch.device(device)
+        self.lib = _lib.load()
+        gens = list(generators)
+        n_nodes = np.array([g.num_points for g in gens], dtype=np.int64)
+        n_clu = np.array([g.num_clusters for g in gens], dtype=np.int64)
+        noff, coff = np.cumsum(n_nodes) - n_nodes, np.cumsum(n_clu) - n_clu
+        self.B, self.N, self.Cn = len(gens), int(n_nodes.sum()), int(n_clu.sum())
+        self.node_off = noff
+        d = lambda a, dt: torch.as_tensor(np.array(a), dtype=dt).to(self.dev)
+        tar = np.concatenate([g.target_points for g in gens]).astype(np.float32)
+        self.x_tar = d(tar, torch.float32)                                   # x_tar == pos_tar (default_feature)
+        self.belong = d(np.concatenate([g.belong_cluster_index + c for g, c in zip(gens, coff)]), torch.int64)
+        self.member_order = d(np.concatenate([g.l0_to_l1_edge_index[0] + o for g, o in zip(gens, noff)]), torch.int64)
+        self.cluster_size = d(np.concatenate([g.cluster_points_count for g in gens]), torch.int64)
+        self.cluster_graph_ptr = d(np.concatenate([[0], np.cumsum(n_clu)]), torch.int64)
+        self.centers = d(np.concatenate([g.cluster_centers_index + o for g, o in zip(gens, noff)]), torch.int64)
+        self.l1_tar = d(np.concatenate([g.l1_dense_edge_index + c for g, c in zip(gens, coff)], axis=1), torch.int64)
+        self.num_clusters = d(n_clu, torch.int64)
+        self.tpo = d(np.broadcast_to(np.asarray(dist_scale, dtype=np.float32), (self.B,)), torch.float32)
+        self.cap = int((n_clu ** 2).sum())
+        i64 = lambda n: torch.empty(n, dtype=torch.int64, device=self.dev)
+        self.e01_j, self.e01_i = i64(max(self.N, 1)), i64(max(self.N, 1))
+        self.e11 = torch.empty(2, max(self.cap, 1), dtype=torch.int64, device=self.dev)
+        self.cmask = torch.empty(max(self.Cn, 1), dtype=torch.uint8, device=self.dev)
+        self.counts = torch.zeros(2, dtype=torch.int64, device=self.dev)
+        self.counts_host = torch.zeros(2, dtype=torch.int64).pin_memory()
+        self.mask_ws = torch.empty(self.lib.cns_graph_mask_workspace_bytes(self.N, self.Cn, self.B), dtype=torch.uint8,
+                                   device=self.dev)
+        self.xy_dev = torch.empty(self.N, 2, dtype=torch.float32, device=self.dev)
+        self.vis_dev = torch.empty(self.N, dtype=torch.uint8, device=self.dev)
+        self.hidden = [torch.zeros(self.Cn, 128, device=self.dev), torch.zeros(self.Cn, 128, device=self.dev)]
+        self.cur, self.have_hidden = 0, False
+        self.out = torch.empty(self.B * 13, dtype=torch.float32, device=self.dev)
+        self.vel_host = torch.empty(self.B, 6).pin_memory()
+        self.h2d_bytes = self.N * 2 * 4 + self.N
+        self.d2h_bytes = self.B * 6 * 4 + 16
+
+    def reset(self):
+        self.have_hidden = False
+
+    def step(self, cur_xy: torch.Tensor, visible: torch.Tensor, wait: bool = True) -> torch.Tensor:
+        """cur_xy (sum N, 2) float32 and visible (sum N,) uint8/bool HOST tensors (pinned for full speed), in
+        the scenes' keypoint order.  Returns the (B, 6) velocities in pinned host memory."""
+        lib, L, dev = self.lib, _lib, self.dev
+        stream = L.stream_ptr(dev)
+        self.xy_dev.copy_(cur_xy, non_blocking=True)
+        self.vis_dev.copy_(visible.view(torch.uint8) if visible.dtype == torch.bool else visible, non_blocking=True)
+        L.check(lib.cns_graph_mask(L.ptr(self.belong), L.ptr(self.member_order), L.ptr(self.cluster_size),
+                                   L.ptr(self.cluster_graph_ptr), L.ptr(self.vis_dev), self.N, self.Cn, self.B,
+                                   L.ptr(self.e01_j), L.ptr(self.e01_i), L.ptr(self.e11), self.e11.shape[1],
+                                   L.ptr(self.cmask), L.ptr(self.counts), L.ptr(self.mask_ws), self.mask_ws.numel(), stream),
+                "cns_graph_mask")
+        self.counts_host.copy_(self.counts, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()          # edge counts size the forward's grids
+        n01, n11 = int(self.counts_host[0]), int(self.counts_host[1])
+        b = L.cns_batch()
+        b.n_nodes, b.n_clusters, b.n_graphs = self.N, self.Cn, self.B
+        b.n_e01, b.n_e11_cur, b.n_e11_tar = n01, n11, self.l1_tar.shape[1]
+        p = lambda t: t.data_ptr()
+        b.x_cur, b.pos_cur, b.x_tar, b.pos_tar = p(self.xy_dev), p(self.xy_dev), p(self.x_tar), p(self.x_tar)
+        b.l0_to_l1_j, b.l0_to_l1_i = p(self.e01_j), p(self.e01_i)
+        b.l1_edge_cur, b.l1_edge_tar = p(self.e11), p(self.l1_tar)
+        b.l1_cur_stride, b.l1_tar_stride = self.e11.shape[1], 0
+        b.cluster_mask, b.cluster_centers = p(self.cmask), p(self.centers)
+        b.node_graph, b.num_clusters, b.tPo_norm = None, p(self.num_clusters), p(self.tpo)
+        h = self.net._handle(dev)
+        ws = self.net._workspace(dev.index, lib.cns_forward_workspace_bytes(C.byref(b)))
+        B = self.B
+        vec, vel, nrm = self.out[:B * 6], self.out[B * 6:B * 12], self.out[B * 12:]
+        hin = self.hidden[self.cur] if self.have_hidden else None
+        hout = self.hidden[self.cur ^ 1]
+        L.check(lib.cns_graphvs_forward(h.raw, C.byref(b), L.ptr(hin), L.ptr(vec), L.ptr(nrm), L.ptr(hout), L.ptr(vel),
+                                        L.ptr(ws), ws.numel(), None, 0, stream), "cns_graphvs_forward")
+        self.cur ^= 1
+        self.have_hidden = True
+        self.vel_host.copy_(vel.view(B, 6), non_blocking=True)
+        if wait:
+            torch.cuda.current_stream(dev).synchronize()
+        return self.vel_host

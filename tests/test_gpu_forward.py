@@ -177,6 +177,40 @@ def test_servo_controller_host_path(state_dict):
         scene.step(vel * 2)
 
 
+def test_batched_servo_device_graphs_match_host_graph_path(net):
+    """BatchedServo (target graphs resident on the device, per-frame masking by cns_graph_mask, hidden
+    carried on the device) == GraphGenerator.get_data + Batch.from_data_list + GraphVS.forward on the
+    same frames: identical graphs feed identical kernels, so the velocities are bit-equal."""
+    from cns_b200.servo import BatchedServo
+    rng = np.random.default_rng(5)
+    np.random.seed(5)
+    scenes = [synth.Scene(rng, n) for n in (30, 200, 64, 512, 12)]
+    servo = BatchedServo(net, [s.generator for s in scenes], [s.tPo_norm for s in scenes], "cuda:0")
+    hidden = None
+    for t in range(4):
+        frames, xy, vis = [], [], []
+        for s in scenes:
+            n = len(s.points)
+            cur = synth.project_norm(s.cur_wcT, s.points)
+            k = int(rng.integers(0, n))                      # any number of unmatched keypoints, incl. 0
+            missing = np.sort(rng.choice(n, size=k, replace=False)) if k else None
+            d = s.generator.get_data(cur, missing_node_indices=missing)
+            d.set_distance_scale(s.tPo_norm)
+            v = np.ones(n, bool)
+            if k:
+                v[missing] = False
+            frames.append(d); xy.append(cur); vis.append(v)
+        batch = Batch.from_data_list(frames)
+        with torch.no_grad():
+            ref = net(batch.to("cuda:0"), hidden, check=True)
+        hidden = ref[2]
+        vel = servo.step(torch.from_numpy(np.concatenate(xy)).float(), torch.from_numpy(np.concatenate(vis)))
+        assert torch.equal(vel, ref.vel.cpu())
+        assert torch.equal(servo.hidden[servo.cur], hidden)
+        for s, v in zip(scenes, vel.numpy()):
+            s.step(v * 2)
+
+
 def test_full_size_batch_properties(net, state_dict):
     """BASELINE config: 1024 graphs x 512 keypoints.  The oracle is too slow for all of it, so:
     (1) spot-check 8 graphs against the oracle, (2) permuting the graphs of the batch permutes the
