@@ -8,5 +8,6 @@ from .data import Batch, GraphData
 from .graph_gen import GraphGenerator
 from .midend import CameraIntrinsic, Correspondence, Midend
 from .model import GraphVS
+from .servo import BatchedServo
 
-__all__ = ["Batch", "GraphData", "GraphGenerator", "CameraIntrinsic", "Correspondence", "Midend", "GraphVS"]
+__all__ = ["Batch", "GraphData", "GraphGenerator", "CameraIntrinsic", "Correspondence", "Midend", "GraphVS", "BatchedServo"]

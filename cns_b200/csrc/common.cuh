@@ -60,6 +60,12 @@ struct Packed {
   //   0: pos_nn.fcs.1^T   1: -lin_src^T   2: lin^T   3: attn_nn.fcs.0^T   4: attn_nn.fcs.1^T
   float* enc_chain;      // [5][128][128]
   float* lin_dst_t;      // [128][128]
+  // tensor-core encoder: attn_nn.fcs.0 is linear in (a_dst - a_src + delta), so it is composed into its
+  // producers once per weight load (A0 = attn_nn.fcs.0):
+  //   0: pos_nn.fcs.1^T   1: -(A0 lin_src)^T   2: lin^T   3: (A0 pos_nn.fcs.1)^T   4: attn_nn.fcs.1^T
+  float* tc_chain;       // [5][128][128]
+  float* tc_lin_dst_t;   // [128][128]  (A0 lin_dst)^T
+  float* tc_adst_bias;   // [128]       A0 b_pos1 + b_attn0
   float* out_t;          // [256][128]
   // PointEdgeConv factorisation  PQ = X @ wt + pos @ wp + b ; columns [P (f) | Q (f)]
   float* c0_wt; float* c0_wp; float* c0_b;      // [128][256], [2][256], [256]

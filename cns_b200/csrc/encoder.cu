@@ -282,8 +282,9 @@ enc_cluster_pre_kernel(EncPreArgs p) {
   }
   __syncthreads();
   float acc[CLU_ROWS];
+  const float ab = p.a_bias ? p.a_bias[o] : 0.f;
 #pragma unroll
-  for (int r = 0; r < CLU_ROWS; ++r) acc[r] = 0.f;
+  for (int r = 0; r < CLU_ROWS; ++r) acc[r] = ab;
 #pragma unroll 4
   for (int k = 0; k < H; ++k) {
     float w = p.lin_dst_t[k * H + o];

@@ -9,9 +9,12 @@
 // per-channel segment softmax over the edges of a cluster is then a sequential walk along TMEM
 // columns inside one thread, with warp-uniform segment boundaries - no shuffles, no atomics.
 //
-//   round A :  T = x (-lin_src)^T + hp pos_nn.1^T        V = x lin^T + hp pos_nn.1^T      (K = 256 each)
-//   epi   A :  t = T + a_dst[cluster] + b_p1  -> 16-bit -> smem (B operand of round B)
-//   round B :  U = t attn_nn.0^T                epi B : u = relu(U + b_a0) -> smem
+// attn_nn.fcs.0 (A0) is linear in its input a_dst[i] - lin_src x_j + delta_ij, so it is composed into
+// the producing weights once per weight load (handle.cu) and a whole GEMM round disappears:
+//
+//   round A :  U = x (-(A0 lin_src))^T + hp (A0 pos_nn.1)^T      V = x lin^T + hp pos_nn.1^T    (K = 256 each)
+//   epi   A :  u = relu(U + a'[cluster]),  a' = A0 (a_dst + b_pos1) + b_attn0 (per cluster, enc_cluster_pre)
+//              -> 16-bit -> smem, MN-major ([channel][edge]): every thread stores its own row, no transposition
 //   round C :  L = u attn_nn.1^T                final : online segment softmax of (L + b_a1) weighting (V + b_p1)
 //
 // x = relu(in_enc(feat)) and hp = relu(pos_nn.0(dpos)) have K = 2 / 4 and are produced by FFMA straight
@@ -27,7 +30,7 @@
 namespace cns {
 
 constexpr int TC_W_BYTES = 128 * 128 * 2;         // one weight matrix, 16-bit
-constexpr int TC_NW = 5;                          // pos_nn.1, -lin_src, lin, attn_nn.0, attn_nn.1
+constexpr int TC_NW = 5;                          // pos_nn.1, -(A0 lin_src), lin, A0 pos_nn.1, attn_nn.1
 constexpr int TC_ACT_BYTES = 64 * 1024;           // all activation buffers of all slots
 
 // ---- weight image: fp32 (k-major "chain" [5][k][o]) -> 16-bit swizzled A-operand tiles ----------
@@ -65,7 +68,8 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
   constexpr int SLOTS = 128 / TN;
   constexpr int ACT_TILE = TN * 256;                 // one [TN x 128] 16-bit operand tile
   constexpr int TMEM_COLS = 256;                     // SLOTS * 2 regions * TN columns
-  constexpr int EPI_THREADS = 128 * SLOTS;
+  constexpr int U_ROW = TN * 2;                      // bytes per channel row of the MN-major u tile
+  constexpr int NPRE = 4;                            // a' rows prefetched per tile (first NPRE segment starts)
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment: align by hand (1 KB of slack is allocated)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -77,7 +81,9 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
   int* ci_s = reinterpret_cast<int*>(tail + 256);                // [SLOTS][TN] cluster id per edge (-1: padding)
 
   const EncEdgeArgs& p = args.e;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // warp-uniform by construction: lets the compiler keep slot addresses / descriptors in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   if (warp == 0) {
     if (lane == 0) {
       mbar_init(smem_u32(&bars[0]), 1);
@@ -95,12 +101,13 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_s;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
 
-  // instruction descriptor: D=f32 (bit 4), A/B format at bits 7/10 (0 f16, 1 bf16), K-major both,
-  // N>>3 at bit 17, M>>4 at bit 24
+  // instruction descriptor: D=f32 (bit 4), A/B format at bits 7/10 (0 f16, 1 bf16), A K-major (bit 15 = 0),
+  // B K-major or MN-major (bit 16), N>>3 at bit 17, M>>4 at bit 24
   const uint32_t fmt = BF16 ? 1u : 0u;
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TN >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t idesc_mn = idesc | (1u << 16);
   const uint32_t w_base = smem_u32(w_s);
 
   {
@@ -114,15 +121,15 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     const uint32_t done = smem_u32(&bars[1 + s]);
     const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((s * 2 + 0) * TN);
     const uint32_t t1 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((s * 2 + 1) * TN);
-    const float b_p1 = p.b_p1[t], b_a0 = p.b_a0[t], b_a1 = p.b_a1[t];
+    const float b_p1 = p.b_p1[t], b_a1 = p.b_a1[t];
     uint32_t done_parity = 0;
     constexpr float LOG2E = 1.4426950408889634f;
 
-    // The slot's thread 0 issues the slot's tensor-core work itself (tcgen05.mma is a single-thread
-    // instruction): after the slot barrier every operand byte written by the 128 threads is visible
-    // to the async proxy, so no dedicated MMA warp / "ready" mbarrier is needed.
-    // One K=128 product = 2 swizzle blocks of 64 k x 4 MMAs (K = 16 = 32 B).
-    auto gemm128 = [&](uint32_t d, int w, uint32_t b, uint32_t acc_first) {
+    // One elected thread of the slot's first warp issues the slot's tensor-core work (tcgen05.mma is a
+    // single-thread instruction): after the slot barrier every operand byte written by the 128 threads is
+    // visible to the async proxy, so no dedicated MMA warp / "ready" mbarrier is needed.
+    // One K=128 product = 8 MMAs of K = 16.
+    auto gemm_kmajor = [&](uint32_t d, int w, uint32_t b, uint32_t acc_first) {
       const uint32_t a = w_base + (uint32_t)w * TC_W_BYTES;
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc)
@@ -133,40 +140,41 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
           umma_f16(d, ad, bd, idesc, (kc | ks) ? 1u : acc_first);
         }
     };
+    auto gemm_mnmajor = [&](uint32_t d, int w, uint32_t b) {     // B tile stored [k][edge]
+      const uint32_t a = w_base + (uint32_t)w * TC_W_BYTES;
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint64_t ad = sw128_desc(a + kc * (128 * 128) + ks * 32);
+          uint64_t bd = mn_major_desc(b + (kc * 4 + ks) * (16 * U_ROW), U_ROW);   // 16 k-rows per MMA
+          umma_f16(d, ad, bd, idesc_mn, (kc | ks) ? 1u : 0u);
+        }
+    };
     auto publish_and_issue = [&](int round) {
       tc_fence_before();          // this thread's earlier TMEM loads are ordered before the next MMAs
       fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor core
       named_bar(1 + s, 128);
-      if (t == 0) {
-        tc_fence_after();
-        const uint32_t b0 = smem_u32(buf0), b1 = smem_u32(buf1);
-        const uint32_t d0 = tmem_base + (uint32_t)((s * 2 + 0) * TN);
-        const uint32_t d1 = tmem_base + (uint32_t)((s * 2 + 1) * TN);
-        if (round == 0) {
-          gemm128(d0, 1, b0, 0);   // T  = x  (-lin_src)^T
-          gemm128(d0, 0, b1, 1);   //    + hp pos_nn.1^T
-          gemm128(d1, 2, b0, 0);   // V  = x  lin^T
-          gemm128(d1, 0, b1, 1);   //    + hp pos_nn.1^T
-        } else if (round == 1) {
-          gemm128(d0, 3, b0, 0);   // U = t attn_nn.0^T     (t lives in buffer 0)
-        } else {
-          gemm128(d0, 4, b1, 0);   // L = u attn_nn.1^T     (u lives in buffer 1)
+      if (wq == 0) {
+        if (elect_one()) {
+          tc_fence_after();
+          const uint32_t b0 = smem_u32(buf0), b1 = smem_u32(buf1);
+          const uint32_t d0 = tmem_base + (uint32_t)((s * 2 + 0) * TN);
+          const uint32_t d1 = tmem_base + (uint32_t)((s * 2 + 1) * TN);
+          if (round == 0) {
+            gemm_kmajor(d0, 1, b0, 0);   // U  = x  (-(A0 lin_src))^T
+            gemm_kmajor(d0, 3, b1, 1);   //    + hp (A0 pos_nn.1)^T
+            gemm_kmajor(d1, 2, b0, 0);   // V  = x  lin^T
+            gemm_kmajor(d1, 0, b1, 1);   //    + hp pos_nn.1^T
+          } else {
+            gemm_mnmajor(d0, 4, b0);     // L = u attn_nn.1^T     (u lives in buffer 0, [channel][edge])
+          }
+          umma_commit(done);
         }
-        umma_commit(done);
+        __syncwarp();
       }
     };
-    if (t == 0) mbar_wait(smem_u32(&bars[0]), 0);      // weights landed (only the issuing thread cares)
-
-    // store a [channel t][edge e] fp32 column pair as 16-bit into the B-operand tile (row e, col t)
-    auto store_pair = [&](unsigned char* buf, int e, float v0, float v1) {
-      // even lane keeps row e (cols t, t+1), odd lane keeps row e+1 (cols t-1, t)
-      const bool odd = lane & 1;
-      float send = odd ? v0 : v1;
-      float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-      uint32_t packed = odd ? pack2<BF16>(recv, v1) : pack2<BF16>(v0, recv);
-      int row = odd ? e + 1 : e, col = odd ? t - 1 : t;
-      *reinterpret_cast<uint32_t*>(buf + sw128_off(TN, row, col)) = packed;
-    };
+    if (wq == 0) mbar_wait(smem_u32(&bars[0]), 0);     // weights landed (only the issuing warp cares)
 
     // Per-edge inputs of the producer (thread = edge pe, channel block kp) are fetched one tile ahead:
     // the index loads are issued before the producer math of the current tile and the dependent
@@ -221,6 +229,9 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         slot[t] = run_m + b_a1; slot[H + t] = run_s; slot[2 * H + t] = ab;
       }
     };
+    // u tile, MN-major: row = channel t (U_ROW bytes of edges), 16-byte chunk index XOR-swizzled by the row
+    unsigned char* const u_row = buf0 + (t >> 3) * (8 * U_ROW) + (t & 7) * U_ROW;
+    const uint32_t u_xor = (uint32_t)(((t & 7) * U_ROW) >> 7) & (uint32_t)(U_ROW / 16 - 1);
 
     for (int it = 0;; ++it) {
       const int g = tile_of(it);
@@ -285,54 +296,74 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         const int cprev = (e == 0) ? -2 : ci[e - 1];
         seg_mask[c0 / 32] = __ballot_sync(0xffffffffu, ci[e] != cprev);
       }
+      // a'[cluster][t] = (A0 (a_dst + b_pos1) + b_attn0)[t] of the tile's first NPRE segment starts: the
+      // loads fly while the tensor core runs round A
+      float aq[NPRE];
+      {
+        uint32_t m0 = seg_mask[0];
+        uint32_t m1 = (TN > 32) ? seg_mask[(TN > 32) ? 1 : 0] : 0u;
+#pragma unroll
+        for (int i = 0; i < NPRE; ++i) {
+          aq[i] = 0.f;
+          int q = -1;
+          if (m0) { q = __ffs(m0) - 1; m0 &= m0 - 1; }
+          else if (TN > 32 && m1) { q = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
+          if (q >= 0) {
+            const int c = ci[q];
+            if (c >= 0) aq[i] = p.a_dst[(size_t)c * H + t];
+          }
+        }
+      }
 
-      // ---- epilogue A: t = T + a_dst[cluster] + b_p1 -> buf0 ------------------------------------
-      // (padding rows of the last tile keep finite garbage; their columns are never read back)
+      // ---- epilogue: u = relu(U + a'[cluster]) -> buf0, MN-major ([channel][edge]: this thread's row) ---
+      // (padding columns of the last tile keep finite garbage; they are never read back)
       mbar_wait(done, done_parity); done_parity ^= 1;
       tc_fence_after();
       {
         float adb = 0.f;
+        int nseg = 0;
 #pragma unroll
         for (int c0 = 0; c0 < TN; c0 += 32) {
           float acc[32];
           tmem_ld32(t0 + c0, acc);
           tmem_ld_wait();
           const uint32_t mask = seg_mask[c0 / 32];
+          uint32_t pk[16];
 #pragma unroll
           for (int q = 0; q < 32; q += 2) {
             float v[2];
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
               if (mask & (1u << (q + h2))) {
-                const int c = ci[c0 + q + h2];
-                if (c >= 0) adb = p.a_dst[(size_t)c * H + t] + b_p1;
+                if (nseg < NPRE) {
+                  adb = aq[0];
+#pragma unroll
+                  for (int i = 0; i + 1 < NPRE; ++i) aq[i] = aq[i + 1];
+                } else {
+                  const int c = ci[c0 + q + h2];
+                  adb = (c >= 0) ? p.a_dst[(size_t)c * H + t] : 0.f;
+                }
+                ++nseg;
               }
-              v[h2] = acc[q + h2] + adb;
+              v[h2] = fmaxf(acc[q + h2] + adb, 0.f);
             }
-            store_pair(buf0, c0 + q, v[0], v[1]);
+            pk[q / 2] = pack2<BF16>(v[0], v[1]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t chunk16 = ((uint32_t)(c0 / 8 + j)) ^ u_xor;
+            *reinterpret_cast<uint4*>(u_row + chunk16 * 16) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           }
         }
       }
       publish_and_issue(1);
 
-      // ---- epilogue B: u = relu(U + b_a0) -> buf1 ------------------------------------------------
-      mbar_wait(done, done_parity); done_parity ^= 1;
-      tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < TN; c0 += 32) {
-        float acc[32];
-        tmem_ld32(t0 + c0, acc);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 32; q += 2)
-          store_pair(buf1, c0 + q, fmaxf(acc[q] + b_a0, 0.f), fmaxf(acc[q + 1] + b_a0, 0.f));
-      }
-      publish_and_issue(2);
-
       // ---- final: per-channel online segment softmax of L weighting V ---------------------------
       // softmax is shift-invariant per channel, so the attn_nn.1 bias drops out; the value bias b_p1
       // is added once per segment (sum p (v + b) = sum p v + b sum p).  One ex2 per element: of the
-      // two rescale factors exp(m_old - m_new), exp(l - m_new) one is always 1.
+      // two rescale factors exp(m_old - m_new), exp(l - m_new) one is always 1.  A segment start only
+      // resets the state (m = l, s = a = 0): the common update then yields s = 1, a = v.  Padding edges
+      // (cluster -1) open a segment that is never flushed.
       mbar_wait(done, done_parity); done_parity ^= 1;
       tc_fence_after();
       {
@@ -346,23 +377,20 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
 #pragma unroll
           for (int q = 0; q < 32; ++q) {
             const int e = c0 + q;
-            if (e < n_valid) {
-              const float l = lg[q], v = vv[q];
-              // edge 0 of a tile opens a new segment only if its cluster differs from the carried one
-              const bool start = (e == 0) ? (ci[0] != run_seg) : ((mask >> q) & 1u);
-              if (start) {
-                if (run_seg >= 0) flush_run(e0 + e);
-                run_seg = ci[e]; run_beg = e0 + e; run_m = l; run_s = 1.f; run_a = v;
-              } else {
-                const float d = l - run_m;
-                const float ex = ex2_approx(-fabsf(d) * LOG2E);
-                const bool up = d > 0.f;
-                const float sc = up ? ex : 1.f, pr = up ? 1.f : ex;
-                run_s = fmaf(run_s, sc, pr);
-                run_a = fmaf(run_a, sc, pr * v);
-                run_m = fmaxf(run_m, l);
-              }
+            const float l = lg[q], v = vv[q];
+            // edge 0 of a tile opens a new segment only if its cluster differs from the carried one
+            const bool start = (e == 0) ? (ci[0] != run_seg) : ((mask >> q) & 1u);
+            if (start) {
+              if (run_seg >= 0) flush_run(e0 + e);
+              run_seg = ci[e]; run_beg = e0 + e; run_m = l; run_s = 0.f; run_a = 0.f;
             }
+            const float d = l - run_m;
+            const float ex = ex2_approx(-fabsf(d) * LOG2E);
+            const bool up = d > 0.f;
+            const float sc = up ? ex : 1.f, pr = up ? 1.f : ex;
+            run_s = fmaf(run_s, sc, pr);
+            run_a = fmaf(run_a, sc, pr * v);
+            run_m = fmaxf(run_m, l);
           }
         }
         if (g + 1 >= t_end && run_seg >= 0) { flush_run(e0 + n_valid); run_seg = -1; }   // chunk end
@@ -422,9 +450,9 @@ int tc_piece_edges(int64_t n_e01, const cns_handle* h) {
 int tc_pack_weights(cns_handle* h, cudaStream_t s) {
   if (!h->tc_w_img) CNS_CUDA_CHECK(cudaMalloc(&h->tc_w_img, 2 * TC_NW * TC_W_BYTES));
   const int total = TC_NW * 128 * 128;
-  tc_pack_weights_kernel<true><<<ceil_div(total, 256), 256, 0, s>>>(h->pk.enc_chain, h->tc_w_img);
+  tc_pack_weights_kernel<true><<<ceil_div(total, 256), 256, 0, s>>>(h->pk.tc_chain, h->tc_w_img);
   CNS_LAUNCH_CHECK();
-  tc_pack_weights_kernel<false><<<ceil_div(total, 256), 256, 0, s>>>(h->pk.enc_chain, h->tc_w_img + TC_NW * TC_W_BYTES);
+  tc_pack_weights_kernel<false><<<ceil_div(total, 256), 256, 0, s>>>(h->pk.tc_chain, h->tc_w_img + TC_NW * TC_W_BYTES);
   CNS_LAUNCH_CHECK();
   // small first-layer weights travel in the kernel parameter space: keep a host copy
   static_assert(sizeof(TcSmallW) == sizeof(h->tc_small_host), "TcSmallW size");

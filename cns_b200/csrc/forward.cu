@@ -115,6 +115,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   EncPreArgs pre{};
   pre.n_clusters = C; pre.x_tar = b->x_tar; pre.pos_tar = b->pos_tar; pre.centers = b->cluster_centers;
   pre.node_graph = b->node_graph; pre.w_in = h->P(P_IN_W); pre.b_in = h->P(P_IN_B); pre.lin_dst_t = pk.lin_dst_t;
+  if (h->precision != CNS_PREC_FP32) { pre.lin_dst_t = pk.tc_lin_dst_t; pre.a_bias = pk.tc_adst_bias; }   // a_dst := A0 (a_dst + b_pos1) + b_attn0
   pre.a_dst = f.a_dst; pre.pos_clu = f.pos_clu; pre.clu_graph = f.clu_graph;
   RUN(enc_cluster_pre(pre, s));
 

@@ -103,6 +103,7 @@ static size_t packed_floats() {
   size_t n = 0;
   n += 5 * 128 * 128;                 // enc_chain
   n += 128 * 128;                     // lin_dst_t
+  n += 5 * 128 * 128 + 128 * 128 + 128;   // tc_chain, tc_lin_dst_t, tc_adst_bias
   n += 256 * 128;                     // out_t
   n += 128 * 256 + 2 * 256 + 256;     // c0
   n += 256 * 512 + 2 * 512 + 512;     // gates
@@ -110,6 +111,16 @@ static size_t packed_floats() {
   n += 128 * 256 + 2 * 256 + 256;     // c1
   n += 4 * 128 * 128;                 // c0_fc, c1_fc, vec0, nrm0
   return n;
+}
+
+// C[r][o] = sum_m S[r][m] A[m][o] (+ bias[o]); one block per row r, 128 columns
+__global__ void compose_kernel(const float* __restrict__ S, const float* __restrict__ A, const float* __restrict__ bias,
+                               float* __restrict__ C, int rows) {
+  const int r = blockIdx.x, o = threadIdx.x;
+  if (r >= rows) return;
+  float acc = bias ? bias[o] : 0.f;
+  for (int m = 0; m < 128; ++m) acc = fmaf(S[r * 128 + m], A[m * 128 + o], acc);
+  C[r * 128 + o] = acc;
 }
 
 static int launch_transpose(const float* src, int ld, int col0, int k_dim, int n_out, float sign,
@@ -152,6 +163,21 @@ int repack(cns_handle* h, cudaStream_t s) {
   if ((rc = launch_edgeconv_pack(h->P(P_G_MSG_W), h->P(P_G_MSG_B), 256, 256, pk.g_wt, pk.g_wp, pk.g_b, s))) return rc;
   if ((rc = launch_edgeconv_pack(h->P(P_K_MSG_W), h->P(P_K_MSG_B), 256, 128, pk.k_wt, pk.k_wp, pk.k_b, s))) return rc;
   if ((rc = launch_edgeconv_pack(h->P(P_C1_MSG_W), h->P(P_C1_MSG_B), 128, 128, pk.c1_wt, pk.c1_wp, pk.c1_b, s))) return rc;
+  // composed operands of the tensor-core encoder (k-major: C[k][o] = sum_m S[k][m] A0t[m][o])
+  {
+    const float* a0t = pk.enc_chain + 3 * 16384;
+    CNS_CUDA_CHECK(cudaMemcpyAsync(pk.tc_chain + 0 * 16384, pk.enc_chain + 0 * 16384, 16384 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CNS_CUDA_CHECK(cudaMemcpyAsync(pk.tc_chain + 2 * 16384, pk.enc_chain + 2 * 16384, 16384 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CNS_CUDA_CHECK(cudaMemcpyAsync(pk.tc_chain + 4 * 16384, pk.enc_chain + 4 * 16384, 16384 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    compose_kernel<<<128, 128, 0, s>>>(pk.enc_chain + 1 * 16384, a0t, nullptr, pk.tc_chain + 1 * 16384, 128);
+    CNS_LAUNCH_CHECK();
+    compose_kernel<<<128, 128, 0, s>>>(pk.enc_chain + 0 * 16384, a0t, nullptr, pk.tc_chain + 3 * 16384, 128);
+    CNS_LAUNCH_CHECK();
+    compose_kernel<<<128, 128, 0, s>>>(pk.lin_dst_t, a0t, nullptr, pk.tc_lin_dst_t, 128);
+    CNS_LAUNCH_CHECK();
+    compose_kernel<<<1, 128, 0, s>>>(h->P(P_POS1_B), a0t, h->P(P_ATT0_B), pk.tc_adst_bias, 1);
+    CNS_LAUNCH_CHECK();
+  }
   if ((rc = tc_pack_weights(h, s)) != CNS_OK) return rc;
   {
     // node-GEMM weight images (bf16 + f16), 2 bytes per element
@@ -227,6 +253,7 @@ int cns_create(cns_handle** out, int device) {
   auto take = [&](size_t nfl) { float* r = p; p += nfl; return r; };
   pk.enc_chain = take(5 * 16384);
   pk.lin_dst_t = take(16384);
+  pk.tc_chain = take(5 * 16384); pk.tc_lin_dst_t = take(16384); pk.tc_adst_bias = take(128);
   pk.out_t = take(256 * 128);
   pk.c0_wt = take(128 * 256); pk.c0_wp = take(2 * 256); pk.c0_b = take(256);
   pk.g_wt = take(256 * 512);  pk.g_wp = take(2 * 512);  pk.g_b = take(512);

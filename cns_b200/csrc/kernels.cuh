@@ -32,6 +32,7 @@ struct EncPreArgs {
   int64_t n_clusters;
   const float* x_tar; const float* pos_tar; const int64_t* centers; const int64_t* node_graph;
   const float* w_in; const float* b_in; const float* lin_dst_t;
+  const float* a_bias;   // optional (128,): added to a_dst (tensor-core encoder: composed attn_nn.0 biases)
   float* a_dst;      // (C,128)
   float* pos_clu;    // (C,2)
   int* clu_graph;    // (C,)

@@ -105,6 +105,29 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand tile (the MN index is the contiguous one): rows of `row_bytes` = 64 (SWIZZLE_64B) or
+// 128 (SWIZZLE_128B) bytes, one row per k, 8-row swizzle atoms `sbo_bytes` = 8 * row_bytes apart.
+// Canonical form (cute/atom/mma_traits_sm100.hpp): Swizzle<B,4,3> o ((T*B',n),(8,k)) : ((1,LBO),(row,SBO)).
+__device__ __forceinline__ uint64_t mn_major_desc(uint32_t smem_addr, uint32_t row_bytes) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                              // LBO: a single MN block, field unused
+  d |= (uint64_t)((8 * row_bytes) >> 4) << 32;         // SBO: next group of 8 k-rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;     // SWIZZLE_128B : SWIZZLE_64B
+  return d;
+}
+
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok));
+  return ok != 0;
+}
+
 template <bool BF16>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   if (BF16) {
