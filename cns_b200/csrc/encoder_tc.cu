@@ -48,10 +48,7 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ enc_chain, unsi
 }
 
 struct TcSmallW {          // passed by value in the kernel parameter space (constant bank)
-  float w_in[128 * 2];
-  float b_in[128];
-  float w_p0[128 * 4];
-  float b_p0[128];
+  float4 w[128][2];        // per channel k: {in_enc.w[k][0], in_enc.w[k][1], in_enc.b[k], pos_nn.0.b[k]}, pos_nn.0.w[k][0..3]
 };
 
 struct TcArgs {
@@ -179,7 +176,8 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     // Per-edge inputs of the producer (thread = edge pe, channel block kp) are fetched one tile ahead:
     // the index loads are issued before the producer math of the current tile and the dependent
     // coordinate gathers right after it, so both latencies hide behind the epilogues.
-    const int pe = t % TN, kp = t / TN;            // channels [kp*TN, kp*TN + TN)
+    const int pe = (TN == 32) ? lane : ((wq & 1) * 32 + lane);   // == t % TN
+    const int kp = (TN == 32) ? wq : (wq >> 1);                  // == t / TN (warp-uniform): channels [kp*TN, kp*TN + TN)
     // Work assignment: the 2 * n_tiles (side, edge tile) items are cut into gridDim.x * SLOTS contiguous
     // chunks, one per slot, the first half of the chunks on the current-frame side, the second half on
     // the target side.  Consecutive tiles in one slot let a cluster cut by a tile boundary carry its
@@ -216,14 +214,21 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     // running softmax state of the cluster that is open at the end of a tile (carried to the next tile)
     float run_m = 0.f, run_s = 0.f, run_a = 0.f;
     int run_seg = -1;
-    int64_t run_beg = 0;                           // global edge index where the open segment started (in this chunk)
     float* const out_side = p.clu_feat + (size_t)side * p.n_clusters * H;
     float* const part_side = p.partial + (size_t)side * p.n_slots * 3 * H;
-    auto flush_run = [&](int64_t g_end) {
+    // A run is a whole cluster unless it is the chunk's first run and the chunk starts inside a cluster, or
+    // it is cut by the chunk's end: only those leave (max, sum, acc) partials for enc_finish.
+    bool run_whole;                                // the open run started at a true cluster start
+    bool chunk_whole_end;                          // the chunk's last edge is the last edge of its cluster
+    {
+      const int64_t ce0 = (int64_t)t_begin * TN, ce1 = min((int64_t)t_end * TN, p.n_e01);
+      run_whole = (ce0 == 0) || (ce0 < p.n_e01 && p.ei[ce0 - 1] != p.ei[ce0]);
+      chunk_whole_end = (ce1 >= p.n_e01) || (ce1 > 0 && p.ei[ce1 - 1] != p.ei[ce1]);
+    }
+    auto flush_run = [&](bool whole) {
       const float ab = fmaf(b_p1, run_s, run_a);
-      const bool complete = (p.clu_rowptr[run_seg] == (int)run_beg) && (p.clu_rowptr[run_seg + 1] == (int)g_end);
-      if (complete) {
-        out_side[(size_t)run_seg * H + t] = fmaxf(ab / (run_s + 1e-16f), 0.f);
+      if (whole) {
+        out_side[(size_t)run_seg * H + t] = fmaxf(__fdividef(ab, run_s + 1e-16f), 0.f);
       } else {
         float* slot = part_side + ((size_t)run_seg + chunk) * 3 * H;
         slot[t] = run_m + b_a1; slot[H + t] = run_s; slot[2 * H + t] = ab;
@@ -248,45 +253,34 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         const float d2 = live ? n_pc.x - n_pt.x : 0.f, d3 = live ? n_pc.y - n_pt.y : 0.f;
         if (kp == 0) ci[pe] = cid;
         fetch_index(tile_of(it + 1));              // in flight during the producer math below
-        // kp is warp-uniform; dispatching on it makes every channel index a compile-time constant so
-        // the first-layer weights are read as immediate constant-bank operands of the FFMAs.
-        auto produce = [&](auto kp_c) {
-          constexpr int KP = decltype(kp_c)::value;
+        // kp and gq are warp-uniform: the first-layer weights are uniform constant-bank loads
+#pragma unroll 1
+        for (int gq = 0; gq < TN / 8; ++gq) {
+          const int k0 = kp * TN + gq * 8;
+          uint32_t xo[4], ho[4];
 #pragma unroll
-          for (int gq = 0; gq < TN / 8; ++gq) {
-            constexpr int kbase = KP * TN;
-            const int k0 = kbase + gq * 8;
-            uint32_t xo[4], ho[4];
+          for (int q = 0; q < 4; ++q) {
+            float xv[2], hv[2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float xv[2], hv[2];
-#pragma unroll
-              for (int h2 = 0; h2 < 2; ++h2) {
-                const int k = k0 + q * 2 + h2;
-                float x = fmaf(sw.w_in[k * 2 + 1], f1, fmaf(sw.w_in[k * 2], f0, sw.b_in[k]));
-                float hp = sw.b_p0[k];
-                hp = fmaf(sw.w_p0[k * 4], d0, hp);
-                hp = fmaf(sw.w_p0[k * 4 + 1], d1, hp);
-                hp = fmaf(sw.w_p0[k * 4 + 2], d2, hp);
-                hp = fmaf(sw.w_p0[k * 4 + 3], d3, hp);
-                xv[h2] = fmaxf(x, 0.f);
-                hv[h2] = fmaxf(hp, 0.f);
-              }
-              xo[q] = pack2<BF16>(xv[0], xv[1]);
-              ho[q] = pack2<BF16>(hv[0], hv[1]);
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const float4 wa = sw.w[k0 + q * 2 + h2][0], wb = sw.w[k0 + q * 2 + h2][1];
+              const float x = fmaf(wa.y, f1, fmaf(wa.x, f0, wa.z));
+              float hp = fmaf(wb.x, d0, wa.w);
+              hp = fmaf(wb.y, d1, hp);
+              hp = fmaf(wb.z, d2, hp);
+              hp = fmaf(wb.w, d3, hp);
+              xv[h2] = fmaxf(x, 0.f);
+              hv[h2] = fmaxf(hp, 0.f);
             }
-            const uint32_t off = sw128_off(TN, pe, k0);
-            *reinterpret_cast<uint4*>(buf0 + off) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
-            *reinterpret_cast<uint4*>(buf1 + off) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+            xo[q] = pack2<BF16>(xv[0], xv[1]);
+            ho[q] = pack2<BF16>(hv[0], hv[1]);
           }
-        };
-        if (kp == 0) produce(std::integral_constant<int, 0>{});
-        else if (kp == 1) produce(std::integral_constant<int, 1>{});
-        else if (SLOTS > 2 && kp == 2) produce(std::integral_constant<int, 2 % (128 / TN)>{});
-        else produce(std::integral_constant<int, 3 % (128 / TN)>{});
+          const uint32_t off = sw128_off(TN, pe, k0);
+          *reinterpret_cast<uint4*>(buf0 + off) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
+          *reinterpret_cast<uint4*>(buf1 + off) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+        }
       }
       publish_and_issue(0);            // also makes ci[] visible to the whole slot
-      fetch_coords(tile_of(it + 1));   // dependent gathers of the next tile fly during the epilogues
 
       // segment-start bit per edge (bit e: ci[e] != ci[e-1]); warp-uniform registers, no per-element LDS
       uint32_t seg_mask[TN / 32];
@@ -319,41 +313,44 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
       // (padding columns of the last tile keep finite garbage; they are never read back)
       mbar_wait(done, done_parity); done_parity ^= 1;
       tc_fence_after();
+      fetch_coords(tile_of(it + 1));   // dependent gathers of the next tile fly during the epilogue and the softmax
       {
         float adb = 0.f;
         int nseg = 0;
-#pragma unroll
-        for (int c0 = 0; c0 < TN; c0 += 32) {
-          float acc[32];
-          tmem_ld32(t0 + c0, acc);
+#pragma unroll 1
+        for (int cg = 0; cg < TN / 8; ++cg) {      // 8 edges per trip: one 16-byte chunk of this thread's row
+          float acc[8];
+          tmem_ld8(t0 + cg * 8, acc);
           tmem_ld_wait();
-          const uint32_t mask = seg_mask[c0 / 32];
-          uint32_t pk[16];
+          const uint32_t m8 = (seg_mask[(TN > 32) ? (cg >> 2) : 0] >> ((cg & 3) * 8)) & 0xffu;
+          uint32_t pk[4];
+          if (__builtin_expect(m8 == 0, 1)) {
 #pragma unroll
-          for (int q = 0; q < 32; q += 2) {
-            float v[2];
+            for (int q = 0; q < 8; q += 2)
+              pk[q / 2] = pack2<BF16>(fmaxf(acc[q] + adb, 0.f), fmaxf(acc[q + 1] + adb, 0.f));
+          } else {
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              if (mask & (1u << (q + h2))) {
-                if (nseg < NPRE) {
-                  adb = aq[0];
+            for (int q = 0; q < 8; q += 2) {
+              float v[2];
 #pragma unroll
-                  for (int i = 0; i + 1 < NPRE; ++i) aq[i] = aq[i + 1];
-                } else {
-                  const int c = ci[c0 + q + h2];
-                  adb = (c >= 0) ? p.a_dst[(size_t)c * H + t] : 0.f;
+              for (int h2 = 0; h2 < 2; ++h2) {
+                if (m8 & (1u << (q + h2))) {
+                  if (nseg < NPRE) {
+                    adb = aq[0];
+#pragma unroll
+                    for (int i = 0; i + 1 < NPRE; ++i) aq[i] = aq[i + 1];
+                  } else {
+                    const int c = ci[cg * 8 + q + h2];
+                    adb = (c >= 0) ? p.a_dst[(size_t)c * H + t] : 0.f;
+                  }
+                  ++nseg;
                 }
-                ++nseg;
+                v[h2] = fmaxf(acc[q + h2] + adb, 0.f);
               }
-              v[h2] = fmaxf(acc[q + h2] + adb, 0.f);
+              pk[q / 2] = pack2<BF16>(v[0], v[1]);
             }
-            pk[q / 2] = pack2<BF16>(v[0], v[1]);
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t chunk16 = ((uint32_t)(c0 / 8 + j)) ^ u_xor;
-            *reinterpret_cast<uint4*>(u_row + chunk16 * 16) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          }
+          *reinterpret_cast<uint4*>(u_row + (((uint32_t)cg ^ u_xor) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
       publish_and_issue(1);
@@ -363,37 +360,44 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
       // is added once per segment (sum p (v + b) = sum p v + b sum p).  One ex2 per element: of the
       // two rescale factors exp(m_old - m_new), exp(l - m_new) one is always 1.  A segment start only
       // resets the state (m = l, s = a = 0): the common update then yields s = 1, a = v.  Padding edges
-      // (cluster -1) open a segment that is never flushed.
+      // (cluster -1) open a run that is never flushed.
       mbar_wait(done, done_parity); done_parity ^= 1;
       tc_fence_after();
       {
-#pragma unroll
-        for (int c0 = 0; c0 < TN; c0 += 32) {
-          float lg[32], vv[32];
-          tmem_ld32(t0 + c0, lg);
-          tmem_ld32(t1 + c0, vv);
+        auto update = [&](float l, float v) {
+          const float d = l - run_m;
+          const float ex = ex2_approx(-fabsf(d) * LOG2E);
+          const bool up = d > 0.f;
+          const float sc = up ? ex : 1.f, pr = up ? 1.f : ex;
+          run_s = fmaf(run_s, sc, pr);
+          run_a = fmaf(run_a, sc, pr * v);
+          run_m = fmaxf(run_m, l);
+        };
+        // edge 0 of a tile opens a new run only if its cluster differs from the carried one
+        const uint32_t first_bit = (ci[0] != run_seg) ? 1u : 0u;
+#pragma unroll 1
+        for (int cg = 0; cg < TN / 8; ++cg) {
+          float lg[8], vv[8];
+          tmem_ld8(t0 + cg * 8, lg);
+          tmem_ld8(t1 + cg * 8, vv);
           tmem_ld_wait();
-          const uint32_t mask = seg_mask[c0 / 32];
+          uint32_t m8 = (seg_mask[(TN > 32) ? (cg >> 2) : 0] >> ((cg & 3) * 8)) & 0xffu;
+          if (cg == 0) m8 = (m8 & ~1u) | first_bit;
+          if (__builtin_expect(m8 == 0, 1)) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const int e = c0 + q;
-            const float l = lg[q], v = vv[q];
-            // edge 0 of a tile opens a new segment only if its cluster differs from the carried one
-            const bool start = (e == 0) ? (ci[0] != run_seg) : ((mask >> q) & 1u);
-            if (start) {
-              if (run_seg >= 0) flush_run(e0 + e);
-              run_seg = ci[e]; run_beg = e0 + e; run_m = l; run_s = 0.f; run_a = 0.f;
+            for (int q = 0; q < 8; ++q) update(lg[q], vv[q]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (m8 & (1u << q)) {
+                if (run_seg >= 0) { flush_run(run_whole); run_whole = true; }   // later runs start at a cluster start
+                run_seg = ci[cg * 8 + q]; run_m = lg[q]; run_s = 0.f; run_a = 0.f;
+              }
+              update(lg[q], vv[q]);
             }
-            const float d = l - run_m;
-            const float ex = ex2_approx(-fabsf(d) * LOG2E);
-            const bool up = d > 0.f;
-            const float sc = up ? ex : 1.f, pr = up ? 1.f : ex;
-            run_s = fmaf(run_s, sc, pr);
-            run_a = fmaf(run_a, sc, pr * v);
-            run_m = fmaxf(run_m, l);
           }
         }
-        if (g + 1 >= t_end && run_seg >= 0) { flush_run(e0 + n_valid); run_seg = -1; }   // chunk end
+        if (g + 1 >= t_end && run_seg >= 0) { flush_run(run_whole && chunk_whole_end); run_seg = -1; }   // chunk end
       }
       named_bar(1 + s, 128);      // everyone is done with ci[] before the next tile overwrites it
     }
@@ -457,11 +461,16 @@ int tc_pack_weights(cns_handle* h, cudaStream_t s) {
   // small first-layer weights travel in the kernel parameter space: keep a host copy
   static_assert(sizeof(TcSmallW) == sizeof(h->tc_small_host), "TcSmallW size");
   TcSmallW* sw = reinterpret_cast<TcSmallW*>(h->tc_small_host);
-  CNS_CUDA_CHECK(cudaMemcpyAsync(sw->w_in, h->P(P_IN_W), sizeof(sw->w_in), cudaMemcpyDeviceToHost, s));
-  CNS_CUDA_CHECK(cudaMemcpyAsync(sw->b_in, h->P(P_IN_B), sizeof(sw->b_in), cudaMemcpyDeviceToHost, s));
-  CNS_CUDA_CHECK(cudaMemcpyAsync(sw->w_p0, h->P(P_POS0_W), sizeof(sw->w_p0), cudaMemcpyDeviceToHost, s));
-  CNS_CUDA_CHECK(cudaMemcpyAsync(sw->b_p0, h->P(P_POS0_B), sizeof(sw->b_p0), cudaMemcpyDeviceToHost, s));
+  float w_in[128 * 2], b_in[128], w_p0[128 * 4], b_p0[128];
+  CNS_CUDA_CHECK(cudaMemcpyAsync(w_in, h->P(P_IN_W), sizeof(w_in), cudaMemcpyDeviceToHost, s));
+  CNS_CUDA_CHECK(cudaMemcpyAsync(b_in, h->P(P_IN_B), sizeof(b_in), cudaMemcpyDeviceToHost, s));
+  CNS_CUDA_CHECK(cudaMemcpyAsync(w_p0, h->P(P_POS0_W), sizeof(w_p0), cudaMemcpyDeviceToHost, s));
+  CNS_CUDA_CHECK(cudaMemcpyAsync(b_p0, h->P(P_POS0_B), sizeof(b_p0), cudaMemcpyDeviceToHost, s));
   CNS_CUDA_CHECK(cudaStreamSynchronize(s));
+  for (int k = 0; k < 128; ++k) {
+    sw->w[k][0] = make_float4(w_in[2 * k], w_in[2 * k + 1], b_in[k], b_p0[k]);
+    sw->w[k][1] = make_float4(w_p0[4 * k], w_p0[4 * k + 1], w_p0[4 * k + 2], w_p0[4 * k + 3]);
+  }
   return CNS_OK;
 }
 
