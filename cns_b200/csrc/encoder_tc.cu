@@ -75,7 +75,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
   unsigned char* tail = act_s + TC_ACT_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);            // [0] = weights landed, [1+s] = MMAs of slot s done
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tail + 128);
-  int* ci_s = reinterpret_cast<int*>(tail + 256);                // [SLOTS][TN] cluster id per edge (-1: padding)
+  int* ci_s = reinterpret_cast<int*>(tail + 256);                // [SLOTS][2][TN] cluster id per edge (-1: padding), double-buffered
 
   const EncEdgeArgs& p = args.e;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -114,7 +114,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     const int wq = warp & 3;                       // TMEM lane quarter of this warp
     unsigned char* buf0 = act_s + (s * 2 + 0) * ACT_TILE;
     unsigned char* buf1 = act_s + (s * 2 + 1) * ACT_TILE;
-    int* ci = ci_s + s * TN;
+    int* const ci_base = ci_s + s * 2 * TN;
     const uint32_t done = smem_u32(&bars[1 + s]);
     const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((s * 2 + 0) * TN);
     const uint32_t t1 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((s * 2 + 1) * TN);
@@ -173,9 +173,9 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     };
     if (wq == 0) mbar_wait(smem_u32(&bars[0]), 0);     // weights landed (only the issuing warp cares)
 
-    // Per-edge inputs of the producer (thread = edge pe, channel block kp) are fetched one tile ahead:
-    // the index loads are issued before the producer math of the current tile and the dependent
-    // coordinate gathers right after it, so both latencies hide behind the epilogues.
+    // Per-edge inputs of the producer (thread = edge pe, channel block kp) are fetched ahead: while tile i
+    // waits for its round A, the coordinate gathers of tile i+1 (their indices arrived a tile ago) and the
+    // index loads of tile i+2 are issued, so both latencies hide behind a whole tile of work.
     const int pe = (TN == 32) ? lane : ((wq & 1) * 32 + lane);   // == t % TN
     const int kp = (TN == 32) ? wq : (wq >> 1);                  // == t / TN (warp-uniform): channels [kp*TN, kp*TN + TN)
     // Work assignment: the 2 * n_tiles (side, edge tile) items are cut into gridDim.x * SLOTS contiguous
@@ -189,27 +189,34 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     const int tpc = args.tiles_per_chunk;
     const int t_begin = chunk * tpc, t_end = min(t_begin + tpc, args.n_tiles);
     auto tile_of = [&](int it) { return t_begin + it; };
-    int n_j = 0, n_cid = -1;                       // next tile: source keypoint / cluster of edge pe
-    float2 n_f = make_float2(0.f, 0.f), n_ps = n_f, n_pt = n_f, n_pc = n_f;
+    int idx_j = 0, idx_c = -1;                     // prefetched tile: source keypoint / cluster of edge pe
+    float2 c_f = make_float2(0.f, 0.f), c_ps = c_f, c_pt = c_f, c_pc = c_f;   // coordinates of the tile produced next
+    bool c_live = false;
     auto fetch_index = [&](int g) {
-      n_cid = -1; n_j = 0;
+      idx_c = -1; idx_j = 0;
       if (g < t_end) {
         const int64_t e = (int64_t)g * TN + pe;
-        if (e < p.n_e01) { n_j = (int)p.ej[e]; n_cid = (int)p.ei[e]; }
+        if (e < p.n_e01) { idx_j = (int)p.ej[e]; idx_c = (int)p.ei[e]; }
       }
     };
-    auto fetch_coords = [&](int g) {
-      if (n_cid >= 0) {
+    auto fetch_coords = [&]() {
+      c_live = idx_c >= 0;
+      if (c_live) {
         const float* __restrict__ fsrc = side ? p.x_tar : p.x_cur;
         const float* __restrict__ psrc = side ? p.pos_tar : p.pos_cur;
-        n_f = reinterpret_cast<const float2*>(fsrc)[n_j];
-        n_ps = reinterpret_cast<const float2*>(psrc)[n_j];
-        n_pt = reinterpret_cast<const float2*>(p.pos_tar)[n_j];
-        n_pc = reinterpret_cast<const float2*>(p.pos_clu)[n_cid];
+        c_f = reinterpret_cast<const float2*>(fsrc)[idx_j];
+        c_ps = reinterpret_cast<const float2*>(psrc)[idx_j];
+        c_pt = reinterpret_cast<const float2*>(p.pos_tar)[idx_j];
+        c_pc = reinterpret_cast<const float2*>(p.pos_clu)[idx_c];
       }
     };
+    // cluster ids travel through a double-buffered smem row: ci(i+1) is written while tile i waits for its
+    // round A (everyone has left tile i-1 by then) and is published by tile i's second slot barrier
     fetch_index(tile_of(0));
-    fetch_coords(tile_of(0));
+    if (kp == 0) ci_base[pe] = idx_c;
+    fetch_coords();
+    fetch_index(tile_of(1));
+    named_bar(1 + s, 128);
 
     // running softmax state of the cluster that is open at the end of a tile (carried to the next tile)
     float run_m = 0.f, run_s = 0.f, run_a = 0.f;
@@ -241,18 +248,41 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     for (int it = 0;; ++it) {
       const int g = tile_of(it);
       if (g >= t_end) break;
-      const int64_t e0 = (int64_t)g * TN;
-      const int n_valid = (int)min((int64_t)TN, p.n_e01 - e0);
+      const int* const ci = ci_base + (it & 1) * TN;
+
+      // segment-start bit per edge (bit e: ci[e] != ci[e-1]); warp-uniform registers, no per-element LDS
+      uint32_t seg_mask[TN / 32];
+#pragma unroll
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        const int e = c0 + lane;
+        const int cprev = (e == 0) ? -2 : ci[e - 1];
+        seg_mask[c0 / 32] = __ballot_sync(0xffffffffu, ci[e] != cprev);
+      }
+      // a'[cluster][t] = (A0 (a_dst + b_pos1) + b_attn0)[t] of the tile's first NPRE segment starts: the
+      // loads fly during the producer math and round A
+      float aq[NPRE];
+      {
+        uint32_t m0 = seg_mask[0];
+        uint32_t m1 = (TN > 32) ? seg_mask[(TN > 32) ? 1 : 0] : 0u;
+#pragma unroll
+        for (int i = 0; i < NPRE; ++i) {
+          aq[i] = 0.f;
+          int q = -1;
+          if (m0) { q = __ffs(m0) - 1; m0 &= m0 - 1; }
+          else if (TN > 32 && m1) { q = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
+          if (q >= 0) {
+            const int c = ci[q];
+            if (c >= 0) aq[i] = p.a_dst[(size_t)c * H + t];
+          }
+        }
+      }
 
       // ---- producer: x -> buf0, hp -> buf1 ---------------------------------------------------------
       {
-        const int cid = n_cid;
-        const bool live = cid >= 0;
-        const float f0 = live ? n_f.x : 0.f, f1 = live ? n_f.y : 0.f;
-        const float d0 = live ? n_pc.x - n_ps.x : 0.f, d1 = live ? n_pc.y - n_ps.y : 0.f;   // pos_i - pos_j
-        const float d2 = live ? n_pc.x - n_pt.x : 0.f, d3 = live ? n_pc.y - n_pt.y : 0.f;
-        if (kp == 0) ci[pe] = cid;
-        fetch_index(tile_of(it + 1));              // in flight during the producer math below
+        const bool live = c_live;
+        const float f0 = live ? c_f.x : 0.f, f1 = live ? c_f.y : 0.f;
+        const float d0 = live ? c_pc.x - c_ps.x : 0.f, d1 = live ? c_pc.y - c_ps.y : 0.f;   // pos_i - pos_j
+        const float d2 = live ? c_pc.x - c_pt.x : 0.f, d3 = live ? c_pc.y - c_pt.y : 0.f;
         // kp and gq are warp-uniform: the first-layer weights are uniform constant-bank loads
 #pragma unroll 1
         for (int gq = 0; gq < TN / 8; ++gq) {
@@ -280,40 +310,15 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
           *reinterpret_cast<uint4*>(buf1 + off) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
         }
       }
-      publish_and_issue(0);            // also makes ci[] visible to the whole slot
-
-      // segment-start bit per edge (bit e: ci[e] != ci[e-1]); warp-uniform registers, no per-element LDS
-      uint32_t seg_mask[TN / 32];
-#pragma unroll
-      for (int c0 = 0; c0 < TN; c0 += 32) {
-        const int e = c0 + lane;
-        const int cprev = (e == 0) ? -2 : ci[e - 1];
-        seg_mask[c0 / 32] = __ballot_sync(0xffffffffu, ci[e] != cprev);
-      }
-      // a'[cluster][t] = (A0 (a_dst + b_pos1) + b_attn0)[t] of the tile's first NPRE segment starts: the
-      // loads fly while the tensor core runs round A
-      float aq[NPRE];
-      {
-        uint32_t m0 = seg_mask[0];
-        uint32_t m1 = (TN > 32) ? seg_mask[(TN > 32) ? 1 : 0] : 0u;
-#pragma unroll
-        for (int i = 0; i < NPRE; ++i) {
-          aq[i] = 0.f;
-          int q = -1;
-          if (m0) { q = __ffs(m0) - 1; m0 &= m0 - 1; }
-          else if (TN > 32 && m1) { q = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
-          if (q >= 0) {
-            const int c = ci[q];
-            if (c >= 0) aq[i] = p.a_dst[(size_t)c * H + t];
-          }
-        }
-      }
+      publish_and_issue(0);
+      if (kp == 0) ci_base[((it + 1) & 1) * TN + pe] = idx_c;    // ci(i+1): its buffer was last read in tile i-1
 
       // ---- epilogue: u = relu(U + a'[cluster]) -> buf0, MN-major ([channel][edge]: this thread's row) ---
       // (padding columns of the last tile keep finite garbage; they are never read back)
       mbar_wait(done, done_parity); done_parity ^= 1;
       tc_fence_after();
-      fetch_coords(tile_of(it + 1));   // dependent gathers of the next tile fly during the epilogue and the softmax
+      fetch_coords();                  // tile i+1: dependent gathers fly during the epilogue and the softmax
+      fetch_index(tile_of(it + 2));    // tile i+2: consumed a whole tile later
       {
         float adb = 0.f;
         int nseg = 0;
@@ -399,7 +404,6 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         }
         if (g + 1 >= t_end && run_seg >= 0) { flush_run(run_whole && chunk_whole_end); run_seg = -1; }   // chunk end
       }
-      named_bar(1 + s, 128);      // everyone is done with ci[] before the next tile overwrites it
     }
   }
 
@@ -410,7 +414,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
 }
 
 // =================================================================================================
-constexpr size_t TC_SMEM_BYTES = TC_NW * TC_W_BYTES + TC_ACT_BYTES + 256 + 128 * sizeof(int) + 1024;
+constexpr size_t TC_SMEM_BYTES = TC_NW * TC_W_BYTES + TC_ACT_BYTES + 256 + 2 * 128 * sizeof(int) + 1024;
 
 template <int TN, bool BF16>
 static int launch_tc(const EncEdgeArgs& a, const unsigned char* w_img, const cns_handle* h, cudaStream_t s) {
