@@ -32,7 +32,11 @@ class cns_batch(C.Structure):
         ("l1_cur_stride", C.c_int64), ("l1_tar_stride", C.c_int64),
         ("cluster_mask", C.c_void_p), ("cluster_centers", C.c_void_p),
         ("node_graph", C.c_void_p), ("num_clusters", C.c_void_p), ("tPo_norm", C.c_void_p),
+        ("flags", C.c_int64),
     ]
+
+
+BATCH_L1_CUR_COMPLETE, BATCH_L1_TAR_COMPLETE = 1, 2
 
 
 _lib = None

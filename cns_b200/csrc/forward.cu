@@ -9,6 +9,7 @@ namespace cns {
 struct FwdBuffers {
   int* err; int* clu_rowptr; int* clu_graph; int* graph_ptr; int* gp_tmp; int* scan_scratch;
   int* cur_rowptr; int* cur_src; int* tar_rowptr; int* tar_src; void* csr_ws;
+  int* alive_idx; int* alive_cnt;
   float* a_dst; float* pos_clu; float* clu_feat; float* partial; float* x_clu;
   float* pq; float* conv0; float* conv1; float* gn0; float* gn1; float* stats0; float* stats1;
   float* x1; float* u; float* hr; float* x2; float* gate;
@@ -28,6 +29,8 @@ static void carve(Arena& ar, const cns_batch* b, FwdBuffers& f, const SaveBuffer
   f.gp_tmp = ar.take<int>(B + 1);
   f.scan_scratch = (int*)ar.take<char>(scan_scratch_bytes(B + 1));
   f.csr_ws = ar.take<char>(csr_workspace_bytes(C));
+  f.alive_idx = ar.take<int>(C + 1);
+  f.alive_cnt = ar.take<int>(B + 1);
   f.a_dst = ar.take<float>(C * H);
   f.partial = ar.take<float>((size_t)2 * f.n_slots * 3 * H);
   f.pq = ar.take<float>(C * 4 * H);
@@ -67,8 +70,8 @@ static int validate(const cns_batch* b) {
               b->n_e11_cur < (1ll << 31) && b->n_e11_tar < (1ll << 31), "sizes must fit int32");
   if (b->n_nodes > 0) CNS_REQUIRE(b->x_cur && b->x_tar && b->pos_cur && b->pos_tar, "NULL keypoint tensor");
   if (b->n_e01 > 0) CNS_REQUIRE(b->l0_to_l1_j && b->l0_to_l1_i, "NULL l0_to_l1 edge list");
-  if (b->n_e11_cur > 0) CNS_REQUIRE(b->l1_edge_cur, "NULL l1_dense_edge_index_cur");
-  if (b->n_e11_tar > 0) CNS_REQUIRE(b->l1_edge_tar, "NULL l1_dense_edge_index_tar");
+  if (b->n_e11_cur > 0 && !(b->flags & CNS_BATCH_L1_CUR_COMPLETE)) CNS_REQUIRE(b->l1_edge_cur, "NULL l1_dense_edge_index_cur");
+  if (b->n_e11_tar > 0 && !(b->flags & CNS_BATCH_L1_TAR_COMPLETE)) CNS_REQUIRE(b->l1_edge_tar, "NULL l1_dense_edge_index_tar");
   if (b->n_clusters > 0) CNS_REQUIRE(b->cluster_mask && b->cluster_centers, "NULL cluster tensor");
   if (b->n_graphs > 0) CNS_REQUIRE(b->num_clusters, "NULL num_clusters");
   return CNS_OK;
@@ -95,10 +98,17 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   // ---- index preparation ------------------------------------------------------------------
   const int64_t cur_stride = b->l1_cur_stride ? b->l1_cur_stride : b->n_e11_cur;
   const int64_t tar_stride = b->l1_tar_stride ? b->l1_tar_stride : b->n_e11_tar;
-  if (C <= PREP_SMALL_MAX && B <= PREP_SMALL_MAX && b->n_e01 <= (1 << 20) && b->n_e11_cur + b->n_e11_tar <= (1 << 20)) {
+  // complete cluster graphs (hint, verified below): no CSR, one column max per graph instead of a gather per row.
+  // Training (save != NULL) keeps the general path: the backward pass walks the CSRs.
+  const bool dense_cur = (b->flags & CNS_BATCH_L1_CUR_COMPLETE) && !sv && B <= 8192;
+  const bool dense_tar = (b->flags & CNS_BATCH_L1_TAR_COMPLETE) && !sv && B <= 8192;
+  if (!dense_cur && b->n_e11_cur > 0) CNS_REQUIRE(b->l1_edge_cur, "NULL l1_dense_edge_index_cur");
+  if (!dense_tar && b->n_e11_tar > 0) CNS_REQUIRE(b->l1_edge_tar, "NULL l1_dense_edge_index_tar");
+  const int64_t ne_cur = dense_cur ? 0 : b->n_e11_cur, ne_tar = dense_tar ? 0 : b->n_e11_tar;   // edges that need a CSR
+  if (C <= PREP_SMALL_MAX && B <= PREP_SMALL_MAX && b->n_e01 <= (1 << 20) && ne_cur + ne_tar <= (1 << 20)) {
     // servo-loop sizes: one single-CTA launch instead of thirteen
     PrepSmallArgs pa{};
-    pa.n_clusters = C; pa.n_graphs = B; pa.n_e01 = b->n_e01; pa.n_e11_cur = b->n_e11_cur; pa.n_e11_tar = b->n_e11_tar;
+    pa.n_clusters = C; pa.n_graphs = B; pa.n_e01 = b->n_e01; pa.n_e11_cur = ne_cur; pa.n_e11_tar = ne_tar;
     pa.num_clusters = b->num_clusters; pa.ei = b->l0_to_l1_i;
     pa.cur_j = b->l1_edge_cur; pa.cur_i = b->l1_edge_cur + cur_stride; pa.tar_j = b->l1_edge_tar; pa.tar_i = b->l1_edge_tar + tar_stride;
     pa.graph_ptr = f.graph_ptr; pa.clu_rowptr = f.clu_rowptr; pa.cur_rowptr = f.cur_rowptr; pa.cur_src = f.cur_src;
@@ -107,8 +117,18 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   } else {
     RUN(sorted_rowptr(b->l0_to_l1_i, b->n_e01, C, f.clu_rowptr, f.err, s));
     RUN(graph_ptr_from_counts(b->num_clusters, B, f.graph_ptr, f.gp_tmp, f.scan_scratch, s));
-    RUN(csr_by_dst(b->l1_edge_cur, b->l1_edge_cur + cur_stride, b->n_e11_cur, C, f.cur_rowptr, f.cur_src, f.csr_ws, f.err, s));
-    RUN(csr_by_dst(b->l1_edge_tar, b->l1_edge_tar + tar_stride, b->n_e11_tar, C, f.tar_rowptr, f.tar_src, f.csr_ws, f.err, s));
+    if (!dense_cur) RUN(csr_by_dst(b->l1_edge_cur, b->l1_edge_cur + cur_stride, b->n_e11_cur, C, f.cur_rowptr, f.cur_src, f.csr_ws, f.err, s));
+    if (!dense_tar) RUN(csr_by_dst(b->l1_edge_tar, b->l1_edge_tar + tar_stride, b->n_e11_tar, C, f.tar_rowptr, f.tar_src, f.csr_ws, f.err, s));
+  }
+  if (dense_cur || dense_tar) {
+    L1CompleteArgs la{};
+    la.n_graphs = B; la.graph_ptr = f.graph_ptr; la.alive_idx = f.alive_idx; la.alive_cnt = f.alive_cnt; la.err = f.err;
+    if (dense_cur) {
+      la.cur_mask = b->cluster_mask;
+      if (b->l1_edge_cur) { la.cur_j = b->l1_edge_cur; la.cur_i = b->l1_edge_cur + cur_stride; la.n_e11_cur = b->n_e11_cur; }
+    }
+    if (dense_tar && b->l1_edge_tar) { la.tar_j = b->l1_edge_tar; la.tar_i = b->l1_edge_tar + tar_stride; la.n_e11_tar = b->n_e11_tar; }
+    RUN(l1_complete_verify(la, s));
   }
 
   // ---- encoder ----------------------------------------------------------------------------
@@ -176,6 +196,12 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
                      unsigned char* const* fc_img, float* conv, float* gnb, float* stats, int* arg) {
     int r;
     if ((r = pq_linear(x, nullptr, wt, wp, bias, 2 * H, img, H)) != CNS_OK) return r;
+    if (dense_cur) {
+      EdgeConvDenseArgs ed{};
+      ed.n_graphs = B; ed.f_out = H; ed.mode = EC_PLAIN; ed.pq = f.pq; ed.graph_ptr = f.graph_ptr; ed.mask = b->cluster_mask;
+      ed.gn_weight = h->P(bn_w); ed.gn_bias = h->P(bn_b); ed.gn_mean_scale = h->P(bn_ms); ed.gn_out = gnb;
+      if ((r = edgeconv_dense(ed, s)) != CNS_OK) return r;
+    } else {
     EdgeConvArgs ec{};
     ec.n_rows = C; ec.f_out = H; ec.mode = EC_PLAIN; ec.pq = f.pq; ec.rowptr = f.cur_rowptr; ec.src = f.cur_src;
     ec.out = conv; ec.argmax = arg;
@@ -184,6 +210,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     gn.n_graphs = B; gn.graph_ptr = f.graph_ptr; gn.x = conv; gn.weight = h->P(bn_w); gn.bias = h->P(bn_b);
     gn.mean_scale = h->P(bn_ms); gn.y = gnb; gn.stats = stats;
     if ((r = graphnorm_relu(gn, s)) != CNS_OK) return r;
+    }
     if (tc) {
       GemmTcArgs ga{};
       ga.m = C; ga.k1 = H; ga.k2 = 0; ga.n_out = H; ga.x1 = gnb; ga.w_img = fc_img[tci]; ga.bias = h->P(fc_b);
@@ -200,14 +227,24 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
 
   // GRU gates on the TARGET cluster graph, candidate on the CURRENT one (graph_vs.py:246-249)
   RUN(pq_linear(f.x1, hidden_in, pk.g_wt, pk.g_wp, pk.g_b, 4 * H, pk.tc_g, 2 * H));
-  {
+  if (dense_tar) {
+    EdgeConvDenseArgs ed{};
+    ed.n_graphs = B; ed.f_out = 2 * H; ed.mode = EC_GATES; ed.pq = f.pq; ed.graph_ptr = f.graph_ptr; ed.mask = nullptr;
+    ed.h = hidden_in; ed.hr = f.hr; ed.u = f.u;
+    RUN(edgeconv_dense(ed, s));
+  } else {
     EdgeConvArgs ec{};
     ec.n_rows = C; ec.f_out = 2 * H; ec.mode = EC_GATES; ec.pq = f.pq; ec.rowptr = f.tar_rowptr; ec.src = f.tar_src;
     ec.h = hidden_in; ec.hr = f.hr; ec.u = f.u; ec.argmax = f.argg; ec.act = f.g;
     RUN(edgeconv_max(ec, s));
   }
   RUN(pq_linear(f.x1, hidden_in ? f.hr : nullptr, pk.k_wt, pk.k_wp, pk.k_b, 2 * H, pk.tc_k, 2 * H));
-  {
+  if (dense_cur) {
+    EdgeConvDenseArgs ed{};
+    ed.n_graphs = B; ed.f_out = H; ed.mode = EC_CANDIDATE; ed.pq = f.pq; ed.graph_ptr = f.graph_ptr; ed.mask = b->cluster_mask;
+    ed.h = hidden_in; ed.u_in = f.u; ed.h_out = hidden_out;
+    RUN(edgeconv_dense(ed, s));
+  } else {
     EdgeConvArgs ec{};
     ec.n_rows = C; ec.f_out = H; ec.mode = EC_CANDIDATE; ec.pq = f.pq; ec.rowptr = f.cur_rowptr; ec.src = f.cur_src;
     ec.h = hidden_in; ec.u_in = f.u; ec.h_out = hidden_out; ec.argmax = f.argk; ec.act = f.ht;
@@ -281,6 +318,7 @@ int cns_forward_status(const void* workspace, void* stream) {
   CNS_CUDA_CHECK(cudaMemcpyAsync(&flag, workspace, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CNS_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
   if (flag == 1) { set_error("l0_to_l1_edge_index_i is not sorted by cluster / out of range"); return CNS_ERR_UNSORTED_EDGES; }
+  if (flag == 3) { set_error("cluster-level edge lists are not the complete graphs claimed by cns_batch.flags"); return CNS_ERR_INVALID_ARGUMENT; }
   if (flag != 0) { set_error("edge index out of range"); return CNS_ERR_INVALID_ARGUMENT; }
   return CNS_OK;
 }

@@ -106,6 +106,27 @@ struct EdgeConvArgs {
 };
 int edgeconv_max(const EdgeConvArgs& a, cudaStream_t s);
 
+// ---- dense_l1.cu: cluster graphs that are complete digraphs (CNS_BATCH_L1_*_COMPLETE) -----------------
+struct L1CompleteArgs {
+  int64_t n_graphs; const int* graph_ptr;
+  const uint8_t* cur_mask;                        // non-NULL: the current-side list is claimed complete over mask != 0
+  const int64_t* cur_j; const int64_t* cur_i; int64_t n_e11_cur;   // NULL: nothing to verify (graph implied by the mask)
+  const int64_t* tar_j; const int64_t* tar_i; int64_t n_e11_tar;   // NULL: target side not claimed / implied
+  int* alive_idx; int* alive_cnt;                 // scratch (C,), (B,)
+  int* err;
+};
+int l1_complete_verify(const L1CompleteArgs& a, cudaStream_t s);
+
+struct EdgeConvDenseArgs {
+  int64_t n_graphs; int f_out; int mode;
+  const float* pq; const int* graph_ptr;
+  const uint8_t* mask;     // node set of every graph: rows with mask != 0, or every row when NULL
+  float* out;              // EC_PLAIN without GraphNorm: (n, f)
+  const float* gn_weight; const float* gn_bias; const float* gn_mean_scale; float* gn_out;   // EC_PLAIN + GraphNorm + ReLU
+  const float* h; float* hr; float* u; const float* u_in; float* h_out;                      // as EdgeConvArgs
+};
+int edgeconv_dense(const EdgeConvDenseArgs& a, cudaStream_t s);
+
 struct GraphNormArgs {
   int64_t n_graphs; const int* graph_ptr; const float* x;
   const float* weight; const float* bias; const float* mean_scale;

@@ -234,6 +234,8 @@ class Batch(GraphData):
                     off = torch.repeat_interleave(node_off if kind == 1 else clu_off, lens)
                     cat = cat + off  # broadcasts over the leading 2 of (2, E) edge lists
                 out[key] = cat
+            elif key == "l1_complete":
+                out[key] = all(bool(v) for v in vals)
             elif isinstance(v0, (int, float)) and not isinstance(v0, bool):
                 out[key] = torch.tensor(vals)
             else:

@@ -247,6 +247,9 @@ class GraphGenerator(object):
             cluster_mask=torch.from_numpy(cluster_mask).bool(),
             cluster_centers_index=i64(self.cluster_centers_index),
             belong_cluster_index=i64(self.belong_cluster_index),
+            # both cluster-level edge lists are complete digraphs (all clusters / alive clusters) in the
+            # source-major order of gen_dense_connect_edges: lets the forward skip the CSR build
+            l1_complete=True,
         )
 
     def default_feature(self, points):

@@ -262,6 +262,8 @@ class GraphVS(nn.Module):
         b.l1_cur_stride, b.l1_tar_stride = 0, 0
         b.cluster_mask, b.cluster_centers = p(cmask), p(ctr)
         b.node_graph, b.num_clusters, b.tPo_norm = p(batch), p(ncl), p(tpo)
+        complete = data.get("l1_complete", False) if isinstance(data, dict) else getattr(data, "l1_complete", False)
+        b.flags = (_lib.BATCH_L1_CUR_COMPLETE | _lib.BATCH_L1_TAR_COMPLETE) if complete is True else 0
         return b, keep
 
     # ------------------------------------------------------------------ forward

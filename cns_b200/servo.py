@@ -88,6 +88,7 @@ class BatchedServo(object):
         b.l1_cur_stride, b.l1_tar_stride = self.e11.shape[1], 0
         b.cluster_mask, b.cluster_centers = p(self.cmask), p(self.centers)
         b.node_graph, b.num_clusters, b.tPo_norm = None, p(self.num_clusters), p(self.tpo)
+        b.flags = L.BATCH_L1_CUR_COMPLETE | L.BATCH_L1_TAR_COMPLETE     # what cns_graph_mask / GraphGenerator emit
         h = self.net._handle(dev)
         ws = self.net._workspace(dev.index, lib.cns_forward_workspace_bytes(C.byref(b)))
         B = self.B

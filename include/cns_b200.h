@@ -105,7 +105,18 @@ typedef struct cns_batch {
   const int64_t* node_graph;      /* (N,)  `batch` vector, or NULL => all zero    */
   const int64_t* num_clusters;    /* (B,)  clusters per graph                     */
   const float* tPo_norm;          /* (B,)  distance scale, or NULL => 1           */
+  int64_t flags;                  /* CNS_BATCH_* hints, 0 = none                   */
 } cns_batch;
+
+/* Structure hints about the cluster-level edge lists.  What GraphGenerator builds (graph_gen.py:31-36 via
+ * :199-228) is, per graph, the complete digraph WITH self loops over a node set, in source-major order:
+ * all clusters for l1_dense_edge_index_tar, the clusters with cluster_mask != 0 for ..._cur.  With the
+ * hint set the forward skips the CSR build and replaces every max-aggregation over neighbours by one
+ * column max per graph.  The claim is verified on the device on every call; a violation is reported by
+ * cns_forward_status (CNS_ERR_INVALID_ARGUMENT) and the outputs of that call are undefined.  Ignored when
+ * `save` != NULL (training keeps the general path). */
+#define CNS_BATCH_L1_CUR_COMPLETE 1
+#define CNS_BATCH_L1_TAR_COMPLETE 2
 
 /* Replaces GraphVS.forward (graph_vs.py:284-322) + GraphVS.postprocess
  * (functions.py:26-38).  hidden_in may be NULL (== init_hidden zeros, graph_vs.py:315).

@@ -124,6 +124,34 @@ def test_deterministic_and_batch_invariant(net):
     assert rel(solo[0], full[0][5:6]) < 1e-5
 
 
+def test_complete_graph_path_matches_general_path_and_is_verified(net):
+    """Batches built by GraphGenerator carry l1_complete (cns_batch.flags): the forward then replaces the
+    per-row neighbour gathers by one column max per graph.  Same result as the general CSR path, and a
+    list that is not the complete digraph it claims to be is reported by check=True."""
+    batch = synth.make_batch(6, 200, seed=11, missing_frac=0.4, n_layouts=3)
+    assert batch.l1_complete is True
+    dev = batch.to("cuda:0")
+    hid = torch.randn(dev.cluster_centers_index.shape[0], 128, device="cuda:0")
+    with torch.no_grad():
+        a = net(dev, hid, check=True)
+        dev.l1_complete = False
+        b = net(dev, hid, check=True)
+    for x, y in zip(a, b):
+        assert rel(x, y) < 1e-6
+    bad = batch.to("cuda:0")
+    bad.l1_dense_edge_index_cur = bad.l1_dense_edge_index_cur[:, 1:].contiguous()      # one edge short
+    with pytest.raises(_lib.CnsError):
+        with torch.no_grad():
+            net(bad, None, check=True)
+    bad = batch.to("cuda:0")
+    e = bad.l1_dense_edge_index_tar.clone()
+    e[1, 5] = e[1, 6]                                                                  # right count, wrong pair
+    bad.l1_dense_edge_index_tar = e
+    with pytest.raises(_lib.CnsError):
+        with torch.no_grad():
+            net(bad, None, check=True)
+
+
 def test_unsorted_cluster_edges_are_reported(net):
     d = synth.Scene(np.random.default_rng(1), 40).frame().to("cuda:0")
     d.l0_to_l1_edge_index_i_cur = d.l0_to_l1_edge_index_i_cur.flip(0).contiguous()
