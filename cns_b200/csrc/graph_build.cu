@@ -128,7 +128,7 @@ int cns_graph_mask(const int64_t* belong, const int64_t* member_order, const int
   CNS_REQUIRE(n_nodes >= 0 && n_clusters >= 0 && n_graphs >= 0, "negative size");
   CNS_REQUIRE(n_nodes < (1ll << 31) && n_clusters < (1ll << 31), "sizes must fit int32");
   CNS_REQUIRE(belong && member_order && cluster_size && cluster_graph_ptr && visible && e01_j && e01_i &&
-              e11_cur && cluster_mask && counts_out && workspace, "NULL pointer");
+              cluster_mask && counts_out && workspace, "NULL pointer");
   if (workspace_bytes < cns_graph_mask_workspace_bytes(n_nodes, n_clusters, n_graphs)) {
     set_error("cns_graph_mask: workspace too small");
     return CNS_ERR_WORKSPACE_TOO_SMALL;
@@ -160,6 +160,10 @@ int cns_graph_mask(const int64_t* belong, const int64_t* member_order, const int
   e01_scatter_kernel<<<ceil_div(n_nodes + 1, T), T, 0, s>>>(member_order, belong, flag, pos, n_nodes, e01_j, e01_i,
                                                             counts_out);
   CNS_LAUNCH_CHECK();
+  if (e11_cur == nullptr) {   // the caller only needs cluster_mask: the cluster graph is implied (CNS_BATCH_L1_CUR_COMPLETE)
+    CNS_CUDA_CHECK(cudaMemsetAsync(counts_out + 1, 0, sizeof(int64_t), s));
+    return CNS_OK;
+  }
   if ((rc = exclusive_scan_i32(alive, n_clusters, arank, scratch, s)) != CNS_OK) return rc;
   if (n_clusters > 0) {
     alive_list_kernel<<<ceil_div(n_clusters, T), T, 0, s>>>(alive, arank, n_clusters, list);

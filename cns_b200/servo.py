@@ -6,10 +6,11 @@ keypoints that were not matched (`Midend.get_graph_data`, cns/midend/corr2graph.
 `GraphGenerator.get_data`, graph_gen.py:236-277) before collating B python objects with
 `Batch.from_data_list` (sim/dataset.py:206-209).  `BatchedServo` keeps that split for B scenes at once
 (SURVEY 8f2): constructor = "target changed" (static tensors uploaded once: target keypoints, cluster
-membership, centres, the full cluster graph); `step(cur_xy, visible)` = one frame: H2D of the current
-keypoint coordinates + visibility mask, `cns_graph_mask` (per-frame sub-graph, bit-exact with
+membership, centres); `step(cur_xy, visible)` = one frame: H2D of the current keypoint coordinates +
+visibility mask, `cns_graph_mask` (per-frame keypoint->cluster edges and cluster mask, bit-exact with
 `_get_graph` + collation), `cns_graphvs_forward` with the hidden state carried on the device, D2H of the
-(B,6) velocities.
+(B,6) velocities.  The cluster-level graphs are complete digraphs (all clusters / alive clusters), so
+they are passed as a flag instead of edge lists (CNS_BATCH_L1_*_COMPLETE).
 """
 import ctypes as C
 from typing import Sequence
@@ -39,16 +40,12 @@ class BatchedServo(object):
         self.cluster_size = d(np.concatenate([g.cluster_points_count for g in gens]), torch.int64)
         self.cluster_graph_ptr = d(np.concatenate([[0], np.cumsum(n_clu)]), torch.int64)
         self.centers = d(np.concatenate([g.cluster_centers_index + o for g, o in zip(gens, noff)]), torch.int64)
-        self.l1_tar = d(np.concatenate([g.l1_dense_edge_index + c for g, c in zip(gens, coff)], axis=1), torch.int64)
         self.num_clusters = d(n_clu, torch.int64)
         self.tpo = d(np.broadcast_to(np.asarray(dist_scale, dtype=np.float32), (self.B,)), torch.float32)
-        self.cap = int((n_clu ** 2).sum())
         i64 = lambda n: torch.empty(n, dtype=torch.int64, device=self.dev)
         self.e01_j, self.e01_i = i64(max(self.N, 1)), i64(max(self.N, 1))
-        self.e11 = torch.empty(2, max(self.cap, 1), dtype=torch.int64, device=self.dev)
         self.cmask = torch.empty(max(self.Cn, 1), dtype=torch.uint8, device=self.dev)
         self.counts = torch.zeros(2, dtype=torch.int64, device=self.dev)
-        self.counts_host = torch.zeros(2, dtype=torch.int64).pin_memory()
         self.mask_ws = torch.empty(self.lib.cns_graph_mask_workspace_bytes(self.N, self.Cn, self.B), dtype=torch.uint8,
                                    device=self.dev)
         self.xy_dev = torch.empty(self.N, 2, dtype=torch.float32, device=self.dev)
@@ -58,37 +55,41 @@ class BatchedServo(object):
         self.out = torch.empty(self.B * 13, dtype=torch.float32, device=self.dev)
         self.vel_host = torch.empty(self.B, 6).pin_memory()
         self.h2d_bytes = self.N * 2 * 4 + self.N
-        self.d2h_bytes = self.B * 6 * 4 + 16
+        self.d2h_bytes = self.B * 6 * 4
 
     def reset(self):
         self.have_hidden = False
 
     def step(self, cur_xy: torch.Tensor, visible: torch.Tensor, wait: bool = True) -> torch.Tensor:
         """cur_xy (sum N, 2) float32 and visible (sum N,) uint8/bool HOST tensors (pinned for full speed), in
-        the scenes' keypoint order.  Returns the (B, 6) velocities in pinned host memory."""
+        the scenes' keypoint order.  Returns the (B, 6) velocities in pinned host memory.
+
+        The current-side cluster graph is never materialised: it is the complete digraph over the clusters
+        that keep a visible keypoint (graph_gen.py:199-228), which the forward handles from cluster_mask
+        alone (CNS_BATCH_L1_CUR_COMPLETE), and the number of keypoint->cluster edges is the number of visible
+        keypoints - so nothing is read back from the device before the velocities."""
         lib, L, dev = self.lib, _lib, self.dev
         stream = L.stream_ptr(dev)
+        vis = visible.view(torch.uint8) if visible.dtype == torch.bool else visible
+        n01 = int(torch.count_nonzero(vis))
         self.xy_dev.copy_(cur_xy, non_blocking=True)
-        self.vis_dev.copy_(visible.view(torch.uint8) if visible.dtype == torch.bool else visible, non_blocking=True)
+        self.vis_dev.copy_(vis, non_blocking=True)
         L.check(lib.cns_graph_mask(L.ptr(self.belong), L.ptr(self.member_order), L.ptr(self.cluster_size),
                                    L.ptr(self.cluster_graph_ptr), L.ptr(self.vis_dev), self.N, self.Cn, self.B,
-                                   L.ptr(self.e01_j), L.ptr(self.e01_i), L.ptr(self.e11), self.e11.shape[1],
+                                   L.ptr(self.e01_j), L.ptr(self.e01_i), None, 0,
                                    L.ptr(self.cmask), L.ptr(self.counts), L.ptr(self.mask_ws), self.mask_ws.numel(), stream),
                 "cns_graph_mask")
-        self.counts_host.copy_(self.counts, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()          # edge counts size the forward's grids
-        n01, n11 = int(self.counts_host[0]), int(self.counts_host[1])
         b = L.cns_batch()
         b.n_nodes, b.n_clusters, b.n_graphs = self.N, self.Cn, self.B
-        b.n_e01, b.n_e11_cur, b.n_e11_tar = n01, n11, self.l1_tar.shape[1]
+        b.n_e01, b.n_e11_cur, b.n_e11_tar = n01, 0, 0
         p = lambda t: t.data_ptr()
         b.x_cur, b.pos_cur, b.x_tar, b.pos_tar = p(self.xy_dev), p(self.xy_dev), p(self.x_tar), p(self.x_tar)
         b.l0_to_l1_j, b.l0_to_l1_i = p(self.e01_j), p(self.e01_i)
-        b.l1_edge_cur, b.l1_edge_tar = p(self.e11), p(self.l1_tar)
-        b.l1_cur_stride, b.l1_tar_stride = self.e11.shape[1], 0
+        b.l1_edge_cur, b.l1_edge_tar = None, None               # both cluster graphs are implied (complete)
+        b.l1_cur_stride, b.l1_tar_stride = 0, 0
         b.cluster_mask, b.cluster_centers = p(self.cmask), p(self.centers)
         b.node_graph, b.num_clusters, b.tPo_norm = None, p(self.num_clusters), p(self.tpo)
-        b.flags = L.BATCH_L1_CUR_COMPLETE | L.BATCH_L1_TAR_COMPLETE     # what cns_graph_mask / GraphGenerator emit
+        b.flags = L.BATCH_L1_CUR_COMPLETE | L.BATCH_L1_TAR_COMPLETE
         h = self.net._handle(dev)
         ws = self.net._workspace(dev.index, lib.cns_forward_workspace_bytes(C.byref(b)))
         B = self.B

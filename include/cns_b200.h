@@ -215,6 +215,9 @@ int cns_linear(const float* x1, int k1, const float* x2, int k2, const float* wt
  *   out: e01_j, e01_i (<=N) ; e11_cur (2, <= sum C_g^2) written as two rows of stride
  *        e11_capacity (pass it as cns_batch.l1_cur_stride) ; cluster_mask (C,) ;
  *        counts_out[0]=E01, [1]=E11cur (device int64).
+ *        e11_cur may be NULL: the current-side cluster graph is then left implied by cluster_mask
+ *        (complete digraph over the alive clusters, what CNS_BATCH_L1_CUR_COMPLETE describes) and
+ *        counts_out[1] is 0.  E01 equals the number of visible keypoints, which the host already knows.
  */
 size_t cns_graph_mask_workspace_bytes(int64_t n_nodes, int64_t n_clusters, int64_t n_graphs);
 int cns_graph_mask(const int64_t* belong, const int64_t* member_order, const int64_t* cluster_size,
