@@ -37,13 +37,16 @@ __global__ void gemm_tc_pack_kernel(const float* __restrict__ wt, int k_dim, int
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(GT_THREADS, 1)
+__global__ void __launch_bounds__(GT_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ GemmTcArgs p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // buffers are sized by the actual K (a K = 128 product needs half the bytes: two CTAs then share an SM,
+  // which matters because ceil(M / 128) tiles rarely divide the SM count)
+  const uint32_t a_bytes = 128u * (uint32_t)(p.k1 + p.k2) * 2u, w_bytes = a_bytes;
   unsigned char* a_s = smem;
-  unsigned char* w_s = smem + GemmTcSmem::A_BYTES;
-  float* vec_s = reinterpret_cast<float*>(w_s + 2 * GemmTcSmem::W_BYTES);
+  unsigned char* w_s = smem + a_bytes;
+  float* vec_s = reinterpret_cast<float*>(w_s + 2 * w_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(vec_s + GemmTcSmem::VEC_FLOATS);   // [0..1] wfull, [2..5] done
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 8);
 
@@ -65,7 +68,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcArgs p) {
     if (lane == 0) {
       for (int c = 0; c < 2 && c < n_chunks; ++c) {
         mbar_expect_tx(smem_u32(&bars[c]), chunk_bytes);
-        bulk_g2s(smem_u32(w_s + c * GemmTcSmem::W_BYTES), p.w_img + (size_t)c * chunk_stride, chunk_bytes, smem_u32(&bars[c]));
+        bulk_g2s(smem_u32(w_s + c * w_bytes), p.w_img + (size_t)c * chunk_stride, chunk_bytes, smem_u32(&bars[c]));
       }
     }
   } else {
@@ -105,7 +108,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcArgs p) {
         const int b = c & 1;
         mbar_wait(smem_u32(&bars[b]), (uint32_t)((c >> 1) & 1));
         tc_fence_after();
-        const uint32_t w_base = smem_u32(w_s + b * GemmTcSmem::W_BYTES);
+        const uint32_t w_base = smem_u32(w_s + b * w_bytes);
         const uint32_t d = tmem_base + (uint32_t)(c * 128);
         for (int kc = 0; kc < K / 64; ++kc)
 #pragma unroll
@@ -116,7 +119,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcArgs p) {
         if (c + 2 < n_chunks) {                      // refill this buffer once its MMAs have drained
           mbar_wait(smem_u32(&bars[2 + c]), 0);
           mbar_expect_tx(smem_u32(&bars[b]), chunk_bytes);
-          bulk_g2s(smem_u32(w_s + b * GemmTcSmem::W_BYTES), p.w_img + (size_t)(c + 2) * chunk_stride, chunk_bytes,
+          bulk_g2s(smem_u32(w_s + b * w_bytes), p.w_img + (size_t)(c + 2) * chunk_stride, chunk_bytes,
                    smem_u32(&bars[b]));
         }
       }
@@ -181,8 +184,9 @@ int gemm_tc(const GemmTcArgs& a, bool bf16, cudaStream_t s) {
     configured = true;
   }
   const int grid = ceil_div(a.m, 128);
-  if (bf16) gemm_tc_kernel<true><<<grid, GT_THREADS, GemmTcSmem::TOTAL, s>>>(a);
-  else gemm_tc_kernel<false><<<grid, GT_THREADS, GemmTcSmem::TOTAL, s>>>(a);
+  const size_t smem = (size_t)3 * 128 * (a.k1 + a.k2) * 2 + GemmTcSmem::VEC_FLOATS * 4 + 256 + 1024;
+  if (bf16) gemm_tc_kernel<true><<<grid, GT_THREADS, smem, s>>>(a);
+  else gemm_tc_kernel<false><<<grid, GT_THREADS, smem, s>>>(a);
   CNS_LAUNCH_CHECK();
   return CNS_OK;
 }
