@@ -32,7 +32,7 @@ class cns_batch(C.Structure):
         ("l1_cur_stride", C.c_int64), ("l1_tar_stride", C.c_int64),
         ("cluster_mask", C.c_void_p), ("cluster_centers", C.c_void_p),
         ("node_graph", C.c_void_p), ("num_clusters", C.c_void_p), ("tPo_norm", C.c_void_p),
-        ("flags", C.c_int64),
+        ("flags", C.c_int64), ("max_clusters_per_graph", C.c_int64),
     ]
 
 

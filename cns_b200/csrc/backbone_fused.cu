@@ -1,0 +1,437 @@
+// Fused cluster-level backbone (tcgen05): PERConv -> PEConvGRUCell -> PERConv in ONE kernel
+// (cns/models/graph_vs.py:115-190,233-251), for batches whose cluster graphs are complete digraphs
+// (CNS_BATCH_L1_*_COMPLETE) with at most 128 clusters per graph.
+//
+// With complete graphs the only coupling between cluster rows is per graph: the column max of the
+// PointEdgeConv messages and the GraphNorm statistics.  A CTA therefore owns a tile of WHOLE graphs
+// (<= 128 cluster rows = the 128 TMEM lanes) and walks the six GEMMs of the chain back to back:
+//
+//   x --c0 [P|Q]--> max/GraphNorm/ReLU --c0.fc + x--> y0
+//   [y0|h] --gates [P|Q]--> max/sigmoid -> r, u ; [y0|h*r] --candidate [P|Q]--> max/tanh -> h' = (1-u) h + u c
+//   h' --c1 [P|Q]--> max/GraphNorm/ReLU --c1.fc + h'--> x2
+//
+// Activations never leave the SM between the layers: the A operand (16-bit, K-major SWIZZLE_128B) is
+// rebuilt in shared memory by every epilogue, accumulators live in TMEM, the per-graph reductions go
+// through one fp32 staging tile (thread = row writes, thread = column reduces, conflict-free with a
+// 129-float row pitch).  Weights stream from L2 as 16 KB atoms (128 outputs x 64 k) through a 4-deep
+// TMA ring that runs ahead across GEMM boundaries.  Warps 0-7: epilogues (warp % 4 = TMEM lane quarter,
+// warp / 4 = column half of each 128-column chunk); warp 8: TMA + MMA issue.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace cns {
+
+constexpr int BF_THREADS = 288;
+constexpr int BF_ATOM = 128 * 128;        // bytes: 128 output rows x 64 k x 2 B
+constexpr int BF_RING = 4;
+constexpr int BF_LD = 129;                // staging row pitch (floats)
+constexpr int BF_NVEC = 1536;             // per-column epilogue vectors of the six GEMMs, concatenated
+constexpr int BF_MAX_ATOMS = 40;
+// vector bases of the six GEMMs inside the concatenation
+constexpr int VB_C0 = 0, VB_C0FC = 256, VB_G = 384, VB_K = 896, VB_C1 = 1152, VB_C1FC = 1408;
+
+constexpr size_t BF_SMEM = 65536 /*A*/ + BF_RING * BF_ATOM /*ring*/ + 128 * BF_LD * 4 /*staging*/ + 3 * BF_NVEC * 4 +
+                           BF_MAX_ATOMS * 16 + 1024 /*bars, tables*/ + 1024 /*alignment slack*/;
+
+// ---- tiles of whole graphs --------------------------------------------------------------------------
+// tile_graph[t] = first graph of tile t (greedy: as many consecutive graphs as fit in 128 rows)
+__global__ void __launch_bounds__(1024)
+tile_pack_kernel(const int* __restrict__ graph_ptr, int n_graphs, int* __restrict__ next, int* __restrict__ tile_graph,
+                 int* __restrict__ n_tiles, int* __restrict__ err) {
+  // next[g] = first graph that does not fit into a tile starting at g (binary search on the prefix sums)
+  for (int g = threadIdx.x; g < n_graphs; g += 1024) {
+    const int lim = graph_ptr[g] + 128;
+    if (graph_ptr[g + 1] > lim) atomicExch(err, 4);     // a graph with more than 128 clusters
+    int lo = g + 1, hi = n_graphs;                      // largest q in [g+1, B] with graph_ptr[q] <= lim
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (graph_ptr[mid] <= lim) lo = mid; else hi = mid - 1;
+    }
+    next[g] = lo;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0, g = 0;
+    while (g < n_graphs) { tile_graph[t++] = g; const int q = next[g]; g = q > g ? q : g + 1; }
+    tile_graph[t] = n_graphs;
+    *n_tiles = t;
+  }
+}
+
+struct BfAtom { const unsigned char* src; int meta; int pad; };   // meta: g | nc << 4 | kc << 8 | first << 12 | last << 13
+
+template <bool BF16>
+__global__ void __launch_bounds__(BF_THREADS, 1)
+backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
+  const int tile = blockIdx.x;
+  if (tile >= *p.n_tiles) return;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* a_s = smem;                                   // [4 k-chunks][128 rows][128 B]
+  unsigned char* ring = a_s + 65536;
+  float* stg = reinterpret_cast<float*>(ring + BF_RING * BF_ATOM);
+  float* vec = stg + 128 * BF_LD;                              // [3][BF_NVEC]: bias, wp row 0, wp row 1
+  BfAtom* atoms = reinterpret_cast<BfAtom*>(vec + 3 * BF_NVEC);
+  unsigned char* tail = reinterpret_cast<unsigned char*>(atoms + BF_MAX_ATOMS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // full[4], empty[4], done[6]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tail + 128);
+  int* n_atoms_s = reinterpret_cast<int*>(tail + 136);
+  int* g_beg = reinterpret_cast<int*>(tail + 144);             // [<=129] local first row of the tile's graphs
+  unsigned char* alive_s = tail + 144 + 132 * 4;               // [128]
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int g0 = p.tile_graph[tile], g1 = p.tile_graph[tile + 1];
+  const int G = g1 - g0;
+  const int row0 = p.graph_ptr[g0];
+  const int R = p.graph_ptr[g1] - row0;
+  if (R > 128) return;                                         // a graph above the advertised bound (status word set by tile_pack)
+  const bool has_h = p.hidden_in != nullptr;
+  const int kh = has_h ? 4 : 2;                                // k-chunks of the two GRU products
+
+  // ---- per-tile tables ---------------------------------------------------------------------------------
+  for (int k = tid; k <= G; k += BF_THREADS) g_beg[k] = p.graph_ptr[g0 + k] - row0;
+  for (int r = tid; r < 128; r += BF_THREADS) alive_s[r] = (r < R && p.mask[row0 + r]) ? 1 : 0;
+  for (int i = tid; i < BF_NVEC; i += BF_THREADS) {
+    const float* b; const float* wp; int j, n;
+    if (i < VB_C0FC) { b = p.c0_b; wp = p.c0_wp; j = i; n = 256; }
+    else if (i < VB_G) { b = p.c0fc_b; wp = nullptr; j = i - VB_C0FC; n = 128; }
+    else if (i < VB_K) { b = p.g_b; wp = p.g_wp; j = i - VB_G; n = 512; }
+    else if (i < VB_C1) { b = p.k_b; wp = p.k_wp; j = i - VB_K; n = 256; }
+    else if (i < VB_C1FC) { b = p.c1_b; wp = p.c1_wp; j = i - VB_C1; n = 256; }
+    else { b = p.c1fc_b; wp = nullptr; j = i - VB_C1FC; n = 128; }
+    vec[i] = b[j];
+    vec[BF_NVEC + i] = wp ? wp[j] : 0.f;
+    vec[2 * BF_NVEC + i] = wp ? wp[n + j] : 0.f;
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int i = 0; i < 14; ++i) mbar_init(smem_u32(&bars[i]), 1);
+      fence_mbar_init();
+      // weight atoms in issue order
+      const unsigned char* img[6] = {p.w_c0, p.w_c0fc, p.w_g, p.w_k, p.w_c1, p.w_c1fc};
+      const int ncs[6] = {2, 1, 4, 2, 2, 1};
+      const int kimg[6] = {2, 2, 4, 4, 2, 2};
+      const int kuse[6] = {2, 2, kh, kh, 2, 2};
+      int n = 0;
+      for (int g = 0; g < 6; ++g)
+        for (int nc = 0; nc < ncs[g]; ++nc)
+          for (int kc = 0; kc < kuse[g]; ++kc) {
+            const bool first = nc == 0 && kc == 0, last = nc == ncs[g] - 1 && kc == kuse[g] - 1;
+            atoms[n].src = img[g] + (size_t)(nc * kimg[g] + kc) * BF_ATOM;
+            atoms[n].meta = g | (nc << 4) | (kc << 8) | ((int)first << 12) | ((int)last << 13);
+            ++n;
+          }
+      *n_atoms_s = n;
+      for (int i = 0; i < BF_RING; ++i) {
+        mbar_expect_tx(smem_u32(&bars[i]), BF_ATOM);
+        bulk_g2s(smem_u32(ring + i * BF_ATOM), atoms[i].src, BF_ATOM, smem_u32(&bars[i]));
+      }
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_ptr_s), 512);
+  } else {
+    // ---- inputs: x -> A k-chunks 0,1 ; h -> A k-chunks 2,3 (16 bytes = 8 elements per store) -----------
+    const int n_src = has_h ? 2 : 1;
+    for (int q = tid; q < n_src * 128 * 16; q += 256) {
+      const int src = q / (128 * 16), rem = q % (128 * 16);
+      const int row = rem >> 4, k = (rem & 15) * 8;
+      float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+      if (row < R) {
+        const float* s = (src ? p.hidden_in : p.x_clu) + (size_t)(row0 + row) * 128 + k;
+        lo = *reinterpret_cast<const float4*>(s);
+        hi = *reinterpret_cast<const float4*>(s + 4);
+      }
+      *reinterpret_cast<uint4*>(a_s + sw128_off(128, row, src * 128 + k)) =
+          make_uint4(pack2<BF16>(lo.x, lo.y), pack2<BF16>(lo.z, lo.w), pack2<BF16>(hi.x, hi.y), pack2<BF16>(hi.z, hi.w));
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
+
+  if (warp == 8) {
+    // =============================== TMA + MMA issue ====================================================
+    const uint32_t fmt = BF16 ? 1u : 0u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t a_base = smem_u32(a_s), r_base = smem_u32(ring);
+    const int n_atoms = *n_atoms_s;
+    int li = BF_RING;
+    for (int mi = 0; mi < n_atoms; ++mi) {
+      const int meta = atoms[mi].meta;
+      if (meta & (1 << 12)) {                   // first atom of a GEMM: wait until its A operand is published
+        named_bar(2, BF_THREADS);
+        tc_fence_after();
+      }
+      if (lane == 0) {
+        const int slot = mi % BF_RING;
+        mbar_wait(smem_u32(&bars[slot]), (uint32_t)((mi / BF_RING) & 1));
+        tc_fence_after();
+        const int g = meta & 15, nc = (meta >> 4) & 15, kc = (meta >> 8) & 15;
+        const uint32_t d = tmem_base + (uint32_t)(nc * 128);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_f16(d, sw128_desc(a_base + kc * BF_ATOM + ks * 32), sw128_desc(r_base + slot * BF_ATOM + ks * 32), idesc,
+                   (kc | ks) ? 1u : 0u);
+        umma_commit(smem_u32(&bars[4 + slot]));
+        if (meta & (1 << 13)) umma_commit(smem_u32(&bars[8 + g]));
+        if (mi >= 1 && li < n_atoms) {          // refill the slot of the previous atom once its MMAs have drained
+          const int ps = (mi - 1) % BF_RING;
+          mbar_wait(smem_u32(&bars[4 + ps]), (uint32_t)(((mi - 1) / BF_RING) & 1));
+          mbar_expect_tx(smem_u32(&bars[ps]), BF_ATOM);
+          bulk_g2s(smem_u32(ring + ps * BF_ATOM), atoms[li].src, BF_ATOM, smem_u32(&bars[ps]));
+          ++li;
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================== epilogues ==========================================================
+    const int wq = warp & 3, half = warp >> 2;
+    const int row = wq * 32 + lane;                  // TMEM lane == local cluster row
+    const bool live = row < R;
+    const bool alive = live && alive_s[row];
+    const int64_t grow = (int64_t)row0 + (live ? row : 0);
+    const float2 ps = live ? reinterpret_cast<const float2*>(p.pos_clu)[grow] : make_float2(0.f, 0.f);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const int col = tid & 127, chalf = tid >> 7;     // column-phase identity: column, graph parity
+    const float* vb = vec; const float* vw0 = vec + BF_NVEC; const float* vw1 = vec + 2 * BF_NVEC;
+    float* srow = stg + row * BF_LD;
+
+    auto wait_done = [&](int g) { mbar_wait(smem_u32(&bars[8 + g]), 0); tc_fence_after(); };
+    auto publish_a = [&]() { fence_proxy_async(); tc_fence_before(); named_bar(2, BF_THREADS); };
+    // value of column c (vector index v) of this thread's row: accumulator + bias + pos . wp
+    auto lin = [&](float acc, int v) { return fmaf(ps.y, vw1[v], fmaf(ps.x, vw0[v], acc + vb[v])); };
+    // this thread's 64 columns of the 128-column TMEM chunk starting at `dcol` -> staging (Q part of a [P|Q] product)
+    auto q_to_staging = [&](int dcol, int vbase) {
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const int c0 = half * 64 + sub * 32;
+        float acc[32];
+        tmem_ld32(t_lane + (uint32_t)(dcol + c0), acc);
+        tmem_ld_wait();
+        if (live) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) srow[c0 + q] = lin(acc[q], vbase + c0 + q);
+        }
+      }
+    };
+    // per graph: max over the node set (all rows, or rows with mask) of staging column `col`, broadcast in place
+    auto colmax_broadcast = [&](bool use_mask) {
+      for (int k = chalf; k < G; k += 2) {
+        const int rb = g_beg[k], re = g_beg[k + 1];
+        float m = -INFINITY;
+        for (int r = rb; r < re; ++r)
+          if (!use_mask || alive_s[r]) m = fmaxf(m, stg[r * BF_LD + col]);
+        for (int r = rb; r < re; ++r) stg[r * BF_LD + col] = m;
+      }
+    };
+    // PERConv tail: conv = P + max (0 for rows outside the node set) -> GraphNorm -> ReLU -> A k-chunks 0,1
+    auto perconv_epilogue = [&](int vbase, const float* gw, const float* gb, const float* gms) {
+      q_to_staging(128, vbase + 128);
+      named_bar(1, 256);
+      colmax_broadcast(true);
+      named_bar(1, 256);
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const int c0 = half * 64 + sub * 32;
+        float acc[32];
+        tmem_ld32(t_lane + (uint32_t)c0, acc);
+        tmem_ld_wait();
+        if (live) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) srow[c0 + q] = alive ? lin(acc[q], vbase + c0 + q) + srow[c0 + q] : 0.f;
+        }
+      }
+      named_bar(1, 256);
+      const float w = gw[col], b = gb[col], ms = gms[col];
+      for (int k = chalf; k < G; k += 2) {
+        const int rb = g_beg[k], re = g_beg[k + 1];
+        const float inv_n = 1.f / (float)(re - rb);
+        float sum = 0.f;
+        for (int r = rb; r < re; ++r) sum += stg[r * BF_LD + col];
+        const float shift = sum * inv_n * ms;
+        float sq = 0.f;
+        for (int r = rb; r < re; ++r) { const float o = stg[r * BF_LD + col] - shift; sq = fmaf(o, o, sq); }
+        const float rstd = 1.f / sqrtf(sq * inv_n + 1e-5f);
+        for (int r = rb; r < re; ++r) {
+          const float o = stg[r * BF_LD + col] - shift;
+          const float y = fmaxf(fmaf(w * o, rstd, b), 0.f);
+          const uint32_t pk = pack2<BF16>(y, 0.f);
+          *reinterpret_cast<unsigned short*>(a_s + sw128_off(128, r, col)) = (unsigned short)(pk & 0xffffu);
+        }
+      }
+    };
+    // fc tail: y = relu(acc + b + residual) ; to_a: 16-bit -> A k-chunks 0,1 ; out: fp32 rows to global
+    auto fc_epilogue = [&](int vbase, const float* resid, bool to_a, float* out) {
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const int c0 = half * 64 + sub * 32;
+        float acc[32];
+        tmem_ld32(t_lane + (uint32_t)c0, acc);
+        tmem_ld_wait();
+        if (live) {
+          const float* rr = resid + grow * 128 + c0;
+#pragma unroll
+          for (int q = 0; q < 32; q += 8) {
+            const float4 r0 = *reinterpret_cast<const float4*>(rr + q), r1 = *reinterpret_cast<const float4*>(rr + q + 4);
+            float y[8];
+            y[0] = acc[q] + vb[vbase + c0 + q] + r0.x;         y[1] = acc[q + 1] + vb[vbase + c0 + q + 1] + r0.y;
+            y[2] = acc[q + 2] + vb[vbase + c0 + q + 2] + r0.z; y[3] = acc[q + 3] + vb[vbase + c0 + q + 3] + r0.w;
+            y[4] = acc[q + 4] + vb[vbase + c0 + q + 4] + r1.x; y[5] = acc[q + 5] + vb[vbase + c0 + q + 5] + r1.y;
+            y[6] = acc[q + 6] + vb[vbase + c0 + q + 6] + r1.z; y[7] = acc[q + 7] + vb[vbase + c0 + q + 7] + r1.w;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], 0.f);
+            if (to_a)
+              *reinterpret_cast<uint4*>(a_s + sw128_off(128, row, c0 + q)) =
+                  make_uint4(pack2<BF16>(y[0], y[1]), pack2<BF16>(y[2], y[3]), pack2<BF16>(y[4], y[5]), pack2<BF16>(y[6], y[7]));
+            if (out) {
+              float* o = out + grow * 128 + c0 + q;
+              *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+            }
+          }
+        }
+      }
+    };
+
+    // ---- GEMM 0: c0 [P|Q] --------------------------------------------------------------------------------
+    publish_a();
+    wait_done(0);
+    perconv_epilogue(VB_C0, p.gn0_w, p.gn0_b, p.gn0_ms);
+    // ---- GEMM 1: c0.fc + x -> y0 (A k-chunks 0,1) ----------------------------------------------------------
+    publish_a();
+    wait_done(1);
+    fc_epilogue(VB_C0FC, p.x_clu, true, nullptr);
+    // ---- GEMM 2: gates on the target graph (every cluster is a node): r -> h*r (A k-chunks 2,3), u -> registers
+    publish_a();
+    wait_done(2);
+    float u[64];
+    {
+      // r: P columns [0,128), Q columns [256,384)
+      q_to_staging(256, VB_G + 256);
+      named_bar(1, 256);
+      colmax_broadcast(false);
+      named_bar(1, 256);
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const int c0 = half * 64 + sub * 32;
+        float acc[32];
+        tmem_ld32(t_lane + (uint32_t)c0, acc);
+        tmem_ld_wait();
+        if (live && has_h) {
+          const float* hr = p.hidden_in + grow * 128 + c0;
+#pragma unroll
+          for (int q = 0; q < 32; q += 8) {
+            const float4 h0 = *reinterpret_cast<const float4*>(hr + q), h1 = *reinterpret_cast<const float4*>(hr + q + 4);
+            const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float o = lin(acc[q + i], VB_G + c0 + q + i) + srow[c0 + q + i];
+              y[i] = hv[i] * (1.f / (1.f + expf(-o)));
+            }
+            *reinterpret_cast<uint4*>(a_s + sw128_off(128, row, 128 + c0 + q)) =
+                make_uint4(pack2<BF16>(y[0], y[1]), pack2<BF16>(y[2], y[3]), pack2<BF16>(y[4], y[5]), pack2<BF16>(y[6], y[7]));
+          }
+        }
+      }
+      named_bar(1, 256);
+      // u: P columns [128,256), Q columns [384,512)
+      q_to_staging(384, VB_G + 384);
+      named_bar(1, 256);
+      colmax_broadcast(false);
+      named_bar(1, 256);
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const int c0 = half * 64 + sub * 32;
+        float acc[32];
+        tmem_ld32(t_lane + (uint32_t)(128 + c0), acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const float o = lin(acc[q], VB_G + 128 + c0 + q) + (live ? srow[c0 + q] : 0.f);
+          u[sub * 32 + q] = 1.f / (1.f + expf(-o));
+        }
+      }
+      named_bar(1, 256);
+    }
+    // ---- GEMM 3: candidate on the current graph: h' = (1 - u) h + u tanh(conv) -> hidden_out, A k-chunks 0,1 ----
+    publish_a();
+    wait_done(3);
+    q_to_staging(128, VB_K + 128);
+    named_bar(1, 256);
+    colmax_broadcast(true);
+    named_bar(1, 256);
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) {
+      const int c0 = half * 64 + sub * 32;
+      float acc[32];
+      tmem_ld32(t_lane + (uint32_t)c0, acc);
+      tmem_ld_wait();
+      if (live) {
+        const float* hr = has_h ? p.hidden_in + grow * 128 + c0 : nullptr;
+        float* ho = p.hidden_out + grow * 128 + c0;
+#pragma unroll
+        for (int q = 0; q < 32; q += 8) {
+          float hv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (hr) {
+            const float4 h0 = *reinterpret_cast<const float4*>(hr + q), h1 = *reinterpret_cast<const float4*>(hr + q + 4);
+            hv[0] = h0.x; hv[1] = h0.y; hv[2] = h0.z; hv[3] = h0.w; hv[4] = h1.x; hv[5] = h1.y; hv[6] = h1.z; hv[7] = h1.w;
+          }
+          float y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float o = alive ? lin(acc[q + i], VB_K + c0 + q + i) + srow[c0 + q + i] : 0.f;
+            const float uu = u[sub * 32 + q + i];
+            y[i] = (1.f - uu) * hv[i] + uu * tanhf(o);
+          }
+          *reinterpret_cast<float4*>(ho + q) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(ho + q + 4) = make_float4(y[4], y[5], y[6], y[7]);
+          *reinterpret_cast<uint4*>(a_s + sw128_off(128, row, c0 + q)) =
+              make_uint4(pack2<BF16>(y[0], y[1]), pack2<BF16>(y[2], y[3]), pack2<BF16>(y[4], y[5]), pack2<BF16>(y[6], y[7]));
+        }
+      }
+    }
+    named_bar(1, 256);          // staging is reused by the next epilogue
+    // ---- GEMM 4: c1 [P|Q] on h' ----------------------------------------------------------------------------
+    publish_a();
+    wait_done(4);
+    perconv_epilogue(VB_C1, p.gn1_w, p.gn1_b, p.gn1_ms);
+    // ---- GEMM 5: c1.fc + h' -> x2 ----------------------------------------------------------------------------
+    publish_a();
+    wait_done(5);
+    fc_epilogue(VB_C1FC, p.hidden_out, false, p.x2);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+size_t backbone_fused_scratch_ints(int64_t n_graphs) { return (size_t)(2 * n_graphs + 8); }
+
+int backbone_fused(const BackboneFusedArgs& a, int* next_scratch, int* err, bool bf16, cudaStream_t s) {
+  if (a.n_graphs == 0 || a.n_clusters == 0) return CNS_OK;
+  static bool configured = false;
+  if (!configured) {
+    CNS_CUDA_CHECK(cudaFuncSetAttribute(backbone_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BF_SMEM));
+    CNS_CUDA_CHECK(cudaFuncSetAttribute(backbone_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BF_SMEM));
+    configured = true;
+  }
+  tile_pack_kernel<<<1, 1024, 0, s>>>(a.graph_ptr, a.n_graphs, next_scratch, const_cast<int*>(a.tile_graph),
+                                      const_cast<int*>(a.n_tiles), err);
+  CNS_LAUNCH_CHECK();
+  // greedy whole-graph tiles: two consecutive tiles always hold more than 128 rows together
+  int64_t grid = 2 * ceil_div(a.n_clusters, 128) + 1;
+  if (grid > a.n_graphs) grid = a.n_graphs;
+  if (bf16) backbone_fused_kernel<true><<<(unsigned)grid, BF_THREADS, BF_SMEM, s>>>(a);
+  else backbone_fused_kernel<false><<<(unsigned)grid, BF_THREADS, BF_SMEM, s>>>(a);
+  CNS_LAUNCH_CHECK();
+  return CNS_OK;
+}
+
+}  // namespace cns

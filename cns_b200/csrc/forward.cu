@@ -9,7 +9,7 @@ namespace cns {
 struct FwdBuffers {
   int* err; int* clu_rowptr; int* clu_graph; int* graph_ptr; int* gp_tmp; int* scan_scratch;
   int* cur_rowptr; int* cur_src; int* tar_rowptr; int* tar_src; void* csr_ws;
-  int* alive_idx; int* alive_cnt;
+  int* alive_idx; int* alive_cnt; int* tile_graph; int* tile_next; int* n_tiles;
   float* a_dst; float* pos_clu; float* clu_feat; float* partial; float* x_clu;
   float* pq; float* conv0; float* conv1; float* gn0; float* gn1; float* stats0; float* stats1;
   float* x1; float* u; float* hr; float* x2; float* gate;
@@ -31,6 +31,7 @@ static void carve(Arena& ar, const cns_batch* b, FwdBuffers& f, const SaveBuffer
   f.csr_ws = ar.take<char>(csr_workspace_bytes(C));
   f.alive_idx = ar.take<int>(C + 1);
   f.alive_cnt = ar.take<int>(B + 1);
+  f.tile_graph = ar.take<int>(B + 2); f.tile_next = ar.take<int>(B + 1); f.n_tiles = ar.take<int>(4);
   f.a_dst = ar.take<float>(C * H);
   f.partial = ar.take<float>((size_t)2 * f.n_slots * 3 * H);
   f.pq = ar.take<float>(C * 4 * H);
@@ -223,6 +224,22 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     return linear(la, s);
   };
 
+  // whole-graph row tiles: the three backbone blocks as one kernel (backbone_fused.cu)
+  const bool fused = tc && dense_cur && dense_tar && b->max_clusters_per_graph > 0 && b->max_clusters_per_graph <= 128 &&
+                     !h->no_fused_backbone;
+  if (fused) {
+    BackboneFusedArgs fa{};
+    fa.n_clusters = C; fa.n_graphs = (int)B; fa.graph_ptr = f.graph_ptr; fa.tile_graph = f.tile_graph; fa.n_tiles = f.n_tiles;
+    fa.x_clu = f.x_clu; fa.hidden_in = hidden_in; fa.pos_clu = f.pos_clu; fa.mask = b->cluster_mask;
+    fa.w_c0 = pk.tc_c0[tci]; fa.w_c0fc = pk.tc_c0_fc[tci]; fa.w_g = pk.tc_g[tci]; fa.w_k = pk.tc_k[tci];
+    fa.w_c1 = pk.tc_c1[tci]; fa.w_c1fc = pk.tc_c1_fc[tci];
+    fa.c0_b = pk.c0_b; fa.c0_wp = pk.c0_wp; fa.g_b = pk.g_b; fa.g_wp = pk.g_wp; fa.k_b = pk.k_b; fa.k_wp = pk.k_wp;
+    fa.c1_b = pk.c1_b; fa.c1_wp = pk.c1_wp; fa.c0fc_b = h->P(P_C0_FC_B); fa.c1fc_b = h->P(P_C1_FC_B);
+    fa.gn0_w = h->P(P_C0_BN_W); fa.gn0_b = h->P(P_C0_BN_B); fa.gn0_ms = h->P(P_C0_BN_MS);
+    fa.gn1_w = h->P(P_C1_BN_W); fa.gn1_b = h->P(P_C1_BN_B); fa.gn1_ms = h->P(P_C1_BN_MS);
+    fa.hidden_out = hidden_out; fa.x2 = f.x2;
+    RUN(backbone_fused(fa, f.tile_next, f.err, tci == 0, s));
+  } else {
   RUN(perconv(f.x_clu, pk.c0_wt, pk.c0_wp, pk.c0_b, P_C0_BN_W, P_C0_BN_B, P_C0_BN_MS, pk.c0_fc_t, P_C0_FC_B, f.x1, pk.tc_c0, pk.tc_c0_fc, f.conv0, f.gn0, f.stats0, f.arg0));
 
   // GRU gates on the TARGET cluster graph, candidate on the CURRENT one (graph_vs.py:246-249)
@@ -251,6 +268,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     RUN(edgeconv_max(ec, s));
   }
   RUN(perconv(hidden_out, pk.c1_wt, pk.c1_wp, pk.c1_b, P_C1_BN_W, P_C1_BN_B, P_C1_BN_MS, pk.c1_fc_t, P_C1_FC_B, f.x2, pk.tc_c1, pk.tc_c1_fc, f.conv1, f.gn1, f.stats1, f.arg1));
+  }
 
   // ---- decoder ----------------------------------------------------------------------------
   PoolHeadArgs ph{};
@@ -318,6 +336,7 @@ int cns_forward_status(const void* workspace, void* stream) {
   CNS_CUDA_CHECK(cudaMemcpyAsync(&flag, workspace, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CNS_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
   if (flag == 1) { set_error("l0_to_l1_edge_index_i is not sorted by cluster / out of range"); return CNS_ERR_UNSORTED_EDGES; }
+  if (flag == 4) { set_error("a graph has more clusters than cns_batch.max_clusters_per_graph / 128"); return CNS_ERR_INVALID_ARGUMENT; }
   if (flag == 3) { set_error("cluster-level edge lists are not the complete graphs claimed by cns_batch.flags"); return CNS_ERR_INVALID_ARGUMENT; }
   if (flag != 0) { set_error("edge index out of range"); return CNS_ERR_INVALID_ARGUMENT; }
   return CNS_OK;

@@ -127,6 +127,21 @@ struct EdgeConvDenseArgs {
 };
 int edgeconv_dense(const EdgeConvDenseArgs& a, cudaStream_t s);
 
+// ---- backbone_fused.cu: PERConv -> GRU -> PERConv over whole-graph row tiles (complete graphs, <= 128 clusters each)
+struct BackboneFusedArgs {
+  int64_t n_clusters; int n_graphs;
+  const int* graph_ptr;
+  const int* tile_graph; const int* n_tiles;      // scratch: (B + 2,), (1,) filled by the tile packer
+  const float* x_clu; const float* hidden_in; const float* pos_clu; const uint8_t* mask;
+  const unsigned char* w_c0; const unsigned char* w_c0fc; const unsigned char* w_g; const unsigned char* w_k;
+  const unsigned char* w_c1; const unsigned char* w_c1fc;      // gemm_tc weight images
+  const float* c0_b; const float* c0_wp; const float* g_b; const float* g_wp; const float* k_b; const float* k_wp;
+  const float* c1_b; const float* c1_wp; const float* c0fc_b; const float* c1fc_b;
+  const float* gn0_w; const float* gn0_b; const float* gn0_ms; const float* gn1_w; const float* gn1_b; const float* gn1_ms;
+  float* hidden_out; float* x2;
+};
+int backbone_fused(const BackboneFusedArgs& a, int* next_scratch, int* err, bool bf16, cudaStream_t s);
+
 struct GraphNormArgs {
   int64_t n_graphs; const int* graph_ptr; const float* x;
   const float* weight; const float* bias; const float* mean_scale;

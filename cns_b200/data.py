@@ -240,6 +240,7 @@ class Batch(GraphData):
                 out[key] = torch.tensor(vals)
             else:
                 out[key] = vals
+        out["max_clusters_per_graph"] = int(n_clu.max())
         out["num_nodes"] = int(n_nodes.sum())
         out["batch"] = torch.repeat_interleave(torch.arange(nb), n_nodes)
         ptr = torch.zeros(nb + 1, dtype=torch.long)

@@ -264,6 +264,12 @@ class GraphVS(nn.Module):
         b.node_graph, b.num_clusters, b.tPo_norm = p(batch), p(ncl), p(tpo)
         complete = data.get("l1_complete", False) if isinstance(data, dict) else getattr(data, "l1_complete", False)
         b.flags = (_lib.BATCH_L1_CUR_COMPLETE | _lib.BATCH_L1_TAR_COMPLETE) if complete is True else 0
+        mc = data.get("max_clusters_per_graph", 0) if isinstance(data, dict) else getattr(data, "max_clusters_per_graph", 0)
+        if not isinstance(mc, int) or isinstance(mc, bool):
+            mc = 0
+        if mc == 0 and b.n_graphs == 1:
+            mc = int(b.n_clusters)                      # a single graph: its cluster count is the bound
+        b.max_clusters_per_graph = mc
         return b, keep
 
     # ------------------------------------------------------------------ forward

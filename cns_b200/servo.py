@@ -32,6 +32,7 @@ class BatchedServo(object):
         noff, coff = np.cumsum(n_nodes) - n_nodes, np.cumsum(n_clu) - n_clu
         self.B, self.N, self.Cn = len(gens), int(n_nodes.sum()), int(n_clu.sum())
         self.node_off = noff
+        self.max_clusters = int(n_clu.max())
         d = lambda a, dt: torch.as_tensor(np.array(a), dtype=dt).to(self.dev)
         tar = np.concatenate([g.target_points for g in gens]).astype(np.float32)
         self.x_tar = d(tar, torch.float32)                                   # x_tar == pos_tar (default_feature)
@@ -90,6 +91,7 @@ class BatchedServo(object):
         b.cluster_mask, b.cluster_centers = p(self.cmask), p(self.centers)
         b.node_graph, b.num_clusters, b.tPo_norm = None, p(self.num_clusters), p(self.tpo)
         b.flags = L.BATCH_L1_CUR_COMPLETE | L.BATCH_L1_TAR_COMPLETE
+        b.max_clusters_per_graph = self.max_clusters
         h = self.net._handle(dev)
         ws = self.net._workspace(dev.index, lib.cns_forward_workspace_bytes(C.byref(b)))
         B = self.B

@@ -106,6 +106,10 @@ typedef struct cns_batch {
   const int64_t* num_clusters;    /* (B,)  clusters per graph                     */
   const float* tPo_norm;          /* (B,)  distance scale, or NULL => 1           */
   int64_t flags;                  /* CNS_BATCH_* hints, 0 = none                   */
+  int64_t max_clusters_per_graph; /* upper bound on num_clusters[g] known to the host, 0 = unknown.  With both
+                                   * COMPLETE hints, a bound <= 128 and a 16-bit precision mode the cluster-level
+                                   * backbone runs as one fused kernel over whole-graph row tiles (verified on the
+                                   * device like the hints)                                                   */
 } cns_batch;
 
 /* Structure hints about the cluster-level edge lists.  What GraphGenerator builds (graph_gen.py:31-36 via
