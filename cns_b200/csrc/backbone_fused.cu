@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(1024)
 tile_pack_kernel(const int* __restrict__ graph_ptr, int n_graphs, int* __restrict__ next, int* __restrict__ tile_graph,
                  int* __restrict__ n_tiles, int* __restrict__ err) {
   // next[g] = first graph that does not fit into a tile starting at g (binary search on the prefix sums)
+  __shared__ int next_s[8192];
   for (int g = threadIdx.x; g < n_graphs; g += 1024) {
     const int lim = graph_ptr[g] + 128;
     if (graph_ptr[g + 1] > lim) atomicExch(err, 4);     // a graph with more than 128 clusters
@@ -48,12 +49,12 @@ tile_pack_kernel(const int* __restrict__ graph_ptr, int n_graphs, int* __restric
       const int mid = (lo + hi + 1) >> 1;
       if (graph_ptr[mid] <= lim) lo = mid; else hi = mid - 1;
     }
-    next[g] = lo;
+    next_s[g] = lo;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     int t = 0, g = 0;
-    while (g < n_graphs) { tile_graph[t++] = g; const int q = next[g]; g = q > g ? q : g + 1; }
+    while (g < n_graphs) { tile_graph[t++] = g; const int q = next_s[g]; g = q > g ? q : g + 1; }
     tile_graph[t] = n_graphs;
     *n_tiles = t;
   }
@@ -203,19 +204,44 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
 
     auto wait_done = [&](int g) { mbar_wait(smem_u32(&bars[8 + g]), 0); tc_fence_after(); };
     auto publish_a = [&]() { fence_proxy_async(); tc_fence_before(); named_bar(2, BF_THREADS); };
-    // value of column c (vector index v) of this thread's row: accumulator + bias + pos . wp
-    auto lin = [&](float acc, int v) { return fmaf(ps.y, vw1[v], fmaf(ps.x, vw0[v], acc + vb[v])); };
-    // this thread's 64 columns of the 128-column TMEM chunk starting at `dcol` -> staging (Q part of a [P|Q] product)
+    // The epilogues walk this thread's 64 columns of a 128-column TMEM chunk in 8 trips of 8 columns (runtime
+    // loops: the whole chain is executed once per tile, so a small instruction footprint matters more than
+    // unrolling).  v[i] = accumulator + bias + pos . wp for vector index vi + i.
+    auto lin8 = [&](const float (&acc)[8], int vi, float (&o)[8]) {
+      const float4 b0 = *reinterpret_cast<const float4*>(vb + vi), b1 = *reinterpret_cast<const float4*>(vb + vi + 4);
+      const float4 x0 = *reinterpret_cast<const float4*>(vw0 + vi), x1 = *reinterpret_cast<const float4*>(vw0 + vi + 4);
+      const float4 y0 = *reinterpret_cast<const float4*>(vw1 + vi), y1 = *reinterpret_cast<const float4*>(vw1 + vi + 4);
+      o[0] = fmaf(ps.y, y0.x, fmaf(ps.x, x0.x, acc[0] + b0.x)); o[1] = fmaf(ps.y, y0.y, fmaf(ps.x, x0.y, acc[1] + b0.y));
+      o[2] = fmaf(ps.y, y0.z, fmaf(ps.x, x0.z, acc[2] + b0.z)); o[3] = fmaf(ps.y, y0.w, fmaf(ps.x, x0.w, acc[3] + b0.w));
+      o[4] = fmaf(ps.y, y1.x, fmaf(ps.x, x1.x, acc[4] + b1.x)); o[5] = fmaf(ps.y, y1.y, fmaf(ps.x, x1.y, acc[5] + b1.y));
+      o[6] = fmaf(ps.y, y1.z, fmaf(ps.x, x1.z, acc[6] + b1.z)); o[7] = fmaf(ps.y, y1.w, fmaf(ps.x, x1.w, acc[7] + b1.w));
+    };
+    auto load8 = [&](const float* src, float (&v)[8]) {
+      const float4 a0 = *reinterpret_cast<const float4*>(src), a1 = *reinterpret_cast<const float4*>(src + 4);
+      v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+    };
+    auto store8 = [&](float* dst, const float (&v)[8]) {
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    };
+    auto store_a8 = [&](int acol, const float (&v)[8]) {     // 8 consecutive k of this thread's A row
+      *reinterpret_cast<uint4*>(a_s + sw128_off(128, row, acol)) =
+          make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7]));
+    };
+    auto sigmoid_fast = [](float x) { return __fdividef(1.f, 1.f + __expf(-x)); };
+    auto tanh_fast = [](float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); };
+    // Q part of a [P|Q] product (TMEM columns dcol..dcol+127) -> staging
     auto q_to_staging = [&](int dcol, int vbase) {
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const int c0 = half * 64 + sub * 32;
-        float acc[32];
-        tmem_ld32(t_lane + (uint32_t)(dcol + c0), acc);
+#pragma unroll 1
+      for (int cg = 0; cg < 8; ++cg) {
+        const int c = half * 64 + cg * 8;
+        float acc[8], o[8];
+        tmem_ld8(t_lane + (uint32_t)(dcol + c), acc);
         tmem_ld_wait();
+        lin8(acc, vbase + c, o);
         if (live) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) srow[c0 + q] = lin(acc[q], vbase + c0 + q);
+          for (int i = 0; i < 8; ++i) srow[c + i] = o[i];
         }
       }
     };
@@ -235,15 +261,16 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
       named_bar(1, 256);
       colmax_broadcast(true);
       named_bar(1, 256);
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const int c0 = half * 64 + sub * 32;
-        float acc[32];
-        tmem_ld32(t_lane + (uint32_t)c0, acc);
+#pragma unroll 1
+      for (int cg = 0; cg < 8; ++cg) {
+        const int c = half * 64 + cg * 8;
+        float acc[8], o[8];
+        tmem_ld8(t_lane + (uint32_t)c, acc);
         tmem_ld_wait();
+        lin8(acc, vbase + c, o);
         if (live) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) srow[c0 + q] = alive ? lin(acc[q], vbase + c0 + q) + srow[c0 + q] : 0.f;
+          for (int i = 0; i < 8; ++i) srow[c + i] = alive ? o[i] + srow[c + i] : 0.f;
         }
       }
       named_bar(1, 256);
@@ -267,33 +294,20 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     };
     // fc tail: y = relu(acc + b + residual) ; to_a: 16-bit -> A k-chunks 0,1 ; out: fp32 rows to global
     auto fc_epilogue = [&](int vbase, const float* resid, bool to_a, float* out) {
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const int c0 = half * 64 + sub * 32;
-        float acc[32];
-        tmem_ld32(t_lane + (uint32_t)c0, acc);
+#pragma unroll 1
+      for (int cg = 0; cg < 8; ++cg) {
+        const int c = half * 64 + cg * 8;
+        float acc[8], r8[8], y[8];
+        tmem_ld8(t_lane + (uint32_t)c, acc);
         tmem_ld_wait();
         if (live) {
-          const float* rr = resid + grow * 128 + c0;
+          load8(resid + grow * 128 + c, r8);
+          const float4 b0 = *reinterpret_cast<const float4*>(vb + vbase + c), b1 = *reinterpret_cast<const float4*>(vb + vbase + c + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-          for (int q = 0; q < 32; q += 8) {
-            const float4 r0 = *reinterpret_cast<const float4*>(rr + q), r1 = *reinterpret_cast<const float4*>(rr + q + 4);
-            float y[8];
-            y[0] = acc[q] + vb[vbase + c0 + q] + r0.x;         y[1] = acc[q + 1] + vb[vbase + c0 + q + 1] + r0.y;
-            y[2] = acc[q + 2] + vb[vbase + c0 + q + 2] + r0.z; y[3] = acc[q + 3] + vb[vbase + c0 + q + 3] + r0.w;
-            y[4] = acc[q + 4] + vb[vbase + c0 + q + 4] + r1.x; y[5] = acc[q + 5] + vb[vbase + c0 + q + 5] + r1.y;
-            y[6] = acc[q + 6] + vb[vbase + c0 + q + 6] + r1.z; y[7] = acc[q + 7] + vb[vbase + c0 + q + 7] + r1.w;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], 0.f);
-            if (to_a)
-              *reinterpret_cast<uint4*>(a_s + sw128_off(128, row, c0 + q)) =
-                  make_uint4(pack2<BF16>(y[0], y[1]), pack2<BF16>(y[2], y[3]), pack2<BF16>(y[4], y[5]), pack2<BF16>(y[6], y[7]));
-            if (out) {
-              float* o = out + grow * 128 + c0 + q;
-              *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
-            }
-          }
+          for (int i = 0; i < 8; ++i) y[i] = fmaxf(acc[i] + bb[i] + r8[i], 0.f);
+          if (to_a) store_a8(c, y);
+          if (out) store8(out + grow * 128 + c, y);
         }
       }
     };
@@ -306,59 +320,50 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     publish_a();
     wait_done(1);
     fc_epilogue(VB_C0FC, p.x_clu, true, nullptr);
-    // ---- GEMM 2: gates on the target graph (every cluster is a node): r -> h*r (A k-chunks 2,3), u -> registers
+    // ---- GEMM 2: gates on the target graph (every cluster is a node): r -> h*r (A k-chunks 2,3), u -> scratch
     publish_a();
     wait_done(2);
-    float u[64];
-    {
-      // r: P columns [0,128), Q columns [256,384)
-      q_to_staging(256, VB_G + 256);
-      named_bar(1, 256);
-      colmax_broadcast(false);
-      named_bar(1, 256);
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const int c0 = half * 64 + sub * 32;
-        float acc[32];
-        tmem_ld32(t_lane + (uint32_t)c0, acc);
+    // r: P columns [0,128), Q columns [256,384)
+    q_to_staging(256, VB_G + 256);
+    named_bar(1, 256);
+    colmax_broadcast(false);
+    named_bar(1, 256);
+    if (has_h) {
+#pragma unroll 1
+      for (int cg = 0; cg < 8; ++cg) {
+        const int c = half * 64 + cg * 8;
+        float acc[8], o[8], hv[8];
+        tmem_ld8(t_lane + (uint32_t)c, acc);
         tmem_ld_wait();
-        if (live && has_h) {
-          const float* hr = p.hidden_in + grow * 128 + c0;
+        lin8(acc, VB_G + c, o);
+        if (live) {
+          load8(p.hidden_in + grow * 128 + c, hv);
 #pragma unroll
-          for (int q = 0; q < 32; q += 8) {
-            const float4 h0 = *reinterpret_cast<const float4*>(hr + q), h1 = *reinterpret_cast<const float4*>(hr + q + 4);
-            const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-            float y[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float o = lin(acc[q + i], VB_G + c0 + q + i) + srow[c0 + q + i];
-              y[i] = hv[i] * (1.f / (1.f + expf(-o)));
-            }
-            *reinterpret_cast<uint4*>(a_s + sw128_off(128, row, 128 + c0 + q)) =
-                make_uint4(pack2<BF16>(y[0], y[1]), pack2<BF16>(y[2], y[3]), pack2<BF16>(y[4], y[5]), pack2<BF16>(y[6], y[7]));
-          }
+          for (int i = 0; i < 8; ++i) o[i] = hv[i] * sigmoid_fast(o[i] + srow[c + i]);
+          store_a8(128 + c, o);
         }
       }
-      named_bar(1, 256);
-      // u: P columns [128,256), Q columns [384,512)
-      q_to_staging(384, VB_G + 384);
-      named_bar(1, 256);
-      colmax_broadcast(false);
-      named_bar(1, 256);
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const int c0 = half * 64 + sub * 32;
-        float acc[32];
-        tmem_ld32(t_lane + (uint32_t)(128 + c0), acc);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const float o = lin(acc[q], VB_G + 128 + c0 + q) + (live ? srow[c0 + q] : 0.f);
-          u[sub * 32 + q] = 1.f / (1.f + expf(-o));
-        }
-      }
-      named_bar(1, 256);
     }
+    named_bar(1, 256);
+    // u: P columns [128,256), Q columns [384,512)
+    q_to_staging(384, VB_G + 384);
+    named_bar(1, 256);
+    colmax_broadcast(false);
+    named_bar(1, 256);
+#pragma unroll 1
+    for (int cg = 0; cg < 8; ++cg) {
+      const int c = half * 64 + cg * 8;
+      float acc[8], o[8];
+      tmem_ld8(t_lane + (uint32_t)(128 + c), acc);
+      tmem_ld_wait();
+      lin8(acc, VB_G + 128 + c, o);
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = sigmoid_fast(o[i] + srow[c + i]);
+        store8(p.u_scratch + grow * 128 + c, o);     // read back by this same thread in the candidate epilogue
+      }
+    }
+    named_bar(1, 256);
     // ---- GEMM 3: candidate on the current graph: h' = (1 - u) h + u tanh(conv) -> hidden_out, A k-chunks 0,1 ----
     publish_a();
     wait_done(3);
@@ -366,34 +371,23 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     named_bar(1, 256);
     colmax_broadcast(true);
     named_bar(1, 256);
-#pragma unroll
-    for (int sub = 0; sub < 2; ++sub) {
-      const int c0 = half * 64 + sub * 32;
-      float acc[32];
-      tmem_ld32(t_lane + (uint32_t)c0, acc);
+#pragma unroll 1
+    for (int cg = 0; cg < 8; ++cg) {
+      const int c = half * 64 + cg * 8;
+      float acc[8], o[8], hv[8], uu[8];
+      tmem_ld8(t_lane + (uint32_t)c, acc);
       tmem_ld_wait();
+      lin8(acc, VB_K + c, o);
       if (live) {
-        const float* hr = has_h ? p.hidden_in + grow * 128 + c0 : nullptr;
-        float* ho = p.hidden_out + grow * 128 + c0;
+        load8(p.u_scratch + grow * 128 + c, uu);
+        if (has_h) load8(p.hidden_in + grow * 128 + c, hv);
 #pragma unroll
-        for (int q = 0; q < 32; q += 8) {
-          float hv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (hr) {
-            const float4 h0 = *reinterpret_cast<const float4*>(hr + q), h1 = *reinterpret_cast<const float4*>(hr + q + 4);
-            hv[0] = h0.x; hv[1] = h0.y; hv[2] = h0.z; hv[3] = h0.w; hv[4] = h1.x; hv[5] = h1.y; hv[6] = h1.z; hv[7] = h1.w;
-          }
-          float y[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float o = alive ? lin(acc[q + i], VB_K + c0 + q + i) + srow[c0 + q + i] : 0.f;
-            const float uu = u[sub * 32 + q + i];
-            y[i] = (1.f - uu) * hv[i] + uu * tanhf(o);
-          }
-          *reinterpret_cast<float4*>(ho + q) = make_float4(y[0], y[1], y[2], y[3]);
-          *reinterpret_cast<float4*>(ho + q + 4) = make_float4(y[4], y[5], y[6], y[7]);
-          *reinterpret_cast<uint4*>(a_s + sw128_off(128, row, c0 + q)) =
-              make_uint4(pack2<BF16>(y[0], y[1]), pack2<BF16>(y[2], y[3]), pack2<BF16>(y[4], y[5]), pack2<BF16>(y[6], y[7]));
+        for (int i = 0; i < 8; ++i) {
+          const float cv = alive ? o[i] + srow[c + i] : 0.f;
+          o[i] = (1.f - uu[i]) * (has_h ? hv[i] : 0.f) + uu[i] * tanh_fast(cv);
         }
+        store8(p.hidden_out + grow * 128 + c, o);
+        store_a8(c, o);
       }
     }
     named_bar(1, 256);          // staging is reused by the next epilogue
@@ -416,6 +410,7 @@ size_t backbone_fused_scratch_ints(int64_t n_graphs) { return (size_t)(2 * n_gra
 
 int backbone_fused(const BackboneFusedArgs& a, int* next_scratch, int* err, bool bf16, cudaStream_t s) {
   if (a.n_graphs == 0 || a.n_clusters == 0) return CNS_OK;
+  CNS_REQUIRE(a.n_graphs <= 8192, "backbone_fused: at most 8192 graphs");
   static bool configured = false;
   if (!configured) {
     CNS_CUDA_CHECK(cudaFuncSetAttribute(backbone_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BF_SMEM));

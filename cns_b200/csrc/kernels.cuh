@@ -139,6 +139,7 @@ struct BackboneFusedArgs {
   const float* c1_b; const float* c1_wp; const float* c0fc_b; const float* c1fc_b;
   const float* gn0_w; const float* gn0_b; const float* gn0_ms; const float* gn1_w; const float* gn1_b; const float* gn1_ms;
   float* hidden_out; float* x2;
+  float* u_scratch;                               // (C,128) update gate, written and re-read by the same thread
 };
 int backbone_fused(const BackboneFusedArgs& a, int* next_scratch, int* err, bool bf16, cudaStream_t s);
 
