@@ -4,7 +4,7 @@
 //
 // With complete graphs the only coupling between cluster rows is per graph: the column max of the
 // PointEdgeConv messages and the GraphNorm statistics.  A CTA therefore owns a tile of WHOLE graphs
-// (<= 128 cluster rows = the 128 TMEM lanes) and walks the six GEMMs of the chain back to back:
+// (<= 128 cluster rows = the 128 TMEM lanes) and walks the GEMMs of the chain back to back:
 //
 //   x --c0 [P|Q]--> max/GraphNorm/ReLU --c0.fc + x--> y0
 //   [y0|h] --gates [P|Q]--> max/sigmoid -> r, u ; [y0|h*r] --candidate [P|Q]--> max/tanh -> h' = (1-u) h + u c
@@ -75,7 +75,7 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
   float* vec = stg + 128 * BF_LD;                              // [3][BF_NVEC]: bias, wp row 0, wp row 1
   BfAtom* atoms = reinterpret_cast<BfAtom*>(vec + 3 * BF_NVEC);
   unsigned char* tail = reinterpret_cast<unsigned char*>(atoms + BF_MAX_ATOMS);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // full[4], empty[4], done[6]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // full[4], empty[4], done[7]
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tail + 128);
   int* n_atoms_s = reinterpret_cast<int*>(tail + 136);
   int* g_beg = reinterpret_cast<int*>(tail + 144);             // [<=129] local first row of the tile's graphs
@@ -108,20 +108,22 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
   }
   if (warp == 8) {
     if (lane == 0) {
-      for (int i = 0; i < 14; ++i) mbar_init(smem_u32(&bars[i]), 1);
+      for (int i = 0; i < 15; ++i) mbar_init(smem_u32(&bars[i]), 1);
       fence_mbar_init();
-      // weight atoms in issue order
-      const unsigned char* img[6] = {p.w_c0, p.w_c0fc, p.w_g, p.w_k, p.w_c1, p.w_c1fc};
-      const int ncs[6] = {2, 1, 4, 2, 2, 1};
-      const int kimg[6] = {2, 2, 4, 4, 2, 2};
-      const int kuse[6] = {2, 2, kh, kh, 2, 2};
+      // weight atoms in issue order.  The gate product runs as two N = 256 halves, update gate first: every
+      // accumulator then fits TMEM columns [0,256) and [256,512) stays free for fp32 row stashes.
+      const unsigned char* img[7] = {p.w_c0, p.w_c0fc, p.w_g, p.w_g, p.w_k, p.w_c1, p.w_c1fc};
+      const int ncs[7] = {2, 1, 2, 2, 2, 2, 1};
+      const int nc0[7] = {0, 0, 1, 0, 0, 0, 0}, ncstep[7] = {1, 1, 2, 2, 1, 1, 1};    // image n-chunk = nc0 + j * ncstep
+      const int kimg[7] = {2, 2, 4, 4, 4, 2, 2};
+      const int kuse[7] = {2, 2, kh, kh, kh, 2, 2};
       int n = 0;
-      for (int g = 0; g < 6; ++g)
-        for (int nc = 0; nc < ncs[g]; ++nc)
+      for (int g = 0; g < 7; ++g)
+        for (int j = 0; j < ncs[g]; ++j)
           for (int kc = 0; kc < kuse[g]; ++kc) {
-            const bool first = nc == 0 && kc == 0, last = nc == ncs[g] - 1 && kc == kuse[g] - 1;
-            atoms[n].src = img[g] + (size_t)(nc * kimg[g] + kc) * BF_ATOM;
-            atoms[n].meta = g | (nc << 4) | (kc << 8) | ((int)first << 12) | ((int)last << 13);
+            const bool first = j == 0 && kc == 0, last = j == ncs[g] - 1 && kc == kuse[g] - 1;
+            atoms[n].src = img[g] + (size_t)((nc0[g] + j * ncstep[g]) * kimg[g] + kc) * BF_ATOM;
+            atoms[n].meta = g | (j << 4) | (kc << 8) | ((int)first << 12) | ((int)last << 13);
             ++n;
           }
       *n_atoms_s = n;
@@ -132,22 +134,6 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     }
     __syncwarp();
     tmem_alloc(smem_u32(tmem_ptr_s), 512);
-  } else {
-    // ---- inputs: x -> A k-chunks 0,1 ; h -> A k-chunks 2,3 (16 bytes = 8 elements per store) -----------
-    const int n_src = has_h ? 2 : 1;
-    for (int q = tid; q < n_src * 128 * 16; q += 256) {
-      const int src = q / (128 * 16), rem = q % (128 * 16);
-      const int row = rem >> 4, k = (rem & 15) * 8;
-      float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-      if (row < R) {
-        const float* s = (src ? p.hidden_in : p.x_clu) + (size_t)(row0 + row) * 128 + k;
-        lo = *reinterpret_cast<const float4*>(s);
-        hi = *reinterpret_cast<const float4*>(s + 4);
-      }
-      *reinterpret_cast<uint4*>(a_s + sw128_off(128, row, src * 128 + k)) =
-          make_uint4(pack2<BF16>(lo.x, lo.y), pack2<BF16>(lo.z, lo.w), pack2<BF16>(hi.x, hi.y), pack2<BF16>(hi.z, hi.w));
-    }
-    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -163,7 +149,15 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     int li = BF_RING;
     for (int mi = 0; mi < n_atoms; ++mi) {
       const int meta = atoms[mi].meta;
+      if (lane == 0 && mi >= 1 && li < n_atoms) {   // refill the slot of the previous atom once its MMAs have drained
+        const int ps = (mi - 1) % BF_RING;
+        mbar_wait(smem_u32(&bars[4 + ps]), (uint32_t)(((mi - 1) / BF_RING) & 1));
+        mbar_expect_tx(smem_u32(&bars[ps]), BF_ATOM);
+        bulk_g2s(smem_u32(ring + ps * BF_ATOM), atoms[li].src, BF_ATOM, smem_u32(&bars[ps]));
+        ++li;
+      }
       if (meta & (1 << 12)) {                   // first atom of a GEMM: wait until its A operand is published
+        __syncwarp();
         named_bar(2, BF_THREADS);
         tc_fence_after();
       }
@@ -171,21 +165,14 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
         const int slot = mi % BF_RING;
         mbar_wait(smem_u32(&bars[slot]), (uint32_t)((mi / BF_RING) & 1));
         tc_fence_after();
-        const int g = meta & 15, nc = (meta >> 4) & 15, kc = (meta >> 8) & 15;
-        const uint32_t d = tmem_base + (uint32_t)(nc * 128);
+        const int g = meta & 15, j = (meta >> 4) & 15, kc = (meta >> 8) & 15;
+        const uint32_t d = tmem_base + (uint32_t)(j * 128);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
           umma_f16(d, sw128_desc(a_base + kc * BF_ATOM + ks * 32), sw128_desc(r_base + slot * BF_ATOM + ks * 32), idesc,
                    (kc | ks) ? 1u : 0u);
         umma_commit(smem_u32(&bars[4 + slot]));
         if (meta & (1 << 13)) umma_commit(smem_u32(&bars[8 + g]));
-        if (mi >= 1 && li < n_atoms) {          // refill the slot of the previous atom once its MMAs have drained
-          const int ps = (mi - 1) % BF_RING;
-          mbar_wait(smem_u32(&bars[4 + ps]), (uint32_t)(((mi - 1) / BF_RING) & 1));
-          mbar_expect_tx(smem_u32(&bars[ps]), BF_ATOM);
-          bulk_g2s(smem_u32(ring + ps * BF_ATOM), atoms[li].src, BF_ATOM, smem_u32(&bars[ps]));
-          ++li;
-        }
       }
       __syncwarp();
     }
@@ -201,6 +188,41 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     const int col = tid & 127, chalf = tid >> 7;     // column-phase identity: column, graph parity
     const float* vb = vec; const float* vw0 = vec + BF_NVEC; const float* vw1 = vec + 2 * BF_NVEC;
     float* srow = stg + row * BF_LD;
+    constexpr int S1 = 256, S2 = 384;                // TMEM stashes (fp32 rows): x then u ; h then h'
+
+    auto load8 = [&](const float* src, float (&v)[8]) {
+      const float4 a0 = *reinterpret_cast<const float4*>(src), a1 = *reinterpret_cast<const float4*>(src + 4);
+      v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+    };
+    auto store8 = [&](float* dst, const float (&v)[8]) {
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    };
+    auto store_a8 = [&](int acol, const float (&v)[8]) {     // 8 consecutive k of this thread's A row
+      *reinterpret_cast<uint4*>(a_s + sw128_off(128, row, acol)) =
+          make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7]));
+    };
+    // ---- inputs: this thread's 64 columns of its x (and h) row -> A operand + fp32 stash in TMEM ------------
+    {
+      float xv[8][8], hv[8][8];
+#pragma unroll
+      for (int cg = 0; cg < 8; ++cg) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { xv[cg][i] = 0.f; hv[cg][i] = 0.f; }
+        if (live) {
+          load8(p.x_clu + grow * 128 + half * 64 + cg * 8, xv[cg]);
+          if (has_h) load8(p.hidden_in + grow * 128 + half * 64 + cg * 8, hv[cg]);
+        }
+      }
+#pragma unroll
+      for (int cg = 0; cg < 8; ++cg) {
+        const int c = half * 64 + cg * 8;
+        store_a8(c, xv[cg]);
+        tmem_st8(t_lane + (uint32_t)(S1 + c), xv[cg]);
+        if (has_h) { store_a8(128 + c, hv[cg]); tmem_st8(t_lane + (uint32_t)(S2 + c), hv[cg]); }
+      }
+      tmem_st_wait();
+    }
 
     auto wait_done = [&](int g) { mbar_wait(smem_u32(&bars[8 + g]), 0); tc_fence_after(); };
     auto publish_a = [&]() { fence_proxy_async(); tc_fence_before(); named_bar(2, BF_THREADS); };
@@ -216,23 +238,11 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
       o[4] = fmaf(ps.y, y1.x, fmaf(ps.x, x1.x, acc[4] + b1.x)); o[5] = fmaf(ps.y, y1.y, fmaf(ps.x, x1.y, acc[5] + b1.y));
       o[6] = fmaf(ps.y, y1.z, fmaf(ps.x, x1.z, acc[6] + b1.z)); o[7] = fmaf(ps.y, y1.w, fmaf(ps.x, x1.w, acc[7] + b1.w));
     };
-    auto load8 = [&](const float* src, float (&v)[8]) {
-      const float4 a0 = *reinterpret_cast<const float4*>(src), a1 = *reinterpret_cast<const float4*>(src + 4);
-      v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-    };
-    auto store8 = [&](float* dst, const float (&v)[8]) {
-      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    };
-    auto store_a8 = [&](int acol, const float (&v)[8]) {     // 8 consecutive k of this thread's A row
-      *reinterpret_cast<uint4*>(a_s + sw128_off(128, row, acol)) =
-          make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7]));
-    };
     auto sigmoid_fast = [](float x) { return __fdividef(1.f, 1.f + __expf(-x)); };
     auto tanh_fast = [](float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); };
     // Q part of a [P|Q] product (TMEM columns dcol..dcol+127) -> staging
     auto q_to_staging = [&](int dcol, int vbase) {
-#pragma unroll 1
+#pragma unroll 2
       for (int cg = 0; cg < 8; ++cg) {
         const int c = half * 64 + cg * 8;
         float acc[8], o[8];
@@ -249,10 +259,22 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     auto colmax_broadcast = [&](bool use_mask) {
       for (int k = chalf; k < G; k += 2) {
         const int rb = g_beg[k], re = g_beg[k + 1];
-        float m = -INFINITY;
-        for (int r = rb; r < re; ++r)
-          if (!use_mask || alive_s[r]) m = fmaxf(m, stg[r * BF_LD + col]);
-        for (int r = rb; r < re; ++r) stg[r * BF_LD + col] = m;
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        int r = rb;
+        for (; r + 4 <= re; r += 4) {           // four independent loads in flight
+          const float a0 = stg[r * BF_LD + col], a1 = stg[(r + 1) * BF_LD + col];
+          const float a2 = stg[(r + 2) * BF_LD + col], a3 = stg[(r + 3) * BF_LD + col];
+          const uint32_t al = use_mask ? ((uint32_t)alive_s[r] | ((uint32_t)alive_s[r + 1] << 8) | ((uint32_t)alive_s[r + 2] << 16) | ((uint32_t)alive_s[r + 3] << 24)) : 0x01010101u;
+          if (al & 0x000000ffu) m0 = fmaxf(m0, a0);
+          if (al & 0x0000ff00u) m1 = fmaxf(m1, a1);
+          if (al & 0x00ff0000u) m2 = fmaxf(m2, a2);
+          if (al & 0xff000000u) m3 = fmaxf(m3, a3);
+        }
+        for (; r < re; ++r)
+          if (!use_mask || alive_s[r]) m0 = fmaxf(m0, stg[r * BF_LD + col]);
+        const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+#pragma unroll 4
+        for (r = rb; r < re; ++r) stg[r * BF_LD + col] = m;
       }
     };
     // PERConv tail: conv = P + max (0 for rows outside the node set) -> GraphNorm -> ReLU -> A k-chunks 0,1
@@ -261,7 +283,7 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
       named_bar(1, 256);
       colmax_broadcast(true);
       named_bar(1, 256);
-#pragma unroll 1
+#pragma unroll 2
       for (int cg = 0; cg < 8; ++cg) {
         const int c = half * 64 + cg * 8;
         float acc[8], o[8];
@@ -279,11 +301,14 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
         const int rb = g_beg[k], re = g_beg[k + 1];
         const float inv_n = 1.f / (float)(re - rb);
         float sum = 0.f;
+#pragma unroll 4
         for (int r = rb; r < re; ++r) sum += stg[r * BF_LD + col];
         const float shift = sum * inv_n * ms;
         float sq = 0.f;
+#pragma unroll 4
         for (int r = rb; r < re; ++r) { const float o = stg[r * BF_LD + col] - shift; sq = fmaf(o, o, sq); }
         const float rstd = 1.f / sqrtf(sq * inv_n + 1e-5f);
+#pragma unroll 4
         for (int r = rb; r < re; ++r) {
           const float o = stg[r * BF_LD + col] - shift;
           const float y = fmaxf(fmaf(w * o, rstd, b), 0.f);
@@ -292,24 +317,44 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
         }
       }
     };
-    // fc tail: y = relu(acc + b + residual) ; to_a: 16-bit -> A k-chunks 0,1 ; out: fp32 rows to global
-    auto fc_epilogue = [&](int vbase, const float* resid, bool to_a, float* out) {
-#pragma unroll 1
+    // fc tail: y = relu(acc + b + residual), residual = fp32 row stash in TMEM ; to_a: 16-bit -> A k-chunks 0,1 ;
+    // out: fp32 rows to global
+    auto fc_epilogue = [&](int vbase, int stash, bool to_a, float* out) {
+#pragma unroll 2
       for (int cg = 0; cg < 8; ++cg) {
         const int c = half * 64 + cg * 8;
         float acc[8], r8[8], y[8];
         tmem_ld8(t_lane + (uint32_t)c, acc);
+        tmem_ld8(t_lane + (uint32_t)(stash + c), r8);
         tmem_ld_wait();
-        if (live) {
-          load8(resid + grow * 128 + c, r8);
-          const float4 b0 = *reinterpret_cast<const float4*>(vb + vbase + c), b1 = *reinterpret_cast<const float4*>(vb + vbase + c + 4);
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const float4 b0 = *reinterpret_cast<const float4*>(vb + vbase + c), b1 = *reinterpret_cast<const float4*>(vb + vbase + c + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = fmaxf(acc[i] + bb[i] + r8[i], 0.f);
+        for (int i = 0; i < 8; ++i) y[i] = fmaxf(acc[i] + bb[i] + r8[i], 0.f);
+        if (live) {
           if (to_a) store_a8(c, y);
           if (out) store8(out + grow * 128 + c, y);
         }
       }
+    };
+    // one half of the gate product: sigmoid(P + column max of Q over the whole graph) for this thread's columns
+    auto gate_half = [&](int vp, int vq, auto&& sink) {
+      q_to_staging(128, vq);
+      named_bar(1, 256);
+      colmax_broadcast(false);
+      named_bar(1, 256);
+#pragma unroll 2
+      for (int cg = 0; cg < 8; ++cg) {
+        const int c = half * 64 + cg * 8;
+        float acc[8], o[8];
+        tmem_ld8(t_lane + (uint32_t)c, acc);
+        tmem_ld_wait();
+        lin8(acc, vp + c, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = sigmoid_fast(o[i] + (live ? srow[c + i] : 0.f));
+        sink(c, o);
+      }
+      named_bar(1, 256);      // staging is reused by the next epilogue
     };
 
     // ---- GEMM 0: c0 [P|Q] --------------------------------------------------------------------------------
@@ -319,86 +364,62 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     // ---- GEMM 1: c0.fc + x -> y0 (A k-chunks 0,1) ----------------------------------------------------------
     publish_a();
     wait_done(1);
-    fc_epilogue(VB_C0FC, p.x_clu, true, nullptr);
-    // ---- GEMM 2: gates on the target graph (every cluster is a node): r -> h*r (A k-chunks 2,3), u -> scratch
+    fc_epilogue(VB_C0FC, S1, true, nullptr);
+    // ---- GEMM 2: update gate u on the target graph (every cluster is a node) -> stash S1 (x is dead) -----------
     publish_a();
     wait_done(2);
-    // r: P columns [0,128), Q columns [256,384)
-    q_to_staging(256, VB_G + 256);
-    named_bar(1, 256);
-    colmax_broadcast(false);
-    named_bar(1, 256);
-    if (has_h) {
-#pragma unroll 1
-      for (int cg = 0; cg < 8; ++cg) {
-        const int c = half * 64 + cg * 8;
-        float acc[8], o[8], hv[8];
-        tmem_ld8(t_lane + (uint32_t)c, acc);
-        tmem_ld_wait();
-        lin8(acc, VB_G + c, o);
-        if (live) {
-          load8(p.hidden_in + grow * 128 + c, hv);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = hv[i] * sigmoid_fast(o[i] + srow[c + i]);
-          store_a8(128 + c, o);
-        }
-      }
-    }
-    named_bar(1, 256);
-    // u: P columns [128,256), Q columns [384,512)
-    q_to_staging(384, VB_G + 384);
-    named_bar(1, 256);
-    colmax_broadcast(false);
-    named_bar(1, 256);
-#pragma unroll 1
-    for (int cg = 0; cg < 8; ++cg) {
-      const int c = half * 64 + cg * 8;
-      float acc[8], o[8];
-      tmem_ld8(t_lane + (uint32_t)(128 + c), acc);
-      tmem_ld_wait();
-      lin8(acc, VB_G + 128 + c, o);
-      if (live) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = sigmoid_fast(o[i] + srow[c + i]);
-        store8(p.u_scratch + grow * 128 + c, o);     // read back by this same thread in the candidate epilogue
-      }
-    }
-    named_bar(1, 256);
-    // ---- GEMM 3: candidate on the current graph: h' = (1 - u) h + u tanh(conv) -> hidden_out, A k-chunks 0,1 ----
-    publish_a();
+    gate_half(VB_G + 128, VB_G + 384, [&](int c, float (&o)[8]) { tmem_st8(t_lane + (uint32_t)(S1 + c), o); });
+    tmem_st_wait();
+    // ---- GEMM 3: reset gate r -> h * r replaces h in A k-chunks 2,3 (the product has already read them) --------
+    publish_a();               // nothing new in A: the barrier only orders this epilogue's TMEM reads before the MMAs
     wait_done(3);
+    gate_half(VB_G, VB_G + 256, [&](int c, float (&o)[8]) {
+      if (has_h) {
+        float hv[8];
+        tmem_ld8(t_lane + (uint32_t)(S2 + c), hv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] *= hv[i];
+        if (live) store_a8(128 + c, o);
+      }
+    });
+    // ---- GEMM 4: candidate on the current graph: h' = (1 - u) h + u tanh(conv) -> hidden_out, A k-chunks 0,1, S2 --
+    publish_a();
+    wait_done(4);
     q_to_staging(128, VB_K + 128);
     named_bar(1, 256);
     colmax_broadcast(true);
     named_bar(1, 256);
-#pragma unroll 1
+#pragma unroll 2
     for (int cg = 0; cg < 8; ++cg) {
       const int c = half * 64 + cg * 8;
       float acc[8], o[8], hv[8], uu[8];
       tmem_ld8(t_lane + (uint32_t)c, acc);
+      tmem_ld8(t_lane + (uint32_t)(S1 + c), uu);
+      if (has_h) tmem_ld8(t_lane + (uint32_t)(S2 + c), hv);
       tmem_ld_wait();
       lin8(acc, VB_K + c, o);
-      if (live) {
-        load8(p.u_scratch + grow * 128 + c, uu);
-        if (has_h) load8(p.hidden_in + grow * 128 + c, hv);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float cv = alive ? o[i] + srow[c + i] : 0.f;
-          o[i] = (1.f - uu[i]) * (has_h ? hv[i] : 0.f) + uu[i] * tanh_fast(cv);
-        }
+      for (int i = 0; i < 8; ++i) {
+        const float cv = alive ? o[i] + srow[c + i] : 0.f;
+        o[i] = (1.f - uu[i]) * (has_h ? hv[i] : 0.f) + uu[i] * tanh_fast(cv);
+      }
+      tmem_st8(t_lane + (uint32_t)(S2 + c), o);
+      if (live) {
         store8(p.hidden_out + grow * 128 + c, o);
         store_a8(c, o);
       }
     }
+    tmem_st_wait();
     named_bar(1, 256);          // staging is reused by the next epilogue
-    // ---- GEMM 4: c1 [P|Q] on h' ----------------------------------------------------------------------------
-    publish_a();
-    wait_done(4);
-    perconv_epilogue(VB_C1, p.gn1_w, p.gn1_b, p.gn1_ms);
-    // ---- GEMM 5: c1.fc + h' -> x2 ----------------------------------------------------------------------------
+    // ---- GEMM 5: c1 [P|Q] on h' ----------------------------------------------------------------------------
     publish_a();
     wait_done(5);
-    fc_epilogue(VB_C1FC, p.hidden_out, false, p.x2);
+    perconv_epilogue(VB_C1, p.gn1_w, p.gn1_b, p.gn1_ms);
+    // ---- GEMM 6: c1.fc + h' -> x2 ----------------------------------------------------------------------------
+    publish_a();
+    wait_done(6);
+    fc_epilogue(VB_C1FC, S2, false, p.x2);
   }
   tc_fence_before();
   __syncthreads();

@@ -99,6 +99,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
                : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
                : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&r)[8]) {
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(r);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :: "r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start>>4 | SBO(1024 B)>>4 at
