@@ -15,14 +15,19 @@
 // through one fp32 staging tile (thread = row writes, thread = column reduces, conflict-free with a
 // 129-float row pitch).  Weights stream from L2 as 16 KB atoms (128 outputs x 64 k) through a 4-deep
 // TMA ring that runs ahead across GEMM boundaries.  Warps 0-7: epilogues (warp % 4 = TMEM lane quarter,
-// warp / 4 = column half of each 128-column chunk); warp 8: TMA + MMA issue.
+// warp / 4 = column slice of each 128-column chunk); the last warp: TMA + MMA issue.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
 
 namespace cns {
 
-constexpr int BF_THREADS = 288;
+constexpr int BF_WORKER_WARPS = 16;                      // epilogue warps: warp % 4 = TMEM lane quarter, warp / 4 = column slice
+constexpr int BF_WORKERS = BF_WORKER_WARPS * 32;
+constexpr int BF_THREADS = BF_WORKERS + 32;             // + one TMA / MMA-issue warp
+constexpr int BF_SLICES = BF_WORKER_WARPS / 4;          // column slices of a 128-column chunk (and graph slots of the column passes)
+constexpr int BF_SLICE_COLS = 128 / BF_SLICES;
+constexpr int BF_GROUPS = BF_SLICE_COLS / 8;            // 8-column trips per thread
 constexpr int BF_ATOM = 128 * 128;        // bytes: 128 output rows x 64 k x 2 B
 constexpr int BF_RING = 4;
 constexpr int BF_LD = 129;                // staging row pitch (floats)
@@ -106,7 +111,7 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     vec[BF_NVEC + i] = wp ? wp[j] : 0.f;
     vec[2 * BF_NVEC + i] = wp ? wp[n + j] : 0.f;
   }
-  if (warp == 8) {
+  if (warp == BF_WORKER_WARPS) {
     if (lane == 0) {
       for (int i = 0; i < 15; ++i) mbar_init(smem_u32(&bars[i]), 1);
       fence_mbar_init();
@@ -140,7 +145,7 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
 
-  if (warp == 8) {
+  if (warp == BF_WORKER_WARPS) {
     // =============================== TMA + MMA issue ====================================================
     const uint32_t fmt = BF16 ? 1u : 0u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
@@ -185,7 +190,7 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     const int64_t grow = (int64_t)row0 + (live ? row : 0);
     const float2 ps = live ? reinterpret_cast<const float2*>(p.pos_clu)[grow] : make_float2(0.f, 0.f);
     const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16);
-    const int col = tid & 127, chalf = tid >> 7;     // column-phase identity: column, graph parity
+    const int col = tid & 127, chalf = tid >> 7;     // column-phase identity: column, graph slot
     const float* vb = vec; const float* vw0 = vec + BF_NVEC; const float* vw1 = vec + 2 * BF_NVEC;
     float* srow = stg + row * BF_LD;
     constexpr int S1 = 256, S2 = 384;                // TMEM stashes (fp32 rows): x then u ; h then h'
@@ -204,19 +209,19 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     };
     // ---- inputs: this thread's 64 columns of its x (and h) row -> A operand + fp32 stash in TMEM ------------
     {
-      float xv[8][8], hv[8][8];
+      float xv[BF_GROUPS][8], hv[BF_GROUPS][8];
 #pragma unroll
-      for (int cg = 0; cg < 8; ++cg) {
+      for (int cg = 0; cg < BF_GROUPS; ++cg) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { xv[cg][i] = 0.f; hv[cg][i] = 0.f; }
         if (live) {
-          load8(p.x_clu + grow * 128 + half * 64 + cg * 8, xv[cg]);
-          if (has_h) load8(p.hidden_in + grow * 128 + half * 64 + cg * 8, hv[cg]);
+          load8(p.x_clu + grow * 128 + half * BF_SLICE_COLS + cg * 8, xv[cg]);
+          if (has_h) load8(p.hidden_in + grow * 128 + half * BF_SLICE_COLS + cg * 8, hv[cg]);
         }
       }
 #pragma unroll
-      for (int cg = 0; cg < 8; ++cg) {
-        const int c = half * 64 + cg * 8;
+      for (int cg = 0; cg < BF_GROUPS; ++cg) {
+        const int c = half * BF_SLICE_COLS + cg * 8;
         store_a8(c, xv[cg]);
         tmem_st8(t_lane + (uint32_t)(S1 + c), xv[cg]);
         if (has_h) { store_a8(128 + c, hv[cg]); tmem_st8(t_lane + (uint32_t)(S2 + c), hv[cg]); }
@@ -243,8 +248,8 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     // Q part of a [P|Q] product (TMEM columns dcol..dcol+127) -> staging
     auto q_to_staging = [&](int dcol, int vbase) {
 #pragma unroll 2
-      for (int cg = 0; cg < 8; ++cg) {
-        const int c = half * 64 + cg * 8;
+      for (int cg = 0; cg < BF_GROUPS; ++cg) {
+        const int c = half * BF_SLICE_COLS + cg * 8;
         float acc[8], o[8];
         tmem_ld8(t_lane + (uint32_t)(dcol + c), acc);
         tmem_ld_wait();
@@ -257,7 +262,7 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     };
     // per graph: max over the node set (all rows, or rows with mask) of staging column `col`, broadcast in place
     auto colmax_broadcast = [&](bool use_mask) {
-      for (int k = chalf; k < G; k += 2) {
+      for (int k = chalf; k < G; k += BF_SLICES) {
         const int rb = g_beg[k], re = g_beg[k + 1];
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
         int r = rb;
@@ -280,12 +285,12 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     // PERConv tail: conv = P + max (0 for rows outside the node set) -> GraphNorm -> ReLU -> A k-chunks 0,1
     auto perconv_epilogue = [&](int vbase, const float* gw, const float* gb, const float* gms) {
       q_to_staging(128, vbase + 128);
-      named_bar(1, 256);
+      named_bar(1, BF_WORKERS);
       colmax_broadcast(true);
-      named_bar(1, 256);
+      named_bar(1, BF_WORKERS);
 #pragma unroll 2
-      for (int cg = 0; cg < 8; ++cg) {
-        const int c = half * 64 + cg * 8;
+      for (int cg = 0; cg < BF_GROUPS; ++cg) {
+        const int c = half * BF_SLICE_COLS + cg * 8;
         float acc[8], o[8];
         tmem_ld8(t_lane + (uint32_t)c, acc);
         tmem_ld_wait();
@@ -295,9 +300,9 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
           for (int i = 0; i < 8; ++i) srow[c + i] = alive ? o[i] + srow[c + i] : 0.f;
         }
       }
-      named_bar(1, 256);
+      named_bar(1, BF_WORKERS);
       const float w = gw[col], b = gb[col], ms = gms[col];
-      for (int k = chalf; k < G; k += 2) {
+      for (int k = chalf; k < G; k += BF_SLICES) {
         const int rb = g_beg[k], re = g_beg[k + 1];
         const float inv_n = 1.f / (float)(re - rb);
         float sum = 0.f;
@@ -321,8 +326,8 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     // out: fp32 rows to global
     auto fc_epilogue = [&](int vbase, int stash, bool to_a, float* out) {
 #pragma unroll 2
-      for (int cg = 0; cg < 8; ++cg) {
-        const int c = half * 64 + cg * 8;
+      for (int cg = 0; cg < BF_GROUPS; ++cg) {
+        const int c = half * BF_SLICE_COLS + cg * 8;
         float acc[8], r8[8], y[8];
         tmem_ld8(t_lane + (uint32_t)c, acc);
         tmem_ld8(t_lane + (uint32_t)(stash + c), r8);
@@ -340,12 +345,12 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     // one half of the gate product: sigmoid(P + column max of Q over the whole graph) for this thread's columns
     auto gate_half = [&](int vp, int vq, auto&& sink) {
       q_to_staging(128, vq);
-      named_bar(1, 256);
+      named_bar(1, BF_WORKERS);
       colmax_broadcast(false);
-      named_bar(1, 256);
+      named_bar(1, BF_WORKERS);
 #pragma unroll 2
-      for (int cg = 0; cg < 8; ++cg) {
-        const int c = half * 64 + cg * 8;
+      for (int cg = 0; cg < BF_GROUPS; ++cg) {
+        const int c = half * BF_SLICE_COLS + cg * 8;
         float acc[8], o[8];
         tmem_ld8(t_lane + (uint32_t)c, acc);
         tmem_ld_wait();
@@ -354,7 +359,7 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
         for (int i = 0; i < 8; ++i) o[i] = sigmoid_fast(o[i] + (live ? srow[c + i] : 0.f));
         sink(c, o);
       }
-      named_bar(1, 256);      // staging is reused by the next epilogue
+      named_bar(1, BF_WORKERS);      // staging is reused by the next epilogue
     };
 
     // ---- GEMM 0: c0 [P|Q] --------------------------------------------------------------------------------
@@ -387,12 +392,12 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     publish_a();
     wait_done(4);
     q_to_staging(128, VB_K + 128);
-    named_bar(1, 256);
+    named_bar(1, BF_WORKERS);
     colmax_broadcast(true);
-    named_bar(1, 256);
+    named_bar(1, BF_WORKERS);
 #pragma unroll 2
-    for (int cg = 0; cg < 8; ++cg) {
-      const int c = half * 64 + cg * 8;
+    for (int cg = 0; cg < BF_GROUPS; ++cg) {
+      const int c = half * BF_SLICE_COLS + cg * 8;
       float acc[8], o[8], hv[8], uu[8];
       tmem_ld8(t_lane + (uint32_t)c, acc);
       tmem_ld8(t_lane + (uint32_t)(S1 + c), uu);
@@ -411,7 +416,7 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
       }
     }
     tmem_st_wait();
-    named_bar(1, 256);          // staging is reused by the next epilogue
+    named_bar(1, BF_WORKERS);          // staging is reused by the next epilogue
     // ---- GEMM 5: c1 [P|Q] on h' ----------------------------------------------------------------------------
     publish_a();
     wait_done(5);
@@ -424,7 +429,7 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
+  if (warp == BF_WORKER_WARPS) tmem_dealloc(tmem_base, 512);
 }
 
 size_t backbone_fused_scratch_ints(int64_t n_graphs) { return (size_t)(2 * n_graphs + 8); }
