@@ -1,11 +1,12 @@
-// Fused cluster-level backbone (tcgen05): PERConv -> PEConvGRUCell -> PERConv in ONE kernel
-// (cns/models/graph_vs.py:115-190,233-251), for batches whose cluster graphs are complete digraphs
+// Fused cluster-level backbone (tcgen05): out_enc -> PERConv -> PEConvGRUCell -> PERConv in ONE kernel
+// (cns/models/graph_vs.py:115-190,229-251), for batches whose cluster graphs are complete digraphs
 // (CNS_BATCH_L1_*_COMPLETE) with at most 128 clusters per graph.
 //
 // With complete graphs the only coupling between cluster rows is per graph: the column max of the
 // PointEdgeConv messages and the GraphNorm statistics.  A CTA therefore owns a tile of WHOLE graphs
 // (<= 128 cluster rows = the 128 TMEM lanes) and walks the GEMMs of the chain back to back:
 //
+//   [cur | tar - cur] --out_enc--> x = relu(.) * cluster_mask
 //   x --c0 [P|Q]--> max/GraphNorm/ReLU --c0.fc + x--> y0
 //   [y0|h] --gates [P|Q]--> max/sigmoid -> r, u ; [y0|h*r] --candidate [P|Q]--> max/tanh -> h' = (1-u) h + u c
 //   h' --c1 [P|Q]--> max/GraphNorm/ReLU --c1.fc + h'--> x2
@@ -31,39 +32,13 @@ constexpr int BF_GROUPS = BF_SLICE_COLS / 8;            // 8-column trips per th
 constexpr int BF_ATOM = 128 * 128;        // bytes: 128 output rows x 64 k x 2 B
 constexpr int BF_RING = 4;
 constexpr int BF_LD = 129;                // staging row pitch (floats)
-constexpr int BF_NVEC = 1536;             // per-column epilogue vectors of the six GEMMs, concatenated
-constexpr int BF_MAX_ATOMS = 40;
+constexpr int BF_NVEC = 1664;             // per-column epilogue vectors of the GEMMs, concatenated
+constexpr int BF_MAX_ATOMS = 48;
 // vector bases of the six GEMMs inside the concatenation
-constexpr int VB_C0 = 0, VB_C0FC = 256, VB_G = 384, VB_K = 896, VB_C1 = 1152, VB_C1FC = 1408;
+constexpr int VB_C0 = 0, VB_C0FC = 256, VB_G = 384, VB_K = 896, VB_C1 = 1152, VB_C1FC = 1408, VB_OUT = 1536;
 
 constexpr size_t BF_SMEM = 65536 /*A*/ + BF_RING * BF_ATOM /*ring*/ + 128 * BF_LD * 4 /*staging*/ + 3 * BF_NVEC * 4 +
                            BF_MAX_ATOMS * 16 + 1024 /*bars, tables*/ + 1024 /*alignment slack*/;
-
-// ---- tiles of whole graphs --------------------------------------------------------------------------
-// tile_graph[t] = first graph of tile t (greedy: as many consecutive graphs as fit in 128 rows)
-__global__ void __launch_bounds__(1024)
-tile_pack_kernel(const int* __restrict__ graph_ptr, int n_graphs, int* __restrict__ next, int* __restrict__ tile_graph,
-                 int* __restrict__ n_tiles, int* __restrict__ err) {
-  // next[g] = first graph that does not fit into a tile starting at g (binary search on the prefix sums)
-  __shared__ int next_s[8192];
-  for (int g = threadIdx.x; g < n_graphs; g += 1024) {
-    const int lim = graph_ptr[g] + 128;
-    if (graph_ptr[g + 1] > lim) atomicExch(err, 4);     // a graph with more than 128 clusters
-    int lo = g + 1, hi = n_graphs;                      // largest q in [g+1, B] with graph_ptr[q] <= lim
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (graph_ptr[mid] <= lim) lo = mid; else hi = mid - 1;
-    }
-    next_s[g] = lo;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0, g = 0;
-    while (g < n_graphs) { tile_graph[t++] = g; const int q = next_s[g]; g = q > g ? q : g + 1; }
-    tile_graph[t] = n_graphs;
-    *n_tiles = t;
-  }
-}
 
 struct BfAtom { const unsigned char* src; int meta; int pad; };   // meta: g | nc << 4 | kc << 8 | first << 12 | last << 13
 
@@ -80,7 +55,7 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
   float* vec = stg + 128 * BF_LD;                              // [3][BF_NVEC]: bias, wp row 0, wp row 1
   BfAtom* atoms = reinterpret_cast<BfAtom*>(vec + 3 * BF_NVEC);
   unsigned char* tail = reinterpret_cast<unsigned char*>(atoms + BF_MAX_ATOMS);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // full[4], empty[4], done[7]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // full[4], empty[4], done[8]
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tail + 128);
   int* n_atoms_s = reinterpret_cast<int*>(tail + 136);
   int* g_beg = reinterpret_cast<int*>(tail + 144);             // [<=129] local first row of the tile's graphs
@@ -92,7 +67,7 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
   const int G = g1 - g0;
   const int row0 = p.graph_ptr[g0];
   const int R = p.graph_ptr[g1] - row0;
-  if (R > 128) return;                                         // a graph above the advertised bound (status word set by tile_pack)
+  if (R > 128) return;                                         // a graph above the advertised bound (status word set by graph_tiles)
   const bool has_h = p.hidden_in != nullptr;
   const int kh = has_h ? 4 : 2;                                // k-chunks of the two GRU products
 
@@ -106,24 +81,25 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     else if (i < VB_K) { b = p.g_b; wp = p.g_wp; j = i - VB_G; n = 512; }
     else if (i < VB_C1) { b = p.k_b; wp = p.k_wp; j = i - VB_K; n = 256; }
     else if (i < VB_C1FC) { b = p.c1_b; wp = p.c1_wp; j = i - VB_C1; n = 256; }
-    else { b = p.c1fc_b; wp = nullptr; j = i - VB_C1FC; n = 128; }
+    else if (i < VB_OUT) { b = p.c1fc_b; wp = nullptr; j = i - VB_C1FC; n = 128; }
+    else { b = p.out_b; wp = nullptr; j = i - VB_OUT; n = 128; }
     vec[i] = b[j];
     vec[BF_NVEC + i] = wp ? wp[j] : 0.f;
     vec[2 * BF_NVEC + i] = wp ? wp[n + j] : 0.f;
   }
   if (warp == BF_WORKER_WARPS) {
     if (lane == 0) {
-      for (int i = 0; i < 15; ++i) mbar_init(smem_u32(&bars[i]), 1);
+      for (int i = 0; i < 16; ++i) mbar_init(smem_u32(&bars[i]), 1);
       fence_mbar_init();
       // weight atoms in issue order.  The gate product runs as two N = 256 halves, update gate first: every
       // accumulator then fits TMEM columns [0,256) and [256,512) stays free for fp32 row stashes.
-      const unsigned char* img[7] = {p.w_c0, p.w_c0fc, p.w_g, p.w_g, p.w_k, p.w_c1, p.w_c1fc};
-      const int ncs[7] = {2, 1, 2, 2, 2, 2, 1};
-      const int nc0[7] = {0, 0, 1, 0, 0, 0, 0}, ncstep[7] = {1, 1, 2, 2, 1, 1, 1};    // image n-chunk = nc0 + j * ncstep
-      const int kimg[7] = {2, 2, 4, 4, 4, 2, 2};
-      const int kuse[7] = {2, 2, kh, kh, kh, 2, 2};
+      const unsigned char* img[8] = {p.w_out, p.w_c0, p.w_c0fc, p.w_g, p.w_g, p.w_k, p.w_c1, p.w_c1fc};
+      const int ncs[8] = {1, 2, 1, 2, 2, 2, 2, 1};
+      const int nc0[8] = {0, 0, 0, 1, 0, 0, 0, 0}, ncstep[8] = {1, 1, 1, 2, 2, 1, 1, 1};    // image n-chunk = nc0 + j * ncstep
+      const int kimg[8] = {4, 2, 2, 4, 4, 4, 2, 2};
+      const int kuse[8] = {4, 2, 2, kh, kh, kh, 2, 2};
       int n = 0;
-      for (int g = 0; g < 7; ++g)
+      for (int g = 0; g < 8; ++g)
         for (int j = 0; j < ncs[g]; ++j)
           for (int kc = 0; kc < kuse[g]; ++kc) {
             const bool first = j == 0 && kc == 0, last = j == ncs[g] - 1 && kc == kuse[g] - 1;
@@ -207,24 +183,29 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
       *reinterpret_cast<uint4*>(a_s + sw128_off(128, row, acol)) =
           make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7]));
     };
-    // ---- inputs: this thread's 64 columns of its x (and h) row -> A operand + fp32 stash in TMEM ------------
+    // ---- inputs: this thread's columns of the two encoder feature rows -> A = [cur | tar - cur] (out_enc,
+    //      graph_vs.py:229-230) ; its h row -> fp32 stash S2 --------------------------------------------------
     {
-      float xv[BF_GROUPS][8], hv[BF_GROUPS][8];
+      float xv[BF_GROUPS][8], dv[BF_GROUPS][8], hv[BF_GROUPS][8];
+      const float* tar = p.clu_feat + (size_t)p.n_clusters * 128;
 #pragma unroll
       for (int cg = 0; cg < BF_GROUPS; ++cg) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { xv[cg][i] = 0.f; hv[cg][i] = 0.f; }
+        for (int i = 0; i < 8; ++i) { xv[cg][i] = 0.f; dv[cg][i] = 0.f; hv[cg][i] = 0.f; }
         if (live) {
-          load8(p.x_clu + grow * 128 + half * BF_SLICE_COLS + cg * 8, xv[cg]);
+          load8(p.clu_feat + grow * 128 + half * BF_SLICE_COLS + cg * 8, xv[cg]);
+          load8(tar + grow * 128 + half * BF_SLICE_COLS + cg * 8, dv[cg]);
           if (has_h) load8(p.hidden_in + grow * 128 + half * BF_SLICE_COLS + cg * 8, hv[cg]);
         }
       }
 #pragma unroll
       for (int cg = 0; cg < BF_GROUPS; ++cg) {
         const int c = half * BF_SLICE_COLS + cg * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dv[cg][i] -= xv[cg][i];
         store_a8(c, xv[cg]);
-        tmem_st8(t_lane + (uint32_t)(S1 + c), xv[cg]);
-        if (has_h) { store_a8(128 + c, hv[cg]); tmem_st8(t_lane + (uint32_t)(S2 + c), hv[cg]); }
+        store_a8(128 + c, dv[cg]);
+        if (has_h) tmem_st8(t_lane + (uint32_t)(S2 + c), hv[cg]);
       }
       tmem_st_wait();
     }
@@ -362,22 +343,45 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
       named_bar(1, BF_WORKERS);      // staging is reused by the next epilogue
     };
 
-    // ---- GEMM 0: c0 [P|Q] --------------------------------------------------------------------------------
+    // ---- GEMM 0: out_enc: x = relu(.) * cluster_mask -> A k-chunks 0,1 + stash S1 ; h -> A k-chunks 2,3 --------
     publish_a();
     wait_done(0);
-    perconv_epilogue(VB_C0, p.gn0_w, p.gn0_b, p.gn0_ms);
-    // ---- GEMM 1: c0.fc + x -> y0 (A k-chunks 0,1) ----------------------------------------------------------
+#pragma unroll 2
+    for (int cg = 0; cg < BF_GROUPS; ++cg) {
+      const int c = half * BF_SLICE_COLS + cg * 8;
+      float acc[8], y[8];
+      tmem_ld8(t_lane + (uint32_t)c, acc);
+      tmem_ld_wait();
+      const float4 b0 = *reinterpret_cast<const float4*>(vb + VB_OUT + c), b1 = *reinterpret_cast<const float4*>(vb + VB_OUT + c + 4);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = alive ? fmaxf(acc[i] + bb[i], 0.f) : 0.f;
+      store_a8(c, y);
+      tmem_st8(t_lane + (uint32_t)(S1 + c), y);
+      if (has_h) {
+        float hv[8];
+        tmem_ld8(t_lane + (uint32_t)(S2 + c), hv);
+        tmem_ld_wait();
+        store_a8(128 + c, hv);
+      }
+    }
+    tmem_st_wait();
+    // ---- GEMM 1: c0 [P|Q] --------------------------------------------------------------------------------
     publish_a();
     wait_done(1);
-    fc_epilogue(VB_C0FC, S1, true, nullptr);
-    // ---- GEMM 2: update gate u on the target graph (every cluster is a node) -> stash S1 (x is dead) -----------
+    perconv_epilogue(VB_C0, p.gn0_w, p.gn0_b, p.gn0_ms);
+    // ---- GEMM 2: c0.fc + x -> y0 (A k-chunks 0,1) ----------------------------------------------------------
     publish_a();
     wait_done(2);
+    fc_epilogue(VB_C0FC, S1, true, nullptr);
+    // ---- GEMM 3: update gate u on the target graph (every cluster is a node) -> stash S1 (x is dead) -----------
+    publish_a();
+    wait_done(3);
     gate_half(VB_G + 128, VB_G + 384, [&](int c, float (&o)[8]) { tmem_st8(t_lane + (uint32_t)(S1 + c), o); });
     tmem_st_wait();
-    // ---- GEMM 3: reset gate r -> h * r replaces h in A k-chunks 2,3 (the product has already read them) --------
+    // ---- GEMM 4: reset gate r -> h * r replaces h in A k-chunks 2,3 (the product has already read them) --------
     publish_a();               // nothing new in A: the barrier only orders this epilogue's TMEM reads before the MMAs
-    wait_done(3);
+    wait_done(4);
     gate_half(VB_G, VB_G + 256, [&](int c, float (&o)[8]) {
       if (has_h) {
         float hv[8];
@@ -388,9 +392,9 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
         if (live) store_a8(128 + c, o);
       }
     });
-    // ---- GEMM 4: candidate on the current graph: h' = (1 - u) h + u tanh(conv) -> hidden_out, A k-chunks 0,1, S2 --
+    // ---- GEMM 5: candidate on the current graph: h' = (1 - u) h + u tanh(conv) -> hidden_out, A k-chunks 0,1, S2 --
     publish_a();
-    wait_done(4);
+    wait_done(5);
     q_to_staging(128, VB_K + 128);
     named_bar(1, BF_WORKERS);
     colmax_broadcast(true);
@@ -417,13 +421,13 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     }
     tmem_st_wait();
     named_bar(1, BF_WORKERS);          // staging is reused by the next epilogue
-    // ---- GEMM 5: c1 [P|Q] on h' ----------------------------------------------------------------------------
-    publish_a();
-    wait_done(5);
-    perconv_epilogue(VB_C1, p.gn1_w, p.gn1_b, p.gn1_ms);
-    // ---- GEMM 6: c1.fc + h' -> x2 ----------------------------------------------------------------------------
+    // ---- GEMM 6: c1 [P|Q] on h' ----------------------------------------------------------------------------
     publish_a();
     wait_done(6);
+    perconv_epilogue(VB_C1, p.gn1_w, p.gn1_b, p.gn1_ms);
+    // ---- GEMM 7: c1.fc + h' -> x2 ----------------------------------------------------------------------------
+    publish_a();
+    wait_done(7);
     fc_epilogue(VB_C1FC, S2, false, p.x2);
   }
   tc_fence_before();
@@ -432,20 +436,14 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
   if (warp == BF_WORKER_WARPS) tmem_dealloc(tmem_base, 512);
 }
 
-size_t backbone_fused_scratch_ints(int64_t n_graphs) { return (size_t)(2 * n_graphs + 8); }
-
-int backbone_fused(const BackboneFusedArgs& a, int* next_scratch, int* err, bool bf16, cudaStream_t s) {
+int backbone_fused(const BackboneFusedArgs& a, bool bf16, cudaStream_t s) {
   if (a.n_graphs == 0 || a.n_clusters == 0) return CNS_OK;
-  CNS_REQUIRE(a.n_graphs <= 8192, "backbone_fused: at most 8192 graphs");
   static bool configured = false;
   if (!configured) {
     CNS_CUDA_CHECK(cudaFuncSetAttribute(backbone_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BF_SMEM));
     CNS_CUDA_CHECK(cudaFuncSetAttribute(backbone_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BF_SMEM));
     configured = true;
   }
-  tile_pack_kernel<<<1, 1024, 0, s>>>(a.graph_ptr, a.n_graphs, next_scratch, const_cast<int*>(a.tile_graph),
-                                      const_cast<int*>(a.n_tiles), err);
-  CNS_LAUNCH_CHECK();
   // greedy whole-graph tiles: two consecutive tiles always hold more than 128 rows together
   int64_t grid = 2 * ceil_div(a.n_clusters, 128) + 1;
   if (grid > a.n_graphs) grid = a.n_graphs;

@@ -258,15 +258,16 @@ enc_edge_fp32_kernel(EncEdgeArgs p) {
 // pos_clu = pos_tar[centre], cluster -> graph id.   (graph_vs.py:207-208,312-313)
 // ---------------------------------------------------------------------------------------------
 constexpr int CLU_ROWS = 8;
+constexpr int PRE_ROWS = 8;      // clusters per CTA of the pre-pass (32 rows per CTA measured 2x slower: too few CTAs in flight)
 
 __global__ void __launch_bounds__(128)
 enc_cluster_pre_kernel(EncPreArgs p) {
-  __shared__ float xs[CLU_ROWS][H];
+  __shared__ float xs[PRE_ROWS][H];
   const int o = threadIdx.x;
-  const int64_t c0 = (int64_t)blockIdx.x * CLU_ROWS;
+  const int64_t c0 = (int64_t)blockIdx.x * PRE_ROWS;
   float w0 = p.w_in[o * 2], w1 = p.w_in[o * 2 + 1], b = p.b_in[o];
 #pragma unroll
-  for (int r = 0; r < CLU_ROWS; ++r) {
+  for (int r = 0; r < PRE_ROWS; ++r) {
     int64_t c = c0 + r;
     float v = 0.f;
     if (c < p.n_clusters) {
@@ -281,18 +282,18 @@ enc_cluster_pre_kernel(EncPreArgs p) {
     xs[r][o] = v;
   }
   __syncthreads();
-  float acc[CLU_ROWS];
+  float acc[PRE_ROWS];
   const float ab = p.a_bias ? p.a_bias[o] : 0.f;
 #pragma unroll
-  for (int r = 0; r < CLU_ROWS; ++r) acc[r] = ab;
+  for (int r = 0; r < PRE_ROWS; ++r) acc[r] = ab;
 #pragma unroll 4
   for (int k = 0; k < H; ++k) {
     float w = p.lin_dst_t[k * H + o];
 #pragma unroll
-    for (int r = 0; r < CLU_ROWS; ++r) acc[r] = fmaf(xs[r][k], w, acc[r]);
+    for (int r = 0; r < PRE_ROWS; ++r) acc[r] = fmaf(xs[r][k], w, acc[r]);
   }
 #pragma unroll
-  for (int r = 0; r < CLU_ROWS; ++r)
+  for (int r = 0; r < PRE_ROWS; ++r)
     if (c0 + r < p.n_clusters) p.a_dst[(c0 + r) * H + o] = acc[r];
 }
 
@@ -317,7 +318,7 @@ enc_finish_kernel(EncFinishArgs p) {
         for (int side = 0; side < 2; ++side) {
           float* feat = p.clu_feat + ((size_t)side * p.n_clusters + c) * H;
           if (p0 == p1) {
-            f[side] = feat[o];
+            if (!p.fix_only) f[side] = feat[o];
           } else {
             const float* part = p.partial + (size_t)side * p.n_slots * 3 * H;
             float m = -INFINITY;
@@ -338,6 +339,7 @@ enc_finish_kernel(EncFinishArgs p) {
         p.clu_feat[((size_t)1 * p.n_clusters + c) * H + o] = 0.f;
       }
     }
+    if (p.fix_only) continue;
     cat[r][o] = f[0];
     cat[r][H + o] = f[1] - f[0];
     if (p.cat_out && c < p.n_clusters) {
@@ -345,7 +347,7 @@ enc_finish_kernel(EncFinishArgs p) {
       p.cat_out[c * 2 * H + H + o] = f[1] - f[0];
     }
   }
-  if (p.cat_out) return;
+  if (p.cat_out || p.fix_only) return;
   __syncthreads();
   float acc[CLU_ROWS];
   float b = p.b_out[o];
@@ -367,7 +369,7 @@ enc_finish_kernel(EncFinishArgs p) {
 // ---------------------------------------------------------------------------------------------
 int enc_cluster_pre(const EncPreArgs& a, cudaStream_t s) {
   if (a.n_clusters == 0) return CNS_OK;
-  enc_cluster_pre_kernel<<<ceil_div(a.n_clusters, CLU_ROWS), 128, 0, s>>>(a);
+  enc_cluster_pre_kernel<<<ceil_div(a.n_clusters, PRE_ROWS), 128, 0, s>>>(a);
   CNS_LAUNCH_CHECK();
   return CNS_OK;
 }

@@ -106,6 +106,14 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   if (!dense_cur && b->n_e11_cur > 0) CNS_REQUIRE(b->l1_edge_cur, "NULL l1_dense_edge_index_cur");
   if (!dense_tar && b->n_e11_tar > 0) CNS_REQUIRE(b->l1_edge_tar, "NULL l1_dense_edge_index_tar");
   const int64_t ne_cur = dense_cur ? 0 : b->n_e11_cur, ne_tar = dense_tar ? 0 : b->n_e11_tar;   // edges that need a CSR
+  // Cluster-level GEMMs (7 % of the FLOPs) go to the tensor cores only in f16 mode: with bf16's 8-bit
+  // mantissa on BOTH the edge-level and the recurrent cluster-level layers the hidden state drifts past
+  // the 2e-2 budget after a few frames, so bf16 mode keeps them in fp32 (measured, DESIGN.md section 2).
+  const bool tc = h->precision == CNS_PREC_F16;
+  const int tci = (h->precision == CNS_PREC_BF16) ? 0 : 1;
+  // whole-graph row tiles: the three backbone blocks as one kernel (backbone_fused.cu)
+  const bool fused = tc && dense_cur && dense_tar && b->max_clusters_per_graph > 0 && b->max_clusters_per_graph <= 128 &&
+                     B <= GRAPH_TILES_MAX && !h->no_fused_backbone;
   if (C <= PREP_SMALL_MAX && B <= PREP_SMALL_MAX && b->n_e01 <= (1 << 20) && ne_cur + ne_tar <= (1 << 20)) {
     // servo-loop sizes: one single-CTA launch instead of thirteen
     PrepSmallArgs pa{};
@@ -115,9 +123,11 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     pa.graph_ptr = f.graph_ptr; pa.clu_rowptr = f.clu_rowptr; pa.cur_rowptr = f.cur_rowptr; pa.cur_src = f.cur_src;
     pa.tar_rowptr = f.tar_rowptr; pa.tar_src = f.tar_src; pa.err = f.err;
     RUN(prep_small(pa, s));
+    if (fused) RUN(graph_tiles(b->num_clusters, B, f.graph_ptr, f.tile_graph, f.n_tiles, f.err, s));
   } else {
     RUN(sorted_rowptr(b->l0_to_l1_i, b->n_e01, C, f.clu_rowptr, f.err, s));
-    RUN(graph_ptr_from_counts(b->num_clusters, B, f.graph_ptr, f.gp_tmp, f.scan_scratch, s));
+    if (fused) { RUN(graph_tiles(b->num_clusters, B, f.graph_ptr, f.tile_graph, f.n_tiles, f.err, s)); }
+    else { RUN(graph_ptr_from_counts(b->num_clusters, B, f.graph_ptr, f.gp_tmp, f.scan_scratch, s)); }
     if (!dense_cur) RUN(csr_by_dst(b->l1_edge_cur, b->l1_edge_cur + cur_stride, b->n_e11_cur, C, f.cur_rowptr, f.cur_src, f.csr_ws, f.err, s));
     if (!dense_tar) RUN(csr_by_dst(b->l1_edge_tar, b->l1_edge_tar + tar_stride, b->n_e11_tar, C, f.tar_rowptr, f.tar_src, f.csr_ws, f.err, s));
   }
@@ -162,14 +172,10 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   ef.piece_e = (h->precision == CNS_PREC_FP32) ? ENC_PIECE_E : tc_piece_edges(b->n_e01, h); ef.clu_rowptr = f.clu_rowptr; ef.partial = f.partial;
   ef.clu_feat = f.clu_feat; ef.out_t = pk.out_t; ef.b_out = h->P(P_OUT_B); ef.cluster_mask = b->cluster_mask;
   ef.x_clu = f.x_clu;
-  // Cluster-level GEMMs (7 % of the FLOPs) go to the tensor cores only in f16 mode: with bf16's 8-bit
-  // mantissa on BOTH the edge-level and the recurrent cluster-level layers the hidden state drifts past
-  // the 2e-2 budget after a few frames, so bf16 mode keeps them in fp32 (measured, DESIGN.md section 2).
-  const bool tc = h->precision == CNS_PREC_F16;
-  const int tci = (h->precision == CNS_PREC_BF16) ? 0 : 1;
-  ef.cat_out = tc ? f.pq : nullptr;       // (C,256) scratch; pq is free until the first [P|Q] projection
+  ef.cat_out = (tc && !fused) ? f.pq : nullptr;       // (C,256) scratch; pq is free until the first [P|Q] projection
+  ef.fix_only = fused ? 1 : 0;
   RUN(enc_finish(ef, s));
-  if (tc) {
+  if (tc && !fused) {
     GemmTcArgs ga{};
     ga.m = C; ga.k1 = 2 * H; ga.k2 = 0; ga.n_out = H; ga.x1 = f.pq; ga.w_img = pk.tc_out[tci];
     ga.bias = h->P(P_OUT_B); ga.row_mask = b->cluster_mask; ga.relu = 1; ga.y = f.x_clu;
@@ -224,21 +230,19 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     return linear(la, s);
   };
 
-  // whole-graph row tiles: the three backbone blocks as one kernel (backbone_fused.cu)
-  const bool fused = tc && dense_cur && dense_tar && b->max_clusters_per_graph > 0 && b->max_clusters_per_graph <= 128 &&
-                     !h->no_fused_backbone;
   if (fused) {
     BackboneFusedArgs fa{};
     fa.n_clusters = C; fa.n_graphs = (int)B; fa.graph_ptr = f.graph_ptr; fa.tile_graph = f.tile_graph; fa.n_tiles = f.n_tiles;
-    fa.x_clu = f.x_clu; fa.hidden_in = hidden_in; fa.pos_clu = f.pos_clu; fa.mask = b->cluster_mask;
+    fa.clu_feat = f.clu_feat; fa.hidden_in = hidden_in; fa.pos_clu = f.pos_clu; fa.mask = b->cluster_mask;
+    fa.w_out = pk.tc_out[tci]; fa.out_b = h->P(P_OUT_B);
     fa.w_c0 = pk.tc_c0[tci]; fa.w_c0fc = pk.tc_c0_fc[tci]; fa.w_g = pk.tc_g[tci]; fa.w_k = pk.tc_k[tci];
     fa.w_c1 = pk.tc_c1[tci]; fa.w_c1fc = pk.tc_c1_fc[tci];
     fa.c0_b = pk.c0_b; fa.c0_wp = pk.c0_wp; fa.g_b = pk.g_b; fa.g_wp = pk.g_wp; fa.k_b = pk.k_b; fa.k_wp = pk.k_wp;
     fa.c1_b = pk.c1_b; fa.c1_wp = pk.c1_wp; fa.c0fc_b = h->P(P_C0_FC_B); fa.c1fc_b = h->P(P_C1_FC_B);
     fa.gn0_w = h->P(P_C0_BN_W); fa.gn0_b = h->P(P_C0_BN_B); fa.gn0_ms = h->P(P_C0_BN_MS);
     fa.gn1_w = h->P(P_C1_BN_W); fa.gn1_b = h->P(P_C1_BN_B); fa.gn1_ms = h->P(P_C1_BN_MS);
-    fa.hidden_out = hidden_out; fa.x2 = f.x2; fa.u_scratch = f.u;
-    RUN(backbone_fused(fa, f.tile_next, f.err, tci == 0, s));
+    fa.hidden_out = hidden_out; fa.x2 = f.x2;
+    RUN(backbone_fused(fa, tci == 0, s));
   } else {
   RUN(perconv(f.x_clu, pk.c0_wt, pk.c0_wp, pk.c0_b, P_C0_BN_W, P_C0_BN_B, P_C0_BN_MS, pk.c0_fc_t, P_C0_FC_B, f.x1, pk.tc_c0, pk.tc_c0_fc, f.conv0, f.gn0, f.stats0, f.arg0));
 

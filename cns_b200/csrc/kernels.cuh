@@ -18,6 +18,10 @@ int csr_by_dst(const int64_t* ej, const int64_t* ei, int64_t n_edges, int64_t n_
 int graph_ptr_from_counts(const int64_t* num_clusters, int64_t n_graphs, int* graph_ptr, int* tmp,
                           int* scratch, cudaStream_t s);
 
+constexpr int GRAPH_TILES_MAX = 4096;
+int graph_tiles(const int64_t* num_clusters, int64_t n_graphs, int* graph_ptr, int* tile_graph, int* n_tiles, int* err,
+                cudaStream_t s);
+
 constexpr int PREP_SMALL_MAX = 4096;
 struct PrepSmallArgs {
   int64_t n_clusters, n_graphs, n_e01, n_e11_cur, n_e11_tar;
@@ -62,6 +66,7 @@ struct EncFinishArgs {
   const float* out_t; const float* b_out; const uint8_t* cluster_mask;
   float* x_clu;      // (C,128)
   float* cat_out;    // optional (C,256): write [cur | tar - cur] and skip out_enc (done by gemm_tc)
+  int fix_only;      // only repair clu_feat (merge cut clusters, zero empty ones): out_enc runs in the fused backbone
 };
 int enc_finish(const EncFinishArgs& a, cudaStream_t s);
 
@@ -132,16 +137,17 @@ struct BackboneFusedArgs {
   int64_t n_clusters; int n_graphs;
   const int* graph_ptr;
   const int* tile_graph; const int* n_tiles;      // scratch: (B + 2,), (1,) filled by the tile packer
-  const float* x_clu; const float* hidden_in; const float* pos_clu; const uint8_t* mask;
+  const float* clu_feat;                          // (2, C, 128) encoder features: current side, target side
+  const float* hidden_in; const float* pos_clu; const uint8_t* mask;
+  const unsigned char* w_out; const float* out_b;
   const unsigned char* w_c0; const unsigned char* w_c0fc; const unsigned char* w_g; const unsigned char* w_k;
   const unsigned char* w_c1; const unsigned char* w_c1fc;      // gemm_tc weight images
   const float* c0_b; const float* c0_wp; const float* g_b; const float* g_wp; const float* k_b; const float* k_wp;
   const float* c1_b; const float* c1_wp; const float* c0fc_b; const float* c1fc_b;
   const float* gn0_w; const float* gn0_b; const float* gn0_ms; const float* gn1_w; const float* gn1_b; const float* gn1_ms;
   float* hidden_out; float* x2;
-  float* u_scratch;                               // (C,128) update gate, written and re-read by the same thread
 };
-int backbone_fused(const BackboneFusedArgs& a, int* next_scratch, int* err, bool bf16, cudaStream_t s);
+int backbone_fused(const BackboneFusedArgs& a, bool bf16, cudaStream_t s);
 
 struct GraphNormArgs {
   int64_t n_graphs; const int* graph_ptr; const float* x;

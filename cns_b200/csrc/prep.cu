@@ -207,6 +207,47 @@ __device__ void block_scan_inplace(int* v, int n, int* out /* n+1 */) {
   __syncthreads();
 }
 
+// graph_ptr (exclusive scan of num_clusters) and the whole-graph row tiles of the fused backbone in one
+// single-CTA launch: tile_graph[t] = first graph of tile t, greedily as many consecutive graphs as fit
+// into 128 rows.  n_graphs <= GRAPH_TILES_MAX.
+__global__ void __launch_bounds__(1024)
+graph_tiles_kernel(const int64_t* __restrict__ num_clusters, int n_graphs, int* __restrict__ graph_ptr,
+                   int* __restrict__ tile_graph, int* __restrict__ n_tiles, int* __restrict__ err) {
+  __shared__ int cnt[GRAPH_TILES_MAX];
+  __shared__ int gp[GRAPH_TILES_MAX + 1];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n_graphs; i += 1024) cnt[i] = (int)num_clusters[i];
+  __syncthreads();
+  block_scan_inplace(cnt, n_graphs, gp);
+  for (int i = tid; i <= n_graphs; i += 1024) graph_ptr[i] = gp[i];
+  // cnt[g] := first graph that does not fit into a tile starting at g (binary search on the prefix sums)
+  for (int g = tid; g < n_graphs; g += 1024) {
+    const int lim = gp[g] + 128;
+    if (gp[g + 1] > lim) atomicExch(err, 4);            // a graph with more than 128 clusters
+    int lo = g + 1, hi = n_graphs;                      // largest q in [g+1, B] with gp[q] <= lim
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (gp[mid] <= lim) lo = mid; else hi = mid - 1;
+    }
+    cnt[g] = lo;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int t = 0, g = 0;
+    while (g < n_graphs) { tile_graph[t++] = g; const int q = cnt[g]; g = q > g ? q : g + 1; }
+    tile_graph[t] = n_graphs;
+    *n_tiles = t;
+  }
+}
+
+int graph_tiles(const int64_t* num_clusters, int64_t n_graphs, int* graph_ptr, int* tile_graph, int* n_tiles, int* err,
+                cudaStream_t s) {
+  CNS_REQUIRE(n_graphs <= GRAPH_TILES_MAX, "graph_tiles: too many graphs");
+  graph_tiles_kernel<<<1, 1024, 0, s>>>(num_clusters, (int)n_graphs, graph_ptr, tile_graph, n_tiles, err);
+  CNS_LAUNCH_CHECK();
+  return CNS_OK;
+}
+
 __global__ void __launch_bounds__(1024)
 prep_small_kernel(PrepSmallArgs p) {
   __shared__ int deg[PREP_SMALL_MAX + 1];
