@@ -258,11 +258,11 @@ enc_edge_fp32_kernel(EncEdgeArgs p) {
 // pos_clu = pos_tar[centre], cluster -> graph id.   (graph_vs.py:207-208,312-313)
 // ---------------------------------------------------------------------------------------------
 constexpr int CLU_ROWS = 8;
-constexpr int PRE_ROWS = 8;      // clusters per CTA of the pre-pass (32 rows per CTA measured 2x slower: too few CTAs in flight)
+constexpr int PRE_ROWS = 16;     // clusters per CTA of the pre-pass
 
 __global__ void __launch_bounds__(128)
 enc_cluster_pre_kernel(EncPreArgs p) {
-  __shared__ float xs[PRE_ROWS][H];
+  __shared__ __align__(16) float xs[PRE_ROWS][H];
   const int o = threadIdx.x;
   const int64_t c0 = (int64_t)blockIdx.x * PRE_ROWS;
   float w0 = p.w_in[o * 2], w1 = p.w_in[o * 2 + 1], b = p.b_in[o];
@@ -286,11 +286,17 @@ enc_cluster_pre_kernel(EncPreArgs p) {
   const float ab = p.a_bias ? p.a_bias[o] : 0.f;
 #pragma unroll
   for (int r = 0; r < PRE_ROWS; ++r) acc[r] = ab;
-#pragma unroll 4
-  for (int k = 0; k < H; ++k) {
-    float w = p.lin_dst_t[k * H + o];
+  // the row values are the same for every thread: one 16-byte broadcast load feeds four FMAs (a scalar
+  // load per FMA makes the kernel shared-memory bound)
+#pragma unroll 2
+  for (int k = 0; k < H; k += 4) {
+    const float wa = p.lin_dst_t[k * H + o], wb = p.lin_dst_t[(k + 1) * H + o];
+    const float wc = p.lin_dst_t[(k + 2) * H + o], wd = p.lin_dst_t[(k + 3) * H + o];
 #pragma unroll
-    for (int r = 0; r < PRE_ROWS; ++r) acc[r] = fmaf(xs[r][k], w, acc[r]);
+    for (int r = 0; r < PRE_ROWS; ++r) {
+      const float4 x = *reinterpret_cast<const float4*>(&xs[r][k]);
+      acc[r] = fmaf(x.w, wd, fmaf(x.z, wc, fmaf(x.y, wb, fmaf(x.x, wa, acc[r]))));
+    }
   }
 #pragma unroll
   for (int r = 0; r < PRE_ROWS; ++r)

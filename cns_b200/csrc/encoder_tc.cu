@@ -41,6 +41,7 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ enc_chain, unsi
   int w = idx / 16384, rem = idx % 16384;
   int k = rem / 128, o = rem % 128;               // enc_chain[w][k][o] = W_w[o][k]
   float v = enc_chain[idx];
+  if (w == 4) v *= 1.4426950408889634f;           // attn_nn.1 emits logits in log2 units (softmax with ex2)
   unsigned short bits;
   if (BF16) bits = __bfloat16_as_ushort(__float2bfloat16_rn(v));
   else bits = __half_as_ushort(__float2half_rn(v));
@@ -118,33 +119,37 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     const uint32_t done = smem_u32(&bars[1 + s]);
     const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((s * 2 + 0) * TN);
     const uint32_t t1 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((s * 2 + 1) * TN);
-    const float b_p1 = p.b_p1[t], b_a1 = p.b_a1[t];
+    const float b_p1 = p.b_p1[t];
     uint32_t done_parity = 0;
-    constexpr float LOG2E = 1.4426950408889634f;
+    constexpr float LN2 = 0.6931471805599453f;
 
     // One elected thread of the slot's first warp issues the slot's tensor-core work (tcgen05.mma is a
     // single-thread instruction): after the slot barrier every operand byte written by the 128 threads is
     // visible to the async proxy, so no dedicated MMA warp / "ready" mbarrier is needed.
     // One K=128 product = 8 MMAs of K = 16.
-    auto gemm_kmajor = [&](uint32_t d, int w, uint32_t b, uint32_t acc_first) {
-      const uint32_t a = w_base + (uint32_t)w * TC_W_BYTES;
+    // Descriptors differ only in their start-address field ((addr >> 4) in the low word; shared memory is
+    // < 256 KB, so adding a 16-byte-unit offset never carries out of the field): the high words and the
+    // low-word bases are loop invariants, one uniform add per operand per MMA.
+    const uint64_t hi_k = sw128_desc(0) & 0xffffffff00000000ull, hi_mn = mn_major_desc(0, U_ROW) & 0xffffffff00000000ull;
+    const uint32_t lo_mn = (uint32_t)mn_major_desc(0, U_ROW);          // LBO placeholder bit
+    const uint32_t w_lo = w_base >> 4, b0_lo = smem_u32(buf0) >> 4, b1_lo = smem_u32(buf1) >> 4;
+    auto gemm_kmajor = [&](uint32_t d, int w, uint32_t b_lo, uint32_t acc_first) {
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          uint64_t ad = sw128_desc(a + kc * (128 * 128) + ks * 32);
-          uint64_t bd = sw128_desc(b + kc * (TN * 128) + ks * 32);
+          const uint64_t ad = hi_k | (uint64_t)(w_lo + (uint32_t)((w * TC_W_BYTES + kc * (128 * 128) + ks * 32) >> 4));
+          const uint64_t bd = hi_k | (uint64_t)(b_lo + (uint32_t)((kc * (TN * 128) + ks * 32) >> 4));
           umma_f16(d, ad, bd, idesc, (kc | ks) ? 1u : acc_first);
         }
     };
-    auto gemm_mnmajor = [&](uint32_t d, int w, uint32_t b) {     // B tile stored [k][edge]
-      const uint32_t a = w_base + (uint32_t)w * TC_W_BYTES;
+    auto gemm_mnmajor = [&](uint32_t d, int w, uint32_t b_lo) {     // B tile stored [k][edge]
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          uint64_t ad = sw128_desc(a + kc * (128 * 128) + ks * 32);
-          uint64_t bd = mn_major_desc(b + (kc * 4 + ks) * (16 * U_ROW), U_ROW);   // 16 k-rows per MMA
+          const uint64_t ad = hi_k | (uint64_t)(w_lo + (uint32_t)((w * TC_W_BYTES + kc * (128 * 128) + ks * 32) >> 4));
+          const uint64_t bd = hi_mn | (uint64_t)(lo_mn + b_lo + (uint32_t)(((kc * 4 + ks) * (16 * U_ROW)) >> 4));   // 16 k-rows per MMA
           umma_f16(d, ad, bd, idesc_mn, (kc | ks) ? 1u : 0u);
         }
     };
@@ -155,7 +160,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
       if (wq == 0) {
         if (elect_one()) {
           tc_fence_after();
-          const uint32_t b0 = smem_u32(buf0), b1 = smem_u32(buf1);
+          const uint32_t b0 = b0_lo, b1 = b1_lo;
           const uint32_t d0 = tmem_base + (uint32_t)((s * 2 + 0) * TN);
           const uint32_t d1 = tmem_base + (uint32_t)((s * 2 + 1) * TN);
           if (round == 0) {
@@ -238,7 +243,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         out_side[(size_t)run_seg * H + t] = fmaxf(__fdividef(ab, run_s + 1e-16f), 0.f);
       } else {
         float* slot = part_side + ((size_t)run_seg + chunk) * 3 * H;
-        slot[t] = run_m + b_a1; slot[H + t] = run_s; slot[2 * H + t] = ab;
+        slot[t] = run_m * LN2; slot[H + t] = run_s; slot[2 * H + t] = ab;     // natural-log units, like the fp32 kernel
       }
     };
     // u tile, MN-major: row = channel t (U_ROW bytes of edges), 16-byte chunk index XOR-swizzled by the row
@@ -369,9 +374,10 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
       mbar_wait(done, done_parity); done_parity ^= 1;
       tc_fence_after();
       {
+        // logits arrive in log2 units (log2(e) is folded into the attn_nn.1 weight image): one ex2, no multiply
         auto update = [&](float l, float v) {
           const float d = l - run_m;
-          const float ex = ex2_approx(-fabsf(d) * LOG2E);
+          const float ex = ex2_approx(-fabsf(d));
           const bool up = d > 0.f;
           const float sc = up ? ex : 1.f, pr = up ? 1.f : ex;
           run_s = fmaf(run_s, sc, pr);
