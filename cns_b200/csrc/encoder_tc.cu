@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(128 * (128 / TN), 1)
 enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ TcSmallW sw) {
   constexpr int SLOTS = 128 / TN;
   constexpr int ACT_TILE = TN * 256;                 // one [TN x 128] 16-bit operand tile
-  constexpr int TMEM_COLS = 256;                     // SLOTS * 2 regions * TN columns
+  constexpr int TMEM_COLS = 512;                     // [0,256): SLOTS * 2 regions * TN accumulator columns; [256,448): weights 0..2
+  constexpr int TMEM_W = 3;                          // weight matrices kept in tensor memory (A operand without a smem fetch per MMA)
+  constexpr int TMEM_W_COL0 = 256;
   constexpr int U_ROW = TN * 2;                      // bytes per channel row of the MN-major u tile
   constexpr int NPRE = 4;                            // a' rows prefetched per tile (first NPRE segment starts)
   extern __shared__ unsigned char smem_raw[];
@@ -100,6 +102,30 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
+  // The first TMEM_W weight matrices move on into tensor memory: with N = 32 an MMA whose A operand sits in
+  // shared memory spends most of its time fetching the 4 KB A slice (measured ~80 cycles per instruction
+  // against 16 of math).  Row o of a matrix = TMEM lane o, k and k+1 share a 32-bit column.
+  if (warp < 4) {
+    mbar_wait(smem_u32(&bars[0]), 0);
+    const int o = tid;                               // 0..127 == TMEM lane
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + TMEM_W_COL0;
+#pragma unroll 1
+    for (int w = 0; w < TMEM_W; ++w) {
+#pragma unroll 1
+      for (int g = 0; g < 8; ++g) {                  // 16 k per trip
+        const uint4 lo = *reinterpret_cast<const uint4*>(w_s + w * TC_W_BYTES + sw128_off(128, o, g * 16));
+        const uint4 hi = *reinterpret_cast<const uint4*>(w_s + w * TC_W_BYTES + sw128_off(128, o, g * 16 + 8));
+        float v[8];
+        uint32_t* u = reinterpret_cast<uint32_t*>(v);
+        u[0] = lo.x; u[1] = lo.y; u[2] = lo.z; u[3] = lo.w; u[4] = hi.x; u[5] = hi.y; u[6] = hi.z; u[7] = hi.w;
+        tmem_st8(t_row + (uint32_t)(w * 64 + g * 8), v);
+      }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   // instruction descriptor: D=f32 (bit 4), A/B format at bits 7/10 (0 f16, 1 bf16), A K-major (bit 15 = 0),
   // B K-major or MN-major (bit 16), N>>3 at bit 17, M>>4 at bit 24
@@ -138,9 +164,13 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
       for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t ad = hi_k | (uint64_t)(w_lo + (uint32_t)((w * TC_W_BYTES + kc * (128 * 128) + ks * 32) >> 4));
           const uint64_t bd = hi_k | (uint64_t)(b_lo + (uint32_t)((kc * (TN * 128) + ks * 32) >> 4));
-          umma_f16(d, ad, bd, idesc, (kc | ks) ? 1u : acc_first);
+          if (w < TMEM_W) {
+            umma_f16_ts(d, tmem_base + (uint32_t)(TMEM_W_COL0 + w * 64 + (kc * 4 + ks) * 8), bd, idesc, (kc | ks) ? 1u : acc_first);
+          } else {
+            const uint64_t ad = hi_k | (uint64_t)(w_lo + (uint32_t)((w * TC_W_BYTES + kc * (128 * 128) + ks * 32) >> 4));
+            umma_f16(d, ad, bd, idesc, (kc | ks) ? 1u : acc_first);
+          }
         }
     };
     auto gemm_mnmajor = [&](uint32_t d, int w, uint32_t b_lo) {     // B tile stored [k][edge]
