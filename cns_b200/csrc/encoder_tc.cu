@@ -52,6 +52,12 @@ struct TcSmallW {          // passed by value in the kernel parameter space (con
   float4 w[128][2];        // per channel k: {in_enc.w[k][0], in_enc.w[k][1], in_enc.b[k], pos_nn.0.b[k]}, pos_nn.0.w[k][0..3]
 };
 
+// the same first-layer weights as fp16 pairs (channel k in the low half, k+1 in the high half) for the packed
+// HFMA2 producer of the f16 mode: per channel pair {in_enc.w[.][0], in_enc.w[.][1], in_enc.b, pos_nn.0.b}, pos_nn.0.w[.][0..3]
+struct TcSmallH {
+  uint4 w[64][2];
+};
+
 struct TcArgs {
   EncEdgeArgs e;
   const unsigned char* w_img;   // 5 swizzled 16-bit weight tiles
@@ -62,7 +68,7 @@ struct TcArgs {
 // =================================================================================================
 template <int TN, bool BF16>
 __global__ void __launch_bounds__(128 * (128 / TN), 1)
-enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ TcSmallW sw) {
+enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ TcSmallW sw, const __grid_constant__ TcSmallH sh) {
   constexpr int SLOTS = 128 / TN;
   constexpr int ACT_TILE = TN * 256;                 // one [TN x 128] 16-bit operand tile
   constexpr int TMEM_COLS = 512;                     // [0,256): SLOTS * 2 regions * TN accumulator columns; [256,448): weights 0..2
@@ -319,6 +325,46 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         const float d0 = live ? c_pc.x - c_ps.x : 0.f, d1 = live ? c_pc.y - c_ps.y : 0.f;   // pos_i - pos_j
         const float d2 = live ? c_pc.x - c_pt.x : 0.f, d3 = live ? c_pc.y - c_pt.y : 0.f;
         // kp and gq are warp-uniform: the first-layer weights are uniform constant-bank loads
+        if (!BF16) {
+          // f16 mode: packed half2 math, two channels per instruction, results land directly in operand format.
+          // (inputs and weights rounded to fp16, fp16 accumulation of 3 / 5 terms: the result is rounded to
+          // fp16 for the tensor core anyway)
+          // every input is split into an fp16 head and an fp16 tail (v = hi + lo to ~22 bits): the geometry lives
+          // in small coordinate differences, which a single fp16 would quantise to 2^-11
+          auto split = [](float v, __half2& hi, __half2& lo) {
+            hi = __float2half2_rn(v);
+            lo = __float2half2_rn(v - __low2float(hi));
+          };
+          __half2 h_f0, l_f0, h_f1, l_f1, h_d0, l_d0, h_d1, l_d1, h_d2, l_d2, h_d3, l_d3;
+          split(f0, h_f0, l_f0); split(f1, h_f1, l_f1);
+          split(d0, h_d0, l_d0); split(d1, h_d1, l_d1); split(d2, h_d2, l_d2); split(d3, h_d3, l_d3);
+          const __half2 zero = __float2half2_rn(0.f);
+#pragma unroll 1
+          for (int gq = 0; gq < TN / 8; ++gq) {
+            const int k0 = kp * TN + gq * 8;
+            uint32_t xo[4], ho[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 wa = sh.w[(k0 >> 1) + q][0], wb = sh.w[(k0 >> 1) + q][1];
+              const __half2 w_i0 = *reinterpret_cast<const __half2*>(&wa.x), w_i1 = *reinterpret_cast<const __half2*>(&wa.y);
+              const __half2 b_i = *reinterpret_cast<const __half2*>(&wa.z), b_p = *reinterpret_cast<const __half2*>(&wa.w);
+              const __half2 w_p0 = *reinterpret_cast<const __half2*>(&wb.x), w_p1 = *reinterpret_cast<const __half2*>(&wb.y);
+              const __half2 w_p2 = *reinterpret_cast<const __half2*>(&wb.z), w_p3 = *reinterpret_cast<const __half2*>(&wb.w);
+              // tails first (small terms), heads last
+              __half2 x2 = __hfma2(w_i1, l_f1, __hmul2(w_i0, l_f0));
+              x2 = __hfma2(w_i1, h_f1, __hfma2(w_i0, h_f0, __hadd2(x2, b_i)));
+              __half2 p2 = __hfma2(w_p3, l_d3, __hfma2(w_p2, l_d2, __hfma2(w_p1, l_d1, __hmul2(w_p0, l_d0))));
+              p2 = __hfma2(w_p3, h_d3, __hfma2(w_p2, h_d2, __hfma2(w_p1, h_d1, __hfma2(w_p0, h_d0, __hadd2(p2, b_p)))));
+              x2 = __hmax2(x2, zero);
+              p2 = __hmax2(p2, zero);
+              xo[q] = *reinterpret_cast<const uint32_t*>(&x2);
+              ho[q] = *reinterpret_cast<const uint32_t*>(&p2);
+            }
+            const uint32_t off = sw128_off(TN, pe, k0);
+            *reinterpret_cast<uint4*>(buf0 + off) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
+            *reinterpret_cast<uint4*>(buf1 + off) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+          }
+        } else
 #pragma unroll 1
         for (int gq = 0; gq < TN / 8; ++gq) {
           const int k0 = kp * TN + gq * 8;
@@ -468,7 +514,19 @@ static int launch_tc(const EncEdgeArgs& a, const unsigned char* w_img, const cns
   tc_chunking(a.n_e01, TN, h->sm_count, &grid, &tpc);
   ta.tiles_per_chunk = tpc;
   const int slots = 128 / TN;
-  kern<<<grid, 128 * slots, TC_SMEM_BYTES, s>>>(ta, *reinterpret_cast<const TcSmallW*>(h->tc_small_host));
+  // fp16 pair table of the first-layer weights (f16 mode), derived from the fp32 table on every launch: 2 KB
+  const TcSmallW* sw = reinterpret_cast<const TcSmallW*>(h->tc_small_host);
+  TcSmallH sh;
+  for (int q = 0; q < 64; ++q) {
+    const float4 a0 = sw->w[2 * q][0], a1 = sw->w[2 * q + 1][0], b0 = sw->w[2 * q][1], b1 = sw->w[2 * q + 1][1];
+    auto pk = [](float lo, float hi) {
+      const __half2 v = __floats2half2_rn(lo, hi);
+      return *reinterpret_cast<const uint32_t*>(&v);
+    };
+    sh.w[q][0] = make_uint4(pk(a0.x, a1.x), pk(a0.y, a1.y), pk(a0.z, a1.z), pk(a0.w, a1.w));
+    sh.w[q][1] = make_uint4(pk(b0.x, b1.x), pk(b0.y, b1.y), pk(b0.z, b1.z), pk(b0.w, b1.w));
+  }
+  kern<<<grid, 128 * slots, TC_SMEM_BYTES, s>>>(ta, *sw, sh);
   CNS_LAUNCH_CHECK();
   return CNS_OK;
 }
