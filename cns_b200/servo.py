@@ -49,34 +49,56 @@ class BatchedServo(object):
         self.counts = torch.zeros(2, dtype=torch.int64, device=self.dev)
         self.mask_ws = torch.empty(self.lib.cns_graph_mask_workspace_bytes(self.N, self.Cn, self.B), dtype=torch.uint8,
                                    device=self.dev)
-        self.xy_dev = torch.empty(self.N, 2, dtype=torch.float32, device=self.dev)
-        self.vis_dev = torch.empty(self.N, dtype=torch.uint8, device=self.dev)
+        # frames in flight (submit / result): inputs and outputs are double-buffered, everything in between is
+        # ordered by the compute stream
+        self.depth = 2
+        self.xy_dev = [torch.empty(self.N, 2, dtype=torch.float32, device=self.dev) for _ in range(self.depth)]
+        self.vis_dev = [torch.empty(self.N, dtype=torch.uint8, device=self.dev) for _ in range(self.depth)]
+        self.vel_host = [torch.empty(self.B, 6).pin_memory() for _ in range(self.depth)]
+        self.copied = [torch.cuda.Event() for _ in range(self.depth)]
+        self.done = [None] * self.depth
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.ticket = 0
         self.hidden = [torch.zeros(self.Cn, 128, device=self.dev), torch.zeros(self.Cn, 128, device=self.dev)]
         self.cur, self.have_hidden = 0, False
         self.out = torch.empty(self.B * 13, dtype=torch.float32, device=self.dev)
-        self.vel_host = torch.empty(self.B, 6).pin_memory()
         self.h2d_bytes = self.N * 2 * 4 + self.N
         self.d2h_bytes = self.B * 6 * 4
 
     def reset(self):
         self.have_hidden = False
 
-    def step(self, cur_xy: torch.Tensor, visible: torch.Tensor, wait: bool = True) -> torch.Tensor:
-        """cur_xy (sum N, 2) float32 and visible (sum N,) uint8/bool HOST tensors (pinned for full speed), in
-        the scenes' keypoint order.  Returns the (B, 6) velocities in pinned host memory.
+    def step(self, cur_xy: torch.Tensor, visible: torch.Tensor) -> torch.Tensor:
+        """One closed-loop frame: `result(submit(cur_xy, visible))`."""
+        return self.result(self.submit(cur_xy, visible))
+
+    def submit(self, cur_xy: torch.Tensor, visible: torch.Tensor) -> int:
+        """Enqueue one frame; returns a ticket for `result`.  cur_xy (sum N, 2) float32 and visible (sum N,)
+        uint8/bool are HOST tensors (pinned for full speed) in the scenes' keypoint order.  Up to `depth`
+        frames may be in flight: the host->device copy of frame t+1 (copy stream) overlaps the kernels of
+        frame t; kernels, hidden state and the device->host copy of the velocities are ordered by the current
+        stream.
 
         The current-side cluster graph is never materialised: it is the complete digraph over the clusters
         that keep a visible keypoint (graph_gen.py:199-228), which the forward handles from cluster_mask
         alone (CNS_BATCH_L1_CUR_COMPLETE), and the number of keypoint->cluster edges is the number of visible
         keypoints - so nothing is read back from the device before the velocities."""
         lib, L, dev = self.lib, _lib, self.dev
-        stream = L.stream_ptr(dev)
+        k = self.ticket % self.depth
+        if self.done[k] is not None:
+            self.done[k].synchronize()                 # the frame that used this slot has delivered its result
+        cur = torch.cuda.current_stream(dev)
+        stream = cur.cuda_stream
         vis = visible.view(torch.uint8) if visible.dtype == torch.bool else visible
         n01 = int(torch.count_nonzero(vis))
-        self.xy_dev.copy_(cur_xy, non_blocking=True)
-        self.vis_dev.copy_(vis, non_blocking=True)
+        with torch.cuda.stream(self.copy_stream):
+            self.xy_dev[k].copy_(cur_xy, non_blocking=True)
+            self.vis_dev[k].copy_(vis, non_blocking=True)
+            self.copied[k].record(self.copy_stream)
+        cur.wait_event(self.copied[k])
+        xy, visd = self.xy_dev[k], self.vis_dev[k]
         L.check(lib.cns_graph_mask(L.ptr(self.belong), L.ptr(self.member_order), L.ptr(self.cluster_size),
-                                   L.ptr(self.cluster_graph_ptr), L.ptr(self.vis_dev), self.N, self.Cn, self.B,
+                                   L.ptr(self.cluster_graph_ptr), L.ptr(visd), self.N, self.Cn, self.B,
                                    L.ptr(self.e01_j), L.ptr(self.e01_i), None, 0,
                                    L.ptr(self.cmask), L.ptr(self.counts), L.ptr(self.mask_ws), self.mask_ws.numel(), stream),
                 "cns_graph_mask")
@@ -84,7 +106,7 @@ class BatchedServo(object):
         b.n_nodes, b.n_clusters, b.n_graphs = self.N, self.Cn, self.B
         b.n_e01, b.n_e11_cur, b.n_e11_tar = n01, 0, 0
         p = lambda t: t.data_ptr()
-        b.x_cur, b.pos_cur, b.x_tar, b.pos_tar = p(self.xy_dev), p(self.xy_dev), p(self.x_tar), p(self.x_tar)
+        b.x_cur, b.pos_cur, b.x_tar, b.pos_tar = p(xy), p(xy), p(self.x_tar), p(self.x_tar)
         b.l0_to_l1_j, b.l0_to_l1_i = p(self.e01_j), p(self.e01_i)
         b.l1_edge_cur, b.l1_edge_tar = None, None               # both cluster graphs are implied (complete)
         b.l1_cur_stride, b.l1_tar_stride = 0, 0
@@ -102,7 +124,15 @@ class BatchedServo(object):
                                         L.ptr(ws), ws.numel(), None, 0, stream), "cns_graphvs_forward")
         self.cur ^= 1
         self.have_hidden = True
-        self.vel_host.copy_(vel.view(B, 6), non_blocking=True)
-        if wait:
-            torch.cuda.current_stream(dev).synchronize()
-        return self.vel_host
+        self.vel_host[k].copy_(vel.view(B, 6), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.done[k] = ev
+        self.ticket += 1
+        return self.ticket - 1
+
+    def result(self, ticket: int) -> torch.Tensor:
+        """Velocities (B, 6) of a submitted frame, in pinned host memory (valid until `depth` more submits)."""
+        k = ticket % self.depth
+        self.done[k].synchronize()
+        return self.vel_host[k]
