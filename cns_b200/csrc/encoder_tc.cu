@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(128 * (128 / TN), 1)
 enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ TcSmallW sw, const __grid_constant__ TcSmallH sh) {
   constexpr int SLOTS = 128 / TN;
   constexpr int ACT_TILE = TN * 256;                 // one [TN x 128] 16-bit operand tile
-  constexpr int TMEM_COLS = 512;                     // [0,256): SLOTS * 2 regions * TN accumulator columns; [256,448): weights 0..2
-  constexpr int TMEM_W = 3;                          // weight matrices kept in tensor memory (A operand without a smem fetch per MMA)
+  constexpr int TMEM_COLS = 512;                     // [0,256): SLOTS * 2 regions * TN accumulator columns; [256,512): weights 0..3
+  constexpr int TMEM_W = 4;                          // weight matrices kept in tensor memory (A operand without a smem fetch per MMA)
   constexpr int TMEM_W_COL0 = 256;
   constexpr int U_ROW = TN * 2;                      // bytes per channel row of the MN-major u tile
   constexpr int NPRE = 4;                            // a' rows prefetched per tile (first NPRE segment starts)
