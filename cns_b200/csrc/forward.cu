@@ -63,6 +63,19 @@ static void carve(Arena& ar, const cns_batch* b, FwdBuffers& f, const SaveBuffer
   }
 }
 
+}  // namespace cns
+
+// target-side results kept across frames (cns_target_cache_create)
+struct cns_target_cache {
+  int device; int precision; long long weights_version;
+  int64_t n_clusters, n_graphs;
+  int has_tiles;
+  float* a_dst; float* pos_clu; int* clu_graph; int* graph_ptr; int* tile_graph; int* n_tiles;
+  void* base;
+};
+
+namespace cns {
+
 static int validate(const cns_batch* b) {
   CNS_REQUIRE(b != nullptr, "batch is NULL");
   CNS_REQUIRE(b->n_nodes >= 0 && b->n_clusters >= 0 && b->n_graphs >= 0 && b->n_e01 >= 0 &&
@@ -91,6 +104,12 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   }
   carve(ar, b, f, sv);
   const int64_t C = b->n_clusters, B = b->n_graphs;
+  const cns_target_cache* tcache = sv ? nullptr : b->target_cache;
+  if (tcache) {
+    CNS_REQUIRE(tcache->device == h->device && tcache->precision == h->precision && tcache->weights_version == h->weights_version &&
+                tcache->n_clusters == C && tcache->n_graphs == B, "stale or foreign cns_target_cache");
+    f.a_dst = tcache->a_dst; f.pos_clu = tcache->pos_clu; f.clu_graph = tcache->clu_graph;
+  }
   const Packed& pk = h->pk;
   int rc;
 #define RUN(expr) if ((rc = (expr)) != CNS_OK) return rc;
@@ -123,10 +142,13 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     pa.graph_ptr = f.graph_ptr; pa.clu_rowptr = f.clu_rowptr; pa.cur_rowptr = f.cur_rowptr; pa.cur_src = f.cur_src;
     pa.tar_rowptr = f.tar_rowptr; pa.tar_src = f.tar_src; pa.err = f.err;
     RUN(prep_small(pa, s));
-    if (fused) RUN(graph_tiles(b->num_clusters, B, f.graph_ptr, f.tile_graph, f.n_tiles, f.err, s));
+    if (fused && tcache && tcache->has_tiles) { f.tile_graph = tcache->tile_graph; f.n_tiles = tcache->n_tiles; }
+    else if (fused) RUN(graph_tiles(b->num_clusters, B, f.graph_ptr, f.tile_graph, f.n_tiles, f.err, s));
   } else {
     RUN(sorted_rowptr(b->l0_to_l1_i, b->n_e01, C, f.clu_rowptr, f.err, s));
-    if (fused) { RUN(graph_tiles(b->num_clusters, B, f.graph_ptr, f.tile_graph, f.n_tiles, f.err, s)); }
+    if (tcache && (!fused || tcache->has_tiles)) {
+      f.graph_ptr = tcache->graph_ptr; f.tile_graph = tcache->tile_graph; f.n_tiles = tcache->n_tiles;
+    } else if (fused) { RUN(graph_tiles(b->num_clusters, B, f.graph_ptr, f.tile_graph, f.n_tiles, f.err, s)); }
     else { RUN(graph_ptr_from_counts(b->num_clusters, B, f.graph_ptr, f.gp_tmp, f.scan_scratch, s)); }
     if (!dense_cur) RUN(csr_by_dst(b->l1_edge_cur, b->l1_edge_cur + cur_stride, b->n_e11_cur, C, f.cur_rowptr, f.cur_src, f.csr_ws, f.err, s));
     if (!dense_tar) RUN(csr_by_dst(b->l1_edge_tar, b->l1_edge_tar + tar_stride, b->n_e11_tar, C, f.tar_rowptr, f.tar_src, f.csr_ws, f.err, s));
@@ -148,7 +170,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   pre.node_graph = b->node_graph; pre.w_in = h->P(P_IN_W); pre.b_in = h->P(P_IN_B); pre.lin_dst_t = pk.lin_dst_t;
   if (h->precision != CNS_PREC_FP32) { pre.lin_dst_t = pk.tc_lin_dst_t; pre.a_bias = pk.tc_adst_bias; }   // a_dst := A0 (a_dst + b_pos1) + b_attn0
   pre.a_dst = f.a_dst; pre.pos_clu = f.pos_clu; pre.clu_graph = f.clu_graph;
-  RUN(enc_cluster_pre(pre, s));
+  if (!tcache) RUN(enc_cluster_pre(pre, s));
 
   EncEdgeArgs ee{};
   ee.n_e01 = b->n_e01; ee.n_clusters = C; ee.n_slots = f.n_slots;
@@ -331,6 +353,55 @@ int cns_graphvs_forward(cns_handle* h, const cns_batch* b, const float* hidden_i
   }
   CNS_CUDA_CHECK(cudaSetDevice(h->device));
   return forward_impl(h, b, hidden_in, vel_si_vec, vel_si_norm, hidden_out, vel, workspace, save, (cudaStream_t)stream);
+}
+
+int cns_target_cache_create(cns_handle* h, const cns_batch* b, void* stream, cns_target_cache** out) {
+  CNS_REQUIRE(h != nullptr && b != nullptr && out != nullptr, "NULL argument");
+  CNS_REQUIRE(h->weights_loaded, "weights not loaded (cns_load_weights)");
+  CNS_REQUIRE(b->n_clusters > 0 && b->n_graphs > 0 && b->x_tar && b->pos_tar && b->cluster_centers && b->num_clusters,
+              "cns_target_cache_create: target tensors missing");
+  CNS_CUDA_CHECK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t C = b->n_clusters, B = b->n_graphs;
+  cns_target_cache* c = new cns_target_cache();
+  c->device = h->device; c->precision = h->precision; c->weights_version = h->weights_version;
+  c->n_clusters = C; c->n_graphs = B;
+  int* tmp = nullptr; int* scratch = nullptr; int* err = nullptr;
+  auto lay = [&](Arena& a) {
+    c->a_dst = a.take<float>(C * H); c->pos_clu = a.take<float>(C * 2 + 2); c->clu_graph = a.take<int>(C + 1);
+    c->graph_ptr = a.take<int>(B + 1); c->tile_graph = a.take<int>(B + 2); c->n_tiles = a.take<int>(4);
+    tmp = a.take<int>(B + 1); scratch = (int*)a.take<char>(scan_scratch_bytes(B + 1)); err = a.take<int>(4);
+  };
+  Arena count(nullptr);
+  lay(count);
+  if (cudaMalloc(&c->base, count.off + 256) != cudaSuccess) { delete c; set_error("cns_target_cache_create: out of memory"); return CNS_ERR_CUDA; }
+  Arena real(c->base);
+  lay(real);
+  int rc = CNS_OK;
+  do {
+    if (cudaMemsetAsync(err, 0, 4 * sizeof(int), s) != cudaSuccess) { rc = CNS_ERR_CUDA; break; }
+    c->has_tiles = B <= GRAPH_TILES_MAX && b->max_clusters_per_graph > 0 && b->max_clusters_per_graph <= 128;
+    if (c->has_tiles) rc = graph_tiles(b->num_clusters, B, c->graph_ptr, c->tile_graph, c->n_tiles, err, s);
+    else rc = graph_ptr_from_counts(b->num_clusters, B, c->graph_ptr, tmp, scratch, s);
+    if (rc != CNS_OK) break;
+    EncPreArgs pre{};
+    pre.n_clusters = C; pre.x_tar = b->x_tar; pre.pos_tar = b->pos_tar; pre.centers = b->cluster_centers;
+    pre.node_graph = b->node_graph; pre.w_in = h->P(P_IN_W); pre.b_in = h->P(P_IN_B); pre.lin_dst_t = h->pk.lin_dst_t;
+    if (h->precision != CNS_PREC_FP32) { pre.lin_dst_t = h->pk.tc_lin_dst_t; pre.a_bias = h->pk.tc_adst_bias; }
+    pre.a_dst = c->a_dst; pre.pos_clu = c->pos_clu; pre.clu_graph = c->clu_graph;
+    rc = enc_cluster_pre(pre, s);
+  } while (false);
+  if (rc != CNS_OK) { cudaFree(c->base); delete c; return rc; }
+  *out = c;
+  return CNS_OK;
+}
+
+int cns_target_cache_destroy(cns_target_cache* c) {
+  if (!c) return CNS_OK;
+  cudaSetDevice(c->device);
+  cudaFree(c->base);
+  delete c;
+  return CNS_OK;
 }
 
 // Error word written by the index-preparation kernels (0 = fine).  Synchronises `stream`.

@@ -59,6 +59,7 @@ class BatchedServo(object):
         self.done = [None] * self.depth
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.ticket = 0
+        self.tcache, self.tcache_handle = None, None       # cns_target_cache: target-side results kept across frames
         self.hidden = [torch.zeros(self.Cn, 128, device=self.dev), torch.zeros(self.Cn, 128, device=self.dev)]
         self.cur, self.have_hidden = 0, False
         self.out = torch.empty(self.B * 13, dtype=torch.float32, device=self.dev)
@@ -67,6 +68,37 @@ class BatchedServo(object):
 
     def reset(self):
         self.have_hidden = False
+
+    def _target_cache(self, h):
+        """Everything the forward derives from the target side alone (per-cluster attention term, cluster
+        positions, graph pointers, backbone tiles) is computed once per target, like the reference's Midend
+        builds its GraphGenerator once per target image."""
+        if self.tcache is not None and self.tcache_handle is h:
+            return self.tcache
+        self.drop_target_cache()
+        L = _lib
+        b = L.cns_batch()
+        b.n_nodes, b.n_clusters, b.n_graphs = self.N, self.Cn, self.B
+        b.x_tar, b.pos_tar = self.x_tar.data_ptr(), self.x_tar.data_ptr()
+        b.cluster_centers, b.num_clusters = self.centers.data_ptr(), self.num_clusters.data_ptr()
+        b.max_clusters_per_graph = self.max_clusters
+        out = C.c_void_p()
+        L.check(self.lib.cns_target_cache_create(h.raw, C.byref(b), L.stream_ptr(self.dev), C.byref(out)),
+                "cns_target_cache_create")
+        self.tcache, self.tcache_handle = out, h
+        return out
+
+    def drop_target_cache(self):
+        """Call after loading new weights into the policy (the cache is tied to the weights it was built with)."""
+        if self.tcache is not None:
+            self.lib.cns_target_cache_destroy(self.tcache)
+        self.tcache, self.tcache_handle = None, None
+
+    def __del__(self):
+        try:
+            self.drop_target_cache()
+        except Exception:
+            pass
 
     def step(self, cur_xy: torch.Tensor, visible: torch.Tensor) -> torch.Tensor:
         """One closed-loop frame: `result(submit(cur_xy, visible))`."""
@@ -115,6 +147,7 @@ class BatchedServo(object):
         b.flags = L.BATCH_L1_CUR_COMPLETE | L.BATCH_L1_TAR_COMPLETE
         b.max_clusters_per_graph = self.max_clusters
         h = self.net._handle(dev)
+        b.target_cache = self._target_cache(h)
         ws = self.net._workspace(dev.index, lib.cns_forward_workspace_bytes(C.byref(b)))
         B = self.B
         vec, vel, nrm = self.out[:B * 6], self.out[B * 6:B * 12], self.out[B * 12:]

@@ -110,6 +110,7 @@ typedef struct cns_batch {
                                    * COMPLETE hints, a bound <= 128 and a 16-bit precision mode the cluster-level
                                    * backbone runs as one fused kernel over whole-graph row tiles (verified on the
                                    * device like the hints)                                                   */
+  const struct cns_target_cache* target_cache;   /* optional, see cns_target_cache_create; NULL = recompute */
 } cns_batch;
 
 /* Structure hints about the cluster-level edge lists.  What GraphGenerator builds (graph_gen.py:31-36 via
@@ -121,6 +122,17 @@ typedef struct cns_batch {
  * `save` != NULL (training keeps the general path). */
 #define CNS_BATCH_L1_CUR_COMPLETE 1
 #define CNS_BATCH_L1_TAR_COMPLETE 2
+
+/* Everything the forward derives from the TARGET side of a batch alone - the reference builds the target graph
+ * once per target image and only re-masks it per frame (Midend.get_graph_data, corr2graph.py:11-22;
+ * GraphGenerator.__init__, graph_gen.py:133-190): the per-cluster attention term of the encoder (in_enc + lin_dst
+ * of the cluster centres, graph_vs.py:207-208), cluster positions, graph pointers and the row tiles of the fused
+ * backbone.  Built from a batch's x_tar / pos_tar / cluster_centers / num_clusters; valid for every later batch
+ * with the same target tensors while the handle keeps its weights and precision (checked: a stale cache is
+ * rejected with CNS_ERR_INVALID_ARGUMENT). */
+typedef struct cns_target_cache cns_target_cache;
+int cns_target_cache_create(cns_handle* h, const cns_batch* b, void* stream, cns_target_cache** out);
+int cns_target_cache_destroy(cns_target_cache* c);
 
 /* Replaces GraphVS.forward (graph_vs.py:284-322) + GraphVS.postprocess
  * (functions.py:26-38).  hidden_in may be NULL (== init_hidden zeros, graph_vs.py:315).
