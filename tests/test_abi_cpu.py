@@ -36,6 +36,17 @@ def test_binding_covers_header(lib):
     assert set(_declared()) <= set(_lib.EXPORTED_SYMBOLS) | {"cns_forward_save_bytes"}
 
 
+def test_batch_struct_matches_header():
+    """ctypes mirror of `struct cns_batch`: same field names in the same order as include/cns_b200.h."""
+    from cns_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "cns_b200.h")).read()
+    body = src[src.index("typedef struct cns_batch {"):src.index("} cns_batch;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"([A-Za-z0-9_]+)\s*;", body)
+    assert names == [n for n, _ in _lib.cns_batch._fields_]
+    assert ctypes.sizeof(_lib.cns_batch) == 8 * len(names)      # int64 / pointer fields only
+
+
 def test_param_table_matches_checkpoint(lib, state_dict):
     from cns_b200 import _lib
     names = _lib.param_names()

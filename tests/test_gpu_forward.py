@@ -239,6 +239,57 @@ def test_batched_servo_device_graphs_match_host_graph_path(net):
             s.step(v * 2)
 
 
+def test_target_cache_is_tied_to_weights_and_shapes(net):
+    """cns_target_cache: same results as recomputing the target side, rejected once the weights change."""
+    from cns_b200.servo import BatchedServo
+    rng = np.random.default_rng(8)
+    np.random.seed(8)
+    scenes = [synth.Scene(rng, n) for n in (40, 90)]
+    servo = BatchedServo(net, [s.generator for s in scenes], [s.tPo_norm for s in scenes], "cuda:0")
+    xy = torch.from_numpy(np.concatenate([synth.project_norm(s.cur_wcT, s.points) for s in scenes])).float()
+    vis = torch.ones(xy.shape[0], dtype=torch.bool)
+    v1 = servo.step(xy, vis).clone()
+    servo.reset()
+    servo.drop_target_cache()
+    v2 = servo.step(xy, vis).clone()
+    assert torch.equal(v1, v2)
+    sd = net.state_dict()
+    net.load_state_dict(sd)                      # re-packs the weights: the handle's weights_version moves on
+    servo.reset()
+    with pytest.raises(_lib.CnsError):
+        servo.step(xy, vis)
+    servo.drop_target_cache()
+    servo.reset()
+    assert torch.equal(servo.step(xy, vis), v1)
+
+
+def test_servo_frames_in_flight_keep_their_order(net):
+    """submit/result with two frames in flight: results equal the one-at-a-time loop, hidden state carried."""
+    from cns_b200.servo import BatchedServo
+    rng = np.random.default_rng(12)
+    np.random.seed(12)
+    scenes = [synth.Scene(rng, n) for n in (64, 33, 128)]
+    gens, tpo = [s.generator for s in scenes], [s.tPo_norm for s in scenes]
+    frames = []
+    for t in range(5):
+        xy = torch.from_numpy(np.concatenate([synth.project_norm(s.cur_wcT, s.points) for s in scenes])).float().pin_memory()
+        vis = (torch.rand(xy.shape[0], generator=torch.Generator().manual_seed(t)) > 0.2).pin_memory()
+        frames.append((xy, vis))
+        for s in scenes:
+            s.step(synth.pbvs_straight(s.cur_wcT, s.tar_wcT) * 2)
+    a = BatchedServo(net, gens, tpo, "cuda:0")
+    one = [a.step(*f).clone() for f in frames]
+    b = BatchedServo(net, gens, tpo, "cuda:0")
+    tickets, two = [], []
+    for i, f in enumerate(frames):
+        tickets.append(b.submit(*f))
+        if i >= 1:
+            two.append(b.result(tickets[i - 1]).clone())
+    two.append(b.result(tickets[-1]).clone())
+    for x, y in zip(one, two):
+        assert torch.equal(x, y)
+
+
 def test_full_size_batch_properties(net, state_dict):
     """BASELINE config: 1024 graphs x 512 keypoints.  The oracle is too slow for all of it, so:
     (1) spot-check 8 graphs against the oracle, (2) permuting the graphs of the batch permutes the

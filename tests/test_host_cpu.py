@@ -63,6 +63,32 @@ def test_graphdata_defaults_and_batching():
     assert hasattr(b, "batch") and not hasattr(frames[0], "batch")
     assert b["x_cur"] is b.x_cur
     assert isinstance(b.intrinsic, list)
+    # structure hints for the C ABI (cns_batch.flags / max_clusters_per_graph): what GraphGenerator built is a
+    # complete cluster graph; a frame of unknown origin in the batch clears the claim
+    assert all(f.l1_complete is True for f in frames) and b.l1_complete is True
+    assert b.max_clusters_per_graph == max(int(f.num_clusters) for f in frames)
+    frames[2].l1_complete = False
+    assert Batch.from_data_list(frames).l1_complete is False
+    moved = b.to("cpu")
+    assert moved.l1_complete is True and moved.max_clusters_per_graph == b.max_clusters_per_graph
+
+
+def test_complete_graph_hint_matches_the_edge_lists():
+    """The claim behind CNS_BATCH_L1_*_COMPLETE, checked on the host: l1_dense_edge_index_tar is every ordered
+    pair (self loops included) over all clusters, ..._cur over the clusters with cluster_mask, both in
+    source-major order (reference graph_gen.py:31-36, 199-228)."""
+    rng = np.random.default_rng(4)
+    np.random.seed(4)
+    s = synth.Scene(rng, 120)
+    for frac in (0.0, 0.5, 0.95):
+        d = s.frame(frac)
+        n = int(d.num_clusters)
+        alive = torch.nonzero(d.cluster_mask).flatten()
+        full = torch.arange(n)
+        for edges, nodes in ((d.l1_dense_edge_index_tar, full), (d.l1_dense_edge_index_cur, alive)):
+            m = nodes.numel()
+            assert edges.shape == (2, m * m)
+            assert torch.equal(edges[0], nodes.repeat_interleave(m)) and torch.equal(edges[1], nodes.repeat(m))
 
 
 def test_small_graph_every_point_its_own_cluster():
