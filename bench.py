@@ -155,8 +155,25 @@ def cpu_reference_rate(n_graphs, n_points, steps, warmup, budget_s=25.0):
     return n_graphs * done / dt, dt / done * 1e3, done, torch.get_num_threads()
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result: libraries that print to fd 1 (NCCL's version banner, ...)
+    are sent to stderr for the rest of the run."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
     args = parse()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -168,13 +185,13 @@ def main():
         rate, ms, done, cores = cpu_reference_rate(args.cpu_sample, args.points, args.steps, args.warmup, 120.0)
         sample = "%d of the %d graphs per step (N=%d keypoints, 10%% missing), fp32 torch CPU" % (
             args.cpu_sample, args.graphs, args.points)
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "servo graphs/sec (fwd)", "value": rate, "unit": "graphs/s",
             "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "sample": sample},
             "cpu_baseline": {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": rate, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "e2e": {"value": rate, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     import torch
@@ -329,7 +346,7 @@ def main():
         line["cpu_baseline"] = {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port",
                                 "sample": "%d graphs x %d keypoints per step, %d steps (%.1f ms/step)" % (
                                     args.cpu_sample, args.points, done, ms)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
