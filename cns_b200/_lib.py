@@ -33,6 +33,7 @@ class cns_batch(C.Structure):
         ("cluster_mask", C.c_void_p), ("cluster_centers", C.c_void_p),
         ("node_graph", C.c_void_p), ("num_clusters", C.c_void_p), ("tPo_norm", C.c_void_p),
         ("flags", C.c_int64), ("max_clusters_per_graph", C.c_int64), ("target_cache", C.c_void_p),
+        ("clu_rowptr", C.c_void_p),
     ]
 
 
@@ -76,6 +77,7 @@ def _declare(lib):
         "cns_linear": (i32, [vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, vp, vp]),
         "cns_target_cache_create": (i32, [vp, C.POINTER(cns_batch), vp, C.POINTER(vp)]),
         "cns_target_cache_destroy": (i32, [vp]),
+        "cns_frame_mask": (i32, [vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, sz, vp]),
         "cns_graph_mask_workspace_bytes": (sz, [i64, i64, i64]),
         "cns_graph_mask": (i32, [vp, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, i64, vp, vp, vp, sz, vp]),
         "cns_label_nearest": (i32, [vp, vp, i64, vp, vp, vp, vp]),

@@ -145,7 +145,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     if (fused && tcache && tcache->has_tiles) { f.tile_graph = tcache->tile_graph; f.n_tiles = tcache->n_tiles; }
     else if (fused) RUN(graph_tiles(b->num_clusters, B, f.graph_ptr, f.tile_graph, f.n_tiles, f.err, s));
   } else {
-    RUN(sorted_rowptr(b->l0_to_l1_i, b->n_e01, C, f.clu_rowptr, f.err, s));
+    if (!b->clu_rowptr || sv) RUN(sorted_rowptr(b->l0_to_l1_i, b->n_e01, C, f.clu_rowptr, f.err, s));
     if (tcache && (!fused || tcache->has_tiles)) {
       f.graph_ptr = tcache->graph_ptr; f.tile_graph = tcache->tile_graph; f.n_tiles = tcache->n_tiles;
     } else if (fused) { RUN(graph_tiles(b->num_clusters, B, f.graph_ptr, f.tile_graph, f.n_tiles, f.err, s)); }
@@ -153,6 +153,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     if (!dense_cur) RUN(csr_by_dst(b->l1_edge_cur, b->l1_edge_cur + cur_stride, b->n_e11_cur, C, f.cur_rowptr, f.cur_src, f.csr_ws, f.err, s));
     if (!dense_tar) RUN(csr_by_dst(b->l1_edge_tar, b->l1_edge_tar + tar_stride, b->n_e11_tar, C, f.tar_rowptr, f.tar_src, f.csr_ws, f.err, s));
   }
+  if (b->clu_rowptr && !sv) f.clu_rowptr = const_cast<int*>(b->clu_rowptr);   // the caller's segment pointers (cns_frame_mask)
   if (dense_cur || dense_tar) {
     L1CompleteArgs la{};
     la.n_graphs = B; la.graph_ptr = f.graph_ptr; la.alive_idx = f.alive_idx; la.alive_cnt = f.alive_cnt; la.err = f.err;

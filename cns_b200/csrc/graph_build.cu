@@ -184,6 +184,16 @@ int cns_graph_mask(const int64_t* belong, const int64_t* member_order, const int
   return CNS_OK;
 }
 
+int cns_frame_mask(const int64_t* member_order, const int32_t* member_ptr, const uint8_t* visible, int64_t n_nodes,
+                   int64_t n_clusters, int64_t* e01_j, int64_t* e01_i, uint8_t* cluster_mask, int32_t* clu_rowptr,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  CNS_REQUIRE(n_nodes >= 0 && n_clusters >= 0 && n_nodes < (1ll << 31) && n_clusters < (1ll << 31), "bad size");
+  CNS_REQUIRE(member_order && member_ptr && visible && e01_j && e01_i && cluster_mask && clu_rowptr && workspace, "NULL pointer");
+  CNS_REQUIRE(workspace_bytes >= (size_t)(n_clusters + 1) * sizeof(int), "cns_frame_mask: workspace too small");
+  return frame_mask(member_order, member_ptr, visible, n_clusters, e01_j, e01_i, cluster_mask, clu_rowptr, (int*)workspace,
+                    (cudaStream_t)stream);
+}
+
 int cns_label_nearest(const double* points, const int64_t* point_graph, int64_t n_points,
                       const double* exemplars, const int64_t* exemplar_ptr, int32_t* labels, void* stream) {
   CNS_REQUIRE(points && exemplars && exemplar_ptr && labels, "NULL pointer");

@@ -18,6 +18,9 @@ int csr_by_dst(const int64_t* ej, const int64_t* ei, int64_t n_edges, int64_t n_
 int graph_ptr_from_counts(const int64_t* num_clusters, int64_t n_graphs, int* graph_ptr, int* tmp,
                           int* scratch, cudaStream_t s);
 
+int frame_mask(const int64_t* member_order, const int* member_ptr, const uint8_t* visible, int64_t n_clusters,
+               int64_t* e01_j, int64_t* e01_i, uint8_t* cluster_mask, int* clu_rowptr, int* cnt_scratch, cudaStream_t s);
+
 constexpr int GRAPH_TILES_MAX = 4096;
 int graph_tiles(const int64_t* num_clusters, int64_t n_graphs, int* graph_ptr, int* tile_graph, int* n_tiles, int* err,
                 cudaStream_t s);

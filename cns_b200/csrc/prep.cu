@@ -240,6 +240,64 @@ graph_tiles_kernel(const int64_t* __restrict__ num_clusters, int n_graphs, int* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Per-frame masking of B resident target graphs in cluster-major form (GraphGenerator._get_graph,
+// graph_gen.py:199-228, for every scene at once): the keypoint -> cluster edge list keeps the visible
+// members of every cluster in their static order, so it is a per-cluster compaction:
+// count (warp per cluster) -> one-CTA scan -> emit (warp per cluster).  The scan IS the cluster rowptr the
+// encoder needs, so the forward does not have to re-derive it from the edge list.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+frame_count_kernel(const int64_t* __restrict__ member_order, const int* __restrict__ member_ptr,
+                   const uint8_t* __restrict__ visible, int n_clusters, int* __restrict__ cnt, uint8_t* __restrict__ cluster_mask) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= n_clusters) return;
+  const int beg = member_ptr[c], end = member_ptr[c + 1];
+  int n = 0;
+  for (int k = beg + lane; k < end; k += 32) n += visible[member_order[k]] ? 1 : 0;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) n += __shfl_xor_sync(0xffffffffu, n, off);
+  if (lane == 0) { cnt[c] = n; cluster_mask[c] = n > 0 ? 1 : 0; }
+}
+
+__global__ void __launch_bounds__(1024)
+frame_scan_kernel(int* cnt, int n, int* rowptr) { block_scan_inplace(cnt, n, rowptr); }
+
+__global__ void __launch_bounds__(256)
+frame_emit_kernel(const int64_t* __restrict__ member_order, const int* __restrict__ member_ptr,
+                  const uint8_t* __restrict__ visible, int n_clusters, const int* __restrict__ rowptr,
+                  int64_t* __restrict__ e01_j, int64_t* __restrict__ e01_i) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= n_clusters) return;
+  const int beg = member_ptr[c], end = member_ptr[c + 1];
+  int out = rowptr[c];
+  for (int k0 = beg; k0 < end; k0 += 32) {
+    const int k = k0 + lane;
+    const int64_t node = k < end ? member_order[k] : 0;
+    const bool v = k < end && visible[node];
+    const unsigned bal = __ballot_sync(0xffffffffu, v);
+    if (v) {
+      const int pos = out + __popc(bal & ((1u << lane) - 1u));
+      e01_j[pos] = node;
+      e01_i[pos] = c;
+    }
+    out += __popc(bal);
+  }
+}
+
+int frame_mask(const int64_t* member_order, const int* member_ptr, const uint8_t* visible, int64_t n_clusters,
+               int64_t* e01_j, int64_t* e01_i, uint8_t* cluster_mask, int* clu_rowptr, int* cnt_scratch, cudaStream_t s) {
+  if (n_clusters == 0) return CNS_OK;
+  const int C = (int)n_clusters;
+  frame_count_kernel<<<ceil_div(C, 8), 256, 0, s>>>(member_order, member_ptr, visible, C, cnt_scratch, cluster_mask);
+  CNS_LAUNCH_CHECK();
+  frame_scan_kernel<<<1, 1024, 0, s>>>(cnt_scratch, C, clu_rowptr);
+  CNS_LAUNCH_CHECK();
+  frame_emit_kernel<<<ceil_div(C, 8), 256, 0, s>>>(member_order, member_ptr, visible, C, clu_rowptr, e01_j, e01_i);
+  CNS_LAUNCH_CHECK();
+  return CNS_OK;
+}
+
 int graph_tiles(const int64_t* num_clusters, int64_t n_graphs, int* graph_ptr, int* tile_graph, int* n_tiles, int* err,
                 cudaStream_t s) {
   CNS_REQUIRE(n_graphs <= GRAPH_TILES_MAX, "graph_tiles: too many graphs");

@@ -7,8 +7,8 @@ keypoints that were not matched (`Midend.get_graph_data`, cns/midend/corr2graph.
 `Batch.from_data_list` (sim/dataset.py:206-209).  `BatchedServo` keeps that split for B scenes at once
 (SURVEY 8f2): constructor = "target changed" (static tensors uploaded once: target keypoints, cluster
 membership, centres); `step(cur_xy, visible)` = one frame: H2D of the current keypoint coordinates +
-visibility mask, `cns_graph_mask` (per-frame keypoint->cluster edges and cluster mask, bit-exact with
-`_get_graph` + collation), `cns_graphvs_forward` with the hidden state carried on the device, D2H of the
+visibility mask, `cns_frame_mask` (per-frame keypoint->cluster edges, cluster mask and cluster segment
+pointers, bit-exact with `_get_graph` + collation), `cns_graphvs_forward` with the hidden state carried on the device, D2H of the
 (B,6) velocities.  The cluster-level graphs are complete digraphs (all clusters / alive clusters), so
 they are passed as a flag instead of edge lists (CNS_BATCH_L1_*_COMPLETE).
 """
@@ -38,17 +38,16 @@ class BatchedServo(object):
         self.x_tar = d(tar, torch.float32)                                   # x_tar == pos_tar (default_feature)
         self.belong = d(np.concatenate([g.belong_cluster_index + c for g, c in zip(gens, coff)]), torch.int64)
         self.member_order = d(np.concatenate([g.l0_to_l1_edge_index[0] + o for g, o in zip(gens, noff)]), torch.int64)
-        self.cluster_size = d(np.concatenate([g.cluster_points_count for g in gens]), torch.int64)
-        self.cluster_graph_ptr = d(np.concatenate([[0], np.cumsum(n_clu)]), torch.int64)
+        csize = np.concatenate([g.cluster_points_count for g in gens]).astype(np.int64)
+        self.member_ptr = d(np.concatenate([[0], np.cumsum(csize)]), torch.int32)       # members of cluster c: member_order[ptr[c]:ptr[c+1]]
         self.centers = d(np.concatenate([g.cluster_centers_index + o for g, o in zip(gens, noff)]), torch.int64)
         self.num_clusters = d(n_clu, torch.int64)
         self.tpo = d(np.broadcast_to(np.asarray(dist_scale, dtype=np.float32), (self.B,)), torch.float32)
         i64 = lambda n: torch.empty(n, dtype=torch.int64, device=self.dev)
         self.e01_j, self.e01_i = i64(max(self.N, 1)), i64(max(self.N, 1))
         self.cmask = torch.empty(max(self.Cn, 1), dtype=torch.uint8, device=self.dev)
-        self.counts = torch.zeros(2, dtype=torch.int64, device=self.dev)
-        self.mask_ws = torch.empty(self.lib.cns_graph_mask_workspace_bytes(self.N, self.Cn, self.B), dtype=torch.uint8,
-                                   device=self.dev)
+        self.clu_rowptr = torch.empty(self.Cn + 1, dtype=torch.int32, device=self.dev)
+        self.mask_ws = torch.empty((self.Cn + 1) * 4, dtype=torch.uint8, device=self.dev)
         # frames in flight (submit / result): inputs and outputs are double-buffered, everything in between is
         # ordered by the compute stream
         self.depth = 2
@@ -129,11 +128,9 @@ class BatchedServo(object):
             self.copied[k].record(self.copy_stream)
         cur.wait_event(self.copied[k])
         xy, visd = self.xy_dev[k], self.vis_dev[k]
-        L.check(lib.cns_graph_mask(L.ptr(self.belong), L.ptr(self.member_order), L.ptr(self.cluster_size),
-                                   L.ptr(self.cluster_graph_ptr), L.ptr(visd), self.N, self.Cn, self.B,
-                                   L.ptr(self.e01_j), L.ptr(self.e01_i), None, 0,
-                                   L.ptr(self.cmask), L.ptr(self.counts), L.ptr(self.mask_ws), self.mask_ws.numel(), stream),
-                "cns_graph_mask")
+        L.check(lib.cns_frame_mask(L.ptr(self.member_order), L.ptr(self.member_ptr), L.ptr(visd), self.N, self.Cn,
+                                   L.ptr(self.e01_j), L.ptr(self.e01_i), L.ptr(self.cmask), L.ptr(self.clu_rowptr),
+                                   L.ptr(self.mask_ws), self.mask_ws.numel(), stream), "cns_frame_mask")
         b = L.cns_batch()
         b.n_nodes, b.n_clusters, b.n_graphs = self.N, self.Cn, self.B
         b.n_e01, b.n_e11_cur, b.n_e11_tar = n01, 0, 0
@@ -148,6 +145,7 @@ class BatchedServo(object):
         b.max_clusters_per_graph = self.max_clusters
         h = self.net._handle(dev)
         b.target_cache = self._target_cache(h)
+        b.clu_rowptr = p(self.clu_rowptr)
         ws = self.net._workspace(dev.index, lib.cns_forward_workspace_bytes(C.byref(b)))
         B = self.B
         vec, vel, nrm = self.out[:B * 6], self.out[B * 6:B * 12], self.out[B * 12:]

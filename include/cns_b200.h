@@ -111,6 +111,7 @@ typedef struct cns_batch {
                                    * backbone runs as one fused kernel over whole-graph row tiles (verified on the
                                    * device like the hints)                                                   */
   const struct cns_target_cache* target_cache;   /* optional, see cns_target_cache_create; NULL = recompute */
+  const int32_t* clu_rowptr;      /* optional (C+1,): segment pointers of l0_to_l1_i (cns_frame_mask); NULL = derived */
 } cns_batch;
 
 /* Structure hints about the cluster-level edge lists.  What GraphGenerator builds (graph_gen.py:31-36 via
@@ -241,6 +242,14 @@ int cns_graph_mask(const int64_t* belong, const int64_t* member_order, const int
                    int64_t n_nodes, int64_t n_clusters, int64_t n_graphs,
                    int64_t* e01_j, int64_t* e01_i, int64_t* e11_cur, int64_t e11_capacity,
                    uint8_t* cluster_mask, int64_t* counts_out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same masking in cluster-major form, for callers that keep the static per-target arrays around
+ * (BatchedServo): member_ptr (C+1,) int32 = prefix sums of cluster_size.  Three launches; additionally returns the
+ * cluster rowptr of the filtered edge list (C+1,) int32, which can be handed to the forward as
+ * cns_batch.clu_rowptr.  workspace: (C+1) int32. */
+int cns_frame_mask(const int64_t* member_order, const int32_t* member_ptr, const uint8_t* visible, int64_t n_nodes,
+                   int64_t n_clusters, int64_t* e01_j, int64_t* e01_i, uint8_t* cluster_mask, int32_t* clu_rowptr,
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* Affinity Propagation message passing (the clustering behind cluster_points, graph_gen.py:104-106 ->

@@ -146,6 +146,45 @@ def test_graph_mask_bit_exact_vs_graph_generator():
     assert torch.equal(cmask.bool().cpu(), ref.cluster_mask)
 
 
+def test_frame_mask_bit_exact_vs_graph_generator():
+    """Cluster-major per-frame masking (cns_frame_mask): keypoint->cluster edges, cluster mask and the cluster
+    segment pointers == GraphGenerator._get_graph + Batch collation, bit-exact (reference graph_gen.py:199-228)."""
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    np.random.seed(5)
+    gens, vis, frames = [], [], []
+    for n in (12, 40, 130, 16, 300, 64):
+        pts = synth.project_norm(synth.sample_target_pose(rng), synth.sample_points(rng, n))
+        g = GraphGenerator(pts)
+        frac = rng.choice([0.0, 0.3, 0.8, 1.0])
+        missing = np.sort(rng.choice(len(pts), size=int(len(pts) * frac), replace=False))
+        v = np.ones(len(pts), bool); v[missing] = False
+        gens.append(g); vis.append(v); frames.append(g.get_data(pts, missing_node_indices=missing))
+    ref = Batch.from_data_list(frames)
+    n_nodes = np.array([g.num_points for g in gens]); n_clu = np.array([g.num_clusters for g in gens])
+    noff = np.cumsum(n_nodes) - n_nodes
+    order = np.concatenate([g.l0_to_l1_edge_index[0] + o for g, o in zip(gens, noff)])
+    csize = np.concatenate([g.cluster_points_count for g in gens]).astype(np.int64)
+    N, Cn = int(n_nodes.sum()), int(n_clu.sum())
+    d = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=DEV)
+    t_order, t_ptr = d(order, torch.int64), d(np.concatenate([[0], np.cumsum(csize)]), torch.int32)
+    t_vis = d(np.concatenate(vis), torch.uint8)
+    e01_j, e01_i = torch.full((N,), -1, dtype=torch.int64, device=DEV), torch.full((N,), -1, dtype=torch.int64, device=DEV)
+    cmask = torch.empty(Cn, dtype=torch.uint8, device=DEV)
+    rowptr = torch.empty(Cn + 1, dtype=torch.int32, device=DEV)
+    ws = torch.empty((Cn + 1) * 4, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.cns_frame_mask(_lib.ptr(t_order), _lib.ptr(t_ptr), _lib.ptr(t_vis), N, Cn, _lib.ptr(e01_j), _lib.ptr(e01_i),
+                                  _lib.ptr(cmask), _lib.ptr(rowptr), _lib.ptr(ws), ws.numel(), _sp()), "frame_mask")
+    n01 = ref.l0_to_l1_edge_index_j_cur.numel()
+    assert int(rowptr[-1]) == n01 == int(t_vis.sum())
+    assert torch.equal(e01_j[:n01].cpu(), ref.l0_to_l1_edge_index_j_cur)
+    assert torch.equal(e01_i[:n01].cpu(), ref.l0_to_l1_edge_index_i_cur)
+    assert torch.equal(cmask.bool().cpu(), ref.cluster_mask)
+    want = torch.zeros(Cn + 1, dtype=torch.int64)
+    want[1:] = torch.cumsum(torch.bincount(ref.l0_to_l1_edge_index_i_cur, minlength=Cn), 0)
+    assert torch.equal(rowptr.cpu().long(), want)
+
+
 def test_label_nearest_matches_numpy_argmax():
     lib = _lib.load()
     rng = np.random.default_rng(4)
