@@ -394,8 +394,52 @@ int enc_edge_fp32(const EncEdgeArgs& a, cudaStream_t s) {
   return CNS_OK;
 }
 
+// Repair only (the fused backbone applies out_enc itself): one thread per cluster finds the clusters that need
+// work - no edges (feature 0) or cut by a softmax-piece boundary (merge the pieces) - and the CTA's 256 threads
+// (side, channel) then handle those few.
+__global__ void __launch_bounds__(256)
+enc_fix_kernel(EncFinishArgs p) {
+  __shared__ int todo[256];
+  __shared__ int n_todo;
+  const int tid = threadIdx.x;
+  if (tid == 0) n_todo = 0;
+  __syncthreads();
+  const int64_t c = (int64_t)blockIdx.x * 256 + tid;
+  if (c < p.n_clusters) {
+    const int beg = p.clu_rowptr[c], end = p.clu_rowptr[c + 1];
+    const bool empty = end == beg;
+    const bool cut = !empty && (beg / p.piece_e != (end - 1) / p.piece_e);
+    if (empty || cut) todo[atomicAdd(&n_todo, 1)] = tid;
+  }
+  __syncthreads();
+  const int side = tid >> 7, o = tid & 127;
+  for (int i = 0; i < n_todo; ++i) {
+    const int64_t cc = (int64_t)blockIdx.x * 256 + todo[i];
+    const int beg = p.clu_rowptr[cc], end = p.clu_rowptr[cc + 1];
+    float* feat = p.clu_feat + ((size_t)side * p.n_clusters + cc) * H;
+    if (end == beg) { feat[o] = 0.f; continue; }
+    const int p0 = beg / p.piece_e, p1 = (end - 1) / p.piece_e;
+    const float* part = p.partial + (size_t)side * p.n_slots * 3 * H;
+    float m = -INFINITY;
+    for (int pc = p0; pc <= p1; ++pc) m = fmaxf(m, part[((size_t)cc + pc) * 3 * H + o]);
+    float s = 0.f, a = 0.f;
+    for (int pc = p0; pc <= p1; ++pc) {
+      const float* slot = part + ((size_t)cc + pc) * 3 * H;
+      const float w = expf(slot[o] - m);
+      s = fmaf(slot[H + o], w, s);
+      a = fmaf(slot[2 * H + o], w, a);
+    }
+    feat[o] = fmaxf(a / (s + 1e-16f), 0.f);
+  }
+}
+
 int enc_finish(const EncFinishArgs& a, cudaStream_t s) {
   if (a.n_clusters == 0) return CNS_OK;
+  if (a.fix_only) {
+    enc_fix_kernel<<<ceil_div(a.n_clusters, 256), 256, 0, s>>>(a);
+    CNS_LAUNCH_CHECK();
+    return CNS_OK;
+  }
   enc_finish_kernel<<<ceil_div(a.n_clusters, CLU_ROWS), 128, 0, s>>>(a);
   CNS_LAUNCH_CHECK();
   return CNS_OK;

@@ -114,6 +114,22 @@ def _field(data, key, default=None):
         return default
 
 
+class TargetCache(object):
+    """Owner of a `cns_target_cache` (include/cns_b200.h)."""
+
+    def __init__(self, handle, b, dev, keep):
+        self.lib, self.raw = _lib.load(), C.c_void_p()
+        _lib.check(self.lib.cns_target_cache_create(handle.raw, C.byref(b), _lib.stream_ptr(dev), C.byref(self.raw)),
+                   "cns_target_cache_create")
+
+    def __del__(self):
+        try:
+            if self.raw:
+                self.lib.cns_target_cache_destroy(self.raw)
+        except Exception:
+            pass
+
+
 class GraphVS(nn.Module):
     # the GraphData / Batch tensors forward() reads (graph_vs.py:285-307); `vel_si` / `vel` ride along for the loss
     INPUT_FIELDS = ("x_cur", "x_tar", "pos_cur", "pos_tar", "l0_to_l1_edge_index_j_cur", "l0_to_l1_edge_index_i_cur",
@@ -273,7 +289,9 @@ class GraphVS(nn.Module):
         return b, keep
 
     # ------------------------------------------------------------------ forward
-    def forward(self, data, hidden: Optional[torch.Tensor] = None, check: bool = False):
+    def forward(self, data, hidden: Optional[torch.Tensor] = None, check: bool = False, target_cache=None):
+        """`target_cache` (optional, from `build_target_cache`): reuse what depends on the target side of the batch
+        only - the reference builds its target graph once per target image (corr2graph.py:11-22)."""
         x_cur = _field(data, "x_cur")
         if not x_cur.is_cuda:
             raise _lib.CnsError(
@@ -282,13 +300,22 @@ class GraphVS(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .autograd import graphvs_autograd
             return graphvs_autograd(self, data, hidden)
-        return self._forward_inference(data, hidden, check)
+        return self._forward_inference(data, hidden, check, target_cache)
 
-    def _forward_inference(self, data, hidden, check=False):
+    def build_target_cache(self, data) -> "TargetCache":
+        """Target-side results of `data` (x_tar / pos_tar / cluster_centers_index / num_clusters), valid for every
+        batch with the same targets while the weights and the precision mode stay unchanged."""
+        b, keep = self.make_batch_struct(data)
+        dev = keep[0].device
+        return TargetCache(self._handle(dev), b, dev, keep)
+
+    def _forward_inference(self, data, hidden, check=False, target_cache=None):
         lib = _lib.load()
         b, keep = self.make_batch_struct(data)
         dev = keep[0].device
         h = self._handle(dev)
+        if target_cache is not None:
+            b.target_cache = target_cache.raw
         nb, nc = b.n_graphs, b.n_clusters
         # one allocation; the (C,128) block first so its rows stay 16-byte aligned
         out = torch.empty(nc * 128 + nb * 13, dtype=torch.float32, device=dev)
