@@ -15,7 +15,7 @@ from cns_b200.graph_gen import GraphGenerator
 from cns_b200.train import TBPTTStepper
 
 CK = os.path.join(ROOT, "checkpoints", "cns.pth")
-which = set(sys.argv[1].split(",")) if len(sys.argv) > 1 else {"c1", "c3", "c4", "c5"}
+which = set(sys.argv[1].split(",")) if len(sys.argv) > 1 else {"c1", "c2", "c3", "c4", "c5"}
 out = {}
 
 
@@ -140,6 +140,25 @@ if "c4" in which:
     stepper = TBPTTStepper(net)
     ms = ev_time(lambda: stepper.step(frames, mean=True), 3, warm=1)
     out["C4_long_seq_train_bs16_200frames"] = {"ms_per_update": ms, "graph_frames_per_s_fwd_bwd": 16 * 200 / ms * 1e3}
+
+if "c2" in which:
+    # headline workload (bench.py) with the recurrent hidden state carried instead of hidden=None
+    import bench
+    net = ckpt.load_model(CK, "cuda:0", precision="f16")
+    batches = [b.to("cuda:0") for b in bench.build_batches(1024, 512, 2022, 2)]
+    tc = net.build_target_cache(batches[0])
+    res = {}
+    with torch.no_grad():
+        hid = net(batches[0], None, target_cache=tc)[2]
+        st = {"h": hid, "i": 0}
+        def carried():
+            st["h"] = net(batches[st["i"] & 1], st["h"], target_cache=tc)[2]; st["i"] += 1
+        def first():
+            net(batches[st["i"] & 1], None, target_cache=tc); st["i"] += 1
+        for name, fn in (("hidden_none", first), ("hidden_carried", carried)):
+            ms = ev_time(fn, 50)
+            res[name] = {"ms": ms, "graphs_per_s": 1024 / ms * 1e3}
+    out["C2_batched_inference_1024x512_f16"] = res
 
 if "c5" in which:
     res = {}
