@@ -412,24 +412,31 @@ enc_fix_kernel(EncFinishArgs p) {
     if (empty || cut) todo[atomicAdd(&n_todo, 1)] = tid;
   }
   __syncthreads();
-  const int side = tid >> 7, o = tid & 127;
-  for (int i = 0; i < n_todo; ++i) {
-    const int64_t cc = (int64_t)blockIdx.x * 256 + todo[i];
+  // one warp per flagged (cluster, side): a lane owns 4 channels
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int item = warp; item < 2 * n_todo; item += 8) {
+    const int side = item & 1;
+    const int64_t cc = (int64_t)blockIdx.x * 256 + todo[item >> 1];
     const int beg = p.clu_rowptr[cc], end = p.clu_rowptr[cc + 1];
-    float* feat = p.clu_feat + ((size_t)side * p.n_clusters + cc) * H;
-    if (end == beg) { feat[o] = 0.f; continue; }
+    float4* feat = reinterpret_cast<float4*>(p.clu_feat + ((size_t)side * p.n_clusters + cc) * H) + lane;
+    if (end == beg) { *feat = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
     const int p0 = beg / p.piece_e, p1 = (end - 1) / p.piece_e;
     const float* part = p.partial + (size_t)side * p.n_slots * 3 * H;
-    float m = -INFINITY;
-    for (int pc = p0; pc <= p1; ++pc) m = fmaxf(m, part[((size_t)cc + pc) * 3 * H + o]);
-    float s = 0.f, a = 0.f;
+    auto slot4 = [&](int pc, int which) { return reinterpret_cast<const float4*>(part + ((size_t)cc + pc) * 3 * H + which * H)[lane]; };
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     for (int pc = p0; pc <= p1; ++pc) {
-      const float* slot = part + ((size_t)cc + pc) * 3 * H;
-      const float w = expf(slot[o] - m);
-      s = fmaf(slot[H + o], w, s);
-      a = fmaf(slot[2 * H + o], w, a);
+      const float4 v = slot4(pc, 0);
+      m = make_float4(fmaxf(m.x, v.x), fmaxf(m.y, v.y), fmaxf(m.z, v.z), fmaxf(m.w, v.w));
     }
-    feat[o] = fmaxf(a / (s + 1e-16f), 0.f);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), a = s;
+    for (int pc = p0; pc <= p1; ++pc) {
+      const float4 lm = slot4(pc, 0), ls = slot4(pc, 1), la = slot4(pc, 2);
+      const float4 w = make_float4(expf(lm.x - m.x), expf(lm.y - m.y), expf(lm.z - m.z), expf(lm.w - m.w));
+      s = make_float4(fmaf(ls.x, w.x, s.x), fmaf(ls.y, w.y, s.y), fmaf(ls.z, w.z, s.z), fmaf(ls.w, w.w, s.w));
+      a = make_float4(fmaf(la.x, w.x, a.x), fmaf(la.y, w.y, a.y), fmaf(la.z, w.z, a.z), fmaf(la.w, w.w, a.w));
+    }
+    *feat = make_float4(fmaxf(a.x / (s.x + 1e-16f), 0.f), fmaxf(a.y / (s.y + 1e-16f), 0.f),
+                        fmaxf(a.z / (s.z + 1e-16f), 0.f), fmaxf(a.w / (s.w + 1e-16f), 0.f));
   }
 }
 

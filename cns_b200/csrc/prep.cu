@@ -260,8 +260,18 @@ frame_count_kernel(const int64_t* __restrict__ member_order, const int* __restri
   if (lane == 0) { cnt[c] = n; cluster_mask[c] = n > 0 ? 1 : 0; }
 }
 
+// exclusive scan of n <= 1024 * 64 counts in one CTA: every thread owns a contiguous run, one block scan of the run totals
 __global__ void __launch_bounds__(1024)
-frame_scan_kernel(int* cnt, int n, int* rowptr) { block_scan_inplace(cnt, n, rowptr); }
+frame_scan_kernel(const int* __restrict__ cnt, int n, int* __restrict__ rowptr) {
+  __shared__ int total;
+  const int per = (n + 1023) / 1024;
+  const int beg = min(threadIdx.x * per, n), end = min(beg + per, n);
+  int sum = 0;
+  for (int i = beg; i < end; ++i) sum += cnt[i];
+  int run = block_exclusive_scan(sum, &total);
+  for (int i = beg; i < end; ++i) { rowptr[i] = run; run += cnt[i]; }
+  if (threadIdx.x == 0) rowptr[n] = total;
+}
 
 __global__ void __launch_bounds__(256)
 frame_emit_kernel(const int64_t* __restrict__ member_order, const int* __restrict__ member_ptr,
