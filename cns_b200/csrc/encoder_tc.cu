@@ -234,6 +234,9 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     int idx_j = 0, idx_c = -1;                     // prefetched tile: source keypoint / cluster of edge pe
     float2 c_f = make_float2(0.f, 0.f), c_ps = c_f, c_pt = c_f, c_pc = c_f;   // coordinates of the tile produced next
     bool c_live = false;
+    // ... and of the tile after it (gathers in flight for a whole tile)
+    float2 n_f = c_f, n_ps = c_f, n_pt = c_f, n_pc = c_f;
+    int n_cid = -1;
     auto fetch_index = [&](int g) {
       idx_c = -1; idx_j = 0;
       if (g < t_end) {
@@ -241,23 +244,27 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         if (e < p.n_e01) { idx_j = (int)p.ej[e]; idx_c = (int)p.ei[e]; }
       }
     };
-    auto fetch_coords = [&]() {
-      c_live = idx_c >= 0;
-      if (c_live) {
+    auto fetch_coords = [&]() {                    // gathers of the tile whose indices sit in idx_* -> n_*
+      n_cid = idx_c;
+      if (n_cid >= 0) {
         const float* __restrict__ fsrc = side ? p.x_tar : p.x_cur;
         const float* __restrict__ psrc = side ? p.pos_tar : p.pos_cur;
-        c_f = reinterpret_cast<const float2*>(fsrc)[idx_j];
-        c_ps = reinterpret_cast<const float2*>(psrc)[idx_j];
-        c_pt = reinterpret_cast<const float2*>(p.pos_tar)[idx_j];
-        c_pc = reinterpret_cast<const float2*>(p.pos_clu)[idx_c];
+        n_f = reinterpret_cast<const float2*>(fsrc)[idx_j];
+        n_ps = reinterpret_cast<const float2*>(psrc)[idx_j];
+        n_pt = reinterpret_cast<const float2*>(p.pos_tar)[idx_j];
+        n_pc = reinterpret_cast<const float2*>(p.pos_clu)[n_cid];
       }
     };
+    auto advance_coords = [&]() { c_f = n_f; c_ps = n_ps; c_pt = n_pt; c_pc = n_pc; c_live = n_cid >= 0; };
     // cluster ids travel through a double-buffered smem row: ci(i+1) is written while tile i waits for its
     // round A (everyone has left tile i-1 by then) and is published by tile i's second slot barrier
     fetch_index(tile_of(0));
     if (kp == 0) ci_base[pe] = idx_c;
     fetch_coords();
+    advance_coords();                              // c_* = tile 0
     fetch_index(tile_of(1));
+    fetch_coords();                                // n_* = tile 1
+    fetch_index(tile_of(2));
     named_bar(1 + s, 128);
 
     // running softmax state of the cluster that is open at the end of a tile (carried to the next tile)
@@ -287,37 +294,37 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     unsigned char* const u_row = buf0 + (t >> 3) * (8 * U_ROW) + (t & 7) * U_ROW;
     const uint32_t u_xor = (uint32_t)(((t & 7) * U_ROW) >> 7) & (uint32_t)(U_ROW / 16 - 1);
 
-    for (int it = 0;; ++it) {
-      const int g = tile_of(it);
-      if (g >= t_end) break;
-      const int* const ci = ci_base + (it & 1) * TN;
-
-      // segment-start bit per edge (bit e: ci[e] != ci[e-1]); warp-uniform registers, no per-element LDS
-      uint32_t seg_mask[TN / 32];
+    // segment-start bits of a tile (bit e: ci[e] != ci[e-1]; warp-uniform registers, no per-element LDS) and the
+    // a'[cluster][t] = (A0 (a_dst + b_pos1) + b_attn0)[t] rows of its first NPRE segment starts
+    uint32_t seg_mask[TN / 32], seg_next[TN / 32];
+    float aq[NPRE], aq_next[NPRE];
+    auto seg_and_prefetch = [&](const int* ci, uint32_t (&sm)[TN / 32], float (&a)[NPRE]) {
 #pragma unroll
       for (int c0 = 0; c0 < TN; c0 += 32) {
         const int e = c0 + lane;
         const int cprev = (e == 0) ? -2 : ci[e - 1];
-        seg_mask[c0 / 32] = __ballot_sync(0xffffffffu, ci[e] != cprev);
+        sm[c0 / 32] = __ballot_sync(0xffffffffu, ci[e] != cprev);
       }
-      // a'[cluster][t] = (A0 (a_dst + b_pos1) + b_attn0)[t] of the tile's first NPRE segment starts: the
-      // loads fly during the producer math and round A
-      float aq[NPRE];
-      {
-        uint32_t m0 = seg_mask[0];
-        uint32_t m1 = (TN > 32) ? seg_mask[(TN > 32) ? 1 : 0] : 0u;
+      uint32_t m0 = sm[0];
+      uint32_t m1 = (TN > 32) ? sm[(TN > 32) ? 1 : 0] : 0u;
 #pragma unroll
-        for (int i = 0; i < NPRE; ++i) {
-          aq[i] = 0.f;
-          int q = -1;
-          if (m0) { q = __ffs(m0) - 1; m0 &= m0 - 1; }
-          else if (TN > 32 && m1) { q = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
-          if (q >= 0) {
-            const int c = ci[q];
-            if (c >= 0) aq[i] = p.a_dst[(size_t)c * H + t];
-          }
+      for (int i = 0; i < NPRE; ++i) {
+        a[i] = 0.f;
+        int q = -1;
+        if (m0) { q = __ffs(m0) - 1; m0 &= m0 - 1; }
+        else if (TN > 32 && m1) { q = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
+        if (q >= 0) {
+          const int c = ci[q];
+          if (c >= 0) a[i] = p.a_dst[(size_t)c * H + t];
         }
       }
+    };
+    seg_and_prefetch(ci_base, seg_mask, aq);       // tile 0
+
+    for (int it = 0;; ++it) {
+      const int g = tile_of(it);
+      if (g >= t_end) break;
+      const int* const ci = ci_base + (it & 1) * TN;
 
       // ---- producer: x -> buf0, hp -> buf1 ---------------------------------------------------------
       {
@@ -393,14 +400,15 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         }
       }
       publish_and_issue(0);
-      if (kp == 0) ci_base[((it + 1) & 1) * TN + pe] = idx_c;    // ci(i+1): its buffer was last read in tile i-1
+      if (kp == 0) ci_base[((it + 1) & 1) * TN + pe] = n_cid;    // ci(i+1): its buffer was last read in tile i-1
 
       // ---- epilogue: u = relu(U + a'[cluster]) -> buf0, MN-major ([channel][edge]: this thread's row) ---
       // (padding columns of the last tile keep finite garbage; they are never read back)
       mbar_wait(done, done_parity); done_parity ^= 1;
       tc_fence_after();
-      fetch_coords();                  // tile i+1: dependent gathers fly during the epilogue and the softmax
-      fetch_index(tile_of(it + 2));    // tile i+2: consumed a whole tile later
+      advance_coords();                // tile i+1: gathered a whole tile ago
+      fetch_coords();                  // tile i+2: dependent gathers fly for a whole tile
+      fetch_index(tile_of(it + 3));    // tile i+3: consumed a whole tile later
       {
         float adb = 0.f;
         int nseg = 0;
@@ -441,6 +449,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         }
       }
       publish_and_issue(1);
+      seg_and_prefetch(ci_base + ((it + 1) & 1) * TN, seg_next, aq_next);   // tile i+1: its a' rows land during the softmax
 
       // ---- final: per-channel online segment softmax of L weighting V ---------------------------
       // softmax is shift-invariant per channel, so the attn_nn.1 bias drops out; the value bias b_p1
@@ -487,6 +496,10 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         }
         if (g + 1 >= t_end && run_seg >= 0) { flush_run(run_whole && chunk_whole_end); run_seg = -1; }   // chunk end
       }
+#pragma unroll
+      for (int i = 0; i < TN / 32; ++i) seg_mask[i] = seg_next[i];
+#pragma unroll
+      for (int i = 0; i < NPRE; ++i) aq[i] = aq_next[i];
     }
   }
 
