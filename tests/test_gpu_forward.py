@@ -300,6 +300,35 @@ def test_servo_frames_in_flight_keep_their_order(net):
         assert torch.equal(x, y)
 
 
+def test_device_scene_batch_matches_host_graph_path():
+    """DeviceSceneBatch.observe(): the same Batch the host path builds for the same poses and
+    visibility - graph tensors bit-exact, coordinates / labels to fp32 rounding - over a few closed-loop steps."""
+    from cns_b200.sim_device import DeviceSceneBatch
+    env = DeviceSceneBatch(6, np.random.default_rng(17), "cuda:0", max_points=200)
+    for step in range(3):
+        poses = env.cur_wcT.cpu().numpy()
+        d = env.observe()
+        vis = d.node_mask.cpu().numpy()
+        frames, o = [], 0
+        for k, s in enumerate(env.scenes):
+            n = len(s.points)
+            missing = np.nonzero(~vis[o:o + n])[0]
+            f = s.generator.get_data(synth.project_norm(poses[k], s.points), missing_node_indices=missing if len(missing) else None)
+            f.set_distance_scale(s.tPo_norm)
+            frames.append(f); o += n
+        ref = Batch.from_data_list(frames)
+        for key in ("l0_to_l1_edge_index_j_cur", "l0_to_l1_edge_index_i_cur", "l1_dense_edge_index_cur",
+                    "l1_dense_edge_index_tar", "cluster_mask", "cluster_centers_index", "num_clusters", "node_mask"):
+            assert torch.equal(d[key].cpu(), ref[key]), key
+        assert float((d.x_cur.cpu() - ref.x_cur).abs().max()) < 1e-6 and torch.equal(d.x_tar.cpu(), ref.x_tar)
+        want = np.stack([synth.pbvs_straight(poses[k], s.tar_wcT) for k, s in enumerate(env.scenes)])
+        assert float((d.vel.cpu() - torch.from_numpy(want).float()).abs().max()) < 1e-6
+        env.feedback(d.vel * 2)
+        nxt = np.stack([synth.integrate(poses[k], want[k] * 2) for k in range(len(env.scenes))])
+        fresh = env.fresh.cpu().numpy()
+        assert np.abs(env.cur_wcT.cpu().numpy()[~fresh] - nxt[~fresh]).max() < 1e-6
+
+
 def test_full_size_batch_properties(net, state_dict):
     """BASELINE config: 1024 graphs x 512 keypoints.  The oracle is too slow for all of it, so:
     (1) spot-check 8 graphs against the oracle, (2) permuting the graphs of the batch permutes the

@@ -180,6 +180,37 @@ def test_projection_matches_reference_camera():
     assert np.allclose(xy, synth.project_norm(wcT, pts), atol=1e-9)
 
 
+def test_batched_pose_algebra_matches_the_scene_functions():
+    """cns_b200/sim_device.py (batched torch, fp64) vs the per-scene numpy functions of synth.py."""
+    from cns_b200 import sim_device as sd
+    rng = np.random.default_rng(11)
+    B = 64
+    cur = np.stack([synth.sample_initial_pose(rng) for _ in range(B)])
+    tar = np.stack([synth.sample_target_pose(rng) for _ in range(B)])
+    n = rng.integers(4, 40, B)
+    pts = [synth.sample_points(rng, k) for k in n]
+    n = np.array([len(p) for p in pts])
+    tc, tt = torch.from_numpy(cur), torch.from_numpy(tar)
+    P, scene = torch.from_numpy(np.concatenate(pts)), torch.from_numpy(np.repeat(np.arange(B), n))
+    xy = sd.project_norm(tc, P, scene).numpy()
+    ref = np.concatenate([synth.project_norm(cur[k], pts[k]) for k in range(B)])
+    assert np.abs(xy - ref).max() < 1e-12
+    v = sd.pbvs_straight(tc, tt).numpy()
+    vref = np.stack([synth.pbvs_straight(cur[k], tar[k]) for k in range(B)])
+    assert np.abs(v - vref).max() < 1e-9
+    vel = rng.normal(size=(B, 6))
+    nxt = sd.integrate(tc, torch.from_numpy(vel)).numpy()
+    nref = np.stack([synth.integrate(cur[k], vel[k]) for k in range(B)])
+    assert np.abs(nxt - nref).max() < 1e-9
+    ang, mm = sd.pose_error(tc, tt)
+    eref = np.array([synth.pose_error(cur[k], tar[k]) for k in range(B)])
+    assert np.abs(ang.numpy() - eref[:, 0]).max() < 1e-7 and np.abs(mm.numpy() - eref[:, 1]).max() < 1e-7
+    # rotations close to pi and close to 0 round-trip through log / exp
+    w = torch.tensor([[np.pi - 1e-7, 0, 0], [0, 1e-9, 0], [1.2, -2.0, 0.4], [0, 0, -(np.pi - 1e-6)]], dtype=torch.float64)
+    R = sd.so3_exp(w)
+    assert float((sd.so3_exp(sd.so3_log(R)) - R).abs().max()) < 1e-7
+
+
 def test_closed_loop_servo_converges(state_dict):
     """Pretrained weights + oracle forward drive a simulated camera to its target pose: this only
     happens when edge direction, softmax, GraphNorm and GRU semantics are the reference's."""

@@ -41,6 +41,10 @@ def get_args():
     ap.add_argument("--max-points", type=int, default=512)
     ap.add_argument("--fused", action="store_true", help="fused loss and clip+AdamW kernels")
     ap.add_argument("--seed", type=int, default=2022)
+    ap.add_argument("--device-env", action="store_true",
+                    help="keep the closed-loop scenes on the GPU (cns_b200.sim_device.DeviceSceneBatch): batched projection, "
+                         "supervisor, pose integration and per-frame graph masking instead of B python scenes per step")
+    ap.add_argument("--refresh-every", type=int, default=400, help="--device-env: new scene geometry every this many frames")
     return ap.parse_args()
 
 
@@ -96,7 +100,12 @@ def main():
         net.load_state_dict(ckpt.read_state_dict(args.load))
     net.train()
     stepper = TBPTTStepper(net, fused=args.fused, lr=args.init_lr, weight_decay=args.weight_decay)
-    envs = SceneBatch(args.batch_size, np.random.default_rng(args.seed + rank), args.max_points)
+    if args.device_env:
+        from cns_b200.sim_device import DeviceSceneBatch
+        envs = DeviceSceneBatch(args.batch_size, np.random.default_rng(args.seed + rank), dev, args.max_points,
+                                refresh_every=args.refresh_every)
+    else:
+        envs = SceneBatch(args.batch_size, np.random.default_rng(args.seed + rank), args.max_points)
     window = args.long_steps if args.long else 8
     best, not_improved = float("inf"), 0
     for epoch in range(args.epochs):
@@ -106,7 +115,7 @@ def main():
 
             def rollout():
                 for _ in range(window):
-                    data = envs.get(dev)
+                    data = envs.observe() if args.device_env else envs.get(dev)
                     frames.append(data)
                     yield data
                     # closed loop: drive the simulators with the predicted velocity, 10 % with the teacher
@@ -115,7 +124,7 @@ def main():
                         vel = net.postprocess((pred[0].detach(), pred[1].detach()), data)
                         n_gt = max(1, int(vel.shape[0] * 0.1))
                         vel[:n_gt] = data.vel[:n_gt].to(vel)
-                    envs.feedback((vel * 2).cpu().numpy())
+                    envs.feedback(vel * 2 if args.device_env else (vel * 2).cpu().numpy())
             losses.append(float(stepper.step(rollout(), mean=args.long)) / (1 if args.long else window))
         mean_loss = float(np.mean(losses))
         if world > 1:
