@@ -269,7 +269,7 @@ pool_head_kernel(PoolHeadArgs p) {
 
   // first layers of both heads: thread = output channel
   float h0 = p.vec0_b[tid], h1 = p.nrm0_b[tid];
-#pragma unroll 4
+#pragma unroll 16     // 32 independent weight loads in flight: at batch 1 this loop is pure L2 latency
   for (int k = 0; k < H; ++k) {
     float x = xs[k];
     h0 = fmaf(x, p.vec0_t[k * H + tid], h0);

@@ -105,5 +105,8 @@ struct cns_handle {
   void* stage_dev;  size_t stage_dev_bytes;
   // recurrent hidden state of cns_servo_step_host (two ping-pong device buffers inside stage_dev)
   int servo_valid; int servo_cur; long long servo_nc;
+  // cns_servo_step_host keeps the target-side results while consecutive frames show the same target (host copy of the
+  // target arrays = the key)
+  struct cns_target_cache* servo_tcache; void* servo_tkey; size_t servo_tkey_bytes;
   const float* P(int id) const { return raw + raw_off[id]; }
 };

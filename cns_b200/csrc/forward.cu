@@ -489,6 +489,30 @@ int cns_servo_step_host(cns_handle* h, const cns_batch* bh, int reset_hidden, fl
   float* out_d = (float*)(db + in_bytes);                 // vec (B,6) | vel (B,6) | nrm (B,1)
   float* hid[2] = {(float*)(db + in_bytes + out_bytes), (float*)(db + in_bytes + out_bytes + hid_bytes)};
   void* ws = db + in_bytes + out_bytes + 2 * hid_bytes;
+  {
+    // same target as the previous frame (the usual case in a servo loop)?  then what depends on the target alone is reused
+    const size_t kb[4] = {(size_t)N * 2 * sizeof(float), (size_t)N * 2 * sizeof(float), (size_t)C * sizeof(int64_t),
+                          (size_t)B * sizeof(int64_t)};
+    const void* kp[4] = {bh->x_tar, bh->pos_tar, bh->cluster_centers, bh->num_clusters};
+    const size_t key_bytes = kb[0] + kb[1] + kb[2] + kb[3];
+    bool same = h->servo_tcache != nullptr && h->servo_tkey_bytes == key_bytes &&
+                h->servo_tcache->precision == h->precision && h->servo_tcache->weights_version == h->weights_version &&
+                h->servo_tcache->n_clusters == C && h->servo_tcache->n_graphs == B;
+    size_t o = 0;
+    for (int i = 0; i < 4 && same; ++i) { same = memcmp((char*)h->servo_tkey + o, kp[i], kb[i]) == 0; o += kb[i]; }
+    if (!same) {
+      if (h->servo_tcache) { cns_target_cache_destroy(h->servo_tcache); h->servo_tcache = nullptr; }
+      free(h->servo_tkey);
+      h->servo_tkey = malloc(key_bytes > 0 ? key_bytes : 1);
+      h->servo_tkey_bytes = key_bytes;
+      CNS_REQUIRE(h->servo_tkey != nullptr, "out of host memory");
+      o = 0;
+      for (int i = 0; i < 4; ++i) { memcpy((char*)h->servo_tkey + o, kp[i], kb[i]); o += kb[i]; }
+      rc = cns_target_cache_create(h, &d, s, &h->servo_tcache);
+      if (rc != CNS_OK) { h->servo_tkey_bytes = 0; return rc; }
+    }
+    d.target_cache = h->servo_tcache;
+  }
   const bool carry = h->servo_valid && !reset_hidden && h->servo_nc == C;
   const float* hin = carry ? hid[h->servo_cur] : nullptr;
   float* hout = hid[h->servo_cur ^ 1];

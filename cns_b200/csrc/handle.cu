@@ -274,6 +274,8 @@ int cns_destroy(cns_handle* h) {
   free_bwd_pack(h);
   if (h->tc_w_img) cudaFree(h->tc_w_img);
   if (h->pk.tc_node_base) cudaFree(h->pk.tc_node_base);
+  if (h->servo_tcache) cns_target_cache_destroy(h->servo_tcache);
+  free(h->servo_tkey);
   if (h->stage_host) cudaFreeHost(h->stage_host);
   if (h->stage_dev) cudaFree(h->stage_dev);
   delete h;
