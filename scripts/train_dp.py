@@ -14,7 +14,8 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-per_rank, n_frames, npts = 32, 4, 256
+per_rank, n_frames, npts = (int(os.environ.get(k, d)) for k, d in (('PER_RANK', 32), ('FRAMES', 4), ('NPTS', 256)))
+check = os.environ.get('CHECK', '1') == '1'       # compare against a single-process pass over the whole global batch
 rng = np.random.default_rng(5); np.random.seed(5)          # identical scenes on every rank
 base = [synth.Scene(rng, npts) for _ in range(4)]
 scenes = [synth.Scene(rng, npts, generator=base[i % 4].generator, points=base[i % 4].points, tar_wcT=base[i % 4].tar_wcT)
@@ -33,7 +34,7 @@ st.bucket.zero()
 loss, _ = st.window_loss(mine)
 loss.backward(); st.bucket.rebind(); st.bucket.allreduce_mean()
 g_dp = st.bucket.flat.clone()
-if rank == 0:
+if rank == 0 and check:
     ref = GraphVS(2, 2, 128).to(dev); ref.load_state_dict(sd); ref.train()
     sr = TBPTTStepper(ref)
     sr.bucket.zero()
