@@ -98,6 +98,8 @@ int l1_complete_verify(const L1CompleteArgs& a, cudaStream_t s) {
 // ---- max aggregation over a complete graph ---------------------------------------------------------------
 __device__ __forceinline__ float sigmoid_(float x) { return 1.f / (1.f + expf(-x)); }
 
+constexpr int ECD_REG_ROWS = 32;   // graphs up to this many cluster rows are held in registers (one pass over [P|Q])
+
 template <int F, int MODE, bool GN>
 __global__ void __launch_bounds__(F)
 edgeconv_dense_kernel(EdgeConvDenseArgs p) {
@@ -108,6 +110,62 @@ edgeconv_dense_kernel(EdgeConvDenseArgs p) {
   const uint8_t* __restrict__ mask = p.mask;
   const float* __restrict__ pq = p.pq;
   auto alive = [&](int r) { return mask == nullptr || mask[r] != 0; };
+
+  // the candidate (four operand streams per row) was measured faster streaming at full occupancy (22 vs 27 us)
+  if (MODE != EC_CANDIDATE && n <= ECD_REG_ROWS) {
+    // the usual case (C ~ 0.8 sqrt(N) clusters per graph): every [P|Q] value of the graph is loaded exactly once,
+    // all loads in flight together, and max / GraphNorm / gates run on registers
+    float pv[ECD_REG_ROWS], qv[ECD_REG_ROWS];
+    unsigned am = 0;
+#pragma unroll
+    for (int i = 0; i < ECD_REG_ROWS; ++i) {
+      const bool in = i < n;
+      if (in && alive(beg + i)) am |= 1u << i;
+      pv[i] = in ? pq[(size_t)(beg + i) * 2 * F + c] : 0.f;
+      qv[i] = in ? pq[(size_t)(beg + i) * 2 * F + F + c] : 0.f;
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < ECD_REG_ROWS; ++i)
+      if (am & (1u << i)) m = fmaxf(m, qv[i]);
+#pragma unroll
+    for (int i = 0; i < ECD_REG_ROWS; ++i) pv[i] = (am & (1u << i)) ? pv[i] + m : 0.f;      // conv
+    if (MODE == EC_PLAIN) {
+      if (!GN) {
+#pragma unroll
+        for (int i = 0; i < ECD_REG_ROWS; ++i)
+          if (i < n) p.out[(size_t)(beg + i) * F + c] = pv[i];
+        return;
+      }
+      const float inv_n = 1.f / (float)n;
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < ECD_REG_ROWS; ++i)
+        if (i < n) sum += pv[i];
+      const float shift = sum * inv_n * p.gn_mean_scale[c];
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < ECD_REG_ROWS; ++i)
+        if (i < n) { const float o = pv[i] - shift; sq = fmaf(o, o, sq); }
+      const float rstd = 1.f / sqrtf(sq * inv_n + 1e-5f);
+      const float w = p.gn_weight[c], b = p.gn_bias[c];
+#pragma unroll
+      for (int i = 0; i < ECD_REG_ROWS; ++i)
+        if (i < n) p.gn_out[(size_t)(beg + i) * F + c] = fmaxf(fmaf(w * (pv[i] - shift), rstd, b), 0.f);
+    } else if (MODE == EC_GATES) {
+#pragma unroll
+      for (int i = 0; i < ECD_REG_ROWS; ++i) {
+        if (i >= n) break;
+        const int row = beg + i;
+        const float gt = sigmoid_(pv[i]);
+        if (c < 128) p.hr[(size_t)row * 128 + c] = (p.h ? p.h[(size_t)row * 128 + c] : 0.f) * gt;
+        else p.u[(size_t)row * 128 + c - 128] = gt;
+      }
+    }
+    return;
+  }
+
+  // larger graphs: stream the rows (L2-resident after the first pass)
   // column max of Q over the node set
   float m = -INFINITY;
   int r = beg;
