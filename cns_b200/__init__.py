@@ -9,5 +9,7 @@ from .graph_gen import GraphGenerator
 from .midend import CameraIntrinsic, Correspondence, Midend
 from .model import GraphVS
 from .servo import BatchedServo
+from .stop_policy import BatchedPixelStop, ErrorHoldingStopPolicy, PixelStopPolicy, align_matches
 
-__all__ = ["Batch", "GraphData", "GraphGenerator", "CameraIntrinsic", "Correspondence", "Midend", "GraphVS", "BatchedServo"]
+__all__ = ["Batch", "GraphData", "GraphGenerator", "CameraIntrinsic", "Correspondence", "Midend", "GraphVS", "BatchedServo",
+           "BatchedPixelStop", "ErrorHoldingStopPolicy", "PixelStopPolicy", "align_matches"]

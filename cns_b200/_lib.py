@@ -80,6 +80,9 @@ def _declare(lib):
         "cns_frame_mask": (i32, [vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, sz, vp]),
         "cns_graph_mask_workspace_bytes": (sz, [i64, i64, i64]),
         "cns_graph_mask": (i32, [vp, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, i64, vp, vp, vp, sz, vp]),
+        "cns_align_matches": (i32, [vp, i64, vp, i64, i64, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp, vp, sz, vp]),
+        "cns_pixel_stop_workspace_bytes": (sz, [i64]),
+        "cns_pixel_stop_error": (i32, [vp, vp, vp, vp, vp, i64, i64, C.c_float, C.c_float, vp, vp, vp, vp, vp, sz, vp]),
         "cns_label_nearest": (i32, [vp, vp, i64, vp, vp, vp, vp]),
         "cns_ap_workspace_bytes": (sz, [i64, i64, i64, i32]),
         "cns_affinity_propagation": (i32, [vp, vp, vp, vp, i64, i64, i64, C.c_double, i32, i32, vp, vp, vp, vp, sz, vp]),

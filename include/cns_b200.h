@@ -252,6 +252,35 @@ int cns_frame_mask(const int64_t* member_order, const int32_t* member_ptr, const
                    int64_t n_clusters, int64_t* e01_j, int64_t* e01_i, uint8_t* cluster_mask, int32_t* clu_rowptr,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the steps either side of the graph path in the servo loop --------------------------------
+ *
+ * cns_align_matches replaces Classic._align_cur_to_tar (cns/frontend/classic.py:142-148) followed by
+ * CameraIntrinsic.pixel_to_norm_camera_plane (cns/utils/perception.py:66-68, called by Midend.get_graph_data,
+ * cns/midend/corr2graph.py:11-22) and the float32 cast of GraphGenerator.get_data (graph_gen.py:257-263):
+ *   cur_pos (n_cur,2) f32 pixel coordinates of the detected keypoints; matches (n_matches,2) int64 rows
+ *   [target index, current index] (a later row overrides an earlier one with the same target index, like numpy's
+ *   fancy assignment) -> cur_xy (n_tar,2) f32 normalized coordinates aligned with the target keypoints (unmatched
+ *   rows: pixel (0,0) normalized, as the reference) and valid (n_tar,) u8.  Bit-exact.  Out-of-range indices are
+ *   skipped and reported by the int at workspace[n_tar] != 0 after the call.  workspace: (n_tar + 1) int32. */
+int cns_align_matches(const float* cur_pos, int64_t n_cur, const int64_t* matches, int64_t n_matches, int64_t n_tar,
+                      double fx, double fy, double cx, double cy, float* cur_xy, uint8_t* valid,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* cns_pixel_stop_error replaces PixelStopPolicy.calculate_error (cns/benchmark/stop_policy.py:86-126) for
+ * n_graphs scenes at once (one CTA per scene; node_ptr (n_graphs+1,) int32 keypoint offsets, NULL = one scene):
+ * witness counts / decayed weights (device state, (n_nodes,) int32 / f32, zero-initialised by the caller) are
+ * updated, the weighted keypoint errors are cut at their 90th percentile and the weighted mean of the rest is
+ * written to err_out (n_graphs,) f32.  Every float32 operation follows numpy's order (np.linalg.norm,
+ * np.percentile "linear" with a float32 virtual index, pairwise np.sum), so the result is bit-identical with the
+ * reference running on numpy 2.x.  reset_flags (n_graphs,) u8 or NULL: scenes whose state is cleared before this
+ * frame (PixelStopPolicy.reset).  A scene without a visible keypoint gets NaN (the reference raises).
+ * n_valid_out (n_graphs,) int32 or NULL.  workspace: cns_pixel_stop_workspace_bytes(n_nodes). */
+size_t cns_pixel_stop_workspace_bytes(int64_t n_nodes);
+int cns_pixel_stop_error(const float* pos_cur, const float* pos_tar, const uint8_t* node_mask, const int32_t* node_ptr,
+                         const uint8_t* reset_flags, int64_t n_nodes, int64_t n_graphs, float decay, float maximum,
+                         float* weight, int32_t* witness, float* err_out, int32_t* n_valid_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* Affinity Propagation message passing (the clustering behind cluster_points, graph_gen.py:104-106 ->
  * sklearn AffinityPropagation(damping=0.9)) for a batch of G problems, bit-exact in fp64 with
  * sklearn's loop.  S (sum n_g^2) is the similarity matrix as sklearn prepares it (median preference on

@@ -48,6 +48,31 @@ def percentile_f32(err, pct=90):
     return F32(a + F32(d * g))
 
 
+def pairwise_sum_f32(a):
+    """What `np.sum` of a contiguous float32 vector computes (numpy's pairwise_sum: leaves of <= 128 elements
+    with 8 running sums, halves split at a multiple of 8).  Restated for the device kernel, which follows it;
+    pinned bitwise against np.sum in tests/test_stop_policy_cpu.py.  PixelStopOracle itself just calls np.sum."""
+    a = np.asarray(a, dtype=np.float32)
+    n = len(a)
+    if n < 8:
+        r = F32(0)
+        for x in a:
+            r = F32(r + x)
+        return r
+    if n <= 128:
+        r = a[:8].copy()
+        full = n - n % 8
+        for i in range(8, full, 8):
+            r = r + a[i:i + 8]                    # eight independent float32 running sums
+        res = F32(F32(F32(r[0] + r[1]) + F32(r[2] + r[3])) + F32(F32(r[4] + r[5]) + F32(r[6] + r[7])))
+        for x in a[full:]:
+            res = F32(res + x)
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return F32(pairwise_sum_f32(a[:n2]) + pairwise_sum_f32(a[n2:]))
+
+
 class PixelStopOracle(object):
     def __init__(self, decay=0.95):
         self.decay = decay
