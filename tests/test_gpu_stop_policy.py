@@ -105,3 +105,17 @@ def test_pixel_stop_requires_cuda():
     with pytest.raises(_lib.CnsError):
         PixelStopPolicy(0.8, device="cpu").calculate_error(
             types.SimpleNamespace(pos_cur=torch.zeros(3, 2), pos_tar=torch.zeros(3, 2), node_mask=torch.ones(3, dtype=torch.bool)))
+
+
+def test_batched_closed_loop_servo_stops_at_the_target():
+    """Device scenes -> graph masking -> GraphVS (f16, hidden carried) -> camera motion, every scene until its
+    PixelStopPolicy fires: the loop must end near the target pose (scripts/servo_closed_loop.py)."""
+    import importlib.util
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("servo_closed_loop", os.path.join(root, "scripts", "servo_closed_loop.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    r = mod.run(B=24, N=128, precision="f16", max_frames=500, layouts=6, seed=5)
+    assert r["stopped"] >= 20, r
+    assert r["final_rot_deg_p50_p90_max"][0] < 0.5 and r["final_trans_mm_p50_p90_max"][0] < 5.0, r
