@@ -212,7 +212,7 @@ def main():
     n_edges = [int(b.l0_to_l1_edge_index_j_cur.numel()) for b in host]
     h2d = sum(v.numel() * v.element_size() for k, v in host[0].items()
               if isinstance(v, torch.Tensor) and k in net.INPUT_FIELDS)
-    # per-batch tensors the forward actually reads on this path (the target side comes from the target cache)
+    # per-batch tensors the forward reads
     read_per_step = sum(host[0][k].numel() * host[0][k].element_size() for k in (
         "x_cur", "pos_cur", "pos_tar", "x_tar", "l0_to_l1_edge_index_j_cur", "l0_to_l1_edge_index_i_cur",
         "l1_dense_edge_index_cur", "l1_dense_edge_index_tar", "cluster_mask"))
@@ -232,11 +232,10 @@ def main():
     handle = net._handle(dev)
     with torch.no_grad():
         # ---------------- device-resident throughput ("value") + live kernel timing ----------------
-        # the rotating batches are the same scenes at successive frames: what depends on the targets alone is built
-        # once (GraphVS.build_target_cache), as the reference's Midend keeps one GraphGenerator per target image
-        tcache = net.build_target_cache(resident[0])
+        # the stateless call of the reference API, GraphVS.forward(Batch, hidden=None): nothing is kept from one
+        # step to the next
         for i in range(args.warmup):
-            net(resident[i % N_ROTATE], None, target_cache=tcache)
+            net(resident[i % N_ROTATE], None)
         barrier()
         sampler = ClockSampler(local)
         sampler.start()
@@ -244,7 +243,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.steps):
-            net(resident[i % N_ROTATE], None, target_cache=tcache)
+            net(resident[i % N_ROTATE], None)
         e1.record()
         barrier()
         kms, kn, launches = C.c_float(), C.c_int(), C.c_longlong()
@@ -252,6 +251,22 @@ def main():
         sampler.stop_flag = True
         total_ms = max_over_ranks(e0.elapsed_time(e1))
         value = args.graphs * world * args.steps / (total_ms * 1e-3)
+
+        # the same loop with a per-target cache (GraphVS.build_target_cache): the rotating batches are the same
+        # scenes at successive frames, and what depends on the targets alone (per-cluster attention term, cluster
+        # positions, tile packing) is built once, as the reference's Midend keeps one GraphGenerator per target
+        # image.  Reported beside `value`, not as `value`.
+        tcache = net.build_target_cache(resident[0])
+        for i in range(args.warmup):
+            net(resident[i % N_ROTATE], None, target_cache=tcache)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(args.steps):
+            net(resident[i % N_ROTATE], None, target_cache=tcache)
+        c1.record()
+        barrier()
+        cached_ms = max_over_ranks(c0.elapsed_time(c1))
 
         # ---------------- end to end: pinned host GraphData in, velocities out ----------------------
         for i in range(args.warmup):
@@ -329,7 +344,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "f16": "f16", "bf16": "bf16"}[args.precision], "data": "synthetic",
         "config": {"workload": workload, "missing_keypoints": MISSING, "weights": "checkpoints/cns.pth",
-                   "hidden": "None (first frame)", "target_cache": "built once for the scenes' targets (GraphVS.build_target_cache)", "l2": "inputs rotate over %d distinct resident batches: a step reads %.0f MB of its batch (keypoints, "
+                   "hidden": "None (first frame)", "call": "GraphVS.forward(Batch, None), stateless (no target cache)", "l2": "inputs rotate over %d distinct resident batches: a step reads %.0f MB of its batch (keypoints, "
                          "keypoint->cluster edges, the cluster edge lists being verified), %.0f MB pass before a batch "
                          "repeats > L2 (126 MB)" % (N_ROTATE, read_per_step / 1e6, N_ROTATE * read_per_step / 1e6),
                    "graphs_per_gpu": args.graphs},
@@ -344,6 +359,10 @@ def main():
                                "api": "GraphVS.forward(Batch.to(device)): the whole prebuilt host Batch is copied "
                                       "every step (DevicePrefetcher), read-back one step behind"}},
         "gpu_launches": int(launches.value),
+        "with_target_cache": {"value": args.graphs * world * args.steps / (cached_ms * 1e-3), "unit": "graphs/s",
+                              "ms_per_step": cached_ms / args.steps,
+                              "note": "same loop with GraphVS.build_target_cache (per-target terms built once outside "
+                                      "the timed region); not the headline"},
         "roofline": {"kernel": "enc_edge (%s)" % args.precision, "bound": "tensor", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": pk_src + " bf16 sustained", "kernel_ms": kernel_ms,

@@ -108,5 +108,7 @@ struct cns_handle {
   // cns_servo_step_host keeps the target-side results while consecutive frames show the same target (host copy of the
   // target arrays = the key)
   struct cns_target_cache* servo_tcache; void* servo_tkey; size_t servo_tkey_bytes;
+  // fork/join pair for work that is independent of the index preparation (per-cluster encoder terms), created lazily
+  cudaStream_t side_stream; cudaEvent_t side_fork, side_join, side_join2;
   const float* P(int id) const { return raw + raw_off[id]; }
 };

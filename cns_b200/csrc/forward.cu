@@ -115,6 +115,30 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
 #define RUN(expr) if ((rc = (expr)) != CNS_OK) return rc;
 
   CNS_CUDA_CHECK(cudaMemsetAsync(f.err, 0, 64 * sizeof(int), s));
+  // ---- per-cluster encoder terms (target side only) ------------------------------------------
+  // independent of the index preparation below: on batches large enough to fill the GPU they run on a forked
+  // stream beside the (single-CTA, latency-bound) scans and rejoin before the edge kernel
+  EncPreArgs pre{};
+  pre.n_clusters = C; pre.x_tar = b->x_tar; pre.pos_tar = b->pos_tar; pre.centers = b->cluster_centers;
+  pre.node_graph = b->node_graph; pre.w_in = h->P(P_IN_W); pre.b_in = h->P(P_IN_B); pre.lin_dst_t = pk.lin_dst_t;
+  if (h->precision != CNS_PREC_FP32) { pre.lin_dst_t = pk.tc_lin_dst_t; pre.a_bias = pk.tc_adst_bias; }   // a_dst := A0 (a_dst + b_pos1) + b_attn0
+  pre.a_dst = f.a_dst; pre.pos_clu = f.pos_clu; pre.clu_graph = f.clu_graph;
+  const bool fork_pre = !tcache && (C > PREP_SMALL_MAX || B > PREP_SMALL_MAX);
+  if (fork_pre) {
+    if (!h->side_stream) {
+      CNS_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+      CNS_CUDA_CHECK(cudaEventCreateWithFlags(&h->side_fork, cudaEventDisableTiming));
+      CNS_CUDA_CHECK(cudaEventCreateWithFlags(&h->side_join, cudaEventDisableTiming));
+      CNS_CUDA_CHECK(cudaEventCreateWithFlags(&h->side_join2, cudaEventDisableTiming));
+    }
+    CNS_CUDA_CHECK(cudaEventRecord(h->side_fork, s));
+    CNS_CUDA_CHECK(cudaStreamWaitEvent(h->side_stream, h->side_fork, 0));
+    RUN(enc_cluster_pre(pre, h->side_stream));
+    CNS_CUDA_CHECK(cudaEventRecord(h->side_join, h->side_stream));
+  }
+  // graph pointers, whole-graph tiles and the hint verification feed the cluster-level backbone only: on the forked
+  // stream they run beside the edge kernel
+  cudaStream_t s2 = fork_pre ? h->side_stream : s;
   // ---- index preparation ------------------------------------------------------------------
   const int64_t cur_stride = b->l1_cur_stride ? b->l1_cur_stride : b->n_e11_cur;
   const int64_t tar_stride = b->l1_tar_stride ? b->l1_tar_stride : b->n_e11_tar;
@@ -148,8 +172,8 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     if (!b->clu_rowptr || sv) RUN(sorted_rowptr(b->l0_to_l1_i, b->n_e01, C, f.clu_rowptr, f.err, s));
     if (tcache && (!fused || tcache->has_tiles)) {
       f.graph_ptr = tcache->graph_ptr; f.tile_graph = tcache->tile_graph; f.n_tiles = tcache->n_tiles;
-    } else if (fused) { RUN(graph_tiles(b->num_clusters, B, f.graph_ptr, f.tile_graph, f.n_tiles, f.err, s)); }
-    else { RUN(graph_ptr_from_counts(b->num_clusters, B, f.graph_ptr, f.gp_tmp, f.scan_scratch, s)); }
+    } else if (fused) { RUN(graph_tiles(b->num_clusters, B, f.graph_ptr, f.tile_graph, f.n_tiles, f.err, s2)); }
+    else { RUN(graph_ptr_from_counts(b->num_clusters, B, f.graph_ptr, f.gp_tmp, f.scan_scratch, s2)); }
     if (!dense_cur) RUN(csr_by_dst(b->l1_edge_cur, b->l1_edge_cur + cur_stride, b->n_e11_cur, C, f.cur_rowptr, f.cur_src, f.csr_ws, f.err, s));
     if (!dense_tar) RUN(csr_by_dst(b->l1_edge_tar, b->l1_edge_tar + tar_stride, b->n_e11_tar, C, f.tar_rowptr, f.tar_src, f.csr_ws, f.err, s));
   }
@@ -162,16 +186,13 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
       if (b->l1_edge_cur) { la.cur_j = b->l1_edge_cur; la.cur_i = b->l1_edge_cur + cur_stride; la.n_e11_cur = b->n_e11_cur; }
     }
     if (dense_tar && b->l1_edge_tar) { la.tar_j = b->l1_edge_tar; la.tar_i = b->l1_edge_tar + tar_stride; la.n_e11_tar = b->n_e11_tar; }
-    RUN(l1_complete_verify(la, s));
+    RUN(l1_complete_verify(la, s2));
   }
+  if (fork_pre) CNS_CUDA_CHECK(cudaEventRecord(h->side_join2, h->side_stream));
 
   // ---- encoder ----------------------------------------------------------------------------
-  EncPreArgs pre{};
-  pre.n_clusters = C; pre.x_tar = b->x_tar; pre.pos_tar = b->pos_tar; pre.centers = b->cluster_centers;
-  pre.node_graph = b->node_graph; pre.w_in = h->P(P_IN_W); pre.b_in = h->P(P_IN_B); pre.lin_dst_t = pk.lin_dst_t;
-  if (h->precision != CNS_PREC_FP32) { pre.lin_dst_t = pk.tc_lin_dst_t; pre.a_bias = pk.tc_adst_bias; }   // a_dst := A0 (a_dst + b_pos1) + b_attn0
-  pre.a_dst = f.a_dst; pre.pos_clu = f.pos_clu; pre.clu_graph = f.clu_graph;
-  if (!tcache) RUN(enc_cluster_pre(pre, s));
+  if (fork_pre) { CNS_CUDA_CHECK(cudaStreamWaitEvent(s, h->side_join, 0)); }
+  else if (!tcache) RUN(enc_cluster_pre(pre, s));
 
   EncEdgeArgs ee{};
   ee.n_e01 = b->n_e01; ee.n_clusters = C; ee.n_slots = f.n_slots;
@@ -206,6 +227,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   }
 
   // ---- backbone ---------------------------------------------------------------------------
+  if (fork_pre) CNS_CUDA_CHECK(cudaStreamWaitEvent(s, h->side_join2, 0));
   auto pq_linear = [&](const float* x1, const float* x2, const float* wt, const float* wp, const float* bias,
                        int n_out, unsigned char* const* img, int k_img) {
     if (tc) {

@@ -276,6 +276,7 @@ int cns_destroy(cns_handle* h) {
   if (h->pk.tc_node_base) cudaFree(h->pk.tc_node_base);
   if (h->servo_tcache) cns_target_cache_destroy(h->servo_tcache);
   free(h->servo_tkey);
+  if (h->side_stream) { cudaStreamDestroy(h->side_stream); cudaEventDestroy(h->side_fork); cudaEventDestroy(h->side_join); cudaEventDestroy(h->side_join2); }
   if (h->stage_host) cudaFreeHost(h->stage_host);
   if (h->stage_dev) cudaFree(h->stage_dev);
   delete h;
