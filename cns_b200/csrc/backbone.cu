@@ -80,6 +80,10 @@ linear_kernel(LinearArgs p) {
       v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
     }
     if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (p.relu_gate) {
+      const float4 g = *reinterpret_cast<const float4*>(p.relu_gate + m * p.n_out + n);
+      v.x = g.x > 0.f ? v.x : 0.f; v.y = g.y > 0.f ? v.y : 0.f; v.z = g.z > 0.f ? v.z : 0.f; v.w = g.w > 0.f ? v.w : 0.f;
+    }
     *reinterpret_cast<float4*>(p.y + m * p.n_out + n) = v;
   }
 }

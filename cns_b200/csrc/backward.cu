@@ -50,7 +50,7 @@ constexpr int N_EBUF = 12;
 struct BwdBuffers {
   int* err; int* curT_rowptr; int* curT_dst; int* tarT_rowptr; int* tarT_dst; void* csr_ws;
   float *dx2, *dz, *dgn, *dconv, *dpq, *dxk, *dxg, *dh_acc, *du, *dconvk, *dconvg, *dx1, *dxclu, *dpre, *cat, *dcat,
-      *dclu, *d_adst, *a_dst, *d_xtc, *xtc, *fe_c, *zeros_h, *dhid, *dgate, *gn_partial, *G, *Gp, *gb, *dw_partial,
+      *dclu, *d_adst, *a_dst, *d_xtc, *xtc, *fe_c, *zeros_h, *dhid, *dgate, *gn_partial, *G, *Gp, *gb, *dw_partial, *cs_partial,
       *small_partial;
   float* E[N_EBUF]; float* FE; float* DP;
   int small_slabs;
@@ -76,6 +76,7 @@ static void carve_bwd(Arena& ar, const cns_batch* b, BwdBuffers& w) {
   w.gn_partial = ar.take<float>(B * 3 * H);
   w.G = ar.take<float>(512 * 256); w.Gp = ar.take<float>(512 * 2); w.gb = ar.take<float>(512);
   w.dw_partial = ar.take<float>(DW_PARTIAL_FLOATS);
+  w.cs_partial = ar.take<float>(592 * 128);       // dw_gemm: slabs * na <= 592 * 128
   w.small_slabs = (int)((std::max<int64_t>(std::max<int64_t>(E, C), B) + 127) / 128) + 1;
   w.small_partial = ar.take<float>((size_t)w.small_slabs * 512 * 4);   // n*q <= 512*2 or 128*8
   for (int i = 0; i < N_EBUF; ++i) w.E[i] = ar.take<float>((size_t)E * H + 4);
@@ -100,18 +101,19 @@ int backward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, con
 
   // ---- helpers ---------------------------------------------------------------------------------
   auto lin = [&](const float* x, int k, const float* wt, int n_out, const float* bias, const float* residual, int relu,
-                 int64_t m, float* y) {
+                 int64_t m, float* y, const float* relu_gate = nullptr) {
     LinearArgs la{};
     la.m = m; la.k1 = k; la.k2 = 0; la.n_out = n_out; la.x1 = x; la.wt = wt; la.bias = bias; la.residual = residual;
-    la.relu = relu; la.y = y;
+    la.relu = relu; la.relu_gate = relu_gate; la.y = y;
     return linear(la, s);
   };
   auto dwg = [&](const float* a, int lda, int na, const float* b0, int ldb0, int tiles0, const float* b1, int ldb1, int nb,
-                 int64_t m, float* out, int ld_out, float scale, int accumulate) {
+                 int64_t m, float* out, int ld_out, float scale, int accumulate, float* colsum_out = nullptr) {
     DwGemmArgs d{};
     d.m = m; d.na = na; d.nb = nb; d.a = a; d.lda = lda; d.b0 = b0; d.ldb0 = ldb0; d.b_tiles0 = tiles0; d.b1 = b1; d.ldb1 = ldb1;
     d.out = out; d.ld_out = ld_out; d.scale = scale; d.accumulate = accumulate; d.partial = w.dw_partial;
     d.max_slabs = (int)(DW_PARTIAL_FLOATS / ((size_t)na * nb));
+    d.colsum_out = colsum_out; d.colsum_partial = w.cs_partial;     // bias gradient from the same pass over `a`
     return dw_gemm(d, s);
   };
   auto dws = [&](const float* a, int lda, int n, const float* sm, int lds, int q, int64_t m, float* out, int ld_out,
@@ -160,10 +162,8 @@ int backward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, con
       RUN(dws(hid_n, 2 * H, H, d_nrm, 1, 1, B, G(P_NRM1_W), H, 1, 1));
       RUN(colsum(d_nrm, 1, 1, B, G(P_NRM1_B), 1));
     }
-    RUN(dwg(dhid_v, 2 * H, H, sv.x_scene, H, 1, nullptr, 0, H, B, G(P_VEC0_W), H, 1.f, 1));
-    RUN(colsum(dhid_v, 2 * H, H, B, G(P_VEC0_B), 1));
-    RUN(dwg(dhid_n, 2 * H, H, sv.x_scene, H, 1, nullptr, 0, H, B, G(P_NRM0_W), H, 1.f, 1));
-    RUN(colsum(dhid_n, 2 * H, H, B, G(P_NRM0_B), 1));
+    RUN(dwg(dhid_v, 2 * H, H, sv.x_scene, H, 1, nullptr, 0, H, B, G(P_VEC0_W), H, 1.f, 1, G(P_VEC0_B)));
+    RUN(dwg(dhid_n, 2 * H, H, sv.x_scene, H, 1, nullptr, 0, H, B, G(P_NRM0_W), H, 1.f, 1, G(P_NRM0_B)));
     RUN(dws(sv.x2, H, H, w.dgate, 1, 1, C, G(P_POOL_W), H, 1, 1));
     RUN(colsum(w.dgate, 1, 1, C, G(P_POOL_B), 1));
   }
@@ -176,8 +176,7 @@ int backward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, con
     int r;
     if ((r = ew1(EW_RELU_BWD, C * H, dy, y, nullptr, nullptr, w.dz, nullptr, nullptr))) return r;
     if ((r = lin(w.dz, H, h->P(fc_w), H, nullptr, nullptr, 0, C, w.dgn))) return r;                 // dgn = dz W_fc
-    if ((r = dwg(w.dz, H, H, gnb, H, 1, nullptr, 0, H, C, G(fc_w), H, 1.f, 1))) return r;
-    if ((r = colsum(w.dz, H, H, C, G(fc_b), 1))) return r;
+    if ((r = dwg(w.dz, H, H, gnb, H, 1, nullptr, 0, H, C, G(fc_w), H, 1.f, 1, G(fc_b)))) return r;
     GraphNormBwdArgs ga{};
     ga.n_graphs = B; ga.graph_ptr = sv.graph_ptr; ga.x = conv; ga.y = gnb; ga.dy = w.dgn; ga.stats = stats;
     ga.weight = h->P(bn_w); ga.mean_scale = h->P(bn_ms); ga.dx = w.dconv; ga.param_partial = w.gn_partial;
@@ -190,9 +189,8 @@ int backward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, con
     ea.in_rowptr = sv.cur_rowptr; ea.dpq = w.dpq;
     if ((r = edgeconv_max_bwd(ea, s))) return r;
     if ((r = lin(w.dpq, 2 * H, pq_bwd, H, nullptr, w.dz, 0, C, dx_out))) return r;                  // dx = dPQ W_pq + dz (skip)
-    if ((r = dwg(w.dpq, 2 * H, 2 * H, x, H, 1, nullptr, 0, H, C, w.G, H, 1.f, 0))) return r;
+    if ((r = dwg(w.dpq, 2 * H, 2 * H, x, H, 1, nullptr, 0, H, C, w.G, H, 1.f, 0, w.gb))) return r;
     if ((r = dws(w.dpq, 2 * H, 2 * H, sv.pos_clu, 2, 2, C, w.Gp, 2, 0, 0))) return r;
-    if ((r = colsum(w.dpq, 2 * H, 2 * H, C, w.gb, 0))) return r;
     return unfold_edgeconv(w.G, w.Gp, w.gb, H, H, G(msg_w), G(msg_b), s);
   };
 
@@ -211,9 +209,8 @@ int backward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, con
     ea.in_rowptr = sv.cur_rowptr; ea.dpq = w.dpq;
     RUN(edgeconv_max_bwd(ea, s));
     RUN(lin(w.dpq, 2 * H, bp.k_bwd, 2 * H, nullptr, nullptr, 0, C, w.dxk));                        // (dx1_k | dhr)
-    RUN(dwg(w.dpq, 2 * H, 2 * H, sv.x1, H, 1, sv.hr, H, 2 * H, C, w.G, 2 * H, 1.f, 0));
+    RUN(dwg(w.dpq, 2 * H, 2 * H, sv.x1, H, 1, sv.hr, H, 2 * H, C, w.G, 2 * H, 1.f, 0, w.gb));
     RUN(dws(w.dpq, 2 * H, 2 * H, sv.pos_clu, 2, 2, C, w.Gp, 2, 0, 0));
-    RUN(colsum(w.dpq, 2 * H, 2 * H, C, w.gb, 0));
     RUN(unfold_edgeconv(w.G, w.Gp, w.gb, 2 * H, H, G(P_K_MSG_W), G(P_K_MSG_B), s));
   }
   RUN(gru_b(w.dxk, hin, sv.g, w.du, w.dconvg, dh_in, C, s));
@@ -223,9 +220,8 @@ int backward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, con
     ea.in_rowptr = sv.tar_rowptr; ea.dpq = w.dpq;
     RUN(edgeconv_max_bwd(ea, s));
     RUN(lin(w.dpq, 4 * H, bp.g_bwd, 2 * H, nullptr, nullptr, 0, C, w.dxg));                        // (dx1_g | dh_g)
-    RUN(dwg(w.dpq, 4 * H, 4 * H, sv.x1, H, 1, hin, H, 2 * H, C, w.G, 2 * H, 1.f, 0));
+    RUN(dwg(w.dpq, 4 * H, 4 * H, sv.x1, H, 1, hin, H, 2 * H, C, w.G, 2 * H, 1.f, 0, w.gb));
     RUN(dws(w.dpq, 4 * H, 4 * H, sv.pos_clu, 2, 2, C, w.Gp, 2, 0, 0));
-    RUN(colsum(w.dpq, 4 * H, 4 * H, C, w.gb, 0));
     RUN(unfold_edgeconv(w.G, w.Gp, w.gb, 2 * H, 2 * H, G(P_G_MSG_W), G(P_G_MSG_B), s));
   }
   if (d_hidden_in) {
@@ -240,8 +236,7 @@ int backward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, con
   // ---- encoder tail: x_clu = relu(out_enc([cur | tar - cur])) * mask (graph_vs.py:229-230) --------
   RUN(out_enc_bwd(0, C, sv.clu_feat, w.dxclu, sv.x_clu, b->cluster_mask, w.cat, w.dpre, nullptr, nullptr, s));
   RUN(lin(w.dpre, H, h->P(P_OUT_W), 2 * H, nullptr, nullptr, 0, C, w.dcat));
-  RUN(dwg(w.dpre, H, H, w.cat, 2 * H, 2, nullptr, 0, 2 * H, C, G(P_OUT_W), 2 * H, 1.f, 1));
-  RUN(colsum(w.dpre, H, H, C, G(P_OUT_B), 1));
+  RUN(dwg(w.dpre, H, H, w.cat, 2 * H, 2, nullptr, 0, 2 * H, C, G(P_OUT_W), 2 * H, 1.f, 1, G(P_OUT_B)));
   RUN(out_enc_bwd(1, C, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w.dcat, w.dclu, s));
 
   // ---- keypoint -> cluster attention, both sides (graph_vs.py:204-214) -----------------------------
@@ -276,34 +271,27 @@ int backward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, con
     sa.dy = w.dclu + (size_t)side * C * H; sa.dL = dL; sa.dV = dV;
     RUN(enc_softmax_bwd(sa, s));
     // attn_nn
-    RUN(dwg(dL, H, H, U, H, 1, nullptr, 0, H, E, G(P_ATT1_W), H, 1.f, 1));
-    RUN(colsum(dL, H, H, E, G(P_ATT1_B), 1));
-    RUN(lin(dL, H, h->P(P_ATT1_W), H, nullptr, nullptr, 0, E, tmp));                               // dU
-    RUN(ew1(EW_RELU_BWD, E * H, tmp, U, nullptr, nullptr, tmp, nullptr, nullptr));                // dU_pre
-    RUN(dwg(tmp, H, H, T, H, 1, nullptr, 0, H, E, G(P_ATT0_W), H, 1.f, 1));
-    RUN(colsum(tmp, H, H, E, G(P_ATT0_B), 1));
+    RUN(dwg(dL, H, H, U, H, 1, nullptr, 0, H, E, G(P_ATT1_W), H, 1.f, 1, G(P_ATT1_B)));
+    RUN(lin(dL, H, h->P(P_ATT1_W), H, nullptr, nullptr, 0, E, tmp, U));                            // dU_pre = (U > 0) dL A1
+    RUN(dwg(tmp, H, H, T, H, 1, nullptr, 0, H, E, G(P_ATT0_W), H, 1.f, 1, G(P_ATT0_B)));
     RUN(lin(tmp, H, h->P(P_ATT0_W), H, nullptr, nullptr, 0, E, dT));                               // dT
     // t = a_dst[i] - a_src + delta
     RUN(seg_sum_rows(dT, sv.clu_rowptr, C, w.d_adst, side, s));                                     // both sides accumulate
     RUN(dwg(dT, H, H, X, H, 1, nullptr, 0, H, E, G(P_LINSRC_W), H, -1.f, 1));                      // a_src = x lin_src^T
     RUN(dwg(dV, H, H, X, H, 1, nullptr, 0, H, E, G(P_LIN_W), H, 1.f, 1));                          // v = x lin^T
     RUN(lin(dV, H, h->P(P_LIN_W), H, nullptr, nullptr, 0, E, dX));
-    RUN(lin(dT, H, bp.neg_lin_src, H, nullptr, dX, 0, E, dX));                                     // dX = dV lin - dT lin_src
+    RUN(lin(dT, H, bp.neg_lin_src, H, nullptr, dX, 0, E, dX, X));                                  // dX = (X > 0)(dV lin - dT lin_src)
     RUN(ew1(EW_ADD, E * H, dT, dV, nullptr, nullptr, tmp, nullptr, nullptr));                      // dDelta
-    RUN(dwg(tmp, H, H, HP, H, 1, nullptr, 0, H, E, G(P_POS1_W), H, 1.f, 1));
-    RUN(colsum(tmp, H, H, E, G(P_POS1_B), 1));
-    RUN(lin(tmp, H, h->P(P_POS1_W), H, nullptr, nullptr, 0, E, dL));                               // dHP (reuse dL)
-    RUN(ew1(EW_RELU_BWD, E * H, dL, HP, nullptr, nullptr, dL, nullptr, nullptr));
+    RUN(dwg(tmp, H, H, HP, H, 1, nullptr, 0, H, E, G(P_POS1_W), H, 1.f, 1, G(P_POS1_B)));
+    RUN(lin(tmp, H, h->P(P_POS1_W), H, nullptr, nullptr, 0, E, dL, HP));                           // dHP_pre (reuse dL)
     RUN(dws(dL, H, H, w.DP, 4, 4, E, G(P_POS0_W), 4, 0, 1));
     RUN(colsum(dL, H, H, E, G(P_POS0_B), 1));
-    RUN(ew1(EW_RELU_BWD, E * H, dX, X, nullptr, nullptr, dX, nullptr, nullptr));                   // through in_enc relu
     RUN(dws(dX, H, H, w.FE, 2, 2, E, G(P_IN_W), 2, 0, 1));
     RUN(colsum(dX, H, H, E, G(P_IN_B), 1));
   }
   // cluster side: a_dst = xt_c lin_dst^T
   RUN(dwg(w.d_adst, H, H, w.xtc, H, 1, nullptr, 0, H, C, G(P_LINDST_W), H, 1.f, 1));
-  RUN(lin(w.d_adst, H, h->P(P_LINDST_W), H, nullptr, nullptr, 0, C, w.d_xtc));
-  RUN(ew1(EW_RELU_BWD, C * H, w.d_xtc, w.xtc, nullptr, nullptr, w.d_xtc, nullptr, nullptr));
+  RUN(lin(w.d_adst, H, h->P(P_LINDST_W), H, nullptr, nullptr, 0, C, w.d_xtc, w.xtc));
   RUN(dws(w.d_xtc, H, H, w.fe_c, 2, 2, C, G(P_IN_W), 2, 0, 1));
   RUN(colsum(w.d_xtc, H, H, C, G(P_IN_B), 1));
 #undef RUN

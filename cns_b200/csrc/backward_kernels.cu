@@ -33,6 +33,10 @@ dw_gemm_kernel(DwGemmArgs p, int rows_per_slab) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   const int lr = tid >> 4, lc = (tid & 15) * 8;   // loader: 16 rows x 16 threads x 8 floats
+  const bool want_cs = p.colsum_out != nullptr && tb == 0;
+  float cs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cs[i] = 0.f;
   for (int64_t base = r0; base < r1; base += DW_CH) {
     const int64_t m = base + lr;
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
@@ -41,6 +45,9 @@ dw_gemm_kernel(DwGemmArgs p, int rows_per_slab) {
       a1 = *reinterpret_cast<const float4*>(A + m * p.lda + lc + 4);
       b0 = *reinterpret_cast<const float4*>(Bp + m * ldb + lc);
       b1 = *reinterpret_cast<const float4*>(Bp + m * ldb + lc + 4);
+    }
+    if (want_cs) {     // column sums of A from the values this thread loads anyway (rows lr, lr+16, ... of the slab)
+      cs[0] += a0.x; cs[1] += a0.y; cs[2] += a0.z; cs[3] += a0.w; cs[4] += a1.x; cs[5] += a1.y; cs[6] += a1.z; cs[7] += a1.w;
     }
     __syncthreads();
     *reinterpret_cast<float4*>(&As[lr][lc]) = a0; *reinterpret_cast<float4*>(&As[lr][lc + 4]) = a1;
@@ -67,13 +74,39 @@ dw_gemm_kernel(DwGemmArgs p, int rows_per_slab) {
     *reinterpret_cast<float4*>(part + (size_t)ra * p.nb + bg * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     *reinterpret_cast<float4*>(part + (size_t)ra * p.nb + 64 + bg * 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
   }
+  if (want_cs) {       // fixed-order sum over the 16 loader rows
+    __syncthreads();
+    *reinterpret_cast<float4*>(&As[lr][lc]) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+    *reinterpret_cast<float4*>(&As[lr][lc + 4]) = make_float4(cs[4], cs[5], cs[6], cs[7]);
+    __syncthreads();
+    if (tid < 128) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < DW_CH; ++r) t += As[r][tid];
+      p.colsum_partial[(size_t)slab * p.na + ta * 128 + tid] = t;
+    }
+  }
 }
 
 // out[r*ld_out + c] (+)= scale * sum_s partial[s][r][c]
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_slabs, int rows, int cols,
-                                       float* __restrict__ out, int ld_out, float scale, int accumulate) {
+                                       float* __restrict__ out, int ld_out, float scale, int accumulate,
+                                       const float* __restrict__ cs_partial, float* __restrict__ cs_out) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * cols) return;
+  if (idx >= rows * cols) {
+    const int r = idx - rows * cols;               // trailing threads: column sums of A (one per output row)
+    if (cs_out == nullptr || r >= rows) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= n_slabs; k += 4) {
+      s0 += cs_partial[(size_t)k * rows + r]; s1 += cs_partial[(size_t)(k + 1) * rows + r];
+      s2 += cs_partial[(size_t)(k + 2) * rows + r]; s3 += cs_partial[(size_t)(k + 3) * rows + r];
+    }
+    for (; k < n_slabs; ++k) s0 += cs_partial[(size_t)k * rows + r];
+    const float t = (s0 + s1) + (s2 + s3);
+    cs_out[r] = accumulate ? cs_out[r] + t : t;
+    return;
+  }
   int r = idx / cols, c = idx % cols;
   // four independent chains (fixed order): the loop is pure load latency otherwise
   const size_t stride = (size_t)rows * cols;
@@ -102,9 +135,10 @@ int dw_gemm(const DwGemmArgs& a, cudaStream_t s) {
   dim3 grid(tiles, slabs);
   dw_gemm_kernel<<<grid, 256, 0, s>>>(a, rows_per_slab);
   CNS_LAUNCH_CHECK();
-  const int total = a.na * a.nb;
+  CNS_REQUIRE(a.colsum_out == nullptr || a.colsum_partial != nullptr, "dw_gemm: colsum needs its partial buffer");
+  const int total = a.na * a.nb + (a.colsum_out ? a.na : 0);
   reduce_partials_kernel<<<ceil_div(total, 256), 256, 0, s>>>(a.partial, slabs, a.na, a.nb, a.out, a.ld_out, a.scale,
-                                                             a.accumulate);
+                                                             a.accumulate, a.colsum_partial, a.colsum_out);
   CNS_LAUNCH_CHECK();
   return CNS_OK;
 }

@@ -81,6 +81,7 @@ struct LinearArgs {
   const float* pos; const float* wp;       // optional (m,2) / (2,n_out)
   const float* residual;                   // optional (m,n_out)
   int relu;
+  const float* relu_gate;                  // optional (m,n_out): y = 0 where relu_gate <= 0 (ReLU backward fused into dX)
   float* y;
 };
 int linear(const LinearArgs& a, cudaStream_t s);
