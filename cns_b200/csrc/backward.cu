@@ -14,6 +14,10 @@ struct BwdPack {           // transposed / negated operands for dX = dY W
   float* base;
   float* c0_bwd; float* g_bwd; float* k_bwd; float* c1_bwd;   // (2F, K) = transpose of *_wt
   float* neg_lin_src;                                          // -lin_src.weight, [out][in]
+  // bf16-split images (gemm_split.cu) of the ten 128 x 128 matrices the edge-level GEMMs multiply by:
+  // 0..4 the recomputed chain (enc_chain 0..4), 5 attn_nn.1, 6 attn_nn.0, 7 lin, 8 -lin_src, 9 pos_nn.1 (all [out][in] = (k, n) for dX)
+  unsigned char* split_img;
+  const unsigned char* img(int i) const { return split_img + (size_t)i * GEMM_SPLIT_IMG_BYTES; }
 };
 
 static int ensure_bwd_pack(cns_handle* h, cudaStream_t s) {
@@ -22,6 +26,7 @@ static int ensure_bwd_pack(cns_handle* h, cudaStream_t s) {
     bp = new BwdPack();
     const size_t n = 256 * 128 + 512 * 256 + 256 * 256 + 256 * 128 + 128 * 128;
     CNS_CUDA_CHECK(cudaMalloc(&bp->base, n * sizeof(float)));
+    CNS_CUDA_CHECK(cudaMalloc(&bp->split_img, 10 * GEMM_SPLIT_IMG_BYTES));
     float* q = bp->base;
     bp->c0_bwd = q; q += 256 * 128; bp->g_bwd = q; q += 512 * 256; bp->k_bwd = q; q += 256 * 256;
     bp->c1_bwd = q; q += 256 * 128; bp->neg_lin_src = q;
@@ -36,6 +41,11 @@ static int ensure_bwd_pack(cns_handle* h, cudaStream_t s) {
     if ((rc = transpose(h->pk.c1_wt, 128, 256, 1.f, bp->c1_bwd, s))) return rc;
     // enc_chain[1] holds -lin_src^T (k-major); transposing it back gives -lin_src in [out][in] layout
     if ((rc = transpose(h->pk.enc_chain + 1 * 16384, 128, 128, 1.f, bp->neg_lin_src, s))) return rc;
+    const float* mats[10] = {h->pk.enc_chain, h->pk.enc_chain + 16384, h->pk.enc_chain + 2 * 16384, h->pk.enc_chain + 3 * 16384,
+                             h->pk.enc_chain + 4 * 16384, h->P(P_ATT1_W), h->P(P_ATT0_W), h->P(P_LIN_W), bp->neg_lin_src,
+                             h->P(P_POS1_W)};
+    for (int i = 0; i < 10; ++i)
+      if ((rc = gemm_split_pack(mats[i], bp->split_img + (size_t)i * GEMM_SPLIT_IMG_BYTES, s))) return rc;
     h->bwd_pack_version = h->weights_version;
   }
   return CNS_OK;
@@ -43,10 +53,11 @@ static int ensure_bwd_pack(cns_handle* h, cudaStream_t s) {
 
 void free_bwd_pack(cns_handle* h) {
   BwdPack* bp = reinterpret_cast<BwdPack*>(h->bwd_pack);
-  if (bp) { cudaFree(bp->base); delete bp; h->bwd_pack = nullptr; }
+  if (bp) { cudaFree(bp->base); cudaFree(bp->split_img); delete bp; h->bwd_pack = nullptr; }
 }
 
 constexpr int N_EBUF = 12;
+constexpr int64_t SPLIT_MIN_ROWS = 4096;   // below this the 96 KB weight image per CTA costs more than the FFMA kernel
 struct BwdBuffers {
   int* err; int* curT_rowptr; int* curT_dst; int* tarT_rowptr; int* tarT_dst; void* csr_ws;
   float *dx2, *dz, *dgn, *dconv, *dpq, *dxk, *dxg, *dh_acc, *du, *dconvk, *dconvg, *dx1, *dxclu, *dpre, *cat, *dcat,
@@ -101,10 +112,12 @@ int backward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, con
 
   // ---- helpers ---------------------------------------------------------------------------------
   auto lin = [&](const float* x, int k, const float* wt, int n_out, const float* bias, const float* residual, int relu,
-                 int64_t m, float* y, const float* relu_gate = nullptr) {
+                 int64_t m, float* y, const float* relu_gate = nullptr, int split_id = -1) {
     LinearArgs la{};
     la.m = m; la.k1 = k; la.k2 = 0; la.n_out = n_out; la.x1 = x; la.wt = wt; la.bias = bias; la.residual = residual;
     la.relu = relu; la.relu_gate = relu_gate; la.y = y;
+    // long edge-level products: tensor cores with split operands (fp32 accuracy); short ones stay on the FFMA kernel
+    if (split_id >= 0 && m >= SPLIT_MIN_ROWS && !h->no_split_gemm) return gemm_split(la, bp.img(split_id), s);
     return linear(la, s);
   };
   auto dwg = [&](const float* a, int lda, int na, const float* b0, int ldb0, int tiles0, const float* b1, int ldb1, int nb,
@@ -259,12 +272,12 @@ int backward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, con
     ga.X = X; ga.HP = HP; ga.FE = w.FE; ga.DP = w.DP;
     RUN(enc_gather(ga, s));
     // forward recompute
-    RUN(lin(HP, H, pk.enc_chain + 0 * 16384, H, h->P(P_POS1_B), nullptr, 0, E, D));                 // delta
-    RUN(lin(X, H, pk.enc_chain + 1 * 16384, H, nullptr, D, 0, E, T));                              // -a_src + delta
+    RUN(lin(HP, H, pk.enc_chain + 0 * 16384, H, h->P(P_POS1_B), nullptr, 0, E, D, nullptr, 0));                 // delta
+    RUN(lin(X, H, pk.enc_chain + 1 * 16384, H, nullptr, D, 0, E, T, nullptr, 1));                              // -a_src + delta
     RUN(add_rows_gather(T, w.a_dst, b->l0_to_l1_i, E, s));                                          // + a_dst[i]
-    RUN(lin(T, H, pk.enc_chain + 3 * 16384, H, h->P(P_ATT0_B), nullptr, 1, E, U));
-    RUN(lin(U, H, pk.enc_chain + 4 * 16384, H, h->P(P_ATT1_B), nullptr, 0, E, L));
-    RUN(lin(X, H, pk.enc_chain + 2 * 16384, H, nullptr, D, 0, E, V));                              // v + delta
+    RUN(lin(T, H, pk.enc_chain + 3 * 16384, H, h->P(P_ATT0_B), nullptr, 1, E, U, nullptr, 3));
+    RUN(lin(U, H, pk.enc_chain + 4 * 16384, H, h->P(P_ATT1_B), nullptr, 0, E, L, nullptr, 4));
+    RUN(lin(X, H, pk.enc_chain + 2 * 16384, H, nullptr, D, 0, E, V, nullptr, 2));                              // v + delta
     // softmax / aggregation / relu backward
     EncSoftmaxBwdArgs sa{};
     sa.n_clusters = C; sa.clu_rowptr = sv.clu_rowptr; sa.L = L; sa.V = V; sa.y = sv.clu_feat + (size_t)side * C * H;
@@ -272,18 +285,18 @@ int backward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, con
     RUN(enc_softmax_bwd(sa, s));
     // attn_nn
     RUN(dwg(dL, H, H, U, H, 1, nullptr, 0, H, E, G(P_ATT1_W), H, 1.f, 1, G(P_ATT1_B)));
-    RUN(lin(dL, H, h->P(P_ATT1_W), H, nullptr, nullptr, 0, E, tmp, U));                            // dU_pre = (U > 0) dL A1
+    RUN(lin(dL, H, h->P(P_ATT1_W), H, nullptr, nullptr, 0, E, tmp, U, 5));                            // dU_pre = (U > 0) dL A1
     RUN(dwg(tmp, H, H, T, H, 1, nullptr, 0, H, E, G(P_ATT0_W), H, 1.f, 1, G(P_ATT0_B)));
-    RUN(lin(tmp, H, h->P(P_ATT0_W), H, nullptr, nullptr, 0, E, dT));                               // dT
+    RUN(lin(tmp, H, h->P(P_ATT0_W), H, nullptr, nullptr, 0, E, dT, nullptr, 6));                               // dT
     // t = a_dst[i] - a_src + delta
     RUN(seg_sum_rows(dT, sv.clu_rowptr, C, w.d_adst, side, s));                                     // both sides accumulate
     RUN(dwg(dT, H, H, X, H, 1, nullptr, 0, H, E, G(P_LINSRC_W), H, -1.f, 1));                      // a_src = x lin_src^T
     RUN(dwg(dV, H, H, X, H, 1, nullptr, 0, H, E, G(P_LIN_W), H, 1.f, 1));                          // v = x lin^T
-    RUN(lin(dV, H, h->P(P_LIN_W), H, nullptr, nullptr, 0, E, dX));
-    RUN(lin(dT, H, bp.neg_lin_src, H, nullptr, dX, 0, E, dX, X));                                  // dX = (X > 0)(dV lin - dT lin_src)
+    RUN(lin(dV, H, h->P(P_LIN_W), H, nullptr, nullptr, 0, E, dX, nullptr, 7));
+    RUN(lin(dT, H, bp.neg_lin_src, H, nullptr, dX, 0, E, dX, X, 8));                                  // dX = (X > 0)(dV lin - dT lin_src)
     RUN(ew1(EW_ADD, E * H, dT, dV, nullptr, nullptr, tmp, nullptr, nullptr));                      // dDelta
     RUN(dwg(tmp, H, H, HP, H, 1, nullptr, 0, H, E, G(P_POS1_W), H, 1.f, 1, G(P_POS1_B)));
-    RUN(lin(tmp, H, h->P(P_POS1_W), H, nullptr, nullptr, 0, E, dL, HP));                           // dHP_pre (reuse dL)
+    RUN(lin(tmp, H, h->P(P_POS1_W), H, nullptr, nullptr, 0, E, dL, HP, 9));                           // dHP_pre (reuse dL)
     RUN(dws(dL, H, H, w.DP, 4, 4, E, G(P_POS0_W), 4, 0, 1));
     RUN(colsum(dL, H, H, E, G(P_POS0_B), 1));
     RUN(dws(dX, H, H, w.FE, 2, 2, E, G(P_IN_W), 2, 0, 1));

@@ -238,6 +238,7 @@ int cns_create(cns_handle** out, int device) {
   h->precision = CNS_PREC_FP32;
   h->tc_tile_n = 32;
   h->no_fused_backbone = getenv("CNS_NO_FUSED_BACKBONE") ? 1 : 0;
+  h->no_split_gemm = getenv("CNS_NO_SPLIT_GEMM") ? 1 : 0;
   h->sm_count = prop.multiProcessorCount;
   size_t off = 0;
   for (int k = 0; k < P_COUNT; ++k) {

@@ -86,6 +86,11 @@ struct LinearArgs {
 };
 int linear(const LinearArgs& a, cudaStream_t s);
 
+// ---- gemm_split.cu: the same contract for 128 x 128 layers on tcgen05 with fp32 accuracy (3-way bf16 operand split)
+constexpr size_t GEMM_SPLIT_IMG_BYTES = 3 * 128 * 128 * 2;
+int gemm_split_pack(const float* wt, unsigned char* img, cudaStream_t s);
+int gemm_split(const LinearArgs& a, const unsigned char* w_img, cudaStream_t s);
+
 // ---- gemm_tc.cu: same contract as `linear` on tcgen05 (16-bit operands), plus an optional row mask
 struct GemmTcArgs {
   int64_t m; int k1, k2, n_out;

@@ -227,3 +227,45 @@ def test_affinity_propagation_device_identical_to_sklearn(seed, sizes):
     np.random.seed(seed + 10); a = cluster_points(sets[0])
     np.random.seed(seed + 10); b = cluster_points_device(sets[0], device=DEV)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_linear_split_matches_fp64():
+    """cns_linear_split (tensor cores, three bf16 slices per operand) must be as accurate as an fp32 FMA chain -
+    it replaces the FFMA GEMMs of the backward pass, whose gradients are held to 1e-4 of fp64 autograd."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(7)
+    ws = torch.empty(lib.cns_linear_split_workspace_bytes(), dtype=torch.uint8, device=DEV)
+    for m, scale in [(1, 1.0), (127, 1.0), (128, 1e-6), (129, 1.0), (5000, 1e3), (40000, 1.0)]:
+        x = (torch.randn(m, 128, generator=g) * scale).to(DEV)
+        x[0, :5] = torch.tensor([1e-30, -3e-38, 1e20, 0.0, -1e-20])[:5].to(DEV) if m > 1 else x[0, :5]
+        wt = (torch.randn(128, 128, generator=g) / 11).to(DEV)
+        bias = torch.randn(128, generator=g).to(DEV) * scale
+        res = (torch.randn(m, 128, generator=g) * scale).to(DEV)
+        gate = torch.randn(m, 128, generator=g).to(DEV)
+        for use_bias, use_res, relu, use_gate in [(0, 0, 0, 0), (1, 1, 1, 0), (1, 1, 0, 1), (0, 1, 0, 1)]:
+            y = torch.full((m, 128), float("nan"), device=DEV)
+            _lib.check(lib.cns_linear_split(_lib.ptr(x), m, _lib.ptr(wt), _lib.ptr(bias if use_bias else None),
+                                            _lib.ptr(res if use_res else None), _lib.ptr(gate if use_gate else None),
+                                            relu, _lib.ptr(y), _lib.ptr(ws), ws.numel(), _sp()), "cns_linear_split")
+            ref = x.double() @ wt.double()
+            if use_bias:
+                ref = ref + bias.double()
+            if use_res:
+                ref = ref + res.double()
+            if relu:
+                ref = ref.clamp_min(0)
+            if use_gate:
+                ref = torch.where(gate > 0, ref, torch.zeros_like(ref))
+            fp32 = x @ wt                                           # cuBLAS fp32 as the yardstick for "fp32 accuracy"
+            denom = (x.double().abs() @ wt.double().abs()).max().item() + 1e-300
+            err = (y.double() - ref).abs().max().item() / denom
+            assert torch.isfinite(y).all() and err < 2e-7, (m, scale, use_bias, use_res, relu, use_gate, err)
+            if not (use_bias or use_res or relu or use_gate):
+                err32 = (fp32.double() - ref).abs().max().item() / denom
+                assert err < 4 * err32 + 1e-8, (err, err32)
+        # in place on the residual, as the backward pass uses it
+        y = res.clone()
+        _lib.check(lib.cns_linear_split(_lib.ptr(x), m, _lib.ptr(wt), None, _lib.ptr(y), None, 0, _lib.ptr(y),
+                                        _lib.ptr(ws), ws.numel(), _sp()), "cns_linear_split")
+        ref = x.double() @ wt.double() + res.double()
+        assert (y.double() - ref).abs().max().item() / ((x.double().abs() @ wt.double().abs()).max().item() + res.abs().max().item()) < 2e-7
