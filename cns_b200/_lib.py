@@ -82,6 +82,8 @@ def _declare(lib):
         "cns_graph_mask": (i32, [vp, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, i64, vp, vp, vp, sz, vp]),
         "cns_linear_split_workspace_bytes": (sz, []),
         "cns_linear_split": (i32, [vp, i64, vp, vp, vp, vp, i32, vp, vp, sz, vp]),
+        "cns_weight_grad_workspace_bytes": (sz, []),
+        "cns_weight_grad": (i32, [vp, i64, vp, i64, i64, vp, vp, i32, i32, vp, sz, vp]),
         "cns_align_matches": (i32, [vp, i64, vp, i64, i64, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp, vp, sz, vp]),
         "cns_pixel_stop_workspace_bytes": (sz, [i64]),
         "cns_pixel_stop_error": (i32, [vp, vp, vp, vp, vp, i64, i64, C.c_float, C.c_float, vp, vp, vp, vp, vp, sz, vp]),

@@ -126,6 +126,7 @@ int backward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, con
     d.m = m; d.na = na; d.nb = nb; d.a = a; d.lda = lda; d.b0 = b0; d.ldb0 = ldb0; d.b_tiles0 = tiles0; d.b1 = b1; d.ldb1 = ldb1;
     d.out = out; d.ld_out = ld_out; d.scale = scale; d.accumulate = accumulate; d.partial = w.dw_partial;
     d.max_slabs = (int)(DW_PARTIAL_FLOATS / ((size_t)na * nb));
+    d.allow_split = h->no_split_gemm ? 0 : 1;
     d.colsum_out = colsum_out; d.colsum_partial = w.cs_partial;     // bias gradient from the same pass over `a`
     return dw_gemm(d, s);
   };

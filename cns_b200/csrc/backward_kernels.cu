@@ -129,12 +129,18 @@ int dw_gemm(const DwGemmArgs& a, cudaStream_t s) {
   const int tiles = (a.na / 128) * (a.nb / 128);
   const int64_t m1 = a.m > 0 ? a.m : 1;
   int slabs = ceil_div(m1, 256);
+  if (a.allow_split && tiles == 1 && a.b_tiles0 >= 1 && a.m >= 4096 && a.lda % 4 == 0 && a.ldb0 % 4 == 0) {
+    // long reductions of a single 128 x 128 tile: tensor cores with split operands, one partial per persistent CTA
+    int rc = dw_split(a.m, a.a, a.lda, a.b0, a.ldb0, a.partial, a.colsum_out ? a.colsum_partial : nullptr, a.max_slabs, &slabs, s);
+    if (rc != CNS_OK) return rc;
+  } else {
   if (slabs > 592 / tiles) slabs = 592 / tiles > 0 ? 592 / tiles : 1;
   if (slabs > a.max_slabs) slabs = a.max_slabs;
   const int rows_per_slab = (int)((m1 + slabs - 1) / slabs);
   dim3 grid(tiles, slabs);
   dw_gemm_kernel<<<grid, 256, 0, s>>>(a, rows_per_slab);
   CNS_LAUNCH_CHECK();
+  }
   CNS_REQUIRE(a.colsum_out == nullptr || a.colsum_partial != nullptr, "dw_gemm: colsum needs its partial buffer");
   const int total = a.na * a.nb + (a.colsum_out ? a.na : 0);
   reduce_partials_kernel<<<ceil_div(total, 256), 256, 0, s>>>(a.partial, slabs, a.na, a.nb, a.out, a.ld_out, a.scale,
@@ -710,3 +716,23 @@ int transpose(const float* src, int rows, int cols, float sign, float* dst, cuda
 }
 
 }  // namespace cns
+
+using namespace cns;
+
+extern "C" {
+
+size_t cns_weight_grad_workspace_bytes(void) { return ((size_t)592 * 128 * 128 + (size_t)592 * 128) * sizeof(float); }
+
+int cns_weight_grad(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, int64_t m, float* dw, float* dbias,
+                    int accumulate, int tensor_cores, void* workspace, size_t workspace_bytes, void* stream) {
+  CNS_REQUIRE(dy && x && dw && workspace && m >= 0, "NULL pointer / bad size");
+  CNS_REQUIRE(workspace_bytes >= cns_weight_grad_workspace_bytes(), "cns_weight_grad: workspace too small");
+  DwGemmArgs d{};
+  d.m = m; d.na = 128; d.nb = 128; d.a = dy; d.lda = (int)ld_dy; d.b0 = x; d.ldb0 = (int)ld_x; d.b_tiles0 = 1;
+  d.out = dw; d.ld_out = 128; d.scale = 1.f; d.accumulate = accumulate;
+  d.partial = (float*)workspace; d.max_slabs = 592; d.allow_split = tensor_cores;
+  d.colsum_out = dbias; d.colsum_partial = (float*)workspace + (size_t)592 * 128 * 128;
+  return dw_gemm(d, (cudaStream_t)stream);
+}
+
+}  // extern "C"

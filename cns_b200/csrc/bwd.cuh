@@ -12,6 +12,7 @@ struct DwGemmArgs {
   const float* b1; int ldb1;
   float* out; int ld_out; float scale; int accumulate;
   float* partial; int max_slabs;
+  int allow_split;                            // 128 x 128 products over many rows may run on the tensor cores (gemm_split.cu)
   float* colsum_out; float* colsum_partial;   // optional: colsum_out[i] (+)= sum_m a[m][i] from the same pass (bias gradient)
 };
 int dw_gemm(const DwGemmArgs& a, cudaStream_t s);

@@ -5,8 +5,9 @@
 // exponent range, so no scaling is needed even for tiny gradients); the six slice products of weight >= 2^-18
 // (hh, hm, mh, hl, lh, mm) accumulate in one fp32 TMEM tile: 48 tcgen05.mma (M128 x N128 x K16) per 128-row tile,
 // error ~2^-24 like an fp32 FMA chain, at 6x fewer tensor FLOPs than the fp32 FFMA kernel has CUDA-core FLOPs.
-// One CTA per 128-row tile: warps 0-7 split the A rows into the three SWIZZLE_128B images and run the epilogue,
-// warp 8 loads the pre-split weight image (96 KB, 1-D TMA bulk copies) and issues the MMAs.
+// Persistent CTAs (one per SM) keep the pre-split weight image (96 KB, 1-D TMA bulk copies) in shared memory and
+// walk the 128-row tiles with three roles: split the A rows into the three SWIZZLE_128B images / issue the MMAs /
+// epilogue, the accumulator double-buffered in TMEM.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -17,7 +18,8 @@ namespace {
 
 constexpr int GS_THREADS = 288;
 constexpr uint32_t GS_SLICE = 128 * 128 * 2;                    // one bf16 slice of a 128 x 128 operand
-constexpr size_t GS_SMEM = 6 * GS_SLICE + 128 * 4 + 64 + 1024;  // A slices, W slices, bias, barriers, alignment slack
+constexpr size_t GS_SMEM = 6 * GS_SLICE + 128 * 4 + 128 + 1024; // A slices, W slices, bias, barriers, alignment slack
+constexpr size_t GS_DW_SMEM = 6 * GS_SLICE + 8 * 128 * 4 + 128 + 1024;
 
 __device__ __forceinline__ void split3(float v, unsigned short& h, unsigned short& m, unsigned short& l) {
   const __nv_bfloat16 bh = __float2bfloat16_rn(v);
@@ -48,57 +50,37 @@ struct SplitArgs {
 
 __global__ void __launch_bounds__(GS_THREADS, 1)
 gemm_split_kernel(const __grid_constant__ SplitArgs p) {
+  // persistent: one CTA per SM walks the 128-row tiles.  Roles: warps 0-3 epilogue (thread = TMEM lane = row),
+  // warps 4-7 split the next tile's rows into the three operand images, warp 8 issues the MMAs.  The fp32
+  // accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the split and the MMAs of tile i+1.
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* a_s = smem;
   unsigned char* w_s = smem + 3 * GS_SLICE;
   float* bias_s = reinterpret_cast<float*>(w_s + 3 * GS_SLICE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 128);   // [0] weights landed, [1] MMAs done
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 128);
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 8);
+  const uint32_t w_full = smem_u32(&bars[0]), a_full = smem_u32(&bars[1]);
+  const uint32_t mma_done0 = smem_u32(&bars[2]), d_free0 = smem_u32(&bars[4]);      // [2], [2]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t m0 = (int64_t)blockIdx.x * 128;
+  const int n_tiles = (int)((p.m + 127) / 128);
 
   if (warp == 8) {
     if (lane == 0) {
-      mbar_init(smem_u32(&bars[0]), 1);
-      mbar_init(smem_u32(&bars[1]), 1);
+      mbar_init(w_full, 1);
+      mbar_init(a_full, 128);
+      mbar_init(mma_done0, 1); mbar_init(mma_done0 + 8, 1);
+      mbar_init(d_free0, 128); mbar_init(d_free0 + 8, 128);
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(smem_u32(tmem_ptr_s), 128);
+    tmem_alloc(smem_u32(tmem_ptr_s), 256);
     if (lane == 0) {
-      mbar_expect_tx(smem_u32(&bars[0]), 3 * GS_SLICE);
-      for (int sl = 0; sl < 3; ++sl)
-        bulk_g2s(smem_u32(w_s + sl * GS_SLICE), p.w_img + (size_t)sl * GS_SLICE, GS_SLICE, smem_u32(&bars[0]));
+      mbar_expect_tx(w_full, 3 * GS_SLICE);
+      for (int sl = 0; sl < 3; ++sl) bulk_g2s(smem_u32(w_s + sl * GS_SLICE), p.w_img + (size_t)sl * GS_SLICE, GS_SLICE, w_full);
     }
-  } else {
-    // A tile: 8 consecutive k of one row per step -> one 16-byte store into each of the three slice images
-    for (int q = tid; q < 128 * 16; q += 256) {
-      const int row = q >> 4, k = (q & 15) * 8;
-      const int64_t m = m0 + row;
-      float v[8];
-      if (m < p.m) {
-        const float4 lo = *reinterpret_cast<const float4*>(p.x + m * 128 + k);
-        const float4 hi = *reinterpret_cast<const float4*>(p.x + m * 128 + k + 4);
-        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
-      }
-      unsigned short h[8], md[8], l[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) split3(v[i], h[i], md[i], l[i]);
-      auto pk4 = [](const unsigned short* s) {
-        return make_uint4((uint32_t)s[0] | ((uint32_t)s[1] << 16), (uint32_t)s[2] | ((uint32_t)s[3] << 16),
-                          (uint32_t)s[4] | ((uint32_t)s[5] << 16), (uint32_t)s[6] | ((uint32_t)s[7] << 16));
-      };
-      const uint32_t off = sw128_off(128, row, k);
-      *reinterpret_cast<uint4*>(a_s + off) = pk4(h);
-      *reinterpret_cast<uint4*>(a_s + GS_SLICE + off) = pk4(md);
-      *reinterpret_cast<uint4*>(a_s + 2 * GS_SLICE + off) = pk4(l);
-    }
-    if (tid < 128) bias_s[tid] = p.bias ? p.bias[tid] : 0.f;
-    fence_proxy_async();
+  } else if (tid < 128) {
+    bias_s[tid] = p.bias ? p.bias[tid] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -110,54 +92,254 @@ gemm_split_kernel(const __grid_constant__ SplitArgs p) {
       // bf16 x bf16 -> fp32, M = 128, N = 128, both operands K-major
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t a_base = smem_u32(a_s), w_base = smem_u32(w_s);
-      mbar_wait(smem_u32(&bars[0]), 0);
-      tc_fence_after();
-      // (A slice, W slice): smallest products first
-      const int pa[6] = {1, 2, 0, 1, 0, 0}, pw[6] = {1, 0, 2, 0, 1, 0};
-      bool first = true;
-      for (int t = 0; t < 6; ++t)
-        for (int kc = 0; kc < 2; ++kc)
+      const int pa[6] = {1, 2, 0, 1, 0, 0}, pw[6] = {1, 0, 2, 0, 1, 0};     // (A slice, W slice): smallest products first
+      mbar_wait(w_full, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (it >= 2) mbar_wait(d_free0 + 8 * buf, (uint32_t)(((it - 2) >> 1) & 1));   // epilogue drained this accumulator
+        mbar_wait(a_full, (uint32_t)(it & 1));
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(buf * 128);
+        bool first = true;
+        for (int t = 0; t < 6; ++t)
+          for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            umma_f16(tmem_base, sw128_desc(a_base + pa[t] * GS_SLICE + kc * (128 * 128) + ks * 32),
-                     sw128_desc(w_base + pw[t] * GS_SLICE + kc * (128 * 128) + ks * 32), idesc, first ? 0u : 1u);
-            first = false;
-          }
-      umma_commit(smem_u32(&bars[1]));
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_f16(d, sw128_desc(a_base + pa[t] * GS_SLICE + kc * (128 * 128) + ks * 32),
+                       sw128_desc(w_base + pw[t] * GS_SLICE + kc * (128 * 128) + ks * 32), idesc, first ? 0u : 1u);
+              first = false;
+            }
+        umma_commit(mma_done0 + 8 * buf);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---- operand split: 8 consecutive k of one row per step -> one 16-byte store into each slice image ----
+    const int ct = tid - 128;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int64_t m0 = (int64_t)tile * 128;
+      if (it > 0) mbar_wait(mma_done0 + 8 * ((it - 1) & 1), (uint32_t)(((it - 1) >> 1) & 1));   // previous tile's MMAs read A
+      for (int q = ct; q < 128 * 16; q += 128) {
+        const int row = q >> 4, k = (q & 15) * 8;
+        const int64_t m = m0 + row;
+        float v[8];
+        if (m < p.m) {
+          const float4 lo = *reinterpret_cast<const float4*>(p.x + m * 128 + k);
+          const float4 hi = *reinterpret_cast<const float4*>(p.x + m * 128 + k + 4);
+          v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+        unsigned short h[8], md[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split3(v[i], h[i], md[i], l[i]);
+        auto pk4 = [](const unsigned short* s) {
+          return make_uint4((uint32_t)s[0] | ((uint32_t)s[1] << 16), (uint32_t)s[2] | ((uint32_t)s[3] << 16),
+                            (uint32_t)s[4] | ((uint32_t)s[5] << 16), (uint32_t)s[6] | ((uint32_t)s[7] << 16));
+        };
+        const uint32_t off = sw128_off(128, row, k);
+        *reinterpret_cast<uint4*>(a_s + off) = pk4(h);
+        *reinterpret_cast<uint4*>(a_s + GS_SLICE + off) = pk4(md);
+        *reinterpret_cast<uint4*>(a_s + 2 * GS_SLICE + off) = pk4(l);
+      }
+      fence_proxy_async();
+      mbar_arrive(a_full);
     }
   } else {
-    // epilogue: thread = row (TMEM lane), 64 of the 128 columns
-    const int wq = warp & 3, half = warp >> 2;
-    const int64_t m = m0 + wq * 32 + lane;
-    const bool live = m < p.m;
-    mbar_wait(smem_u32(&bars[1]), 0);
-    tc_fence_after();
+    // ---- epilogue: thread = row (TMEM lane), all 128 columns in four 32-column reads ----
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int64_t m = (int64_t)tile * 128 + warp * 32 + lane;
+      const bool live = m < p.m;
+      mbar_wait(mma_done0 + 8 * buf, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int n0 = 0; n0 < 128; n0 += 32) {
+        float acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 128 + n0), acc);
+        tmem_ld_wait();
+        if (live) {
+          float* yrow = p.y + m * 128 + n0;
+          const float* rrow = p.residual ? p.residual + m * 128 + n0 : nullptr;
+          const float* grow = p.relu_gate ? p.relu_gate + m * 128 + n0 : nullptr;
 #pragma unroll
-    for (int sub = 0; sub < 2; ++sub) {
-      const int n0 = half * 64 + sub * 32;
-      float acc[32];
-      tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)n0, acc);
-      tmem_ld_wait();
-      if (live) {
-        float* yrow = p.y + m * 128 + n0;
-        const float* rrow = p.residual ? p.residual + m * 128 + n0 : nullptr;
-        const float* grow = p.relu_gate ? p.relu_gate + m * 128 + n0 : nullptr;
-#pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n0 + q);
-          float4 v = make_float4(acc[q] + b4.x, acc[q + 1] + b4.y, acc[q + 2] + b4.z, acc[q + 3] + b4.w);
-          if (rrow) {
-            const float4 r = *reinterpret_cast<const float4*>(rrow + q);
-            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+          for (int q = 0; q < 32; q += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n0 + q);
+            float4 v = make_float4(acc[q] + b4.x, acc[q + 1] + b4.y, acc[q + 2] + b4.z, acc[q + 3] + b4.w);
+            if (rrow) {
+              const float4 r = *reinterpret_cast<const float4*>(rrow + q);
+              v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            }
+            if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            if (grow) {
+              const float4 g = *reinterpret_cast<const float4*>(grow + q);
+              v.x = g.x > 0.f ? v.x : 0.f; v.y = g.y > 0.f ? v.y : 0.f; v.z = g.z > 0.f ? v.z : 0.f; v.w = g.w > 0.f ? v.w : 0.f;
+            }
+            *reinterpret_cast<float4*>(yrow + q) = v;
           }
-          if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          if (grow) {
-            const float4 g = *reinterpret_cast<const float4*>(grow + q);
-            v.x = g.x > 0.f ? v.x : 0.f; v.y = g.y > 0.f ? v.y : 0.f; v.z = g.z > 0.f ? v.z : 0.f; v.w = g.w > 0.f ? v.w : 0.f;
-          }
-          *reinterpret_cast<float4*>(yrow + q) = v;
         }
       }
+      tc_fence_before();
+      mbar_arrive(d_free0 + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 8) tmem_dealloc(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dW = A^T B over m rows (weight gradients of the same layers): D[i][j] = sum_m A[m][i] B[m][j], i, j < 128.
+// The reduction index is the row index, so both operands are MN-major: a 128-row block of A (or B), split into
+// three bf16 slices and stored row by row with the 128-byte swizzle, is exactly the byte image the K-major tiles
+// above use - only the descriptors differ (MN-major, LBO = the second 64-column block, SBO = the next 8 rows).
+// Persistent CTAs each own a contiguous range of 128-row blocks and accumulate all of them into ONE TMEM tile
+// (48 MMAs per block); the per-CTA partial products go through the fixed-order reduce_partials_kernel.
+// ---------------------------------------------------------------------------------------------------------------
+struct DwSplitArgs {
+  int64_t m; const float* a; int lda; const float* b; int ldb;
+  float* partial; float* colsum_partial; int blocks_per_cta;
+};
+
+__device__ __forceinline__ uint64_t mn128_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((128 * 128) >> 4) << 16;             // LBO: next block of 64 MN elements (128 rows x 128 B further)
+  d |= (uint64_t)(1024 >> 4) << 32;                    // SBO: next group of 8 k-rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(GS_THREADS, 1)
+dw_split_kernel(const __grid_constant__ DwSplitArgs p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* a_s = smem;                           // [3 slices][2 column blocks][128 rows][128 B]
+  unsigned char* b_s = smem + 3 * GS_SLICE;
+  float* cs_s = reinterpret_cast<float*>(b_s + 3 * GS_SLICE);          // [8][128] column-sum staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cs_s + 8 * 128);
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 4);
+  const uint32_t full = smem_u32(&bars[0]), mma_done = smem_u32(&bars[1]);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_blocks = (int)((p.m + 127) / 128);
+  const int blk0 = blockIdx.x * p.blocks_per_cta;
+  const int blk1 = min(n_blocks, blk0 + p.blocks_per_cta);
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_init(full, 256);
+      mbar_init(mma_done, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_ptr_s), 128);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      // bf16 x bf16 -> fp32, M = 128, N = 128, A and B MN-major (bits 15 / 16)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t a_base = smem_u32(a_s), b_base = smem_u32(b_s);
+      const int pa[6] = {1, 2, 0, 1, 0, 0}, pb[6] = {1, 0, 2, 0, 1, 0};
+      bool first = true;
+      for (int blk = blk0, it = 0; blk < blk1; ++blk, ++it) {
+        mbar_wait(full, (uint32_t)(it & 1));
+        tc_fence_after();
+        for (int t = 0; t < 6; ++t)
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {             // 16 rows (two 8-row groups) per MMA
+            umma_f16(tmem_base, mn128_desc(a_base + pa[t] * GS_SLICE + ks * 2048),
+                     mn128_desc(b_base + pb[t] * GS_SLICE + ks * 2048), idesc, first ? 0u : 1u);
+            first = false;
+          }
+        umma_commit(mma_done);
+      }
+    }
+  } else {
+    // warps 0-3 split the A rows, warps 4-7 the B rows of the block
+    const bool is_b = warp >= 4;
+    const int ct = tid & 127;
+    const float* __restrict__ src = is_b ? p.b : p.a;
+    const int ld = is_b ? p.ldb : p.lda;
+    unsigned char* dst = is_b ? b_s : a_s;
+    float cs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cs[i] = 0.f;
+    for (int blk = blk0, it = 0; blk < blk1; ++blk, ++it) {
+      const int64_t m0 = (int64_t)blk * 128;
+      if (it > 0) mbar_wait(mma_done, (uint32_t)((it - 1) & 1));
+      for (int q = ct; q < 128 * 16; q += 128) {
+        const int row = q >> 4, c = (q & 15) * 8;
+        const int64_t m = m0 + row;
+        float v[8];
+        if (m < p.m) {
+          const float4 lo = *reinterpret_cast<const float4*>(src + m * ld + c);
+          const float4 hi = *reinterpret_cast<const float4*>(src + m * ld + c + 4);
+          v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+        if (!is_b) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cs[i] += v[i];    // column sums of A (bias gradient), fixed order per thread
+        }
+        unsigned short h[8], md[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split3(v[i], h[i], md[i], l[i]);
+        auto pk4 = [](const unsigned short* s) {
+          return make_uint4((uint32_t)s[0] | ((uint32_t)s[1] << 16), (uint32_t)s[2] | ((uint32_t)s[3] << 16),
+                            (uint32_t)s[4] | ((uint32_t)s[5] << 16), (uint32_t)s[6] | ((uint32_t)s[7] << 16));
+        };
+        const uint32_t off = sw128_off(128, row, c);
+        *reinterpret_cast<uint4*>(dst + off) = pk4(h);
+        *reinterpret_cast<uint4*>(dst + GS_SLICE + off) = pk4(md);
+        *reinterpret_cast<uint4*>(dst + 2 * GS_SLICE + off) = pk4(l);
+      }
+      fence_proxy_async();
+      mbar_arrive(full);
+    }
+    // column sums: thread ct owns columns (ct & 15) * 8 .. + 7 for the rows (ct >> 4) + 8 j
+    if (!is_b && p.colsum_partial) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cs_s[(ct >> 4) * 128 + (ct & 15) * 8 + i] = cs[i];
+    }
+    named_bar(1, 256);
+    if (!is_b && p.colsum_partial) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += cs_s[r * 128 + ct];
+      p.colsum_partial[(size_t)blockIdx.x * 128 + ct] = t;
+    }
+    // epilogue: the CTA's partial product, thread = row i, 64 columns per warp group
+    const int n_it = blk1 - blk0;
+    const int wq = warp & 3, half = warp >> 2;
+    float* prow = p.partial + ((size_t)blockIdx.x * 128 + wq * 32 + lane) * 128 + half * 64;
+    if (n_it > 0) {
+      mbar_wait(mma_done, (uint32_t)((n_it - 1) & 1));
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) {
+      float acc[32];
+      if (n_it > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(half * 64 + sub * 32), acc);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) acc[q] = 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 32; q += 4)
+        *reinterpret_cast<float4*>(prow + sub * 32 + q) = make_float4(acc[q], acc[q + 1], acc[q + 2], acc[q + 3]);
     }
   }
   tc_fence_before();
@@ -187,8 +369,40 @@ int gemm_split(const LinearArgs& a, const unsigned char* w_img, cudaStream_t s) 
   SplitArgs p;
   p.m = a.m; p.x = a.x1; p.w_img = w_img; p.bias = a.bias; p.residual = a.residual; p.relu_gate = a.relu_gate;
   p.relu = a.relu; p.y = a.y;
-  gemm_split_kernel<<<ceil_div(a.m, 128), GS_THREADS, GS_SMEM, s>>>(p);
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    CNS_CUDA_CHECK(cudaGetDevice(&dev));
+    CNS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int tiles = ceil_div(a.m, 128);
+  gemm_split_kernel<<<tiles < n_sm ? tiles : n_sm, GS_THREADS, GS_SMEM, s>>>(p);
   CNS_LAUNCH_CHECK();
+  return CNS_OK;
+}
+
+// stage 1 of dw_gemm for a single 128 x 128 output tile on the tensor cores; returns the number of partials
+int dw_split(int64_t m, const float* a, int lda, const float* b, int ldb, float* partial, float* colsum_partial, int max_slabs,
+             int* n_slabs, cudaStream_t s) {
+  static bool configured = false;
+  static int n_sm = 0;
+  if (!configured) {
+    int dev = 0;
+    CNS_CUDA_CHECK(cudaGetDevice(&dev));
+    CNS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    CNS_CUDA_CHECK(cudaFuncSetAttribute(dw_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_DW_SMEM));
+    configured = true;
+  }
+  const int n_blocks = ceil_div(m, 128);
+  int ctas = n_blocks < n_sm ? n_blocks : n_sm;
+  if (ctas > max_slabs) ctas = max_slabs;
+  DwSplitArgs p;
+  p.m = m; p.a = a; p.lda = lda; p.b = b; p.ldb = ldb; p.partial = partial; p.colsum_partial = colsum_partial;
+  p.blocks_per_cta = (n_blocks + ctas - 1) / ctas;
+  ctas = (n_blocks + p.blocks_per_cta - 1) / p.blocks_per_cta;
+  dw_split_kernel<<<ctas, GS_THREADS, GS_DW_SMEM, s>>>(p);
+  CNS_LAUNCH_CHECK();
+  *n_slabs = ctas;
   return CNS_OK;
 }
 

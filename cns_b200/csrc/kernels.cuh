@@ -90,6 +90,8 @@ int linear(const LinearArgs& a, cudaStream_t s);
 constexpr size_t GEMM_SPLIT_IMG_BYTES = 3 * 128 * 128 * 2;
 int gemm_split_pack(const float* wt, unsigned char* img, cudaStream_t s);
 int gemm_split(const LinearArgs& a, const unsigned char* w_img, cudaStream_t s);
+int dw_split(int64_t m, const float* a, int lda, const float* b, int ldb, float* partial, float* colsum_partial, int max_slabs,
+             int* n_slabs, cudaStream_t s);
 
 // ---- gemm_tc.cu: same contract as `linear` on tcgen05 (16-bit operands), plus an optional row mask
 struct GemmTcArgs {

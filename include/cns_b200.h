@@ -261,6 +261,16 @@ int cns_frame_mask(const int64_t* member_order, const int32_t* member_ptr, const
                    int64_t n_clusters, int64_t* e01_j, int64_t* e01_i, uint8_t* cluster_mask, int32_t* clu_rowptr,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Weight / bias gradient of one 128 -> 128 Linear layer (what autograd computes for nn.Linear inside GraphVS,
+ * graph_vs.py:16-31): dw[o][i] (+)= sum_m dy[m][o] x[m][i], dbias[o] (+)= sum_m dy[m][o] (dbias may be NULL), rows
+ * with strides ld_dy / ld_x floats.  Split-M partial products + a fixed-order reduction (deterministic).  With
+ * tensor_cores != 0 and m >= 4096 the partial products run on tcgen05 with both operands split into three bf16
+ * slices (fp32 accuracy, gemm_split.cu); otherwise on the fp32 FFMA kernel.  workspace:
+ * cns_weight_grad_workspace_bytes(). */
+size_t cns_weight_grad_workspace_bytes(void);
+int cns_weight_grad(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, int64_t m, float* dw, float* dbias,
+                    int accumulate, int tensor_cores, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- the steps either side of the graph path in the servo loop --------------------------------
  *
  * cns_align_matches replaces Classic._align_cur_to_tar (cns/frontend/classic.py:142-148) followed by

@@ -269,3 +269,44 @@ def test_linear_split_matches_fp64():
                                         _lib.ptr(ws), ws.numel(), _sp()), "cns_linear_split")
         ref = x.double() @ wt.double() + res.double()
         assert (y.double() - ref).abs().max().item() / ((x.double().abs() @ wt.double().abs()).max().item() + res.abs().max().item()) < 2e-7
+
+
+def test_weight_grad_tensor_core_path_matches_fp64():
+    """cns_weight_grad: dW = dY^T X and dbias over many rows, tensor-core (split bf16, MN-major operands) and FFMA
+    paths against fp64; both must be fp32-accurate and deterministic."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11)
+    ws = torch.empty(lib.cns_weight_grad_workspace_bytes(), dtype=torch.uint8, device=DEV)
+    for m, scale in [(4096, 1.0), (4097, 1e-4), (50000, 1.0), (118000, 3.0), (300, 1.0)]:
+        dy = (torch.randn(m, 128, generator=g) * scale).to(DEV)
+        x = torch.randn(m, 128, generator=g).to(DEV)
+        ref_w = dy.double().t() @ x.double()
+        ref_b = dy.double().sum(0)
+        den_w = (dy.double().abs().t() @ x.double().abs()).max().item()
+        den_b = dy.double().abs().sum(0).max().item()
+        outs = []
+        for tc in (1, 0, 1):
+            dw = torch.full((128, 128), float("nan"), device=DEV)
+            db = torch.full((128,), float("nan"), device=DEV)
+            _lib.check(lib.cns_weight_grad(_lib.ptr(dy), 128, _lib.ptr(x), 128, m, _lib.ptr(dw), _lib.ptr(db), 0, tc,
+                                           _lib.ptr(ws), ws.numel(), _sp()), "cns_weight_grad")
+            ew = (dw.double() - ref_w).abs().max().item() / den_w
+            eb = (db.double() - ref_b).abs().max().item() / den_b
+            assert ew < 3e-7 and eb < 3e-7, (m, scale, tc, ew, eb)
+            outs.append((dw.clone(), db.clone()))
+        assert torch.equal(outs[0][0], outs[2][0]) and torch.equal(outs[0][1], outs[2][1])       # deterministic
+        # accumulate on top of an existing gradient
+        dw0 = torch.randn(128, 128, generator=g).to(DEV)
+        dw = dw0.clone()
+        _lib.check(lib.cns_weight_grad(_lib.ptr(dy), 128, _lib.ptr(x), 128, m, _lib.ptr(dw), None, 1, 1,
+                                       _lib.ptr(ws), ws.numel(), _sp()), "cns_weight_grad")
+        assert (dw.double() - dw0.double() - ref_w).abs().max().item() / (den_w + 1) < 3e-7
+    # strided operands (columns of a wider matrix), as the backward pass passes them
+    m = 9000
+    wide = torch.randn(m, 256, generator=g).to(DEV)
+    x = torch.randn(m, 128, generator=g).to(DEV)
+    dw = torch.empty(128, 128, device=DEV)
+    _lib.check(lib.cns_weight_grad(C.c_void_p(wide.data_ptr() + 128 * 4), 256, _lib.ptr(x), 128, m, _lib.ptr(dw), None, 0, 1,
+                                   _lib.ptr(ws), ws.numel(), _sp()), "cns_weight_grad")
+    ref = wide[:, 128:].double().t() @ x.double()
+    assert (dw.double() - ref).abs().max().item() / ref.abs().max().item() < 1e-6
