@@ -16,10 +16,11 @@ namespace cns {
 
 namespace {
 
-constexpr int GS_THREADS = 288;
+constexpr int GS_THREADS = 13 * 32;        // gemm_split: warps 0-3 epilogue, 4-11 operand split, 12 MMA issue
+constexpr int DW_THREADS = 17 * 32;        // dw_split: warps 0-7 split A (+ epilogue), 8-15 split B, 16 MMA issue
 constexpr uint32_t GS_SLICE = 128 * 128 * 2;                    // one bf16 slice of a 128 x 128 operand
 constexpr size_t GS_SMEM = 6 * GS_SLICE + 128 * 4 + 128 + 1024; // A slices, W slices, bias, barriers, alignment slack
-constexpr size_t GS_DW_SMEM = 6 * GS_SLICE + 8 * 128 * 4 + 128 + 1024;
+constexpr size_t GS_DW_SMEM = 6 * GS_SLICE + 16 * 128 * 4 + 128 + 1024;
 
 __device__ __forceinline__ void split3(float v, unsigned short& h, unsigned short& m, unsigned short& l) {
   const __nv_bfloat16 bh = __float2bfloat16_rn(v);
@@ -27,6 +28,48 @@ __device__ __forceinline__ void split3(float v, unsigned short& h, unsigned shor
   const __nv_bfloat16 bm = __float2bfloat16_rn(r1);
   const float r2 = r1 - __bfloat162float(bm);                   // exact
   h = __bfloat16_as_ushort(bh); m = __bfloat16_as_ushort(bm); l = __bfloat16_as_ushort(__float2bfloat16_rn(r2));
+}
+
+
+// Split NB x (row, 8 consecutive columns) chunks of a 128-row block per call: all 2 NB loads are issued before the
+// first use, so a thread keeps 32 NB bytes in flight (the loop is a pure stream; one chunk at a time leaves HBM idle).
+template <int NB>
+__device__ __forceinline__ void split_rows(const float* __restrict__ src, int64_t ld, int64_t m0, int64_t m_end, int q0,
+                                           int q_stride, unsigned char* dst, float* cs) {
+  float4 lo[NB], hi[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const int q = q0 + j * q_stride;
+    const int64_t m = m0 + (q >> 4);
+    const int c = (q & 15) * 8;
+    if (m < m_end) {
+      lo[j] = *reinterpret_cast<const float4*>(src + m * ld + c);
+      hi[j] = *reinterpret_cast<const float4*>(src + m * ld + c + 4);
+    } else {
+      lo[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      hi[j] = lo[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const int q = q0 + j * q_stride;
+    const float v[8] = {lo[j].x, lo[j].y, lo[j].z, lo[j].w, hi[j].x, hi[j].y, hi[j].z, hi[j].w};
+    if (cs) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cs[i] += v[i];
+    }
+    unsigned short h[8], md[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split3(v[i], h[i], md[i], l[i]);
+    auto pk4 = [](const unsigned short* t) {
+      return make_uint4((uint32_t)t[0] | ((uint32_t)t[1] << 16), (uint32_t)t[2] | ((uint32_t)t[3] << 16),
+                        (uint32_t)t[4] | ((uint32_t)t[5] << 16), (uint32_t)t[6] | ((uint32_t)t[7] << 16));
+    };
+    const uint32_t off = sw128_off(128, q >> 4, (q & 15) * 8);
+    *reinterpret_cast<uint4*>(dst + off) = pk4(h);
+    *reinterpret_cast<uint4*>(dst + GS_SLICE + off) = pk4(md);
+    *reinterpret_cast<uint4*>(dst + 2 * GS_SLICE + off) = pk4(l);
+  }
 }
 
 __global__ void split_pack_kernel(const float* __restrict__ wt, unsigned char* __restrict__ img) {
@@ -51,7 +94,7 @@ struct SplitArgs {
 __global__ void __launch_bounds__(GS_THREADS, 1)
 gemm_split_kernel(const __grid_constant__ SplitArgs p) {
   // persistent: one CTA per SM walks the 128-row tiles.  Roles: warps 0-3 epilogue (thread = TMEM lane = row),
-  // warps 4-7 split the next tile's rows into the three operand images, warp 8 issues the MMAs.  The fp32
+  // warps 4-11 split the next tile's rows into the three operand images, warp 12 issues the MMAs.  The fp32
   // accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the split and the MMAs of tile i+1.
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -65,10 +108,10 @@ gemm_split_kernel(const __grid_constant__ SplitArgs p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = (int)((p.m + 127) / 128);
 
-  if (warp == 8) {
+  if (warp == 12) {
     if (lane == 0) {
       mbar_init(w_full, 1);
-      mbar_init(a_full, 128);
+      mbar_init(a_full, 256);
       mbar_init(mma_done0, 1); mbar_init(mma_done0 + 8, 1);
       mbar_init(d_free0, 128); mbar_init(d_free0 + 8, 128);
       fence_mbar_init();
@@ -87,7 +130,7 @@ gemm_split_kernel(const __grid_constant__ SplitArgs p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  if (warp == 8) {
+  if (warp == 12) {
     if (lane == 0) {
       // bf16 x bf16 -> fp32, M = 128, N = 128, both operands K-major
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
@@ -120,30 +163,7 @@ gemm_split_kernel(const __grid_constant__ SplitArgs p) {
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int64_t m0 = (int64_t)tile * 128;
       if (it > 0) mbar_wait(mma_done0 + 8 * ((it - 1) & 1), (uint32_t)(((it - 1) >> 1) & 1));   // previous tile's MMAs read A
-      for (int q = ct; q < 128 * 16; q += 128) {
-        const int row = q >> 4, k = (q & 15) * 8;
-        const int64_t m = m0 + row;
-        float v[8];
-        if (m < p.m) {
-          const float4 lo = *reinterpret_cast<const float4*>(p.x + m * 128 + k);
-          const float4 hi = *reinterpret_cast<const float4*>(p.x + m * 128 + k + 4);
-          v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        }
-        unsigned short h[8], md[8], l[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) split3(v[i], h[i], md[i], l[i]);
-        auto pk4 = [](const unsigned short* s) {
-          return make_uint4((uint32_t)s[0] | ((uint32_t)s[1] << 16), (uint32_t)s[2] | ((uint32_t)s[3] << 16),
-                            (uint32_t)s[4] | ((uint32_t)s[5] << 16), (uint32_t)s[6] | ((uint32_t)s[7] << 16));
-        };
-        const uint32_t off = sw128_off(128, row, k);
-        *reinterpret_cast<uint4*>(a_s + off) = pk4(h);
-        *reinterpret_cast<uint4*>(a_s + GS_SLICE + off) = pk4(md);
-        *reinterpret_cast<uint4*>(a_s + 2 * GS_SLICE + off) = pk4(l);
-      }
+      split_rows<8>(p.x, 128, m0, p.m, ct, 256, a_s, nullptr);
       fence_proxy_async();
       mbar_arrive(a_full);
     }
@@ -189,7 +209,7 @@ gemm_split_kernel(const __grid_constant__ SplitArgs p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 8) tmem_dealloc(tmem_base, 256);
+  if (warp == 12) tmem_dealloc(tmem_base, 256);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -214,14 +234,14 @@ __device__ __forceinline__ uint64_t mn128_desc(uint32_t smem_addr) {
   return d;
 }
 
-__global__ void __launch_bounds__(GS_THREADS, 1)
+__global__ void __launch_bounds__(DW_THREADS, 1)
 dw_split_kernel(const __grid_constant__ DwSplitArgs p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* a_s = smem;                           // [3 slices][2 column blocks][128 rows][128 B]
   unsigned char* b_s = smem + 3 * GS_SLICE;
-  float* cs_s = reinterpret_cast<float*>(b_s + 3 * GS_SLICE);          // [8][128] column-sum staging
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cs_s + 8 * 128);
+  float* cs_s = reinterpret_cast<float*>(b_s + 3 * GS_SLICE);          // [16][128] column-sum staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cs_s + 16 * 128);
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 4);
   const uint32_t full = smem_u32(&bars[0]), mma_done = smem_u32(&bars[1]);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -229,9 +249,9 @@ dw_split_kernel(const __grid_constant__ DwSplitArgs p) {
   const int blk0 = blockIdx.x * p.blocks_per_cta;
   const int blk1 = min(n_blocks, blk0 + p.blocks_per_cta);
 
-  if (warp == 8) {
+  if (warp == 16) {
     if (lane == 0) {
-      mbar_init(full, 256);
+      mbar_init(full, 512);
       mbar_init(mma_done, 1);
       fence_mbar_init();
     }
@@ -243,7 +263,7 @@ dw_split_kernel(const __grid_constant__ DwSplitArgs p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  if (warp == 8) {
+  if (warp == 16) {
     if (lane == 0) {
       // bf16 x bf16 -> fp32, M = 128, N = 128, A and B MN-major (bits 15 / 16)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
@@ -264,9 +284,9 @@ dw_split_kernel(const __grid_constant__ DwSplitArgs p) {
       }
     }
   } else {
-    // warps 0-3 split the A rows, warps 4-7 the B rows of the block
-    const bool is_b = warp >= 4;
-    const int ct = tid & 127;
+    // warps 0-7 split the A rows, warps 8-15 the B rows of the block
+    const bool is_b = warp >= 8;
+    const int ct = tid & 255;
     const float* __restrict__ src = is_b ? p.b : p.a;
     const int ld = is_b ? p.ldb : p.lda;
     unsigned char* dst = is_b ? b_s : a_s;
@@ -276,51 +296,25 @@ dw_split_kernel(const __grid_constant__ DwSplitArgs p) {
     for (int blk = blk0, it = 0; blk < blk1; ++blk, ++it) {
       const int64_t m0 = (int64_t)blk * 128;
       if (it > 0) mbar_wait(mma_done, (uint32_t)((it - 1) & 1));
-      for (int q = ct; q < 128 * 16; q += 128) {
-        const int row = q >> 4, c = (q & 15) * 8;
-        const int64_t m = m0 + row;
-        float v[8];
-        if (m < p.m) {
-          const float4 lo = *reinterpret_cast<const float4*>(src + m * ld + c);
-          const float4 hi = *reinterpret_cast<const float4*>(src + m * ld + c + 4);
-          v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        }
-        if (!is_b) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) cs[i] += v[i];    // column sums of A (bias gradient), fixed order per thread
-        }
-        unsigned short h[8], md[8], l[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) split3(v[i], h[i], md[i], l[i]);
-        auto pk4 = [](const unsigned short* s) {
-          return make_uint4((uint32_t)s[0] | ((uint32_t)s[1] << 16), (uint32_t)s[2] | ((uint32_t)s[3] << 16),
-                            (uint32_t)s[4] | ((uint32_t)s[5] << 16), (uint32_t)s[6] | ((uint32_t)s[7] << 16));
-        };
-        const uint32_t off = sw128_off(128, row, c);
-        *reinterpret_cast<uint4*>(dst + off) = pk4(h);
-        *reinterpret_cast<uint4*>(dst + GS_SLICE + off) = pk4(md);
-        *reinterpret_cast<uint4*>(dst + 2 * GS_SLICE + off) = pk4(l);
-      }
+      for (int q0 = ct; q0 < 128 * 16; q0 += 4 * 256) split_rows<4>(src, ld, m0, p.m, q0, 256, dst, is_b ? nullptr : cs);
       fence_proxy_async();
       mbar_arrive(full);
     }
-    // column sums: thread ct owns columns (ct & 15) * 8 .. + 7 for the rows (ct >> 4) + 8 j
+    // column sums: thread ct owns columns (ct & 15) * 8 .. + 7 for the rows (ct >> 4) + 16 j
     if (!is_b && p.colsum_partial) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) cs_s[(ct >> 4) * 128 + (ct & 15) * 8 + i] = cs[i];
     }
-    named_bar(1, 256);
-    if (!is_b && p.colsum_partial) {
+    named_bar(1, 512);
+    if (tid < 128 && p.colsum_partial) {
       float t = 0.f;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) t += cs_s[r * 128 + ct];
-      p.colsum_partial[(size_t)blockIdx.x * 128 + ct] = t;
+      for (int r = 0; r < 16; ++r) t += cs_s[r * 128 + tid];
+      p.colsum_partial[(size_t)blockIdx.x * 128 + tid] = t;
     }
-    // epilogue: the CTA's partial product, thread = row i, 64 columns per warp group
+    // epilogue (warps 0-7): the CTA's partial product, thread = row i, 64 columns per warp group
     const int n_it = blk1 - blk0;
+    if (warp < 8) {
     const int wq = warp & 3, half = warp >> 2;
     float* prow = p.partial + ((size_t)blockIdx.x * 128 + wq * 32 + lane) * 128 + half * 64;
     if (n_it > 0) {
@@ -341,11 +335,12 @@ dw_split_kernel(const __grid_constant__ DwSplitArgs p) {
       for (int q = 0; q < 32; q += 4)
         *reinterpret_cast<float4*>(prow + sub * 32 + q) = make_float4(acc[q], acc[q + 1], acc[q + 2], acc[q + 3]);
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 8) tmem_dealloc(tmem_base, 128);
+  if (warp == 16) tmem_dealloc(tmem_base, 128);
 }
 
 }  // namespace
@@ -400,7 +395,7 @@ int dw_split(int64_t m, const float* a, int lda, const float* b, int ldb, float*
   p.m = m; p.a = a; p.lda = lda; p.b = b; p.ldb = ldb; p.partial = partial; p.colsum_partial = colsum_partial;
   p.blocks_per_cta = (n_blocks + ctas - 1) / ctas;
   ctas = (n_blocks + p.blocks_per_cta - 1) / p.blocks_per_cta;
-  dw_split_kernel<<<ctas, GS_THREADS, GS_DW_SMEM, s>>>(p);
+  dw_split_kernel<<<ctas, DW_THREADS, GS_DW_SMEM, s>>>(p);
   CNS_LAUNCH_CHECK();
   *n_slabs = ctas;
   return CNS_OK;
