@@ -16,10 +16,11 @@ namespace cns {
 
 namespace {
 
-constexpr int GS_THREADS = 13 * 32;        // gemm_split: warps 0-3 epilogue, 4-11 operand split, 12 MMA issue
+constexpr int GS_THREADS = 17 * 32;        // gemm_split: warps 0-7 epilogue, 8-15 operand split, 16 MMA issue
 constexpr int DW_THREADS = 17 * 32;        // dw_split: warps 0-7 split A (+ epilogue), 8-15 split B, 16 MMA issue
 constexpr uint32_t GS_SLICE = 128 * 128 * 2;                    // one bf16 slice of a 128 x 128 operand
-constexpr size_t GS_SMEM = 6 * GS_SLICE + 128 * 4 + 128 + 1024; // A slices, W slices, bias, barriers, alignment slack
+constexpr int GS_STAGE_LD = 20;                                 // floats per staged 16-column row (16-byte aligned, conflict-free)
+constexpr size_t GS_SMEM = 6 * GS_SLICE + 128 * 4 + 128 + 8 * 32 * GS_STAGE_LD * 4 + 1024;   // A, W slices, bias, barriers, epilogue tiles, slack
 constexpr size_t GS_DW_SMEM = 6 * GS_SLICE + 16 * 128 * 4 + 128 + 1024;
 
 __device__ __forceinline__ void split3(float v, unsigned short& h, unsigned short& m, unsigned short& l) {
@@ -30,45 +31,60 @@ __device__ __forceinline__ void split3(float v, unsigned short& h, unsigned shor
   h = __bfloat16_as_ushort(bh); m = __bfloat16_as_ushort(bm); l = __bfloat16_as_ushort(__float2bfloat16_rn(r2));
 }
 
+// the same for two neighbouring elements with packed conversions (cvt.rn.bf16x2.f32 instead of three F2F each):
+// returns the packed (a | b << 16) words of the three slices
+__device__ __forceinline__ void split3x2(float a, float b, uint32_t& h, uint32_t& m, uint32_t& l) {
+  auto pack = [](float x, float y) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(x, y);
+    return *reinterpret_cast<uint32_t*>(&t);
+  };
+  h = pack(a, b);
+  const float ra = a - __uint_as_float(h << 16), rb = b - __uint_as_float(h & 0xffff0000u);
+  m = pack(ra, rb);
+  l = pack(ra - __uint_as_float(m << 16), rb - __uint_as_float(m & 0xffff0000u));
+}
 
-// Split NB x (row, 8 consecutive columns) chunks of a 128-row block per call: all 2 NB loads are issued before the
-// first use, so a thread keeps 32 NB bytes in flight (the loop is a pure stream; one chunk at a time leaves HBM idle).
+// A thread's share of a 128-row block: NB x (row, 8 consecutive columns) chunks.  Loading and splitting are separate
+// steps so the loads of the NEXT block are in flight (32 NB bytes per thread) while the tensor core still reads the
+// current operand images - the loop is a pure stream and would otherwise expose the HBM latency once per tile.
 template <int NB>
-__device__ __forceinline__ void split_rows(const float* __restrict__ src, int64_t ld, int64_t m0, int64_t m_end, int q0,
-                                           int q_stride, unsigned char* dst, float* cs) {
-  float4 lo[NB], hi[NB];
+struct RowChunks { float4 lo[NB], hi[NB]; };
+
+template <int NB>
+__device__ __forceinline__ void load_rows(RowChunks<NB>& r, const float* __restrict__ src, int64_t ld, int64_t m0, int64_t m_end,
+                                          int q0, int q_stride) {
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
     const int q = q0 + j * q_stride;
     const int64_t m = m0 + (q >> 4);
     const int c = (q & 15) * 8;
     if (m < m_end) {
-      lo[j] = *reinterpret_cast<const float4*>(src + m * ld + c);
-      hi[j] = *reinterpret_cast<const float4*>(src + m * ld + c + 4);
+      r.lo[j] = *reinterpret_cast<const float4*>(src + m * ld + c);
+      r.hi[j] = *reinterpret_cast<const float4*>(src + m * ld + c + 4);
     } else {
-      lo[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      hi[j] = lo[j];
+      r.lo[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      r.hi[j] = r.lo[j];
     }
   }
+}
+
+template <int NB>
+__device__ __forceinline__ void split_store_rows(const RowChunks<NB>& r, int q0, int q_stride, unsigned char* dst, float* cs) {
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
     const int q = q0 + j * q_stride;
-    const float v[8] = {lo[j].x, lo[j].y, lo[j].z, lo[j].w, hi[j].x, hi[j].y, hi[j].z, hi[j].w};
+    const float v[8] = {r.lo[j].x, r.lo[j].y, r.lo[j].z, r.lo[j].w, r.hi[j].x, r.hi[j].y, r.hi[j].z, r.hi[j].w};
     if (cs) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) cs[i] += v[i];
     }
-    unsigned short h[8], md[8], l[8];
+    uint32_t h[4], md[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) split3(v[i], h[i], md[i], l[i]);
-    auto pk4 = [](const unsigned short* t) {
-      return make_uint4((uint32_t)t[0] | ((uint32_t)t[1] << 16), (uint32_t)t[2] | ((uint32_t)t[3] << 16),
-                        (uint32_t)t[4] | ((uint32_t)t[5] << 16), (uint32_t)t[6] | ((uint32_t)t[7] << 16));
-    };
+    for (int i = 0; i < 4; ++i) split3x2(v[2 * i], v[2 * i + 1], h[i], md[i], l[i]);
     const uint32_t off = sw128_off(128, q >> 4, (q & 15) * 8);
-    *reinterpret_cast<uint4*>(dst + off) = pk4(h);
-    *reinterpret_cast<uint4*>(dst + GS_SLICE + off) = pk4(md);
-    *reinterpret_cast<uint4*>(dst + 2 * GS_SLICE + off) = pk4(l);
+    *reinterpret_cast<uint4*>(dst + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(dst + GS_SLICE + off) = make_uint4(md[0], md[1], md[2], md[3]);
+    *reinterpret_cast<uint4*>(dst + 2 * GS_SLICE + off) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
@@ -93,8 +109,8 @@ struct SplitArgs {
 
 __global__ void __launch_bounds__(GS_THREADS, 1)
 gemm_split_kernel(const __grid_constant__ SplitArgs p) {
-  // persistent: one CTA per SM walks the 128-row tiles.  Roles: warps 0-3 epilogue (thread = TMEM lane = row),
-  // warps 4-11 split the next tile's rows into the three operand images, warp 12 issues the MMAs.  The fp32
+  // persistent: one CTA per SM walks the 128-row tiles.  Roles: warps 0-7 epilogue, warps 8-15 split the
+  // next tile's rows into the three operand images, warp 16 issues the MMAs.  The fp32
   // accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the split and the MMAs of tile i+1.
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -103,17 +119,18 @@ gemm_split_kernel(const __grid_constant__ SplitArgs p) {
   float* bias_s = reinterpret_cast<float*>(w_s + 3 * GS_SLICE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 128);
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 8);
+  float* stage_s = reinterpret_cast<float*>(bars + 16);           // [8 warps][32 rows][GS_STAGE_LD]
   const uint32_t w_full = smem_u32(&bars[0]), a_full = smem_u32(&bars[1]);
   const uint32_t mma_done0 = smem_u32(&bars[2]), d_free0 = smem_u32(&bars[4]);      // [2], [2]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = (int)((p.m + 127) / 128);
 
-  if (warp == 12) {
+  if (warp == 16) {
     if (lane == 0) {
       mbar_init(w_full, 1);
       mbar_init(a_full, 256);
       mbar_init(mma_done0, 1); mbar_init(mma_done0 + 8, 1);
-      mbar_init(d_free0, 128); mbar_init(d_free0 + 8, 128);
+      mbar_init(d_free0, 256); mbar_init(d_free0 + 8, 256);
       fence_mbar_init();
     }
     __syncwarp();
@@ -130,7 +147,7 @@ gemm_split_kernel(const __grid_constant__ SplitArgs p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  if (warp == 12) {
+  if (warp == 16) {
     if (lane == 0) {
       // bf16 x bf16 -> fp32, M = 128, N = 128, both operands K-major
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
@@ -156,49 +173,70 @@ gemm_split_kernel(const __grid_constant__ SplitArgs p) {
         umma_commit(mma_done0 + 8 * buf);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 8) {
     // ---- operand split: 8 consecutive k of one row per step -> one 16-byte store into each slice image ----
-    const int ct = tid - 128;
+    const int ct = tid - 256;
+    RowChunks<8> rows;
+    if ((int)blockIdx.x < n_tiles) load_rows<8>(rows, p.x, 128, (int64_t)blockIdx.x * 128, p.m, ct, 256);
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int64_t m0 = (int64_t)tile * 128;
       if (it > 0) mbar_wait(mma_done0 + 8 * ((it - 1) & 1), (uint32_t)(((it - 1) >> 1) & 1));   // previous tile's MMAs read A
-      split_rows<8>(p.x, 128, m0, p.m, ct, 256, a_s, nullptr);
+      split_store_rows<8>(rows, ct, 256, a_s, nullptr);
       fence_proxy_async();
       mbar_arrive(a_full);
+      const int next = tile + gridDim.x;
+      if (next < n_tiles) load_rows<8>(rows, p.x, 128, (int64_t)next * 128, p.m, ct, 256);      // in flight during the MMAs
     }
   } else {
-    // ---- epilogue: thread = row (TMEM lane), all 128 columns in four 32-column reads ----
+    // ---- epilogue (warps 0-7: TMEM lane quarter = warp & 3, column half = warp >> 2).  A TMEM read hands every lane
+    // one ROW; going to global memory like that costs one L1 sector cycle per 16 bytes (32 rows per instruction) and
+    // was measured to double the kernel time.  Each warp therefore turns 32 x 16 sub-chunks through a private
+    // shared-memory tile and moves residual / gate / output with 4 lanes per row (64 contiguous bytes).  All loads of
+    // a sub-chunk are issued before its first store: y may alias the residual, so the compiler would otherwise
+    // serialise load -> store -> load.
+    float* stage = stage_s + warp * (32 * GS_STAGE_LD);
+    const int wq = warp & 3, ch = warp >> 2;
+    const int er = lane >> 2, ec = (lane & 3) * 4;          // this lane's row (mod 8) and column within the sub-chunk
+    const bool has_res = p.residual != nullptr, has_gate = p.relu_gate != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
-      const int64_t m = (int64_t)tile * 128 + warp * 32 + lane;
-      const bool live = m < p.m;
+      const int64_t mw = (int64_t)tile * 128 + wq * 32;      // first row of this warp
       mbar_wait(mma_done0 + 8 * buf, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
 #pragma unroll 1
-      for (int n0 = 0; n0 < 128; n0 += 32) {
+      for (int c = 0; c < 2; ++c) {
+        const int n0 = ch * 64 + c * 32;
         float acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 128 + n0), acc);
-        tmem_ld_wait();
-        if (live) {
-          float* yrow = p.y + m * 128 + n0;
-          const float* rrow = p.residual ? p.residual + m * 128 + n0 : nullptr;
-          const float* grow = p.relu_gate ? p.relu_gate + m * 128 + n0 : nullptr;
+        tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * 128 + n0), acc);
 #pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n0 + q);
-            float4 v = make_float4(acc[q] + b4.x, acc[q + 1] + b4.y, acc[q + 2] + b4.z, acc[q + 3] + b4.w);
-            if (rrow) {
-              const float4 r = *reinterpret_cast<const float4*>(rrow + q);
-              v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-            }
+        for (int hf = 0; hf < 2; ++hf) {
+          const int nb = n0 + 16 * hf;
+          float4 res[4], gate[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int64_t m = mw + 8 * j + er;
+            const bool ok = m < p.m;
+            res[j] = (ok && has_res) ? *reinterpret_cast<const float4*>(p.residual + m * 128 + nb + ec) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gate[j] = (ok && has_gate) ? *reinterpret_cast<const float4*>(p.relu_gate + m * 128 + nb + ec) : make_float4(1.f, 1.f, 1.f, 1.f);
+          }
+          if (hf == 0) tmem_ld_wait();
+          __syncwarp();                                      // the previous sub-chunk has been read out of `stage`
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(stage + lane * GS_STAGE_LD + 4 * q) =
+                make_float4(acc[16 * hf + 4 * q], acc[16 * hf + 4 * q + 1], acc[16 * hf + 4 * q + 2], acc[16 * hf + 4 * q + 3]);
+          __syncwarp();
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + nb + ec);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int64_t m = mw + 8 * j + er;
+            const float4 a4 = *reinterpret_cast<const float4*>(stage + (8 * j + er) * GS_STAGE_LD + ec);
+            float4 v = make_float4(a4.x + b4.x + res[j].x, a4.y + b4.y + res[j].y, a4.z + b4.z + res[j].z, a4.w + b4.w + res[j].w);
             if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            if (grow) {
-              const float4 g = *reinterpret_cast<const float4*>(grow + q);
-              v.x = g.x > 0.f ? v.x : 0.f; v.y = g.y > 0.f ? v.y : 0.f; v.z = g.z > 0.f ? v.z : 0.f; v.w = g.w > 0.f ? v.w : 0.f;
-            }
-            *reinterpret_cast<float4*>(yrow + q) = v;
+            v.x = gate[j].x > 0.f ? v.x : 0.f; v.y = gate[j].y > 0.f ? v.y : 0.f;
+            v.z = gate[j].z > 0.f ? v.z : 0.f; v.w = gate[j].w > 0.f ? v.w : 0.f;
+            if (m < p.m) *reinterpret_cast<float4*>(p.y + m * 128 + nb + ec) = v;
           }
         }
       }
@@ -209,7 +247,7 @@ gemm_split_kernel(const __grid_constant__ SplitArgs p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 12) tmem_dealloc(tmem_base, 256);
+  if (warp == 16) tmem_dealloc(tmem_base, 256);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -293,12 +331,14 @@ dw_split_kernel(const __grid_constant__ DwSplitArgs p) {
     float cs[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) cs[i] = 0.f;
+    RowChunks<8> rows;
+    if (blk0 < blk1) load_rows<8>(rows, src, ld, (int64_t)blk0 * 128, p.m, ct, 256);
     for (int blk = blk0, it = 0; blk < blk1; ++blk, ++it) {
-      const int64_t m0 = (int64_t)blk * 128;
       if (it > 0) mbar_wait(mma_done, (uint32_t)((it - 1) & 1));
-      for (int q0 = ct; q0 < 128 * 16; q0 += 4 * 256) split_rows<4>(src, ld, m0, p.m, q0, 256, dst, is_b ? nullptr : cs);
+      split_store_rows<8>(rows, ct, 256, dst, is_b ? nullptr : cs);
       fence_proxy_async();
       mbar_arrive(full);
+      if (blk + 1 < blk1) load_rows<8>(rows, src, ld, (int64_t)(blk + 1) * 128, p.m, ct, 256);   // in flight during the MMAs
     }
     // column sums: thread ct owns columns (ct & 15) * 8 .. + 7 for the rows (ct >> 4) + 16 j
     if (!is_b && p.colsum_partial) {
