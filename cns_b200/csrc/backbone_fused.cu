@@ -438,11 +438,10 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
 
 int backbone_fused(const BackboneFusedArgs& a, bool bf16, cudaStream_t s) {
   if (a.n_graphs == 0 || a.n_clusters == 0) return CNS_OK;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured)) {
     CNS_CUDA_CHECK(cudaFuncSetAttribute(backbone_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BF_SMEM));
     CNS_CUDA_CHECK(cudaFuncSetAttribute(backbone_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BF_SMEM));
-    configured = true;
   }
   // greedy whole-graph tiles: two consecutive tiles always hold more than 128 rows together
   int64_t grid = 2 * ceil_div(a.n_clusters, 128) + 1;

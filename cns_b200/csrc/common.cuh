@@ -36,6 +36,16 @@ extern long long g_launch_count;   // kernels launched by this library (host-sid
     }                                                            \
   } while (0)
 
+// Function attributes (dynamic shared memory opt-in) are per device: true the first time `seen` meets the current one.
+inline bool first_use_on_device(unsigned long long& seen) {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) return true;
+  const unsigned long long bit = 1ull << (d & 63);
+  if (seen & bit) return false;
+  seen |= bit;
+  return true;
+}
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -382,11 +382,10 @@ int enc_cluster_pre(const EncPreArgs& a, cudaStream_t s) {
 
 int enc_edge_fp32(const EncEdgeArgs& a, cudaStream_t s) {
   if (a.n_e01 == 0) return CNS_OK;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured)) {
     CNS_CUDA_CHECK(cudaFuncSetAttribute(enc_edge_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(EncSmem)));
-    configured = true;
   }
   dim3 grid(ceil_div(a.n_e01, TE), 2);
   enc_edge_fp32_kernel<<<grid, 256, sizeof(EncSmem), s>>>(a);

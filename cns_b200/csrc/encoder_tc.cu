@@ -514,11 +514,10 @@ constexpr size_t TC_SMEM_BYTES = TC_NW * TC_W_BYTES + TC_ACT_BYTES + 256 + 2 * 1
 
 template <int TN, bool BF16>
 static int launch_tc(const EncEdgeArgs& a, const unsigned char* w_img, const cns_handle* h, cudaStream_t s) {
-  static bool configured = false;
+  static unsigned long long configured = 0;
   auto kern = enc_edge_tc_kernel<TN, BF16>;
-  if (!configured) {
+  if (first_use_on_device(configured)) {
     CNS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-    configured = true;
   }
   TcArgs ta;
   ta.e = a;

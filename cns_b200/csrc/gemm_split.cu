@@ -396,15 +396,14 @@ int gemm_split(const LinearArgs& a, const unsigned char* w_img, cudaStream_t s) 
   if (a.m == 0) return CNS_OK;
   CNS_REQUIRE(a.k1 == 128 && a.k2 == 0 && a.n_out == 128 && a.pos == nullptr && w_img != nullptr,
               "gemm_split: 128 x 128 layers without a position term only");
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured)) {
     CNS_CUDA_CHECK(cudaFuncSetAttribute(gemm_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
-    configured = true;
   }
   SplitArgs p;
   p.m = a.m; p.x = a.x1; p.w_img = w_img; p.bias = a.bias; p.residual = a.residual; p.relu_gate = a.relu_gate;
   p.relu = a.relu; p.y = a.y;
-  static int n_sm = 0;
+  static int n_sm = 0;      // one process per GPU model: every device of a box has the same SM count
   if (!n_sm) {
     int dev = 0;
     CNS_CUDA_CHECK(cudaGetDevice(&dev));
@@ -419,14 +418,13 @@ int gemm_split(const LinearArgs& a, const unsigned char* w_img, cudaStream_t s) 
 // stage 1 of dw_gemm for a single 128 x 128 output tile on the tensor cores; returns the number of partials
 int dw_split(int64_t m, const float* a, int lda, const float* b, int ldb, float* partial, float* colsum_partial, int max_slabs,
              int* n_slabs, cudaStream_t s) {
-  static bool configured = false;
+  static unsigned long long configured = 0;
   static int n_sm = 0;
-  if (!configured) {
+  if (first_use_on_device(configured)) {
     int dev = 0;
     CNS_CUDA_CHECK(cudaGetDevice(&dev));
     CNS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     CNS_CUDA_CHECK(cudaFuncSetAttribute(dw_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_DW_SMEM));
-    configured = true;
   }
   const int n_blocks = ceil_div(m, 128);
   int ctas = n_blocks < n_sm ? n_blocks : n_sm;

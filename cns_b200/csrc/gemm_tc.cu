@@ -177,11 +177,10 @@ int gemm_tc(const GemmTcArgs& a, bool bf16, cudaStream_t s) {
   CNS_REQUIRE(a.n_out % 128 == 0 && a.n_out <= 512, "gemm_tc: n_out must be 128..512, multiple of 128");
   CNS_REQUIRE((a.k1 == 128 || a.k1 == 256) && (a.k2 == 0 || a.k2 == 128) && a.k1 + a.k2 <= 256, "gemm_tc: K must be 128 or 256");
   CNS_REQUIRE(a.w_img != nullptr, "gemm_tc: weight image missing");
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured)) {
     CNS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmTcSmem::TOTAL));
     CNS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmTcSmem::TOTAL));
-    configured = true;
   }
   const int grid = ceil_div(a.m, 128);
   const size_t smem = (size_t)3 * 128 * (a.k1 + a.k2) * 2 + GemmTcSmem::VEC_FLOATS * 4 + 256 + 1024;

@@ -129,6 +129,42 @@ __global__ void csr_count_kernel(const int64_t* __restrict__ dst, int64_t n_edge
   atomicAdd(&deg[i], 1);
 }
 
+// Ascending in-place sort of one CSR row.  The fill kernels place edges with an atomic cursor, so the order inside a
+// row depends on scheduling; sorting makes the CSR - and with it every sum over a row in the backward pass and the
+// tie-breaking of the arg-max - identical from run to run.  Rows are short (cluster graphs: <= a few dozen entries).
+__device__ __forceinline__ void sort_row_i32(int* __restrict__ a, int n) {
+  if (n <= 48) {
+    for (int i = 1; i < n; ++i) {
+      const int v = a[i];
+      int j = i - 1;
+      while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; --j; }
+      a[j + 1] = v;
+    }
+    return;
+  }
+  auto sift = [&](int root, int end) {        // heap sort for the rare long row
+    for (;;) {
+      int child = 2 * root + 1;
+      if (child >= end) break;
+      if (child + 1 < end && a[child] < a[child + 1]) ++child;
+      if (a[root] >= a[child]) break;
+      const int t = a[root]; a[root] = a[child]; a[child] = t;
+      root = child;
+    }
+  };
+  for (int i = n / 2 - 1; i >= 0; --i) sift(i, n);
+  for (int end = n - 1; end > 0; --end) {
+    const int t = a[0]; a[0] = a[end]; a[end] = t;
+    sift(0, end);
+  }
+}
+
+__global__ void csr_sort_rows_kernel(const int* __restrict__ rowptr, int64_t n_rows, int* __restrict__ out_src) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  sort_row_i32(out_src + rowptr[i], rowptr[i + 1] - rowptr[i]);
+}
+
 __global__ void csr_fill_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                                 int64_t n_edges, int64_t n_rows, const int* __restrict__ rowptr,
                                 int* __restrict__ cursor, int* __restrict__ out_src) {
@@ -161,6 +197,8 @@ int csr_by_dst(const int64_t* ej, const int64_t* ei, int64_t n_edges, int64_t n_
   CNS_CUDA_CHECK(cudaMemsetAsync(cursor, 0, (size_t)(n_rows + 1) * sizeof(int), s));
   if (n_edges > 0) {
     csr_fill_kernel<<<ceil_div(n_edges, 256), 256, 0, s>>>(ej, ei, n_edges, n_rows, rowptr, cursor, src);
+    CNS_LAUNCH_CHECK();
+    csr_sort_rows_kernel<<<ceil_div(n_rows, 128), 128, 0, s>>>(rowptr, n_rows, src);
     CNS_LAUNCH_CHECK();
   }
   return CNS_OK;
@@ -356,6 +394,8 @@ prep_small_kernel(PrepSmallArgs p) {
       const int slot = rowptr[i] + atomicAdd(&cur[i], 1);
       src[slot] = (int)ej[e];
     }
+    __syncthreads();
+    for (int i = tid; i < C; i += 1024) sort_row_i32(src + rowptr[i], rowptr[i + 1] - rowptr[i]);   // canonical order
   }
 }
 

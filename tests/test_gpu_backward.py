@@ -179,3 +179,21 @@ def test_fused_stepper_trains(state_dict):
         st.hidden = None
         losses.append(float(st.step(batches)))
     assert losses[-1] < losses[0]
+
+
+def test_gradients_are_bit_identical_from_run_to_run(state_dict):
+    """No fp atomics and a canonical CSR order: two fresh models on the same inputs give bit-identical gradients,
+    on the FFMA path (few edges) and on the tensor-core split-GEMM path (>= 4096 keypoint->cluster edges)."""
+    from cns_b200 import GraphVS, synth
+    for n_graphs, n_pts in ((12, 150), (24, 400)):
+        batch = synth.make_batch(n_graphs, n_pts, seed=9, n_layouts=3).to("cuda:0")
+        grads = []
+        for _ in range(2):
+            net = GraphVS(2, 2, 128).to("cuda:0")
+            net.load_state_dict(state_dict)
+            net.train()
+            pred = net(batch, None)
+            (pred[0].square().sum() + pred[2].square().sum()).backward()
+            grads.append({n: p.grad.detach().clone() for n, p in net.named_parameters()})
+        bad = [n for n in grads[0] if not torch.equal(grads[0][n], grads[1][n])]
+        assert not bad, (n_graphs, n_pts, bad)

@@ -348,3 +348,30 @@ def test_full_size_batch_properties(net, state_dict):
     with torch.no_grad():
         pp = net(Batch.from_data_list([frames[i] for i in perm]).to("cuda:0"), None)
     assert rel(pp[0], pred[0][torch.as_tensor(perm, device="cuda")]) < 1e-5
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process(state_dict):
+    """Kernel attributes (dynamic shared memory opt-in) are per device: a model on cuda:1 after one on cuda:0, all
+    precision modes and a training step, must give the same results."""
+    batch = synth.make_batch(12, 150, seed=9, n_layouts=3)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        net = GraphVS(2, 2, 128).to(dev)
+        net.load_state_dict(state_dict)
+        net.eval()
+        res = []
+        for prec in ("fp32", "f16", "bf16"):
+            net.set_precision(prec)
+            with torch.no_grad():
+                p = net(batch.to(dev), None)
+            res.append(p.vel.cpu())
+        net.set_precision("fp32")
+        net.train()
+        pred = net(batch.to(dev), None)
+        (pred[0].square().sum() + pred[2].square().sum()).backward()
+        res.append(torch.cat([q.grad.flatten().cpu() for q in net.parameters()]))
+        outs.append(res)
+    for k, (a, b) in enumerate(zip(*outs)):
+        assert torch.isfinite(b).all(), k
+        assert torch.equal(a, b), (k, float((a - b).abs().max()), float(a.abs().max()))
