@@ -225,7 +225,8 @@ int cns_linear(const float* x1, int k1, const float* x2, int k2, const float* wt
  * slices and the six significant slice products accumulate in fp32 (gemm_split.cu).  Used by the backward pass for the
  * edge-level GEMMs (the recomputed PointTransformerConv chain and dX = dY W, graph_vs.py:195-214 under autograd).
  * y = gate(act(x wt + bias + residual)): x (m,128), wt (128,128) row-major (k, n), bias (128) / residual (m,128) /
- * relu_gate (m,128: y = 0 where relu_gate <= 0) optional.  workspace: cns_linear_split_workspace_bytes(). */
+ * relu_gate (m,128: y = 0 where relu_gate <= 0) optional.  y may be the residual buffer (in place); it must not
+ * overlap x or relu_gate.  workspace: cns_linear_split_workspace_bytes(). */
 size_t cns_linear_split_workspace_bytes(void);
 int cns_linear_split(const float* x, int64_t m, const float* wt, const float* bias, const float* residual,
                      const float* relu_gate, int relu, float* y, void* workspace, size_t workspace_bytes, void* stream);
