@@ -131,10 +131,11 @@ int backward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, con
     return dw_gemm(d, s);
   };
   auto dws = [&](const float* a, int lda, int n, const float* sm, int lds, int q, int64_t m, float* out, int ld_out,
-                 int transposed, int accumulate) {
+                 int transposed, int accumulate, float* ones_out = nullptr) {
     DwSmallArgs d{};
     d.m = m; d.n = n; d.q = q; d.a = a; d.lda = lda; d.s = sm; d.lds = lds; d.out = out; d.ld_out = ld_out;
     d.transposed = transposed; d.scale = 1.f; d.accumulate = accumulate; d.partial = w.small_partial; d.max_slabs = w.small_slabs;
+    d.ones_out = ones_out;
     return dw_small(d, s);
   };
   auto colsum = [&](const float* a, int lda, int n, int64_t m, float* out, int accumulate) {
@@ -298,16 +299,13 @@ int backward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, con
     RUN(ew1(EW_ADD, E * H, dT, dV, nullptr, nullptr, tmp, nullptr, nullptr));                      // dDelta
     RUN(dwg(tmp, H, H, HP, H, 1, nullptr, 0, H, E, G(P_POS1_W), H, 1.f, 1, G(P_POS1_B)));
     RUN(lin(tmp, H, h->P(P_POS1_W), H, nullptr, nullptr, 0, E, dL, HP, 9));                           // dHP_pre (reuse dL)
-    RUN(dws(dL, H, H, w.DP, 4, 4, E, G(P_POS0_W), 4, 0, 1));
-    RUN(colsum(dL, H, H, E, G(P_POS0_B), 1));
-    RUN(dws(dX, H, H, w.FE, 2, 2, E, G(P_IN_W), 2, 0, 1));
-    RUN(colsum(dX, H, H, E, G(P_IN_B), 1));
+    RUN(dws(dL, H, H, w.DP, 4, 4, E, G(P_POS0_W), 4, 0, 1, G(P_POS0_B)));
+    RUN(dws(dX, H, H, w.FE, 2, 2, E, G(P_IN_W), 2, 0, 1, G(P_IN_B)));
   }
   // cluster side: a_dst = xt_c lin_dst^T
   RUN(dwg(w.d_adst, H, H, w.xtc, H, 1, nullptr, 0, H, C, G(P_LINDST_W), H, 1.f, 1));
   RUN(lin(w.d_adst, H, h->P(P_LINDST_W), H, nullptr, nullptr, 0, C, w.d_xtc, w.xtc));
-  RUN(dws(w.d_xtc, H, H, w.fe_c, 2, 2, C, G(P_IN_W), 2, 0, 1));
-  RUN(colsum(w.d_xtc, H, H, C, G(P_IN_B), 1));
+  RUN(dws(w.d_xtc, H, H, w.fe_c, 2, 2, C, G(P_IN_W), 2, 0, 1, G(P_IN_B)));
 #undef RUN
   return CNS_OK;
 }

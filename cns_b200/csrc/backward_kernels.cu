@@ -185,6 +185,8 @@ dw_small_kernel(DwSmallArgs p, int rows_per_slab) {
           acc[q] = fmaf(a1, ss[(r + 1) * p.q + q], acc[q]);
           acc[q] = fmaf(a2, ss[(r + 2) * p.q + q], acc[q]);
           acc[q] = fmaf(a3, ss[(r + 3) * p.q + q], acc[q]);
+        } else if (q == p.q && p.ones_out) {
+          acc[q] += (a0 + a1) + (a2 + a3);
         }
     } else {
       acc[0] += (a0 + a1) + (a2 + a3);
@@ -196,11 +198,15 @@ dw_small_kernel(DwSmallArgs p, int rows_per_slab) {
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         if (q < p.q) acc[q] = fmaf(a0, ss[r * p.q + q], acc[q]);
+        else if (q == p.q && p.ones_out) acc[q] += a0;
     } else {
       acc[0] += a0;
     }
   }
-  for (int q = 0; q < p.q; ++q) p.partial[((size_t)slab * p.n + n) * p.q + q] = acc[q];
+  const int qq = p.q + (p.ones_out ? 1 : 0);
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    if (q < qq) p.partial[((size_t)slab * p.n + n) * qq + q] = acc[q];
 }
 
 // fixed-order reduction over the slabs: a CTA owns 32 consecutive outputs, its 8 warps take the slabs k = w mod 8
@@ -211,7 +217,8 @@ reduce_small_kernel(DwSmallArgs p, int n_slabs) {
   __shared__ float part[8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int idx = blockIdx.x * 32 + lane;
-  const int total = p.n * p.q;
+  const int qq = p.q + (p.ones_out ? 1 : 0);
+  const int total = p.n * qq;
   float s0 = 0.f, s1 = 0.f;
   if (idx < total) {
     int k = w;
@@ -227,14 +234,16 @@ reduce_small_kernel(DwSmallArgs p, int n_slabs) {
     float s = 0.f;
 #pragma unroll
     for (int g = 0; g < 8; ++g) s += part[g][lane];
-    const int n = idx / p.q, q = idx % p.q;
-    float* o = p.transposed ? p.out + (size_t)q * p.ld_out + n : p.out + (size_t)n * p.ld_out + q;
+    const int n = idx / qq, q = idx % qq;
+    float* o = q == p.q ? p.ones_out + n
+                        : (p.transposed ? p.out + (size_t)q * p.ld_out + n : p.out + (size_t)n * p.ld_out + q);
     *o = p.accumulate ? *o + p.scale * s : p.scale * s;
   }
 }
 
 int dw_small(const DwSmallArgs& a, cudaStream_t s) {
   CNS_REQUIRE(a.q >= 1 && a.q <= 8, "dw_small: q must be 1..8");
+  CNS_REQUIRE(a.ones_out == nullptr || (a.s != nullptr && a.q <= 7), "dw_small: the fused column sum needs s and q <= 7");
   const int64_t m1 = a.m > 0 ? a.m : 1;
   int slabs = ceil_div(m1, DWS_ROWS);
   if (slabs > a.max_slabs) slabs = a.max_slabs;
@@ -246,7 +255,7 @@ int dw_small(const DwSmallArgs& a, cudaStream_t s) {
   dim3 grid(ceil_div(a.n, 128), slabs);
   dw_small_kernel<<<grid, 128, 0, s>>>(a, rows_per_slab);
   CNS_LAUNCH_CHECK();
-  reduce_small_kernel<<<ceil_div(a.n * a.q, 32), 256, 0, s>>>(a, slabs);
+  reduce_small_kernel<<<ceil_div(a.n * (a.q + (a.ones_out ? 1 : 0)), 32), 256, 0, s>>>(a, slabs);
   CNS_LAUNCH_CHECK();
   return CNS_OK;
 }

@@ -23,6 +23,7 @@ struct DwSmallArgs {
   const float* s; int lds;       // (m, q) or NULL (ones)
   float* out; int ld_out; int transposed; float scale; int accumulate;
   float* partial; int max_slabs;
+  float* ones_out;               // optional (needs s, q <= 7): ones_out[n] (+)= sum_m a[m][n] from the same pass (bias gradient)
 };
 int dw_small(const DwSmallArgs& a, cudaStream_t s);
 
