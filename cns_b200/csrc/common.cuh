@@ -114,8 +114,10 @@ struct cns_handle {
   // pinned / device staging for the *_host entry point
   void* stage_host; size_t stage_host_bytes;
   void* stage_dev;  size_t stage_dev_bytes;
-  // recurrent hidden state of cns_servo_step_host (two ping-pong device buffers inside stage_dev)
+  // recurrent hidden state of cns_servo_step_host: two ping-pong device buffers in their OWN allocation (the layout of
+  // stage_dev changes from frame to frame with the number of visible keypoints / alive clusters)
   int servo_valid; int servo_cur; long long servo_nc;
+  void* servo_hid; size_t servo_hid_bytes;
   // cns_servo_step_host keeps the target-side results while consecutive frames show the same target (host copy of the
   // target arrays = the key)
   struct cns_target_cache* servo_tcache; void* servo_tkey; size_t servo_tkey_bytes;

@@ -479,14 +479,20 @@ int cns_servo_step_host(cns_handle* h, const cns_batch* bh, int reset_hidden, fl
   const size_t out_bytes = align_up((size_t)B * 13 * sizeof(float));
   const size_t hid_bytes = align_up((size_t)C * H * sizeof(float));
   const size_t ws_bytes = cns_forward_workspace_bytes(bh);
-  const size_t dev_need = in_bytes + out_bytes + 2 * hid_bytes + ws_bytes;
+  const size_t dev_need = in_bytes + out_bytes + ws_bytes;
   const size_t host_need = in_bytes + out_bytes;
   if (dev_need > h->stage_dev_bytes) {
     if (h->stage_dev) CNS_CUDA_CHECK(cudaFree(h->stage_dev));
     h->stage_dev = nullptr; h->stage_dev_bytes = 0;
     CNS_CUDA_CHECK(cudaMalloc(&h->stage_dev, dev_need + dev_need / 4));
     h->stage_dev_bytes = dev_need + dev_need / 4;
-    h->servo_valid = 0;
+  }
+  if (2 * hid_bytes > h->servo_hid_bytes) {
+    // a different cluster count: the carried state could not be used anyway (`carry` below needs servo_nc == C)
+    if (h->servo_hid) CNS_CUDA_CHECK(cudaFree(h->servo_hid));
+    h->servo_hid = nullptr; h->servo_hid_bytes = 0; h->servo_valid = 0;
+    CNS_CUDA_CHECK(cudaMalloc(&h->servo_hid, 2 * hid_bytes));
+    h->servo_hid_bytes = 2 * hid_bytes;
   }
   if (host_need > h->stage_host_bytes) {
     if (h->stage_host) CNS_CUDA_CHECK(cudaFreeHost(h->stage_host));
@@ -509,8 +515,9 @@ int cns_servo_step_host(cns_handle* h, const cns_batch* bh, int reset_hidden, fl
   d.num_clusters = (const int64_t*)(db + o_nc);
   d.tPo_norm = bh->tPo_norm ? (const float*)(db + o_tp) : nullptr;
   float* out_d = (float*)(db + in_bytes);                 // vec (B,6) | vel (B,6) | nrm (B,1)
-  float* hid[2] = {(float*)(db + in_bytes + out_bytes), (float*)(db + in_bytes + out_bytes + hid_bytes)};
-  void* ws = db + in_bytes + out_bytes + 2 * hid_bytes;
+  // fixed addresses: slot k of the ping-pong pair never moves while the cluster count stays the same
+  float* hid[2] = {(float*)h->servo_hid, (float*)((char*)h->servo_hid + h->servo_hid_bytes / 2)};
+  void* ws = db + in_bytes + out_bytes;
   {
     // same target as the previous frame (the usual case in a servo loop)?  then what depends on the target alone is reused
     const size_t kb[4] = {(size_t)N * 2 * sizeof(float), (size_t)N * 2 * sizeof(float), (size_t)C * sizeof(int64_t),
@@ -577,7 +584,6 @@ int cns_graphvs_forward_host(cns_handle* h, const cns_batch* bh, const float* hi
     vec = a.take<float>(B * 6); nrm = a.take<float>(B); hout = a.take<float>(C * H); vel = a.take<float>(B * 6);
     ws = a.take<char>(cns_forward_workspace_bytes(bh));
   };
-  h->servo_valid = 0;      // this entry point reuses the staging buffer of cns_servo_step_host
   cns_batch d; float *hin, *vec, *nrm, *hout, *vel; void* ws;
   plan(ar, d, hin, vec, nrm, hout, vel, ws);
   if (ar.off > h->stage_dev_bytes) {

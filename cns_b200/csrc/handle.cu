@@ -280,6 +280,7 @@ int cns_destroy(cns_handle* h) {
   if (h->side_stream) { cudaStreamDestroy(h->side_stream); cudaEventDestroy(h->side_fork); cudaEventDestroy(h->side_join); cudaEventDestroy(h->side_join2); }
   if (h->stage_host) cudaFreeHost(h->stage_host);
   if (h->stage_dev) cudaFree(h->stage_dev);
+  if (h->servo_hid) cudaFree(h->servo_hid);
   delete h;
   return CNS_OK;
 }

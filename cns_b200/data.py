@@ -48,13 +48,20 @@ class GraphData(object):
             raise AttributeError(key) from None
 
     def __setattr__(self, key, value):
-        self._f[key] = value
+        self[key] = value
 
     def __getitem__(self, key):
         return self._f[key]
 
     def __setitem__(self, key, value):
-        self._f[key] = value
+        f = self._f
+        # `l1_complete` says "the cluster-level edge lists are the complete digraphs GraphGenerator emitted"
+        # (cns_batch.flags); an edge list or mask assigned afterwards (custom edge augmentation) voids the claim,
+        # and the forward then takes the general CSR path
+        if key.startswith("l1_dense_edge_index") or key == "cluster_mask":
+            if key in f and f.get("l1_complete") is True:
+                f["l1_complete"] = False
+        f[key] = value
 
     def __contains__(self, key):
         return key in self._f
@@ -118,11 +125,16 @@ class GraphData(object):
 
 class DevicePrefetcher(object):
     """Iterates host (ideally pinned) GraphData/Batch objects as device-resident ones, issuing the
-    host->device copy of item i+1 on a side stream while the caller computes on item i."""
+    host->device copy of item i+1 on a side stream while the caller computes on item i.
 
-    def __init__(self, items, device, depth: int = 1, fields=None):
+    LIFETIME: by default the tensors of a yielded item are views into a ring of `depth + 2` persistent staging
+    slots: an item stays valid for the next `depth + 1` calls of `next()` and is then overwritten.  Streaming
+    inference (use, then drop) is the intended consumer.  Pass `owning=True` when items are kept longer - e.g. the
+    frames of a TBPTT window whose backward runs after the whole window: every item then gets fresh device tensors."""
+
+    def __init__(self, items, device, depth: int = 1, fields=None, owning: bool = False):
         self.items, self.device, self.depth = iter(items), torch.device(device), max(1, depth)
-        self.fields = fields
+        self.fields, self.owning = fields, owning
         self.stream = torch.cuda.Stream(self.device)
         self.queue = []
         # persistent staging slots (no allocator traffic in steady state): slot -> {field: byte buffer}
@@ -140,6 +152,9 @@ class DevicePrefetcher(object):
                 out[k] = v
                 continue
             if self.fields is not None and k not in self.fields:
+                continue
+            if self.owning:
+                out[k] = v.to(self.device, non_blocking=True)
                 continue
             nbytes = v.numel() * v.element_size()
             buf = bufs.get(k)
@@ -181,6 +196,10 @@ class DevicePrefetcher(object):
             raise StopIteration
         dev, ev, slot = self.queue.pop(0)
         cur.wait_event(ev)
+        if self.owning:          # allocated on the copy stream, consumed on the caller's: tell the caching allocator
+            for _, v in dev.items():
+                if isinstance(v, torch.Tensor):
+                    v.record_stream(cur)
         self.last = slot
         self._fill()
         return dev

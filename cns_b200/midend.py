@@ -64,6 +64,34 @@ class Correspondence(object):
     detector_name: str = "Unknown"
     tar_img_changed: bool = True
 
+    @classmethod
+    def concat(cls, corr):
+        """Correspondences of several detectors on the same image pair, stacked (`cns/frontend/utils.py:31-68`);
+        None entries are skipped, all None -> None.  `match` rows are shifted by the running keypoint counts (the
+        reference shifts the current-side column by `cur_pos.shape[1]`, i.e. always 2 - nothing downstream of the
+        frontend reads `match`, the graph path uses `cur_pos_aligned` / `valid_mask`)."""
+        valid = [c for c in corr if c is not None]
+        if not valid:
+            return None
+        tar_off = cur_off = 0
+        matches = []
+        for c in valid:
+            m = np.array(c.match, copy=True)
+            m[:, 0] += tar_off
+            m[:, 1] += cur_off
+            tar_off += c.tar_pos.shape[0]
+            cur_off += c.cur_pos.shape[0]
+            matches.append(m)
+        return cls(
+            intrinsic=valid[0].intrinsic, tar_img=valid[0].tar_img, cur_img=valid[0].cur_img,
+            tar_pos=np.concatenate([c.tar_pos for c in valid], axis=0),
+            cur_pos=np.concatenate([c.cur_pos for c in valid], axis=0),
+            match=np.concatenate(matches, axis=0),
+            valid_mask=np.concatenate([c.valid_mask for c in valid], axis=0),
+            cur_pos_aligned=np.concatenate([c.cur_pos_aligned for c in valid], axis=0),
+            detector_name=" + ".join(c.detector_name for c in valid),
+            tar_img_changed=any(c.tar_img_changed for c in valid))
+
 
 class Midend(object):
     def __init__(self):

@@ -135,7 +135,8 @@ class TBPTTStepper(object):
     """One optimizer update from a window of recurrent frames."""
 
     def __init__(self, net, optimizers: Optional[Dict[str, torch.optim.Optimizer]] = None, clip_norm: float = 10.0,
-                 group=None, fused: bool = False, lr: float = 5e-4, weight_decay: float = 1e-4):
+                 group=None, fused: bool = True, lr: float = 5e-4, weight_decay: float = 1e-4,
+                 hidden_reset: str = "scene"):
         self.net = net
         self.clip_norm = clip_norm
         self.bucket = GradBucket(list(net.parameters()))
@@ -147,15 +148,40 @@ class TBPTTStepper(object):
             self.optimizers = optimizers if optimizers is not None else make_optimizers(net, lr, weight_decay)
         self.group = group
         self.hidden = None
+        self.hidden_reset = hidden_reset
+        self._counts = None          # num_clusters (B,) of the frame `hidden` belongs to
+
+    def _carry_hidden(self, data):
+        """Hidden state for this frame.  The reference drops the state of the WHOLE batch when any scene is new
+        (train_gvs_short_seq.py:28) - harmless there because its loader restarts all scenes together
+        (sim/dataset.py:242-246).  Scenes here restart one by one, so with `hidden_reset="scene"` (default) only the
+        cluster rows of the restarted scenes are zeroed (a restarted scene may come back with a different cluster
+        count: its rows are spliced in as zeros); `hidden_reset="batch"` is the reference's literal rule."""
+        if self.hidden is None:
+            return None
+        new_scene = torch.as_tensor(data.new_scene).reshape(-1)
+        counts = torch.as_tensor(data.num_clusters).reshape(-1).to(self.hidden.device)
+        fresh = new_scene.to(self.hidden.device, torch.bool)
+        if not bool(fresh.any()):
+            return self.hidden if int(counts.sum()) == self.hidden.shape[0] else None
+        old = self._counts
+        if self.hidden_reset != "scene" or old is None or old.numel() != counts.numel() or bool(fresh.all()) \
+                or not bool(((old == counts) | fresh).all()):
+            return None
+        graph = torch.repeat_interleave(torch.arange(counts.numel(), device=counts.device), counts)
+        new_ptr, old_ptr = torch.cumsum(counts, 0) - counts, torch.cumsum(old, 0) - old
+        keep = ~fresh[graph]
+        row = torch.arange(graph.numel(), device=counts.device) - new_ptr[graph] + old_ptr[graph]
+        row = torch.where(keep, row, torch.zeros_like(row))
+        return self.hidden.index_select(0, row) * keep[:, None].to(self.hidden.dtype)
 
     def window_loss(self, frames: Iterable, mean: bool = False):
         """Sum (short-seq) or mean (long-seq) of the per-frame objectives, hidden carried with grad."""
         losses, logs = [], []
         for data in frames:
-            if bool(torch.as_tensor(data.new_scene).any()):
-                self.hidden = None
-            pred = self.net(data, self.hidden)
+            pred = self.net(data, self._carry_hidden(data))
             self.hidden = pred[2]
+            self._counts = torch.as_tensor(data.num_clusters).reshape(-1).to(self.hidden.device).clone()
             self.last_pred = pred          # closed-loop callers read the prediction between frames
             if self.fused:
                 loss_t, triple = fused_objectives(pred, data)

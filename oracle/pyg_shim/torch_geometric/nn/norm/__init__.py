@@ -9,7 +9,7 @@ Parameters: weight (ones), bias (zeros), mean_scale (ones); eps = 1e-5.
 import torch
 import torch.nn as tnn
 
-from ..utils import scatter
+from ...utils import scatter
 
 
 class GraphNorm(tnn.Module):

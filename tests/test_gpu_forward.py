@@ -215,6 +215,39 @@ def test_servo_controller_host_path(state_dict):
         scene.step(vel * 2)
 
 
+def test_servo_controller_host_path_varying_visibility(state_dict):
+    """The carried hidden state must survive frames whose staged input block changes size: the number of
+    visible keypoints crosses multiples of 32 (the staging alignment), whole clusters lose all their
+    keypoints (fewer cluster-level edges) and come back; every frame is checked against the oracle."""
+    from cns_b200.controller import GraphVSController
+    ctl = GraphVSController(os.path.join(ROOT, "checkpoints", "cns_state_dict.pth"), "cuda:0")
+    rng = np.random.default_rng(33)
+    np.random.seed(33)
+    scene = synth.Scene(rng, 150)
+    gen = scene.generator
+    labels = np.asarray(gen.belong_cluster_index)
+    n = len(scene.points)
+    hid = None
+    miss_counts = [0, 15, 31, 33, 64, 1, 97, 40, 0, 70]
+    for t, k in enumerate(miss_counts):
+        cur = synth.project_norm(scene.cur_wcT, scene.points)
+        missing = set(rng.choice(n, size=k, replace=False).tolist()) if k else set()
+        if t in (3, 4, 6):      # empty cluster (t % number of clusters) as well
+            missing |= set(np.nonzero(labels == (t % gen.num_clusters))[0].tolist())
+        missing = np.array(sorted(missing), dtype=np.int64)
+        d = gen.get_data(cur, missing_node_indices=missing if len(missing) else None)
+        d.set_distance_scale(scene.tPo_norm)
+        if t == 0:
+            d.start_new_scene()
+        if t in (3, 4, 6):
+            assert not bool(d.cluster_mask.all())
+        vel = ctl(d)
+        ov, on, hid = cns_oracle.forward(state_dict, d, hid, dtype=torch.float64)
+        ovel = cns_oracle.postprocess((ov, on), d.tPo_norm.reshape(1))[0].numpy()
+        assert np.abs(vel - ovel).max() < 1e-4 * np.abs(ovel).max(), "frame %d" % t
+        scene.step(vel * 2)
+
+
 def test_batched_servo_device_graphs_match_host_graph_path(net):
     """BatchedServo (target graphs resident on the device, per-frame masking by cns_graph_mask, hidden
     carried on the device) == GraphGenerator.get_data + Batch.from_data_list + GraphVS.forward on the

@@ -39,7 +39,9 @@ def get_args():
     ap.add_argument("--long-steps", type=int, default=200)
     ap.add_argument("--updates-per-epoch", type=int, default=50)
     ap.add_argument("--max-points", type=int, default=512)
-    ap.add_argument("--fused", action="store_true", help="fused loss and clip+AdamW kernels")
+    ap.add_argument("--fused", dest="fused", action="store_true", default=True,
+                    help="fused loss and clip+AdamW kernels (cns_objectives / cns_clip_adamw); the default")
+    ap.add_argument("--no-fused", dest="fused", action="store_false", help="torch loss + torch AdamW objects")
     ap.add_argument("--seed", type=int, default=2022)
     ap.add_argument("--device-env", action="store_true",
                     help="keep the closed-loop scenes on the GPU (cns_b200.sim_device.DeviceSceneBatch): batched projection, "
@@ -91,15 +93,23 @@ def main():
         torch.cuda.set_device(local)
         args.device = "cuda:%d" % local
         dist.init_process_group("nccl", device_id=torch.device(args.device))
-    assert args.hdim == 128, "libcns_sm100 is built for hidden_dim 128 (the shipped checkpoint)"
+    if args.hdim != 128:
+        raise SystemExit("--hdim %d: libcns_sm100's kernels are specialised for hidden_dim 128, the only configuration the "
+                         "reference ships weights for (checkpoints/cns.pth, train_cns.py:56-61); see INTEGRATION.md" % args.hdim)
     dev = torch.device(args.device)
     np.random.seed(args.seed + rank)
     torch.manual_seed(0)                       # identical initial weights on every rank
     net = GraphVS(2, 2, args.hdim, regress_norm=True).to(dev)
-    if args.load:
-        net.load_state_dict(ckpt.read_state_dict(args.load))
+    load = args.load if args.load and args.load.lower() != "none" else None        # the reference spells "none"
+    if load:
+        net.load_state_dict(ckpt.read_state_dict(load))       # state dict, cns.pth or a Trainer checkpoint
     net.train()
     stepper = TBPTTStepper(net, fused=args.fused, lr=args.init_lr, weight_decay=args.weight_decay)
+    if load:
+        try:          # resume the optimizer state when the file is a Trainer checkpoint (trainer.py:333-348)
+            ckpt.load_checkpoint(load, net, stepper.optimizers, getattr(stepper, "fused_opt", None))
+        except ValueError:
+            pass
     if args.device_env:
         from cns_b200.sim_device import DeviceSceneBatch
         envs = DeviceSceneBatch(args.batch_size, np.random.default_rng(args.seed + rank), dev, args.max_points,
@@ -136,9 +146,9 @@ def main():
                 epoch, mean_loss, time.time() - t0,
                 args.updates_per_epoch * window * args.batch_size * world / (time.time() - t0)))
             if args.save:
-                os.makedirs(os.path.join("checkpoints", args.name), exist_ok=True)
-                ckpt.save_checkpoint(os.path.join("checkpoints", args.name, "checkpoint_last.pth"), epoch, net,
-                                     stepper.optimizers, mean_loss, mean_loss < best, not_improved)
+                # Trainer format (trainer.py:138-162): loadable by the unmodified reference
+                ckpt.save_checkpoint(epoch, net, stepper.optimizers, mean_loss, mean_loss < best, not_improved,
+                                     os.path.join("checkpoints", args.name), fused_opt=getattr(stepper, "fused_opt", None))
         if mean_loss < best:
             best, not_improved = mean_loss, 0
         else:
