@@ -16,10 +16,20 @@ over one 1024-graph batch.
           e2e.full_graph: GraphVS.forward on a prebuilt host Batch copied whole every step.
   roofline     : the dominant kernel (encoder edge kernel), timed live with CUDA events on its
                  launching stream (cns_profile_begin/end).
-  cpu_baseline : the oracle (CPU port of the reference forward) on a bounded sample of the same
-                 workload, on this box's host cores.
-`--impl reference` times that CPU implementation alone (the reference itself is Python on PyG,
-which cannot be installed here; the port in oracle/ is the stand-in, kind "port").
+                 `frac` is quoted against the BURST bf16 peak while the K-step loop is shorter than 1 s
+                 (it runs at boost clocks); `roofline.sustained` repeats the loop for >= 2 s and quotes
+                 the same kernel against the sustained peak.
+  cpu_baseline : the oracle (CPU port of the reference forward) on the same workload (full 1024-graph
+                 batch, bounded number of steps; batch-size sweep beside it), on this box's host cores.
+  fp32_mode    : the same device-resident loop in the fp32-tolerance mode (rel 1e-4 parity).
+  train        : BASELINE configs[2] - short-sequence training update (8-frame truncated BPTT, 256 graphs
+                 x 512 keypoints per GPU, fused loss, ONE NCCL all-reduce of the flat gradient bucket
+                 inside the timed region when world > 1, fused clip + AdamW): graph-frames/s fwd+bwd.
+  latency      : BASELINE configs[0] - batch-1 recurrent servo frames through GraphVSController
+                 (host GraphData in, velocity out): p50 / p90, the CPU port beside it.
+  per_rank_ms  : min / max over ranks of the per-step time of the `value` loop.
+`--impl reference` times that CPU implementation alone on the full workload (the reference itself is
+Python on PyG, which cannot be installed here; the port in oracle/ is the stand-in, kind "port").
 """
 import argparse
 import ctypes as C
@@ -49,8 +59,13 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("CNS_PRECISION", "f16"), choices=["fp32", "f16", "bf16"])
     ap.add_argument("--graphs", type=int, default=N_GRAPHS)
     ap.add_argument("--points", type=int, default=N_POINTS)
-    ap.add_argument("--cpu-sample", type=int, default=64, help="graphs per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="graphs per CPU-baseline step (0 = the full batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fp32 / train / latency / sustained legs")
+    ap.add_argument("--train-graphs", type=int, default=256)
+    ap.add_argument("--train-frames", type=int, default=8)
+    ap.add_argument("--train-updates", type=int, default=5)
+    ap.add_argument("--latency-frames", type=int, default=200)
     return ap.parse_args()
 
 
@@ -133,7 +148,7 @@ def tensor_bytes(batch):
     return sum(v.numel() * v.element_size() for _, v in batch.items() if isinstance(v, torch.Tensor))
 
 
-def cpu_reference_rate(n_graphs, n_points, steps, warmup, budget_s=25.0):
+def cpu_reference_rate(n_graphs, n_points, steps, warmup, budget_s=25.0, batch=None):
     """graphs/s of the CPU port of the reference forward (oracle/cns_oracle.py), all host threads."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -141,7 +156,8 @@ def cpu_reference_rate(n_graphs, n_points, steps, warmup, budget_s=25.0):
     from cns_b200 import ckpt
     torch.set_num_threads(os.cpu_count() or 1)
     sd = ckpt.read_state_dict(os.path.join(ROOT, "checkpoints", "cns.pth"))
-    batch = build_batches(n_graphs, n_points, 2022, 1)[0]
+    if batch is None:
+        batch = build_batches(n_graphs, n_points, 2022, 1)[0]
     with torch.no_grad():
         for _ in range(max(1, warmup)):
             cns_oracle.forward(sd, batch, None)
@@ -153,6 +169,40 @@ def cpu_reference_rate(n_graphs, n_points, steps, warmup, budget_s=25.0):
                 break
         dt = time.perf_counter() - t0
     return n_graphs * done / dt, dt / done * 1e3, done, torch.get_num_threads()
+
+
+def sub_batch(host_batch_scenes, n):
+    """The first `n` scenes' current frames as one host Batch (CPU-baseline sweep)."""
+    from cns_b200.data import Batch
+    return Batch.from_data_list([s.frame(MISSING) for s in host_batch_scenes[:n]])
+
+
+def cpu_latency(scene, frames, warm=5):
+    """Batch-1 recurrent frames through the CPU port: per-frame wall times (ms)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cns_oracle
+    from cns_b200 import ckpt
+    sd = ckpt.read_state_dict(os.path.join(ROOT, "checkpoints", "cns.pth"))
+    hid, out = None, []
+    with torch.no_grad():
+        for t in range(frames + warm):
+            d = scene.frame(MISSING)
+            t0 = time.perf_counter()
+            vec, nrm, hid = cns_oracle.forward(sd, d, hid)
+            vel = cns_oracle.postprocess((vec, nrm), d.tPo_norm.reshape(1))[0].numpy()
+            if t >= warm:
+                out.append((time.perf_counter() - t0) * 1e3)
+            scene.step(vel * 2)
+    return out
+
+
+def workload_config(args):
+    """`config` of the JSON line - identical in the b200 and the reference arm."""
+    return {"workload": "cns.pth batched inference, %d synthetic servo graphs x %d keypoints per GPU" % (args.graphs, args.points),
+            "graphs_per_gpu": args.graphs, "keypoints_per_graph": args.points, "missing_keypoints": MISSING,
+            "weights": "checkpoints/cns.pth", "hidden": "None (first frame)",
+            "call": "GraphVS.forward(Batch, None), stateless (no target cache)"}
 
 
 _JSON_FD = None
@@ -177,26 +227,26 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = "cns.pth batched inference, %d synthetic servo graphs x %d keypoints per GPU" % (args.graphs, args.points)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        rate, ms, done, cores = cpu_reference_rate(args.cpu_sample, args.points, args.steps, args.warmup, 120.0)
-        sample = "%d of the %d graphs per step (N=%d keypoints, 10%% missing), fp32 torch CPU" % (
-            args.cpu_sample, args.graphs, args.points)
+        n_cpu = args.cpu_sample or args.graphs
+        rate, ms, done, cores = cpu_reference_rate(n_cpu, args.points, args.steps, args.warmup, 150.0)
+        sample = "%d of the %d graphs per step (N=%d keypoints, 10%% missing), fp32 torch CPU, %d steps" % (
+            n_cpu, args.graphs, args.points, done)
         emit({
             "impl": "reference", "metric": "servo graphs/sec (fwd)", "value": rate, "unit": "graphs/s",
             "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "sample": sample},
+            "config": workload_config(args),
             "cpu_baseline": {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     import torch
     import torch.distributed as dist
-    from cns_b200 import _lib, ckpt
+    from cns_b200 import _lib, ckpt, synth
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -229,27 +279,47 @@ def main():
             return float(t.item())
         return ms
 
-    handle = net._handle(dev)
+    def gather_ms(ms):
+        """(max over ranks, [min, max]) of a per-rank elapsed time."""
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            lo, hi = t.clone(), t.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            return float(hi.item()), [float(lo.item()), float(hi.item())]
+        return ms, [ms, ms]
+
+    def forward_loop(model, steps, warmup, profile=True, **kw):
+        """`steps` stateless forwards over the rotating resident batches: (elapsed ms on this rank, mean encoder-edge
+        kernel ms, launches counted by the library)."""
+        hd = model._handle(dev)
+        for i in range(warmup):
+            model(resident[i % N_ROTATE], None, **kw)
+        barrier()
+        if profile:
+            _lib.check(lib.cns_profile_begin(hd.raw), "profile_begin")
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(steps):
+            model(resident[i % N_ROTATE], None, **kw)
+        t1.record()
+        barrier()
+        kms, kn, nl = C.c_float(), C.c_int(), C.c_longlong()
+        if profile:
+            _lib.check(lib.cns_profile_end(hd.raw, C.byref(kms), C.byref(kn), C.byref(nl)), "profile_end")
+        return t0.elapsed_time(t1), kms.value / max(kn.value, 1), int(nl.value)
+
+    extras = not args.no_extras
+    fp32 = train = latency = sustained = None
     with torch.no_grad():
         # ---------------- device-resident throughput ("value") + live kernel timing ----------------
         # the stateless call of the reference API, GraphVS.forward(Batch, hidden=None): nothing is kept from one
         # step to the next
-        for i in range(args.warmup):
-            net(resident[i % N_ROTATE], None)
-        barrier()
         sampler = ClockSampler(local)
         sampler.start()
-        _lib.check(lib.cns_profile_begin(handle.raw), "profile_begin")
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(args.steps):
-            net(resident[i % N_ROTATE], None)
-        e1.record()
-        barrier()
-        kms, kn, launches = C.c_float(), C.c_int(), C.c_longlong()
-        _lib.check(lib.cns_profile_end(handle.raw, C.byref(kms), C.byref(kn), C.byref(launches)), "profile_end")
+        my_ms, kernel_ms, launches = forward_loop(net, args.steps, args.warmup)
         sampler.stop_flag = True
-        total_ms = max_over_ranks(e0.elapsed_time(e1))
+        total_ms, rank_ms = gather_ms(my_ms)
         value = args.graphs * world * args.steps / (total_ms * 1e-3)
 
         # the same loop with a per-target cache (GraphVS.build_target_cache): the rotating batches are the same
@@ -257,16 +327,30 @@ def main():
         # positions, tile packing) is built once, as the reference's Midend keeps one GraphGenerator per target
         # image.  Reported beside `value`, not as `value`.
         tcache = net.build_target_cache(resident[0])
-        for i in range(args.warmup):
-            net(resident[i % N_ROTATE], None, target_cache=tcache)
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for i in range(args.steps):
-            net(resident[i % N_ROTATE], None, target_cache=tcache)
-        c1.record()
-        barrier()
-        cached_ms = max_over_ranks(c0.elapsed_time(c1))
+        cached_ms = max_over_ranks(forward_loop(net, args.steps, args.warmup, profile=False, target_cache=tcache)[0])
+
+        if extras:
+            # ---------------- the same loop for >= 2 s: clocks settle at their sustained level ---------------
+            n_sus = max(args.steps, int(2200.0 / max(my_ms / args.steps, 1e-3)))
+            sus_sampler = ClockSampler(local)
+            sus_sampler.start()
+            sus_ms, sus_kernel_ms, _ = forward_loop(net, min(n_sus, 256), 0)     # the library keeps 256 event pairs
+            n_prof = min(n_sus, 256)
+            rest_ms = forward_loop(net, n_sus - n_prof, 0, profile=False)[0] if n_sus > n_prof else 0.0
+            sus_sampler.stop_flag = True
+            sus_total = max_over_ranks(sus_ms + rest_ms)
+            sustained = {"steps": n_sus, "seconds": sus_total * 1e-3, "ms_per_step": sus_total / n_sus,
+                         "value": args.graphs * world * n_sus / (sus_total * 1e-3), "kernel_ms": sus_kernel_ms,
+                         "clocks": sus_sampler.summary()}
+            # ---------------- fp32-tolerance mode (rel 1e-4 parity), same loop -------------------------------
+            if args.precision != "fp32":
+                net32 = ckpt.load_model(os.path.join(ROOT, "checkpoints", "cns.pth"), dev, precision="fp32")
+                f_ms, f_kernel_ms, f_launches = forward_loop(net32, args.steps, args.warmup)
+                f_total = max_over_ranks(f_ms)
+                fp32 = {"value": args.graphs * world * args.steps / (f_total * 1e-3), "unit": "graphs/s",
+                        "ms_per_step": f_total / args.steps, "kernel_ms": f_kernel_ms, "gpu_launches": f_launches,
+                        "tolerance": "rel 1e-4 vs the fp64 oracle (tests/test_gpu_forward.py)"}
+                del net32
 
         # ---------------- end to end: pinned host GraphData in, velocities out ----------------------
         for i in range(args.warmup):
@@ -321,6 +405,88 @@ def main():
         barrier()
         e2e_ms = max_over_ranks(g0.elapsed_time(g1))
         e2e = args.graphs * world * args.steps / (e2e_ms * 1e-3)
+        h2d_servo, d2h_servo = servo.h2d_bytes, servo.d2h_bytes
+        del servo
+
+    if extras:
+        # ---------------- training update (BASELINE configs[2]): fwd + bwd, all-reduce inside -------------
+        from cns_b200 import GraphVS
+        from cns_b200.data import Batch
+        from cns_b200.train import TBPTTStepper
+        tb, tf = min(args.train_graphs, args.graphs), args.train_frames
+        tscenes = scenes[:tb]
+        window = []
+        for t in range(tf):
+            fr = [s.frame(MISSING, with_labels=True) for s in tscenes]
+            if t == 0:
+                for f in fr:
+                    f.start_new_scene()
+            window.append(Batch.from_data_list(fr).to(dev))
+            for s in tscenes:
+                s.step(synth.pbvs_straight(s.cur_wcT, s.tar_wcT) * 2)
+        tnet = GraphVS(2, 2, 128).to(dev)
+        tnet.load_state_dict(ckpt.read_state_dict(os.path.join(ROOT, "checkpoints", "cns.pth")))
+        tnet.train()
+        stepper = TBPTTStepper(tnet, fused=True, lr=1e-5)
+        for _ in range(2):
+            stepper.hidden = None
+            stepper.step(window)
+        barrier()
+        th = tnet._handle(dev, training=True)
+        _lib.check(lib.cns_profile_begin(th.raw), "profile_begin")
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        for _ in range(args.train_updates):
+            stepper.hidden = None
+            loss = stepper.step(window)
+        u1.record()
+        barrier()
+        tk, tn, tl = C.c_float(), C.c_int(), C.c_longlong()
+        _lib.check(lib.cns_profile_end(th.raw, C.byref(tk), C.byref(tn), C.byref(tl)), "profile_end")
+        upd_ms = max_over_ranks(u0.elapsed_time(u1)) / args.train_updates
+        ar_ms = None
+        if world > 1:        # the collective alone (1.86 MB flat bucket), for the record
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.all_reduce(stepper.bucket.flat)
+            barrier()
+            a0.record()
+            for _ in range(20):
+                dist.all_reduce(stepper.bucket.flat)
+            a1.record()
+            barrier()
+            ar_ms = max_over_ranks(a0.elapsed_time(a1)) / 20
+        train = {"workload": "short-sequence training update: %d-frame truncated BPTT, %d graphs x %d keypoints per GPU, fused "
+                             "loss, gradient all-reduce (world %d) + fused clip/AdamW inside the timed region" % (tf, tb, args.points, world),
+                 "ms_per_update": upd_ms, "value": tb * tf * world / (upd_ms * 1e-3), "unit": "graph-frames/s (fwd+bwd)",
+                 "updates": args.train_updates, "loss": float(loss), "allreduce_ms": ar_ms,
+                 "allreduce_bytes": int(stepper.bucket.flat.numel() * 4), "gpu_launches_per_update": int(tl.value) // max(args.train_updates, 1),
+                 "enc_edge_fwd_kernel_ms": tk.value / max(tn.value, 1), "precision": "fp32-tolerance kernels (training)"}
+        del stepper, tnet, window
+
+        # ---------------- batch-1 latency (BASELINE configs[0]) through GraphVSController, rank 0 --------
+        if rank == 0:
+            from cns_b200.controller import GraphVSController
+            import numpy as np
+            lat = {}
+            for prec in (args.precision, "fp32") if args.precision != "fp32" else ("fp32",):
+                ctl = GraphVSController(os.path.join(ROOT, "checkpoints", "cns.pth"), dev, precision=prec)
+                sc = synth.Scene(np.random.default_rng(7), args.points, generator=scenes[0].generator, points=scenes[0].points,
+                                 tar_wcT=scenes[0].tar_wcT)
+                times = []
+                for t in range(args.latency_frames + 20):
+                    d = sc.frame(MISSING)
+                    if t == 0:
+                        d.start_new_scene()
+                    t0 = time.perf_counter()
+                    v = ctl(d)                                            # host GraphData in, np velocity out (synchronous)
+                    if t >= 20:
+                        times.append((time.perf_counter() - t0) * 1e3)
+                    sc.step(v * 2)
+                times.sort()
+                lat[prec] = {"p50_ms": times[len(times) // 2], "p90_ms": times[int(len(times) * 0.9)], "frames": len(times)}
+            latency = {"workload": "batch 1, %d keypoints, recurrent (hidden carried), GraphVSController(host GraphData) -> velocity" % args.points,
+                       "unit": "ms per frame (host wall clock, synchronous)", **lat}
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -328,29 +494,33 @@ def main():
         return
 
     pk, pk_src = peaks()
-    kernel_ms = kms.value / max(kn.value, 1)
-    flops_per_launch = FLOP_PER_EDGE_SIDE * 2 * (sum(n_edges[i % N_ROTATE] for i in range(args.steps)) / args.steps)
+    edges_per_step = sum(n_edges[i % N_ROTATE] for i in range(args.steps)) / args.steps
+    flops_per_launch = FLOP_PER_EDGE_SIDE * 2 * edges_per_step
     achieved = flops_per_launch / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else 0.0
-    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    # a K-step loop shorter than 1 s runs at boost clocks: the burst peak is its denominator; the >= 2 s loop
+    # (roofline.sustained) is quoted against the sustained peak
+    burst = total_ms < 1000.0
+    peak = pk["bf16_tflops"] if burst else pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "enc_edge_traffic.json")) as f:
             traffic = json.load(f).get(args.precision, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
+    config = workload_config(args)
+    config["l2"] = ("inputs rotate over %d distinct resident batches: a step reads %.0f MB of its batch (keypoints, "
+                    "keypoint->cluster edges, the cluster edge lists being verified), %.0f MB pass before a batch "
+                    "repeats > L2 (126 MB)" % (N_ROTATE, read_per_step / 1e6, N_ROTATE * read_per_step / 1e6))
     line = {
         "metric": "servo graphs/sec (fwd)", "value": value, "unit": "graphs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "f16": "f16", "bf16": "bf16"}[args.precision], "data": "synthetic",
-        "config": {"workload": workload, "missing_keypoints": MISSING, "weights": "checkpoints/cns.pth",
-                   "hidden": "None (first frame)", "call": "GraphVS.forward(Batch, None), stateless (no target cache)", "l2": "inputs rotate over %d distinct resident batches: a step reads %.0f MB of its batch (keypoints, "
-                         "keypoint->cluster edges, the cluster edge lists being verified), %.0f MB pass before a batch "
-                         "repeats > L2 (126 MB)" % (N_ROTATE, read_per_step / 1e6, N_ROTATE * read_per_step / 1e6),
-                   "graphs_per_gpu": args.graphs},
+        "config": config,
         "clocks": sampler.summary(),
+        "per_rank_ms": {"min": rank_ms[0] / args.steps, "max": rank_ms[1] / args.steps, "what": "ms per step of the `value` loop"},
         "e2e": {"value": e2e, "unit": "graphs/s", "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": servo.h2d_bytes, "d2h_bytes_per_step": servo.d2h_bytes,
+                "h2d_bytes_per_step": h2d_servo, "d2h_bytes_per_step": d2h_servo,
                 "api": "BatchedServo.submit/result(cur_xy, visible): target graphs resident on the device, per-frame "
                        "graph masking on the device, two frames in flight (H2D of frame i+1 overlaps frame i), "
                        "every frame's velocities read back on the host",
@@ -358,22 +528,53 @@ def main():
                                "d2h_bytes_per_step": d2h_full,
                                "api": "GraphVS.forward(Batch.to(device)): the whole prebuilt host Batch is copied "
                                       "every step (DevicePrefetcher), read-back one step behind"}},
-        "gpu_launches": int(launches.value),
+        "gpu_launches": int(launches),
         "with_target_cache": {"value": args.graphs * world * args.steps / (cached_ms * 1e-3), "unit": "graphs/s",
                               "ms_per_step": cached_ms / args.steps,
                               "note": "same loop with GraphVS.build_target_cache (per-target terms built once outside "
                                       "the timed region); not the headline"},
         "roofline": {"kernel": "enc_edge (%s)" % args.precision, "bound": "tensor", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": pk_src + " bf16 sustained", "kernel_ms": kernel_ms,
-                     "kernel_share_of_step": kernel_ms / (total_ms / args.steps),
+                     "peak_source": pk_src + (" bf16 burst (timed loop %.1f ms < 1 s)" % total_ms if burst else " bf16 sustained"),
+                     "kernel_ms": kernel_ms,
+                     "kernel_share_of_step": kernel_ms / (my_ms / args.steps),
                      "flops_per_launch": flops_per_launch},
     }
+    if sustained is not None:
+        sp = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        sa = flops_per_launch / (sustained["kernel_ms"] * 1e-3) / 1e12 if sustained["kernel_ms"] > 0 else 0.0
+        line["roofline"]["sustained"] = {"achieved": sa, "peak": sp, "frac": sa / sp, **sustained}
+    if fp32 is not None:
+        fa = flops_per_launch / (fp32["kernel_ms"] * 1e-3) / 1e12 if fp32["kernel_ms"] > 0 else 0.0
+        fp32["roofline"] = {"kernel": "enc_edge (fp32 mode)", "bound": "tensor", "achieved": fa, "peak": pk["bf16_tflops"],
+                            "unit": "TFLOP/s", "frac": fa / pk["bf16_tflops"],
+                            "note": "algorithmic fp32 flops of the reference chain (not the operand-split products) over the bf16 burst peak"}
+        line["fp32_mode"] = fp32
+    if train is not None:
+        line["train"] = train
+    if latency is not None:
+        line["latency"] = latency
     if world == 1 and not args.no_cpu_baseline:
-        rate, ms, done, cores = cpu_reference_rate(args.cpu_sample, args.points, 50, 1, 20.0)
-        line["cpu_baseline"] = {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port",
-                                "sample": "%d graphs x %d keypoints per step, %d steps (%.1f ms/step)" % (
-                                    args.cpu_sample, args.points, done, ms)}
+        n_cpu = args.cpu_sample or args.graphs
+        rate, ms, done, cores = cpu_reference_rate(n_cpu, args.points, 30, 1, 15.0, batch=sub_batch(scenes, n_cpu))
+        sweep = {}
+        for nb in (64, 256):
+            if nb < n_cpu:
+                r2, m2, d2, _ = cpu_reference_rate(nb, args.points, 30, 1, 5.0, batch=sub_batch(scenes, nb))
+                sweep[str(nb)] = {"graphs_per_s": r2, "ms_per_step": m2, "steps": d2}
+        sweep[str(n_cpu)] = {"graphs_per_s": rate, "ms_per_step": ms, "steps": done}
+        best = max(v["graphs_per_s"] for v in sweep.values())
+        line["cpu_baseline"] = {"value": best, "unit": "graphs/s", "cores": cores, "kind": "port",
+                                "sample": "best of a batch-size sweep of the oracle port, fp32 torch CPU, %d keypoints per graph; "
+                                          "full batch: %d graphs per step, %d steps (%.0f ms/step)" % (args.points, n_cpu, done, ms),
+                                "batch_sweep": sweep}
+        if latency is not None:
+            import numpy as np
+            sc = synth.Scene(np.random.default_rng(7), args.points, generator=scenes[0].generator, points=scenes[0].points,
+                             tar_wcT=scenes[0].tar_wcT)
+            ct = sorted(cpu_latency(sc, 30))
+            line["latency"]["cpu_port"] = {"p50_ms": ct[len(ct) // 2], "p90_ms": ct[int(len(ct) * 0.9)], "frames": len(ct),
+                                           "cores": cores}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
