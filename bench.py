@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--graphs", type=int, default=N_GRAPHS)
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--cpu-sample", type=int, default=0, help="graphs per CPU-baseline step (0 = the full batch)")
+    ap.add_argument("--cpu-chunk", type=int, default=64, help="reference arm: graphs per forward call (0 = one call per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the fp32 / train / latency / sustained legs")
     ap.add_argument("--train-graphs", type=int, default=256)
@@ -148,22 +149,32 @@ def tensor_bytes(batch):
     return sum(v.numel() * v.element_size() for _, v in batch.items() if isinstance(v, torch.Tensor))
 
 
-def cpu_reference_rate(n_graphs, n_points, steps, warmup, budget_s=25.0, batch=None):
-    """graphs/s of the CPU port of the reference forward (oracle/cns_oracle.py), all host threads."""
+def cpu_reference_rate(n_graphs, n_points, steps, warmup, budget_s=25.0, batch=None, chunk=0):
+    """graphs/s of the CPU port of the reference forward (oracle/cns_oracle.py), all host threads.  A step covers all
+    `n_graphs` graphs; with `chunk` > 0 it does so as ceil(n_graphs / chunk) forward calls of `chunk` graphs (the CPU
+    port is fastest at moderate batch sizes - cache footprint - so this is its best way through the workload)."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cns_oracle
     from cns_b200 import ckpt
     torch.set_num_threads(os.cpu_count() or 1)
     sd = ckpt.read_state_dict(os.path.join(ROOT, "checkpoints", "cns.pth"))
-    if batch is None:
-        batch = build_batches(n_graphs, n_points, 2022, 1)[0]
+    if batch is None and chunk and chunk < n_graphs:
+        from cns_b200 import synth
+        from cns_b200.data import Batch
+        scenes = synth.make_scenes(n_graphs, n_points, seed=2022, n_layouts=64)
+        frames = [s.frame(MISSING) for s in scenes]
+        batches = [Batch.from_data_list(frames[i:i + chunk]) for i in range(0, n_graphs, chunk)]
+    else:
+        batches = [batch if batch is not None else build_batches(n_graphs, n_points, 2022, 1)[0]]
     with torch.no_grad():
         for _ in range(max(1, warmup)):
-            cns_oracle.forward(sd, batch, None)
+            for b in batches:
+                cns_oracle.forward(sd, b, None)
         t0, done = time.perf_counter(), 0
         for _ in range(steps):
-            cns_oracle.forward(sd, batch, None)
+            for b in batches:
+                cns_oracle.forward(sd, b, None)
             done += 1
             if time.perf_counter() - t0 > budget_s:
                 break
@@ -232,9 +243,11 @@ def main():
         if rank != 0:
             return
         n_cpu = args.cpu_sample or args.graphs
-        rate, ms, done, cores = cpu_reference_rate(n_cpu, args.points, args.steps, args.warmup, 150.0)
-        sample = "%d of the %d graphs per step (N=%d keypoints, 10%% missing), fp32 torch CPU, %d steps" % (
-            n_cpu, args.graphs, args.points, done)
+        rate, ms, done, cores = cpu_reference_rate(n_cpu, args.points, args.steps, args.warmup, 150.0, chunk=args.cpu_chunk)
+        sample = "all %d of the %d graphs per step (N=%d keypoints, 10%% missing) as %d forward calls of %d graphs (the port's " \
+                 "fastest batch size, see cpu_baseline.batch_sweep of the b200 arm), fp32 torch CPU, %d steps" % (
+                     n_cpu, args.graphs, args.points, -(-n_cpu // max(args.cpu_chunk, 1)) if args.cpu_chunk else 1,
+                     args.cpu_chunk or n_cpu, done)
         emit({
             "impl": "reference", "metric": "servo graphs/sec (fwd)", "value": rate, "unit": "graphs/s",
             "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": ms,

@@ -64,6 +64,7 @@ def _declare(lib):
         "cns_graphvs_forward": (i32, [vp, C.POINTER(cns_batch), vp, vp, vp, vp, vp, vp, sz, vp, sz, vp]),
         "cns_forward_status": (i32, [vp, vp]),
         "cns_objectives": (i32, [vp, vp, vp, i64, C.c_float, vp, vp, vp, vp]),
+        "cns_postprocess": (i32, [vp, vp, vp, i64, vp, vp]),
         "cns_clip_adamw_workspace_bytes": (sz, []),
         "cns_clip_adamw": (i32, [vp, vp, vp, vp, vp, i64] + [C.c_float] * 6 + [i64, C.c_float, vp, vp, sz, vp]),
         "cns_backward_workspace_bytes": (sz, [C.POINTER(cns_batch)]),

@@ -19,7 +19,10 @@ from . import _lib
 
 def _prepare_similarity(X: np.ndarray):
     """S as sklearn's AffinityPropagation.fit + _affinity_propagation build it (incl. noise).  Returns
-    (S, degenerate) - degenerate inputs (all similarities equal) are left to sklearn itself."""
+    (S, degenerate labels | None): for inputs whose similarities are all equal sklearn returns before it draws
+    any noise (`_equal_similarities_and_preferences`, _affinity_propagation.py:35-55): every sample its own
+    cluster when the preference exceeds the common similarity, one cluster otherwise - restated here, no
+    scikit-learn call."""
     from sklearn.metrics import euclidean_distances
     X = np.ascontiguousarray(X, dtype=np.float64)
     n = X.shape[0]
@@ -27,12 +30,13 @@ def _prepare_similarity(X: np.ndarray):
     preference = np.median(S)
     mask = np.ones(S.shape, dtype=bool)
     np.fill_diagonal(mask, 0)
-    if n == 1 or (np.all(S[mask].flat == S[mask].flat[0]) and True):
-        return S, True
+    if n == 1 or np.all(S[mask].flat == S[mask].flat[0]):
+        labels = np.arange(n) if preference > S.flat[n - 1] else np.zeros(n, dtype=np.int64)
+        return S, labels
     S.flat[:: n + 1] = preference
     rs = np.random.mtrand._rand                       # check_random_state(None)
     S += (np.finfo(S.dtype).eps * S + np.finfo(S.dtype).tiny * 100) * rs.standard_normal(size=(n, n))
-    return S, False
+    return S, None
 
 
 def _labels_from_exemplars(S: np.ndarray, E: np.ndarray):
@@ -64,9 +68,8 @@ def affinity_propagation_device(point_sets: Sequence[np.ndarray], damping=0.9, m
     mats, out, todo = [], [None] * len(point_sets), []
     for k, X in enumerate(point_sets):
         S, degenerate = _prepare_similarity(X)
-        if degenerate:
-            from sklearn.cluster import AffinityPropagation
-            out[k] = AffinityPropagation(damping=damping).fit_predict(np.asarray(X))
+        if degenerate is not None:
+            out[k] = degenerate
         else:
             todo.append(k)
             mats.append(S)

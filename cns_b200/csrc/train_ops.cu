@@ -66,6 +66,26 @@ objectives_kernel(const float* __restrict__ vec, const float* __restrict__ nrm, 
   }
 }
 
+// GraphVS.postprocess on (B,6) predictions (functions.py:26-38): unit direction x (1 + ELU(norm)), translation x tPo_norm.
+// (the inference forward emits this fused from the pool/head kernel; this is the stand-alone form for training loops)
+__global__ void __launch_bounds__(256)
+postprocess_kernel(const float* __restrict__ vec, const float* __restrict__ nrm, const float* __restrict__ tpo, int64_t nb,
+                   float* __restrict__ vel) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nb) return;
+  float v[6], vv = 0.f;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) { v[q] = vec[g * 6 + q]; vv = fmaf(v[q], v[q], vv); }
+  float scale = 1.f;
+  if (nrm) {
+    const float n = nrm[g];
+    scale = (1.f + (n > 0.f ? n : expm1f(n))) / (sqrtf(vv) + 1e-7f);
+  }
+  const float t = tpo ? tpo[g] : 1.f;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) vel[g * 6 + q] = v[q] * scale * (q < 3 ? t : 1.f);
+}
+
 // ---- clip + AdamW -------------------------------------------------------------------------------
 constexpr int NORM_BLOCKS = 256;
 
@@ -122,6 +142,15 @@ int cns_objectives(const float* vel_si_vec, const float* vel_si_norm, const floa
   CNS_REQUIRE(n_graphs > 0, "empty batch");
   objectives_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(vel_si_vec, vel_si_norm, vel_si_gt, n_graphs, grad_scale, loss_out3,
                                                          d_vec, d_norm);
+  CNS_LAUNCH_CHECK();
+  return CNS_OK;
+}
+
+int cns_postprocess(const float* vel_si_vec, const float* vel_si_norm, const float* tPo_norm, int64_t n_graphs,
+                    float* vel, void* stream) {
+  CNS_REQUIRE(vel_si_vec && vel, "NULL pointer");
+  if (n_graphs <= 0) return CNS_OK;
+  postprocess_kernel<<<ceil_div(n_graphs, 256), 256, 0, (cudaStream_t)stream>>>(vel_si_vec, vel_si_norm, tPo_norm, n_graphs, vel);
   CNS_LAUNCH_CHECK();
   return CNS_OK;
 }

@@ -1,53 +1,44 @@
-"""Velocity post-processing and training objectives (reference cns/models/functions.py).
+"""`postprocess` / `objectives` of the reference API (cns/models/functions.py:26-65) as calls into libcns_sm100.
 
-`postprocess` (functions.py:26-38): unit direction x (1 + ELU(norm)); translational part
-scaled by the scene distance `tPo_norm`.  The inference forward already produces this
-fused in the pool/head kernel (`RawPred.vel`); the torch version here is the generic
-entry the reference API exposes and what training uses on (B, 6) tensors.
-`objectives` (functions.py:41-65): 1 - cos(direction) + MSE on the inverse-ELU norm.
+Thin shim: the arithmetic is in `cns_postprocess` (unit direction x (1 + ELU(norm)), translation x `tPo_norm`) and
+`cns_objectives` (1 - cos direction loss + MSE on the inverse-ELU of |gt|, forward and gradient in one launch;
+csrc/train_ops.cu).  Like the rest of the package there is no CPU implementation: CPU tensors raise.
 """
 import torch
-import torch.nn.functional as F
+
+from . import _lib
 
 
 def _field(data, key):
     return data[key] if isinstance(data, dict) else getattr(data, key)
 
 
-def alpha_p_elu(x, alpha=1.0):
-    return alpha + F.elu(x, alpha=alpha)
-
-
-def reverse_alpha_p_elu(y: torch.Tensor, alpha=1.0, eps=1e-7):
-    return torch.where(y < alpha, torch.log(y / alpha + eps), y - alpha)
-
-
-def scaled_cosine_similarity_loss(pred, target):
-    return 1 - F.cosine_similarity(pred, target, dim=-1)
+def _need_cuda(t, what):
+    if not t.is_cuda:
+        raise _lib.CnsError("%s runs on CUDA tensors only (libcns_sm100 has no CPU path)" % what)
 
 
 def postprocess(raw_pred, data, post_scale: bool) -> torch.Tensor:
-    vel_vec, vel_norm = raw_pred[0], raw_pred[1]
-    if vel_norm is None:
-        vel = vel_vec
-    else:
-        vel = vel_vec / (torch.norm(vel_vec, dim=-1, keepdim=True) + 1e-7) * alpha_p_elu(vel_norm, alpha=1)
-    if post_scale:
-        vel = vel.clone()
-        vel[:, :3] *= _field(data, "tPo_norm").to(vel).view(-1, 1)
+    """functions.py:26-38.  No gradient flows through the result (the reference only uses it to drive the simulator
+    / robot, train_gvs_short_seq.py:41-44)."""
+    vec, nrm = raw_pred[0].detach(), raw_pred[1]
+    _need_cuda(vec, "postprocess")
+    vec = vec.contiguous().float()
+    nrm = None if nrm is None else nrm.detach().contiguous().float()
+    tpo = _field(data, "tPo_norm").to(vec.device, torch.float32).reshape(-1).contiguous() if post_scale else None
+    vel = torch.empty_like(vec)
+    _lib.check(_lib.load().cns_postprocess(_lib.ptr(vec), _lib.ptr(nrm), _lib.ptr(tpo), vec.shape[0], _lib.ptr(vel),
+                                           _lib.stream_ptr(vec.device)), "cns_postprocess")
     return vel
 
 
 def objectives(raw_pred, data, gt_si: bool, weight=1):
-    vel_vec, vel_norm = raw_pred[0], raw_pred[1]
-    gt = _field(data, "vel_si" if gt_si else "vel").to(vel_vec)
-    dir_loss = scaled_cosine_similarity_loss(vel_vec * weight, gt * weight).mean()
-    if vel_norm is None:
-        norm_loss = F.mse_loss(vel_vec * weight, gt * weight, reduction="mean")
-    else:
-        gt_norm = torch.norm(gt, dim=-1, keepdim=True)
-        norm_loss = F.mse_loss(vel_norm, reverse_alpha_p_elu(gt_norm, eps=1e-5), reduction="mean")
-    loss = dir_loss + norm_loss
-    # one host sync instead of the reference's three .item() calls
-    d, n, t = torch.stack([dir_loss.detach(), norm_loss.detach(), loss.detach()]).tolist()
+    """functions.py:41-65 -> ({"dir_loss", "norm_loss", "total_loss"}, loss); `loss` carries the gradient
+    (`cns_objectives` computes it in the same launch).  `weight` scales both arguments of a cosine similarity and is
+    therefore without effect in the regress_norm=True form this library implements."""
+    from .train import fused_objectives
+    _need_cuda(raw_pred[0], "objectives")
+    gt = _field(data, "vel_si" if gt_si else "vel")
+    loss, triple = fused_objectives(raw_pred, {"vel_si": gt})
+    d, n, t = triple.tolist()          # one host sync instead of the reference's three .item() calls
     return {"dir_loss": d, "norm_loss": n, "total_loss": t}, loss

@@ -165,6 +165,12 @@ int cns_graphvs_backward(cns_handle* h, const cns_batch* b, const float* hidden_
 int cns_objectives(const float* vel_si_vec, const float* vel_si_norm, const float* vel_si_gt, int64_t n_graphs,
                    float grad_scale, float* loss_out3, float* d_vec, float* d_norm, void* stream);
 
+/* GraphVS.postprocess (functions.py:26-38, post_scale=True) on device predictions: vel (B,6) = vel_si_vec /
+ * (|vel_si_vec| + 1e-7) * (1 + ELU(vel_si_norm)), translational part x tPo_norm.  vel_si_norm NULL: vel = vel_si_vec
+ * (regress_norm=False); tPo_norm NULL: no distance scaling (post_scale=False). */
+int cns_postprocess(const float* vel_si_vec, const float* vel_si_norm, const float* tPo_norm, int64_t n_graphs,
+                    float* vel, void* stream);
+
 /* clip_grad_norm_(max_norm) + AdamW over flat parameter / gradient / moment buffers (trainer.py:96-100,
  * train_cns.py:65-69); decay_mask (n) u8 selects the decayed group.  `grad_div` pre-divides the gradients
  * (world size after a summing all-reduce).  grad_norm_out: optional device float (pre-clip norm). */

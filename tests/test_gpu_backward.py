@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import cns_oracle
-from cns_b200 import Batch, GraphVS, ckpt, synth
+from cns_b200 import Batch, GraphVS, _lib, ckpt, synth
 from cns_b200.train import TBPTTStepper, make_optimizers
 
 pytestmark = pytest.mark.gpu
@@ -120,23 +120,30 @@ def test_tbptt_step_matches_oracle_step(state_dict):
     assert torch.isfinite(out[0]).all()
 
 
-def test_fused_objectives_match_reference_loss():
-    """cns_objectives (loss + gradients in one launch) vs functions.objectives + torch autograd."""
+def test_objectives_and_postprocess_match_the_oracle():
+    """GraphVS.objectives / postprocess (functions.py:26-65 -> cns_objectives / cns_postprocess) vs the CPU oracle's
+    restatement with torch autograd: loss triple, gradients w.r.t. both heads, post-processed velocity."""
     from cns_b200 import functions
-    from cns_b200.train import fused_objectives
     g = torch.Generator().manual_seed(0)
-    vec = torch.randn(37, 6, generator=g).cuda().requires_grad_(True)
-    nrm = torch.randn(37, 1, generator=g).cuda().requires_grad_(True)
+    vec_h, nrm_h = torch.randn(37, 6, generator=g), torch.randn(37, 1, generator=g)
     gt = torch.randn(37, 6, generator=g) * torch.rand(37, 1, generator=g) * 2     # norms on both sides of 1
-    data = {"vel_si": gt.cuda()}
-    res, loss_ref = functions.objectives((vec, nrm), data, gt_si=True)
-    gv_ref, gn_ref = torch.autograd.grad(loss_ref * 3.0, (vec, nrm))
-    loss, triple = fused_objectives((vec, nrm), data)
+    tpo = torch.rand(37, generator=g) + 0.3
+    vec, nrm = vec_h.cuda().requires_grad_(True), nrm_h.cuda().requires_grad_(True)
+    data = {"vel_si": gt.cuda(), "tPo_norm": tpo.cuda()}
+    res, loss = functions.objectives((vec, nrm), data, gt_si=True)
     gv, gn = torch.autograd.grad(loss * 3.0, (vec, nrm))
-    assert abs(float(loss) - float(loss_ref)) < 1e-6
-    t = triple.cpu().tolist()
-    assert abs(t[0] - res["dir_loss"]) < 1e-6 and abs(t[1] - res["norm_loss"]) < 1e-6
-    assert float((gv - gv_ref).abs().max()) < 1e-6 and float((gn - gn_ref).abs().max()) < 1e-6
+    vo, no = vec_h.double().requires_grad_(True), nrm_h.double().requires_grad_(True)
+    d_ref, n_ref, t_ref = cns_oracle.objectives((vo, no), gt.double())
+    gv_ref, gn_ref = torch.autograd.grad(t_ref * 3.0, (vo, no))
+    assert abs(float(loss) - float(t_ref)) < 1e-6
+    assert abs(res["dir_loss"] - float(d_ref)) < 1e-6 and abs(res["norm_loss"] - float(n_ref)) < 1e-6
+    assert abs(res["total_loss"] - float(t_ref)) < 1e-6
+    assert float((gv.cpu().double() - gv_ref).abs().max()) < 1e-6 and float((gn.cpu().double() - gn_ref).abs().max()) < 1e-6
+    vel = GraphVS.postprocess((vec, nrm), data)
+    vel_ref = cns_oracle.postprocess((vec_h.double(), nrm_h.double()), tpo.double())
+    assert float((vel.cpu().double() - vel_ref).abs().max()) < 1e-6 * float(vel_ref.abs().max())
+    with pytest.raises(_lib.CnsError):
+        functions.objectives((vec_h, nrm_h), {"vel_si": gt}, gt_si=True)          # no CPU path
 
 
 def test_fused_clip_adamw_matches_torch(state_dict):

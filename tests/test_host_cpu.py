@@ -161,9 +161,9 @@ def test_live_reference_cross_check(state_dict):
     res, loss = fn.objectives((rv, rn), rb, gt_si=True)
     dl, nl, tl = cns_oracle.objectives((ov, on), gt)
     assert abs(float(loss) - float(tl)) < 1e-5
-    from cns_b200 import functions
-    res2, loss2 = functions.objectives((ov, on), mb, gt_si=True)
-    assert abs(float(loss) - float(loss2)) < 1e-5 and abs(res["dir_loss"] - res2["dir_loss"]) < 1e-5
+    assert abs(res["dir_loss"] - float(dl)) < 1e-5 and abs(res["norm_loss"] - float(nl)) < 1e-5
+    rvel = fn.postprocess((rv, rn), rb, post_scale=True)
+    assert float((rvel - cns_oracle.postprocess((ov, on), mb.tPo_norm.reshape(-1))).abs().max()) < 1e-6
 
 
 @needs_ref
@@ -227,3 +227,22 @@ def test_closed_loop_servo_converges(state_dict):
     e1 = synth.pose_error(scene.cur_wcT, scene.tar_wcT)
     assert e1[0] < 1.0 and e1[1] < 10.0, (e0, e1)   # < 1 degree, < 10 mm
     assert e1[0] < 0.1 * e0[0]
+
+
+def test_degenerate_similarity_rule_matches_sklearn():
+    """cluster._prepare_similarity restates sklearn's early exit for mutually equal similarities (no noise drawn,
+    numpy's global stream untouched) instead of calling scikit-learn behind the device path's back."""
+    import warnings
+    from sklearn.cluster import AffinityPropagation
+    from cns_b200.cluster import _prepare_similarity
+    for X in (np.tile([[0.3, -0.2]], (20, 1)), np.array([[0.0, 0.0], [1.0, 0.0]]), np.array([[0.5, 0.5]])):
+        np.random.seed(3)
+        state = np.random.get_state()[1].copy()
+        _, labels = _prepare_similarity(X)
+        assert np.array_equal(np.random.get_state()[1], state)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = AffinityPropagation(damping=0.9).fit_predict(X)
+        assert labels is not None and np.array_equal(labels, ref), (X.shape, labels, ref)
+    _, labels = _prepare_similarity(np.random.default_rng(0).random((30, 2)))
+    assert labels is None
