@@ -105,7 +105,9 @@ struct cns_handle {
   void* bwd_pack; long long bwd_pack_version;   // transposed operands of the backward pass (backward.cu)
   // tensor-core (tcgen05) encoder operands: bf16 image then f16 image, 5 swizzled 32 KB tiles each
   unsigned char* tc_w_img;
-  float tc_small_host[128 * 2 + 128 + 128 * 4 + 128];   // in_enc / pos_nn.0 weights passed as kernel params
+  unsigned char* tc_w_split;                            // fp32 mode: bf16 (hi, lo) slices of the same five matrices (encoder_split.cu)
+  int no_split_encoder;                                 // CNS_NO_SPLIT_ENCODER=1: fp32 mode keeps the FFMA edge kernel (A-B runs)
+  alignas(16) float tc_small_host[128 * 2 + 128 + 128 * 4 + 128];   // in_enc / pos_nn.0 weights passed as kernel params
   int tc_tile_n;                                        // edges per tensor-core tile (32 or 64)
   int no_split_gemm;                                    // CNS_NO_SPLIT_GEMM=1: backward GEMMs stay on the fp32 FFMA kernel (A-B runs)
   int no_fused_backbone;                                // CNS_NO_FUSED_BACKBONE=1: keep the per-layer kernels (debugging / A-B runs)

@@ -121,7 +121,9 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   EncPreArgs pre{};
   pre.n_clusters = C; pre.x_tar = b->x_tar; pre.pos_tar = b->pos_tar; pre.centers = b->cluster_centers;
   pre.node_graph = b->node_graph; pre.w_in = h->P(P_IN_W); pre.b_in = h->P(P_IN_B); pre.lin_dst_t = pk.lin_dst_t;
-  if (h->precision != CNS_PREC_FP32) { pre.lin_dst_t = pk.tc_lin_dst_t; pre.a_bias = pk.tc_adst_bias; }   // a_dst := A0 (a_dst + b_pos1) + b_attn0
+  // every tensor-core edge kernel (16-bit modes and the operand-split fp32 mode) consumes the composed form
+  const bool composed = h->precision != CNS_PREC_FP32 || !h->no_split_encoder;
+  if (composed) { pre.lin_dst_t = pk.tc_lin_dst_t; pre.a_bias = pk.tc_adst_bias; }   // a_dst := A0 (a_dst + b_pos1) + b_attn0
   pre.a_dst = f.a_dst; pre.pos_clu = f.pos_clu; pre.clu_graph = f.clu_graph;
   const bool fork_pre = !tcache && (C > PREP_SMALL_MAX || B > PREP_SMALL_MAX);
   if (fork_pre) {
@@ -205,7 +207,8 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   const bool timed = h->timing && h->ev_n < 256;
   if (timed) CNS_CUDA_CHECK(cudaEventRecord(h->ev[2 * h->ev_n], s));
   if (h->precision == CNS_PREC_FP32) {
-    RUN(enc_edge_fp32(ee, s));
+    if (h->no_split_encoder) { RUN(enc_edge_fp32(ee, s)); }
+    else { RUN(enc_edge_split(ee, h, s)); }
   } else {
     RUN(enc_edge_tc(ee, h->precision, h, s));
   }
@@ -213,7 +216,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
 
   EncFinishArgs ef{};
   ef.n_clusters = C; ef.n_slots = f.n_slots;
-  ef.piece_e = (h->precision == CNS_PREC_FP32) ? ENC_PIECE_E : tc_piece_edges(b->n_e01, h); ef.clu_rowptr = f.clu_rowptr; ef.partial = f.partial;
+  ef.piece_e = (h->precision == CNS_PREC_FP32) ? (h->no_split_encoder ? ENC_PIECE_E : split_piece_edges(b->n_e01, h)) : tc_piece_edges(b->n_e01, h); ef.clu_rowptr = f.clu_rowptr; ef.partial = f.partial;
   ef.clu_feat = f.clu_feat; ef.out_t = pk.out_t; ef.b_out = h->P(P_OUT_B); ef.cluster_mask = b->cluster_mask;
   ef.x_clu = f.x_clu;
   ef.cat_out = (tc && !fused) ? f.pq : nullptr;       // (C,256) scratch; pq is free until the first [P|Q] projection
@@ -410,7 +413,7 @@ int cns_target_cache_create(cns_handle* h, const cns_batch* b, void* stream, cns
     EncPreArgs pre{};
     pre.n_clusters = C; pre.x_tar = b->x_tar; pre.pos_tar = b->pos_tar; pre.centers = b->cluster_centers;
     pre.node_graph = b->node_graph; pre.w_in = h->P(P_IN_W); pre.b_in = h->P(P_IN_B); pre.lin_dst_t = h->pk.lin_dst_t;
-    if (h->precision != CNS_PREC_FP32) { pre.lin_dst_t = h->pk.tc_lin_dst_t; pre.a_bias = h->pk.tc_adst_bias; }
+    if (h->precision != CNS_PREC_FP32 || !h->no_split_encoder) { pre.lin_dst_t = h->pk.tc_lin_dst_t; pre.a_bias = h->pk.tc_adst_bias; }
     pre.a_dst = c->a_dst; pre.pos_clu = c->pos_clu; pre.clu_graph = c->clu_graph;
     rc = enc_cluster_pre(pre, s);
   } while (false);

@@ -179,6 +179,7 @@ int repack(cns_handle* h, cudaStream_t s) {
     CNS_LAUNCH_CHECK();
   }
   if ((rc = tc_pack_weights(h, s)) != CNS_OK) return rc;
+  if ((rc = split_pack_weights(h, s)) != CNS_OK) return rc;
   {
     // node-GEMM weight images (bf16 + f16), 2 bytes per element
     struct Item { const float* wt; int k, n; unsigned char** dst; };
@@ -239,6 +240,7 @@ int cns_create(cns_handle** out, int device) {
   h->tc_tile_n = 32;
   h->no_fused_backbone = getenv("CNS_NO_FUSED_BACKBONE") ? 1 : 0;
   h->no_split_gemm = getenv("CNS_NO_SPLIT_GEMM") ? 1 : 0;
+  h->no_split_encoder = getenv("CNS_NO_SPLIT_ENCODER") ? 1 : 0;
   h->sm_count = prop.multiProcessorCount;
   size_t off = 0;
   for (int k = 0; k < P_COUNT; ++k) {
@@ -274,6 +276,7 @@ int cns_destroy(cns_handle* h) {
   cudaFree(h->packed_base);
   free_bwd_pack(h);
   if (h->tc_w_img) cudaFree(h->tc_w_img);
+  if (h->tc_w_split) cudaFree(h->tc_w_split);
   if (h->pk.tc_node_base) cudaFree(h->pk.tc_node_base);
   if (h->servo_tcache) cns_target_cache_destroy(h->servo_tcache);
   free(h->servo_tkey);

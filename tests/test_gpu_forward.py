@@ -396,6 +396,37 @@ def test_full_size_batch_properties(net, state_dict):
     assert rel(pp[0], pred[0][torch.as_tensor(perm, device="cuda")]) < 1e-5
 
 
+def test_split_operand_encoder_vs_ffma_encoder(state_dict, monkeypatch):
+    """fp32 mode runs the encoder edge chain on tcgen05 with bf16 (hi, lo) operand splits (encoder_split.cu); the
+    FFMA kernel it replaces is still there behind CNS_NO_SPLIT_ENCODER=1.  Both must sit within 1e-4 of the fp64
+    oracle on ragged batches with missing keypoints over recurrent frames, and close to each other."""
+    path = os.path.join(ROOT, "checkpoints", "cns.pth")
+    tc = ckpt.load_model(path, "cuda:0")
+    monkeypatch.setenv("CNS_NO_SPLIT_ENCODER", "1")
+    ffma = ckpt.load_model(path, "cuda:0")
+    ffma._handle(torch.device("cuda:0"))            # the switch is read when the handle is created
+    monkeypatch.delenv("CNS_NO_SPLIT_ENCODER")
+    rng = np.random.default_rng(12)
+    np.random.seed(12)
+    scenes = [synth.Scene(rng, n) for n in (4, 17, 33, 100, 512, 700, 64, 31)]
+    h_tc = h_ff = h_o = None
+    for frame in range(3):
+        frames = [s.frame(float(rng.uniform(0, 0.6))) for s in scenes]
+        batch = Batch.from_data_list(frames)
+        ov, on, h_o = cns_oracle.forward(state_dict, batch, h_o, dtype=torch.float64)
+        with torch.no_grad():
+            a = tc(batch.to("cuda:0"), h_tc, check=True)
+            b = ffma(batch.to("cuda:0"), h_ff, check=True)
+        h_tc, h_ff = a[2], b[2]
+        for got in (a, b):
+            assert rel(got[0], ov) < 1e-4 and rel(got[1], on) < 1e-4 and rel(got[2], h_o) < 1e-4
+        assert rel(a[2], b[2]) < 5e-5 and rel(a[0], b[0]) < 5e-5
+        print("frame %d: split %.2e / %.2e   ffma %.2e / %.2e (vel / hidden vs fp64)" % (
+            frame, rel(a[0], ov), rel(a[2], h_o), rel(b[0], ov), rel(b[2], h_o)))
+        for s, v in zip(scenes, a.vel.cpu().numpy()):
+            s.step(v * 2)
+
+
 @pytest.mark.parametrize("precision", ["f16", "bf16"])
 def test_full_size_batch_16bit_modes(state_dict, precision):
     """The headline shape in the headline mode: 1024 graphs x 512 keypoints through the tcgen05 encoder kernel and
