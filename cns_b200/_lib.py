@@ -89,6 +89,12 @@ def _declare(lib):
         "cns_pixel_stop_workspace_bytes": (sz, [i64]),
         "cns_pixel_stop_error": (i32, [vp, vp, vp, vp, vp, i64, i64, C.c_float, C.c_float, vp, vp, vp, vp, vp, sz, vp]),
         "cns_label_nearest": (i32, [vp, vp, i64, vp, vp, vp, vp]),
+        "cns_ap_similarity": (i32, [vp, vp, vp, vp, i64, vp, vp]),
+        "cns_segment_median_workspace_bytes": (sz, [i64]),
+        "cns_segment_median": (i32, [vp, vp, i64, i64, vp, vp, sz, vp]),
+        "cns_ap_prepare": (i32, [vp, vp, vp, vp, vp, vp, i64, vp]),
+        "cns_ap_labels": (i32, [vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, sz, vp]),
+        "cns_graph_layout": (i32, [vp, vp, vp, vp, i64, vp, vp, vp, vp]),
         "cns_ap_workspace_bytes": (sz, [i64, i64, i64, i32]),
         "cns_affinity_propagation": (i32, [vp, vp, vp, vp, i64, i64, i64, C.c_double, i32, i32, vp, vp, vp, vp, sz, vp]),
     }

@@ -110,53 +110,67 @@ def label_nearest_exemplar(points, exemplar_indices, device="cuda:0") -> np.ndar
     return labels.cpu().numpy().astype(np.int64)
 
 
+def _cuda_present() -> bool:
+    try:
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
 class GraphGenerator(object):
-    # "host": scikit-learn on the CPU exactly like the reference; "device": the same Affinity Propagation
-    # with its message passing on the GPU (cns_b200/cluster.py, label-identical to sklearn)
-    CLUSTER_BACKEND = "host"
+    # Where the clustering and the layout derived from it run:
+    #   "device": everything on the GPU (cns_b200/cluster.py: similarity, median preference, Affinity Propagation,
+    #             exemplar refinement, member order, median centres) - bit-identical with the host path;
+    #   "host"  : scikit-learn + numpy on the CPU exactly like the reference.
+    # None (default) = "device" whenever a CUDA device is present.
+    CLUSTER_BACKEND = None
     CLUSTER_DEVICE = "cuda:0"
 
     @classmethod
-    def build_many(cls, target_point_sets, device="cuda:0"):
-        """Generators for many targets with ONE batched device clustering call.  Labels equal the
-        reference's sequential construction as long as no set needs the KMeans(4) fallback (the
-        fallback draws from numpy's global RNG after, not between, the AP noise draws)."""
-        from .cluster import affinity_propagation_device
+    def backend(cls) -> str:
+        return cls.CLUSTER_BACKEND or ("device" if _cuda_present() else "host")
+
+    @classmethod
+    def build_many(cls, target_point_sets, device=None):
+        """Generators for many targets with ONE batched device clustering + layout call.  Equal to the reference's
+        sequential construction as long as no set needs the KMeans(4) fallback (the fallback draws from numpy's
+        global RNG after, not between, the AP noise draws)."""
+        from .cluster import build_graphs_device
         sets = [np.asarray(p) for p in target_point_sets]
         big = [k for k, p in enumerate(sets) if len(p) > 16]
-        labels = dict(zip(big, affinity_propagation_device([sets[k] for k in big], device=device))) if big else {}
-        out = []
-        for k, p in enumerate(sets):
-            lab = labels.get(k)
-            if lab is not None and np.unique(lab).shape[0] < 4:
-                from sklearn.cluster import KMeans
-                lab = KMeans(n_clusters=4).fit_predict(p)
-            out.append(cls(p, labels=lab) if lab is not None else cls(p))
-        return out
+        layouts = dict(zip(big, build_graphs_device([sets[k] for k in big], device=device or cls.CLUSTER_DEVICE))) if big else {}
+        return [cls(p, layout=layouts.get(k)) for k, p in enumerate(sets)]
 
     @classmethod
     def from_exemplars(cls, target_points, exemplar_indices, device="cuda:0"):
         """Graph whose clusters are the Voronoi cells of the given exemplar keypoints (labels computed
-        on the device).  Used where host-side Affinity Propagation is impractical (N > ~1000)."""
+        on the device)."""
         return cls(target_points, labels=label_nearest_exemplar(target_points, exemplar_indices, device))
 
-    def __init__(self, target_points, labels=None):
+    def __init__(self, target_points, labels=None, layout=None):
         target_points = np.asarray(target_points)
         self.num_points = len(target_points)
         self.target_points = target_points
         n = self.num_points
+        self.cluster_method = "given" if labels is not None else "one-cluster-per-point"
 
+        if layout is None and labels is None and n > 16 and self.backend() == "device":
+            from .cluster import build_graphs_device
+            layout = build_graphs_device([target_points], device=self.CLUSTER_DEVICE)[0]
+        if layout is not None:
+            # everything below was computed on the device (cns_ap_labels / cns_graph_layout)
+            self.cluster_method = layout.method
+            self.yhat = layout.labels
+            self.cluster_ids = np.arange(layout.cluster_size.shape[0], dtype=np.int64)
+            self.cluster_points_count = layout.cluster_size
+            self._finish(layout.labels.astype(np.int64), layout.member_order, layout.cluster_size, layout.centers)
+            return
         if labels is not None:
             self.yhat = np.asarray(labels)
             self.cluster_ids, self.cluster_points_count = np.unique(self.yhat, return_counts=True)
         elif n > 16:
-            if self.CLUSTER_BACKEND == "device":
-                from .cluster import cluster_points_device
-                self.yhat, self.cluster_ids, self.cluster_points_count = \
-                    cluster_points_device(target_points, device=self.CLUSTER_DEVICE)
-            else:
-                self.yhat, self.cluster_ids, self.cluster_points_count = \
-                    try_cluster_points(target_points, max_tries=3)
+            self.cluster_method = "affinity-propagation-host"
+            self.yhat, self.cluster_ids, self.cluster_points_count = try_cluster_points(target_points, max_tries=3)
         else:
             self.yhat = np.arange(n)
             self.cluster_ids = self.yhat.copy()
@@ -181,8 +195,18 @@ class GraphGenerator(object):
         is_min = dist == seg_min[seg_id]
         pos = np.arange(n)
         first = np.minimum.reduceat(np.where(is_min, pos, n), starts) if n else pos
-        self.cluster_centers_index = order[first].astype(np.int64)
+        self._finish(rank, order, sizes, order[first].astype(np.int64))
 
+    def _finish(self, rank, order, sizes, centers):
+        """Edge lists and inverse permutations from (cluster rank per point, cluster-major member order, member counts,
+        centre per cluster) - integer bookkeeping shared by the host and the device path (graph_gen.py:166-196)."""
+        n, target_points = self.num_points, self.target_points
+        sizes = np.asarray(sizes, dtype=np.int64)
+        starts = np.cumsum(sizes) - sizes
+        self.belong_cluster_index = rank
+        self._member_order, self._member_starts, self._member_sizes = order, starts, sizes
+        seg_id = np.repeat(np.arange(sizes.shape[0]), sizes)
+        self.cluster_centers_index = np.asarray(centers, dtype=np.int64)
         self.cluster_points_index = [order[s:s + c] for s, c in zip(starts, sizes)]
         self.l0_to_l1_edge_index = np.stack([order.astype(np.int64), seg_id.astype(np.int64)], axis=0)
         self.l1_dense_edge_index = gen_dense_connect_edges(np.arange(len(self.cluster_ids)))

@@ -320,6 +320,39 @@ int cns_affinity_propagation(const double* S, const int64_t* pt_off, const int64
                              unsigned char* E_out, int32_t* n_iter_out, int32_t* converged_host,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- device graph builder around the Affinity Propagation loop (cns/midend/graph_gen.py:104-196) -----------------
+ * Batched over G target point sets: points (sum n, 2) f64, pt_off / mat_off (G+1) int64 prefix sums of n_g / n_g^2,
+ * row_graph (sum n) int32 - all on the device.  Every fp64 result is bit-identical with the numpy / scikit-learn
+ * expression it replaces (same operation order, no contraction).
+ *
+ * cns_ap_similarity   : S = -euclidean_distances(X, squared=True) as sklearn.cluster.AffinityPropagation.fit builds it
+ *                       (_affinity_propagation.py:517).
+ * cns_segment_median  : np.median of each fp64 segment values[seg_off[s]:seg_off[s+1]] (exact radix select; the AP
+ *                       preference is median(S), _affinity_propagation.py:526).  max_segment = longest segment.
+ * cns_ap_prepare      : S.flat[::n+1] = preference; S += (eps * S + tiny * 100) * noise (_affinity_propagation.py:68-78);
+ *                       noise (sum n^2) f64 = the HOST RandomState's standard_normal((n, n)) draws, in order.
+ * cns_ap_labels       : exemplar indicator E (from cns_affinity_propagation) -> labels: assignment, exemplar refinement,
+ *                       re-assignment, gapless relabelling (_affinity_propagation.py:147-166).  labels_out (sum n) int32
+ *                       (-1 everywhere when no exemplar emerged), exemplars_out (sum n) int32: the K_g cluster-centre
+ *                       point indices of problem g ascending at [pt_off[g], pt_off[g] + K_g), n_clusters_out (G).
+ *                       workspace: 2 * align256(4 * sum n) bytes.
+ * cns_graph_layout    : GraphGenerator.__init__ after clustering (graph_gen.py:146-196) from gapless labels:
+ *                       member_order (sum n) int32 = l0_to_l1_edge_index[0] (cluster-major, ascending point index, local
+ *                       to the problem), cluster_size / centers (sum K) int32 at clu_off (G+1) int64 prefix of K_g:
+ *                       centre = member nearest to the per-cluster coordinate median, first minimum. */
+int cns_ap_similarity(const double* points, const int64_t* pt_off, const int64_t* mat_off, const int32_t* row_graph,
+                      int64_t n_rows_total, double* S_out, void* stream);
+size_t cns_segment_median_workspace_bytes(int64_t n_segments);
+int cns_segment_median(const double* values, const int64_t* seg_off, int64_t n_segments, int64_t max_segment,
+                       double* median_out, void* workspace, size_t workspace_bytes, void* stream);
+int cns_ap_prepare(double* S, const double* noise, const double* preference, const int64_t* pt_off,
+                   const int64_t* mat_off, const int32_t* row_graph, int64_t n_rows_total, void* stream);
+int cns_ap_labels(const double* S, const unsigned char* E, const int64_t* pt_off, const int64_t* mat_off,
+                  int64_t n_graphs, int64_t n_rows_total, int32_t* labels_out, int32_t* exemplars_out,
+                  int32_t* n_clusters_out, void* workspace, size_t workspace_bytes, void* stream);
+int cns_graph_layout(const double* points, const int32_t* labels, const int64_t* pt_off, const int64_t* clu_off,
+                     int64_t n_graphs, int32_t* member_order, int32_t* cluster_size, int32_t* centers, void* stream);
+
 /* 1-NN keypoint -> exemplar labelling, the only nearest-neighbour search of the
  * reference's clustering (sklearn AffinityPropagation final assignment,
  * argmax_k -||x - e_k||^2 ).  points (N,2) f64 ; point_graph (N,) graph id of
