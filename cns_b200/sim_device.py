@@ -26,6 +26,11 @@ from . import _lib, synth
 from .data import Batch
 
 
+def synth_intrinsic():
+    """(width, height, fx, fy, cx, cy) of CameraIntrinsic.default() (utils/perception.py:62-64)."""
+    return (640.0, 480.0, 540.0, 540.0, 320.0, 240.0)
+
+
 # ---------------------------------------------------------------------------------- SO(3) / SE(3), batched
 def so3_exp(w: torch.Tensor) -> torch.Tensor:
     """Rotation vectors (B,3) -> matrices (B,3,3) (Rodrigues)."""
@@ -101,15 +106,52 @@ def pose_error(cur_wcT: torch.Tensor, tar_wcT: torch.Tensor):
 
 # ---------------------------------------------------------------------------------- the environment
 class DeviceSceneBatch(object):
+    """B closed-loop point scenes resident on one GPU.
+
+    aug=False (default)   : the plain environment of round 1 - uniform random keypoint drop-out of a per-scene
+                            fraction in `missing`, straight-line PBVS labels, `tPo_norm` of the whole scene.
+    aug=True              : the reference's training distribution (sim/dataset.py:88-141 / dataset_long.py:81-140,
+                            `ObsAug.Default` = mismatch | area shift | jitter; `discard=True` adds RandomDiscard):
+                            10 % mismatched keypoints (N >= 10), position jitter, area-shift drop-out for scenes with
+                            >= 64 keypoints (`BatchedObservationSampler`), the 80 % cap on removed keypoints, zeroed
+                            coordinates of removed keypoints, and the supervisor shown the visible keypoints (or their
+                            area-shift weighted centre), which also sets `tPo_norm` per frame.
+    supervisor            : "pbvs_straight" (short sequences, dataset.py:33) | "pbvs_hybrid" (long, dataset_long.py:21)
+                            | "pbvs_center".
+    long_seq=True         : dataset_long.py's variants - rotating mismatches held for an exponential interval
+                            (`BatchedMismatcher`), jitter 0.0005 instead of 0.002.
+    reinit                : "scene" - a scene that converged / timed out / left the workspace restarts alone from a new
+                            initial pose (its hidden-state rows are reset by TBPTTStepper); "all" - the reference's
+                            loaders (dataset.py:242-246, dataset_long.py:215-222): nothing restarts alone, ALL scenes get
+                            new geometry, targets and poses once more than half of them need it.
+    """
+    TARGET_POSE_R_MEAN = 0.7              # np.mean(env.target_pose_r), sim/environment.py:52 (dist_scale of the sampler)
+
     def __init__(self, batch_size: int, rng: np.random.Generator, device="cuda:0", max_points: int = 512,
-                 max_steps: int = 200, missing=(0.0, 0.2), refresh_every: int = 0):
+                 max_steps: int = 200, missing=(0.0, 0.2), refresh_every: int = 0, aug: bool = False,
+                 supervisor: str = "pbvs_straight", long_seq: bool = False, reinit: str = "scene", discard: bool = False,
+                 min_points: int = 4):
+        assert reinit in ("scene", "all")
         self.B, self.rng, self.dev = batch_size, rng, torch.device(device)
         self.max_points, self.max_steps, self.missing, self.refresh_every = max_points, max_steps, missing, refresh_every
+        self.min_points = min_points
+        self.aug, self.supervisor, self.long_seq, self.reinit, self.discard = aug, supervisor, long_seq, reinit, discard
         self.lib = _lib.load()
         self.gen = torch.Generator(device=self.dev)
         self.gen.manual_seed(int(rng.integers(0, 2 ** 31 - 1)))
         self.calls = 0
-        self._build([synth.Scene(rng, int(rng.integers(4, max_points + 1))) for _ in range(batch_size)])
+        self.reinit_all_count = 0
+        self._build(self._new_scenes())
+
+    def _new_scenes(self):
+        """B fresh scenes; with a CUDA device all their target graphs come from ONE batched device clustering call."""
+        from .graph_gen import GraphGenerator
+        rng = self.rng
+        protos = [(synth.sample_points(rng, int(rng.integers(self.min_points, self.max_points + 1))), synth.sample_target_pose(rng))
+                  for _ in range(self.B)]
+        tars = [synth.project_norm(T, P) for P, T in protos]
+        gens = GraphGenerator.build_many(tars, device=self.dev) if GraphGenerator.backend() == "device" else [GraphGenerator(t) for t in tars]
+        return [synth.Scene(rng, len(P), generator=g, points=P, tar_wcT=T) for (P, T), g in zip(protos, gens)]
 
     # -- static part: geometry, target graphs ------------------------------------------------------------
     def _build(self, scenes):
@@ -123,9 +165,12 @@ class DeviceSceneBatch(object):
         d = lambda a, dt: torch.as_tensor(np.array(a), dtype=dt).to(dev)
         self.points = d(np.concatenate([s.points for s in scenes]), torch.float64)
         self.scene_of = d(np.repeat(np.arange(self.B), n_nodes), torch.int64)
+        self.n_nodes = d(n_nodes, torch.int64)
+        self.node_start = d(noff, torch.int64)
         self.tar_wcT = d(np.stack([s.tar_wcT for s in scenes]), torch.float64)
         self.cur_wcT = d(np.stack([s.cur_wcT for s in scenes]), torch.float64)
-        self.tpo = d([s.tPo_norm for s in scenes], torch.float32)
+        self.tpo_static = d([s.tPo_norm for s in scenes], torch.float32)
+        self.tpo = self.tpo_static
         self.x_tar = d(np.concatenate([g.target_points for g in gens]), torch.float32)
         self.belong = d(np.concatenate([g.belong_cluster_index + c for g, c in zip(gens, coff)]), torch.int64)
         self.member_order = d(np.concatenate([g.l0_to_l1_edge_index[0] + o for g, o in zip(gens, noff)]), torch.int64)
@@ -145,54 +190,157 @@ class DeviceSceneBatch(object):
         self.ws = torch.empty(self.lib.cns_graph_mask_workspace_bytes(self.N, self.Cn, self.B), dtype=torch.uint8, device=dev)
         self.steps = torch.zeros(self.B, dtype=torch.int64, device=dev)
         self.fresh = torch.ones(self.B, dtype=torch.bool, device=dev)
+        self.gt_vel = torch.zeros(self.B, 6, dtype=torch.float64, device=dev)
+        if self.aug:
+            from . import sim_aug
+            med = d(np.stack([np.median(g.target_points, axis=0) for g in gens]), torch.float64)
+            self._tar_med = med
+            self.sampler = sim_aug.BatchedObservationSampler(self.x_tar.double(), self.scene_of, self.B, med, 5.0, self.gen)
+            self.mismatcher = sim_aug.BatchedMismatcher(self.scene_of, self.n_nodes, 2.0, 0.1, self.gen)
+            # int(N * 0.1) mismatched (N >= 10), int(N * 0.1) discarded (10 <= N < 64, RandomDiscard only)
+            ten = (self.n_nodes.double() * 0.1).to(torch.int64)
+            self.n_mismatch = torch.where(self.n_nodes >= 10, ten, torch.zeros_like(ten))
+            self.n_discard = torch.where((self.n_nodes >= 10) & (self.n_nodes < 64), ten, torch.zeros_like(ten)) \
+                if self.discard else torch.zeros_like(ten)
+            self.mismatcher.counts = self.n_mismatch
 
     # -- per frame ------------------------------------------------------------------------------------------
+    def _visibility(self, cur_xy):
+        """(cur_xy', visible (sum N,) bool, mismatch (sum N,) bool, wPo (B,3)) of this frame."""
+        dev, so = self.dev, self.scene_of
+        if not self.aug:
+            frac = torch.rand(self.B, generator=self.gen, device=dev) * (self.missing[1] - self.missing[0]) + self.missing[0]
+            visible = torch.rand(self.N, generator=self.gen, device=dev) >= frac[so]
+            from .sim_aug import segment_mean
+            return cur_xy, visible, torch.zeros_like(visible), segment_mean(self.points, so, self.B)
+        from . import sim_aug
+        intr = synth_intrinsic()
+        pos = sim_aug.random_positions(so, self.n_nodes, self.gen)
+        if self.long_seq:                                  # rotating mismatches held for an exponential interval
+            mism, order = self.mismatcher(synth.DT)
+            cur_xy = sim_aug.rotate_within_subsets(cur_xy, so, mism, order, self.n_mismatch)
+        else:                                              # 10 % of the keypoints land anywhere in the image
+            mism = pos < self.n_mismatch[so]
+            u = torch.rand(self.N, 2, generator=self.gen, device=dev, dtype=torch.float64)
+            rnd = (u * torch.tensor([intr[0], intr[1]], dtype=torch.float64, device=dev)
+                   - torch.tensor([intr[4], intr[5]], dtype=torch.float64, device=dev)) / \
+                torch.tensor([intr[2], intr[3]], dtype=torch.float64, device=dev)
+            cur_xy = torch.where(mism[:, None], rnd, cur_xy)
+        scale = 0.0005 if self.long_seq else 0.002
+        cur_xy = cur_xy + scale * (torch.rand(self.N, 2, generator=self.gen, device=dev, dtype=torch.float64) * 2 - 1)
+        # drop-out: area shift for N >= 64, equal-probability discard for 10 <= N < 64 (if enabled)
+        observed, ratio = self.sampler(self.steps.double() * synth.DT, self.cur_wcT, self.TARGET_POSE_R_MEAN)
+        big = (self.n_nodes >= 64)[so]
+        discard = (pos >= self.n_mismatch[so]) & (pos < (self.n_mismatch + self.n_discard)[so])
+        removed = torch.where(big, ~observed, discard)
+        # "if too much points are removed, preserve some": keep only the first int(0.8 N) removed indices
+        rank = torch.cumsum(removed.to(torch.int64), 0) - removed.to(torch.int64)
+        rank = rank - rank[self.node_start][so]
+        n_removed = torch.zeros(self.B, dtype=torch.int64, device=dev).index_add_(0, so, removed.to(torch.int64))
+        cap = (self.n_nodes.double() * 0.8).to(torch.int64)
+        over = (n_removed.double() >= 0.8 * self.n_nodes.double())[so]
+        removed = removed & (~over | (rank < cap[so]))
+        visible = ~removed
+        cur_xy = torch.where(removed[:, None], torch.zeros_like(cur_xy), cur_xy)
+        # the points the supervisor is shown (dataset.py:136-141)
+        w_center = sim_aug.segment_mean(self.points, so, self.B, weight=ratio)
+        v_center = sim_aug.segment_mean(self.points[visible], so[visible], self.B)
+        wPo = torch.where((self.n_nodes >= 64)[:, None], w_center, v_center)
+        return cur_xy, visible, mism, wPo
+
     def observe(self) -> Batch:
         """One frame of every scene as the `Batch` GraphVS reads (per-frame tensors are fresh copies: the frames of
         a TBPTT window stay valid while the environment moves on)."""
         L, lib, dev = _lib, self.lib, self.dev
-        cur_xy = project_norm(self.cur_wcT, self.points, self.scene_of).float()
-        frac = torch.rand(self.B, generator=self.gen, device=dev) * (self.missing[1] - self.missing[0]) + self.missing[0]
-        visible = (torch.rand(self.N, generator=self.gen, device=dev) >= frac[self.scene_of]).to(torch.uint8)
+        cur_xy = project_norm(self.cur_wcT, self.points, self.scene_of)
+        cur_xy, visible_b, mismatch, wPo = self._visibility(cur_xy)
+        cur_xy = cur_xy.float()
+        visible = visible_b.to(torch.uint8)
         L.check(lib.cns_graph_mask(L.ptr(self.belong), L.ptr(self.member_order), L.ptr(self.cluster_size),
                                    L.ptr(self.cluster_graph_ptr), L.ptr(visible), self.N, self.Cn, self.B,
                                    L.ptr(self.e01_j), L.ptr(self.e01_i), L.ptr(self.e11), self.e11.shape[1],
                                    L.ptr(self.cmask), L.ptr(self.counts), L.ptr(self.ws), self.ws.numel(), L.stream_ptr(dev)),
                 "cns_graph_mask")
         n01, n11 = self.counts.tolist()                     # the only device -> host read of the step (16 bytes)
-        vel = pbvs_straight(self.cur_wcT, self.tar_wcT).float()
-        vel_si = vel.clone()
-        vel_si[:, :3] /= (self.tpo[:, None] + 1e-7)
+        if self.aug:
+            from .sim_aug import supervisor_vel
+            vel64, tpo, vel_si64 = supervisor_vel(self.supervisor, self.cur_wcT, self.tar_wcT, wPo)
+            self.gt_vel = vel64
+            vel, vel_si, self.tpo = vel64.float(), vel_si64.float(), tpo.float()
+        else:
+            vel64 = pbvs_straight(self.cur_wcT, self.tar_wcT)
+            self.gt_vel = vel64
+            vel = vel64.float()
+            vel_si = vel.clone()
+            vel_si[:, :3] /= (self.tpo[:, None] + 1e-7)
         data = {
             "x_cur": cur_xy, "pos_cur": cur_xy, "x_tar": self.x_tar, "pos_tar": self.x_tar,
             "l0_to_l1_edge_index_j_cur": self.e01_j[:n01].clone(), "l0_to_l1_edge_index_i_cur": self.e01_i[:n01].clone(),
             "l1_dense_edge_index_cur": self.e11[:, :n11].clone(), "l1_dense_edge_index_tar": self.l1_tar,
-            "cluster_mask": self.cmask[:self.Cn].clone().bool(), "node_mask": visible.bool(),
+            "cluster_mask": self.cmask[:self.Cn].clone().bool(), "node_mask": visible_b,
             "cluster_centers_index": self.centers, "belong_cluster_index": self.belong,
             "num_clusters": self.num_clusters, "tPo_norm": self.tpo, "batch": self.node_graph,
-            "new_scene": self.fresh.clone(), "vel": vel, "vel_si": vel_si,
+            "new_scene": self.fresh.clone(), "vel": vel, "vel_si": vel_si, "mismatch_mask": mismatch,
             "l1_complete": True, "max_clusters_per_graph": self.max_clusters,
         }
         self.fresh.zero_()
         return Batch(**data)
 
-    def feedback(self, vel: torch.Tensor):
-        """Apply camera velocities (B,6) for one 50 Hz step; scenes that converged (< 1 deg, < 2 mm), timed out or
-        left the workspace restart from a new initial pose."""
-        self.cur_wcT = integrate(self.cur_wcT, vel.to(self.dev, torch.float64))
-        self.steps += 1
+    # -- the reference's re-initialisation tests (sim/environment.py:151-203) -----------------------------------
+    def abnormal_pose(self) -> torch.Tensor:
+        pos = self.cur_wcT[:, :3, 3]
+        from .sim_aug import segment_mean
+        wPo = segment_mean(self.points, self.scene_of, self.B)
+        cur_cwT = se3_inv(self.cur_wcT)
+        cPo_z = (cur_cwT[:, 2, :3] * wPo).sum(-1) + cur_cwT[:, 2, 3]
+        low = pos[:, 2] < 0.5 * math.sin(30) * 0.5          # sic: environment.py:163 feeds degrees to np.sin
+        return ~torch.isfinite(self.cur_wcT).all(-1).all(-1) | low | (self.cur_wcT[:, 2, 2] > -0.1) | \
+            (pos.norm(dim=-1) > 0.9 * 2) | (cPo_z < 0)
+
+    def need_reinit(self) -> torch.Tensor:
         ang, mm = pose_error(self.cur_wcT, self.tar_wcT)
-        lost = ~torch.isfinite(self.cur_wcT).all(-1).all(-1) | (self.cur_wcT[:, :3, 3].norm(dim=-1) > 1.8) | \
-            (self.cur_wcT[:, 2, 2] > -0.1)
-        done = ((ang < 1.0) & (mm < 2.0)) | (self.steps > self.max_steps) | lost
-        if bool(done.any()):
-            idx = torch.nonzero(done).flatten()
+        return ((ang < 1.0) & (mm < 2.0)) | (self.steps > self.max_steps) | self.abnormal_pose()
+
+    def reinit_all(self):
+        self.reinit_all_count += 1
+        self._build(self._new_scenes())
+
+    def feedback(self, vel: torch.Tensor):
+        """Apply camera velocities (B,6) for one 50 Hz step.  Scenes in an abnormal pose are driven by the supervisor's
+        velocity instead (DataLoader.feedback, dataset.py:211-218).  Then re-initialisation by the `reinit` rule."""
+        vel = vel.to(self.dev, torch.float64)
+        if self.aug:
+            vel = torch.where(self.abnormal_pose()[:, None], self.gt_vel, vel)
+        self.cur_wcT = integrate(self.cur_wcT, vel)
+        self.steps += 1
+        self.calls += 1
+        need = self.need_reinit()
+        if self.reinit == "all":
+            if float(need.double().mean()) > 0.5:
+                self.reinit_all()
+            return
+        if bool(need.any()):
+            idx = torch.nonzero(need).flatten()
             self.cur_wcT[idx] = self._sample_initial_pose(idx.numel())
             self.steps[idx] = 0
             self.fresh[idx] = True
-        self.calls += 1
+            if self.aug:                      # a restarted scene gets a fresh drop-out process (dataset.py:79-83)
+                from . import sim_aug
+                new = sim_aug.BatchedObservationSampler(self.x_tar.double(), self.scene_of, self.B, self._tar_med, 5.0, self.gen)
+                sc, pt = need, need[self.scene_of]
+                s = self.sampler
+                for name in ("state", "last_time", "tau_total", "no_event_rval"):
+                    setattr(s, name, torch.where(pt, getattr(new, name), getattr(s, name)))
+                s.center = torch.where(sc[:, None], new.center, s.center)
+                s.dpose_norm_accum = torch.where(sc, new.dpose_norm_accum, s.dpose_norm_accum)
+                for name in ("offset", "g0", "g1"):
+                    setattr(s.perlin, name, torch.where(sc[:, None, None], getattr(new.perlin, name), getattr(s.perlin, name)))
+                s.perlin.prev_floor = torch.where(sc[:, None, None], new.perlin.prev_floor, s.perlin.prev_floor)
+                if s.prev_wcT is not None:
+                    s.prev_wcT = torch.where(sc[:, None, None], self.cur_wcT, s.prev_wcT)
+                self.mismatcher.reset(idx)
         if self.refresh_every and self.calls % self.refresh_every == 0:
-            self._build([synth.Scene(self.rng, int(self.rng.integers(4, self.max_points + 1))) for _ in range(self.B)])
+            self._build(self._new_scenes())
 
     def _sample_initial_pose(self, n: int) -> torch.Tensor:
         """Camera on a spherical shell looking at the origin with bounded roll / pitch / yaw perturbation

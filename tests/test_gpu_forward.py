@@ -493,3 +493,70 @@ def test_second_device_in_the_same_process(state_dict):
     for k, (a, b) in enumerate(zip(*outs)):
         assert torch.isfinite(b).all(), k
         assert torch.equal(a, b), (k, float((a - b).abs().max()), float(a.abs().max()))
+
+
+@pytest.mark.parametrize("long_seq", [False, True])
+def test_device_scene_batch_reference_augmentations(net, long_seq):
+    """DeviceSceneBatch(aug=True): the reference's training distribution on the device.  Invariants of
+    sim/dataset.py:88-141 / dataset_long.py:81-140 per frame, graph tensors bit-exact with the host generator for the
+    same visibility, labels equal to the reference-checked batched supervisors, and the loaders' "re-initialise all
+    scenes once more than half need it" rule."""
+    from cns_b200 import sim_aug
+    from cns_b200.sim_device import DeviceSceneBatch
+    env = DeviceSceneBatch(12, np.random.default_rng(23), "cuda:0", max_points=300, aug=True, long_seq=long_seq, reinit="all",
+                           supervisor="pbvs_hybrid" if long_seq else "pbvs_straight", discard=True)
+    n = env.n_nodes.cpu().numpy()
+    scene_of = env.scene_of.cpu().numpy()
+    removed_seen = mism_seen = 0
+    for step in range(6):
+        poses = env.cur_wcT.clone()
+        d = env.observe()
+        vis = d.node_mask.cpu().numpy()
+        mism = d.mismatch_mask.cpu().numpy()
+        xy = d.x_cur.cpu().numpy()
+        clean = synth_project(env, poses)
+        frames, o = [], 0
+        for k, s in enumerate(env.scenes):
+            m = n[k]
+            v, mm = vis[o:o + m], mism[o:o + m]
+            assert (~v).sum() < max(0.8 * m, 1)                                   # the 80 % cap
+            assert mm.sum() == (int(m * 0.1) if m >= 10 else 0)
+            if m < 10:
+                assert v.all()
+            assert not xy[o:o + m][~v].any()                                      # removed keypoints are zeroed
+            ok = v & ~mm
+            jit = 0.0005 if long_seq else 0.002
+            assert np.abs(xy[o:o + m][ok] - clean[o:o + m][ok]).max() <= jit + 1e-6   # jitter only
+            missing = np.nonzero(~v)[0]
+            f = s.generator.get_data(xy[o:o + m], missing_node_indices=missing if len(missing) else None)
+            frames.append(f)
+            removed_seen += (~v).sum(); mism_seen += mm.sum()
+            o += m
+        ref = Batch.from_data_list(frames)
+        for key in ("l0_to_l1_edge_index_j_cur", "l0_to_l1_edge_index_i_cur", "l1_dense_edge_index_cur", "cluster_mask"):
+            assert torch.equal(d[key].cpu(), ref[key]), key
+        # labels: supervisor on the visible keypoints' centre (N < 64) - the batched functions are checked against the
+        # reference in tests/test_sim_aug_cpu.py
+        small = torch.from_numpy(n < 64).to("cuda:0")
+        v_t = d.node_mask
+        wPo = sim_aug.segment_mean(env.points[v_t], env.scene_of[v_t], env.B)
+        vel, tpo, vel_si = sim_aug.supervisor_vel(env.supervisor, poses, env.tar_wcT, wPo)
+        assert float((d.vel - vel.float())[small].abs().max()) < 1e-6 and float((d.tPo_norm - tpo.float())[small].abs().max()) < 1e-6
+        assert float((d.vel_si[:, :3] * (d.tPo_norm[:, None] + 1e-7) - d.vel[:, :3]).abs().max()) < 1e-5
+        with torch.no_grad():
+            pred = net(d, None, check=True)
+        assert torch.isfinite(pred.vel).all()
+        env.feedback(d.vel * 2)
+    assert removed_seen > 0 and mism_seen > 0
+    # more than half of the scenes past their step budget: everything is re-initialised together, with new geometry
+    before = env.points.clone()
+    env.steps[:8] = env.max_steps + 1
+    env.feedback(torch.zeros(env.B, 6, device="cuda:0"))
+    assert env.reinit_all_count == 1 and bool(env.fresh.all()) and int(env.steps.max()) == 0
+    assert env.points.shape != before.shape or not torch.equal(env.points, before)
+    assert bool(env.observe().new_scene.all())
+
+
+def synth_project(env, poses):
+    from cns_b200.sim_device import project_norm
+    return project_norm(poses, env.points, env.scene_of).float().cpu().numpy()

@@ -46,7 +46,13 @@ def get_args():
     ap.add_argument("--device-env", action="store_true",
                     help="keep the closed-loop scenes on the GPU (cns_b200.sim_device.DeviceSceneBatch): batched projection, "
                          "supervisor, pose integration and per-frame graph masking instead of B python scenes per step")
-    ap.add_argument("--refresh-every", type=int, default=400, help="--device-env: new scene geometry every this many frames")
+    ap.add_argument("--refresh-every", type=int, default=0, help="--device-env --reinit scene: new scene geometry every this many frames")
+    ap.add_argument("--no-aug", dest="aug", action="store_false", default=True,
+                    help="--device-env: plain scenes (uniform drop-out, whole-scene tPo_norm) instead of the reference's "
+                         "training augmentations (mismatch, jitter, area-shift drop-out; sim/dataset.py:88-141)")
+    ap.add_argument("--reinit", choices=["all", "scene"], default="all",
+                    help="--device-env: 'all' = the reference's loaders (every scene re-initialised together once more than "
+                         "half need it, sim/dataset.py:242-246), 'scene' = scenes restart one by one")
     return ap.parse_args()
 
 
@@ -112,8 +118,11 @@ def main():
             pass
     if args.device_env:
         from cns_b200.sim_device import DeviceSceneBatch
+        # short sequences: straight-line PBVS supervisor (sim/dataset.py:33); long: the hybrid law, rotating mismatches and
+        # the smaller jitter of sim/dataset_long.py:21,81-97
         envs = DeviceSceneBatch(args.batch_size, np.random.default_rng(args.seed + rank), dev, args.max_points,
-                                refresh_every=args.refresh_every)
+                                refresh_every=args.refresh_every, aug=args.aug, reinit=args.reinit, long_seq=args.long,
+                                supervisor="pbvs_hybrid" if (args.long and args.aug) else "pbvs_straight")
     else:
         envs = SceneBatch(args.batch_size, np.random.default_rng(args.seed + rank), args.max_points)
     window = args.long_steps if args.long else 8
