@@ -201,14 +201,17 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
         const uint32_t d0 = tmem_base + (uint32_t)((s * 2 + 0) * TN);
         const uint32_t d1 = tmem_base + (uint32_t)((s * 2 + 1) * TN);
         if (round == 0) {
+          // everything that reads the x tiles first, commit after U: the epilogue may then overwrite the x tiles with u
+          // while V's hp half (hp tiles only) still runs; the round-C commit covers it
+          gemm3_kmajor(d1, 2, xh_lo, xl_lo, 0);   // V  = x  lin^T
           gemm3_kmajor(d0, 1, xh_lo, xl_lo, 0);   // U  = x  (-(A0 lin_src))^T
           gemm3_kmajor(d0, 3, ph_lo, pl_lo, 1);   //    + hp (A0 pos_nn.1)^T
-          gemm3_kmajor(d1, 2, xh_lo, xl_lo, 0);   // V  = x  lin^T
-          gemm3_kmajor(d1, 0, ph_lo, pl_lo, 1);   //    + hp pos_nn.1^T
+          umma_commit(done);
+          gemm3_kmajor(d1, 0, ph_lo, pl_lo, 1);   // V += hp pos_nn.1^T
         } else {
           gemm3_mnmajor(d0, xh_lo, xl_lo);        // L = u attn_nn.1^T   (u lives in the x tiles, [channel][edge])
+          umma_commit(done);
         }
-        umma_commit(done);
       }
       __syncwarp();
     }

@@ -201,14 +201,18 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
           const uint32_t d0 = tmem_base + (uint32_t)((s * 2 + 0) * TN);
           const uint32_t d1 = tmem_base + (uint32_t)((s * 2 + 1) * TN);
           if (round == 0) {
+            // The epilogue needs U complete and buffer 0 (x) free: everything that reads buffer 0 goes first and the
+            // commit follows U.  V's hp half only reads buffer 1: it runs behind the commit, under the epilogue, and
+            // is covered by the round-C commit (a commit tracks every earlier MMA of the issuing thread).
+            gemm_kmajor(d1, 2, b0, 0);   // V  = x  lin^T
             gemm_kmajor(d0, 1, b0, 0);   // U  = x  (-(A0 lin_src))^T
             gemm_kmajor(d0, 3, b1, 1);   //    + hp (A0 pos_nn.1)^T
-            gemm_kmajor(d1, 2, b0, 0);   // V  = x  lin^T
-            gemm_kmajor(d1, 0, b1, 1);   //    + hp pos_nn.1^T
+            umma_commit(done);
+            gemm_kmajor(d1, 0, b1, 1);   // V += hp pos_nn.1^T
           } else {
             gemm_mnmajor(d0, 4, b0);     // L = u attn_nn.1^T     (u lives in buffer 0, [channel][edge])
+            umma_commit(done);
           }
-          umma_commit(done);
         }
         __syncwarp();
       }
@@ -412,11 +416,9 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
       {
         float adb = 0.f;
         int nseg = 0;
-#pragma unroll 1
-        for (int cg = 0; cg < TN / 8; ++cg) {      // 8 edges per trip: one 16-byte chunk of this thread's row
-          float acc[8];
-          tmem_ld8(t0 + cg * 8, acc);
-          tmem_ld_wait();
+        // 8 edges per group = one 16-byte chunk of this thread's row.  The TMEM load of group g+1 is issued before
+        // group g is processed (two register buffers), so only the first load of a phase is exposed.
+        auto epi_group = [&](const float (&acc)[8], int cg) {
           const uint32_t m8 = (seg_mask[(TN > 32) ? (cg >> 2) : 0] >> ((cg & 3) * 8)) & 0xffu;
           uint32_t pk[4];
           if (__builtin_expect(m8 == 0, 1)) {
@@ -446,6 +448,15 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
             }
           }
           *reinterpret_cast<uint4*>(u_row + (((uint32_t)cg ^ u_xor) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        };
+        // (a two-buffer software prefetch of the next group's TMEM load was measured: no gain, the doubled loop bodies
+        // cost as much in instruction-cache misses as the exposed load latency they hide)
+#pragma unroll 1
+        for (int cg = 0; cg < TN / 8; ++cg) {
+          float acc[8];
+          tmem_ld8(t0 + cg * 8, acc);
+          tmem_ld_wait();
+          epi_group(acc, cg);
         }
       }
       publish_and_issue(1);
@@ -472,17 +483,22 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         };
         // edge 0 of a tile opens a new run only if its cluster differs from the carried one
         const uint32_t first_bit = (ci[0] != run_seg) ? 1u : 0u;
-#pragma unroll 1
-        for (int cg = 0; cg < TN / 8; ++cg) {
-          float lg[8], vv[8];
-          tmem_ld8(t0 + cg * 8, lg);
-          tmem_ld8(t1 + cg * 8, vv);
-          tmem_ld_wait();
+        auto sm_group = [&](const float (&lg)[8], const float (&vv)[8], int cg) {
           uint32_t m8 = (seg_mask[(TN > 32) ? (cg >> 2) : 0] >> ((cg & 3) * 8)) & 0xffu;
           if (cg == 0) m8 = (m8 & ~1u) | first_bit;
           if (__builtin_expect(m8 == 0, 1)) {
+            // no segment start among these 8 edges: one rescale for the group (to the group maximum), then
+            // sub / ex2 / add / fma per element
+            float gm = fmaxf(fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3])), fmaxf(fmaxf(lg[4], lg[5]), fmaxf(lg[6], lg[7])));
+            gm = fmaxf(gm, run_m);
+            const float sc = ex2_approx(run_m - gm);
+            run_s *= sc; run_a *= sc; run_m = gm;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) update(lg[q], vv[q]);
+            for (int q = 0; q < 8; ++q) {
+              const float e = ex2_approx(lg[q] - gm);
+              run_s += e;
+              run_a = fmaf(e, vv[q], run_a);
+            }
           } else {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -493,6 +509,14 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
               update(lg[q], vv[q]);
             }
           }
+        };
+#pragma unroll 1
+        for (int cg = 0; cg < TN / 8; ++cg) {
+          float lg[8], vv[8];
+          tmem_ld8(t0 + cg * 8, lg);
+          tmem_ld8(t1 + cg * 8, vv);
+          tmem_ld_wait();
+          sm_group(lg, vv, cg);
         }
         if (g + 1 >= t_end && run_seg >= 0) { flush_run(run_whole && chunk_whole_end); run_seg = -1; }   // chunk end
       }

@@ -8,7 +8,7 @@ import cns_oracle
 from cns_b200 import Batch, ckpt, synth
 print("imports ok", flush=True)
 sd = ckpt.read_state_dict(os.path.join(ROOT, "checkpoints", "cns_state_dict.pth"))
-net = ckpt.load_model(os.path.join(ROOT, "checkpoints", "cns.pth"), "cuda:0")
+net = ckpt.load_model(os.path.join(ROOT, "checkpoints", "cns.pth"), "cuda:0", precision=os.environ.get("CNS_PROBE_PRECISION", "fp32"))
 print("model ok", flush=True)
 h = net._handle(torch.device("cuda:0"))
 torch.cuda.synchronize()
