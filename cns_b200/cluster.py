@@ -70,7 +70,12 @@ def _labels_from_exemplars(S: np.ndarray, E: np.ndarray):
 
 
 def affinity_propagation_device(point_sets: Sequence[np.ndarray], damping=0.9, max_iter=200, convergence_iter=15,
-                                device="cuda:0"):
+                                device=None):
+    with torch.cuda.device(_resolve_device(device)):
+        return _affinity_propagation_device(point_sets, damping, max_iter, convergence_iter, _resolve_device(device))
+
+
+def _affinity_propagation_device(point_sets, damping, max_iter, convergence_iter, device):
     """Labels (one int array per point set) identical to
     `AffinityPropagation(damping=damping).fit_predict(X)` called on the sets in order."""
     lib = _lib.load()
@@ -110,7 +115,7 @@ def affinity_propagation_device(point_sets: Sequence[np.ndarray], damping=0.9, m
     return out
 
 
-def cluster_points_device(points, device="cuda:0"):
+def cluster_points_device(points, device=None):
     """Drop-in for `cluster_points` (graph_gen.py:104-113) with the AP iterations on the GPU."""
     yhat = affinity_propagation_device([points], device=device)[0]
     ids, counts = np.unique(yhat, return_counts=True)
@@ -127,8 +132,22 @@ class DeviceLayout(object):
     __slots__ = ("labels", "cluster_size", "centers", "member_order", "n_iter", "converged", "method")
 
 
+def _resolve_device(device):
+    """None -> the calling thread's current CUDA device (one process per GPU: every rank clusters on its own)."""
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    dev = torch.device(device)
+    return dev if dev.index is not None else torch.device("cuda", torch.cuda.current_device())
+
+
 def build_graphs_device(point_sets: Sequence[np.ndarray], damping=0.9, max_iter=200, convergence_iter=15,
-                        device="cuda:0", return_similarity=False) -> List[DeviceLayout]:
+                        device=None, return_similarity=False) -> List[DeviceLayout]:
+    # the library launches on the CURRENT device: make `device` current for the duration of the call
+    with torch.cuda.device(_resolve_device(device)):
+        return _build_graphs_device(point_sets, damping, max_iter, convergence_iter, _resolve_device(device), return_similarity)
+
+
+def _build_graphs_device(point_sets, damping, max_iter, convergence_iter, device, return_similarity):
     """Clustering + layout of every point set (each with more than 16 points: smaller sets never reach the
     clustering in the reference, graph_gen.py:137-144) in ONE batch of device calls.  Consumes numpy's global
     RandomState like the sequential host construction (one (n, n) standard-normal draw per set, in order), provided

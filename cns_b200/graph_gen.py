@@ -95,19 +95,21 @@ def _segment_median(values, order_by_label, starts, sizes):
     return med
 
 
-def label_nearest_exemplar(points, exemplar_indices, device="cuda:0") -> np.ndarray:
+def label_nearest_exemplar(points, exemplar_indices, device=None) -> np.ndarray:
     """1-NN keypoint -> exemplar assignment on the GPU (`cns_label_nearest`): the final labelling step
     of sklearn's AffinityPropagation (argmax_k -||x - e_k||^2, first maximum wins), in fp64."""
-    import ctypes as C  # noqa: F401
     from . import _lib
+    from .cluster import _resolve_device
     lib = _lib.load()
-    pts = torch.as_tensor(np.ascontiguousarray(points, dtype=np.float64), device=device)
-    ex = pts[torch.as_tensor(np.asarray(exemplar_indices, dtype=np.int64), device=device)].contiguous()
-    xptr = torch.tensor([0, ex.shape[0]], dtype=torch.int64, device=device)
-    labels = torch.empty(pts.shape[0], dtype=torch.int32, device=device)
-    _lib.check(lib.cns_label_nearest(_lib.ptr(pts), None, pts.shape[0], _lib.ptr(ex), _lib.ptr(xptr),
-                                     _lib.ptr(labels), _lib.stream_ptr(torch.device(device))), "cns_label_nearest")
-    return labels.cpu().numpy().astype(np.int64)
+    device = _resolve_device(device)
+    with torch.cuda.device(device):
+        pts = torch.as_tensor(np.ascontiguousarray(points, dtype=np.float64), device=device)
+        ex = pts[torch.as_tensor(np.asarray(exemplar_indices, dtype=np.int64), device=device)].contiguous()
+        xptr = torch.tensor([0, ex.shape[0]], dtype=torch.int64, device=device)
+        labels = torch.empty(pts.shape[0], dtype=torch.int32, device=device)
+        _lib.check(lib.cns_label_nearest(_lib.ptr(pts), None, pts.shape[0], _lib.ptr(ex), _lib.ptr(xptr),
+                                         _lib.ptr(labels), _lib.stream_ptr(device)), "cns_label_nearest")
+        return labels.cpu().numpy().astype(np.int64)
 
 
 def _cuda_present() -> bool:
@@ -124,7 +126,7 @@ class GraphGenerator(object):
     #   "host"  : scikit-learn + numpy on the CPU exactly like the reference.
     # None (default) = "device" whenever a CUDA device is present.
     CLUSTER_BACKEND = None
-    CLUSTER_DEVICE = "cuda:0"
+    CLUSTER_DEVICE = None         # None = the current CUDA device of the calling process / thread
 
     @classmethod
     def backend(cls) -> str:
@@ -142,7 +144,7 @@ class GraphGenerator(object):
         return [cls(p, layout=layouts.get(k)) for k, p in enumerate(sets)]
 
     @classmethod
-    def from_exemplars(cls, target_points, exemplar_indices, device="cuda:0"):
+    def from_exemplars(cls, target_points, exemplar_indices, device=None):
         """Graph whose clusters are the Voronoi cells of the given exemplar keypoints (labels computed
         on the device)."""
         return cls(target_points, labels=label_nearest_exemplar(target_points, exemplar_indices, device))

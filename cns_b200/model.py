@@ -151,6 +151,7 @@ class GraphVS(nn.Module):
         self._handles = {}       # device index -> (_lib.Handle, weight version)
         self._workspaces = {}    # device index -> uint8 tensor
         self._names = None
+        self._param_cache = None
 
     # ------------------------------------------------------------------ reference API
     def init_hidden(self, size0):
@@ -194,14 +195,25 @@ class GraphVS(nn.Module):
                 h.set_precision(precision)
 
     def _ordered_params(self):
-        if self._names is None:
-            self._names = _lib.param_names()
-        sd = dict(self.named_parameters())
-        return [sd[n] for n in self._names]
+        """The 43 parameters in the library's canonical order.  Cached: `nn.Module` swaps Parameter objects only in
+        `_apply` (.to / .cuda / .float ...), which drops the cache; load_state_dict and optimizers write in place."""
+        if self._param_cache is None:
+            if self._names is None:
+                self._names = _lib.param_names()
+            sd = dict(self.named_parameters())
+            self._param_cache = [sd[n] for n in self._names]
+        return self._param_cache
+
+    def _apply(self, fn, *args, **kwargs):
+        self._param_cache = None
+        out = super()._apply(fn, *args, **kwargs)
+        self._param_cache = None
+        return out
 
     def _handle(self, device: torch.device, training: bool = False) -> "_lib.Handle":
         params = self._ordered_params()
-        version = tuple((p.data_ptr(), p._version) for p in params)
+        # in-place writes bump _version, re-allocation changes the storage pointer: one pass over 43 tensors (~8 us)
+        version = (sum([p._version for p in params]), params[0].data_ptr(), params[-1].data_ptr(), id(params))
         idx = device.index if device.index is not None else torch.cuda.current_device()
         key = (idx, "train") if training else idx       # training always uses the fp32 kernels
         ent = self._handles.get(key)
