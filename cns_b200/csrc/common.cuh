@@ -88,6 +88,10 @@ struct Packed {
   unsigned char* tc_c0[2]; unsigned char* tc_c0_fc[2]; unsigned char* tc_g[2]; unsigned char* tc_k[2];
   unsigned char* tc_c1[2]; unsigned char* tc_c1_fc[2]; unsigned char* tc_out[2];
   unsigned char* tc_node_base;
+  // bf16 (hi, lo) split images of the same seven matrices for the fp32 mode (gemm_tc_split.cu)
+  unsigned char* tc2_c0; unsigned char* tc2_c0_fc; unsigned char* tc2_g; unsigned char* tc2_k;
+  unsigned char* tc2_c1; unsigned char* tc2_c1_fc; unsigned char* tc2_out;
+  unsigned char* tc2_base;
 };
 
 }  // namespace cns

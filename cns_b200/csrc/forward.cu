@@ -155,6 +155,8 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   // mantissa on BOTH the edge-level and the recurrent cluster-level layers the hidden state drifts past
   // the 2e-2 budget after a few frames, so bf16 mode keeps them in fp32 (measured).
   const bool tc = h->precision == CNS_PREC_F16;
+  // fp32 mode: the same GEMMs with bf16 (hi, lo) operand splits (three tensor-core products, ~1e-5 of fp64)
+  const bool tc2 = h->precision == CNS_PREC_FP32 && !h->no_split_encoder;
   const int tci = (h->precision == CNS_PREC_BF16) ? 0 : 1;
   // whole-graph row tiles: the three backbone blocks as one kernel (backbone_fused.cu)
   const bool fused = tc && dense_cur && dense_tar && b->max_clusters_per_graph > 0 && b->max_clusters_per_graph <= 128 &&
@@ -219,26 +221,26 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   ef.piece_e = (h->precision == CNS_PREC_FP32) ? (h->no_split_encoder ? ENC_PIECE_E : split_piece_edges(b->n_e01, h)) : tc_piece_edges(b->n_e01, h); ef.clu_rowptr = f.clu_rowptr; ef.partial = f.partial;
   ef.clu_feat = f.clu_feat; ef.out_t = pk.out_t; ef.b_out = h->P(P_OUT_B); ef.cluster_mask = b->cluster_mask;
   ef.x_clu = f.x_clu;
-  ef.cat_out = (tc && !fused) ? f.pq : nullptr;       // (C,256) scratch; pq is free until the first [P|Q] projection
+  ef.cat_out = ((tc && !fused) || tc2) ? f.pq : nullptr;       // (C,256) scratch; pq is free until the first [P|Q] projection
   ef.fix_only = fused ? 1 : 0;
   RUN(enc_finish(ef, s));
-  if (tc && !fused) {
+  if ((tc && !fused) || tc2) {
     GemmTcArgs ga{};
-    ga.m = C; ga.k1 = 2 * H; ga.k2 = 0; ga.n_out = H; ga.x1 = f.pq; ga.w_img = pk.tc_out[tci];
+    ga.m = C; ga.k1 = 2 * H; ga.k2 = 0; ga.n_out = H; ga.x1 = f.pq; ga.w_img = tc2 ? pk.tc2_out : pk.tc_out[tci];
     ga.bias = h->P(P_OUT_B); ga.row_mask = b->cluster_mask; ga.relu = 1; ga.y = f.x_clu;
-    RUN(gemm_tc(ga, tci == 0, s));
+    if (tc2) { RUN(gemm_tc_split(ga, s)); } else { RUN(gemm_tc(ga, tci == 0, s)); }
   }
 
   // ---- backbone ---------------------------------------------------------------------------
   if (fork_pre) CNS_CUDA_CHECK(cudaStreamWaitEvent(s, h->side_join2, 0));
   auto pq_linear = [&](const float* x1, const float* x2, const float* wt, const float* wp, const float* bias,
-                       int n_out, unsigned char* const* img, int k_img) {
-    if (tc) {
+                       int n_out, unsigned char* const* img, int k_img, const unsigned char* img2) {
+    if (tc || tc2) {
       GemmTcArgs ga{};
-      ga.m = C; ga.k1 = H; ga.k2 = x2 ? H : 0; ga.n_out = n_out; ga.x1 = x1; ga.x2 = x2; ga.w_img = img[tci];
+      ga.m = C; ga.k1 = H; ga.k2 = x2 ? H : 0; ga.n_out = n_out; ga.x1 = x1; ga.x2 = x2; ga.w_img = tc2 ? img2 : img[tci];
       ga.k_img = k_img;
       ga.bias = bias; ga.pos = f.pos_clu; ga.wp = wp; ga.relu = 0; ga.y = f.pq;
-      return gemm_tc(ga, tci == 0, s);
+      return tc2 ? gemm_tc_split(ga, s) : gemm_tc(ga, tci == 0, s);
     }
     LinearArgs la{};
     la.m = C; la.k1 = H; la.k2 = x2 ? H : 0; la.n_out = n_out;
@@ -248,9 +250,10 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   };
   auto perconv = [&](const float* x, const float* wt, const float* wp, const float* bias, int bn_w, int bn_b,
                      int bn_ms, const float* fc_t, int fc_b, float* y, unsigned char* const* img,
-                     unsigned char* const* fc_img, float* conv, float* gnb, float* stats, int* arg) {
+                     unsigned char* const* fc_img, float* conv, float* gnb, float* stats, int* arg,
+                     const unsigned char* img2, const unsigned char* fc_img2) {
     int r;
-    if ((r = pq_linear(x, nullptr, wt, wp, bias, 2 * H, img, H)) != CNS_OK) return r;
+    if ((r = pq_linear(x, nullptr, wt, wp, bias, 2 * H, img, H, img2)) != CNS_OK) return r;
     if (dense_cur) {
       EdgeConvDenseArgs ed{};
       ed.n_graphs = B; ed.f_out = H; ed.mode = EC_PLAIN; ed.pq = f.pq; ed.graph_ptr = f.graph_ptr; ed.mask = b->cluster_mask;
@@ -266,11 +269,11 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     gn.mean_scale = h->P(bn_ms); gn.y = gnb; gn.stats = stats;
     if ((r = graphnorm_relu(gn, s)) != CNS_OK) return r;
     }
-    if (tc) {
+    if (tc || tc2) {
       GemmTcArgs ga{};
-      ga.m = C; ga.k1 = H; ga.k2 = 0; ga.n_out = H; ga.x1 = gnb; ga.w_img = fc_img[tci]; ga.bias = h->P(fc_b);
+      ga.m = C; ga.k1 = H; ga.k2 = 0; ga.n_out = H; ga.x1 = gnb; ga.w_img = tc2 ? fc_img2 : fc_img[tci]; ga.bias = h->P(fc_b);
       ga.residual = x; ga.relu = 1; ga.y = y;
-      return gemm_tc(ga, tci == 0, s);
+      return tc2 ? gemm_tc_split(ga, s) : gemm_tc(ga, tci == 0, s);
     }
     LinearArgs la{};
     la.m = C; la.k1 = H; la.k2 = 0; la.n_out = H; la.x1 = gnb; la.wt = fc_t; la.bias = h->P(fc_b);
@@ -292,10 +295,10 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     fa.hidden_out = hidden_out; fa.x2 = f.x2;
     RUN(backbone_fused(fa, tci == 0, s));
   } else {
-  RUN(perconv(f.x_clu, pk.c0_wt, pk.c0_wp, pk.c0_b, P_C0_BN_W, P_C0_BN_B, P_C0_BN_MS, pk.c0_fc_t, P_C0_FC_B, f.x1, pk.tc_c0, pk.tc_c0_fc, f.conv0, f.gn0, f.stats0, f.arg0));
+  RUN(perconv(f.x_clu, pk.c0_wt, pk.c0_wp, pk.c0_b, P_C0_BN_W, P_C0_BN_B, P_C0_BN_MS, pk.c0_fc_t, P_C0_FC_B, f.x1, pk.tc_c0, pk.tc_c0_fc, f.conv0, f.gn0, f.stats0, f.arg0, pk.tc2_c0, pk.tc2_c0_fc));
 
   // GRU gates on the TARGET cluster graph, candidate on the CURRENT one (graph_vs.py:246-249)
-  RUN(pq_linear(f.x1, hidden_in, pk.g_wt, pk.g_wp, pk.g_b, 4 * H, pk.tc_g, 2 * H));
+  RUN(pq_linear(f.x1, hidden_in, pk.g_wt, pk.g_wp, pk.g_b, 4 * H, pk.tc_g, 2 * H, pk.tc2_g));
   if (dense_tar) {
     EdgeConvDenseArgs ed{};
     ed.n_graphs = B; ed.f_out = 2 * H; ed.mode = EC_GATES; ed.pq = f.pq; ed.graph_ptr = f.graph_ptr; ed.mask = nullptr;
@@ -307,7 +310,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     ec.h = hidden_in; ec.hr = f.hr; ec.u = f.u; ec.argmax = f.argg; ec.act = f.g;
     RUN(edgeconv_max(ec, s));
   }
-  RUN(pq_linear(f.x1, hidden_in ? f.hr : nullptr, pk.k_wt, pk.k_wp, pk.k_b, 2 * H, pk.tc_k, 2 * H));
+  RUN(pq_linear(f.x1, hidden_in ? f.hr : nullptr, pk.k_wt, pk.k_wp, pk.k_b, 2 * H, pk.tc_k, 2 * H, pk.tc2_k));
   if (dense_cur) {
     EdgeConvDenseArgs ed{};
     ed.n_graphs = B; ed.f_out = H; ed.mode = EC_CANDIDATE; ed.pq = f.pq; ed.graph_ptr = f.graph_ptr; ed.mask = b->cluster_mask;
@@ -319,7 +322,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     ec.h = hidden_in; ec.u_in = f.u; ec.h_out = hidden_out; ec.argmax = f.argk; ec.act = f.ht;
     RUN(edgeconv_max(ec, s));
   }
-  RUN(perconv(hidden_out, pk.c1_wt, pk.c1_wp, pk.c1_b, P_C1_BN_W, P_C1_BN_B, P_C1_BN_MS, pk.c1_fc_t, P_C1_FC_B, f.x2, pk.tc_c1, pk.tc_c1_fc, f.conv1, f.gn1, f.stats1, f.arg1));
+  RUN(perconv(hidden_out, pk.c1_wt, pk.c1_wp, pk.c1_b, P_C1_BN_W, P_C1_BN_B, P_C1_BN_MS, pk.c1_fc_t, P_C1_FC_B, f.x2, pk.tc_c1, pk.tc_c1_fc, f.conv1, f.gn1, f.stats1, f.arg1, pk.tc2_c1, pk.tc2_c1_fc));
   }
 
   // ---- decoder ----------------------------------------------------------------------------

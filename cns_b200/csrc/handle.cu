@@ -195,6 +195,19 @@ int repack(cns_handle* h, cudaStream_t s) {
     }
     for (auto& it : items)
       if ((rc = gemm_tc_pack(it.wt, it.k, it.n, it.dst[0], it.dst[1], s)) != CNS_OK) return rc;
+    // (hi, lo) split images for the fp32 mode
+    unsigned char** split_dst[] = {&pk.tc2_c0, &pk.tc2_c0_fc, &pk.tc2_g, &pk.tc2_k, &pk.tc2_c1, &pk.tc2_c1_fc, &pk.tc2_out};
+    if (!pk.tc2_base) {
+      size_t total = 0;
+      for (auto& it : items) total += (size_t)it.k * it.n * 2 * 2;
+      CNS_CUDA_CHECK(cudaMalloc(&pk.tc2_base, total));
+      unsigned char* q = pk.tc2_base;
+      int i = 0;
+      for (auto& it : items) { *split_dst[i++] = q; q += (size_t)it.k * it.n * 2 * 2; }
+    }
+    int i = 0;
+    for (auto& it : items)
+      if ((rc = gemm_tc_split_pack(it.wt, it.k, it.n, *split_dst[i++], s)) != CNS_OK) return rc;
   }
   h->weights_loaded = true;
   ++h->weights_version;
@@ -278,6 +291,7 @@ int cns_destroy(cns_handle* h) {
   if (h->tc_w_img) cudaFree(h->tc_w_img);
   if (h->tc_w_split) cudaFree(h->tc_w_split);
   if (h->pk.tc_node_base) cudaFree(h->pk.tc_node_base);
+  if (h->pk.tc2_base) cudaFree(h->pk.tc2_base);
   if (h->servo_tcache) cns_target_cache_destroy(h->servo_tcache);
   free(h->servo_tkey);
   if (h->side_stream) { cudaStreamDestroy(h->side_stream); cudaEventDestroy(h->side_fork); cudaEventDestroy(h->side_join); cudaEventDestroy(h->side_join2); }

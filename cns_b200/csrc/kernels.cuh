@@ -110,6 +110,9 @@ struct GemmTcArgs {
 };
 int gemm_tc(const GemmTcArgs& a, bool bf16, cudaStream_t s);
 int gemm_tc_pack(const float* wt, int k_dim, int n_out, unsigned char* img_bf16, unsigned char* img_f16, cudaStream_t s);
+// the same GEMM at fp32 accuracy: bf16 (hi, lo) operand split, three products (gemm_tc_split.cu); w_img from gemm_tc_split_pack
+int gemm_tc_split(const GemmTcArgs& a, cudaStream_t s);
+int gemm_tc_split_pack(const float* wt, int k_dim, int n_out, unsigned char* img, cudaStream_t s);
 
 enum EdgeConvMode { EC_PLAIN = 0, EC_GATES = 1, EC_CANDIDATE = 2 };
 struct EdgeConvArgs {

@@ -147,7 +147,7 @@ def test_complete_graph_path_matches_general_path_and_is_verified(net):
         dev.l1_complete = False
         b = net(dev, hid, check=True)
     for x, y in zip(a, b):
-        assert rel(x, y) < 1e-6
+        assert rel(x, y) < 1e-5      # same arithmetic up to the fp32 rounding of GraphNorm statistics, seen through the (hi, lo) operand split
     # an edge list assigned after construction voids the hint by itself (custom edge augmentation): the forward
     # then takes the general CSR path and computes what the edge list says
     cut = batch.to("cuda:0")
