@@ -15,6 +15,11 @@
 // of attn_nn.1 live in tensor memory (A operand of TS-mode MMAs: used by 2 of the 3 products, no shared-memory
 // fetch), the other four lo slices stay in shared memory (128 KB).  TMEM: 128 accumulator columns (2 slots x
 // {U/L, V} x 32 edges) + 6 x 64 weight columns.  Activation tiles: 2 slots x {x_hi, x_lo, hp_hi, hp_lo} x 8 KB.
+//
+// That budget leaves room for only two MMA slots of N = 32, i.e. 8 warps if a slot were one 32-edge tile - too few to
+// hide the latencies of the SIMT phases.  So a slot's 32 MMA columns are TWO independent 16-edge sub-tiles, each
+// walked by its own 4 warps through its own contiguous chunk of the edge list (own running softmax state): 16 warps
+// per SM, the per-thread work between two MMA round trips halves, the MMA work per edge stays the same.
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "kernels.cuh"
@@ -24,8 +29,10 @@ namespace cns {
 
 namespace {
 
-constexpr int SP_TN = 32;                          // edges per tile (MMA N)
-constexpr int SP_SLOTS = 2;                        // tiles in flight per CTA
+constexpr int SP_TN = 32;                          // MMA N: edges per slot tile
+constexpr int SP_SUB = 2;                          // independent sub-tiles (edge streams) per slot
+constexpr int SP_TS = SP_TN / SP_SUB;              // 16 edges per sub-tile
+constexpr int SP_SLOTS = 2;                        // MMA slots per CTA
 constexpr int SP_W_BYTES = 128 * 128 * 2;          // one 16-bit slice of a weight matrix
 constexpr int SP_NW = 5;
 constexpr int SP_TMEM_SLICES = 6;                  // hi0..hi4, lo4
@@ -33,7 +40,7 @@ constexpr int SP_SMEM_SLICES = 4;                  // lo0..lo3
 constexpr int SP_ACT_TILE = SP_TN * 256;           // one [32 x 128] 16-bit operand tile
 constexpr int SP_ACT_BYTES = SP_SLOTS * 4 * SP_ACT_TILE;
 constexpr int SP_ACC_COLS = SP_SLOTS * 2 * SP_TN;  // 128
-constexpr size_t SP_SMEM_BYTES = SP_SMEM_SLICES * SP_W_BYTES + SP_ACT_BYTES + 256 + SP_SLOTS * 2 * SP_TN * sizeof(int) + 1024;
+constexpr size_t SP_SMEM_BYTES = SP_SMEM_SLICES * SP_W_BYTES + SP_ACT_BYTES + 256 + SP_SLOTS * 2 * SP_TN * sizeof(int) + 4096 + 1024;
 static_assert(SP_TMEM_SLICES * SP_W_BYTES <= SP_SMEM_SLICES * SP_W_BYTES + SP_ACT_BYTES, "staging area for the TMEM-bound slices");
 static_assert(SP_ACC_COLS + SP_TMEM_SLICES * 64 <= 512, "tensor memory budget");
 
@@ -74,9 +81,9 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
-__global__ void __launch_bounds__(128 * SP_SLOTS, 1)
+__global__ void __launch_bounds__(128 * SP_SUB * SP_SLOTS, 1)
 enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant__ SpSmallW sw) {
-  constexpr int TN = SP_TN, SLOTS = SP_SLOTS;
+  constexpr int TN = SP_TN, SLOTS = SP_SLOTS, TS = SP_TS;
   constexpr int U_ROW = TN * 2;                      // bytes per channel row of an MN-major u tile
   constexpr int NPRE = 4;
   constexpr uint32_t W_COL0 = SP_ACC_COLS;           // first weight column in tensor memory
@@ -87,7 +94,8 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
   unsigned char* tail = act_s + SP_ACT_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);                  // [0] weights landed, [1+s] MMAs of slot s done
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tail + 128);
-  int* ci_s = reinterpret_cast<int*>(tail + 256);                      // [SLOTS][2][TN]
+  int* ci_s = reinterpret_cast<int*>(tail + 256);                      // [SLOTS][SUB][2][TS] cluster id per edge, double-buffered
+  float4* sw_s = reinterpret_cast<float4*>(tail + 256 + SLOTS * 2 * TN * sizeof(int));   // first-layer weights [128][2]
 
   const EncEdgeArgs& p = args.e;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -107,19 +115,19 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
         bulk_g2s(smem_u32(w_s + j * SP_W_BYTES), args.w_img + (size_t)j * SP_W_BYTES, SP_W_BYTES, smem_u32(&bars[0]));
     }
   }
+  if (tid < 256) sw_s[tid] = sw.w[tid >> 1][tid & 1];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
   {
     // row o of a slice = TMEM lane o, k and k+1 share a 32-bit column.  A warp reaches the lane quarter warp % 4:
-    // warps 0-3 move slices 0..2, warps 4-7 slices 3..5.
+    // warp group g = warp / 4 moves slices g and g + 4.
     mbar_wait(smem_u32(&bars[0]), 0);
     const int o = tid & 127;
     const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + W_COL0;
-    const int j0 = (warp >> 2) * 3;
 #pragma unroll 1
-    for (int j = j0; j < j0 + 3; ++j) {
+    for (int j = (warp >> 2); j < SP_TMEM_SLICES; j += 4) {
 #pragma unroll 1
       for (int g = 0; g < 8; ++g) {
         const uint4 lo = *reinterpret_cast<const uint4*>(w_s + j * SP_W_BYTES + sw128_off(128, o, g * 16));
@@ -148,17 +156,18 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((128u >> 4) << 24);
   const uint32_t idesc_mn = idesc | (1u << 16);
 
-  const int s = warp >> 2;                       // slot
-  const int t = tid & 127;                       // thread in slot == output channel == TMEM lane
+  const int s = warp >> 3;                       // MMA slot
+  const int sub = (warp >> 2) & 1;               // sub-tile (edge stream) of the slot
+  const int t = tid & 127;                       // thread in sub-slot == output channel == TMEM lane
   const int wq = warp & 3;                       // TMEM lane quarter
   unsigned char* const xh = act_s + (s * 4 + 0) * SP_ACT_TILE;      // x hi  (round C: u hi)
   unsigned char* const xl = act_s + (s * 4 + 1) * SP_ACT_TILE;      // x lo  (round C: u lo)
   unsigned char* const ph = act_s + (s * 4 + 2) * SP_ACT_TILE;      // hp hi
   unsigned char* const pl = act_s + (s * 4 + 3) * SP_ACT_TILE;      // hp lo
-  int* const ci_base = ci_s + s * 2 * TN;
+  int* const ci_base = ci_s + (s * SP_SUB + sub) * 2 * TS;
   const uint32_t done = smem_u32(&bars[1 + s]);
-  const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((s * 2 + 0) * TN);
-  const uint32_t t1 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((s * 2 + 1) * TN);
+  const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((s * 2 + 0) * TN + sub * TS);
+  const uint32_t t1 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((s * 2 + 1) * TN + sub * TS);
   const float b_p1 = p.b_p1[t];
   uint32_t done_parity = 0;
   constexpr float LN2 = 0.6931471805599453f;
@@ -194,8 +203,8 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
   auto publish_and_issue = [&](int round) {
     tc_fence_before();
     fence_proxy_async();
-    named_bar(1 + s, 128);
-    if (wq == 0) {
+    named_bar(1 + s, 128 * SP_SUB);
+    if (wq == 0 && sub == 0) {
       if (elect_one()) {
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)((s * 2 + 0) * TN);
@@ -216,12 +225,13 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
       __syncwarp();
     }
   };
-  if (wq == 0) mbar_wait(smem_u32(&bars[0]), 1);     // the shared-memory lo slices landed (second phase of the barrier)
+  if (wq == 0 && sub == 0) mbar_wait(smem_u32(&bars[0]), 1);     // the shared-memory lo slices landed (second phase of the barrier)
 
-  const int pe = lane;                           // edge of this thread in the producer
-  const int kp = wq;                             // channel block [kp*32, kp*32 + 32)
-  const int n_chunks_side = ((int)gridDim.x * SLOTS) / 2;
-  const int chunk_q = (int)blockIdx.x * SLOTS + s;
+  const int pe = lane & (TS - 1);                // edge of this thread in the producer
+  const int kp = wq * 2 + (lane >> 4);           // channel block [kp*16, kp*16 + 16)
+  const int row = sub * TS + pe;                 // row of that edge in the slot's operand tiles
+  const int n_chunks_side = ((int)gridDim.x * SLOTS * SP_SUB) / 2;
+  const int chunk_q = ((int)blockIdx.x * SLOTS + s) * SP_SUB + sub;
   const int side = chunk_q / n_chunks_side;
   const int chunk = chunk_q - side * n_chunks_side;
   const int tpc = args.tiles_per_chunk;
@@ -234,7 +244,7 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
   auto fetch_index = [&](int g) {
     idx_c = -1; idx_j = 0;
     if (g < t_end) {
-      const int64_t e = (int64_t)g * TN + pe;
+      const int64_t e = (int64_t)g * TS + pe;
       if (e < p.n_e01) { idx_j = (int)p.ej[e]; idx_c = (int)p.ei[e]; }
     }
   };
@@ -257,7 +267,7 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
   fetch_index(t_begin + 1);
   fetch_coords();
   fetch_index(t_begin + 2);
-  named_bar(1 + s, 128);
+  named_bar(1 + s, 128 * SP_SUB);
 
   float run_m = 0.f, run_s = 0.f, run_a = 0.f;
   int run_seg = -1;
@@ -265,7 +275,7 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
   float* const part_side = p.partial + (size_t)side * p.n_slots * 3 * H;
   bool run_whole, chunk_whole_end;
   {
-    const int64_t ce0 = (int64_t)t_begin * TN, ce1 = min((int64_t)t_end * TN, p.n_e01);
+    const int64_t ce0 = (int64_t)t_begin * TS, ce1 = min((int64_t)max(t_end, t_begin) * TS, p.n_e01);
     run_whole = (ce0 == 0) || (ce0 < p.n_e01 && p.ei[ce0 - 1] != p.ei[ce0]);
     chunk_whole_end = (ce1 >= p.n_e01) || (ce1 > 0 && p.ei[ce1 - 1] != p.ei[ce1]);
   }
@@ -285,8 +295,8 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
   uint32_t seg_mask, seg_next;
   float aq[NPRE], aq_next[NPRE];
   auto seg_and_prefetch = [&](const int* ci, uint32_t& sm, float (&a)[NPRE]) {
-    const int cprev = (lane == 0) ? -2 : ci[lane - 1];
-    sm = __ballot_sync(0xffffffffu, ci[lane] != cprev);
+    const int cprev = (pe == 0) ? -2 : ci[pe - 1];
+    sm = __ballot_sync(0xffffffffu, ci[pe] != cprev) & ((1u << TS) - 1u);
     uint32_t m0 = sm;
 #pragma unroll
     for (int i = 0; i < NPRE; ++i) {
@@ -301,10 +311,11 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
   };
   seg_and_prefetch(ci_base, seg_mask, aq);
 
-  for (int it = 0;; ++it) {
+  // both sub-tiles of a slot share its barriers and MMAs: every stream runs the same number of tiles; tiles past the
+  // end of a stream are padding (cluster -1 everywhere: zero operands, a run that is never flushed)
+  for (int it = 0; it < tpc; ++it) {
     const int g = t_begin + it;
-    if (g >= t_end) break;
-    const int* const ci = ci_base + (it & 1) * TN;
+    const int* const ci = ci_base + (it & 1) * TS;
 
     // ---- producer: x -> (xh, xl), hp -> (ph, pl): fp32 first layers, split on the way out -------------------
     {
@@ -313,15 +324,15 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
       const float d0 = live ? c_pc.x - c_ps.x : 0.f, d1 = live ? c_pc.y - c_ps.y : 0.f;   // pos_i - pos_j
       const float d2 = live ? c_pc.x - c_pt.x : 0.f, d3 = live ? c_pc.y - c_pt.y : 0.f;
 #pragma unroll 1
-      for (int gq = 0; gq < TN / 8; ++gq) {
-        const int k0 = kp * TN + gq * 8;
+      for (int gq = 0; gq < TS / 8; ++gq) {
+        const int k0 = kp * TS + gq * 8;
         uint32_t xo[4], xt[4], ho[4], ht[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float xv[2], hv[2];
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
-            const float4 wa = sw.w[k0 + q * 2 + h2][0], wb = sw.w[k0 + q * 2 + h2][1];
+            const float4 wa = sw_s[(k0 + q * 2 + h2) * 2], wb = sw_s[(k0 + q * 2 + h2) * 2 + 1];
             const float x = fmaf(wa.y, f1, fmaf(wa.x, f0, wa.z));
             float hp = fmaf(wb.x, d0, wa.w);
             hp = fmaf(wb.y, d1, hp);
@@ -333,7 +344,7 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
           split2(xv[0], xv[1], xo[q], xt[q]);
           split2(hv[0], hv[1], ho[q], ht[q]);
         }
-        const uint32_t off = sw128_off(TN, pe, k0);
+        const uint32_t off = sw128_off(TN, row, k0);
         *reinterpret_cast<uint4*>(xh + off) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
         *reinterpret_cast<uint4*>(xl + off) = make_uint4(xt[0], xt[1], xt[2], xt[3]);
         *reinterpret_cast<uint4*>(ph + off) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
@@ -341,7 +352,7 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
       }
     }
     publish_and_issue(0);
-    if (kp == 0) ci_base[((it + 1) & 1) * TN + pe] = n_cid;
+    if (kp == 0) ci_base[((it + 1) & 1) * TS + pe] = n_cid;
 
     // ---- epilogue: u = relu(U + a'[cluster]) -> (u hi, u lo), MN-major rows of this thread's channel ---------
     mbar_wait(done, done_parity); done_parity ^= 1;
@@ -353,7 +364,7 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
       float adb = 0.f;
       int nseg = 0;
 #pragma unroll 1
-      for (int cg = 0; cg < TN / 8; ++cg) {
+      for (int cg = 0; cg < TS / 8; ++cg) {
         float acc[8];
         tmem_ld8(t0 + cg * 8, acc);
         tmem_ld_wait();
@@ -379,13 +390,13 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
           }
           split2(v[0], v[1], pk[q / 2], pt[q / 2]);
         }
-        const uint32_t off = u_off + (((uint32_t)cg ^ u_xor) << 4);
+        const uint32_t off = u_off + (((uint32_t)(sub * (TS / 8) + cg) ^ u_xor) << 4);
         *reinterpret_cast<uint4*>(xh + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(xl + off) = make_uint4(pt[0], pt[1], pt[2], pt[3]);
       }
     }
     publish_and_issue(1);
-    seg_and_prefetch(ci_base + ((it + 1) & 1) * TN, seg_next, aq_next);
+    seg_and_prefetch(ci_base + ((it + 1) & 1) * TS, seg_next, aq_next);
 
     // ---- final: per-channel online segment softmax of L weighting V (see encoder_tc.cu) ---------------------
     mbar_wait(done, done_parity); done_parity ^= 1;
@@ -402,7 +413,7 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
       };
       const uint32_t first_bit = (ci[0] != run_seg) ? 1u : 0u;
 #pragma unroll 1
-      for (int cg = 0; cg < TN / 8; ++cg) {
+      for (int cg = 0; cg < TS / 8; ++cg) {
         float lg[8], vv[8];
         tmem_ld8(t0 + cg * 8, lg);
         tmem_ld8(t1 + cg * 8, vv);
@@ -423,7 +434,7 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
           }
         }
       }
-      if (g + 1 >= t_end && run_seg >= 0) { flush_run(run_whole && chunk_whole_end); run_seg = -1; }
+      if (g + 1 >= t_end && run_seg >= 0) { flush_run(run_whole && chunk_whole_end); run_seg = -1; }   // (also true on padding tiles: nothing open)
     }
     seg_mask = seg_next;
 #pragma unroll
@@ -436,12 +447,16 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// grid size and 16-edge tiles per stream: grid * SLOTS * SUB streams, half of them per side; a stream (= softmax piece)
+// keeps at least two tiles (32 edges) whenever the input has that many, so the partial-slot table sized by the
+// forward (clusters + edges / 32 + 2 slots per side) always suffices
 void sp_chunking(int64_t n_e01, int sm_count, int* grid, int* tiles_per_chunk) {
-  const int n_tiles = ceil_div(n_e01, SP_TN);
+  const int n_tiles = ceil_div(n_e01, SP_TS);
+  const int streams_per_cta = SP_SLOTS * SP_SUB;
   int g = sm_count;
-  const int want = ceil_div(2 * (int64_t)n_tiles, SP_SLOTS);
+  const int want = (int)((2 * (int64_t)n_tiles) / (2 * streams_per_cta));      // CTAs that still get >= 2 tiles per stream
   if (g > want) g = want > 0 ? want : 1;
-  const int chunks_side = (g * SP_SLOTS) / 2;
+  const int chunks_side = (g * streams_per_cta) / 2;
   *grid = g;
   *tiles_per_chunk = ceil_div(n_tiles > 0 ? n_tiles : 1, chunks_side);
 }
@@ -451,7 +466,7 @@ void sp_chunking(int64_t n_e01, int sm_count, int* grid, int* tiles_per_chunk) {
 int split_piece_edges(int64_t n_e01, const cns_handle* h) {
   int grid, tpc;
   sp_chunking(n_e01, h->sm_count, &grid, &tpc);
-  return tpc * SP_TN;
+  return tpc * SP_TS;
 }
 
 int split_pack_weights(cns_handle* h, cudaStream_t s) {
@@ -472,13 +487,13 @@ int enc_edge_split(const EncEdgeArgs& a, const cns_handle* h, cudaStream_t s) {
   SpArgs ta;
   ta.e = a;
   ta.w_img = h->tc_w_split;
-  ta.n_tiles = ceil_div(a.n_e01, SP_TN);
+  ta.n_tiles = ceil_div(a.n_e01, SP_TS);
   int grid, tpc;
   sp_chunking(a.n_e01, h->sm_count, &grid, &tpc);
   ta.tiles_per_chunk = tpc;
   static_assert(sizeof(SpSmallW) == sizeof(h->tc_small_host), "first-layer weight table");
   const SpSmallW* sw = reinterpret_cast<const SpSmallW*>(h->tc_small_host);
-  enc_edge_split_kernel<<<grid, 128 * SP_SLOTS, SP_SMEM_BYTES, s>>>(ta, *sw);
+  enc_edge_split_kernel<<<grid, 128 * SP_SUB * SP_SLOTS, SP_SMEM_BYTES, s>>>(ta, *sw);
   CNS_LAUNCH_CHECK();
   return CNS_OK;
 }
