@@ -2,7 +2,8 @@
   C1  batch-1 recurrent servo latency (p50/p90), N=512, through GraphVSController; CPU oracle beside it
   C3  short-sequence training update (8 frames TBPTT + clip + 2x AdamW), bs 256, N~U{4..512} and N=512
   C4  long-sequence update (200 recurrent frames, one backward), bs 16
-  C5  keypoint-count sweep 128..8192, forward only, ~512k keypoints per batch
+  C5  keypoint-count sweep 128..8192, 64 k graphs per keypoint count, forward only, Affinity Propagation on the device for
+      every layout; under torchrun the graphs are split over the ranks
 Writes one JSON document to stdout / profiles/configs_<tag>.json.  GPU box only."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -161,35 +162,71 @@ if "c2" in which:
     out["C2_batched_inference_1024x512_f16"] = res
 
 if "c5" in which:
+    # BASELINE configs[4] as written: keypoint-count sweep 128..8192, 64 k graphs per keypoint count, forward only, split
+    # over the ranks (torchrun: every rank takes 64 k / world graphs).  Every layout is clustered by Affinity Propagation
+    # on the device (cns_b200/cluster.py), also above 1024 keypoints where scikit-learn needs minutes per target.
+    # A rank holds one resident chunk of graphs (<= ~2 M keypoints, distinct camera poses, 4 layouts) and passes over it
+    # until its share of the 64 k graphs is done; all passes are timed.
+    import torch.distributed as dist
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    TOTAL = 65536
     res = {}
-    net = ckpt.load_model(CK, "cuda:0", precision="f16")
-    for n in (128, 256, 512, 1024, 2048, 4096, 8192):
-        nb = max(8, 524288 // n)
-        rng = np.random.default_rng(n); np.random.seed(n)
-        n_layouts = 4
+    net = ckpt.load_model(CK, dev, precision=os.environ.get("CNS_PRECISION", "f16"))
+    sweep = [int(x) for x in os.environ.get("CNS_C5_N", "128,256,512,1024,2048,4096,8192").split(",")]
+    for n in sweep:
+        share = TOTAL // world
+        chunk = max(8, min(share, (1 << 21) // n))
+        passes = -(-share // chunk)
+        rng = np.random.default_rng(n + rank); np.random.seed(n + rank)
+        t0 = time.perf_counter()
         base = []
-        for _ in range(n_layouts):
+        for _ in range(4):
             pts3 = synth.sample_points(rng, n)
             tar = synth.sample_target_pose(rng)
-            xy = synth.project_norm(tar, pts3)
-            if n <= 1024:
-                gen = GraphGenerator(xy)
-                how = "affinity propagation (host sklearn)"
-            else:
-                k = int(round(0.8 * np.sqrt(n)))
-                gen = GraphGenerator.from_exemplars(xy, rng.choice(n, size=k, replace=False), device="cuda:0")
-                how = "random exemplars + cns_label_nearest (device 1-NN)"
-            base.append((pts3, tar, gen))
+            base.append((pts3, tar, GraphGenerator(synth.project_norm(tar, pts3))))
+        t_cluster = (time.perf_counter() - t0) / 4
         frames = []
-        for g in range(nb):
-            pts3, tar, gen = base[g % n_layouts]
-            sc = synth.Scene(rng, n, generator=gen, points=pts3, tar_wcT=tar)
-            frames.append(sc.frame(0.1))
-        batch = Batch.from_data_list(frames).to("cuda:0")
+        for g in range(chunk):
+            pts3, tar, gen = base[g % 4]
+            frames.append(synth.Scene(rng, n, generator=gen, points=pts3, tar_wcT=tar).frame(0.1))
+        batch = Batch.from_data_list(frames).to(dev)
+        del frames
         with torch.no_grad():
-            ms = ev_time(lambda: net(batch, None), 10)
-        res[str(n)] = {"graphs": nb, "clusters_per_graph": gen.num_clusters, "ms": ms, "graphs_per_s": nb / ms * 1e3,
-                       "keypoints_per_s": nb * n / ms * 1e3, "clustering": how}
-    out["C5_keypoint_sweep_fwd_f16"] = res
+            for _ in range(2):
+                net(batch, None)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(passes):
+                net(batch, None)
+            b.record()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        done = passes * chunk * world
+        res[str(n)] = {"graphs": done, "graphs_per_rank_chunk": chunk, "passes": passes, "ms_total": ms,
+                       "graphs_per_s": done / ms * 1e3, "keypoints_per_s": done * n / ms * 1e3,
+                       "clusters_per_graph": [int(b_[2].num_clusters) for b_ in base],
+                       "clustering": base[0][2].cluster_method, "cluster_seconds_per_target": t_cluster}
+        del batch
+        torch.cuda.empty_cache()
+    if rank == 0:
+        out["C5_keypoint_sweep_64k_graphs_fwd_%s_%dgpu" % (os.environ.get("CNS_PRECISION", "f16"), world)] = res
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        sys.exit(0)
 
 print(json.dumps(out, indent=1))
