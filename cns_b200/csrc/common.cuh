@@ -113,6 +113,7 @@ struct cns_handle {
   int no_split_encoder;                                 // CNS_NO_SPLIT_ENCODER=1: fp32 mode keeps the FFMA edge kernel (A-B runs)
   alignas(16) float tc_small_host[128 * 2 + 128 + 128 * 4 + 128];   // in_enc / pos_nn.0 weights passed as kernel params
   int tc_tile_n;                                        // edges per tensor-core tile (32 or 64)
+  int tc_slots;                                         // tiles in flight per SM of the 32-edge kernel: 4, 5 or 6 (CNS_TC_SLOTS)
   int no_split_gemm;                                    // CNS_NO_SPLIT_GEMM=1: backward GEMMs stay on the fp32 FFMA kernel (A-B runs)
   int no_fused_backbone;                                // CNS_NO_FUSED_BACKBONE=1: keep the per-layer kernels (debugging / A-B runs)
   // optional CUDA-event timing of the dominant kernel (encoder edge kernel), see cns_profile_*

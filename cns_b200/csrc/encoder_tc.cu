@@ -1,11 +1,14 @@
 // tcgen05 (5th-gen tensor core) version of the encoder edge kernel (CNS_PREC_BF16 / CNS_PREC_F16).
 //
 // One persistent CTA per SM.  The five 128x128 weight matrices of the keypoint->cluster attention
-// chain (cns/models/graph_vs.py:195-214) stay resident in shared memory for the whole kernel
-// (160 KB of 16-bit operands, fetched once per CTA with 1-D TMA bulk copies).  Edges are processed
-// in tiles of TN edges; each tile is a "slot" owned by 4 warps (thread == output channel == TMEM
-// lane) and SLOTS = 128/TN tiles are in flight per CTA so that the SIMT epilogues of one tile
-// overlap the tensor-core work of the others.  Accumulators are transposed (D[channel][edge]): the
+// chain (cns/models/graph_vs.py:195-214) stay resident for the whole kernel, fetched once per CTA with 1-D TMA
+// bulk copies: the three in front of the round-A commit in TENSOR memory (A operand of TS-mode MMAs, no
+// shared-memory fetch per instruction), the other two in shared memory (64 KB).  Edges are processed
+// in tiles of TN = 32 edges; each tile is a "slot" owned by 4 warps (thread == output channel == TMEM
+// lane) and SLOTS = 5 tiles are in flight per CTA (20 warps; 320 accumulator + 192 weight TMEM columns) so that
+// the SIMT epilogues of one tile overlap the tensor-core work of the others - round 1 kept four matrices in TMEM
+// plus all five in shared memory and had room for 4 slots only (0.264 ms); 5 slots: 0.227 ms, 6 slots (two matrices
+// in TMEM, more shared-memory A fetches): 0.227 ms.  Accumulators are transposed (D[channel][edge]): the
 // per-channel segment softmax over the edges of a cluster is then a sequential walk along TMEM
 // columns inside one thread, with warp-uniform segment boundaries - no shuffles, no atomics.
 //
@@ -31,7 +34,6 @@ namespace cns {
 
 constexpr int TC_W_BYTES = 128 * 128 * 2;         // one weight matrix, 16-bit
 constexpr int TC_NW = 5;                          // pos_nn.1, -(A0 lin_src), lin, A0 pos_nn.1, attn_nn.1
-constexpr int TC_ACT_BYTES = 64 * 1024;           // all activation buffers of all slots
 
 // ---- weight image: fp32 (k-major "chain" [5][k][o]) -> 16-bit swizzled A-operand tiles ----------
 template <bool BF16>
@@ -67,22 +69,45 @@ struct TcArgs {
 };
 
 // =================================================================================================
-template <int TN, bool BF16>
-__global__ void __launch_bounds__(128 * (128 / TN), 1)
+// Which weight matrices live where, by the number of tiles in flight.  TMEM has 512 columns: SLOTS * 2 * TN for the
+// accumulators, 64 per resident matrix.  4 slots: matrices 0..3 in tensor memory, attn_nn.1 (4) in shared memory.
+// 5 slots: the three matrices in front of the round-A commit (1, 2, 3: U and V's x half) in tensor memory, 0 and 4 in
+// shared memory.  6 slots: U's two matrices (1, 3) in tensor memory.  -1 = not there.
+__host__ __device__ constexpr int tc_tmem_slot(int slots, int w) {
+  return slots <= 4 ? (w < 4 ? w : -1) : slots == 5 ? (w == 1 ? 0 : w == 2 ? 1 : w == 3 ? 2 : -1) : (w == 1 ? 0 : w == 3 ? 1 : -1);
+}
+__host__ __device__ constexpr int tc_smem_slot(int slots, int w) {
+  return slots <= 4 ? (w == 4 ? 0 : -1) : slots == 5 ? (w == 0 ? 0 : w == 4 ? 1 : -1) : (w == 0 ? 0 : w == 2 ? 1 : w == 4 ? 2 : -1);
+}
+__host__ __device__ constexpr int tc_n_tmem(int slots) { return slots <= 4 ? 4 : slots == 5 ? 3 : 2; }
+// resident shared-memory matrices + activation tiles; the same area first stages the TMEM-bound matrices
+__host__ __device__ constexpr size_t tc_main_bytes(int slots, int tn) {
+  const size_t run = (size_t)(TC_NW - tc_n_tmem(slots)) * TC_W_BYTES + (size_t)slots * 2 * tn * 256;   // x (later u) and hp tiles per slot
+  const size_t stage = (size_t)tc_n_tmem(slots) * TC_W_BYTES;
+  return run > stage ? run : stage;
+}
+__host__ __device__ constexpr size_t tc_smem_bytes(int slots, int tn) {
+  return tc_main_bytes(slots, tn) + 256 + (size_t)slots * 2 * tn * sizeof(int) + 1024;
+}
+
+template <int TN, bool BF16, int SLOTS_>
+__global__ void __launch_bounds__(128 * SLOTS_, 1)
 enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ TcSmallW sw, const __grid_constant__ TcSmallH sh) {
-  constexpr int SLOTS = 128 / TN;
+  constexpr int SLOTS = SLOTS_;
   constexpr int ACT_TILE = TN * 256;                 // one [TN x 128] 16-bit operand tile
-  constexpr int TMEM_COLS = 512;                     // [0,256): SLOTS * 2 regions * TN accumulator columns; [256,512): weights 0..3
-  constexpr int TMEM_W = 4;                          // weight matrices kept in tensor memory (A operand without a smem fetch per MMA)
-  constexpr int TMEM_W_COL0 = 256;
+  constexpr int TMEM_COLS = 512;                     // [0, ACC): SLOTS * 2 regions * TN accumulator columns; then 64 per resident matrix
+  constexpr int TMEM_W = tc_n_tmem(SLOTS);           // weight matrices kept in tensor memory (A operand without a smem fetch per MMA)
+  constexpr int SMEM_W = TC_NW - TMEM_W;             // ... and in shared memory
+  constexpr int TMEM_W_COL0 = SLOTS * 2 * TN;
+  static_assert(TMEM_W_COL0 + TMEM_W * 64 <= 512, "tensor memory budget");
   constexpr int U_ROW = TN * 2;                      // bytes per channel row of the MN-major u tile
   constexpr int NPRE = 4;                            // a' rows prefetched per tile (first NPRE segment starts)
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment: align by hand (1 KB of slack is allocated)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* w_s = smem;                                     // 5 x 32 KB
-  unsigned char* act_s = smem + TC_NW * TC_W_BYTES;              // SLOTS x 2 x ACT_TILE = 64 KB
-  unsigned char* tail = act_s + TC_ACT_BYTES;
+  unsigned char* w_s = smem;                                     // SMEM_W x 32 KB (staging area of the TMEM-bound matrices first)
+  unsigned char* act_s = smem + SMEM_W * TC_W_BYTES;             // SLOTS x 2 x ACT_TILE
+  unsigned char* tail = smem + tc_main_bytes(SLOTS, TN);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);            // [0] = weights landed, [1+s] = MMAs of slot s done
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tail + 128);
   int* ci_s = reinterpret_cast<int*>(tail + 256);                // [SLOTS][2][TN] cluster id per edge (-1: padding), double-buffered
@@ -100,24 +125,27 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     __syncwarp();
     tmem_alloc(smem_u32(tmem_ptr_s), TMEM_COLS);
     if (lane == 0) {
-      mbar_expect_tx(smem_u32(&bars[0]), TC_NW * TC_W_BYTES);
+      // staging pass: the TMEM-bound matrices land in [w_s, ...) (weight + activation area), slot order
+      mbar_expect_tx(smem_u32(&bars[0]), TMEM_W * TC_W_BYTES);
       for (int w = 0; w < TC_NW; ++w)
-        bulk_g2s(smem_u32(w_s + w * TC_W_BYTES), args.w_img + (size_t)w * TC_W_BYTES, TC_W_BYTES, smem_u32(&bars[0]));
+        if (tc_tmem_slot(SLOTS, w) >= 0)
+          bulk_g2s(smem_u32(w_s + tc_tmem_slot(SLOTS, w) * TC_W_BYTES), args.w_img + (size_t)w * TC_W_BYTES, TC_W_BYTES,
+                   smem_u32(&bars[0]));
     }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
-  // The first TMEM_W weight matrices move on into tensor memory: with N = 32 an MMA whose A operand sits in
-  // shared memory spends most of its time fetching the 4 KB A slice (measured ~80 cycles per instruction
-  // against 16 of math).  Row o of a matrix = TMEM lane o, k and k+1 share a 32-bit column.
-  if (warp < 4) {
+  // Those matrices move on into tensor memory: with N = 32 an MMA whose A operand sits in shared memory spends most
+  // of its time fetching the 4 KB A slice (measured ~80 cycles per instruction against 16 of math).  Row o of a
+  // matrix = TMEM lane o, k and k+1 share a 32-bit column.  Warp group g = warp / 4 moves matrices g, g + SLOTS, ...
+  {
     mbar_wait(smem_u32(&bars[0]), 0);
-    const int o = tid;                               // 0..127 == TMEM lane
-    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + TMEM_W_COL0;
+    const int o = tid & 127;                         // TMEM lane
+    const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TMEM_W_COL0;
 #pragma unroll 1
-    for (int w = 0; w < TMEM_W; ++w) {
+    for (int w = warp >> 2; w < TMEM_W; w += SLOTS) {
 #pragma unroll 1
       for (int g = 0; g < 8; ++g) {                  // 16 k per trip
         const uint4 lo = *reinterpret_cast<const uint4*>(w_s + w * TC_W_BYTES + sw128_off(128, o, g * 16));
@@ -131,8 +159,16 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     tmem_st_wait();
   }
   tc_fence_before();
+  fence_proxy_async();          // generic-proxy reads of the staging area before the TMA writes that follow
   __syncthreads();
   tc_fence_after();
+  if (warp == 0 && lane == 0) {
+    mbar_expect_tx(smem_u32(&bars[0]), SMEM_W * TC_W_BYTES);
+    for (int w = 0; w < TC_NW; ++w)
+      if (tc_smem_slot(SLOTS, w) >= 0)
+        bulk_g2s(smem_u32(w_s + tc_smem_slot(SLOTS, w) * TC_W_BYTES), args.w_img + (size_t)w * TC_W_BYTES, TC_W_BYTES,
+                 smem_u32(&bars[0]));
+  }
 
   // instruction descriptor: D=f32 (bit 4), A/B format at bits 7/10 (0 f16, 1 bf16), A K-major (bit 15 = 0),
   // B K-major or MN-major (bit 16), N>>3 at bit 17, M>>4 at bit 24
@@ -146,8 +182,8 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     const int s = warp >> 2;                       // slot
     const int t = tid & 127;                       // thread in slot == output channel == TMEM lane
     const int wq = warp & 3;                       // TMEM lane quarter of this warp
-    unsigned char* buf0 = act_s + (s * 2 + 0) * ACT_TILE;
-    unsigned char* buf1 = act_s + (s * 2 + 1) * ACT_TILE;
+    unsigned char* buf0 = act_s + (s * 2 + 0) * ACT_TILE;      // x, then u
+    unsigned char* buf1 = act_s + (s * 2 + 1) * ACT_TILE;      // hp
     int* const ci_base = ci_s + s * 2 * TN;
     const uint32_t done = smem_u32(&bars[1 + s]);
     const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((s * 2 + 0) * TN);
@@ -172,10 +208,11 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t bd = hi_k | (uint64_t)(b_lo + (uint32_t)((kc * (TN * 128) + ks * 32) >> 4));
-          if (w < TMEM_W) {
-            umma_f16_ts(d, tmem_base + (uint32_t)(TMEM_W_COL0 + w * 64 + (kc * 4 + ks) * 8), bd, idesc, (kc | ks) ? 1u : acc_first);
+          if (tc_tmem_slot(SLOTS, w) >= 0) {
+            umma_f16_ts(d, tmem_base + (uint32_t)(TMEM_W_COL0 + tc_tmem_slot(SLOTS, w) * 64 + (kc * 4 + ks) * 8), bd, idesc,
+                        (kc | ks) ? 1u : acc_first);
           } else {
-            const uint64_t ad = hi_k | (uint64_t)(w_lo + (uint32_t)((w * TC_W_BYTES + kc * (128 * 128) + ks * 32) >> 4));
+            const uint64_t ad = hi_k | (uint64_t)(w_lo + (uint32_t)((tc_smem_slot(SLOTS, w) * TC_W_BYTES + kc * (128 * 128) + ks * 32) >> 4));
             umma_f16(d, ad, bd, idesc, (kc | ks) ? 1u : acc_first);
           }
         }
@@ -185,7 +222,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
       for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t ad = hi_k | (uint64_t)(w_lo + (uint32_t)((w * TC_W_BYTES + kc * (128 * 128) + ks * 32) >> 4));
+          const uint64_t ad = hi_k | (uint64_t)(w_lo + (uint32_t)((tc_smem_slot(SLOTS, w) * TC_W_BYTES + kc * (128 * 128) + ks * 32) >> 4));
           const uint64_t bd = hi_mn | (uint64_t)(lo_mn + b_lo + (uint32_t)(((kc * 4 + ks) * (16 * U_ROW)) >> 4));   // 16 k-rows per MMA
           umma_f16(d, ad, bd, idesc_mn, (kc | ks) ? 1u : 0u);
         }
@@ -204,6 +241,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
             // The epilogue needs U complete and buffer 0 (x) free: everything that reads buffer 0 goes first and the
             // commit follows U.  V's hp half only reads buffer 1: it runs behind the commit, under the epilogue, and
             // is covered by the round-C commit (a commit tracks every earlier MMA of the issuing thread).
+            // (Measured: giving u its own tile so that the commit can follow U's 16 MMAs alone changes nothing.)
             gemm_kmajor(d1, 2, b0, 0);   // V  = x  lin^T
             gemm_kmajor(d0, 1, b0, 0);   // U  = x  (-(A0 lin_src))^T
             gemm_kmajor(d0, 3, b1, 1);   //    + hp (A0 pos_nn.1)^T
@@ -217,7 +255,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         __syncwarp();
       }
     };
-    if (wq == 0) mbar_wait(smem_u32(&bars[0]), 0);     // weights landed (only the issuing warp cares)
+    if (wq == 0) mbar_wait(smem_u32(&bars[0]), 1);     // shared-memory matrices landed (second phase; only the issuing warp cares)
 
     // Per-edge inputs of the producer (thread = edge pe, channel block kp) are fetched ahead: while tile i
     // waits for its round A, the coordinate gathers of tile i+1 (their indices arrived a tile ago) and the
@@ -230,10 +268,10 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     // running (max, sum, acc) in registers; only chunk boundaries leave partials for enc_finish.
     const int n_chunks_side = ((int)gridDim.x * SLOTS) / 2;
     const int chunk_q = (int)blockIdx.x * SLOTS + s;
-    const int side = chunk_q / n_chunks_side;
-    const int chunk = chunk_q - side * n_chunks_side;
+    const int side = min(chunk_q / n_chunks_side, 1);
+    const int chunk = chunk_q - side * n_chunks_side;                       // >= n_chunks_side: the odd stream out, no tiles
     const int tpc = args.tiles_per_chunk;
-    const int t_begin = chunk * tpc, t_end = min(t_begin + tpc, args.n_tiles);
+    const int t_begin = min(chunk * tpc, args.n_tiles), t_end = min(t_begin + tpc, args.n_tiles);
     auto tile_of = [&](int it) { return t_begin + it; };
     int idx_j = 0, idx_c = -1;                     // prefetched tile: source keypoint / cluster of edge pe
     float2 c_f = make_float2(0.f, 0.f), c_ps = c_f, c_pt = c_f, c_pc = c_f;   // coordinates of the tile produced next
@@ -534,12 +572,11 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
 }
 
 // =================================================================================================
-constexpr size_t TC_SMEM_BYTES = TC_NW * TC_W_BYTES + TC_ACT_BYTES + 256 + 2 * 128 * sizeof(int) + 1024;
-
-template <int TN, bool BF16>
+template <int TN, bool BF16, int SLOTS>
 static int launch_tc(const EncEdgeArgs& a, const unsigned char* w_img, const cns_handle* h, cudaStream_t s) {
   static unsigned long long configured = 0;
-  auto kern = enc_edge_tc_kernel<TN, BF16>;
+  auto kern = enc_edge_tc_kernel<TN, BF16, SLOTS>;
+  constexpr size_t TC_SMEM_BYTES = tc_smem_bytes(SLOTS, TN);
   if (first_use_on_device(configured)) {
     CNS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
   }
@@ -548,10 +585,10 @@ static int launch_tc(const EncEdgeArgs& a, const unsigned char* w_img, const cns
   ta.w_img = w_img;
   ta.n_tiles = ceil_div(a.n_e01, TN);
   int grid, tpc;
-  tc_chunking(a.n_e01, TN, h->sm_count, &grid, &tpc);
+  tc_chunking(a.n_e01, TN, SLOTS, h->sm_count, &grid, &tpc);
   ta.tiles_per_chunk = tpc;
   { static const int v = getenv("CNS_TC_FP32_FIRST") ? atoi(getenv("CNS_TC_FP32_FIRST")) : 0; ta.fp32_first = v; }
-  const int slots = 128 / TN;
+  const int slots = SLOTS;
   // fp16 pair table of the first-layer weights (f16 mode), derived from the fp32 table on every launch: 2 KB
   const TcSmallW* sw = reinterpret_cast<const TcSmallW*>(h->tc_small_host);
   TcSmallH sh;
@@ -570,20 +607,22 @@ static int launch_tc(const EncEdgeArgs& a, const unsigned char* w_img, const cns
 }
 
 // grid size and tiles per slot-chunk for n_e01 edges: (grid * slots) / 2 contiguous chunks per side
-void tc_chunking(int64_t n_e01, int tile_n, int sm_count, int* grid, int* tiles_per_chunk) {
-  const int slots = 128 / tile_n;
+void tc_chunking(int64_t n_e01, int tile_n, int slots, int sm_count, int* grid, int* tiles_per_chunk) {
   const int n_tiles = ceil_div(n_e01, tile_n);
   int g = sm_count;
   const int want = ceil_div(2 * (int64_t)n_tiles, slots);
   if (g > want) g = want > 0 ? want : 1;
-  const int chunks_side = (g * slots) / 2;
+  int chunks_side = (g * slots) / 2;
+  if (chunks_side < 1) { chunks_side = 1; if (g * slots < 2) g = (2 + slots - 1) / slots; }
   *grid = g;
   *tiles_per_chunk = ceil_div(n_tiles > 0 ? n_tiles : 1, chunks_side);
 }
 
+static int tc_slots(const cns_handle* h) { return h->tc_tile_n == 64 ? 2 : (h->tc_slots >= 4 && h->tc_slots <= 6 ? h->tc_slots : 4); }
+
 int tc_piece_edges(int64_t n_e01, const cns_handle* h) {
   int grid, tpc;
-  tc_chunking(n_e01, h->tc_tile_n, h->sm_count, &grid, &tpc);
+  tc_chunking(n_e01, h->tc_tile_n, tc_slots(h), h->sm_count, &grid, &tpc);
   return tpc * h->tc_tile_n;
 }
 
@@ -613,15 +652,19 @@ int tc_pack_weights(cns_handle* h, cudaStream_t s) {
 int enc_edge_tc(const EncEdgeArgs& a, int precision, const cns_handle* h, cudaStream_t s) {
   if (a.n_e01 == 0) return CNS_OK;
   CNS_REQUIRE(h->tc_w_img != nullptr, "tensor-core weight image missing");
-  const int tn = h->tc_tile_n;
+  const int tn = h->tc_tile_n, slots = tc_slots(h);
   if (precision == CNS_PREC_BF16) {
-    if (tn == 32) return launch_tc<32, true>(a, h->tc_w_img, h, s);
-    return launch_tc<64, true>(a, h->tc_w_img, h, s);
+    if (tn == 64) return launch_tc<64, true, 2>(a, h->tc_w_img, h, s);
+    if (slots == 5) return launch_tc<32, true, 5>(a, h->tc_w_img, h, s);
+    if (slots == 6) return launch_tc<32, true, 6>(a, h->tc_w_img, h, s);
+    return launch_tc<32, true, 4>(a, h->tc_w_img, h, s);
   }
   if (precision == CNS_PREC_F16) {
     const unsigned char* img = h->tc_w_img + TC_NW * TC_W_BYTES;
-    if (tn == 32) return launch_tc<32, false>(a, img, h, s);
-    return launch_tc<64, false>(a, img, h, s);
+    if (tn == 64) return launch_tc<64, false, 2>(a, img, h, s);
+    if (slots == 5) return launch_tc<32, false, 5>(a, img, h, s);
+    if (slots == 6) return launch_tc<32, false, 6>(a, img, h, s);
+    return launch_tc<32, false, 4>(a, img, h, s);
   }
   set_error("enc_edge_tc: unsupported precision %d", precision);
   return CNS_ERR_UNSUPPORTED;

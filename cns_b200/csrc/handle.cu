@@ -254,6 +254,7 @@ int cns_create(cns_handle** out, int device) {
   h->no_fused_backbone = getenv("CNS_NO_FUSED_BACKBONE") ? 1 : 0;
   h->no_split_gemm = getenv("CNS_NO_SPLIT_GEMM") ? 1 : 0;
   h->no_split_encoder = getenv("CNS_NO_SPLIT_ENCODER") ? 1 : 0;
+  h->tc_slots = getenv("CNS_TC_SLOTS") ? atoi(getenv("CNS_TC_SLOTS")) : 5;
   h->sm_count = prop.multiProcessorCount;
   size_t off = 0;
   for (int k = 0; k < P_COUNT; ++k) {

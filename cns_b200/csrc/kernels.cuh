@@ -62,7 +62,7 @@ int tc_pack_weights(cns_handle* h, cudaStream_t s);
 int enc_edge_split(const EncEdgeArgs& a, const cns_handle* h, cudaStream_t s);   // fp32-accurate: bf16 (hi, lo) operand split on tcgen05
 int split_pack_weights(cns_handle* h, cudaStream_t s);
 int split_piece_edges(int64_t n_e01, const cns_handle* h);
-void tc_chunking(int64_t n_e01, int tile_n, int sm_count, int* grid, int* tiles_per_chunk);
+void tc_chunking(int64_t n_e01, int tile_n, int slots, int sm_count, int* grid, int* tiles_per_chunk);
 int tc_piece_edges(int64_t n_e01, const cns_handle* h);   // edges per softmax piece (= slot chunk) of enc_edge_tc
 
 struct EncFinishArgs {
