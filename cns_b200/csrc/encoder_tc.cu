@@ -65,7 +65,6 @@ struct TcArgs {
   const unsigned char* w_img;   // 5 swizzled 16-bit weight tiles
   int n_tiles;                  // edge tiles of TN edges
   int tiles_per_chunk;          // consecutive tiles handled by one slot (per side)
-  int fp32_first;               // f16 mode: compute the two first layers in fp32 (CNS_TC_FP32_FIRST=1) instead of packed half2
 };
 
 // =================================================================================================
@@ -375,7 +374,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         const float d0 = live ? c_pc.x - c_ps.x : 0.f, d1 = live ? c_pc.y - c_ps.y : 0.f;   // pos_i - pos_j
         const float d2 = live ? c_pc.x - c_pt.x : 0.f, d3 = live ? c_pc.y - c_pt.y : 0.f;
         // kp and gq are warp-uniform: the first-layer weights are uniform constant-bank loads
-        if (!BF16 && !args.fp32_first) {
+        if constexpr (!BF16) {
           // f16 mode: packed half2 math, two channels per instruction, results land directly in operand format.
           // (inputs and weights rounded to fp16, fp16 accumulation of 3 / 5 terms: the result is rounded to
           // fp16 for the tensor core anyway)
@@ -587,7 +586,6 @@ static int launch_tc(const EncEdgeArgs& a, const unsigned char* w_img, const cns
   int grid, tpc;
   tc_chunking(a.n_e01, TN, SLOTS, h->sm_count, &grid, &tpc);
   ta.tiles_per_chunk = tpc;
-  { static const int v = getenv("CNS_TC_FP32_FIRST") ? atoi(getenv("CNS_TC_FP32_FIRST")) : 0; ta.fp32_first = v; }
   const int slots = SLOTS;
   // fp16 pair table of the first-layer weights (f16 mode), derived from the fp32 table on every launch: 2 KB
   const TcSmallW* sw = reinterpret_cast<const TcSmallW*>(h->tc_small_host);
