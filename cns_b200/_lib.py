@@ -57,6 +57,8 @@ def _declare(lib):
         "cns_param_numel": (i64, [i32]),
         "cns_set_precision": (i32, [vp, i32]),
         "cns_set_tc_tile": (i32, [vp, i32]),
+        "cns_set_option": (i32, [vp, C.c_char_p, C.c_longlong]),
+        "cns_get_counter": (C.c_longlong, [vp, C.c_char_p]),
         "cns_profile_begin": (i32, [vp]),
         "cns_profile_end": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
         "cns_forward_workspace_bytes": (sz, [C.POINTER(cns_batch)]),
@@ -170,6 +172,12 @@ class Handle(object):
     def set_precision(self, name: str):
         check(load().cns_set_precision(self._h, PRECISIONS[name]), "cns_set_precision")
         self.precision = name
+
+    def set_option(self, name: str, value: int):
+        check(load().cns_set_option(self._h, name.encode(), int(value)), "cns_set_option(%s)" % name)
+
+    def counter(self, name: str) -> int:
+        return int(load().cns_get_counter(self._h, name.encode()))
 
     def load_weights(self, tensors, on_device: bool):
         lib = load()

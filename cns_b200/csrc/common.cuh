@@ -130,5 +130,9 @@ struct cns_handle {
   struct cns_target_cache* servo_tcache; void* servo_tkey; size_t servo_tkey_bytes;
   // fork/join pair for work that is independent of the index preparation (per-cluster encoder terms), created lazily
   cudaStream_t side_stream; cudaEvent_t side_fork, side_join, side_join2;
+  // CUDA-graph cache of cns_graphvs_forward (forward.cu): a call whose whole argument set (sizes, pointers, mode) was seen
+  // before is replayed as one graph launch instead of ~10 kernel launches + 3 event fork/joins
+  int use_graphs; void* graph_cache; cudaStream_t cap_stream;
+  long long graph_replays, graph_captures;
   const float* P(int id) const { return raw + raw_off[id]; }
 };

@@ -91,8 +91,11 @@ static int validate(const cns_batch* b) {
   return CNS_OK;
 }
 
+// `cap_ev`: the call is being captured into a CUDA graph with kernel timing on - the encoder edge kernel is bracketed by
+// these two events (recorded as external event nodes, readable after every replay) instead of the handle's event ring
 int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, float* vel_si_vec,
-                 float* vel_si_norm, float* hidden_out, float* vel, void* workspace, void* save, cudaStream_t s) {
+                 float* vel_si_norm, float* hidden_out, float* vel, void* workspace, void* save, cudaStream_t s,
+                 cudaEvent_t* cap_ev = nullptr) {
   Arena ar(workspace);
   FwdBuffers f;
   SaveBuffers sv_store;
@@ -206,8 +209,9 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   ee.w_in = h->P(P_IN_W); ee.b_in = h->P(P_IN_B); ee.w_p0 = h->P(P_POS0_W); ee.b_p0 = h->P(P_POS0_B);
   ee.enc_chain = pk.enc_chain; ee.b_p1 = h->P(P_POS1_B); ee.b_a0 = h->P(P_ATT0_B); ee.b_a1 = h->P(P_ATT1_B);
   ee.clu_feat = f.clu_feat; ee.partial = f.partial;
-  const bool timed = h->timing && h->ev_n < 256;
+  const bool timed = !cap_ev && h->timing && h->ev_n < 256;
   if (timed) CNS_CUDA_CHECK(cudaEventRecord(h->ev[2 * h->ev_n], s));
+  if (cap_ev) CNS_CUDA_CHECK(cudaEventRecordWithFlags(cap_ev[0], s, cudaEventRecordExternal));
   if (h->precision == CNS_PREC_FP32) {
     if (h->no_split_encoder) { RUN(enc_edge_fp32(ee, s)); }
     else { RUN(enc_edge_split(ee, h, s)); }
@@ -215,6 +219,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     RUN(enc_edge_tc(ee, h->precision, h, s));
   }
   if (timed) { CNS_CUDA_CHECK(cudaEventRecord(h->ev[2 * h->ev_n + 1], s)); ++h->ev_n; }
+  if (cap_ev) CNS_CUDA_CHECK(cudaEventRecordWithFlags(cap_ev[1], s, cudaEventRecordExternal));
 
   EncFinishArgs ef{};
   ef.n_clusters = C; ef.n_slots = f.n_slots;
@@ -339,6 +344,133 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   return CNS_OK;
 }
 
+
+// ---- CUDA-graph cache ---------------------------------------------------------------------------------------------
+// forward_impl is a pure enqueue (no host read of device data), so a call whose whole argument set repeats - a servo
+// loop over persistent buffers, a throughput loop over resident batches - can be replayed as ONE graph launch.  An
+// argument set is captured the second time it is seen (one-off calls never pay for a capture); entries are evicted
+// least-recently-used.  Everything that shapes the enqueue is part of the key.
+struct GraphEntry {
+  uint64_t key; int seen; cudaGraphExec_t exec; long long launches; unsigned long long last_use;
+  cudaEvent_t ev[2]; int timed, replayed;
+};
+constexpr int GRAPH_CACHE_N = 48;
+struct GraphCache { GraphEntry e[GRAPH_CACHE_N]; unsigned long long clock; };
+
+static uint64_t fnv(uint64_t hsh, const void* p, size_t n) {
+  const unsigned char* c = (const unsigned char*)p;
+  for (size_t i = 0; i < n; ++i) { hsh ^= c[i]; hsh *= 1099511628211ull; }
+  return hsh;
+}
+
+static void graph_entry_drop(GraphEntry& g) {
+  if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (g.ev[0]) { cudaEventDestroy(g.ev[0]); cudaEventDestroy(g.ev[1]); }
+  memset(&g, 0, sizeof(g));
+}
+
+void graph_cache_clear(cns_handle* h) {
+  GraphCache* gc = (GraphCache*)h->graph_cache;
+  if (!gc) return;
+  for (int i = 0; i < GRAPH_CACHE_N; ++i) graph_entry_drop(gc->e[i]);
+  delete gc;
+  h->graph_cache = nullptr;
+}
+
+void graph_cache_begin_timing(cns_handle* h) {
+  GraphCache* gc = (GraphCache*)h->graph_cache;
+  if (gc) for (int i = 0; i < GRAPH_CACHE_N; ++i) gc->e[i].replayed = 0;
+}
+
+// the encoder-edge-kernel time of the LAST replay of every timed graph replayed since cns_profile_begin
+int graph_cache_collect_timing(cns_handle* h, float* ms_total, int* n) {
+  *ms_total = 0.f; *n = 0;
+  GraphCache* gc = (GraphCache*)h->graph_cache;
+  if (!gc) return CNS_OK;
+  for (int i = 0; i < GRAPH_CACHE_N; ++i) {
+    GraphEntry& g = gc->e[i];
+    if (!g.exec || !g.timed || !g.replayed) continue;
+    float ms = 0.f;
+    CNS_CUDA_CHECK(cudaEventSynchronize(g.ev[1]));
+    CNS_CUDA_CHECK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
+    *ms_total += ms; ++*n;
+    g.replayed = 0;
+  }
+  return CNS_OK;
+}
+
+static int forward_graphed(cns_handle* h, const cns_batch* b, const float* hidden_in, float* vel_si_vec,
+                           float* vel_si_norm, float* hidden_out, float* vel, void* workspace, cudaStream_t s) {
+  if (!h->graph_cache) { h->graph_cache = new GraphCache(); memset(h->graph_cache, 0, sizeof(GraphCache)); }
+  GraphCache* gc = (GraphCache*)h->graph_cache;
+  uint64_t key = 1469598103934665603ull;
+  key = fnv(key, b, sizeof(*b));
+  const void* ptrs[6] = {hidden_in, vel_si_vec, vel_si_norm, hidden_out, vel, workspace};
+  key = fnv(key, ptrs, sizeof(ptrs));
+  const long long mode[8] = {h->precision, h->weights_version, h->timing, h->tc_tile_n, h->tc_slots, 0,
+                             h->no_fused_backbone * 2 + h->no_split_encoder, b->target_cache ? b->target_cache->weights_version : 0};
+  key = fnv(key, mode, sizeof(mode));
+  if (key == 0) key = 1;
+  GraphEntry* hit = nullptr; GraphEntry* victim = &gc->e[0];
+  for (int i = 0; i < GRAPH_CACHE_N; ++i) {
+    if (gc->e[i].key == key) { hit = &gc->e[i]; break; }
+    if (gc->e[i].last_use < victim->last_use) victim = &gc->e[i];
+  }
+  ++gc->clock;
+  if (hit && hit->exec) {
+    hit->last_use = gc->clock; hit->replayed = 1;
+    CNS_CUDA_CHECK(cudaGraphLaunch(hit->exec, s));
+    g_launch_count += hit->launches;
+    ++h->graph_replays;
+    return CNS_OK;
+  }
+  if (!hit || hit->seen < 0) {          // first sight (or not capturable): plain enqueue
+    if (!hit) { graph_entry_drop(*victim); victim->key = key; victim->seen = 1; victim->last_use = gc->clock; }
+    else hit->last_use = gc->clock;
+    return forward_impl(h, b, hidden_in, vel_si_vec, vel_si_norm, hidden_out, vel, workspace, nullptr, s);
+  }
+  // second sight: capture, instantiate, launch
+  hit->last_use = gc->clock;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {   // the caller is capturing already
+    cudaGetLastError();
+    return forward_impl(h, b, hidden_in, vel_si_vec, vel_si_norm, hidden_out, vel, workspace, nullptr, s);
+  }
+  // the legacy default stream cannot be captured: record on the handle's side stream instead (a graph can be launched
+  // into any stream)
+  cudaStream_t cs = s;
+  if (s == nullptr || s == cudaStreamLegacy) {
+    if (!h->cap_stream) CNS_CUDA_CHECK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    cs = h->cap_stream;
+  }
+  hit->timed = h->timing;
+  if (hit->timed && !hit->ev[0]) { CNS_CUDA_CHECK(cudaEventCreate(&hit->ev[0])); CNS_CUDA_CHECK(cudaEventCreate(&hit->ev[1])); }
+  const long long l0 = g_launch_count;
+  CNS_CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+  int rc = forward_impl(h, b, hidden_in, vel_si_vec, vel_si_norm, hidden_out, vel, workspace, nullptr, cs, hit->timed ? hit->ev : nullptr);
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+  hit->launches = g_launch_count - l0;
+  g_launch_count = l0;
+  if (rc == CNS_OK && ce == cudaSuccess && graph) {
+    ce = cudaGraphInstantiate(&hit->exec, graph, 0);
+    if (ce != cudaSuccess) hit->exec = nullptr;
+  }
+  if (graph) cudaGraphDestroy(graph);
+  if (rc != CNS_OK || ce != cudaSuccess || !hit->exec) {
+    cudaGetLastError();
+    hit->seen = -1;                     // never try again for this argument set
+    if (rc != CNS_OK) return rc;        // an argument error: the plain path reports the same
+    return forward_impl(h, b, hidden_in, vel_si_vec, vel_si_norm, hidden_out, vel, workspace, nullptr, s);
+  }
+  ++h->graph_captures;
+  hit->replayed = 1;
+  CNS_CUDA_CHECK(cudaGraphLaunch(hit->exec, s));
+  g_launch_count += hit->launches;
+  ++h->graph_replays;
+  return CNS_OK;
+}
+
 }  // namespace cns
 
 using namespace cns;
@@ -381,6 +513,8 @@ int cns_graphvs_forward(cns_handle* h, const cns_batch* b, const float* hidden_i
     return CNS_ERR_WORKSPACE_TOO_SMALL;
   }
   CNS_CUDA_CHECK(cudaSetDevice(h->device));
+  if (h->use_graphs && !save)
+    return forward_graphed(h, b, hidden_in, vel_si_vec, vel_si_norm, hidden_out, vel, workspace, (cudaStream_t)stream);
   return forward_impl(h, b, hidden_in, vel_si_vec, vel_si_norm, hidden_out, vel, workspace, save, (cudaStream_t)stream);
 }
 

@@ -255,6 +255,7 @@ int cns_create(cns_handle** out, int device) {
   h->no_split_gemm = getenv("CNS_NO_SPLIT_GEMM") ? 1 : 0;
   h->no_split_encoder = getenv("CNS_NO_SPLIT_ENCODER") ? 1 : 0;
   h->tc_slots = getenv("CNS_TC_SLOTS") ? atoi(getenv("CNS_TC_SLOTS")) : 5;
+  h->use_graphs = getenv("CNS_NO_GRAPHS") ? 0 : 1;
   h->sm_count = prop.multiProcessorCount;
   size_t off = 0;
   for (int k = 0; k < P_COUNT; ++k) {
@@ -293,6 +294,8 @@ int cns_destroy(cns_handle* h) {
   if (h->tc_w_split) cudaFree(h->tc_w_split);
   if (h->pk.tc_node_base) cudaFree(h->pk.tc_node_base);
   if (h->pk.tc2_base) cudaFree(h->pk.tc2_base);
+  graph_cache_clear(h);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->servo_tcache) cns_target_cache_destroy(h->servo_tcache);
   free(h->servo_tkey);
   if (h->side_stream) { cudaStreamDestroy(h->side_stream); cudaEventDestroy(h->side_fork); cudaEventDestroy(h->side_join); cudaEventDestroy(h->side_join2); }
@@ -339,6 +342,7 @@ int cns_profile_begin(cns_handle* h) {
   if (!h->ev[0]) for (int i = 0; i < 2 * 256; ++i) CNS_CUDA_CHECK(cudaEventCreate(&h->ev[i]));
   h->ev_n = 0;
   h->timing = 1;
+  graph_cache_begin_timing(h);
   g_launch_count = 0;
   return CNS_OK;
 }
@@ -353,8 +357,15 @@ int cns_profile_end(cns_handle* h, float* enc_edge_ms_total, int* n_timed, long 
     CNS_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]));
     total += ms;
   }
+  int n = h->ev_n;
+  {
+    float gms = 0.f; int gn = 0;
+    int rc = graph_cache_collect_timing(h, &gms, &gn);
+    if (rc != CNS_OK) return rc;
+    total += gms; n += gn;
+  }
   if (enc_edge_ms_total) *enc_edge_ms_total = total;
-  if (n_timed) *n_timed = h->ev_n;
+  if (n_timed) *n_timed = n;
   if (launches) *launches = g_launch_count;
   return CNS_OK;
 }
@@ -366,6 +377,22 @@ int cns_set_tc_tile(cns_handle* h, int tile_n) {
   CNS_REQUIRE(tile_n == 32 || tile_n == 64, "tile_n must be 32 or 64");
   h->tc_tile_n = tile_n;
   return CNS_OK;
+}
+
+int cns_set_option(cns_handle* h, const char* name, long long value) {
+  CNS_REQUIRE(h != nullptr && name != nullptr, "NULL argument");
+  if (!strcmp(name, "cuda_graphs")) { h->use_graphs = value != 0; if (!value) graph_cache_clear(h); return CNS_OK; }
+  if (!strcmp(name, "tc_slots")) { CNS_REQUIRE(value >= 4 && value <= 6, "tc_slots must be 4..6"); h->tc_slots = (int)value; return CNS_OK; }
+  set_error("cns_set_option: unknown option '%s'", name);
+  return CNS_ERR_INVALID_ARGUMENT;
+}
+
+long long cns_get_counter(cns_handle* h, const char* name) {
+  if (!h || !name) return -1;
+  if (!strcmp(name, "graph_replays")) return h->graph_replays;
+  if (!strcmp(name, "graph_captures")) return h->graph_captures;
+  if (!strcmp(name, "kernel_launches")) return g_launch_count;
+  return -1;
 }
 
 int cns_set_precision(cns_handle* h, int precision) {

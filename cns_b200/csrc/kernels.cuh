@@ -7,6 +7,11 @@ namespace cns {
 constexpr int ENC_TILE_E = 128;   // edges per encoder tile
 constexpr int ENC_PIECE_E = 64;   // softmax piece granularity (partials are indexed per piece)
 
+// ---- forward.cu: CUDA-graph cache of the forward ------------------------------------------
+void graph_cache_clear(cns_handle* h);
+void graph_cache_begin_timing(cns_handle* h);
+int graph_cache_collect_timing(cns_handle* h, float* ms_total, int* n);
+
 // ---- prep.cu ------------------------------------------------------------------------------
 int exclusive_scan_i32(const int* in, int64_t n, int* out, int* scratch, cudaStream_t s);
 size_t scan_scratch_bytes(int64_t n);

@@ -340,8 +340,9 @@ class GraphVS(nn.Module):
             if hidden.shape != (nc, 128):
                 raise _lib.CnsError("hidden has shape %s, expected (%d, 128)" % (tuple(hidden.shape), nc))
         nbytes = lib.cns_forward_workspace_bytes(C.byref(b))
-        ws = self._workspace(dev.index, nbytes)
         stream = _lib.stream_ptr(dev)
+        # one workspace per stream: forwards enqueued on different streams may overlap on the device
+        ws = self._workspace(dev.index, nbytes, ("fwd", stream.value))
         _lib.check(lib.cns_graphvs_forward(
             h.raw, C.byref(b), _lib.ptr(hidden), _lib.ptr(vec), _lib.ptr(nrm), _lib.ptr(hid), _lib.ptr(vel),
             _lib.ptr(ws), ws.numel(), None, 0, stream), "cns_graphvs_forward")

@@ -44,24 +44,29 @@ class BatchedServo(object):
         self.num_clusters = d(n_clu, torch.int64)
         self.tpo = d(np.broadcast_to(np.asarray(dist_scale, dtype=np.float32), (self.B,)), torch.float32)
         i64 = lambda n: torch.empty(n, dtype=torch.int64, device=self.dev)
-        self.e01_j, self.e01_i = i64(max(self.N, 1)), i64(max(self.N, 1))
-        self.cmask = torch.empty(max(self.Cn, 1), dtype=torch.uint8, device=self.dev)
-        self.clu_rowptr = torch.empty(self.Cn + 1, dtype=torch.int32, device=self.dev)
-        self.mask_ws = torch.empty((self.Cn + 1) * 4, dtype=torch.uint8, device=self.dev)
-        # frames in flight (submit / result): inputs and outputs are double-buffered, everything in between is
-        # ordered by the compute stream
+        # frames in flight (submit / result): every per-frame buffer exists `depth` times and every slot has its own
+        # compute stream, so the kernels of consecutive frames may overlap on the device (the cluster-level backbone of
+        # frame t leaves most SMs idle in its second wave; the encoder of frame t+1 fills them).  A carried hidden
+        # state orders frame t+1 behind frame t through an event.
         self.depth = 2
-        self.xy_dev = [torch.empty(self.N, 2, dtype=torch.float32, device=self.dev) for _ in range(self.depth)]
-        self.vis_dev = [torch.empty(self.N, dtype=torch.uint8, device=self.dev) for _ in range(self.depth)]
-        self.vel_host = [torch.empty(self.B, 6).pin_memory() for _ in range(self.depth)]
-        self.copied = [torch.cuda.Event() for _ in range(self.depth)]
+        D = range(self.depth)
+        self.e01_j, self.e01_i = [i64(max(self.N, 1)) for _ in D], [i64(max(self.N, 1)) for _ in D]
+        self.cmask = [torch.empty(max(self.Cn, 1), dtype=torch.uint8, device=self.dev) for _ in D]
+        self.clu_rowptr = [torch.empty(self.Cn + 1, dtype=torch.int32, device=self.dev) for _ in D]
+        self.mask_ws = [torch.empty((self.Cn + 1) * 4, dtype=torch.uint8, device=self.dev) for _ in D]
+        self.xy_dev = [torch.empty(self.N, 2, dtype=torch.float32, device=self.dev) for _ in D]
+        self.vis_dev = [torch.empty(self.N, dtype=torch.uint8, device=self.dev) for _ in D]
+        self.vel_host = [torch.empty(self.B, 6).pin_memory() for _ in D]
+        self.out = [torch.empty(self.B * 13, dtype=torch.float32, device=self.dev) for _ in D]
+        self.copied = [torch.cuda.Event() for _ in D]
         self.done = [None] * self.depth
         self.copy_stream = torch.cuda.Stream(self.dev)
+        self.streams = [torch.cuda.Stream(self.dev) for _ in D]
         self.ticket = 0
         self.tcache, self.tcache_handle = None, None       # cns_target_cache: target-side results kept across frames
         self.hidden = [torch.zeros(self.Cn, 128, device=self.dev), torch.zeros(self.Cn, 128, device=self.dev)]
         self.cur, self.have_hidden = 0, False
-        self.out = torch.empty(self.B * 13, dtype=torch.float32, device=self.dev)
+        self.hidden_ready = None                           # event: the newest hidden state is complete
         self.h2d_bytes = self.N * 2 * 4 + self.N
         self.d2h_bytes = self.B * 6 * 4
 
@@ -107,8 +112,8 @@ class BatchedServo(object):
         """Enqueue one frame; returns a ticket for `result`.  cur_xy (sum N, 2) float32 and visible (sum N,)
         uint8/bool are HOST tensors (pinned for full speed) in the scenes' keypoint order.  Up to `depth`
         frames may be in flight: the host->device copy of frame t+1 (copy stream) overlaps the kernels of
-        frame t; kernels, hidden state and the device->host copy of the velocities are ordered by the current
-        stream.
+        frame t, and so do its kernels when no hidden state is carried (every slot has its own compute stream;
+        what the caller enqueued on the current stream before the call is waited for).
 
         The current-side cluster graph is never materialised: it is the complete digraph over the clusters
         that keep a visible keypoint (graph_gen.py:199-228), which the forward handles from cluster_mask
@@ -118,47 +123,54 @@ class BatchedServo(object):
         k = self.ticket % self.depth
         if self.done[k] is not None:
             self.done[k].synchronize()                 # the frame that used this slot has delivered its result
-        cur = torch.cuda.current_stream(dev)
-        stream = cur.cuda_stream
+        st = self.streams[k]
+        st.wait_stream(torch.cuda.current_stream(dev))  # whatever the caller enqueued (new weights, ...) comes first
+        stream = st.cuda_stream
         vis = visible.view(torch.uint8) if visible.dtype == torch.bool else visible
         n01 = int(torch.count_nonzero(vis))
         with torch.cuda.stream(self.copy_stream):
             self.xy_dev[k].copy_(cur_xy, non_blocking=True)
             self.vis_dev[k].copy_(vis, non_blocking=True)
             self.copied[k].record(self.copy_stream)
-        cur.wait_event(self.copied[k])
+        st.wait_event(self.copied[k])
+        if self.have_hidden and self.hidden_ready is not None:
+            st.wait_event(self.hidden_ready)
         xy, visd = self.xy_dev[k], self.vis_dev[k]
+        e01_j, e01_i, cmask, clu_rowptr, mask_ws = self.e01_j[k], self.e01_i[k], self.cmask[k], self.clu_rowptr[k], self.mask_ws[k]
         L.check(lib.cns_frame_mask(L.ptr(self.member_order), L.ptr(self.member_ptr), L.ptr(visd), self.N, self.Cn,
-                                   L.ptr(self.e01_j), L.ptr(self.e01_i), L.ptr(self.cmask), L.ptr(self.clu_rowptr),
-                                   L.ptr(self.mask_ws), self.mask_ws.numel(), stream), "cns_frame_mask")
+                                   L.ptr(e01_j), L.ptr(e01_i), L.ptr(cmask), L.ptr(clu_rowptr),
+                                   L.ptr(mask_ws), mask_ws.numel(), stream), "cns_frame_mask")
         b = L.cns_batch()
         b.n_nodes, b.n_clusters, b.n_graphs = self.N, self.Cn, self.B
         b.n_e01, b.n_e11_cur, b.n_e11_tar = n01, 0, 0
         p = lambda t: t.data_ptr()
         b.x_cur, b.pos_cur, b.x_tar, b.pos_tar = p(xy), p(xy), p(self.x_tar), p(self.x_tar)
-        b.l0_to_l1_j, b.l0_to_l1_i = p(self.e01_j), p(self.e01_i)
+        b.l0_to_l1_j, b.l0_to_l1_i = p(e01_j), p(e01_i)
         b.l1_edge_cur, b.l1_edge_tar = None, None               # both cluster graphs are implied (complete)
         b.l1_cur_stride, b.l1_tar_stride = 0, 0
-        b.cluster_mask, b.cluster_centers = p(self.cmask), p(self.centers)
+        b.cluster_mask, b.cluster_centers = p(cmask), p(self.centers)
         b.node_graph, b.num_clusters, b.tPo_norm = None, p(self.num_clusters), p(self.tpo)
         b.flags = L.BATCH_L1_CUR_COMPLETE | L.BATCH_L1_TAR_COMPLETE
         b.max_clusters_per_graph = self.max_clusters
         h = self.net._handle(dev)
         b.target_cache = self._target_cache(h)
-        b.clu_rowptr = p(self.clu_rowptr)
-        ws = self.net._workspace(dev.index, lib.cns_forward_workspace_bytes(C.byref(b)))
+        b.clu_rowptr = p(clu_rowptr)
+        ws = self.net._workspace(dev.index, lib.cns_forward_workspace_bytes(C.byref(b)), ("fwd", stream))
         B = self.B
-        vec, vel, nrm = self.out[:B * 6], self.out[B * 6:B * 12], self.out[B * 12:]
+        out = self.out[k]
+        vec, vel, nrm = out[:B * 6], out[B * 6:B * 12], out[B * 12:]
         hin = self.hidden[self.cur] if self.have_hidden else None
         hout = self.hidden[self.cur ^ 1]
         L.check(lib.cns_graphvs_forward(h.raw, C.byref(b), L.ptr(hin), L.ptr(vec), L.ptr(nrm), L.ptr(hout), L.ptr(vel),
-                                        L.ptr(ws), ws.numel(), None, 0, stream), "cns_graphvs_forward")
+                                        L.ptr(ws), ws.numel(), None, 0, C.c_void_p(stream)), "cns_graphvs_forward")
         self.cur ^= 1
         self.have_hidden = True
-        self.vel_host[k].copy_(vel.view(B, 6), non_blocking=True)
+        with torch.cuda.stream(st):
+            self.vel_host[k].copy_(vel.view(B, 6), non_blocking=True)
         ev = torch.cuda.Event()
-        ev.record(cur)
+        ev.record(st)
         self.done[k] = ev
+        self.hidden_ready = ev
         self.ticket += 1
         return self.ticket - 1
 

@@ -73,6 +73,12 @@ const char* cns_param_name(int k);      /* e.g. "encoder.in_enc.fcs.0.weight" */
 int64_t cns_param_numel(int k);
 int cns_set_precision(cns_handle* h, int precision /* cns_precision */);
 int cns_set_tc_tile(cns_handle* h, int tile_n /* 32 or 64: edges per tensor-core tile */);
+/* Tuning switches (no reference counterpart): "cuda_graphs" 0/1 - replay repeated cns_graphvs_forward calls (same sizes,
+ * pointers and mode) as one CUDA-graph launch, default 1 (CNS_NO_GRAPHS=1 in the environment turns it off);
+ * "tc_slots" 4..6 - edge tiles in flight per SM. */
+int cns_set_option(cns_handle* h, const char* name, long long value);
+/* "graph_replays", "graph_captures", "kernel_launches" (library-wide host-side count); -1 for an unknown name */
+long long cns_get_counter(cns_handle* h, const char* name);
 
 /* Measurement hooks: between begin and end every cns_graphvs_forward brackets its dominant
  * kernel (the encoder edge kernel) with CUDA events on the launching stream (first 256

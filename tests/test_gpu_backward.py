@@ -71,7 +71,7 @@ def test_hidden_state_gradient(state_dict):
     """d loss / d hidden_in (what BPTT chains through) vs the oracle."""
     bt = _frames([60, 200], 1, seed=5)[0]
     nc = int(bt.num_clusters.sum())
-    h0 = torch.randn(nc, 128, dtype=torch.float64) * 0.3
+    h0 = torch.randn(nc, 128, dtype=torch.float64, generator=torch.Generator().manual_seed(11)) * 0.3
     W = {k: v.double() for k, v in state_dict.items()}
     h_ref = h0.clone().requires_grad_(True)
     vec, nrm, hid = cns_oracle.forward(W, bt, h_ref, dtype=torch.float64)

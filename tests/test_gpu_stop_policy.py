@@ -77,7 +77,7 @@ def test_batched_pixel_stop_matches_oracle_per_scene():
 
 def test_scene_without_visible_keypoint_gives_nan():
     bat = BatchedPixelStop([4, 6], waiting_time=0.3, device=DEV)
-    pos = torch.rand(10, 2)
+    pos = torch.rand(10, 2, generator=torch.Generator().manual_seed(5))
     mask = torch.tensor([0, 0, 0, 0, 1, 1, 0, 1, 1, 1], dtype=torch.bool)
     err = bat.errors(pos, pos * 0.9, mask).cpu().numpy()
     assert np.isnan(err[0]) and np.isfinite(err[1])
