@@ -63,6 +63,7 @@ struct TcSmallH {
 struct TcArgs {
   EncEdgeArgs e;
   const unsigned char* w_img;   // 5 swizzled 16-bit weight tiles
+  const unsigned char* w_first; // f16 mode: first-layer A tile (tc_mma_first)
   int n_tiles;                  // edge tiles of TN edges
   int tiles_per_chunk;          // consecutive tiles handled by one slot (per side)
 };
@@ -85,8 +86,15 @@ __host__ __device__ constexpr size_t tc_main_bytes(int slots, int tn) {
   const size_t stage = (size_t)tc_n_tmem(slots) * TC_W_BYTES;
   return run > stage ? run : stage;
 }
+// f16 mode, 32-edge tiles, <= 5 slots: the two first layers (K = 2 / 4 inputs) run on the tensor core as one K = 16
+// step: a 16 KB A tile [channel][16 k of in_enc | 16 k of pos_nn.0] and one [edge][16 k] input tile (4 KB) per slot
+__host__ __device__ constexpr bool tc_mma_first(int slots, int tn, bool bf16) { return !bf16 && tn == 32 && slots <= 5; }
+constexpr int TC_FIRST_W_BYTES = 128 * 128;       // one SWIZZLE_128B tile of 128 rows; 64 of the 128 bytes per row are used
+__host__ __device__ constexpr size_t tc_first_bytes(int slots, int tn) {
+  return tc_mma_first(slots, tn, false) ? (size_t)TC_FIRST_W_BYTES + (size_t)slots * tn * 128 : 0;
+}
 __host__ __device__ constexpr size_t tc_smem_bytes(int slots, int tn) {
-  return tc_main_bytes(slots, tn) + 256 + (size_t)slots * 2 * tn * sizeof(int) + 1024;
+  return tc_main_bytes(slots, tn) + tc_first_bytes(slots, tn) + 256 + (size_t)slots * 2 * tn * sizeof(int) + 1024;
 }
 
 template <int TN, bool BF16, int SLOTS_>
@@ -106,7 +114,10 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* w_s = smem;                                     // SMEM_W x 32 KB (staging area of the TMEM-bound matrices first)
   unsigned char* act_s = smem + SMEM_W * TC_W_BYTES;             // SLOTS x 2 x ACT_TILE
-  unsigned char* tail = smem + tc_main_bytes(SLOTS, TN);
+  constexpr bool MMA_FIRST = tc_mma_first(SLOTS, TN, BF16);
+  unsigned char* wfirst_s = smem + tc_main_bytes(SLOTS, TN);     // first-layer A tile, then SLOTS input tiles [TN][128 B]
+  unsigned char* in16_s = wfirst_s + TC_FIRST_W_BYTES;
+  unsigned char* tail = smem + tc_main_bytes(SLOTS, TN) + tc_first_bytes(SLOTS, TN);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);            // [0] = weights landed, [1+s] = MMAs of slot s done
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tail + 128);
   int* ci_s = reinterpret_cast<int*>(tail + 256);                // [SLOTS][2][TN] cluster id per edge (-1: padding), double-buffered
@@ -162,11 +173,12 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   if (warp == 0 && lane == 0) {
-    mbar_expect_tx(smem_u32(&bars[0]), SMEM_W * TC_W_BYTES);
+    mbar_expect_tx(smem_u32(&bars[0]), SMEM_W * TC_W_BYTES + (MMA_FIRST ? TC_FIRST_W_BYTES : 0));
     for (int w = 0; w < TC_NW; ++w)
       if (tc_smem_slot(SLOTS, w) >= 0)
         bulk_g2s(smem_u32(w_s + tc_smem_slot(SLOTS, w) * TC_W_BYTES), args.w_img + (size_t)w * TC_W_BYTES, TC_W_BYTES,
                  smem_u32(&bars[0]));
+    if (MMA_FIRST) bulk_g2s(smem_u32(wfirst_s), args.w_first, TC_FIRST_W_BYTES, smem_u32(&bars[0]));
   }
 
   // instruction descriptor: D=f32 (bit 4), A/B format at bits 7/10 (0 f16, 1 bf16), A K-major (bit 15 = 0),
@@ -216,6 +228,22 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
           }
         }
     };
+    // the same with the B tile stored MN-major ([k][edge], like the u tile): x / hp tiles written by the first-layer epilogue
+    auto gemm_mn_any = [&](uint32_t d, int w, uint32_t b_lo, uint32_t acc_first) {
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t bd = hi_mn | (uint64_t)(lo_mn + b_lo + (uint32_t)(((kc * 4 + ks) * (16 * U_ROW)) >> 4));
+          if (tc_tmem_slot(SLOTS, w) >= 0) {
+            umma_f16_ts(d, tmem_base + (uint32_t)(TMEM_W_COL0 + tc_tmem_slot(SLOTS, w) * 64 + (kc * 4 + ks) * 8), bd, idesc_mn,
+                        (kc | ks) ? 1u : acc_first);
+          } else {
+            const uint64_t ad = hi_k | (uint64_t)(w_lo + (uint32_t)((tc_smem_slot(SLOTS, w) * TC_W_BYTES + kc * (128 * 128) + ks * 32) >> 4));
+            umma_f16(d, ad, bd, idesc_mn, (kc | ks) ? 1u : acc_first);
+          }
+        }
+    };
     auto gemm_mnmajor = [&](uint32_t d, int w, uint32_t b_lo) {     // B tile stored [k][edge]
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc)
@@ -236,7 +264,19 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
           const uint32_t b0 = b0_lo, b1 = b1_lo;
           const uint32_t d0 = tmem_base + (uint32_t)((s * 2 + 0) * TN);
           const uint32_t d1 = tmem_base + (uint32_t)((s * 2 + 1) * TN);
-          if (round == 0) {
+          if (MMA_FIRST && round == 2) {
+            // first layers: X = W_in [f | 1], HP = W_p0 [dpos | 1] (K = 16: fp16 head + tail of every input, bias column)
+            const uint32_t wf_lo = smem_u32(wfirst_s) >> 4, in_lo = smem_u32(in16_s + s * (TN * 128)) >> 4;
+            umma_f16(d0, hi_k | (uint64_t)wf_lo, hi_k | (uint64_t)in_lo, idesc, 0u);
+            umma_f16(d1, hi_k | (uint64_t)(wf_lo + 2), hi_k | (uint64_t)in_lo, idesc, 0u);
+            umma_commit(done);
+          } else if (MMA_FIRST && round == 0) {
+            gemm_mn_any(d1, 2, b0, 0);   // V  = x  lin^T               (x, hp tiles are MN-major here)
+            gemm_mn_any(d0, 1, b0, 0);   // U  = x  (-(A0 lin_src))^T
+            gemm_mn_any(d0, 3, b1, 1);   //    + hp (A0 pos_nn.1)^T
+            umma_commit(done);
+            gemm_mn_any(d1, 0, b1, 1);   // V += hp pos_nn.1^T
+          } else if (round == 0) {
             // The epilogue needs U complete and buffer 0 (x) free: everything that reads buffer 0 goes first and the
             // commit follows U.  V's hp half only reads buffer 1: it runs behind the commit, under the epilogue, and
             // is covered by the round-C commit (a commit tracks every earlier MMA of the issuing thread).
@@ -374,7 +414,21 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         const float d0 = live ? c_pc.x - c_ps.x : 0.f, d1 = live ? c_pc.y - c_ps.y : 0.f;   // pos_i - pos_j
         const float d2 = live ? c_pc.x - c_pt.x : 0.f, d3 = live ? c_pc.y - c_pt.y : 0.f;
         // kp and gq are warp-uniform: the first-layer weights are uniform constant-bank loads
-        if constexpr (!BF16) {
+        if constexpr (MMA_FIRST) {
+          // f16 mode: the first layers run on the tensor core.  One warp writes the [edge][16 k] input tile: every input
+          // as an fp16 head and an fp16 tail (v = hi + lo to ~22 bits: the geometry lives in small coordinate
+          // differences), then a 1 for the bias column; products are exact and accumulate in fp32.
+          if (kp == 0) {
+            auto split = [](float v) {
+              const __half hi = __float2half_rn(v);
+              const __half lo = __float2half_rn(v - __half2float(hi));
+              return (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+            };
+            unsigned char* in16 = in16_s + s * (TN * 128);
+            *reinterpret_cast<uint4*>(in16 + sw128_off(TN, pe, 0)) = make_uint4(split(f0), split(f1), split(d0), split(d1));
+            *reinterpret_cast<uint4*>(in16 + sw128_off(TN, pe, 8)) = make_uint4(split(d2), split(d3), 0x00003c00u, 0u);   // 1.0, 0
+          }
+        } else if constexpr (!BF16) {
           // f16 mode: packed half2 math, two channels per instruction, results land directly in operand format.
           // (inputs and weights rounded to fp16, fp16 accumulation of 3 / 5 terms: the result is rounded to
           // fp16 for the tensor core anyway)
@@ -438,6 +492,25 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
           const uint32_t off = sw128_off(TN, pe, k0);
           *reinterpret_cast<uint4*>(buf0 + off) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
           *reinterpret_cast<uint4*>(buf1 + off) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+        }
+      }
+      if constexpr (MMA_FIRST) {
+        publish_and_issue(2);
+        mbar_wait(done, done_parity); done_parity ^= 1;
+        tc_fence_after();
+        // x = relu(X) -> buf0, hp = relu(HP) -> buf1, both MN-major ([channel][edge]: this thread's rows)
+        unsigned char* const hp_row = buf1 + (t >> 3) * (8 * U_ROW) + (t & 7) * U_ROW;
+#pragma unroll 1
+        for (int cg = 0; cg < TN / 8; ++cg) {
+          float xa[8], ha[8];
+          tmem_ld8(t0 + cg * 8, xa);
+          tmem_ld8(t1 + cg * 8, ha);
+          tmem_ld_wait();
+          const uint32_t o16 = ((uint32_t)cg ^ u_xor) << 4;
+          *reinterpret_cast<uint4*>(u_row + o16) = make_uint4(pack2_relu<BF16>(xa[0], xa[1]), pack2_relu<BF16>(xa[2], xa[3]),
+                                                              pack2_relu<BF16>(xa[4], xa[5]), pack2_relu<BF16>(xa[6], xa[7]));
+          *reinterpret_cast<uint4*>(hp_row + o16) = make_uint4(pack2_relu<BF16>(ha[0], ha[1]), pack2_relu<BF16>(ha[2], ha[3]),
+                                                               pack2_relu<BF16>(ha[4], ha[5]), pack2_relu<BF16>(ha[6], ha[7]));
         }
       }
       publish_and_issue(0);
@@ -582,6 +655,7 @@ static int launch_tc(const EncEdgeArgs& a, const unsigned char* w_img, const cns
   TcArgs ta;
   ta.e = a;
   ta.w_img = w_img;
+  ta.w_first = h->tc_w_img + 2 * TC_NW * TC_W_BYTES;
   ta.n_tiles = ceil_div(a.n_e01, TN);
   int grid, tpc;
   tc_chunking(a.n_e01, TN, SLOTS, h->sm_count, &grid, &tpc);
@@ -625,7 +699,7 @@ int tc_piece_edges(int64_t n_e01, const cns_handle* h) {
 }
 
 int tc_pack_weights(cns_handle* h, cudaStream_t s) {
-  if (!h->tc_w_img) CNS_CUDA_CHECK(cudaMalloc(&h->tc_w_img, 2 * TC_NW * TC_W_BYTES));
+  if (!h->tc_w_img) CNS_CUDA_CHECK(cudaMalloc(&h->tc_w_img, 2 * TC_NW * TC_W_BYTES + TC_FIRST_W_BYTES));
   const int total = TC_NW * 128 * 128;
   tc_pack_weights_kernel<true><<<ceil_div(total, 256), 256, 0, s>>>(h->pk.tc_chain, h->tc_w_img);
   CNS_LAUNCH_CHECK();
@@ -644,6 +718,21 @@ int tc_pack_weights(cns_handle* h, cudaStream_t s) {
     sw->w[k][0] = make_float4(w_in[2 * k], w_in[2 * k + 1], b_in[k], b_p0[k]);
     sw->w[k][1] = make_float4(w_p0[4 * k], w_p0[4 * k + 1], w_p0[4 * k + 2], w_p0[4 * k + 3]);
   }
+  // first-layer A tile of the f16 tensor-core path (tc_mma_first): row = channel, k 0..15 = in_enc against the input
+  // columns [f0 hi, f0 lo, f1 hi, f1 lo, dpos 0..3 hi/lo, 1, 0, 0, 0], k 16..31 = pos_nn.0 against the same columns
+  static unsigned short first[TC_FIRST_W_BYTES / 2];
+  memset(first, 0, sizeof(first));
+  auto put = [&](int o, int k, float v) {
+    first[sw128_off(128, o, k) / 2] = __half_as_ushort(__float2half_rn(v));
+  };
+  for (int o = 0; o < 128; ++o) {
+    put(o, 0, w_in[2 * o]); put(o, 1, w_in[2 * o]); put(o, 2, w_in[2 * o + 1]); put(o, 3, w_in[2 * o + 1]);
+    put(o, 12, b_in[o]);
+    for (int i = 0; i < 4; ++i) { put(o, 16 + 4 + 2 * i, w_p0[4 * o + i]); put(o, 16 + 5 + 2 * i, w_p0[4 * o + i]); }
+    put(o, 16 + 12, b_p0[o]);
+  }
+  CNS_CUDA_CHECK(cudaMemcpyAsync(h->tc_w_img + 2 * TC_NW * TC_W_BYTES, first, sizeof(first), cudaMemcpyHostToDevice, s));
+  CNS_CUDA_CHECK(cudaStreamSynchronize(s));
   return CNS_OK;
 }
 

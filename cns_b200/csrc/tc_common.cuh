@@ -161,4 +161,13 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   }
 }
 
+// max(., 0) and the 16-bit conversion in one instruction
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
+  uint32_t r;
+  if (BF16) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 }  // namespace cns

@@ -67,6 +67,9 @@ class BatchedServo(object):
         self.hidden = [torch.zeros(self.Cn, 128, device=self.dev), torch.zeros(self.Cn, 128, device=self.dev)]
         self.cur, self.have_hidden = 0, False
         self.hidden_ready = None                           # event: the newest hidden state is complete
+        self.done_ev = [torch.cuda.Event() for _ in D]
+        self._slot_cache = [None] * self.depth
+        self._p_member_order, self._p_member_ptr = _lib.ptr(self.member_order), _lib.ptr(self.member_ptr)
         self.h2d_bytes = self.N * 2 * 4 + self.N
         self.d2h_bytes = self.B * 6 * 4
 
@@ -127,7 +130,7 @@ class BatchedServo(object):
         st.wait_stream(torch.cuda.current_stream(dev))  # whatever the caller enqueued (new weights, ...) comes first
         stream = st.cuda_stream
         vis = visible.view(torch.uint8) if visible.dtype == torch.bool else visible
-        n01 = int(torch.count_nonzero(vis))
+        n01 = int(np.count_nonzero(vis.numpy())) if not vis.is_cuda else int(torch.count_nonzero(vis))
         with torch.cuda.stream(self.copy_stream):
             self.xy_dev[k].copy_(cur_xy, non_blocking=True)
             self.vis_dev[k].copy_(vis, non_blocking=True)
@@ -135,44 +138,53 @@ class BatchedServo(object):
         st.wait_event(self.copied[k])
         if self.have_hidden and self.hidden_ready is not None:
             st.wait_event(self.hidden_ready)
-        xy, visd = self.xy_dev[k], self.vis_dev[k]
-        e01_j, e01_i, cmask, clu_rowptr, mask_ws = self.e01_j[k], self.e01_i[k], self.cmask[k], self.clu_rowptr[k], self.mask_ws[k]
-        L.check(lib.cns_frame_mask(L.ptr(self.member_order), L.ptr(self.member_ptr), L.ptr(visd), self.N, self.Cn,
-                                   L.ptr(e01_j), L.ptr(e01_i), L.ptr(cmask), L.ptr(clu_rowptr),
-                                   L.ptr(mask_ws), mask_ws.numel(), stream), "cns_frame_mask")
-        b = L.cns_batch()
-        b.n_nodes, b.n_clusters, b.n_graphs = self.N, self.Cn, self.B
-        b.n_e01, b.n_e11_cur, b.n_e11_tar = n01, 0, 0
-        p = lambda t: t.data_ptr()
-        b.x_cur, b.pos_cur, b.x_tar, b.pos_tar = p(xy), p(xy), p(self.x_tar), p(self.x_tar)
-        b.l0_to_l1_j, b.l0_to_l1_i = p(e01_j), p(e01_i)
-        b.l1_edge_cur, b.l1_edge_tar = None, None               # both cluster graphs are implied (complete)
-        b.l1_cur_stride, b.l1_tar_stride = 0, 0
-        b.cluster_mask, b.cluster_centers = p(cmask), p(self.centers)
-        b.node_graph, b.num_clusters, b.tPo_norm = None, p(self.num_clusters), p(self.tpo)
-        b.flags = L.BATCH_L1_CUR_COMPLETE | L.BATCH_L1_TAR_COMPLETE
-        b.max_clusters_per_graph = self.max_clusters
         h = self.net._handle(dev)
+        b, ptrs = self._slot_batch(k)
+        b.n_e01 = n01
         b.target_cache = self._target_cache(h)
-        b.clu_rowptr = p(clu_rowptr)
+        L.check(lib.cns_frame_mask(self._p_member_order, self._p_member_ptr, ptrs["vis"], self.N, self.Cn,
+                                   ptrs["e01_j"], ptrs["e01_i"], ptrs["cmask"], ptrs["clu_rowptr"],
+                                   ptrs["mask_ws"], self.mask_ws[k].numel(), stream), "cns_frame_mask")
         ws = self.net._workspace(dev.index, lib.cns_forward_workspace_bytes(C.byref(b)), ("fwd", stream))
         B = self.B
-        out = self.out[k]
-        vec, vel, nrm = out[:B * 6], out[B * 6:B * 12], out[B * 12:]
         hin = self.hidden[self.cur] if self.have_hidden else None
         hout = self.hidden[self.cur ^ 1]
-        L.check(lib.cns_graphvs_forward(h.raw, C.byref(b), L.ptr(hin), L.ptr(vec), L.ptr(nrm), L.ptr(hout), L.ptr(vel),
+        L.check(lib.cns_graphvs_forward(h.raw, C.byref(b), L.ptr(hin), ptrs["vec"], ptrs["nrm"], L.ptr(hout), ptrs["vel"],
                                         L.ptr(ws), ws.numel(), None, 0, C.c_void_p(stream)), "cns_graphvs_forward")
         self.cur ^= 1
         self.have_hidden = True
         with torch.cuda.stream(st):
-            self.vel_host[k].copy_(vel.view(B, 6), non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(st)
+            self.vel_host[k].copy_(self.out[k][B * 6:B * 12].view(B, 6), non_blocking=True)
+            ev = self.done_ev[k]
+            ev.record(st)
         self.done[k] = ev
         self.hidden_ready = ev
         self.ticket += 1
         return self.ticket - 1
+
+    def _slot_batch(self, k):
+        """cns_batch of slot k (everything but n_e01 and the target cache is fixed) and the raw pointers of its buffers."""
+        if self._slot_cache[k] is None:
+            L, B = _lib, self.B
+            p = lambda t: t.data_ptr()
+            xy, out = self.xy_dev[k], self.out[k]
+            b = L.cns_batch()
+            b.n_nodes, b.n_clusters, b.n_graphs = self.N, self.Cn, self.B
+            b.n_e11_cur, b.n_e11_tar = 0, 0
+            b.x_cur, b.pos_cur, b.x_tar, b.pos_tar = p(xy), p(xy), p(self.x_tar), p(self.x_tar)
+            b.l0_to_l1_j, b.l0_to_l1_i = p(self.e01_j[k]), p(self.e01_i[k])
+            b.l1_edge_cur, b.l1_edge_tar = None, None               # both cluster graphs are implied (complete)
+            b.l1_cur_stride, b.l1_tar_stride = 0, 0
+            b.cluster_mask, b.cluster_centers = p(self.cmask[k]), p(self.centers)
+            b.node_graph, b.num_clusters, b.tPo_norm = None, p(self.num_clusters), p(self.tpo)
+            b.flags = L.BATCH_L1_CUR_COMPLETE | L.BATCH_L1_TAR_COMPLETE
+            b.max_clusters_per_graph = self.max_clusters
+            b.clu_rowptr = p(self.clu_rowptr[k])
+            ptrs = {"vis": L.ptr(self.vis_dev[k]), "e01_j": L.ptr(self.e01_j[k]), "e01_i": L.ptr(self.e01_i[k]),
+                    "cmask": L.ptr(self.cmask[k]), "clu_rowptr": L.ptr(self.clu_rowptr[k]), "mask_ws": L.ptr(self.mask_ws[k]),
+                    "vec": L.ptr(out[:B * 6]), "vel": L.ptr(out[B * 6:B * 12]), "nrm": L.ptr(out[B * 12:])}
+            self._slot_cache[k] = (b, ptrs)
+        return self._slot_cache[k]
 
     def result(self, ticket: int) -> torch.Tensor:
         """Velocities (B, 6) of a submitted frame, in pinned host memory (valid until `depth` more submits)."""
