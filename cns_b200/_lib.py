@@ -12,6 +12,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcns_sm100.so")
+if os.environ.get("CNS_LIB"):           # another build of the same library (A-B runs, scripts/build_variant.sh)
+    LIB_PATH = os.path.abspath(os.environ["CNS_LIB"])
 
 CNS_OK = 0
 PREC_FP32, PREC_F16, PREC_BF16 = 0, 1, 2

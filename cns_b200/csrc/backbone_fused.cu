@@ -40,6 +40,14 @@ constexpr int VB_C0 = 0, VB_C0FC = 256, VB_G = 384, VB_K = 896, VB_C1 = 1152, VB
 constexpr size_t BF_SMEM = 65536 /*A*/ + BF_RING * BF_ATOM /*ring*/ + 128 * BF_LD * 4 /*staging*/ + 3 * BF_NVEC * 4 +
                            BF_MAX_ATOMS * 16 + 1024 /*bars, tables*/ + 1024 /*alignment slack*/;
 
+#ifdef BF_TIMELINE
+// A-B / debugging builds only (scripts/build_variant.sh ... -DBF_TIMELINE): clock64 stamps of tile 0's worker thread 0
+__device__ long long g_bf_timeline[64];
+#define BF_MARK(i) do { if (blockIdx.x == 0 && tid == 0) g_bf_timeline[i] = clock64(); } while (0)
+#else
+#define BF_MARK(i) do { } while (0)
+#endif
+
 struct BfAtom { const unsigned char* src; int meta; int pad; };   // meta: g | nc << 4 | kc << 8 | first << 12 | last << 13
 
 template <bool BF16>
@@ -71,22 +79,13 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
   const bool has_h = p.hidden_in != nullptr;
   const int kh = has_h ? 4 : 2;                                // k-chunks of the two GRU products
 
+  BF_MARK(0);
   // ---- per-tile tables ---------------------------------------------------------------------------------
   for (int k = tid; k <= G; k += BF_THREADS) g_beg[k] = p.graph_ptr[g0 + k] - row0;
   for (int r = tid; r < 128; r += BF_THREADS) alive_s[r] = (r < R && p.mask[row0 + r]) ? 1 : 0;
-  for (int i = tid; i < BF_NVEC; i += BF_THREADS) {
-    const float* b; const float* wp; int j, n;
-    if (i < VB_C0FC) { b = p.c0_b; wp = p.c0_wp; j = i; n = 256; }
-    else if (i < VB_G) { b = p.c0fc_b; wp = nullptr; j = i - VB_C0FC; n = 128; }
-    else if (i < VB_K) { b = p.g_b; wp = p.g_wp; j = i - VB_G; n = 512; }
-    else if (i < VB_C1) { b = p.k_b; wp = p.k_wp; j = i - VB_K; n = 256; }
-    else if (i < VB_C1FC) { b = p.c1_b; wp = p.c1_wp; j = i - VB_C1; n = 256; }
-    else if (i < VB_OUT) { b = p.c1fc_b; wp = nullptr; j = i - VB_C1FC; n = 128; }
-    else { b = p.out_b; wp = nullptr; j = i - VB_OUT; n = 128; }
-    vec[i] = b[j];
-    vec[BF_NVEC + i] = wp ? wp[j] : 0.f;
-    vec[2 * BF_NVEC + i] = wp ? wp[n + j] : 0.f;
-  }
+  // per-column epilogue vectors [bias | wp row 0 | wp row 1] of all GEMMs: packed once per weight load (bf_pack_vec)
+  for (int i = tid; i < 3 * BF_NVEC / 4; i += BF_THREADS)
+    reinterpret_cast<float4*>(vec)[i] = reinterpret_cast<const float4*>(p.vec_tab)[i];
   if (warp == BF_WORKER_WARPS) {
     if (lane == 0) {
       for (int i = 0; i < 16; ++i) mbar_init(smem_u32(&bars[i]), 1);
@@ -130,13 +129,6 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     int li = BF_RING;
     for (int mi = 0; mi < n_atoms; ++mi) {
       const int meta = atoms[mi].meta;
-      if (lane == 0 && mi >= 1 && li < n_atoms) {   // refill the slot of the previous atom once its MMAs have drained
-        const int ps = (mi - 1) % BF_RING;
-        mbar_wait(smem_u32(&bars[4 + ps]), (uint32_t)(((mi - 1) / BF_RING) & 1));
-        mbar_expect_tx(smem_u32(&bars[ps]), BF_ATOM);
-        bulk_g2s(smem_u32(ring + ps * BF_ATOM), atoms[li].src, BF_ATOM, smem_u32(&bars[ps]));
-        ++li;
-      }
       if (meta & (1 << 12)) {                   // first atom of a GEMM: wait until its A operand is published
         __syncwarp();
         named_bar(2, BF_THREADS);
@@ -154,6 +146,16 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
                    (kc | ks) ? 1u : 0u);
         umma_commit(smem_u32(&bars[4 + slot]));
         if (meta & (1 << 13)) umma_commit(smem_u32(&bars[8 + g]));
+        // refill the slot of the PREVIOUS atom once its MMAs have drained - after this atom's MMAs are queued, so the
+        // tensor pipe keeps working while the completion of the previous group is awaited (waiting first serialised
+        // issue -> completion -> issue: ~760 cycles per atom against ~270 of MMA work)
+        if (mi >= 1 && li < n_atoms) {
+          const int ps = (mi - 1) % BF_RING;
+          mbar_wait(smem_u32(&bars[4 + ps]), (uint32_t)(((mi - 1) / BF_RING) & 1));
+          mbar_expect_tx(smem_u32(&bars[ps]), BF_ATOM);
+          bulk_g2s(smem_u32(ring + ps * BF_ATOM), atoms[li].src, BF_ATOM, smem_u32(&bars[ps]));
+          ++li;
+        }
       }
       __syncwarp();
     }
@@ -183,35 +185,41 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
       *reinterpret_cast<uint4*>(a_s + sw128_off(128, row, acol)) =
           make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7]));
     };
-    // ---- inputs: this thread's columns of the two encoder feature rows -> A = [cur | tar - cur] (out_enc,
-    //      graph_vs.py:229-230) ; its h row -> fp32 stash S2 --------------------------------------------------
+    // ---- inputs -> A = [cur | tar - cur] (out_enc, graph_vs.py:229-230) ; h -> staging (fp32) -----------------------
+    // Coalesced: a warp reads one 512-byte row per instruction (lane = 4 columns), 8 rows per warp; thread = row loads
+    // (32 sectors per instruction) kept the load/store unit saturated for ~14 us per tile.
     {
-      float xv[BF_GROUPS][8], dv[BF_GROUPS][8], hv[BF_GROUPS][8];
       const float* tar = p.clu_feat + (size_t)p.n_clusters * 128;
+      constexpr int RPW = 128 / BF_WORKER_WARPS;       // rows per warp
+      float4 xv[RPW], dv[RPW], hv[RPW];
 #pragma unroll
-      for (int cg = 0; cg < BF_GROUPS; ++cg) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { xv[cg][i] = 0.f; dv[cg][i] = 0.f; hv[cg][i] = 0.f; }
-        if (live) {
-          load8(p.clu_feat + grow * 128 + half * BF_SLICE_COLS + cg * 8, xv[cg]);
-          load8(tar + grow * 128 + half * BF_SLICE_COLS + cg * 8, dv[cg]);
-          if (has_h) load8(p.hidden_in + grow * 128 + half * BF_SLICE_COLS + cg * 8, hv[cg]);
+      for (int i = 0; i < RPW; ++i) {
+        const int r = warp + i * BF_WORKER_WARPS;
+        xv[i] = dv[i] = hv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < R) {
+          const size_t o = (size_t)(row0 + r) * 128 + lane * 4;
+          xv[i] = *reinterpret_cast<const float4*>(p.clu_feat + o);
+          dv[i] = *reinterpret_cast<const float4*>(tar + o);
+          if (has_h) hv[i] = *reinterpret_cast<const float4*>(p.hidden_in + o);
         }
       }
 #pragma unroll
-      for (int cg = 0; cg < BF_GROUPS; ++cg) {
-        const int c = half * BF_SLICE_COLS + cg * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dv[cg][i] -= xv[cg][i];
-        store_a8(c, xv[cg]);
-        store_a8(128 + c, dv[cg]);
-        if (has_h) tmem_st8(t_lane + (uint32_t)(S2 + c), hv[cg]);
+      for (int i = 0; i < RPW; ++i) {
+        const int r = warp + i * BF_WORKER_WARPS;
+        *reinterpret_cast<uint2*>(a_s + sw128_off(128, r, lane * 4)) =
+            make_uint2(pack2<BF16>(xv[i].x, xv[i].y), pack2<BF16>(xv[i].z, xv[i].w));
+        *reinterpret_cast<uint2*>(a_s + sw128_off(128, r, 128 + lane * 4)) =
+            make_uint2(pack2<BF16>(dv[i].x - xv[i].x, dv[i].y - xv[i].y), pack2<BF16>(dv[i].z - xv[i].z, dv[i].w - xv[i].w));
+        if (has_h) {
+          float* d = stg + r * BF_LD + lane * 4;
+          d[0] = hv[i].x; d[1] = hv[i].y; d[2] = hv[i].z; d[3] = hv[i].w;
+        }
       }
-      tmem_st_wait();
     }
-
-    auto wait_done = [&](int g) { mbar_wait(smem_u32(&bars[8 + g]), 0); tc_fence_after(); };
-    auto publish_a = [&]() { fence_proxy_async(); tc_fence_before(); named_bar(2, BF_THREADS); };
+    BF_MARK(1);      // inputs loaded, A tile of out_enc written
+    auto wait_done = [&](int g) { mbar_wait(smem_u32(&bars[8 + g]), 0); tc_fence_after(); BF_MARK(2 + 2 * g); };
+    int bf_stage = 0;
+    auto publish_a = [&]() { fence_proxy_async(); tc_fence_before(); BF_MARK(3 + 2 * (bf_stage - 1) + (bf_stage == 0 ? 30 : 0)); ++bf_stage; named_bar(2, BF_THREADS); };
     // The epilogues walk this thread's 64 columns of a 128-column TMEM chunk in 8 trips of 8 columns (runtime
     // loops: the whole chain is executed once per tile, so a small instruction footprint matters more than
     // unrolling).  v[i] = accumulator + bias + pos . wp for vector index vi + i.
@@ -358,11 +366,12 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
       for (int i = 0; i < 8; ++i) y[i] = alive ? fmaxf(acc[i] + bb[i], 0.f) : 0.f;
       store_a8(c, y);
       tmem_st8(t_lane + (uint32_t)(S1 + c), y);
-      if (has_h) {
+      if (has_h) {               // h: staging (prologue) -> fp32 stash S2 + A k-chunks 2,3
         float hv[8];
-        tmem_ld8(t_lane + (uint32_t)(S2 + c), hv);
-        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hv[i] = srow[c + i];
         store_a8(128 + c, hv);
+        tmem_st8(t_lane + (uint32_t)(S2 + c), hv);
       }
     }
     tmem_st_wait();
@@ -429,11 +438,46 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     publish_a();
     wait_done(7);
     fc_epilogue(VB_C1FC, S2, false, p.x2);
+    BF_MARK(17);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (warp == BF_WORKER_WARPS) tmem_dealloc(tmem_base, 512);
+}
+
+#ifdef BF_TIMELINE
+extern "C" int cns_bf_timeline(long long* out) {
+  return cudaMemcpyFromSymbol(out, g_bf_timeline, sizeof(g_bf_timeline)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
+__global__ void bf_pack_vec_kernel(BackboneFusedArgs p, float* __restrict__ vec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BF_NVEC) return;
+  const float* b; const float* wp; int j, n;
+  if (i < VB_C0FC) { b = p.c0_b; wp = p.c0_wp; j = i; n = 256; }
+  else if (i < VB_G) { b = p.c0fc_b; wp = nullptr; j = i - VB_C0FC; n = 128; }
+  else if (i < VB_K) { b = p.g_b; wp = p.g_wp; j = i - VB_G; n = 512; }
+  else if (i < VB_C1) { b = p.k_b; wp = p.k_wp; j = i - VB_K; n = 256; }
+  else if (i < VB_C1FC) { b = p.c1_b; wp = p.c1_wp; j = i - VB_C1; n = 256; }
+  else if (i < VB_OUT) { b = p.c1fc_b; wp = nullptr; j = i - VB_C1FC; n = 128; }
+  else { b = p.out_b; wp = nullptr; j = i - VB_OUT; n = 128; }
+  vec[i] = b[j];
+  vec[BF_NVEC + i] = wp ? wp[j] : 0.f;
+  vec[2 * BF_NVEC + i] = wp ? wp[n + j] : 0.f;
+}
+
+// per-column epilogue vectors of the fused kernel, rebuilt with every weight (re)pack
+int bf_pack_vec(cns_handle* h, cudaStream_t s) {
+  if (!h->pk.bf_vec) CNS_CUDA_CHECK(cudaMalloc(&h->pk.bf_vec, 3 * BF_NVEC * sizeof(float)));
+  BackboneFusedArgs a{};
+  const Packed& pk = h->pk;
+  a.c0_b = pk.c0_b; a.c0_wp = pk.c0_wp; a.g_b = pk.g_b; a.g_wp = pk.g_wp; a.k_b = pk.k_b; a.k_wp = pk.k_wp;
+  a.c1_b = pk.c1_b; a.c1_wp = pk.c1_wp; a.c0fc_b = h->P(P_C0_FC_B); a.c1fc_b = h->P(P_C1_FC_B); a.out_b = h->P(P_OUT_B);
+  bf_pack_vec_kernel<<<ceil_div(BF_NVEC, 256), 256, 0, s>>>(a, h->pk.bf_vec);
+  CNS_LAUNCH_CHECK();
+  return CNS_OK;
 }
 
 int backbone_fused(const BackboneFusedArgs& a, bool bf16, cudaStream_t s) {

@@ -92,6 +92,7 @@ struct Packed {
   unsigned char* tc2_c0; unsigned char* tc2_c0_fc; unsigned char* tc2_g; unsigned char* tc2_k;
   unsigned char* tc2_c1; unsigned char* tc2_c1_fc; unsigned char* tc2_out;
   unsigned char* tc2_base;
+  float* bf_vec;         // [3][1664] per-column epilogue vectors of the fused backbone kernel (bias | wp row 0 | wp row 1)
 };
 
 }  // namespace cns

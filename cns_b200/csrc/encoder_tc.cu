@@ -33,6 +33,9 @@
 namespace cns {
 
 constexpr int TC_W_BYTES = 128 * 128 * 2;         // one weight matrix, 16-bit
+#ifndef TC_NPRE
+#define TC_NPRE 2
+#endif
 constexpr int TC_NW = 5;                          // pos_nn.1, -(A0 lin_src), lin, A0 pos_nn.1, attn_nn.1
 
 // ---- weight image: fp32 (k-major "chain" [5][k][o]) -> 16-bit swizzled A-operand tiles ----------
@@ -108,7 +111,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
   constexpr int TMEM_W_COL0 = SLOTS * 2 * TN;
   static_assert(TMEM_W_COL0 + TMEM_W * 64 <= 512, "tensor memory budget");
   constexpr int U_ROW = TN * 2;                      // bytes per channel row of the MN-major u tile
-  constexpr int NPRE = 4;                            // a' rows prefetched per tile (first NPRE segment starts)
+  constexpr int NPRE = TC_NPRE;                      // a' rows prefetched per tile (first NPRE segment starts)
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment: align by hand (1 KB of slack is allocated)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);

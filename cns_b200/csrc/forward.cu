@@ -297,7 +297,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     fa.c1_b = pk.c1_b; fa.c1_wp = pk.c1_wp; fa.c0fc_b = h->P(P_C0_FC_B); fa.c1fc_b = h->P(P_C1_FC_B);
     fa.gn0_w = h->P(P_C0_BN_W); fa.gn0_b = h->P(P_C0_BN_B); fa.gn0_ms = h->P(P_C0_BN_MS);
     fa.gn1_w = h->P(P_C1_BN_W); fa.gn1_b = h->P(P_C1_BN_B); fa.gn1_ms = h->P(P_C1_BN_MS);
-    fa.hidden_out = hidden_out; fa.x2 = f.x2;
+    fa.vec_tab = pk.bf_vec; fa.hidden_out = hidden_out; fa.x2 = f.x2;
     RUN(backbone_fused(fa, tci == 0, s));
   } else {
   RUN(perconv(f.x_clu, pk.c0_wt, pk.c0_wp, pk.c0_b, P_C0_BN_W, P_C0_BN_B, P_C0_BN_MS, pk.c0_fc_t, P_C0_FC_B, f.x1, pk.tc_c0, pk.tc_c0_fc, f.conv0, f.gn0, f.stats0, f.arg0, pk.tc2_c0, pk.tc2_c0_fc));

@@ -209,6 +209,7 @@ int repack(cns_handle* h, cudaStream_t s) {
     for (auto& it : items)
       if ((rc = gemm_tc_split_pack(it.wt, it.k, it.n, *split_dst[i++], s)) != CNS_OK) return rc;
   }
+  if ((rc = bf_pack_vec(h, s)) != CNS_OK) return rc;
   h->weights_loaded = true;
   ++h->weights_version;
   return CNS_OK;
@@ -294,6 +295,7 @@ int cns_destroy(cns_handle* h) {
   if (h->tc_w_split) cudaFree(h->tc_w_split);
   if (h->pk.tc_node_base) cudaFree(h->pk.tc_node_base);
   if (h->pk.tc2_base) cudaFree(h->pk.tc2_base);
+  if (h->pk.bf_vec) cudaFree(h->pk.bf_vec);
   graph_cache_clear(h);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->servo_tcache) cns_target_cache_destroy(h->servo_tcache);

@@ -167,8 +167,10 @@ struct BackboneFusedArgs {
   const float* c0_b; const float* c0_wp; const float* g_b; const float* g_wp; const float* k_b; const float* k_wp;
   const float* c1_b; const float* c1_wp; const float* c0fc_b; const float* c1fc_b;
   const float* gn0_w; const float* gn0_b; const float* gn0_ms; const float* gn1_w; const float* gn1_b; const float* gn1_ms;
+  const float* vec_tab;                           // (3, 1664) per-column epilogue vectors (bf_pack_vec)
   float* hidden_out; float* x2;
 };
+int bf_pack_vec(cns_handle* h, cudaStream_t s);
 int backbone_fused(const BackboneFusedArgs& a, bool bf16, cudaStream_t s);
 
 struct GraphNormArgs {
