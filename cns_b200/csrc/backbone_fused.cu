@@ -14,7 +14,7 @@
 // Activations never leave the SM between the layers: the A operand (16-bit, K-major SWIZZLE_128B) is
 // rebuilt in shared memory by every epilogue, accumulators live in TMEM, the per-graph reductions go
 // through one fp32 staging tile (thread = row writes, thread = column reduces, conflict-free with a
-// 129-float row pitch).  Weights stream from L2 as 16 KB atoms (128 outputs x 64 k) through a 4-deep
+// 132-float row pitch).  Weights stream from L2 as 16 KB atoms (128 outputs x 64 k) through a 4-deep
 // TMA ring that runs ahead across GEMM boundaries.  Warps 0-7: epilogues (warp % 4 = TMEM lane quarter,
 // warp / 4 = column slice of each 128-column chunk); the last warp: TMA + MMA issue.
 #include "common.cuh"
@@ -31,7 +31,7 @@ constexpr int BF_SLICE_COLS = 128 / BF_SLICES;
 constexpr int BF_GROUPS = BF_SLICE_COLS / 8;            // 8-column trips per thread
 constexpr int BF_ATOM = 128 * 128;        // bytes: 128 output rows x 64 k x 2 B
 constexpr int BF_RING = 4;
-constexpr int BF_LD = 129;                // staging row pitch (floats)
+constexpr int BF_LD = 132;                // staging row pitch (floats): 16-byte aligned rows; float4 accesses are conflict-free by row AND by column
 constexpr int BF_NVEC = 1664;             // per-column epilogue vectors of the GEMMs, concatenated
 constexpr int BF_MAX_ATOMS = 48;
 // vector bases of the six GEMMs inside the concatenation
@@ -68,6 +68,7 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
   int* n_atoms_s = reinterpret_cast<int*>(tail + 136);
   int* g_beg = reinterpret_cast<int*>(tail + 144);             // [<=129] local first row of the tile's graphs
   unsigned char* alive_s = tail + 144 + 132 * 4;               // [128]
+  unsigned char* g_first = alive_s + 128;                      // [128] local first row of the graph a row belongs to
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -83,6 +84,10 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
   // ---- per-tile tables ---------------------------------------------------------------------------------
   for (int k = tid; k <= G; k += BF_THREADS) g_beg[k] = p.graph_ptr[g0 + k] - row0;
   for (int r = tid; r < 128; r += BF_THREADS) alive_s[r] = (r < R && p.mask[row0 + r]) ? 1 : 0;
+  for (int k = tid; k < G; k += BF_THREADS) {
+    const int rb = p.graph_ptr[g0 + k] - row0, re = p.graph_ptr[g0 + k + 1] - row0;
+    for (int r = rb; r < re; ++r) g_first[r] = (unsigned char)rb;
+  }
   // per-column epilogue vectors [bias | wp row 0 | wp row 1] of all GEMMs: packed once per weight load (bf_pack_vec)
   for (int i = tid; i < 3 * BF_NVEC / 4; i += BF_THREADS)
     reinterpret_cast<float4*>(vec)[i] = reinterpret_cast<const float4*>(p.vec_tab)[i];
@@ -168,9 +173,9 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     const int64_t grow = (int64_t)row0 + (live ? row : 0);
     const float2 ps = live ? reinterpret_cast<const float2*>(p.pos_clu)[grow] : make_float2(0.f, 0.f);
     const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16);
-    const int col = tid & 127, chalf = tid >> 7;     // column-phase identity: column, graph slot
     const float* vb = vec; const float* vw0 = vec + BF_NVEC; const float* vw1 = vec + 2 * BF_NVEC;
     float* srow = stg + row * BF_LD;
+    const float* mrow = stg + (live ? (int)g_first[row] : 0) * BF_LD;   // first row of this row's graph: where the column maxima land
     constexpr int S1 = 256, S2 = 384;                // TMEM stashes (fp32 rows): x then u ; h then h'
 
     auto load8 = [&](const float* src, float (&v)[8]) {
@@ -184,6 +189,10 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     auto store_a8 = [&](int acol, const float (&v)[8]) {     // 8 consecutive k of this thread's A row
       *reinterpret_cast<uint4*>(a_s + sw128_off(128, row, acol)) =
           make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7]));
+    };
+    auto rows_to_global = [&](float* out) {                // staging rows [0, R) -> out rows [row0, row0 + R)
+      for (int r = warp; r < R; r += BF_WORKER_WARPS)
+        *reinterpret_cast<float4*>(out + (size_t)(row0 + r) * 128 + lane * 4) = *reinterpret_cast<const float4*>(stg + r * BF_LD + lane * 4);
     };
     // ---- inputs -> A = [cur | tar - cur] (out_enc, graph_vs.py:229-230) ; h -> staging (fp32) -----------------------
     // Coalesced: a warp reads one 512-byte row per instruction (lane = 4 columns), 8 rows per warp; thread = row loads
@@ -211,8 +220,7 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
         *reinterpret_cast<uint2*>(a_s + sw128_off(128, r, 128 + lane * 4)) =
             make_uint2(pack2<BF16>(dv[i].x - xv[i].x, dv[i].y - xv[i].y), pack2<BF16>(dv[i].z - xv[i].z, dv[i].w - xv[i].w));
         if (has_h) {
-          float* d = stg + r * BF_LD + lane * 4;
-          d[0] = hv[i].x; d[1] = hv[i].y; d[2] = hv[i].z; d[3] = hv[i].w;
+          *reinterpret_cast<float4*>(stg + r * BF_LD + lane * 4) = hv[i];
         }
       }
     }
@@ -243,40 +251,46 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
         tmem_ld8(t_lane + (uint32_t)(dcol + c), acc);
         tmem_ld_wait();
         lin8(acc, vbase + c, o);
-        if (live) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) srow[c + i] = o[i];
-        }
+        if (live) store8(srow + c, o);
       }
     };
-    // per graph: max over the node set (all rows, or rows with mask) of staging column `col`, broadcast in place
-    auto colmax_broadcast = [&](bool use_mask) {
-      for (int k = chalf; k < G; k += BF_SLICES) {
+    // Column passes: a warp owns a graph at a time (graphs warp, warp + 16, ...), a lane four adjacent columns, so a warp
+    // reads one 512-byte staging row per instruction.
+    // per graph: max over the node set (all rows, or rows with mask), left in the graph's FIRST row (row threads read it
+    // through `mrow`) or written to every row of the graph (epilogues that go on to overwrite their own row)
+    auto max4 = [](float4& m, const float4 v) { m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w); };
+    auto colmax = [&](bool use_mask, bool broadcast) {
+      for (int k = warp; k < G; k += BF_WORKER_WARPS) {
         const int rb = g_beg[k], re = g_beg[k + 1];
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        float4 m0 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), m1 = m0;
+        float* base = stg + lane * 4;
         int r = rb;
-        for (; r + 4 <= re; r += 4) {           // four independent loads in flight
-          const float a0 = stg[r * BF_LD + col], a1 = stg[(r + 1) * BF_LD + col];
-          const float a2 = stg[(r + 2) * BF_LD + col], a3 = stg[(r + 3) * BF_LD + col];
-          const uint32_t al = use_mask ? ((uint32_t)alive_s[r] | ((uint32_t)alive_s[r + 1] << 8) | ((uint32_t)alive_s[r + 2] << 16) | ((uint32_t)alive_s[r + 3] << 24)) : 0x01010101u;
-          if (al & 0x000000ffu) m0 = fmaxf(m0, a0);
-          if (al & 0x0000ff00u) m1 = fmaxf(m1, a1);
-          if (al & 0x00ff0000u) m2 = fmaxf(m2, a2);
-          if (al & 0xff000000u) m3 = fmaxf(m3, a3);
+        for (; r + 2 <= re; r += 2) {
+          const float4 a0 = *reinterpret_cast<const float4*>(base + r * BF_LD);
+          const float4 a1 = *reinterpret_cast<const float4*>(base + (r + 1) * BF_LD);
+          if (!use_mask || alive_s[r]) max4(m0, a0);
+          if (!use_mask || alive_s[r + 1]) max4(m1, a1);
         }
-        for (; r < re; ++r)
-          if (!use_mask || alive_s[r]) m0 = fmaxf(m0, stg[r * BF_LD + col]);
-        const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-#pragma unroll 4
-        for (r = rb; r < re; ++r) stg[r * BF_LD + col] = m;
+        if (r < re && (!use_mask || alive_s[r])) max4(m0, *reinterpret_cast<const float4*>(base + r * BF_LD));
+        max4(m0, m1);
+        *reinterpret_cast<float4*>(base + rb * BF_LD) = m0;
+        if (broadcast)
+          for (r = rb + 1; r < re; ++r) *reinterpret_cast<float4*>(base + r * BF_LD) = m0;
       }
     };
+    auto colmax_first = [&](bool use_mask) { colmax(use_mask, false); };
+    auto colmax_broadcast = [&](bool use_mask) { colmax(use_mask, true); };
     // PERConv tail: conv = P + max (0 for rows outside the node set) -> GraphNorm -> ReLU -> A k-chunks 0,1
     auto perconv_epilogue = [&](int vbase, const float* gw, const float* gb, const float* gms) {
+      BF_MARK(40);
       q_to_staging(128, vbase + 128);
+      BF_MARK(41);
       named_bar(1, BF_WORKERS);
+      BF_MARK(42);
       colmax_broadcast(true);
+      BF_MARK(43);
       named_bar(1, BF_WORKERS);
+      BF_MARK(44);
 #pragma unroll 2
       for (int cg = 0; cg < BF_GROUPS; ++cg) {
         const int c = half * BF_SLICE_COLS + cg * 8;
@@ -285,29 +299,45 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
         tmem_ld_wait();
         lin8(acc, vbase + c, o);
         if (live) {
+          float mx[8];
+          load8(srow + c, mx);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) srow[c + i] = alive ? o[i] + srow[c + i] : 0.f;
+          for (int i = 0; i < 8; ++i) o[i] = alive ? o[i] + mx[i] : 0.f;
+          store8(srow + c, o);
         }
       }
+      BF_MARK(45);
       named_bar(1, BF_WORKERS);
-      const float w = gw[col], b = gb[col], ms = gms[col];
-      for (int k = chalf; k < G; k += BF_SLICES) {
+      BF_MARK(46);
+      const float4 w = *reinterpret_cast<const float4*>(gw + lane * 4), b = *reinterpret_cast<const float4*>(gb + lane * 4);
+      const float4 ms = *reinterpret_cast<const float4*>(gms + lane * 4);
+      for (int k = warp; k < G; k += BF_WORKER_WARPS) {
         const int rb = g_beg[k], re = g_beg[k + 1];
         const float inv_n = 1.f / (float)(re - rb);
-        float sum = 0.f;
-#pragma unroll 4
-        for (int r = rb; r < re; ++r) sum += stg[r * BF_LD + col];
-        const float shift = sum * inv_n * ms;
-        float sq = 0.f;
-#pragma unroll 4
-        for (int r = rb; r < re; ++r) { const float o = stg[r * BF_LD + col] - shift; sq = fmaf(o, o, sq); }
-        const float rstd = 1.f / sqrtf(sq * inv_n + 1e-5f);
-#pragma unroll 4
+        const float* base = stg + lane * 4;
+        // one pass: sum and sum of squares; mean((x - s)^2) = E[x^2] - 2 s E[x] + s^2 with s = mean * mean_scale
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), sq = sum;
+#pragma unroll 2
         for (int r = rb; r < re; ++r) {
-          const float o = stg[r * BF_LD + col] - shift;
-          const float y = fmaxf(fmaf(w * o, rstd, b), 0.f);
-          const uint32_t pk = pack2<BF16>(y, 0.f);
-          *reinterpret_cast<unsigned short*>(a_s + sw128_off(128, r, col)) = (unsigned short)(pk & 0xffffu);
+          const float4 v = *reinterpret_cast<const float4*>(base + r * BF_LD);
+          sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+          sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y); sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
+        }
+        auto stat = [&](float su, float s2, float msc, float wc, float& shift, float& scale) {
+          const float mean = su * inv_n;
+          shift = mean * msc;
+          const float var = fmaxf(fmaf(shift, shift - 2.f * mean, s2 * inv_n), 0.f);
+          scale = wc / sqrtf(var + 1e-5f);
+        };
+        float4 sh, sc;
+        stat(sum.x, sq.x, ms.x, w.x, sh.x, sc.x); stat(sum.y, sq.y, ms.y, w.y, sh.y, sc.y);
+        stat(sum.z, sq.z, ms.z, w.z, sh.z, sc.z); stat(sum.w, sq.w, ms.w, w.w, sh.w, sc.w);
+#pragma unroll 2
+        for (int r = rb; r < re; ++r) {
+          const float4 v = *reinterpret_cast<const float4*>(base + r * BF_LD);
+          const float y0 = fmaxf(fmaf(v.x - sh.x, sc.x, b.x), 0.f), y1 = fmaxf(fmaf(v.y - sh.y, sc.y, b.y), 0.f);
+          const float y2 = fmaxf(fmaf(v.z - sh.z, sc.z, b.z), 0.f), y3 = fmaxf(fmaf(v.w - sh.w, sc.w, b.w), 0.f);
+          *reinterpret_cast<uint2*>(a_s + sw128_off(128, r, lane * 4)) = make_uint2(pack2<BF16>(y0, y1), pack2<BF16>(y2, y3));
         }
       }
     };
@@ -327,15 +357,16 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
         for (int i = 0; i < 8; ++i) y[i] = fmaxf(acc[i] + bb[i] + r8[i], 0.f);
         if (live) {
           if (to_a) store_a8(c, y);
-          if (out) store8(out + grow * 128 + c, y);
+          if (out) store8(srow + c, y);
         }
       }
+      if (out) { named_bar(1, BF_WORKERS); rows_to_global(out); }
     };
     // one half of the gate product: sigmoid(P + column max of Q over the whole graph) for this thread's columns
     auto gate_half = [&](int vp, int vq, auto&& sink) {
       q_to_staging(128, vq);
       named_bar(1, BF_WORKERS);
-      colmax_broadcast(false);
+      colmax_first(false);
       named_bar(1, BF_WORKERS);
 #pragma unroll 2
       for (int cg = 0; cg < BF_GROUPS; ++cg) {
@@ -344,8 +375,10 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
         tmem_ld8(t_lane + (uint32_t)c, acc);
         tmem_ld_wait();
         lin8(acc, vp + c, o);
+        float mx[8];
+        load8(mrow + c, mx);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = sigmoid_fast(o[i] + (live ? srow[c + i] : 0.f));
+        for (int i = 0; i < 8; ++i) o[i] = sigmoid_fast(o[i] + (live ? mx[i] : 0.f));
         sink(c, o);
       }
       named_bar(1, BF_WORKERS);      // staging is reused by the next epilogue
@@ -368,8 +401,7 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
       tmem_st8(t_lane + (uint32_t)(S1 + c), y);
       if (has_h) {               // h: staging (prologue) -> fp32 stash S2 + A k-chunks 2,3
         float hv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) hv[i] = srow[c + i];
+        load8(srow + c, hv);
         store_a8(128 + c, hv);
         tmem_st8(t_lane + (uint32_t)(S2 + c), hv);
       }
@@ -417,18 +449,22 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
       if (has_h) tmem_ld8(t_lane + (uint32_t)(S2 + c), hv);
       tmem_ld_wait();
       lin8(acc, VB_K + c, o);
+      float mx[8];
+      load8(srow + c, mx);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float cv = alive ? o[i] + srow[c + i] : 0.f;
+        const float cv = alive ? o[i] + mx[i] : 0.f;
         o[i] = (1.f - uu[i]) * (has_h ? hv[i] : 0.f) + uu[i] * tanh_fast(cv);
       }
       tmem_st8(t_lane + (uint32_t)(S2 + c), o);
       if (live) {
-        store8(p.hidden_out + grow * 128 + c, o);
+        store8(srow + c, o);           // in place (this thread's own row and columns)
         store_a8(c, o);
       }
     }
     tmem_st_wait();
+    named_bar(1, BF_WORKERS);
+    rows_to_global(p.hidden_out);      // coalesced: a warp writes one 512-byte row per instruction
     named_bar(1, BF_WORKERS);          // staging is reused by the next epilogue
     // ---- GEMM 6: c1 [P|Q] on h' ----------------------------------------------------------------------------
     publish_a();

@@ -31,3 +31,10 @@ prev = t[0]
 for i in order:
     print("%-34s +%7d cycles  (t=%7d)" % (names[i], t[i] - prev, t[i] - t[0]))
     prev = t[i]
+
+sub = {40: "perconv(c1): start", 41: "Q -> staging", 42: "barrier", 43: "column max + broadcast", 44: "barrier",
+       45: "P + max -> staging", 46: "barrier", 15: "GraphNorm + A tile (-> publish)"}
+prev = t[40]
+for i in (40, 41, 42, 43, 44, 45, 46, 15):
+    print("  %-32s +%7d cycles" % (sub[i], t[i] - prev))
+    prev = t[i]
