@@ -81,6 +81,9 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
   const int kh = has_h ? 4 : 2;                                // k-chunks of the two GRU products
 
   BF_MARK(0);
+#ifdef BF_TIMELINE
+  if (blockIdx.x == 0 && tid == 0) { g_bf_timeline[60] = G; g_bf_timeline[61] = R; g_bf_timeline[50] = g_bf_timeline[51] = g_bf_timeline[52] = 0; }
+#endif
   // ---- per-tile tables ---------------------------------------------------------------------------------
   for (int k = tid; k <= G; k += BF_THREADS) g_beg[k] = p.graph_ptr[g0 + k] - row0;
   for (int r = tid; r < 128; r += BF_THREADS) alive_s[r] = (r < R && p.mask[row0 + r]) ? 1 : 0;
@@ -231,10 +234,18 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     // The epilogues walk this thread's 64 columns of a 128-column TMEM chunk in 8 trips of 8 columns (runtime
     // loops: the whole chain is executed once per tile, so a small instruction footprint matters more than
     // unrolling).  v[i] = accumulator + bias + pos . wp for vector index vi + i.
+    // Table reads go through a non-volatile ld.shared (the tables are read-only after the prologue): the compiler may then
+    // hoist them above the staging / A-tile stores of the previous column group, which ordinary loads cannot pass
+    // (possible aliasing) - every group used to wait for its own six table loads behind the previous group's stores.
+    auto lds4 = [](const float* ptr) {
+      float4 v;
+      asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(ptr)));
+      return v;
+    };
     auto lin8 = [&](const float (&acc)[8], int vi, float (&o)[8]) {
-      const float4 b0 = *reinterpret_cast<const float4*>(vb + vi), b1 = *reinterpret_cast<const float4*>(vb + vi + 4);
-      const float4 x0 = *reinterpret_cast<const float4*>(vw0 + vi), x1 = *reinterpret_cast<const float4*>(vw0 + vi + 4);
-      const float4 y0 = *reinterpret_cast<const float4*>(vw1 + vi), y1 = *reinterpret_cast<const float4*>(vw1 + vi + 4);
+      const float4 b0 = lds4(vb + vi), b1 = lds4(vb + vi + 4);
+      const float4 x0 = lds4(vw0 + vi), x1 = lds4(vw0 + vi + 4);
+      const float4 y0 = lds4(vw1 + vi), y1 = lds4(vw1 + vi + 4);
       o[0] = fmaf(ps.y, y0.x, fmaf(ps.x, x0.x, acc[0] + b0.x)); o[1] = fmaf(ps.y, y0.y, fmaf(ps.x, x0.y, acc[1] + b0.y));
       o[2] = fmaf(ps.y, y0.z, fmaf(ps.x, x0.z, acc[2] + b0.z)); o[3] = fmaf(ps.y, y0.w, fmaf(ps.x, x0.w, acc[3] + b0.w));
       o[4] = fmaf(ps.y, y1.x, fmaf(ps.x, x1.x, acc[4] + b1.x)); o[5] = fmaf(ps.y, y1.y, fmaf(ps.x, x1.y, acc[5] + b1.y));
@@ -244,38 +255,51 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
     auto tanh_fast = [](float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); };
     // Q part of a [P|Q] product (TMEM columns dcol..dcol+127) -> staging
     auto q_to_staging = [&](int dcol, int vbase) {
-#pragma unroll 2
-      for (int cg = 0; cg < BF_GROUPS; ++cg) {
-        const int c = half * BF_SLICE_COLS + cg * 8;
-        float acc[8], o[8];
-        tmem_ld8(t_lane + (uint32_t)(dcol + c), acc);
+#pragma unroll 1
+      for (int cp = 0; cp < BF_GROUPS; cp += 2) {          // two TMEM loads per wait
+        float acc[2][8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) tmem_ld8(t_lane + (uint32_t)(dcol + half * BF_SLICE_COLS + (cp + j) * 8), acc[j]);
         tmem_ld_wait();
-        lin8(acc, vbase + c, o);
-        if (live) store8(srow + c, o);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = half * BF_SLICE_COLS + (cp + j) * 8;
+          float o[8];
+          lin8(acc[j], vbase + c, o);
+          if (live) store8(srow + c, o);
+        }
       }
     };
     // Column passes: a warp owns a graph at a time (graphs warp, warp + 16, ...), a lane four adjacent columns, so a warp
     // reads one 512-byte staging row per instruction.
     // per graph: max over the node set (all rows, or rows with mask), left in the graph's FIRST row (row threads read it
     // through `mrow`) or written to every row of the graph (epilogues that go on to overwrite their own row)
-    auto max4 = [](float4& m, const float4 v) { m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w); };
+    // A unit of column work = (graph, half of the 128 columns): units warp, warp + 16, ... ; a lane owns two adjacent
+    // columns, so a typical tile (6 graphs) keeps 12 of the 16 warps busy and a warp's serial walk over the rows is short.
+    auto max2 = [](float2& m, const float2 v) { m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); };
     auto colmax = [&](bool use_mask, bool broadcast) {
-      for (int k = warp; k < G; k += BF_WORKER_WARPS) {
+      for (int u = warp; u < 2 * G; u += BF_WORKER_WARPS) {
+        const int k = u >> 1;
         const int rb = g_beg[k], re = g_beg[k + 1];
-        float4 m0 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), m1 = m0;
-        float* base = stg + lane * 4;
+        float* base = stg + (u & 1) * 64 + lane * 2;
+        float2 m0 = make_float2(-INFINITY, -INFINITY), m1 = m0, m2 = m0, m3 = m0;
         int r = rb;
-        for (; r + 2 <= re; r += 2) {
-          const float4 a0 = *reinterpret_cast<const float4*>(base + r * BF_LD);
-          const float4 a1 = *reinterpret_cast<const float4*>(base + (r + 1) * BF_LD);
-          if (!use_mask || alive_s[r]) max4(m0, a0);
-          if (!use_mask || alive_s[r + 1]) max4(m1, a1);
+        for (; r + 4 <= re; r += 4) {           // four independent loads in flight
+          const float2 a0 = *reinterpret_cast<const float2*>(base + r * BF_LD), a1 = *reinterpret_cast<const float2*>(base + (r + 1) * BF_LD);
+          const float2 a2 = *reinterpret_cast<const float2*>(base + (r + 2) * BF_LD), a3 = *reinterpret_cast<const float2*>(base + (r + 3) * BF_LD);
+          if (!use_mask || alive_s[r]) max2(m0, a0);
+          if (!use_mask || alive_s[r + 1]) max2(m1, a1);
+          if (!use_mask || alive_s[r + 2]) max2(m2, a2);
+          if (!use_mask || alive_s[r + 3]) max2(m3, a3);
         }
-        if (r < re && (!use_mask || alive_s[r])) max4(m0, *reinterpret_cast<const float4*>(base + r * BF_LD));
-        max4(m0, m1);
-        *reinterpret_cast<float4*>(base + rb * BF_LD) = m0;
-        if (broadcast)
-          for (r = rb + 1; r < re; ++r) *reinterpret_cast<float4*>(base + r * BF_LD) = m0;
+        for (; r < re; ++r)
+          if (!use_mask || alive_s[r]) max2(m0, *reinterpret_cast<const float2*>(base + r * BF_LD));
+        max2(m0, m1); max2(m2, m3); max2(m0, m2);
+        *reinterpret_cast<float2*>(base + rb * BF_LD) = m0;
+        if (broadcast) {
+#pragma unroll 4
+          for (r = rb + 1; r < re; ++r) *reinterpret_cast<float2*>(base + r * BF_LD) = m0;
+        }
       }
     };
     auto colmax_first = [&](bool use_mask) { colmax(use_mask, false); };
@@ -291,13 +315,17 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
       BF_MARK(43);
       named_bar(1, BF_WORKERS);
       BF_MARK(44);
-#pragma unroll 2
-      for (int cg = 0; cg < BF_GROUPS; ++cg) {
-        const int c = half * BF_SLICE_COLS + cg * 8;
-        float acc[8], o[8];
-        tmem_ld8(t_lane + (uint32_t)c, acc);
-        tmem_ld_wait();
-        lin8(acc, vbase + c, o);
+#pragma unroll 1
+      for (int cp = 0; cp < BF_GROUPS; cp += 2) {
+      float accp[2][8];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) tmem_ld8(t_lane + (uint32_t)(half * BF_SLICE_COLS + (cp + j) * 8), accp[j]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = half * BF_SLICE_COLS + (cp + j) * 8;
+        float o[8];
+        lin8(accp[j], vbase + c, o);
         if (live) {
           float mx[8];
           load8(srow + c, mx);
@@ -306,39 +334,52 @@ backbone_fused_kernel(const __grid_constant__ BackboneFusedArgs p) {
           store8(srow + c, o);
         }
       }
+      }
       BF_MARK(45);
       named_bar(1, BF_WORKERS);
       BF_MARK(46);
-      const float4 w = *reinterpret_cast<const float4*>(gw + lane * 4), b = *reinterpret_cast<const float4*>(gb + lane * 4);
-      const float4 ms = *reinterpret_cast<const float4*>(gms + lane * 4);
-      for (int k = warp; k < G; k += BF_WORKER_WARPS) {
+      for (int u = warp; u < 2 * G; u += BF_WORKER_WARPS) {
+        const int k = u >> 1, c0 = (u & 1) * 64 + lane * 2;
         const int rb = g_beg[k], re = g_beg[k + 1];
-        const float inv_n = 1.f / (float)(re - rb);
-        const float* base = stg + lane * 4;
-        // one pass: sum and sum of squares; mean((x - s)^2) = E[x^2] - 2 s E[x] + s^2 with s = mean * mean_scale
-        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), sq = sum;
-#pragma unroll 2
-        for (int r = rb; r < re; ++r) {
-          const float4 v = *reinterpret_cast<const float4*>(base + r * BF_LD);
-          sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
-          sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y); sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
+        const float inv_n = __fdividef(1.f, (float)(re - rb));
+        const float* base = stg + c0;
+        const float2 w = *reinterpret_cast<const float2*>(gw + c0), b = *reinterpret_cast<const float2*>(gb + c0);
+        const float2 ms = *reinterpret_cast<const float2*>(gms + c0);
+        // one pass: sum and sum of squares (two independent chains); mean((x - s)^2) = E[x^2] - 2 s E[x] + s^2 with
+        // s = mean * mean_scale
+        float2 su0 = make_float2(0.f, 0.f), su1 = su0, sq0 = su0, sq1 = su0;
+        int r = rb;
+        for (; r + 2 <= re; r += 2) {
+          const float2 v0 = *reinterpret_cast<const float2*>(base + r * BF_LD), v1 = *reinterpret_cast<const float2*>(base + (r + 1) * BF_LD);
+          su0.x += v0.x; su0.y += v0.y; su1.x += v1.x; su1.y += v1.y;
+          sq0.x = fmaf(v0.x, v0.x, sq0.x); sq0.y = fmaf(v0.y, v0.y, sq0.y); sq1.x = fmaf(v1.x, v1.x, sq1.x); sq1.y = fmaf(v1.y, v1.y, sq1.y);
         }
+        if (r < re) {
+          const float2 v0 = *reinterpret_cast<const float2*>(base + r * BF_LD);
+          su0.x += v0.x; su0.y += v0.y; sq0.x = fmaf(v0.x, v0.x, sq0.x); sq0.y = fmaf(v0.y, v0.y, sq0.y);
+        }
+        BF_MARK(47 + 3 * (u >= BF_WORKER_WARPS));
         auto stat = [&](float su, float s2, float msc, float wc, float& shift, float& scale) {
           const float mean = su * inv_n;
           shift = mean * msc;
           const float var = fmaxf(fmaf(shift, shift - 2.f * mean, s2 * inv_n), 0.f);
-          scale = wc / sqrtf(var + 1e-5f);
+          scale = wc * rsqrtf(var + 1e-5f);
         };
-        float4 sh, sc;
-        stat(sum.x, sq.x, ms.x, w.x, sh.x, sc.x); stat(sum.y, sq.y, ms.y, w.y, sh.y, sc.y);
-        stat(sum.z, sq.z, ms.z, w.z, sh.z, sc.z); stat(sum.w, sq.w, ms.w, w.w, sh.w, sc.w);
-#pragma unroll 2
-        for (int r = rb; r < re; ++r) {
-          const float4 v = *reinterpret_cast<const float4*>(base + r * BF_LD);
-          const float y0 = fmaxf(fmaf(v.x - sh.x, sc.x, b.x), 0.f), y1 = fmaxf(fmaf(v.y - sh.y, sc.y, b.y), 0.f);
-          const float y2 = fmaxf(fmaf(v.z - sh.z, sc.z, b.z), 0.f), y3 = fmaxf(fmaf(v.w - sh.w, sc.w, b.w), 0.f);
-          *reinterpret_cast<uint2*>(a_s + sw128_off(128, r, lane * 4)) = make_uint2(pack2<BF16>(y0, y1), pack2<BF16>(y2, y3));
+        float2 sh, sc;
+        stat(su0.x + su1.x, sq0.x + sq1.x, ms.x, w.x, sh.x, sc.x);
+        stat(su0.y + su1.y, sq0.y + sq1.y, ms.y, w.y, sh.y, sc.y);
+        BF_MARK(48 + 3 * (u >= BF_WORKER_WARPS));
+        auto norm_store = [&](int rr, const float2 v) {
+          *reinterpret_cast<uint32_t*>(a_s + sw128_off(128, rr, c0)) =
+              pack2_relu<BF16>(fmaf(v.x - sh.x, sc.x, b.x), fmaf(v.y - sh.y, sc.y, b.y));
+        };
+        for (r = rb; r + 4 <= re; r += 4) {     // loads first: a load cannot pass the (possibly aliasing) store in front of it
+          const float2 v0 = *reinterpret_cast<const float2*>(base + r * BF_LD), v1 = *reinterpret_cast<const float2*>(base + (r + 1) * BF_LD);
+          const float2 v2 = *reinterpret_cast<const float2*>(base + (r + 2) * BF_LD), v3 = *reinterpret_cast<const float2*>(base + (r + 3) * BF_LD);
+          norm_store(r, v0); norm_store(r + 1, v1); norm_store(r + 2, v2); norm_store(r + 3, v3);
         }
+        for (; r < re; ++r) norm_store(r, *reinterpret_cast<const float2*>(base + r * BF_LD));
+        BF_MARK(49 + 3 * (u >= BF_WORKER_WARPS));
       }
     };
     // fc tail: y = relu(acc + b + residual), residual = fp32 row stash in TMEM ; to_a: 16-bit -> A k-chunks 0,1 ;

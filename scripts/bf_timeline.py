@@ -38,3 +38,9 @@ prev = t[40]
 for i in (40, 41, 42, 43, 44, 45, 46, 15):
     print("  %-32s +%7d cycles" % (sub[i], t[i] - prev))
     prev = t[i]
+
+print("tile 0: G = %d graphs, R = %d rows" % (t[60], t[61]))
+for base, name in ((47, "unit 0"), (50, "unit 16")):
+    if t[base]:
+        print("  GraphNorm %s: stats pass done +%d (from barrier), scale/shift +%d, normalise + A +%d" % (
+            name, t[base] - t[46], t[base + 1] - t[base], t[base + 2] - t[base + 1]))
