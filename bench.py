@@ -8,14 +8,20 @@ Workload (BASELINE.json configs[1]): pretrained checkpoints/cns.pth, batched inf
 graphs; inference needs no collective).  One "step" = one GraphVS forward (+ fused postprocess)
 over one 1024-graph batch.
 
-  value : graphs/s with the batches already resident in HBM (CUDA events, max over ranks).
-  e2e   : the same through the public API from HOST (pinned) memory, servo form (BatchedServo.step):
+  value : graphs/s with the batches already resident in HBM (CUDA events, max over ranks): K stateless
+          GraphVS.forward(Batch, None) calls, consecutive calls rotating over N_STREAMS (3) CUDA streams so that
+          up to three forwards are in flight (the encoder of step i+1 fills the SMs that the latency-bound
+          cluster-level kernels of step i leave idle); a call whose argument set repeats is replayed by the library
+          as ONE CUDA-graph launch.  `one_stream` = the same calls strictly one after the other.
+  e2e   : the same through the public API from HOST (pinned) memory, servo form (BatchedServo.submit/result):
           the target-side graphs are per-scene state resident on the device (the reference's Midend
           builds them once per target), a step copies the current keypoint coordinates + visibility
-          in, masks the graphs on the device, runs the forward and reads the (B,6) velocities back.
+          in, masks the graphs on the device, runs the forward and reads the (B,6) velocities back; up to three
+          frames in flight, every frame's velocities reach the host inside the timed region.
           e2e.full_graph: GraphVS.forward on a prebuilt host Batch copied whole every step.
   roofline     : the dominant kernel (encoder edge kernel), timed live with CUDA events on its
-                 launching stream (cns_profile_begin/end).
+                 launching stream (cns_profile_begin/end; inside a replayed graph the pair is a pair of external
+                 event-record nodes) in the ONE-stream loop, where the kernel has the GPU to itself.
                  `frac` is quoted against the BURST bf16 peak while the K-step loop is shorter than 1 s
                  (it runs at boost clocks); `roofline.sustained` repeats the loop for >= 2 s and quotes
                  the same kernel against the sustained peak.
@@ -46,6 +52,7 @@ sys.path.insert(0, ROOT)
 
 N_GRAPHS, N_POINTS, MISSING = 1024, 512, 0.1
 PREROLL = 2           # untimed steps enqueued between the barrier and the start event of a timed loop
+N_STREAMS = int(os.environ.get("CNS_BENCH_STREAMS", "3"))   # CUDA streams the `value` loop alternates between (must divide N_ROTATE)
 PRIME = 12            # untimed steps after the warm-up: every (batch, stream) argument set is seen twice -> CUDA-graph replay
 N_ROTATE = 6          # distinct input batches cycled through so that the bytes a step reads exceed L2 (126 MB)
 # algorithmic FLOPs of the encoder edge kernel per (edge, side): 5 GEMMs 128x128 + in_enc + pos_nn.0
@@ -215,8 +222,8 @@ def workload_config(args):
     return {"workload": "cns.pth batched inference, %d synthetic servo graphs x %d keypoints per GPU" % (args.graphs, args.points),
             "graphs_per_gpu": args.graphs, "keypoints_per_graph": args.points, "missing_keypoints": MISSING,
             "weights": "checkpoints/cns.pth", "hidden": "None (first frame)",
-            "call": "GraphVS.forward(Batch, None), stateless (no target cache); consecutive steps alternate between two CUDA "
-                    "streams (<= 2 forwards in flight), repeated argument sets replay as CUDA graphs"}
+            "call": "GraphVS.forward(Batch, None), stateless (no target cache); consecutive steps rotate over a few CUDA "
+                    "streams (<= %d forwards in flight), repeated argument sets replay as CUDA graphs" % N_STREAMS}
 
 
 _JSON_FD = None
@@ -305,14 +312,14 @@ def main():
             return float(hi.item()), [float(lo.item()), float(hi.item())]
         return ms, [ms, ms]
 
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    streams = [torch.cuda.Stream(dev) for _ in range(N_STREAMS)]
 
-    def enqueue(model, first, n, two_streams, **kw):
+    def enqueue(model, first, n, multi_stream, **kw):
         """`n` stateless forwards over the rotating resident batches, step i on batch (first + i) % N_ROTATE.  With
-        `two_streams` consecutive steps alternate between two CUDA streams (<= 2 forwards in flight: the encoder of
-        step i+1 fills the SMs the second wave of step i's cluster-level backbone leaves idle); the streams fork from
+        `multi_stream` consecutive steps rotate over N_STREAMS CUDA streams (<= N_STREAMS forwards in flight: the encoder
+        of step i+1 fills the SMs the second wave of step i's cluster-level backbone leaves idle); the streams fork from
         and join the current stream, so events recorded on it bracket all of the work."""
-        if not two_streams:
+        if not multi_stream:
             for i in range(n):
                 model(resident[(first + i) % N_ROTATE], None, **kw)
             return
@@ -320,31 +327,31 @@ def main():
         for st in streams:
             st.wait_stream(cur)
         for i in range(n):
-            with torch.cuda.stream(streams[(first + i) % 2]):
+            with torch.cuda.stream(streams[(first + i) % N_STREAMS]):
                 model(resident[(first + i) % N_ROTATE], None, **kw)
         for st in streams:
             cur.wait_stream(st)
 
-    def forward_loop(model, steps, warmup, profile=True, two_streams=False, **kw):
+    def forward_loop(model, steps, warmup, profile=True, multi_stream=False, **kw):
         """`steps` stateless forwards: (elapsed ms on this rank, mean encoder-edge kernel ms, launches counted by the
         library).  Untimed before the start event: `warmup` steps, then PRIME more so that the library has seen every
         (batch, stream) argument set twice and replays it as a CUDA graph, then a barrier and PREROLL steps."""
         hd = model._handle(dev)
-        enqueue(model, 0, warmup, two_streams, **kw)
+        enqueue(model, 0, warmup, multi_stream, **kw)
         if profile:
             _lib.check(lib.cns_profile_begin(hd.raw), "profile_begin")     # timed graphs are captured with their event pair
-        enqueue(model, warmup, PRIME, two_streams, **kw)
+        enqueue(model, warmup, PRIME, multi_stream, **kw)
         barrier()
         # pre-roll: the barrier leaves the GPU idle; two more untimed steps are enqueued right in front of the start event
         # so the timed steps run back to back with work (an idle -> busy transition and a host hiccup of up to a step
         # would otherwise land inside a 9 ms region; at 8 ranks that showed as one rank 9 % slow)
         first = warmup + PRIME
-        enqueue(model, first, PREROLL, two_streams, **kw)
+        enqueue(model, first, PREROLL, multi_stream, **kw)
         if profile:
             _lib.check(lib.cns_profile_begin(hd.raw), "profile_begin")
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
-        enqueue(model, first + PREROLL, steps, two_streams, **kw)
+        enqueue(model, first + PREROLL, steps, multi_stream, **kw)
         t1.record()
         barrier()
         kms, kn, nl = C.c_float(), C.c_int(), C.c_longlong()
@@ -362,10 +369,10 @@ def main():
         #     has the GPU to itself
         one_ms, kernel_ms, launches = forward_loop(net, args.steps, args.warmup)
         one_total, one_rank = gather_ms(one_ms)
-        # (b) `value`: the same calls alternating between two CUDA streams (<= 2 forwards in flight)
+        # (b) `value`: the same calls rotating over N_STREAMS CUDA streams (<= N_STREAMS forwards in flight)
         sampler = ClockSampler(local)
         sampler.start()
-        my_ms, _, _ = forward_loop(net, args.steps, args.warmup, profile=False, two_streams=True)
+        my_ms, _, _ = forward_loop(net, args.steps, args.warmup, profile=False, multi_stream=True)
         sampler.stop_flag = True
         total_ms, rank_ms = gather_ms(my_ms)
         value = args.graphs * world * args.steps / (total_ms * 1e-3)
@@ -377,14 +384,14 @@ def main():
         # positions, tile packing) is built once, as the reference's Midend keeps one GraphGenerator per target
         # image.  Reported beside `value`, not as `value`.
         tcache = net.build_target_cache(resident[0])
-        cached_ms = max_over_ranks(forward_loop(net, args.steps, args.warmup, profile=False, two_streams=True, target_cache=tcache)[0])
+        cached_ms = max_over_ranks(forward_loop(net, args.steps, args.warmup, profile=False, multi_stream=True, target_cache=tcache)[0])
 
         if extras:
             # ---------------- the same loop for >= 2 s: clocks settle at their sustained level ---------------
             n_sus = max(args.steps, int(2200.0 / max(my_ms / args.steps, 1e-3)))
             sus_sampler = ClockSampler(local)
             sus_sampler.start()
-            sus_ms = forward_loop(net, n_sus, 0, profile=False, two_streams=True)[0]
+            sus_ms = forward_loop(net, n_sus, 0, profile=False, multi_stream=True)[0]
             # ... and, right behind it, the one-stream loop that times the encoder edge kernel at those clocks
             _, sus_kernel_ms, _ = forward_loop(net, 64, 0)
             sus_sampler.stop_flag = True
@@ -396,7 +403,7 @@ def main():
             if args.precision != "fp32":
                 net32 = ckpt.load_model(os.path.join(ROOT, "checkpoints", "cns.pth"), dev, precision="fp32")
                 f1_ms, f_kernel_ms, f_launches = forward_loop(net32, args.steps, args.warmup)
-                f_ms = forward_loop(net32, args.steps, args.warmup, profile=False, two_streams=True)[0]
+                f_ms = forward_loop(net32, args.steps, args.warmup, profile=False, multi_stream=True)[0]
                 f_total = max_over_ranks(f_ms)
                 fp32 = {"value": args.graphs * world * args.steps / (f_total * 1e-3), "unit": "graphs/s",
                         "ms_per_step": f_total / args.steps, "one_stream_ms_per_step": max_over_ranks(f1_ms) / args.steps,
@@ -433,7 +440,7 @@ def main():
         # per step H2D of the current keypoint coordinates + visibility, per-frame graph masking on the
         # device, forward, D2H of the velocities; each step waits for its own result (closed loop).
         from cns_b200.servo import BatchedServo
-        servo = BatchedServo(net, [s.generator for s in scenes], [s.tPo_norm for s in scenes], dev)
+        servo = BatchedServo(net, [s.generator for s in scenes], [s.tPo_norm for s in scenes], dev, depth=N_STREAMS)
         frames = [(b.pos_cur, b.node_mask.view(torch.uint8)) for b in host]     # pinned host tensors
         for i in range(args.warmup + PRIME):           # PRIME: every frame's argument set seen twice -> graph replay
             servo.reset()
@@ -445,14 +452,14 @@ def main():
         g0.record()
         # two frames in flight: frame i+1's inputs are copied while frame i computes; every frame's velocities
         # are read back on the host inside the timed region
-        prev = None
+        pending = []
         for i in range(args.steps):
             servo.reset()                                 # hidden=None, the workload `value` is quoted on
-            t = servo.submit(*frames[i % N_ROTATE])
-            if prev is not None:
-                vel = servo.result(prev)
-            prev = t
-        vel = servo.result(prev)
+            pending.append(servo.submit(*frames[i % N_ROTATE]))
+            if len(pending) == servo.depth:
+                vel = servo.result(pending.pop(0))
+        while pending:
+            vel = servo.result(pending.pop(0))
         g1.record()
         barrier()
         e2e_ms = max_over_ranks(g0.elapsed_time(g1))
@@ -576,8 +583,8 @@ def main():
         "e2e": {"value": e2e, "unit": "graphs/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": h2d_servo, "d2h_bytes_per_step": d2h_servo,
                 "api": "BatchedServo.submit/result(cur_xy, visible): target graphs resident on the device, per-frame "
-                       "graph masking on the device, two frames in flight on two compute streams (H2D and kernels of "
-                       "frame i+1 overlap frame i), every frame's velocities read back on the host",
+                       "graph masking on the device, %d frames in flight, each slot on its own compute stream (H2D and "
+                       "kernels of later frames overlap frame i), every frame's velocities read back on the host" % N_STREAMS,
                 "full_graph": {"value": e2e_full, "ms_per_step": full_ms / args.steps, "h2d_bytes_per_step": h2d,
                                "d2h_bytes_per_step": d2h_full,
                                "api": "GraphVS.forward(Batch.to(device)): the whole prebuilt host Batch is copied "

@@ -23,7 +23,7 @@ from .graph_gen import GraphGenerator
 
 
 class BatchedServo(object):
-    def __init__(self, net, generators: Sequence[GraphGenerator], dist_scale, device="cuda:0"):
+    def __init__(self, net, generators: Sequence[GraphGenerator], dist_scale, device="cuda:0", depth: int = 2):
         self.net, self.dev = net, torch.device(device)
         self.lib = _lib.load()
         gens = list(generators)
@@ -48,7 +48,7 @@ class BatchedServo(object):
         # compute stream, so the kernels of consecutive frames may overlap on the device (the cluster-level backbone of
         # frame t leaves most SMs idle in its second wave; the encoder of frame t+1 fills them).  A carried hidden
         # state orders frame t+1 behind frame t through an event.
-        self.depth = 2
+        self.depth = max(1, int(depth))
         D = range(self.depth)
         self.e01_j, self.e01_i = [i64(max(self.N, 1)) for _ in D], [i64(max(self.N, 1)) for _ in D]
         self.cmask = [torch.empty(max(self.Cn, 1), dtype=torch.uint8, device=self.dev) for _ in D]

@@ -560,3 +560,70 @@ def test_device_scene_batch_reference_augmentations(net, long_seq):
 def synth_project(env, poses):
     from cns_b200.sim_device import project_norm
     return project_norm(poses, env.points, env.scene_of).float().cpu().numpy()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16"])
+def test_cuda_graph_replay_equals_plain_enqueue(state_dict, precision):
+    """A forward whose whole argument set repeats (same sizes, pointers, mode) is captured the second time and replayed
+    as one CUDA-graph launch from the third: same bits as the plain enqueue, inputs re-read on every replay."""
+    net = ckpt.load_model(os.path.join(ROOT, "checkpoints", "cns.pth"), "cuda:0", precision=precision)
+    batch = synth.make_batch(5, 150, seed=4, missing_frac=0.2, n_layouts=3).to("cuda:0")
+    h = net._handle(torch.device("cuda:0"))
+    lib = _lib.load()
+    b, keep = net.make_batch_struct(batch)
+    nb, nc = b.n_graphs, b.n_clusters
+    ws = torch.empty(lib.cns_forward_workspace_bytes(C.byref(b)) + 1024, dtype=torch.uint8, device="cuda:0")
+    out = torch.zeros(nc * 128 + nb * 13, device="cuda:0")
+    hid, vec = out[:nc * 128], out[nc * 128:nc * 128 + nb * 6]
+    vel, nrm = out[nc * 128 + nb * 6:nc * 128 + nb * 12], out[nc * 128 + nb * 12:]
+
+    def call(stream):
+        _lib.check(lib.cns_graphvs_forward(h.raw, C.byref(b), None, _lib.ptr(vec), _lib.ptr(nrm), _lib.ptr(hid), _lib.ptr(vel),
+                                           _lib.ptr(ws), ws.numel(), None, 0, C.c_void_p(stream)), "forward")
+        _lib.check(lib.cns_forward_status(_lib.ptr(ws), C.c_void_p(stream)), "status")
+        return out.clone()
+
+    side = torch.cuda.Stream("cuda:0")
+    for stream in (0, side.cuda_stream):        # the legacy default stream (captured on an internal stream) and a real one
+        h.set_option("cuda_graphs", 0)
+        ref = call(stream)
+        h.set_option("cuda_graphs", 1)
+        r0, c0 = h.counter("graph_replays"), h.counter("graph_captures")
+        got = [call(stream) for _ in range(4)]
+        assert h.counter("graph_captures") == c0 + 1 and h.counter("graph_replays") == r0 + 3
+        for g in got:
+            assert torch.equal(g, ref)
+        # new input values behind the same pointers: a replay reads them
+        batch.pos_cur.mul_(1.01)
+        batch.x_cur.copy_(batch.pos_cur)
+        moved = call(stream)
+        h.set_option("cuda_graphs", 0)
+        assert torch.equal(moved, call(stream)) and not torch.equal(moved, ref)
+        batch.pos_cur.div_(1.01)
+        batch.x_cur.copy_(batch.pos_cur)
+    h.set_option("cuda_graphs", 1)
+    with pytest.raises(_lib.CnsError):
+        h.set_option("no_such_option", 1)
+
+
+def test_forwards_on_two_streams_do_not_interfere(state_dict):
+    """GraphVS.forward keeps one workspace per CUDA stream: forwards enqueued on different streams may overlap on the
+    device (bench.py alternates two streams) and still give the results of the one-after-the-other loop."""
+    net = ckpt.load_model(os.path.join(ROOT, "checkpoints", "cns.pth"), "cuda:0", precision="f16")
+    batches = [synth.make_batch(24, 256, seed=20 + i, missing_frac=0.1, n_layouts=4).to("cuda:0") for i in range(4)]
+    with torch.no_grad():
+        ref = [[t.clone() for t in net(b, None)] for b in batches]
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream("cuda:0"), torch.cuda.Stream("cuda:0")]
+        for st in streams:
+            st.wait_stream(torch.cuda.current_stream())
+        got = []
+        for rep in range(3):                       # the third pass replays CUDA graphs
+            got = []
+            for i, b in enumerate(batches):
+                with torch.cuda.stream(streams[i % 2]):
+                    got.append(net(b, None))
+        torch.cuda.synchronize()
+    for g, r in zip(got, ref):
+        for x, y in zip(g, r):
+            assert torch.equal(x, y)
