@@ -87,6 +87,7 @@ struct Packed {
   // 16-bit swizzled B-operand images for gemm_tc: index 0 = bf16, 1 = f16
   unsigned char* tc_c0[2]; unsigned char* tc_c0_fc[2]; unsigned char* tc_g[2]; unsigned char* tc_k[2];
   unsigned char* tc_c1[2]; unsigned char* tc_c1_fc[2]; unsigned char* tc_out[2];
+  unsigned char* tc_adst[2];                    // (A0 lin_dst): the per-cluster attention term a' as a gemm_tc product (f16 mode)
   unsigned char* tc_node_base;
   // bf16 (hi, lo) split images of the same seven matrices for the fp32 mode (gemm_tc_split.cu)
   unsigned char* tc2_c0; unsigned char* tc2_c0_fc; unsigned char* tc2_g; unsigned char* tc2_k;
@@ -116,6 +117,7 @@ struct cns_handle {
   int tc_tile_n;                                        // edges per tensor-core tile (32 or 64)
   int tc_slots;                                         // tiles in flight per SM of the 32-edge kernel: 4, 5 or 6 (CNS_TC_SLOTS)
   int no_split_gemm;                                    // CNS_NO_SPLIT_GEMM=1: backward GEMMs stay on the fp32 FFMA kernel (A-B runs)
+  int no_tc_cluster_pre;                                // CNS_NO_TC_CLUSTER_PRE=1: per-cluster encoder terms stay on the FFMA kernel (A-B runs)
   int no_fused_backbone;                                // CNS_NO_FUSED_BACKBONE=1: keep the per-layer kernels (debugging / A-B runs)
   // optional CUDA-event timing of the dominant kernel (encoder edge kernel), see cns_profile_*
   int timing; int ev_n; cudaEvent_t ev[2 * 256];

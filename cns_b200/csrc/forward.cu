@@ -91,6 +91,20 @@ static int validate(const cns_batch* b) {
   return CNS_OK;
 }
 
+// per-cluster encoder terms a' = A0 (lin_dst x_c + b_pos1) + b_attn0, pos_clu, clu_graph: in f16 mode one gemm_tc product
+// whose A rows are produced on the fly from the cluster centres (the FFMA kernel took 36 us at 19 k clusters)
+static int cluster_pre(cns_handle* h, const EncPreArgs& pre, cudaStream_t s) {
+  if (h->precision == CNS_PREC_F16 && pre.a_bias && h->pk.tc_adst[1] && !h->no_tc_cluster_pre) {
+    GemmTcArgs ga{};
+    ga.m = pre.n_clusters; ga.k1 = H; ga.k2 = 0; ga.n_out = H; ga.w_img = h->pk.tc_adst[1];
+    ga.bias = pre.a_bias; ga.relu = 0; ga.y = pre.a_dst;
+    ga.centers = pre.centers; ga.ctr_xy = pre.x_tar; ga.ctr_pos = pre.pos_tar; ga.w_in = pre.w_in; ga.b_in = pre.b_in;
+    ga.node_graph = pre.node_graph; ga.pos_out = pre.pos_clu; ga.clu_graph = pre.clu_graph;
+    return gemm_tc(ga, false, s);
+  }
+  return enc_cluster_pre(pre, s);
+}
+
 // `cap_ev`: the call is being captured into a CUDA graph with kernel timing on - the encoder edge kernel is bracketed by
 // these two events (recorded as external event nodes, readable after every replay) instead of the handle's event ring
 int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, float* vel_si_vec,
@@ -138,7 +152,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     }
     CNS_CUDA_CHECK(cudaEventRecord(h->side_fork, s));
     CNS_CUDA_CHECK(cudaStreamWaitEvent(h->side_stream, h->side_fork, 0));
-    RUN(enc_cluster_pre(pre, h->side_stream));
+    RUN(cluster_pre(h, pre, h->side_stream));
     CNS_CUDA_CHECK(cudaEventRecord(h->side_join, h->side_stream));
   }
   // graph pointers, whole-graph tiles and the hint verification feed the cluster-level backbone only: on the forked
@@ -199,7 +213,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
 
   // ---- encoder ----------------------------------------------------------------------------
   if (fork_pre) { CNS_CUDA_CHECK(cudaStreamWaitEvent(s, h->side_join, 0)); }
-  else if (!tcache) RUN(enc_cluster_pre(pre, s));
+  else if (!tcache) RUN(cluster_pre(h, pre, s));
 
   EncEdgeArgs ee{};
   ee.n_e01 = b->n_e01; ee.n_clusters = C; ee.n_slots = f.n_slots;
@@ -408,7 +422,7 @@ static int forward_graphed(cns_handle* h, const cns_batch* b, const float* hidde
   const void* ptrs[6] = {hidden_in, vel_si_vec, vel_si_norm, hidden_out, vel, workspace};
   key = fnv(key, ptrs, sizeof(ptrs));
   const long long mode[8] = {h->precision, h->weights_version, h->timing, h->tc_tile_n, h->tc_slots, 0,
-                             h->no_fused_backbone * 2 + h->no_split_encoder, b->target_cache ? b->target_cache->weights_version : 0};
+                             h->no_fused_backbone * 2 + h->no_split_encoder + 4 * h->no_tc_cluster_pre, b->target_cache ? b->target_cache->weights_version : 0};
   key = fnv(key, mode, sizeof(mode));
   if (key == 0) key = 1;
   GraphEntry* hit = nullptr; GraphEntry* victim = &gc->e[0];
@@ -552,7 +566,7 @@ int cns_target_cache_create(cns_handle* h, const cns_batch* b, void* stream, cns
     pre.node_graph = b->node_graph; pre.w_in = h->P(P_IN_W); pre.b_in = h->P(P_IN_B); pre.lin_dst_t = h->pk.lin_dst_t;
     if (h->precision != CNS_PREC_FP32 || !h->no_split_encoder) { pre.lin_dst_t = h->pk.tc_lin_dst_t; pre.a_bias = h->pk.tc_adst_bias; }
     pre.a_dst = c->a_dst; pre.pos_clu = c->pos_clu; pre.clu_graph = c->clu_graph;
-    rc = enc_cluster_pre(pre, s);
+    rc = cluster_pre(h, pre, s);
   } while (false);
   if (rc != CNS_OK) { cudaFree(c->base); delete c; return rc; }
   *out = c;

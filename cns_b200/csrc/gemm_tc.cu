@@ -79,7 +79,22 @@ gemm_tc_kernel(const __grid_constant__ GemmTcArgs p) {
       const int k = kc8 * 8;
       const int64_t m = m0 + row;
       float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-      if (m < p.m) {
+      if (m < p.m && p.centers) {
+        // centre-feature producer: 8 channels of relu(in_enc(x_tar[centre])) (K = 2: cheaper than reading a row)
+        const int64_t ctr = p.centers[m];
+        const float2 f = reinterpret_cast<const float2*>(p.ctr_xy)[ctr];
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 w = __ldg(reinterpret_cast<const float2*>(p.w_in) + k + i);
+          v[i] = fmaxf(fmaf(w.y, f.y, fmaf(w.x, f.x, __ldg(p.b_in + k + i))), 0.f);
+        }
+        lo = make_float4(v[0], v[1], v[2], v[3]); hi = make_float4(v[4], v[5], v[6], v[7]);
+        if (kc8 == 0) {
+          reinterpret_cast<float2*>(p.pos_out)[m] = reinterpret_cast<const float2*>(p.ctr_pos)[ctr];
+          p.clu_graph[m] = p.node_graph ? (int)p.node_graph[ctr] : 0;
+        }
+      } else if (m < p.m) {
         const float* src = (k < p.k1) ? p.x1 + m * p.k1 + k : p.x2 + m * p.k2 + (k - p.k1);
         lo = *reinterpret_cast<const float4*>(src);
         hi = *reinterpret_cast<const float4*>(src + 4);

@@ -185,7 +185,7 @@ int repack(cns_handle* h, cudaStream_t s) {
     struct Item { const float* wt; int k, n; unsigned char** dst; };
     Item items[] = {{pk.c0_wt, 128, 256, pk.tc_c0}, {pk.c0_fc_t, 128, 128, pk.tc_c0_fc}, {pk.g_wt, 256, 512, pk.tc_g},
                     {pk.k_wt, 256, 256, pk.tc_k},   {pk.c1_wt, 128, 256, pk.tc_c1},   {pk.c1_fc_t, 128, 128, pk.tc_c1_fc},
-                    {pk.out_t, 256, 128, pk.tc_out}};
+                    {pk.out_t, 256, 128, pk.tc_out}, {pk.tc_lin_dst_t, 128, 128, pk.tc_adst}};
     if (!pk.tc_node_base) {
       size_t total = 0;
       for (auto& it : items) total += (size_t)it.k * it.n * 2 * 2;
@@ -199,15 +199,13 @@ int repack(cns_handle* h, cudaStream_t s) {
     unsigned char** split_dst[] = {&pk.tc2_c0, &pk.tc2_c0_fc, &pk.tc2_g, &pk.tc2_k, &pk.tc2_c1, &pk.tc2_c1_fc, &pk.tc2_out};
     if (!pk.tc2_base) {
       size_t total = 0;
-      for (auto& it : items) total += (size_t)it.k * it.n * 2 * 2;
+      for (int i = 0; i < 7; ++i) total += (size_t)items[i].k * items[i].n * 2 * 2;
       CNS_CUDA_CHECK(cudaMalloc(&pk.tc2_base, total));
       unsigned char* q = pk.tc2_base;
-      int i = 0;
-      for (auto& it : items) { *split_dst[i++] = q; q += (size_t)it.k * it.n * 2 * 2; }
+      for (int i = 0; i < 7; ++i) { *split_dst[i] = q; q += (size_t)items[i].k * items[i].n * 2 * 2; }
     }
-    int i = 0;
-    for (auto& it : items)
-      if ((rc = gemm_tc_split_pack(it.wt, it.k, it.n, *split_dst[i++], s)) != CNS_OK) return rc;
+    for (int i = 0; i < 7; ++i)
+      if ((rc = gemm_tc_split_pack(items[i].wt, items[i].k, items[i].n, *split_dst[i], s)) != CNS_OK) return rc;
   }
   if ((rc = bf_pack_vec(h, s)) != CNS_OK) return rc;
   h->weights_loaded = true;
@@ -253,6 +251,7 @@ int cns_create(cns_handle** out, int device) {
   h->precision = CNS_PREC_FP32;
   h->tc_tile_n = 32;
   h->no_fused_backbone = getenv("CNS_NO_FUSED_BACKBONE") ? 1 : 0;
+  h->no_tc_cluster_pre = getenv("CNS_NO_TC_CLUSTER_PRE") ? 1 : 0;
   h->no_split_gemm = getenv("CNS_NO_SPLIT_GEMM") ? 1 : 0;
   h->no_split_encoder = getenv("CNS_NO_SPLIT_ENCODER") ? 1 : 0;
   h->tc_slots = getenv("CNS_TC_SLOTS") ? atoi(getenv("CNS_TC_SLOTS")) : 5;

@@ -112,6 +112,10 @@ struct GemmTcArgs {
   const uint8_t* row_mask;                 // optional (m,): rows with 0 are written as zeros
   int relu;
   float* y;
+  // optional A-row producer instead of x1 (k1 = 128): row m = relu(in_enc(ctr_xy[centers[m]])), the per-cluster centre
+  // feature of the encoder (graph_vs.py:207-208); also emits pos_out[m] = ctr_pos[centers[m]] and the cluster's graph id
+  const int64_t* centers; const float* ctr_xy; const float* ctr_pos; const float* w_in; const float* b_in;
+  const int64_t* node_graph; float* pos_out; int* clu_graph;
 };
 int gemm_tc(const GemmTcArgs& a, bool bf16, cudaStream_t s);
 int gemm_tc_pack(const float* wt, int k_dim, int n_out, unsigned char* img_bf16, unsigned char* img_f16, cudaStream_t s);
