@@ -229,92 +229,120 @@ int graphnorm_relu(const GraphNormArgs& a, cudaStream_t s) {
 // =============================================================================================
 // pool_head: softmax-gated sum over the graph's un-masked clusters, two 2-layer heads, and the
 // velocity post-processing  vel = vec/(|vec|+1e-7) * (1+elu(norm)), vel[:3] *= tPo_norm
-// (graph_vs.py:254-270, functions.py:26-38).  One CTA of 128 threads per graph.
+// (graph_vs.py:254-270, functions.py:26-38).
+// A CTA of 8 warps owns 8 graphs: warp w pools graph w (a lane owns 4 channels, rows are read as whole 512-byte
+// lines), then the 256 threads run the first layer of both heads for all 8 graphs at once - one weight load feeds
+// 8 FMAs (one CTA per graph re-read the two 64 KB head matrices from L2 for every graph: 134 MB per 1024 graphs).
 // A graph whose clusters are all masked yields x_scene = 0 (PyG would drop the row).
 // =============================================================================================
-__global__ void __launch_bounds__(128)
+constexpr int PH_G = 8;          // graphs per CTA
+
+__global__ void __launch_bounds__(256)
 pool_head_kernel(PoolHeadArgs p) {
-  __shared__ float xs[H];
-  __shared__ float hid[2][H];
-  __shared__ float red[4];
-  __shared__ float outv[8];
-  const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int beg = p.graph_ptr[g], end = p.graph_ptr[g + 1];
+  __shared__ __align__(16) float xs[PH_G][H];
+  __shared__ __align__(16) float hid[2][PH_G][H];
+  __shared__ float outv[PH_G][8];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t g0 = (int64_t)blockIdx.x * PH_G;
 
-  // gate logits: one warp per row, float4 per lane
-  const float4 gw = reinterpret_cast<const float4*>(p.pool_w)[lane];
-  const float gb = p.pool_b[0];
-  float wmax = -INFINITY;
-  for (int r = beg + wid; r < end; r += 4) {
-    if (!p.cluster_mask[r]) continue;
-    float4 x = reinterpret_cast<const float4*>(p.x + (size_t)r * H)[lane];
-    float d = x.x * gw.x + x.y * gw.y + x.z * gw.z + x.w * gw.w;
+  // ---- pooling: warp = graph ----------------------------------------------------------------------------
+  {
+    const int64_t g = g0 + wid;
+    float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+    float den = 0.f;
+    if (g < p.n_graphs) {
+      const int beg = p.graph_ptr[g], end = p.graph_ptr[g + 1];
+      const float4 gw = reinterpret_cast<const float4*>(p.pool_w)[lane];
+      const float gb = p.pool_b[0];
+      // online softmax over the rows (one pass: the row is in registers when its gate is known)
+      float m = -INFINITY;
+      for (int r = beg; r < end; ++r) {
+        if (!p.cluster_mask[r]) continue;
+        const float4 x = reinterpret_cast<const float4*>(p.x + (size_t)r * H)[lane];
+        float d = x.x * gw.x + x.y * gw.y + x.z * gw.z + x.w * gw.w;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-    d += gb;
-    if (lane == 0) p.gate[r] = d;
-    wmax = fmaxf(wmax, d);
+        for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+        d += gb;
+        if (lane == 0 && p.gate) p.gate[r] = d;
+        const float mn = fmaxf(m, d);
+        const float sc = expf(m - mn), e = expf(d - mn);      // m = -inf on the first row: sc = 0
+        den = fmaf(den, sc, e);
+        num.x = fmaf(num.x, sc, e * x.x); num.y = fmaf(num.y, sc, e * x.y);
+        num.z = fmaf(num.z, sc, e * x.z); num.w = fmaf(num.w, sc, e * x.w);
+        m = mn;
+      }
+    }
+    const float inv = (den > 0.f) ? 1.f / (den + 1e-16f) : 0.f;
+    const float4 xsc = make_float4(num.x * inv, num.y * inv, num.z * inv, num.w * inv);
+    reinterpret_cast<float4*>(xs[wid])[lane] = xsc;
+    if (p.x_scene && g < p.n_graphs) reinterpret_cast<float4*>(p.x_scene + (size_t)g * H)[lane] = xsc;
   }
-  if (lane == 0) red[wid] = wmax;
-  __syncthreads();
-  const float m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-  // every thread (channel) walks the rows: denominator and weighted sum
-  float den = 0.f, num = 0.f;
-  for (int r = beg; r < end; ++r) {
-    if (!p.cluster_mask[r]) continue;
-    float e = expf(p.gate[r] - m);
-    den += e;
-    num = fmaf(e, p.x[(size_t)r * H + tid], num);
-  }
-  const float xsc = (den > 0.f) ? num / (den + 1e-16f) : 0.f;
-  xs[tid] = xsc;
-  if (p.x_scene) p.x_scene[(size_t)g * H + tid] = xsc;
-  __syncthreads();
-
-  // first layers of both heads: thread = output channel
-  float h0 = p.vec0_b[tid], h1 = p.nrm0_b[tid];
-#pragma unroll 16     // 32 independent weight loads in flight: at batch 1 this loop is pure L2 latency
-  for (int k = 0; k < H; ++k) {
-    float x = xs[k];
-    h0 = fmaf(x, p.vec0_t[k * H + tid], h0);
-    h1 = fmaf(x, p.nrm0_t[k * H + tid], h1);
-  }
-  h0 = fmaxf(h0, 0.f); h1 = fmaxf(h1, 0.f);
-  hid[0][tid] = h0; hid[1][tid] = h1;
-  if (p.hid) { p.hid[((size_t)g * 2) * H + tid] = h0; p.hid[((size_t)g * 2 + 1) * H + tid] = h1; }
   __syncthreads();
 
-  // second layers: 7 dot products of length 128, spread over the 4 warps
-  for (int q = wid; q < 7; q += 4) {
-    const float* w = (q < 6) ? p.vec1_w + q * H : p.nrm1_w;
-    const float* hv = (q < 6) ? hid[0] : hid[1];
-    float4 a = reinterpret_cast<const float4*>(w)[lane];
-    float4 b = reinterpret_cast<const float4*>(hv)[lane];
-    float d = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+  // ---- first layers of both heads: thread = (head, output channel), all 8 graphs per weight load ---------
+  {
+    const int o = tid & (H - 1), hd = tid >> 7;
+    const float* __restrict__ wt = hd ? p.nrm0_t : p.vec0_t;
+    const float b = hd ? p.nrm0_b[o] : p.vec0_b[o];
+    float acc[PH_G];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-    if (lane == 0) outv[q] = d + ((q < 6) ? p.vec1_b[q] : p.nrm1_b[0]);
-  }
-  __syncthreads();
-  if (tid < 6) {
-    p.vel_si_vec[(size_t)g * 6 + tid] = outv[tid];
-    if (p.vel) {
-      float nn = 0.f;
+    for (int g = 0; g < PH_G; ++g) acc[g] = b;
+#pragma unroll 4
+    for (int k = 0; k < H; k += 4) {
+      const float w0 = wt[k * H + o], w1 = wt[(k + 1) * H + o], w2 = wt[(k + 2) * H + o], w3 = wt[(k + 3) * H + o];
 #pragma unroll
-      for (int q = 0; q < 6; ++q) nn = fmaf(outv[q], outv[q], nn);
-      float nr = outv[6];
-      float scale = 1.f + (nr > 0.f ? nr : expm1f(nr));
-      float v = outv[tid] / (sqrtf(nn) + 1e-7f) * scale;
-      if (tid < 3) v *= (p.tPo_norm ? p.tPo_norm[g] : 1.f);
-      p.vel[(size_t)g * 6 + tid] = v;
+      for (int g = 0; g < PH_G; ++g) {
+        const float4 x = *reinterpret_cast<const float4*>(&xs[g][k]);      // broadcast read
+        acc[g] = fmaf(x.w, w3, fmaf(x.z, w2, fmaf(x.y, w1, fmaf(x.x, w0, acc[g]))));
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < PH_G; ++g) {
+      const float v = fmaxf(acc[g], 0.f);
+      hid[hd][g][o] = v;
+      if (p.hid && g0 + g < p.n_graphs) p.hid[((size_t)(g0 + g) * 2 + hd) * H + o] = v;
     }
   }
-  if (tid == 6) p.vel_si_norm[g] = outv[6];
+  __syncthreads();
+
+  // ---- second layers + post-processing: warp = graph, 7 dot products of length 128 -----------------------
+  {
+    const int64_t g = g0 + wid;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+      const float* w = (q < 6) ? p.vec1_w + q * H : p.nrm1_w;
+      const float* hv = (q < 6) ? hid[0][wid] : hid[1][wid];
+      const float4 a = reinterpret_cast<const float4*>(w)[lane];
+      const float4 b = reinterpret_cast<const float4*>(hv)[lane];
+      float d = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+      if (lane == 0) outv[wid][q] = d + ((q < 6) ? p.vec1_b[q] : p.nrm1_b[0]);
+    }
+    __syncwarp();
+    if (g < p.n_graphs) {
+      const float* ov = outv[wid];
+      if (lane < 6) {
+        p.vel_si_vec[(size_t)g * 6 + lane] = ov[lane];
+        if (p.vel) {
+          float nn = 0.f;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) nn = fmaf(ov[q], ov[q], nn);
+          const float nr = ov[6];
+          const float scale = 1.f + (nr > 0.f ? nr : expm1f(nr));
+          float v = ov[lane] / (sqrtf(nn) + 1e-7f) * scale;
+          if (lane < 3) v *= (p.tPo_norm ? p.tPo_norm[g] : 1.f);
+          p.vel[(size_t)g * 6 + lane] = v;
+        }
+      }
+      if (lane == 6) p.vel_si_norm[g] = ov[6];
+    }
+  }
 }
 
 int pool_head(const PoolHeadArgs& a, cudaStream_t s) {
   if (a.n_graphs == 0) return CNS_OK;
-  pool_head_kernel<<<(unsigned)a.n_graphs, 128, 0, s>>>(a);
+  pool_head_kernel<<<(unsigned)ceil_div(a.n_graphs, PH_G), 256, 0, s>>>(a);
   CNS_LAUNCH_CHECK();
   return CNS_OK;
 }
