@@ -7,6 +7,7 @@
 //  pool_head     : AttentionalAggregation + both velocity heads + postprocess, one CTA per graph
 #include "common.cuh"
 #include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace cns {
 
@@ -239,6 +240,17 @@ constexpr int PH_G = 8;          // graphs per CTA
 
 __global__ void __launch_bounds__(256)
 pool_head_kernel(PoolHeadArgs p) {
+  // both head matrices (2 x 64 KB) arrive by two 1-D TMA bulk copies while the warps pool their graphs
+  extern __shared__ __align__(128) unsigned char ph_smem[];
+  float* w_s = reinterpret_cast<float*>(ph_smem);
+  __shared__ __align__(8) uint64_t w_bar;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&w_bar), 1);
+    fence_mbar_init();
+    mbar_expect_tx(smem_u32(&w_bar), 2 * H * H * sizeof(float));
+    bulk_g2s(smem_u32(w_s), p.vec0_t, H * H * sizeof(float), smem_u32(&w_bar));
+    bulk_g2s(smem_u32(w_s + H * H), p.nrm0_t, H * H * sizeof(float), smem_u32(&w_bar));
+  }
   __shared__ __align__(16) float xs[PH_G][H];
   __shared__ __align__(16) float hid[2][PH_G][H];
   __shared__ float outv[PH_G][8];
@@ -254,11 +266,11 @@ pool_head_kernel(PoolHeadArgs p) {
       const int beg = p.graph_ptr[g], end = p.graph_ptr[g + 1];
       const float4 gw = reinterpret_cast<const float4*>(p.pool_w)[lane];
       const float gb = p.pool_b[0];
-      // online softmax over the rows (one pass: the row is in registers when its gate is known)
+      // online softmax over the un-masked rows (one pass: the row is in registers when its gate is known); the mask
+      // bytes of 32 rows arrive with one load and four rows are in flight at a time - a load per row behind a mask
+      // byte behind the previous row made this loop a chain of L2 round trips
       float m = -INFINITY;
-      for (int r = beg; r < end; ++r) {
-        if (!p.cluster_mask[r]) continue;
-        const float4 x = reinterpret_cast<const float4*>(p.x + (size_t)r * H)[lane];
+      auto take = [&](const float4 x, int r) {
         float d = x.x * gw.x + x.y * gw.y + x.z * gw.z + x.w * gw.w;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
@@ -270,6 +282,25 @@ pool_head_kernel(PoolHeadArgs p) {
         num.x = fmaf(num.x, sc, e * x.x); num.y = fmaf(num.y, sc, e * x.y);
         num.z = fmaf(num.z, sc, e * x.z); num.w = fmaf(num.w, sc, e * x.w);
         m = mn;
+      };
+      for (int base = beg; base < end; base += 32) {
+        const int rr = base + lane;
+        uint32_t bits = __ballot_sync(0xffffffffu, rr < end && p.cluster_mask[rr]);
+        while (bits) {
+          int r[4];
+          float4 x[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            r[i] = -1;
+            if (bits) { r[i] = base + __ffs(bits) - 1; bits &= bits - 1; }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (r[i] >= 0) x[i] = reinterpret_cast<const float4*>(p.x + (size_t)r[i] * H)[lane];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (r[i] >= 0) take(x[i], r[i]);
+        }
       }
     }
     const float inv = (den > 0.f) ? 1.f / (den + 1e-16f) : 0.f;
@@ -282,8 +313,9 @@ pool_head_kernel(PoolHeadArgs p) {
   // ---- first layers of both heads: thread = (head, output channel), all 8 graphs per weight load ---------
   {
     const int o = tid & (H - 1), hd = tid >> 7;
-    const float* __restrict__ wt = hd ? p.nrm0_t : p.vec0_t;
+    const float* __restrict__ wt = w_s + hd * (H * H);
     const float b = hd ? p.nrm0_b[o] : p.vec0_b[o];
+    mbar_wait(smem_u32(&w_bar), 0);
     float acc[PH_G];
 #pragma unroll
     for (int g = 0; g < PH_G; ++g) acc[g] = b;
@@ -342,7 +374,11 @@ pool_head_kernel(PoolHeadArgs p) {
 
 int pool_head(const PoolHeadArgs& a, cudaStream_t s) {
   if (a.n_graphs == 0) return CNS_OK;
-  pool_head_kernel<<<(unsigned)ceil_div(a.n_graphs, PH_G), 256, 0, s>>>(a);
+  static unsigned long long configured = 0;
+  constexpr int PH_SMEM = 2 * H * H * (int)sizeof(float);
+  if (first_use_on_device(configured))
+    CNS_CUDA_CHECK(cudaFuncSetAttribute(pool_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
+  pool_head_kernel<<<(unsigned)ceil_div(a.n_graphs, PH_G), 256, PH_SMEM, s>>>(a);
   CNS_LAUNCH_CHECK();
   return CNS_OK;
 }
