@@ -33,9 +33,6 @@
 namespace cns {
 
 constexpr int TC_W_BYTES = 128 * 128 * 2;         // one weight matrix, 16-bit
-#ifndef TC_NPRE
-#define TC_NPRE 2
-#endif
 constexpr int TC_NW = 5;                          // pos_nn.1, -(A0 lin_src), lin, A0 pos_nn.1, attn_nn.1
 
 // ---- weight image: fp32 (k-major "chain" [5][k][o]) -> 16-bit swizzled A-operand tiles ----------
@@ -96,8 +93,10 @@ constexpr int TC_FIRST_W_BYTES = 128 * 128;       // one SWIZZLE_128B tile of 12
 __host__ __device__ constexpr size_t tc_first_bytes(int slots, int tn) {
   return tc_mma_first(slots, tn, false) ? (size_t)TC_FIRST_W_BYTES + (size_t)slots * tn * 128 : 0;
 }
+constexpr int TC_NSTG = 8;                        // a' rows staged in shared memory per tile (its first 8 segment starts)
 __host__ __device__ constexpr size_t tc_smem_bytes(int slots, int tn) {
-  return tc_main_bytes(slots, tn) + tc_first_bytes(slots, tn) + 256 + (size_t)slots * 2 * tn * sizeof(int) + 1024;
+  return tc_main_bytes(slots, tn) + tc_first_bytes(slots, tn) + (size_t)slots * TC_NSTG * 128 * sizeof(float) + 256 +
+         (size_t)slots * 2 * tn * sizeof(int) + 1024;
 }
 
 template <int TN, bool BF16, int SLOTS_>
@@ -111,7 +110,6 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
   constexpr int TMEM_W_COL0 = SLOTS * 2 * TN;
   static_assert(TMEM_W_COL0 + TMEM_W * 64 <= 512, "tensor memory budget");
   constexpr int U_ROW = TN * 2;                      // bytes per channel row of the MN-major u tile
-  constexpr int NPRE = TC_NPRE;                      // a' rows prefetched per tile (first NPRE segment starts)
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment: align by hand (1 KB of slack is allocated)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -120,7 +118,8 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
   constexpr bool MMA_FIRST = tc_mma_first(SLOTS, TN, BF16);
   unsigned char* wfirst_s = smem + tc_main_bytes(SLOTS, TN);     // first-layer A tile, then SLOTS input tiles [TN][128 B]
   unsigned char* in16_s = wfirst_s + TC_FIRST_W_BYTES;
-  unsigned char* tail = smem + tc_main_bytes(SLOTS, TN) + tc_first_bytes(SLOTS, TN);
+  float* astg_s = reinterpret_cast<float*>(smem + tc_main_bytes(SLOTS, TN) + tc_first_bytes(SLOTS, TN));   // [SLOTS][TC_NSTG][128]
+  unsigned char* tail = reinterpret_cast<unsigned char*>(astg_s + SLOTS * TC_NSTG * 128);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);            // [0] = weights landed, [1+s] = MMAs of slot s done
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tail + 128);
   int* ci_s = reinterpret_cast<int*>(tail + 256);                // [SLOTS][2][TN] cluster id per edge (-1: padding), double-buffered
@@ -381,10 +380,12 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     const uint32_t u_xor = (uint32_t)(((t & 7) * U_ROW) >> 7) & (uint32_t)(U_ROW / 16 - 1);
 
     // segment-start bits of a tile (bit e: ci[e] != ci[e-1]; warp-uniform registers, no per-element LDS) and the
-    // a'[cluster][t] = (A0 (a_dst + b_pos1) + b_attn0)[t] rows of its first NPRE segment starts
+    // a'[cluster][t] = (A0 (a_dst + b_pos1) + b_attn0)[t] values of its first TC_NSTG segment starts: staged in shared
+    // memory by cp.async a tile ahead (no registers held, no scoreboard wait when the epilogue reaches a segment start;
+    // register prefetch of 2 .. 8 rows was measured: the more rows, the slower)
     uint32_t seg_mask[TN / 32], seg_next[TN / 32];
-    float aq[NPRE], aq_next[NPRE];
-    auto seg_and_prefetch = [&](const int* ci, uint32_t (&sm)[TN / 32], float (&a)[NPRE]) {
+    float* const astg = astg_s + s * (TC_NSTG * 128) + t;          // this thread's column: astg[k * 128]
+    auto seg_and_prefetch = [&](const int* ci, uint32_t (&sm)[TN / 32]) {
 #pragma unroll
       for (int c0 = 0; c0 < TN; c0 += 32) {
         const int e = c0 + lane;
@@ -393,19 +394,19 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
       }
       uint32_t m0 = sm[0];
       uint32_t m1 = (TN > 32) ? sm[(TN > 32) ? 1 : 0] : 0u;
-#pragma unroll
-      for (int i = 0; i < NPRE; ++i) {
-        a[i] = 0.f;
-        int q = -1;
+#pragma unroll 1
+      for (int k = 0; k < TC_NSTG; ++k) {
+        int q;
         if (m0) { q = __ffs(m0) - 1; m0 &= m0 - 1; }
         else if (TN > 32 && m1) { q = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
-        if (q >= 0) {
-          const int c = ci[q];
-          if (c >= 0) a[i] = p.a_dst[(size_t)c * H + t];
-        }
+        else break;
+        const int c = ci[q];
+        if (c >= 0) cp_async4(smem_u32(astg + k * 128), p.a_dst + (size_t)c * H + t);
+        else astg[k * 128] = 0.f;
       }
+      cp_async_commit();
     };
-    seg_and_prefetch(ci_base, seg_mask, aq);       // tile 0
+    seg_and_prefetch(ci_base, seg_mask);           // tile 0
 
     for (int it = 0;; ++it) {
       const int g = tile_of(it);
@@ -547,10 +548,8 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
 #pragma unroll
               for (int h2 = 0; h2 < 2; ++h2) {
                 if (m8 & (1u << (q + h2))) {
-                  if (nseg < NPRE) {
-                    adb = aq[0];
-#pragma unroll
-                    for (int i = 0; i + 1 < NPRE; ++i) aq[i] = aq[i + 1];
+                  if (nseg < TC_NSTG) {
+                    adb = astg[nseg * 128];
                   } else {
                     const int c = ci[cg * 8 + q + h2];
                     adb = (c >= 0) ? p.a_dst[(size_t)c * H + t] : 0.f;
@@ -564,8 +563,10 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
           }
           *reinterpret_cast<uint4*>(u_row + (((uint32_t)cg ^ u_xor) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         };
-        // (a two-buffer software prefetch of the next group's TMEM load was measured: no gain, the doubled loop bodies
-        // cost as much in instruction-cache misses as the exposed load latency they hide)
+        cp_async_wait_all();             // this thread's staged a' values (issued a tile ago)
+        // (16 columns per TMEM load - two exposed load latencies per tile instead of four - measured slower, 0.200 against
+        // 0.190 ms, like the two-buffer software prefetch before it: the larger loop body costs more in instruction-cache
+        // misses than the load latency it hides)
 #pragma unroll 1
         for (int cg = 0; cg < TN / 8; ++cg) {
           float acc[8];
@@ -575,7 +576,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         }
       }
       publish_and_issue(1);
-      seg_and_prefetch(ci_base + ((it + 1) & 1) * TN, seg_next, aq_next);   // tile i+1: its a' rows land during the softmax
+      seg_and_prefetch(ci_base + ((it + 1) & 1) * TN, seg_next);   // tile i+1: its a' values land during the softmax
 
       // ---- final: per-channel online segment softmax of L weighting V ---------------------------
       // softmax is shift-invariant per channel, so the attn_nn.1 bias drops out; the value bias b_p1
@@ -637,8 +638,6 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
       }
 #pragma unroll
       for (int i = 0; i < TN / 32; ++i) seg_mask[i] = seg_next[i];
-#pragma unroll
-      for (int i = 0; i < NPRE; ++i) aq[i] = aq_next[i];
     }
   }
 
