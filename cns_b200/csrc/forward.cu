@@ -67,6 +67,7 @@ static void carve(Arena& ar, const cns_batch* b, FwdBuffers& f, const SaveBuffer
 
 // target-side results kept across frames (cns_target_cache_create)
 struct cns_target_cache {
+  long long uid;                    // unique per created cache (a destroyed cache's address may come back: the graph cache keys on this)
   int device; int precision; long long weights_version;
   int64_t n_clusters, n_graphs;
   int has_tiles;
@@ -422,7 +423,7 @@ static int forward_graphed(cns_handle* h, const cns_batch* b, const float* hidde
   const void* ptrs[6] = {hidden_in, vel_si_vec, vel_si_norm, hidden_out, vel, workspace};
   key = fnv(key, ptrs, sizeof(ptrs));
   const long long mode[8] = {h->precision, h->weights_version, h->timing, h->tc_tile_n, h->tc_slots, 0,
-                             h->no_fused_backbone * 2 + h->no_split_encoder + 4 * h->no_tc_cluster_pre, b->target_cache ? b->target_cache->weights_version : 0};
+                             h->no_fused_backbone * 2 + h->no_split_encoder + 4 * h->no_tc_cluster_pre, b->target_cache ? b->target_cache->uid : 0};
   key = fnv(key, mode, sizeof(mode));
   if (key == 0) key = 1;
   GraphEntry* hit = nullptr; GraphEntry* victim = &gc->e[0];
@@ -541,6 +542,8 @@ int cns_target_cache_create(cns_handle* h, const cns_batch* b, void* stream, cns
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t C = b->n_clusters, B = b->n_graphs;
   cns_target_cache* c = new cns_target_cache();
+  static long long next_uid = 0;
+  c->uid = ++next_uid;
   c->device = h->device; c->precision = h->precision; c->weights_version = h->weights_version;
   c->n_clusters = C; c->n_graphs = B;
   int* tmp = nullptr; int* scratch = nullptr; int* err = nullptr;

@@ -74,27 +74,41 @@ gemm_tc_kernel(const __grid_constant__ GemmTcArgs p) {
   } else {
     // ---- A tile: fp32 rows -> 16-bit SWIZZLE_128B, 16 bytes (8 elements) per store ----------------
     const int chunks_per_row = K / 8;
+    if (p.centers) {
+      // centre-feature producer (K = 128): this thread owns 8 channels (k .. k+7) of rows tid / 16 + 16 j, j < 8: the
+      // in_enc weights are loaded once, the eight centre indices and then the eight coordinate pairs in one batch each
+      // (a load per item behind the previous item's shared-memory store was a chain of 16 L2 round trips)
+      const int k = (tid & 15) * 8, r0 = tid >> 4;
+      float2 cw[8]; float cb[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { cw[i] = __ldg(reinterpret_cast<const float2*>(p.w_in) + k + i); cb[i] = __ldg(p.b_in + k + i); }
+      int64_t ctr[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const int64_t m = m0 + r0 + 16 * j; ctr[j] = m < p.m ? p.centers[m] : -1; }
+      float2 f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = ctr[j] >= 0 ? reinterpret_cast<const float2*>(p.ctr_xy)[ctr[j]] : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int row = r0 + 16 * j;
+        const int64_t m = m0 + row;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = ctr[j] >= 0 ? fmaxf(fmaf(cw[i].y, f[j].y, fmaf(cw[i].x, f[j].x, cb[i])), 0.f) : 0.f;
+        *reinterpret_cast<uint4*>(a_s + sw128_off(128, row, k)) =
+            make_uint4(pack2<BF16>(v[0], v[1]), pack2<BF16>(v[2], v[3]), pack2<BF16>(v[4], v[5]), pack2<BF16>(v[6], v[7]));
+        if (k == 0 && ctr[j] >= 0) {
+          reinterpret_cast<float2*>(p.pos_out)[m] = reinterpret_cast<const float2*>(p.ctr_pos)[ctr[j]];
+          p.clu_graph[m] = p.node_graph ? (int)p.node_graph[ctr[j]] : 0;
+        }
+      }
+    } else
     for (int q = tid; q < 128 * chunks_per_row; q += 256) {
       const int row = q / chunks_per_row, kc8 = q % chunks_per_row;
       const int k = kc8 * 8;
       const int64_t m = m0 + row;
       float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-      if (m < p.m && p.centers) {
-        // centre-feature producer: 8 channels of relu(in_enc(x_tar[centre])) (K = 2: cheaper than reading a row)
-        const int64_t ctr = p.centers[m];
-        const float2 f = reinterpret_cast<const float2*>(p.ctr_xy)[ctr];
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 w = __ldg(reinterpret_cast<const float2*>(p.w_in) + k + i);
-          v[i] = fmaxf(fmaf(w.y, f.y, fmaf(w.x, f.x, __ldg(p.b_in + k + i))), 0.f);
-        }
-        lo = make_float4(v[0], v[1], v[2], v[3]); hi = make_float4(v[4], v[5], v[6], v[7]);
-        if (kc8 == 0) {
-          reinterpret_cast<float2*>(p.pos_out)[m] = reinterpret_cast<const float2*>(p.ctr_pos)[ctr];
-          p.clu_graph[m] = p.node_graph ? (int)p.node_graph[ctr] : 0;
-        }
-      } else if (m < p.m) {
+      if (m < p.m) {
         const float* src = (k < p.k1) ? p.x1 + m * p.k1 + k : p.x2 + m * p.k2 + (k - p.k1);
         lo = *reinterpret_cast<const float4*>(src);
         hi = *reinterpret_cast<const float4*>(src + 4);
