@@ -128,7 +128,7 @@ int dw_gemm(const DwGemmArgs& a, cudaStream_t s) {
   CNS_REQUIRE(a.na % 128 == 0 && a.nb % 128 == 0, "dw_gemm: dims must be multiples of 128");
   const int tiles = (a.na / 128) * (a.nb / 128);
   const int64_t m1 = a.m > 0 ? a.m : 1;
-  int slabs = ceil_div(m1, 256);
+  int slabs = ceil_div(m1, 64);          // (256-row slabs left 19 CTAs per tile at 4.8 k cluster rows)
   if (a.allow_split && tiles == 1 && a.b_tiles0 >= 1 && a.m >= 4096 && a.lda % 4 == 0 && a.ldb0 % 4 == 0) {
     // long reductions of a single 128 x 128 tile: tensor cores with split operands, one partial per persistent CTA
     int rc = dw_split(a.m, a.a, a.lda, a.b0, a.ldb0, a.partial, a.colsum_out ? a.colsum_partial : nullptr, a.max_slabs, &slabs, s);
@@ -245,7 +245,9 @@ int dw_small(const DwSmallArgs& a, cudaStream_t s) {
   CNS_REQUIRE(a.q >= 1 && a.q <= 8, "dw_small: q must be 1..8");
   CNS_REQUIRE(a.ones_out == nullptr || (a.s != nullptr && a.q <= 7), "dw_small: the fused column sum needs s and q <= 7");
   const int64_t m1 = a.m > 0 ? a.m : 1;
-  int slabs = ceil_div(m1, DWS_ROWS);
+  // short reductions (cluster / graph rows): 32-row slabs - a thread's serial walk over its rows is the whole cost there
+  // (128 rows = 32 dependent L2 round trips for 38 CTAs); long ones (one row per keypoint->cluster edge) keep 128
+  int slabs = ceil_div(m1, m1 <= 16384 ? 32 : DWS_ROWS);
   if (slabs > a.max_slabs) slabs = a.max_slabs;
   int rows_per_slab = (int)((m1 + slabs - 1) / slabs);
   if (rows_per_slab > DWS_ROWS) {          // more rows than the smem staging holds: use more, smaller slabs

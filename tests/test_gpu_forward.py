@@ -58,7 +58,7 @@ def test_golden_fixtures(net, name):
 
 
 @pytest.mark.parametrize("sizes,missing", [([40], 0.0), ([5, 16, 17, 64], 0.2), ([512] * 6, 0.1),
-                                           ([24, 100, 300, 512, 33], 0.3), ([2000], 0.05)])
+                                           ([24, 100, 300, 512, 33], 0.3), ([2000], 0.05), ([1500, 2048, 900], 0.1)])
 def test_forward_matches_oracle_recurrent(net, state_dict, sizes, missing):
     """Ragged batches, missing keypoints, clusters larger than a 64-edge softmax piece (N=2000),
     hidden state carried over 3 frames with the camera moved by the predicted velocity."""
@@ -76,7 +76,9 @@ def test_forward_matches_oracle_recurrent(net, state_dict, sizes, missing):
 
 
 @pytest.mark.parametrize("prec", ["f16", "bf16"])
-@pytest.mark.parametrize("sizes,missing", [([24, 100, 300, 512, 33], 0.3), ([512] * 6, 0.1), ([7], 0.0), ([2000], 0.05)])
+@pytest.mark.parametrize("sizes,missing", [([24, 100, 300, 512, 33], 0.3), ([512] * 6, 0.1), ([7], 0.0), ([2000], 0.05),
+                                           ([1500, 2048, 900], 0.1)])     # graphs of 30-45 clusters: few graphs per backbone tile,
+                                                                          # more than 32 rows per graph in the pooling kernel
 def test_tensor_core_modes_match_oracle(state_dict, prec, sizes, missing):
     """tcgen05 paths (encoder edge kernel + node GEMMs with 16-bit operands, fp32 accumulation in
     TMEM): 5 recurrent frames, hidden carried, within the per-dtype tolerance of the fp64 oracle."""
