@@ -141,13 +141,17 @@ def _resolve_device(device):
 
 
 def build_graphs_device(point_sets: Sequence[np.ndarray], damping=0.9, max_iter=200, convergence_iter=15,
-                        device=None, return_similarity=False) -> List[DeviceLayout]:
+                        device=None, return_similarity=False, noise_generator=None) -> List[DeviceLayout]:
+    """`noise_generator` (a CUDA torch.Generator): draw Affinity Propagation's tie-breaking noise on the device instead of
+    from numpy's global RandomState.  Same distribution, not scikit-learn's numbers - for callers that generate random
+    training scenes (DeviceSceneBatch), where 17 M host-drawn normals per 256 scenes were the largest part of a re-init."""
     # the library launches on the CURRENT device: make `device` current for the duration of the call
     with torch.cuda.device(_resolve_device(device)):
-        return _build_graphs_device(point_sets, damping, max_iter, convergence_iter, _resolve_device(device), return_similarity)
+        return _build_graphs_device(point_sets, damping, max_iter, convergence_iter, _resolve_device(device), return_similarity,
+                                    noise_generator)
 
 
-def _build_graphs_device(point_sets, damping, max_iter, convergence_iter, device, return_similarity):
+def _build_graphs_device(point_sets, damping, max_iter, convergence_iter, device, return_similarity, noise_generator=None):
     """Clustering + layout of every point set (each with more than 16 points: smaller sets never reach the
     clustering in the reference, graph_gen.py:137-144) in ONE batch of device calls.  Consumes numpy's global
     RandomState like the sequential host construction (one (n, n) standard-normal draw per set, in order), provided
@@ -179,16 +183,22 @@ def _build_graphs_device(point_sets, damping, max_iter, convergence_iter, device
     # (in the plane that means: all points coincide, i.e. min(S) == 0)
     smin = torch.segment_reduce(S, "min", lengths=torch.from_numpy(ns * ns).to(dev)).cpu().numpy()
     degenerate = [bool(ns[g] == 1 or smin[g] == 0.0) for g in range(G)]
-    rs = np.random.mtrand._rand                                          # check_random_state(None)
-    noise = torch.empty(NM, dtype=torch.float64).pin_memory() if NM < (1 << 28) else torch.empty(NM, dtype=torch.float64)
-    nz = noise.numpy()
-    for g in range(G):
-        n = int(ns[g])
-        if degenerate[g]:
-            nz[int(mat_off[g]):int(mat_off[g + 1])] = 0.0
-        else:
-            nz[int(mat_off[g]):int(mat_off[g + 1])] = rs.standard_normal(size=(n, n)).reshape(-1)
-    noise_d = noise.to(dev, non_blocking=True)
+    if noise_generator is not None:
+        noise_d = torch.randn(NM, dtype=torch.float64, device=dev, generator=noise_generator)
+        for g in range(G):
+            if degenerate[g]:
+                noise_d[int(mat_off[g]):int(mat_off[g + 1])] = 0.0
+    else:
+        rs = np.random.mtrand._rand                                          # check_random_state(None)
+        noise = torch.empty(NM, dtype=torch.float64).pin_memory() if NM < (1 << 28) else torch.empty(NM, dtype=torch.float64)
+        nz = noise.numpy()
+        for g in range(G):
+            n = int(ns[g])
+            if degenerate[g]:
+                nz[int(mat_off[g]):int(mat_off[g + 1])] = 0.0
+            else:
+                nz[int(mat_off[g]):int(mat_off[g + 1])] = rs.standard_normal(size=(n, n)).reshape(-1)
+        noise_d = noise.to(dev, non_blocking=True)
     S_raw = S.clone() if return_similarity else None
     L.check(lib.cns_ap_prepare(L.ptr(S), L.ptr(noise_d), L.ptr(pref), L.ptr(t_pt), L.ptr(t_mat), L.ptr(t_rg), NR, stream),
             "cns_ap_prepare")

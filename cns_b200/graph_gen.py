@@ -133,14 +133,15 @@ class GraphGenerator(object):
         return cls.CLUSTER_BACKEND or ("device" if _cuda_present() else "host")
 
     @classmethod
-    def build_many(cls, target_point_sets, device=None):
+    def build_many(cls, target_point_sets, device=None, noise_generator=None):
         """Generators for many targets with ONE batched device clustering + layout call.  Equal to the reference's
         sequential construction as long as no set needs the KMeans(4) fallback (the fallback draws from numpy's
-        global RNG after, not between, the AP noise draws)."""
+        global RNG after, not between, the AP noise draws).  `noise_generator`: see cluster.build_graphs_device."""
         from .cluster import build_graphs_device
         sets = [np.asarray(p) for p in target_point_sets]
         big = [k for k, p in enumerate(sets) if len(p) > 16]
-        layouts = dict(zip(big, build_graphs_device([sets[k] for k in big], device=device or cls.CLUSTER_DEVICE))) if big else {}
+        layouts = dict(zip(big, build_graphs_device([sets[k] for k in big], device=device or cls.CLUSTER_DEVICE,
+                                                    noise_generator=noise_generator))) if big else {}
         return [cls(p, layout=layouts.get(k)) for k, p in enumerate(sets)]
 
     @classmethod

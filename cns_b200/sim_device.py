@@ -54,20 +54,19 @@ def so3_log(R: torch.Tensor) -> torch.Tensor:
     scale = torch.where(small, 0.5 + th * th / 12, th / (2 * torch.sin(th).clamp_min(1e-12)))
     out = v * scale[:, None]
     near_pi = th > math.pi - 1e-4
-    if bool(near_pi.any()):                      # axis from the symmetric part (rare)
-        Rp = R[near_pi]
-        d = (Rp.diagonal(dim1=-2, dim2=-1) + 1) / 2
-        ax = d.clamp_min(0).sqrt()
-        i = d.argmax(-1)
-        rows = torch.arange(Rp.shape[0], device=R.device)
-        sgn = torch.sign((Rp + Rp.transpose(1, 2))[rows, i, :])
-        sgn[rows, i] = 1
-        ax = ax * sgn
-        ax = ax / ax.norm(dim=-1, keepdim=True)
-        flip = torch.sign((v[near_pi] * ax).sum(-1, keepdim=True))
-        flip[flip == 0] = 1
-        out[near_pi] = ax * flip * th[near_pi][:, None]
-    return out
+    # axis from the symmetric part near pi (rare) - computed for every row and selected, so that no device -> host read
+    # (`if near_pi.any()`) stalls the caller four times per frame
+    d = (R.diagonal(dim1=-2, dim2=-1) + 1) / 2
+    ax = d.clamp_min(0).sqrt()
+    i = d.argmax(-1)
+    rows = torch.arange(R.shape[0], device=R.device)
+    sgn = torch.sign((R + R.transpose(1, 2))[rows, i, :])
+    sgn[rows, i] = 1
+    ax = ax * sgn
+    ax = ax / ax.norm(dim=-1, keepdim=True).clamp_min(1e-300)
+    flip = torch.sign((v * ax).sum(-1, keepdim=True))
+    flip = torch.where(flip == 0, torch.ones_like(flip), flip)
+    return torch.where(near_pi[:, None], ax * flip * th[:, None], out)
 
 
 def se3_inv(T: torch.Tensor) -> torch.Tensor:
@@ -130,8 +129,10 @@ class DeviceSceneBatch(object):
     def __init__(self, batch_size: int, rng: np.random.Generator, device="cuda:0", max_points: int = 512,
                  max_steps: int = 200, missing=(0.0, 0.2), refresh_every: int = 0, aug: bool = False,
                  supervisor: str = "pbvs_straight", long_seq: bool = False, reinit: str = "scene", discard: bool = False,
-                 min_points: int = 4):
+                 min_points: int = 4, device_noise: bool = True):
         assert reinit in ("scene", "all")
+        self.device_noise = device_noise
+        self._intr_dev = None
         self.B, self.rng, self.dev = batch_size, rng, torch.device(device)
         self.max_points, self.max_steps, self.missing, self.refresh_every = max_points, max_steps, missing, refresh_every
         self.min_points = min_points
@@ -150,7 +151,10 @@ class DeviceSceneBatch(object):
         protos = [(synth.sample_points(rng, int(rng.integers(self.min_points, self.max_points + 1))), synth.sample_target_pose(rng))
                   for _ in range(self.B)]
         tars = [synth.project_norm(T, P) for P, T in protos]
-        gens = GraphGenerator.build_many(tars, device=self.dev) if GraphGenerator.backend() == "device" else [GraphGenerator(t) for t in tars]
+        # random training scenes: the clustering's tie-breaking noise is drawn on the device (same distribution as
+        # scikit-learn's host draw, which costs 0.25 s per 256 scenes)
+        gens = GraphGenerator.build_many(tars, device=self.dev, noise_generator=self.gen if self.device_noise else None) \
+            if GraphGenerator.backend() == "device" else [GraphGenerator(t) for t in tars]
         return [synth.Scene(rng, len(P), generator=g, points=P, tar_wcT=T) for (P, T), g in zip(protos, gens)]
 
     # -- static part: geometry, target graphs ------------------------------------------------------------
@@ -222,9 +226,11 @@ class DeviceSceneBatch(object):
         else:                                              # 10 % of the keypoints land anywhere in the image
             mism = pos < self.n_mismatch[so]
             u = torch.rand(self.N, 2, generator=self.gen, device=dev, dtype=torch.float64)
-            rnd = (u * torch.tensor([intr[0], intr[1]], dtype=torch.float64, device=dev)
-                   - torch.tensor([intr[4], intr[5]], dtype=torch.float64, device=dev)) / \
-                torch.tensor([intr[2], intr[3]], dtype=torch.float64, device=dev)
+            if self._intr_dev is None:             # (three host->device constants per frame cost 0.9 ms)
+                self._intr_dev = tuple(torch.tensor(v, dtype=torch.float64, device=dev)
+                                       for v in ([intr[0], intr[1]], [intr[4], intr[5]], [intr[2], intr[3]]))
+            wh, cxy, fxy = self._intr_dev
+            rnd = (u * wh - cxy) / fxy
             cur_xy = torch.where(mism[:, None], rnd, cur_xy)
         scale = 0.0005 if self.long_seq else 0.002
         cur_xy = cur_xy + scale * (torch.rand(self.N, 2, generator=self.gen, device=dev, dtype=torch.float64) * 2 - 1)

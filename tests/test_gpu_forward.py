@@ -321,8 +321,10 @@ def test_target_cache_is_tied_to_weights_and_shapes(net):
     assert torch.equal(servo.step(xy, vis), v1)
 
 
-def test_servo_frames_in_flight_keep_their_order(net):
-    """submit/result with two frames in flight: results equal the one-at-a-time loop, hidden state carried."""
+@pytest.mark.parametrize("depth", [2, 3])
+def test_servo_frames_in_flight_keep_their_order(net, depth):
+    """submit/result with `depth` frames in flight (every slot on its own compute stream): results equal the one-at-a-time
+    loop, hidden state carried from slot to slot."""
     from cns_b200.servo import BatchedServo
     rng = np.random.default_rng(12)
     np.random.seed(12)
@@ -337,13 +339,14 @@ def test_servo_frames_in_flight_keep_their_order(net):
             s.step(synth.pbvs_straight(s.cur_wcT, s.tar_wcT) * 2)
     a = BatchedServo(net, gens, tpo, "cuda:0")
     one = [a.step(*f).clone() for f in frames]
-    b = BatchedServo(net, gens, tpo, "cuda:0")
+    b = BatchedServo(net, gens, tpo, "cuda:0", depth=depth)
     tickets, two = [], []
     for i, f in enumerate(frames):
         tickets.append(b.submit(*f))
-        if i >= 1:
-            two.append(b.result(tickets[i - 1]).clone())
-    two.append(b.result(tickets[-1]).clone())
+        if i >= depth - 1:
+            two.append(b.result(tickets[i - depth + 1]).clone())
+    for t in tickets[len(two):]:
+        two.append(b.result(t).clone())
     for x, y in zip(one, two):
         assert torch.equal(x, y)
 
