@@ -173,8 +173,9 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   // mantissa on BOTH the edge-level and the recurrent cluster-level layers the hidden state drifts past
   // the 2e-2 budget after a few frames, so bf16 mode keeps them in fp32 (measured).
   const bool tc = h->precision == CNS_PREC_F16;
-  // fp32 mode: the same GEMMs with bf16 (hi, lo) operand splits (three tensor-core products, ~1e-5 of fp64)
-  const bool tc2 = h->precision == CNS_PREC_FP32 && !h->no_split_encoder;
+  // fp32 mode: the same GEMMs with bf16 (hi, lo) operand splits (three tensor-core products, ~1e-5 of fp64); bf16 mode takes
+  // them too (its cluster level has to stay at fp32 accuracy, see above - on the tensor cores instead of the FFMA kernel)
+  const bool tc2 = (h->precision == CNS_PREC_FP32 && !h->no_split_encoder) || (h->precision == CNS_PREC_BF16 && !h->no_split_gemm);
   const int tci = (h->precision == CNS_PREC_BF16) ? 0 : 1;
   // whole-graph row tiles: the three backbone blocks as one kernel (backbone_fused.cu)
   const bool fused = tc && dense_cur && dense_tar && b->max_clusters_per_graph > 0 && b->max_clusters_per_graph <= 128 &&
