@@ -149,7 +149,8 @@ class GraphVS(nn.Module):
         self.hidden_dim = hidden_dim
         self.precision = precision
         self._handles = {}       # device index -> (_lib.Handle, weight version)
-        self._workspaces = {}    # device index -> uint8 tensor
+        self._workspaces = {}    # (device index, key) -> uint8 tensor
+        self._retired_workspaces = []
         self._names = None
         self._param_cache = None
 
@@ -233,6 +234,11 @@ class GraphVS(nn.Module):
     def _workspace(self, idx: int, nbytes: int, key: str = "fwd") -> torch.Tensor:
         ws = self._workspaces.get((idx, key))
         if ws is None or ws.numel() < nbytes:
+            if ws is not None:
+                # kernels enqueued on another stream than the one this was allocated under may still use the old block
+                # (BatchedServo's slots): keep it alive instead of handing it back to the caching allocator.  Sizes grow
+                # geometrically, so only a handful of blocks are ever retired.
+                self._retired_workspaces.append(ws)
             ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=torch.device("cuda", idx))
             self._workspaces[(idx, key)] = ws
         return ws
