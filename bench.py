@@ -446,7 +446,10 @@ def main():
             servo.reset()
             vel = servo.step(*frames[i % N_ROTATE])
         ref = net(resident[(args.warmup + PRIME - 1) % N_ROTATE], None).vel.cpu()
-        assert torch.equal(vel, ref), "servo path and batch path disagree"
+        # (the servo path takes the target side from the per-target cache - values kept in f16 - so the two paths agree to
+        # the operand rounding of the mode, not bit for bit)
+        err = float((vel - ref).abs().max() / ref.abs().max())
+        assert err < (1e-5 if args.precision == "fp32" else 5e-3), "servo path and batch path disagree (%.2e)" % err
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()

@@ -117,6 +117,7 @@ struct cns_handle {
   int tc_tile_n;                                        // edges per tensor-core tile (32 or 64)
   int tc_slots;                                         // tiles in flight per SM of the 32-edge kernel: 4, 5 or 6 (CNS_TC_SLOTS)
   int no_split_gemm;                                    // CNS_NO_SPLIT_GEMM=1: backward GEMMs stay on the fp32 FFMA kernel (A-B runs)
+  int no_edge_cache;                                    // CNS_NO_EDGE_CACHE=1: target caches keep no per-keypoint logits / values (A-B runs)
   int no_tc_cluster_pre;                                // CNS_NO_TC_CLUSTER_PRE=1: per-cluster encoder terms stay on the FFMA kernel (A-B runs)
   int no_fused_backbone;                                // CNS_NO_FUSED_BACKBONE=1: keep the per-layer kernels (debugging / A-B runs)
   // optional CUDA-event timing of the dominant kernel (encoder edge kernel), see cns_profile_*
@@ -133,9 +134,10 @@ struct cns_handle {
   struct cns_target_cache* servo_tcache; void* servo_tkey; size_t servo_tkey_bytes;
   // fork/join pair for work that is independent of the index preparation (per-cluster encoder terms), created lazily
   cudaStream_t side_stream; cudaEvent_t side_fork, side_join, side_join2;
+  cudaStream_t low_stream; cudaEvent_t low_fork, low_join;      // lowest-priority stream: cached target side beside the edge kernel
   // CUDA-graph cache of cns_graphvs_forward (forward.cu): a call whose whole argument set (sizes, pointers, mode) was seen
   // before is replayed as one graph launch instead of ~10 kernel launches + 3 event fork/joins
   int use_graphs; void* graph_cache; cudaStream_t cap_stream;
-  long long graph_replays, graph_captures;
+  long long graph_replays, graph_captures, edge_cache_forwards;
   const float* P(int id) const { return raw + raw_off[id]; }
 };

@@ -323,7 +323,7 @@ enc_finish_kernel(EncFinishArgs p) {
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
           float* feat = p.clu_feat + ((size_t)side * p.n_clusters + c) * H;
-          if (p0 == p1) {
+          if (p0 == p1 || (p.cur_only && side == 1)) {      // (target side from a cache: already final)
             if (!p.fix_only) f[side] = feat[o];
           } else {
             const float* part = p.partial + (size_t)side * p.n_slots * 3 * H;
@@ -419,6 +419,7 @@ enc_fix_kernel(EncFinishArgs p) {
     const int beg = p.clu_rowptr[cc], end = p.clu_rowptr[cc + 1];
     float4* feat = reinterpret_cast<float4*>(p.clu_feat + ((size_t)side * p.n_clusters + cc) * H) + lane;
     if (end == beg) { *feat = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+    if (p.cur_only && side == 1) continue;               // target side from a cache: already final
     const int p0 = beg / p.piece_e, p1 = (end - 1) / p.piece_e;
     const float* part = p.partial + (size_t)side * p.n_slots * 3 * H;
     auto slot4 = [&](int pc, int which) { return reinterpret_cast<const float4*>(part + ((size_t)cc + pc) * 3 * H + which * H)[lane]; };

@@ -66,6 +66,9 @@ struct TcArgs {
   const unsigned char* w_first; // f16 mode: first-layer A tile (tc_mma_first)
   int n_tiles;                  // edge tiles of TN edges
   int tiles_per_chunk;          // consecutive tiles handled by one slot (per side)
+  int side_mode;                // 0: both sides (first half of the slot chunks = current frame, second half = target),
+                                // 1: current side only, 2: target side only
+  float* store_l; __half* store_v;   // STORE kernels: per-keypoint logits (log2 units, fp32) and values (f16) instead of the softmax
 };
 
 // =================================================================================================
@@ -96,10 +99,10 @@ __host__ __device__ constexpr size_t tc_first_bytes(int slots, int tn) {
 constexpr int TC_NSTG = 8;                        // a' rows staged in shared memory per tile (its first 8 segment starts)
 __host__ __device__ constexpr size_t tc_smem_bytes(int slots, int tn) {
   return tc_main_bytes(slots, tn) + tc_first_bytes(slots, tn) + (size_t)slots * TC_NSTG * 128 * sizeof(float) + 256 +
-         (size_t)slots * 2 * tn * sizeof(int) + 1024;
+         (size_t)slots * 4 * tn * sizeof(int) + 1024;
 }
 
-template <int TN, bool BF16, int SLOTS_>
+template <int TN, bool BF16, int SLOTS_, bool STORE = false>
 __global__ void __launch_bounds__(128 * SLOTS_, 1)
 enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ TcSmallW sw, const __grid_constant__ TcSmallH sh) {
   constexpr int SLOTS = SLOTS_;
@@ -123,6 +126,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);            // [0] = weights landed, [1+s] = MMAs of slot s done
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tail + 128);
   int* ci_s = reinterpret_cast<int*>(tail + 256);                // [SLOTS][2][TN] cluster id per edge (-1: padding), double-buffered
+  int* ej_s = ci_s + SLOTS * 2 * TN;                             // STORE: [SLOTS][2][TN] keypoint id per edge
 
   const EncEdgeArgs& p = args.e;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -307,10 +311,12 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     // chunks, one per slot, the first half of the chunks on the current-frame side, the second half on
     // the target side.  Consecutive tiles in one slot let a cluster cut by a tile boundary carry its
     // running (max, sum, acc) in registers; only chunk boundaries leave partials for enc_finish.
-    const int n_chunks_side = ((int)gridDim.x * SLOTS) / 2;
+    // (side_mode 1 / 2: every chunk belongs to that one side - the other side comes from a target cache, or this is the
+    // kernel that fills one)
+    const int n_chunks_side = args.side_mode ? (int)gridDim.x * SLOTS : ((int)gridDim.x * SLOTS) / 2;
     const int chunk_q = (int)blockIdx.x * SLOTS + s;
-    const int side = min(chunk_q / n_chunks_side, 1);
-    const int chunk = chunk_q - side * n_chunks_side;                       // >= n_chunks_side: the odd stream out, no tiles
+    const int side = args.side_mode ? args.side_mode - 1 : min(chunk_q / n_chunks_side, 1);
+    const int chunk = chunk_q - (args.side_mode ? 0 : side * n_chunks_side);   // >= n_chunks_side: the odd stream out, no tiles
     const int tpc = args.tiles_per_chunk;
     const int t_begin = min(chunk * tpc, args.n_tiles), t_end = min(t_begin + tpc, args.n_tiles);
     auto tile_of = [&](int it) { return t_begin + it; };
@@ -319,7 +325,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     bool c_live = false;
     // ... and of the tile after it (gathers in flight for a whole tile)
     float2 n_f = c_f, n_ps = c_f, n_pt = c_f, n_pc = c_f;
-    int n_cid = -1;
+    int n_cid = -1, n_j = 0;
     auto fetch_index = [&](int g) {
       idx_c = -1; idx_j = 0;
       if (g < t_end) {
@@ -328,7 +334,7 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
       }
     };
     auto fetch_coords = [&]() {                    // gathers of the tile whose indices sit in idx_* -> n_*
-      n_cid = idx_c;
+      n_cid = idx_c; n_j = idx_j;
       if (n_cid >= 0) {
         const float* __restrict__ fsrc = side ? p.x_tar : p.x_cur;
         const float* __restrict__ psrc = side ? p.pos_tar : p.pos_cur;
@@ -343,8 +349,9 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
     // round A (everyone has left tile i-1 by then) and is published by tile i's second slot barrier
     // (with the first layers on the tensor core only the slot's first warp consumes the coordinates; letting the other
     // three warps skip the gathers was measured SLOWER, 0.202 against 0.193 ms - all four keep them)
+    int* const ej_base = ej_s + s * 2 * TN;
     fetch_index(tile_of(0));
-    if (kp == 0) ci_base[pe] = idx_c;
+    if (kp == 0) { ci_base[pe] = idx_c; if (STORE) ej_base[pe] = idx_j; }
     fetch_coords();
     advance_coords();                              // c_* = tile 0
     fetch_index(tile_of(1));
@@ -520,7 +527,10 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
         }
       }
       publish_and_issue(0);
-      if (kp == 0) ci_base[((it + 1) & 1) * TN + pe] = n_cid;    // ci(i+1): its buffer was last read in tile i-1
+      if (kp == 0) {                                              // ci(i+1): its buffer was last read in tile i-1
+        ci_base[((it + 1) & 1) * TN + pe] = n_cid;
+        if (STORE) ej_base[((it + 1) & 1) * TN + pe] = n_j;
+      }
 
       // ---- epilogue: u = relu(U + a'[cluster]) -> buf0, MN-major ([channel][edge]: this thread's row) ---
       // (padding columns of the last tile keep finite garbage; they are never read back)
@@ -586,6 +596,25 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
       // (cluster -1) open a run that is never flushed.
       mbar_wait(done, done_parity); done_parity ^= 1;
       tc_fence_after();
+      if constexpr (STORE) {
+        // target-cache fill: logit (+ attn_nn.1 bias: shift-invariant, dropped) and value of every (keypoint, channel)
+        const int* const ej = ej_base + (it & 1) * TN;
+#pragma unroll 1
+        for (int cg = 0; cg < TN / 8; ++cg) {
+          float lg[8], vv[8];
+          tmem_ld8(t0 + cg * 8, lg);
+          tmem_ld8(t1 + cg * 8, vv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (ci[cg * 8 + q] >= 0) {
+              const size_t o = (size_t)ej[cg * 8 + q] * H + t;
+              args.store_l[o] = lg[q];
+              args.store_v[o] = __float2half_rn(vv[q]);
+            }
+          }
+        }
+      } else
       {
         // logits arrive in log2 units (log2(e) is folded into the attn_nn.1 weight image): one ex2, no multiply
         auto update = [&](float l, float v) {
@@ -648,10 +677,10 @@ enc_edge_tc_kernel(const __grid_constant__ TcArgs args, const __grid_constant__ 
 }
 
 // =================================================================================================
-template <int TN, bool BF16, int SLOTS>
+template <int TN, bool BF16, int SLOTS, bool STORE = false>
 static int launch_tc(const EncEdgeArgs& a, const unsigned char* w_img, const cns_handle* h, cudaStream_t s) {
   static unsigned long long configured = 0;
-  auto kern = enc_edge_tc_kernel<TN, BF16, SLOTS>;
+  auto kern = enc_edge_tc_kernel<TN, BF16, SLOTS, STORE>;
   constexpr size_t TC_SMEM_BYTES = tc_smem_bytes(SLOTS, TN);
   if (first_use_on_device(configured)) {
     CNS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
@@ -662,8 +691,11 @@ static int launch_tc(const EncEdgeArgs& a, const unsigned char* w_img, const cns
   ta.w_first = h->tc_w_img + 2 * TC_NW * TC_W_BYTES;
   ta.n_tiles = ceil_div(a.n_e01, TN);
   int grid, tpc;
-  tc_chunking(a.n_e01, TN, SLOTS, h->sm_count, &grid, &tpc);
+  tc_chunking(a.n_e01, TN, SLOTS, h->sm_count, a.side_mode ? 1 : 2, &grid, &tpc);
   ta.tiles_per_chunk = tpc;
+  ta.side_mode = a.side_mode;
+  ta.store_l = a.store_l; ta.store_v = reinterpret_cast<__half*>(a.store_v);
+  CNS_REQUIRE(!STORE || (a.store_l && a.store_v && a.side_mode == 2), "enc_edge_tc: the store kernel fills a target cache");
   const int slots = SLOTS;
   // fp16 pair table of the first-layer weights (f16 mode), derived from the fp32 table on every launch: 2 KB
   const TcSmallW* sw = reinterpret_cast<const TcSmallW*>(h->tc_small_host);
@@ -682,24 +714,98 @@ static int launch_tc(const EncEdgeArgs& a, const unsigned char* w_img, const cns
   return CNS_OK;
 }
 
-// grid size and tiles per slot-chunk for n_e01 edges: (grid * slots) / 2 contiguous chunks per side
-void tc_chunking(int64_t n_e01, int tile_n, int slots, int sm_count, int* grid, int* tiles_per_chunk) {
+// grid size and tiles per slot-chunk for n_e01 edges: (grid * slots) / sides contiguous chunks per side (sides = 2: both
+// sides in one launch; 1: a single side, the other one comes from / goes to a target cache)
+void tc_chunking(int64_t n_e01, int tile_n, int slots, int sm_count, int sides, int* grid, int* tiles_per_chunk) {
   const int n_tiles = ceil_div(n_e01, tile_n);
   int g = sm_count;
-  const int want = ceil_div(2 * (int64_t)n_tiles, slots);
+  const int want = ceil_div(sides * (int64_t)n_tiles, slots);
   if (g > want) g = want > 0 ? want : 1;
-  int chunks_side = (g * slots) / 2;
-  if (chunks_side < 1) { chunks_side = 1; if (g * slots < 2) g = (2 + slots - 1) / slots; }
+  int chunks_side = (g * slots) / sides;
+  if (chunks_side < 1) { chunks_side = 1; if (g * slots < sides) g = (sides + slots - 1) / slots; }
   *grid = g;
   *tiles_per_chunk = ceil_div(n_tiles > 0 ? n_tiles : 1, chunks_side);
 }
 
 static int tc_slots(const cns_handle* h) { return h->tc_tile_n == 64 ? 2 : (h->tc_slots >= 4 && h->tc_slots <= 6 ? h->tc_slots : 4); }
 
-int tc_piece_edges(int64_t n_e01, const cns_handle* h) {
+int tc_piece_edges(int64_t n_e01, const cns_handle* h, int sides) {
   int grid, tpc;
-  tc_chunking(n_e01, h->tc_tile_n, tc_slots(h), h->sm_count, &grid, &tpc);
+  tc_chunking(n_e01, h->tc_tile_n, tc_slots(h), h->sm_count, sides, &grid, &tpc);
   return tpc * h->tc_tile_n;
+}
+
+// =================================================================================================
+// Target side from a cns_target_cache (forward.cu): the per-keypoint logits L (log2 units) and values V of the target side
+// depend on the target alone, so a servo loop computes them once per target (store kernel above) and every frame only
+// runs the per-channel segment softmax over the keypoints that are visible in that frame - a streaming pass over
+// 768 bytes per visible keypoint instead of the five 128 x 128 GEMMs.  One CTA per cluster, thread = channel.
+// =================================================================================================
+__global__ void __launch_bounds__(128)
+enc_tar_cached_kernel(const int64_t* __restrict__ ej, const int* __restrict__ clu_rowptr, int64_t n_clusters,
+                      const float* __restrict__ lc, const __half* __restrict__ vc, const float* __restrict__ b_p1,
+                      float* __restrict__ out /* clu_feat of the target side (C,128) */) {
+  // One WARP per cluster: a warp reads a keypoint's whole row per instruction (lane = 4 channels: 16 bytes of logits,
+  // 8 bytes of values) and keeps four rows in flight.  No shared memory and 40 registers: this kernel shares the SMs with
+  // the encoder edge kernel (207 KB of shared memory, 45 k registers per SM), so only what fits beside it runs concurrently.
+  const int lane = threadIdx.x & 31;
+  const int64_t c = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (c >= n_clusters) return;
+  const int rb = clu_rowptr[c], re = clu_rowptr[c + 1];
+  float m[4], sa[4], aa[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; sa[i] = 0.f; aa[i] = 0.f; }
+  auto take = [&](const float4 l, const uint2 vraw) {
+    const __half2 v01 = *reinterpret_cast<const __half2*>(&vraw.x), v23 = *reinterpret_cast<const __half2*>(&vraw.y);
+    const float lv[4] = {l.x, l.y, l.z, l.w};
+    const float vv[4] = {__low2float(v01), __high2float(v01), __low2float(v23), __high2float(v23)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float gm = fmaxf(lv[i], m[i]);
+      const float sc = ex2_approx(m[i] - gm), ee = ex2_approx(lv[i] - gm);     // m = -inf at the start: sc = 0
+      sa[i] = fmaf(sa[i], sc, ee);
+      aa[i] = fmaf(aa[i], sc, ee * vv[i]);
+      m[i] = gm;
+    }
+  };
+  // four rows of 768 bytes in flight; the keypoint ids of the NEXT four are fetched before this group's rows are waited
+  // for (a lane holds one id of the window; the rows' addresses come by shuffle), so a group costs one memory round trip
+  int e = rb;
+  int64_t jw = (e + (lane & 7) < re) ? ej[e + (lane & 7)] : 0;       // ids of edges e .. e+7 in lanes 0..7 (replicated)
+  for (; e < re; e += 4) {
+    const int64_t j0 = __shfl_sync(0xffffffffu, jw, 0), j1 = __shfl_sync(0xffffffffu, jw, 1);
+    const int64_t j2 = __shfl_sync(0xffffffffu, jw, 2), j3 = __shfl_sync(0xffffffffu, jw, 3);
+    const int n = re - e;                                            // rows left (>= 1); rows beyond it are not loaded
+    float4 l0, l1 = make_float4(0.f, 0.f, 0.f, 0.f), l2 = l1, l3 = l1;
+    uint2 v0, v1 = make_uint2(0u, 0u), v2 = v1, v3 = v1;
+    l0 = reinterpret_cast<const float4*>(lc + j0 * H)[lane]; v0 = reinterpret_cast<const uint2*>(vc + j0 * H)[lane];
+    if (n > 1) { l1 = reinterpret_cast<const float4*>(lc + j1 * H)[lane]; v1 = reinterpret_cast<const uint2*>(vc + j1 * H)[lane]; }
+    if (n > 2) { l2 = reinterpret_cast<const float4*>(lc + j2 * H)[lane]; v2 = reinterpret_cast<const uint2*>(vc + j2 * H)[lane]; }
+    if (n > 3) { l3 = reinterpret_cast<const float4*>(lc + j3 * H)[lane]; v3 = reinterpret_cast<const uint2*>(vc + j3 * H)[lane]; }
+    // next window: ids of edges e+4 .. e+11
+    const int64_t jn_hi = (e + 8 + (lane & 3) < re) ? ej[e + 8 + (lane & 3)] : 0;
+    const int64_t keep = __shfl_sync(0xffffffffu, jw, 4 + (lane & 3));
+    jw = (lane & 7) < 4 ? keep : jn_hi;
+    take(l0, v0);
+    if (n > 1) take(l1, v1);
+    if (n > 2) take(l2, v2);
+    if (n > 3) take(l3, v3);
+  }
+  // sum p (v + b) = sum p v + b sum p ; relu ; no visible keypoint -> 0 (like the scatter of an empty segment)
+  const float4 b4 = reinterpret_cast<const float4*>(b_p1)[lane];
+  const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+  float o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = re > rb ? fmaxf(__fdividef(fmaf(bb[i], sa[i], aa[i]), sa[i] + 1e-16f), 0.f) : 0.f;
+  reinterpret_cast<float4*>(out + c * H)[lane] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+int enc_tar_cached(const int64_t* ej, const int* clu_rowptr, int64_t n_clusters, const float* lc, const void* vc,
+                   const float* b_p1, float* out, cudaStream_t s) {
+  if (n_clusters == 0) return CNS_OK;
+  enc_tar_cached_kernel<<<(unsigned)ceil_div(n_clusters, 4), 128, 0, s>>>(ej, clu_rowptr, n_clusters, lc, reinterpret_cast<const __half*>(vc), b_p1, out);
+  CNS_LAUNCH_CHECK();
+  return CNS_OK;
 }
 
 int tc_pack_weights(cns_handle* h, cudaStream_t s) {
@@ -744,6 +850,10 @@ int enc_edge_tc(const EncEdgeArgs& a, int precision, const cns_handle* h, cudaSt
   if (a.n_e01 == 0) return CNS_OK;
   CNS_REQUIRE(h->tc_w_img != nullptr, "tensor-core weight image missing");
   const int tn = h->tc_tile_n, slots = tc_slots(h);
+  if (a.store_l) {          // target-cache fill: one configuration per precision
+    if (precision == CNS_PREC_BF16) return launch_tc<32, true, 5, true>(a, h->tc_w_img, h, s);
+    return launch_tc<32, false, 5, true>(a, h->tc_w_img + TC_NW * TC_W_BYTES, h, s);
+  }
   if (precision == CNS_PREC_BF16) {
     if (tn == 64) return launch_tc<64, true, 2>(a, h->tc_w_img, h, s);
     if (slots == 5) return launch_tc<32, true, 5>(a, h->tc_w_img, h, s);

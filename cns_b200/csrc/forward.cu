@@ -72,6 +72,10 @@ struct cns_target_cache {
   int64_t n_clusters, n_graphs;
   int has_tiles;
   float* a_dst; float* pos_clu; int* clu_graph; int* graph_ptr; int* tile_graph; int* n_tiles;
+  // per-keypoint target-side logits (fp32, log2 units) and values (f16) of the keypoint -> cluster attention (16-bit modes,
+  // when the caller passed the keypoint -> cluster assignment of ALL target keypoints): the per-frame target side is then a
+  // streaming segment softmax over the visible keypoints (enc_tar_cached) instead of half of the encoder edge kernel
+  int64_t n_nodes; float* edge_l; void* edge_v;
   void* base;
 };
 
@@ -217,7 +221,34 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   if (fork_pre) { CNS_CUDA_CHECK(cudaStreamWaitEvent(s, h->side_join, 0)); }
   else if (!tcache) RUN(cluster_pre(h, pre, s));
 
+  // target side from the cache: a streaming softmax on the forked stream beside the (then current-side only) edge kernel
+  const bool tar_cached = tcache && tcache->n_nodes > 0 && tcache->n_nodes == b->n_nodes && h->precision != CNS_PREC_FP32;
+  const bool fork_tar = tar_cached && !fork_pre && (C > PREP_SMALL_MAX || B > PREP_SMALL_MAX) && !getenv("CNS_TAR_SERIAL");
+  if (fork_tar && !h->low_stream) {
+    // the streaming kernel runs beside the edge kernel on a LOW-priority stream and is enqueued AFTER it: its 19 k small
+    // CTAs would otherwise fill every SM first and the edge kernel (one 207 KB CTA per SM) would wait for them to drain
+    int lo = 0, hi = 0;
+    CNS_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CNS_CUDA_CHECK(cudaStreamCreateWithPriority(&h->low_stream, cudaStreamNonBlocking, lo));
+    CNS_CUDA_CHECK(cudaEventCreateWithFlags(&h->low_fork, cudaEventDisableTiming));
+    CNS_CUDA_CHECK(cudaEventCreateWithFlags(&h->low_join, cudaEventDisableTiming));
+  }
+  if (fork_tar) CNS_CUDA_CHECK(cudaEventRecord(h->low_fork, s));
+  auto launch_tar = [&]() -> int {
+    ++h->edge_cache_forwards;          // (enqueues, also while a graph is being captured; replays are not counted)
+    cudaStream_t st = s;
+    if (fork_tar) {
+      CNS_CUDA_CHECK(cudaStreamWaitEvent(h->low_stream, h->low_fork, 0));
+      st = h->low_stream;
+    }
+    int r = enc_tar_cached(b->l0_to_l1_j, f.clu_rowptr, C, tcache->edge_l, tcache->edge_v, h->P(P_POS1_B),
+                           f.clu_feat + (size_t)C * H, st);
+    if (r != CNS_OK) return r;
+    if (fork_tar) CNS_CUDA_CHECK(cudaEventRecord(h->low_join, h->low_stream));
+    return CNS_OK;
+  };
   EncEdgeArgs ee{};
+  ee.side_mode = tar_cached ? 1 : 0;
   ee.n_e01 = b->n_e01; ee.n_clusters = C; ee.n_slots = f.n_slots;
   ee.x_cur = b->x_cur; ee.x_tar = b->x_tar; ee.pos_cur = b->pos_cur; ee.pos_tar = b->pos_tar;
   ee.ej = b->l0_to_l1_j; ee.ei = b->l0_to_l1_i;
@@ -236,10 +267,13 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   }
   if (timed) { CNS_CUDA_CHECK(cudaEventRecord(h->ev[2 * h->ev_n + 1], s)); ++h->ev_n; }
   if (cap_ev) CNS_CUDA_CHECK(cudaEventRecordWithFlags(cap_ev[1], s, cudaEventRecordExternal));
+  if (tar_cached) RUN(launch_tar());
 
   EncFinishArgs ef{};
   ef.n_clusters = C; ef.n_slots = f.n_slots;
-  ef.piece_e = (h->precision == CNS_PREC_FP32) ? (h->no_split_encoder ? ENC_PIECE_E : split_piece_edges(b->n_e01, h)) : tc_piece_edges(b->n_e01, h); ef.clu_rowptr = f.clu_rowptr; ef.partial = f.partial;
+  ef.piece_e = (h->precision == CNS_PREC_FP32) ? (h->no_split_encoder ? ENC_PIECE_E : split_piece_edges(b->n_e01, h)) : tc_piece_edges(b->n_e01, h, tar_cached ? 1 : 2); ef.clu_rowptr = f.clu_rowptr; ef.partial = f.partial;
+  ef.cur_only = tar_cached ? 1 : 0;
+  if (fork_tar) CNS_CUDA_CHECK(cudaStreamWaitEvent(s, h->low_join, 0));      // the cached target side has landed
   ef.clu_feat = f.clu_feat; ef.out_t = pk.out_t; ef.b_out = h->P(P_OUT_B); ef.cluster_mask = b->cluster_mask;
   ef.x_clu = f.x_clu;
   ef.cat_out = ((tc && !fused) || tc2) ? f.pq : nullptr;       // (C,256) scratch; pq is free until the first [P|Q] projection
@@ -548,10 +582,17 @@ int cns_target_cache_create(cns_handle* h, const cns_batch* b, void* stream, cns
   c->device = h->device; c->precision = h->precision; c->weights_version = h->weights_version;
   c->n_clusters = C; c->n_graphs = B;
   int* tmp = nullptr; int* scratch = nullptr; int* err = nullptr;
+  // the edge cache needs: a 16-bit mode, every target keypoint's cluster (n_e01 == n_nodes edges, any order) and the
+  // tensor-core kernels' default tile configuration
+  const bool want_edges = h->precision != CNS_PREC_FP32 && b->n_e01 > 0 && b->n_e01 == b->n_nodes && b->l0_to_l1_j && b->l0_to_l1_i &&
+                          h->tc_tile_n == 32 && !h->no_edge_cache;
+  const int64_t N = b->n_nodes;
+  c->n_nodes = want_edges ? N : 0;
   auto lay = [&](Arena& a) {
     c->a_dst = a.take<float>(C * H); c->pos_clu = a.take<float>(C * 2 + 2); c->clu_graph = a.take<int>(C + 1);
     c->graph_ptr = a.take<int>(B + 1); c->tile_graph = a.take<int>(B + 2); c->n_tiles = a.take<int>(4);
     tmp = a.take<int>(B + 1); scratch = (int*)a.take<char>(scan_scratch_bytes(B + 1)); err = a.take<int>(4);
+    if (want_edges) { c->edge_l = a.take<float>(N * H); c->edge_v = a.take<char>(N * H * 2); }
   };
   Arena count(nullptr);
   lay(count);
@@ -571,6 +612,18 @@ int cns_target_cache_create(cns_handle* h, const cns_batch* b, void* stream, cns
     if (h->precision != CNS_PREC_FP32 || !h->no_split_encoder) { pre.lin_dst_t = h->pk.tc_lin_dst_t; pre.a_bias = h->pk.tc_adst_bias; }
     pre.a_dst = c->a_dst; pre.pos_clu = c->pos_clu; pre.clu_graph = c->clu_graph;
     rc = cluster_pre(h, pre, s);
+    if (rc != CNS_OK || !want_edges) break;
+    // fill the edge cache: the target side of the encoder edge kernel over ALL target keypoints, storing logits and values
+    EncEdgeArgs ee{};
+    ee.n_e01 = N; ee.n_clusters = C; ee.n_slots = 0;
+    ee.x_cur = b->x_tar; ee.x_tar = b->x_tar; ee.pos_cur = b->pos_tar; ee.pos_tar = b->pos_tar;
+    ee.ej = b->l0_to_l1_j; ee.ei = b->l0_to_l1_i;
+    ee.pos_clu = c->pos_clu; ee.a_dst = c->a_dst; ee.clu_rowptr = nullptr;
+    ee.w_in = h->P(P_IN_W); ee.b_in = h->P(P_IN_B); ee.w_p0 = h->P(P_POS0_W); ee.b_p0 = h->P(P_POS0_B);
+    ee.enc_chain = h->pk.enc_chain; ee.b_p1 = h->P(P_POS1_B); ee.b_a0 = h->P(P_ATT0_B); ee.b_a1 = h->P(P_ATT1_B);
+    ee.clu_feat = nullptr; ee.partial = nullptr;
+    ee.side_mode = 2; ee.store_l = c->edge_l; ee.store_v = c->edge_v;
+    rc = enc_edge_tc(ee, h->precision, h, s);
   } while (false);
   if (rc != CNS_OK) { cudaFree(c->base); delete c; return rc; }
   *out = c;

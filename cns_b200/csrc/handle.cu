@@ -252,6 +252,7 @@ int cns_create(cns_handle** out, int device) {
   h->tc_tile_n = 32;
   h->no_fused_backbone = getenv("CNS_NO_FUSED_BACKBONE") ? 1 : 0;
   h->no_tc_cluster_pre = getenv("CNS_NO_TC_CLUSTER_PRE") ? 1 : 0;
+  h->no_edge_cache = getenv("CNS_NO_EDGE_CACHE") ? 1 : 0;
   h->no_split_gemm = getenv("CNS_NO_SPLIT_GEMM") ? 1 : 0;
   h->no_split_encoder = getenv("CNS_NO_SPLIT_ENCODER") ? 1 : 0;
   h->tc_slots = getenv("CNS_TC_SLOTS") ? atoi(getenv("CNS_TC_SLOTS")) : 5;
@@ -297,6 +298,7 @@ int cns_destroy(cns_handle* h) {
   if (h->pk.bf_vec) cudaFree(h->pk.bf_vec);
   graph_cache_clear(h);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h->low_stream) { cudaStreamDestroy(h->low_stream); cudaEventDestroy(h->low_fork); cudaEventDestroy(h->low_join); }
   if (h->servo_tcache) cns_target_cache_destroy(h->servo_tcache);
   free(h->servo_tkey);
   if (h->side_stream) { cudaStreamDestroy(h->side_stream); cudaEventDestroy(h->side_fork); cudaEventDestroy(h->side_join); cudaEventDestroy(h->side_join2); }
@@ -392,6 +394,7 @@ long long cns_get_counter(cns_handle* h, const char* name) {
   if (!h || !name) return -1;
   if (!strcmp(name, "graph_replays")) return h->graph_replays;
   if (!strcmp(name, "graph_captures")) return h->graph_captures;
+  if (!strcmp(name, "edge_cache_forwards")) return h->edge_cache_forwards;
   if (!strcmp(name, "kernel_launches")) return g_launch_count;
   return -1;
 }

@@ -60,6 +60,10 @@ struct EncEdgeArgs {
   const float* enc_chain; const float* b_p1; const float* b_a0; const float* b_a1;
   float* clu_feat;   // (2, C, 128): relu(ptconv) for cur / tar
   float* partial;    // (2, n_slots, 3, 128)
+  // enc_edge_tc only: 0 = both sides, 1 = current side only (the target side comes from a cns_target_cache), 2 = target side
+  // only; store_l / store_v (with side_mode 2): fill a target cache - per-keypoint logits (fp32, log2 units) and values (f16)
+  // instead of the segment softmax
+  int side_mode; float* store_l; void* store_v;
 };
 int enc_edge_fp32(const EncEdgeArgs& a, cudaStream_t s);
 int enc_edge_tc(const EncEdgeArgs& a, int precision, const cns_handle* h, cudaStream_t s);
@@ -67,8 +71,10 @@ int tc_pack_weights(cns_handle* h, cudaStream_t s);
 int enc_edge_split(const EncEdgeArgs& a, const cns_handle* h, cudaStream_t s);   // fp32-accurate: bf16 (hi, lo) operand split on tcgen05
 int split_pack_weights(cns_handle* h, cudaStream_t s);
 int split_piece_edges(int64_t n_e01, const cns_handle* h);
-void tc_chunking(int64_t n_e01, int tile_n, int slots, int sm_count, int* grid, int* tiles_per_chunk);
-int tc_piece_edges(int64_t n_e01, const cns_handle* h);   // edges per softmax piece (= slot chunk) of enc_edge_tc
+void tc_chunking(int64_t n_e01, int tile_n, int slots, int sm_count, int sides, int* grid, int* tiles_per_chunk);
+int tc_piece_edges(int64_t n_e01, const cns_handle* h, int sides);   // edges per softmax piece (= slot chunk) of enc_edge_tc
+int enc_tar_cached(const int64_t* ej, const int* clu_rowptr, int64_t n_clusters, const float* lc, const void* vc,
+                   const float* b_p1, float* out, cudaStream_t s);    // target side from cached per-keypoint logits / values
 
 struct EncFinishArgs {
   int64_t n_clusters, n_slots;
@@ -78,6 +84,7 @@ struct EncFinishArgs {
   float* x_clu;      // (C,128)
   float* cat_out;    // optional (C,256): write [cur | tar - cur] and skip out_enc (done by gemm_tc)
   int fix_only;      // only repair clu_feat (merge cut clusters, zero empty ones): out_enc runs in the fused backbone
+  int cur_only;      // the target-side features are final (enc_tar_cached): merge / zero the current side only
 };
 int enc_finish(const EncFinishArgs& a, cudaStream_t s);
 

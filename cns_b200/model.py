@@ -325,6 +325,14 @@ class GraphVS(nn.Module):
         batch with the same targets while the weights and the precision mode stay unchanged."""
         b, keep = self.make_batch_struct(data)
         dev = keep[0].device
+        belong = _field(data, "belong_cluster_index")
+        if belong is not None and belong.numel() == b.n_nodes:
+            # every target keypoint with its cluster: the cache then also keeps the target side's per-keypoint attention
+            # logits / values (16-bit modes), and a forward only re-runs their softmax over the visible keypoints
+            belong = belong.to(dev, torch.int64).contiguous()
+            ident = torch.arange(b.n_nodes, dtype=torch.int64, device=dev)
+            keep += [belong, ident]
+            b.n_e01, b.l0_to_l1_j, b.l0_to_l1_i = b.n_nodes, ident.data_ptr(), belong.data_ptr()
         return TargetCache(self._handle(dev), b, dev, keep)
 
     def _forward_inference(self, data, hidden, check=False, target_cache=None):

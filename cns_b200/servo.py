@@ -41,6 +41,7 @@ class BatchedServo(object):
         csize = np.concatenate([g.cluster_points_count for g in gens]).astype(np.int64)
         self.member_ptr = d(np.concatenate([[0], np.cumsum(csize)]), torch.int32)       # members of cluster c: member_order[ptr[c]:ptr[c+1]]
         self.centers = d(np.concatenate([g.cluster_centers_index + o for g, o in zip(gens, noff)]), torch.int64)
+        self.member_cluster = d(np.repeat(np.arange(int(n_clu.sum())), csize), torch.int64)   # cluster of member_order[k]
         self.num_clusters = d(n_clu, torch.int64)
         self.tpo = d(np.broadcast_to(np.asarray(dist_scale, dtype=np.float32), (self.B,)), torch.float32)
         i64 = lambda n: torch.empty(n, dtype=torch.int64, device=self.dev)
@@ -89,6 +90,10 @@ class BatchedServo(object):
         b.x_tar, b.pos_tar = self.x_tar.data_ptr(), self.x_tar.data_ptr()
         b.cluster_centers, b.num_clusters = self.centers.data_ptr(), self.num_clusters.data_ptr()
         b.max_clusters_per_graph = self.max_clusters
+        # every target keypoint with its cluster (cluster-major): lets the cache keep the target side's per-keypoint
+        # attention logits / values, so that a frame only re-runs their softmax over the visible keypoints
+        b.n_e01 = self.N
+        b.l0_to_l1_j, b.l0_to_l1_i = self.member_order.data_ptr(), self.member_cluster.data_ptr()
         out = C.c_void_p()
         L.check(self.lib.cns_target_cache_create(h.raw, C.byref(b), L.stream_ptr(self.dev), C.byref(out)),
                 "cns_target_cache_create")

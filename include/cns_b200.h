@@ -77,7 +77,8 @@ int cns_set_tc_tile(cns_handle* h, int tile_n /* 32 or 64: edges per tensor-core
  * pointers and mode) as one CUDA-graph launch, default 1 (CNS_NO_GRAPHS=1 in the environment turns it off);
  * "tc_slots" 4..6 - edge tiles in flight per SM. */
 int cns_set_option(cns_handle* h, const char* name, long long value);
-/* "graph_replays", "graph_captures", "kernel_launches" (library-wide host-side count); -1 for an unknown name */
+/* "graph_replays", "graph_captures", "edge_cache_forwards" (forwards enqueued with the target side taken from a
+ * cns_target_cache's per-keypoint cache), "kernel_launches" (library-wide host-side count); -1 for an unknown name */
 long long cns_get_counter(cns_handle* h, const char* name);
 
 /* Measurement hooks: between begin and end every cns_graphvs_forward brackets its dominant

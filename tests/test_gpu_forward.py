@@ -632,3 +632,35 @@ def test_forwards_on_two_streams_do_not_interfere(state_dict):
     for g, r in zip(got, ref):
         for x, y in zip(g, r):
             assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("precision", ["f16", "bf16"])
+def test_target_edge_cache_matches_recomputed_target_side(state_dict, precision):
+    """A target cache built with every keypoint's cluster keeps the target side's per-keypoint attention logits (fp32) and
+    values (f16); a forward then runs the edge kernel on the current side only and a streaming softmax over the visible
+    keypoints for the target side.  Same result as recomputing the target side, up to the f16 rounding of the cached values,
+    and still inside the mode's tolerance of the fp64 oracle."""
+    net = ckpt.load_model(os.path.join(ROOT, "checkpoints", "cns.pth"), "cuda:0", precision=precision)
+    h = net._handle(torch.device("cuda:0"))
+    rng = np.random.default_rng(21)
+    np.random.seed(21)
+    scenes = [synth.Scene(rng, n) for n in (300, 40, 512, 17, 128)]
+    first = Batch.from_data_list([s.frame(0.0) for s in scenes]).to("cuda:0")
+    cache = net.build_target_cache(first)                     # belongs to the targets, not to a frame
+    hid_g = hid_c = hid_o = None
+    for t in range(3):
+        frames = [s.frame(0.3) for s in scenes]               # 30 % of the keypoints missing, different ones every frame
+        batch = Batch.from_data_list(frames)
+        dev = batch.to("cuda:0")
+        n0 = h.counter("edge_cache_forwards")
+        with torch.no_grad():
+            plain = net(dev, hid_g, check=True)
+            cached = net(dev, hid_c, check=True, target_cache=cache)
+        assert h.counter("edge_cache_forwards") == n0 + 1
+        hid_g, hid_c = plain[2], cached[2]
+        for a, b in zip(plain, cached):
+            assert rel(b, a) < 3e-3
+        ov, on, hid_o = cns_oracle.forward(state_dict, batch, hid_o, dtype=torch.float64)
+        assert rel(cached[0], ov) < TOL[precision] and rel(cached[2], hid_o) < TOL[precision]
+        for s, v in zip(scenes, cached.vel.cpu().numpy()):
+            s.step(v * 2)
