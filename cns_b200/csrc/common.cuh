@@ -117,6 +117,7 @@ struct cns_handle {
   int tc_tile_n;                                        // edges per tensor-core tile (32 or 64)
   int tc_slots;                                         // tiles in flight per SM of the 32-edge kernel: 4, 5 or 6 (CNS_TC_SLOTS)
   int no_split_gemm;                                    // CNS_NO_SPLIT_GEMM=1: backward GEMMs stay on the fp32 FFMA kernel (A-B runs)
+  int no_edge_subtract;                                 // CNS_NO_EDGE_SUBTRACT=1: cached target side always re-sums the visible keypoints (A-B runs)
   int no_edge_cache;                                    // CNS_NO_EDGE_CACHE=1: target caches keep no per-keypoint logits / values (A-B runs)
   int no_tc_cluster_pre;                                // CNS_NO_TC_CLUSTER_PRE=1: per-cluster encoder terms stay on the FFMA kernel (A-B runs)
   int no_fused_backbone;                                // CNS_NO_FUSED_BACKBONE=1: keep the per-layer kernels (debugging / A-B runs)

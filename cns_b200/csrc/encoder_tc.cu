@@ -741,24 +741,43 @@ int tc_piece_edges(int64_t n_e01, const cns_handle* h, int sides) {
 // runs the per-channel segment softmax over the keypoints that are visible in that frame - a streaming pass over
 // 768 bytes per visible keypoint instead of the five 128 x 128 GEMMs.  One CTA per cluster, thread = channel.
 // =================================================================================================
+struct TarCachedArgs {
+  const int64_t* ej; const int* clu_rowptr; int64_t n_clusters;      // this frame: visible keypoints, cluster-major
+  const float* lc; const __half* vc; const float* b_p1;
+  // per target (cache): every member of every cluster (cluster-major) and the softmax statistics over ALL of them
+  const int* all_src; const int* all_rowptr; const float* all_stats;  // (N,), (C+1,), (C,3,128): max | sum | weighted sum
+  const uint8_t* visible;                                             // (N,) 1 = keypoint visible in this frame
+  float* out;                                                         // target-side clu_feat (C,128); NULL: write statistics
+  float* stats_out;
+};
+
+// One WARP per cluster: a warp reads a keypoint's whole row per instruction (lane = 4 channels: 16 bytes of logits,
+// 8 bytes of values) and keeps four rows in flight.  No shared memory: this kernel shares the SMs with the encoder edge
+// kernel (207 KB of shared memory, 45 k registers per SM), so only what fits beside it runs concurrently.
+// A cluster that keeps most of its keypoints is not re-summed: its statistics over ALL members are cached, and only the
+// rows of the MISSING members are read and subtracted (sum_visible = sum_all - sum_missing, both relative to the cached
+// maximum) - 10 % of the rows at the usual 10 % of unmatched keypoints.  If the visible mass of any channel falls below
+// 2^-8 of the total (a dominant keypoint went missing: the subtraction would cancel), the warp re-sums the visible rows.
 __global__ void __launch_bounds__(128)
-enc_tar_cached_kernel(const int64_t* __restrict__ ej, const int* __restrict__ clu_rowptr, int64_t n_clusters,
-                      const float* __restrict__ lc, const __half* __restrict__ vc, const float* __restrict__ b_p1,
-                      float* __restrict__ out /* clu_feat of the target side (C,128) */) {
-  // One WARP per cluster: a warp reads a keypoint's whole row per instruction (lane = 4 channels: 16 bytes of logits,
-  // 8 bytes of values) and keeps four rows in flight.  No shared memory and 40 registers: this kernel shares the SMs with
-  // the encoder edge kernel (207 KB of shared memory, 45 k registers per SM), so only what fits beside it runs concurrently.
+enc_tar_cached_kernel(const TarCachedArgs p) {
   const int lane = threadIdx.x & 31;
   const int64_t c = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (c >= n_clusters) return;
-  const int rb = clu_rowptr[c], re = clu_rowptr[c + 1];
+  if (c >= p.n_clusters) return;
+  const float* __restrict__ lc = p.lc;
+  const __half* __restrict__ vc = p.vc;
   float m[4], sa[4], aa[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; sa[i] = 0.f; aa[i] = 0.f; }
-  auto take = [&](const float4 l, const uint2 vraw) {
+  auto row = [&](int64_t j, float4& l, uint2& v) {
+    l = reinterpret_cast<const float4*>(lc + j * H)[lane];
+    v = reinterpret_cast<const uint2*>(vc + j * H)[lane];
+  };
+  auto unpack = [](const float4 l, const uint2 vraw, float (&lv)[4], float (&vv)[4]) {
     const __half2 v01 = *reinterpret_cast<const __half2*>(&vraw.x), v23 = *reinterpret_cast<const __half2*>(&vraw.y);
-    const float lv[4] = {l.x, l.y, l.z, l.w};
-    const float vv[4] = {__low2float(v01), __high2float(v01), __low2float(v23), __high2float(v23)};
+    lv[0] = l.x; lv[1] = l.y; lv[2] = l.z; lv[3] = l.w;
+    vv[0] = __low2float(v01); vv[1] = __high2float(v01); vv[2] = __low2float(v23); vv[3] = __high2float(v23);
+  };
+  auto take = [&](const float4 l, const uint2 vraw) {               // online softmax update
+    float lv[4], vv[4];
+    unpack(l, vraw, lv, vv);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float gm = fmaxf(lv[i], m[i]);
@@ -768,42 +787,116 @@ enc_tar_cached_kernel(const int64_t* __restrict__ ej, const int* __restrict__ cl
       m[i] = gm;
     }
   };
-  // four rows of 768 bytes in flight; the keypoint ids of the NEXT four are fetched before this group's rows are waited
-  // for (a lane holds one id of the window; the rows' addresses come by shuffle), so a group costs one memory round trip
-  int e = rb;
-  int64_t jw = (e + (lane & 7) < re) ? ej[e + (lane & 7)] : 0;       // ids of edges e .. e+7 in lanes 0..7 (replicated)
-  for (; e < re; e += 4) {
-    const int64_t j0 = __shfl_sync(0xffffffffu, jw, 0), j1 = __shfl_sync(0xffffffffu, jw, 1);
-    const int64_t j2 = __shfl_sync(0xffffffffu, jw, 2), j3 = __shfl_sync(0xffffffffu, jw, 3);
-    const int n = re - e;                                            // rows left (>= 1); rows beyond it are not loaded
-    float4 l0, l1 = make_float4(0.f, 0.f, 0.f, 0.f), l2 = l1, l3 = l1;
-    uint2 v0, v1 = make_uint2(0u, 0u), v2 = v1, v3 = v1;
-    l0 = reinterpret_cast<const float4*>(lc + j0 * H)[lane]; v0 = reinterpret_cast<const uint2*>(vc + j0 * H)[lane];
-    if (n > 1) { l1 = reinterpret_cast<const float4*>(lc + j1 * H)[lane]; v1 = reinterpret_cast<const uint2*>(vc + j1 * H)[lane]; }
-    if (n > 2) { l2 = reinterpret_cast<const float4*>(lc + j2 * H)[lane]; v2 = reinterpret_cast<const uint2*>(vc + j2 * H)[lane]; }
-    if (n > 3) { l3 = reinterpret_cast<const float4*>(lc + j3 * H)[lane]; v3 = reinterpret_cast<const uint2*>(vc + j3 * H)[lane]; }
-    // next window: ids of edges e+4 .. e+11
-    const int64_t jn_hi = (e + 8 + (lane & 3) < re) ? ej[e + 8 + (lane & 3)] : 0;
-    const int64_t keep = __shfl_sync(0xffffffffu, jw, 4 + (lane & 3));
-    jw = (lane & 7) < 4 ? keep : jn_hi;
-    take(l0, v0);
-    if (n > 1) take(l1, v1);
-    if (n > 2) take(l2, v2);
-    if (n > 3) take(l3, v3);
+  // direct pass over a list of keypoint ids (int64 `ej` or int32 `all_src`): four rows in flight, next ids prefetched
+  auto direct = [&](auto ids, int rb, int re) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; sa[i] = 0.f; aa[i] = 0.f; }
+    int e = rb;
+    int64_t jw = (e + (lane & 7) < re) ? (int64_t)ids[e + (lane & 7)] : 0;   // ids of rows e .. e+7 in lanes 0..7 (replicated)
+    for (; e < re; e += 4) {
+      const int64_t j0 = __shfl_sync(0xffffffffu, jw, 0), j1 = __shfl_sync(0xffffffffu, jw, 1);
+      const int64_t j2 = __shfl_sync(0xffffffffu, jw, 2), j3 = __shfl_sync(0xffffffffu, jw, 3);
+      const int n = re - e;
+      float4 l0, l1 = make_float4(0.f, 0.f, 0.f, 0.f), l2 = l1, l3 = l1;
+      uint2 v0, v1 = make_uint2(0u, 0u), v2 = v1, v3 = v1;
+      row(j0, l0, v0);
+      if (n > 1) row(j1, l1, v1);
+      if (n > 2) row(j2, l2, v2);
+      if (n > 3) row(j3, l3, v3);
+      const int64_t jn_hi = (e + 8 + (lane & 3) < re) ? (int64_t)ids[e + 8 + (lane & 3)] : 0;
+      const int64_t keep = __shfl_sync(0xffffffffu, jw, 4 + (lane & 3));
+      jw = (lane & 7) < 4 ? keep : jn_hi;
+      take(l0, v0);
+      if (n > 1) take(l1, v1);
+      if (n > 2) take(l2, v2);
+      if (n > 3) take(l3, v3);
+    }
+  };
+  if (!p.out) {                      // cache fill: statistics over all members of the cluster
+    direct(p.all_src, p.all_rowptr[c], p.all_rowptr[c + 1]);
+    float* st = p.stats_out + c * 3 * H;
+    reinterpret_cast<float4*>(st)[lane] = make_float4(m[0], m[1], m[2], m[3]);
+    reinterpret_cast<float4*>(st + H)[lane] = make_float4(sa[0], sa[1], sa[2], sa[3]);
+    reinterpret_cast<float4*>(st + 2 * H)[lane] = make_float4(aa[0], aa[1], aa[2], aa[3]);
+    return;
   }
+  const int rb = p.clu_rowptr[c], re = p.clu_rowptr[c + 1];
+  bool done = false;
+  if (p.all_stats && re > rb) {
+    const int ab0 = p.all_rowptr[c], ae0 = p.all_rowptr[c + 1];
+    const int n_missing = (ae0 - ab0) - (re - rb);
+    if (n_missing == 0 || 2 * n_missing < re - rb) {                 // subtract the missing members from the totals
+      const float* st = p.all_stats + c * 3 * H;
+      const float4 m4 = reinterpret_cast<const float4*>(st)[lane], s4 = reinterpret_cast<const float4*>(st + H)[lane];
+      const float4 a4 = reinterpret_cast<const float4*>(st + 2 * H)[lane];
+      m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w;
+      sa[0] = s4.x; sa[1] = s4.y; sa[2] = s4.z; sa[3] = s4.w;
+      aa[0] = a4.x; aa[1] = a4.y; aa[2] = a4.z; aa[3] = a4.w;
+      const float tot[4] = {s4.x, s4.y, s4.z, s4.w};
+      for (int base = ab0; base < ae0 && n_missing > 0; base += 32) {
+        const int a = base + lane;
+        const int j = a < ae0 ? p.all_src[a] : 0;
+        uint32_t miss = __ballot_sync(0xffffffffu, a < ae0 && !p.visible[j]);
+        while (miss) {                                               // up to four missing rows in flight
+          int src[4]; int n = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { src[k] = 0; if (miss) { src[k] = __ffs(miss) - 1; miss &= miss - 1; n = k + 1; } }
+          float4 l[4]; uint2 v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int jk = __shfl_sync(0xffffffffu, j, src[k]);
+            if (k < n) row(jk, l[k], v[k]);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < n) {
+              float lv[4], vv[4];
+              unpack(l[k], v[k], lv, vv);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float pr = ex2_approx(lv[i] - m[i]);
+                sa[i] -= pr;
+                aa[i] = fmaf(-pr, vv[i], aa[i]);
+              }
+            }
+          }
+        }
+      }
+      bool ok = true;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ok = ok && sa[i] > tot[i] * 0.00390625f;
+      done = __all_sync(0xffffffffu, ok);
+    }
+  }
+  if (!done) direct(p.ej, rb, re);
   // sum p (v + b) = sum p v + b sum p ; relu ; no visible keypoint -> 0 (like the scatter of an empty segment)
-  const float4 b4 = reinterpret_cast<const float4*>(b_p1)[lane];
+  const float4 b4 = reinterpret_cast<const float4*>(p.b_p1)[lane];
   const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
   float o[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) o[i] = re > rb ? fmaxf(__fdividef(fmaf(bb[i], sa[i], aa[i]), sa[i] + 1e-16f), 0.f) : 0.f;
-  reinterpret_cast<float4*>(out + c * H)[lane] = make_float4(o[0], o[1], o[2], o[3]);
+  reinterpret_cast<float4*>(p.out + c * H)[lane] = make_float4(o[0], o[1], o[2], o[3]);
 }
 
-int enc_tar_cached(const int64_t* ej, const int* clu_rowptr, int64_t n_clusters, const float* lc, const void* vc,
-                   const float* b_p1, float* out, cudaStream_t s) {
-  if (n_clusters == 0) return CNS_OK;
-  enc_tar_cached_kernel<<<(unsigned)ceil_div(n_clusters, 4), 128, 0, s>>>(ej, clu_rowptr, n_clusters, lc, reinterpret_cast<const __half*>(vc), b_p1, out);
+__global__ void mark_visible_kernel(const int64_t* __restrict__ ej, int64_t n, uint8_t* __restrict__ flag) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) flag[ej[e]] = 1;
+}
+
+int enc_tar_cached(const EncTarCachedArgs& a, cudaStream_t s) {
+  if (a.n_clusters == 0) return CNS_OK;
+  TarCachedArgs p{};
+  p.ej = a.ej; p.clu_rowptr = a.clu_rowptr; p.n_clusters = a.n_clusters; p.lc = a.lc; p.vc = reinterpret_cast<const __half*>(a.vc);
+  p.b_p1 = a.b_p1; p.all_src = a.all_src; p.all_rowptr = a.all_rowptr; p.all_stats = a.all_stats; p.visible = a.visible;
+  p.out = a.out; p.stats_out = a.stats_out;
+  if (a.out && a.all_stats) {        // which keypoints this frame shows (the subtract path walks a cluster's full member list)
+    CNS_CUDA_CHECK(cudaMemsetAsync(a.visible, 0, (size_t)a.n_nodes, s));
+    if (a.n_e01 > 0) {
+      mark_visible_kernel<<<ceil_div(a.n_e01, 256), 256, 0, s>>>(a.ej, a.n_e01, a.visible);
+      CNS_LAUNCH_CHECK();
+    }
+  }
+  enc_tar_cached_kernel<<<(unsigned)ceil_div(a.n_clusters, 4), 128, 0, s>>>(p);
   CNS_LAUNCH_CHECK();
   return CNS_OK;
 }

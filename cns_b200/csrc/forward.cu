@@ -7,7 +7,7 @@
 namespace cns {
 
 struct FwdBuffers {
-  int* err; int* clu_rowptr; int* clu_graph; int* graph_ptr; int* gp_tmp; int* scan_scratch;
+  int* err; uint8_t* vis_flag; int* clu_rowptr; int* clu_graph; int* graph_ptr; int* gp_tmp; int* scan_scratch;
   int* cur_rowptr; int* cur_src; int* tar_rowptr; int* tar_src; void* csr_ws;
   int* alive_idx; int* alive_cnt; int* tile_graph; int* tile_next; int* n_tiles;
   float* a_dst; float* pos_clu; float* clu_feat; float* partial; float* x_clu;
@@ -25,6 +25,7 @@ static void carve(Arena& ar, const cns_batch* b, FwdBuffers& f, const SaveBuffer
   memset(&f, 0, sizeof(f));
   f.n_slots = C + (b->n_e01 + 31) / 32 + 2;   // one partial slot per (cluster, softmax piece) pair; pieces >= 32 edges
   f.err = ar.take<int>(64);
+  f.vis_flag = ar.take<uint8_t>(b->n_nodes + 1);      // keypoints visible in this frame (target side from a cache)
   f.clu_graph = ar.take<int>(C + 1);
   f.gp_tmp = ar.take<int>(B + 1);
   f.scan_scratch = (int*)ar.take<char>(scan_scratch_bytes(B + 1));
@@ -76,6 +77,9 @@ struct cns_target_cache {
   // when the caller passed the keypoint -> cluster assignment of ALL target keypoints): the per-frame target side is then a
   // streaming segment softmax over the visible keypoints (enc_tar_cached) instead of half of the encoder edge kernel
   int64_t n_nodes; float* edge_l; void* edge_v;
+  // ... plus every cluster's full member list (cluster-major) and its softmax statistics over ALL members: a frame that
+  // keeps most keypoints of a cluster only reads the rows of the missing ones and subtracts them from the totals
+  int* all_rowptr; int* all_src; float* all_stats;
   void* base;
 };
 
@@ -241,8 +245,12 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
       CNS_CUDA_CHECK(cudaStreamWaitEvent(h->low_stream, h->low_fork, 0));
       st = h->low_stream;
     }
-    int r = enc_tar_cached(b->l0_to_l1_j, f.clu_rowptr, C, tcache->edge_l, tcache->edge_v, h->P(P_POS1_B),
-                           f.clu_feat + (size_t)C * H, st);
+    EncTarCachedArgs ta{};
+    ta.ej = b->l0_to_l1_j; ta.n_e01 = b->n_e01; ta.clu_rowptr = f.clu_rowptr; ta.n_clusters = C; ta.n_nodes = b->n_nodes;
+    ta.lc = tcache->edge_l; ta.vc = tcache->edge_v; ta.b_p1 = h->P(P_POS1_B);
+    ta.all_src = tcache->all_src; ta.all_rowptr = tcache->all_rowptr; ta.all_stats = h->no_edge_subtract ? nullptr : tcache->all_stats;
+    ta.visible = f.vis_flag; ta.out = f.clu_feat + (size_t)C * H;
+    int r = enc_tar_cached(ta, st);
     if (r != CNS_OK) return r;
     if (fork_tar) CNS_CUDA_CHECK(cudaEventRecord(h->low_join, h->low_stream));
     return CNS_OK;
@@ -581,7 +589,7 @@ int cns_target_cache_create(cns_handle* h, const cns_batch* b, void* stream, cns
   c->uid = ++next_uid;
   c->device = h->device; c->precision = h->precision; c->weights_version = h->weights_version;
   c->n_clusters = C; c->n_graphs = B;
-  int* tmp = nullptr; int* scratch = nullptr; int* err = nullptr;
+  int* tmp = nullptr; int* scratch = nullptr; int* err = nullptr; void* csr_ws = nullptr;
   // the edge cache needs: a 16-bit mode, every target keypoint's cluster (n_e01 == n_nodes edges, any order) and the
   // tensor-core kernels' default tile configuration
   const bool want_edges = h->precision != CNS_PREC_FP32 && b->n_e01 > 0 && b->n_e01 == b->n_nodes && b->l0_to_l1_j && b->l0_to_l1_i &&
@@ -592,7 +600,11 @@ int cns_target_cache_create(cns_handle* h, const cns_batch* b, void* stream, cns
     c->a_dst = a.take<float>(C * H); c->pos_clu = a.take<float>(C * 2 + 2); c->clu_graph = a.take<int>(C + 1);
     c->graph_ptr = a.take<int>(B + 1); c->tile_graph = a.take<int>(B + 2); c->n_tiles = a.take<int>(4);
     tmp = a.take<int>(B + 1); scratch = (int*)a.take<char>(scan_scratch_bytes(B + 1)); err = a.take<int>(4);
-    if (want_edges) { c->edge_l = a.take<float>(N * H); c->edge_v = a.take<char>(N * H * 2); }
+    if (want_edges) {
+      c->edge_l = a.take<float>(N * H); c->edge_v = a.take<char>(N * H * 2);
+      c->all_rowptr = a.take<int>(C + 1); c->all_src = a.take<int>(N + 1); c->all_stats = a.take<float>(C * 3 * H);
+      csr_ws = a.take<char>(csr_workspace_bytes(C));
+    }
   };
   Arena count(nullptr);
   lay(count);
@@ -624,6 +636,14 @@ int cns_target_cache_create(cns_handle* h, const cns_batch* b, void* stream, cns
     ee.clu_feat = nullptr; ee.partial = nullptr;
     ee.side_mode = 2; ee.store_l = c->edge_l; ee.store_v = c->edge_v;
     rc = enc_edge_tc(ee, h->precision, h, s);
+    if (rc != CNS_OK) break;
+    // cluster-major member lists and the per-cluster statistics over all members
+    rc = csr_by_dst(b->l0_to_l1_j, b->l0_to_l1_i, N, C, c->all_rowptr, c->all_src, csr_ws, err, s);
+    if (rc != CNS_OK) break;
+    EncTarCachedArgs ta{};
+    ta.n_clusters = C; ta.n_nodes = N; ta.lc = c->edge_l; ta.vc = c->edge_v; ta.b_p1 = h->P(P_POS1_B);
+    ta.all_src = c->all_src; ta.all_rowptr = c->all_rowptr; ta.stats_out = c->all_stats;
+    rc = enc_tar_cached(ta, s);
   } while (false);
   if (rc != CNS_OK) { cudaFree(c->base); delete c; return rc; }
   *out = c;

@@ -253,6 +253,7 @@ int cns_create(cns_handle** out, int device) {
   h->no_fused_backbone = getenv("CNS_NO_FUSED_BACKBONE") ? 1 : 0;
   h->no_tc_cluster_pre = getenv("CNS_NO_TC_CLUSTER_PRE") ? 1 : 0;
   h->no_edge_cache = getenv("CNS_NO_EDGE_CACHE") ? 1 : 0;
+  h->no_edge_subtract = getenv("CNS_NO_EDGE_SUBTRACT") ? 1 : 0;
   h->no_split_gemm = getenv("CNS_NO_SPLIT_GEMM") ? 1 : 0;
   h->no_split_encoder = getenv("CNS_NO_SPLIT_ENCODER") ? 1 : 0;
   h->tc_slots = getenv("CNS_TC_SLOTS") ? atoi(getenv("CNS_TC_SLOTS")) : 5;

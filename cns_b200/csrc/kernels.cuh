@@ -73,8 +73,16 @@ int split_pack_weights(cns_handle* h, cudaStream_t s);
 int split_piece_edges(int64_t n_e01, const cns_handle* h);
 void tc_chunking(int64_t n_e01, int tile_n, int slots, int sm_count, int sides, int* grid, int* tiles_per_chunk);
 int tc_piece_edges(int64_t n_e01, const cns_handle* h, int sides);   // edges per softmax piece (= slot chunk) of enc_edge_tc
-int enc_tar_cached(const int64_t* ej, const int* clu_rowptr, int64_t n_clusters, const float* lc, const void* vc,
-                   const float* b_p1, float* out, cudaStream_t s);    // target side from cached per-keypoint logits / values
+// target side from a target cache's per-keypoint logits / values (enc_tar_cached_kernel); out == NULL: fill `stats_out`
+// with the per-cluster softmax statistics over all members (cache creation)
+struct EncTarCachedArgs {
+  const int64_t* ej; int64_t n_e01; const int* clu_rowptr; int64_t n_clusters, n_nodes;
+  const float* lc; const void* vc; const float* b_p1;
+  const int* all_src; const int* all_rowptr; const float* all_stats;
+  uint8_t* visible;          // (n_nodes,) scratch
+  float* out; float* stats_out;
+};
+int enc_tar_cached(const EncTarCachedArgs& a, cudaStream_t s);
 
 struct EncFinishArgs {
   int64_t n_clusters, n_slots;

@@ -648,8 +648,10 @@ def test_target_edge_cache_matches_recomputed_target_side(state_dict, precision)
     first = Batch.from_data_list([s.frame(0.0) for s in scenes]).to("cuda:0")
     cache = net.build_target_cache(first)                     # belongs to the targets, not to a frame
     hid_g = hid_c = hid_o = None
-    for t in range(3):
-        frames = [s.frame(0.3) for s in scenes]               # 30 % of the keypoints missing, different ones every frame
+    # 30 % / none / 70 % / 10 % of the keypoints missing, different ones every frame: a cluster that keeps most of its
+    # keypoints subtracts the missing ones from its cached totals, the others re-sum the visible ones
+    for t, missing in enumerate((0.3, 0.0, 0.7, 0.1)):
+        frames = [s.frame(missing) for s in scenes]
         batch = Batch.from_data_list(frames)
         dev = batch.to("cuda:0")
         n0 = h.counter("edge_cache_forwards")
