@@ -328,7 +328,7 @@ class GraphVS(nn.Module):
         belong = _field(data, "belong_cluster_index")
         if belong is not None and belong.numel() == b.n_nodes:
             # every target keypoint with its cluster: the cache then also keeps the target side's per-keypoint attention
-            # logits / values (16-bit modes), and a forward only re-runs their softmax over the visible keypoints
+            # logits / values (f16 mode), and a forward only re-runs their softmax over the visible keypoints
             belong = belong.to(dev, torch.int64).contiguous()
             ident = torch.arange(b.n_nodes, dtype=torch.int64, device=dev)
             keep += [belong, ident]

@@ -139,7 +139,7 @@ typedef struct cns_batch {
  * with the same target tensors while the handle keeps its weights and precision (checked: a stale cache is
  * rejected with CNS_ERR_INVALID_ARGUMENT).
  * When `b` also lists EVERY target keypoint with its cluster (n_e01 == n_nodes; l0_to_l1_j = keypoint index, l0_to_l1_i =
- * cluster index, any order - belong_cluster_index of graph_gen.py:266) and the precision mode is 16-bit, the cache also keeps
+ * cluster index, any order - belong_cluster_index of graph_gen.py:266) and the precision mode is f16, the cache also keeps
  * the target side of the keypoint -> cluster attention per keypoint (logits fp32 + values f16, 768 bytes per keypoint): a
  * forward with such a cache runs the attention chain on the current side only and a streaming segment softmax over the
  * keypoints that are visible in that frame for the target side (graph_vs.py:195-214: the target-side messages do not
