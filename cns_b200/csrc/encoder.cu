@@ -396,15 +396,16 @@ int enc_edge_fp32(const EncEdgeArgs& a, cudaStream_t s) {
 // Repair only (the fused backbone applies out_enc itself): one thread per cluster finds the clusters that need
 // work - no edges (feature 0) or cut by a softmax-piece boundary (merge the pieces) - and the CTA's 256 threads
 // (side, channel) then handle those few.
+constexpr int FIX_CLUSTERS = 64;     // clusters per CTA: the flagged ones are a serial chain per warp, so spread them over many CTAs
 __global__ void __launch_bounds__(256)
 enc_fix_kernel(EncFinishArgs p) {
-  __shared__ int todo[256];
+  __shared__ int todo[FIX_CLUSTERS];
   __shared__ int n_todo;
   const int tid = threadIdx.x;
   if (tid == 0) n_todo = 0;
   __syncthreads();
-  const int64_t c = (int64_t)blockIdx.x * 256 + tid;
-  if (c < p.n_clusters) {
+  const int64_t c = (int64_t)blockIdx.x * FIX_CLUSTERS + tid;
+  if (tid < FIX_CLUSTERS && c < p.n_clusters) {
     const int beg = p.clu_rowptr[c], end = p.clu_rowptr[c + 1];
     const bool empty = end == beg;
     const bool cut = !empty && (beg / p.piece_e != (end - 1) / p.piece_e);
@@ -415,7 +416,7 @@ enc_fix_kernel(EncFinishArgs p) {
   const int warp = tid >> 5, lane = tid & 31;
   for (int item = warp; item < 2 * n_todo; item += 8) {
     const int side = item & 1;
-    const int64_t cc = (int64_t)blockIdx.x * 256 + todo[item >> 1];
+    const int64_t cc = (int64_t)blockIdx.x * FIX_CLUSTERS + todo[item >> 1];
     const int beg = p.clu_rowptr[cc], end = p.clu_rowptr[cc + 1];
     float4* feat = reinterpret_cast<float4*>(p.clu_feat + ((size_t)side * p.n_clusters + cc) * H) + lane;
     if (end == beg) { *feat = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
@@ -443,7 +444,7 @@ enc_fix_kernel(EncFinishArgs p) {
 int enc_finish(const EncFinishArgs& a, cudaStream_t s) {
   if (a.n_clusters == 0) return CNS_OK;
   if (a.fix_only) {
-    enc_fix_kernel<<<ceil_div(a.n_clusters, 256), 256, 0, s>>>(a);
+    enc_fix_kernel<<<ceil_div(a.n_clusters, FIX_CLUSTERS), 256, 0, s>>>(a);
     CNS_LAUNCH_CHECK();
     return CNS_OK;
   }

@@ -304,7 +304,7 @@ graph_tiles_kernel(const int64_t* __restrict__ num_clusters, int n_graphs, int* 
 // Per-frame masking of B resident target graphs in cluster-major form (GraphGenerator._get_graph,
 // graph_gen.py:199-228, for every scene at once): the keypoint -> cluster edge list keeps the visible
 // members of every cluster in their static order, so it is a per-cluster compaction:
-// count (warp per cluster) -> one-CTA scan -> emit (warp per cluster).  The scan IS the cluster rowptr the
+// count (warp per cluster) -> scan (1024 clusters per CTA) -> emit (warp per cluster).  The scan IS the cluster rowptr the
 // encoder needs, so the forward does not have to re-derive it from the edge list.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -320,17 +320,20 @@ frame_count_kernel(const int64_t* __restrict__ member_order, const int* __restri
   if (lane == 0) { cnt[c] = n; cluster_mask[c] = n > 0 ? 1 : 0; }
 }
 
-// exclusive scan of n <= 1024 * 64 counts in one CTA: every thread owns a contiguous run, one block scan of the run totals
+// exclusive scan of the counts, 1024 per CTA: a CTA first sums everything in front of its chunk (coalesced, L2-resident,
+// at most n / 1024 loads per thread), then scans its own 1024 -- no serial single-CTA pass over the whole array
 __global__ void __launch_bounds__(1024)
 frame_scan_kernel(const int* __restrict__ cnt, int n, int* __restrict__ rowptr) {
-  __shared__ int total;
-  const int per = (n + 1023) / 1024;
-  const int beg = min(threadIdx.x * per, n), end = min(beg + per, n);
-  int sum = 0;
-  for (int i = beg; i < end; ++i) sum += cnt[i];
-  int run = block_exclusive_scan(sum, &total);
-  for (int i = beg; i < end; ++i) { rowptr[i] = run; run += cnt[i]; }
-  if (threadIdx.x == 0) rowptr[n] = total;
+  __shared__ int front, total;
+  const int base = blockIdx.x * SCAN_BLOCK, i = base + threadIdx.x;
+  int pre = 0;
+  for (int k = threadIdx.x; k < base; k += SCAN_BLOCK) pre += cnt[k];
+  block_exclusive_scan(pre, &front);
+  __syncthreads();
+  const int v = i < n ? cnt[i] : 0;
+  const int ex = block_exclusive_scan(v, &total) + front;
+  if (i < n) rowptr[i] = ex;
+  if (i == n - 1) rowptr[n] = ex + v;
 }
 
 __global__ void __launch_bounds__(256)
@@ -361,7 +364,7 @@ int frame_mask(const int64_t* member_order, const int* member_ptr, const uint8_t
   const int C = (int)n_clusters;
   frame_count_kernel<<<ceil_div(C, 8), 256, 0, s>>>(member_order, member_ptr, visible, C, cnt_scratch, cluster_mask);
   CNS_LAUNCH_CHECK();
-  frame_scan_kernel<<<1, 1024, 0, s>>>(cnt_scratch, C, clu_rowptr);
+  frame_scan_kernel<<<ceil_div(C, SCAN_BLOCK), SCAN_BLOCK, 0, s>>>(cnt_scratch, C, clu_rowptr);
   CNS_LAUNCH_CHECK();
   frame_emit_kernel<<<ceil_div(C, 8), 256, 0, s>>>(member_order, member_ptr, visible, C, clu_rowptr, e01_j, e01_i);
   CNS_LAUNCH_CHECK();
