@@ -185,6 +185,41 @@ def test_frame_mask_bit_exact_vs_graph_generator():
     assert torch.equal(rowptr.cpu().long(), want)
 
 
+@pytest.mark.parametrize("n_clusters", [1, 1024, 1025, 70001])
+def test_frame_mask_many_clusters(n_clusters):
+    """The scan of cns_frame_mask runs 1024 clusters per CTA: sizes around the CTA boundary and far beyond it (ragged
+    clusters, some empty, some fully hidden) against the same compaction written in numpy."""
+    lib = _lib.load()
+    rng = np.random.default_rng(n_clusters)
+    csize = rng.integers(0, 13, size=n_clusters)
+    csize[0] = max(csize[0], 1)
+    N = int(csize.sum())
+    order = rng.permutation(N).astype(np.int64)
+    ptr = np.concatenate([[0], np.cumsum(csize)]).astype(np.int32)
+    vis = rng.random(N) < 0.6
+    hidden_clusters = rng.choice(n_clusters, size=max(1, n_clusters // 50), replace=False)
+    for c in hidden_clusters:
+        vis[order[ptr[c]:ptr[c + 1]]] = False
+    owner = np.repeat(np.arange(n_clusters), csize)
+    keep = vis[order]
+    want_j, want_i = order[keep], owner[keep]
+    want_ptr = np.concatenate([[0], np.cumsum(np.bincount(want_i, minlength=n_clusters))])
+    d = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=DEV)
+    t_order, t_ptr, t_vis = d(order, torch.int64), d(ptr, torch.int32), d(vis, torch.uint8)
+    e01_j = torch.full((max(N, 1),), -1, dtype=torch.int64, device=DEV)
+    e01_i = torch.full((max(N, 1),), -1, dtype=torch.int64, device=DEV)
+    cmask = torch.empty(n_clusters, dtype=torch.uint8, device=DEV)
+    rowptr = torch.empty(n_clusters + 1, dtype=torch.int32, device=DEV)
+    ws = torch.empty((n_clusters + 1) * 4, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.cns_frame_mask(_lib.ptr(t_order), _lib.ptr(t_ptr), _lib.ptr(t_vis), N, n_clusters, _lib.ptr(e01_j),
+                                  _lib.ptr(e01_i), _lib.ptr(cmask), _lib.ptr(rowptr), _lib.ptr(ws), ws.numel(), _sp()), "frame_mask")
+    n01 = len(want_j)
+    assert np.array_equal(rowptr.cpu().numpy(), want_ptr)
+    assert np.array_equal(e01_j[:n01].cpu().numpy(), want_j)
+    assert np.array_equal(e01_i[:n01].cpu().numpy(), want_i)
+    assert np.array_equal(cmask.cpu().numpy().astype(bool), np.diff(want_ptr) > 0)
+
+
 def test_label_nearest_matches_numpy_argmax():
     lib = _lib.load()
     rng = np.random.default_rng(4)
