@@ -386,6 +386,7 @@ int cns_set_tc_tile(cns_handle* h, int tile_n) {
 int cns_set_option(cns_handle* h, const char* name, long long value) {
   CNS_REQUIRE(h != nullptr && name != nullptr, "NULL argument");
   if (!strcmp(name, "cuda_graphs")) { h->use_graphs = value != 0; if (!value) graph_cache_clear(h); return CNS_OK; }
+  if (!strcmp(name, "target_edge_cache")) { h->no_edge_cache = value == 0; return CNS_OK; }   // read by cns_target_cache_create
   if (!strcmp(name, "tc_slots")) { CNS_REQUIRE(value >= 4 && value <= 6, "tc_slots must be 4..6"); h->tc_slots = (int)value; return CNS_OK; }
   set_error("cns_set_option: unknown option '%s'", name);
   return CNS_ERR_INVALID_ARGUMENT;

@@ -75,7 +75,8 @@ int cns_set_precision(cns_handle* h, int precision /* cns_precision */);
 int cns_set_tc_tile(cns_handle* h, int tile_n /* 32 or 64: edges per tensor-core tile */);
 /* Tuning switches (no reference counterpart): "cuda_graphs" 0/1 - replay repeated cns_graphvs_forward calls (same sizes,
  * pointers and mode) as one CUDA-graph launch, default 1 (CNS_NO_GRAPHS=1 in the environment turns it off);
- * "tc_slots" 4..6 - edge tiles in flight per SM. */
+ * "tc_slots" 4..6 - edge tiles in flight per SM; "target_edge_cache" 0/1 - whether cns_target_cache_create keeps the
+ * per-keypoint target-side logits / values (default 1; caches created while it is 0 recompute the target side per frame). */
 int cns_set_option(cns_handle* h, const char* name, long long value);
 /* "graph_replays", "graph_captures", "edge_cache_forwards" (forwards enqueued with the target side taken from a
  * cns_target_cache's per-keypoint cache), "kernel_launches" (library-wide host-side count); -1 for an unknown name */
