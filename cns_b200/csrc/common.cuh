@@ -89,7 +89,7 @@ struct Packed {
   unsigned char* tc_c1[2]; unsigned char* tc_c1_fc[2]; unsigned char* tc_out[2];
   unsigned char* tc_adst[2];                    // (A0 lin_dst): the per-cluster attention term a' as a gemm_tc product (f16 mode)
   unsigned char* tc_node_base;
-  // bf16 (hi, lo) split images of the same seven matrices for the fp32 mode (gemm_tc_split.cu)
+  // (hi, lo) split images of the same seven matrices for the fp32 mode (gemm_tc_split.cu; slice format = cns_handle::split_f16)
   unsigned char* tc2_c0; unsigned char* tc2_c0_fc; unsigned char* tc2_g; unsigned char* tc2_k;
   unsigned char* tc2_c1; unsigned char* tc2_c1_fc; unsigned char* tc2_out;
   unsigned char* tc2_base;
@@ -111,11 +111,12 @@ struct cns_handle {
   void* bwd_pack; long long bwd_pack_version;   // transposed operands of the backward pass (backward.cu)
   // tensor-core (tcgen05) encoder operands: bf16 image then f16 image, 5 swizzled 32 KB tiles each
   unsigned char* tc_w_img;
-  unsigned char* tc_w_split;                            // fp32 mode: bf16 (hi, lo) slices of the same five matrices (encoder_split.cu)
+  unsigned char* tc_w_split;                            // fp32 mode: (hi, lo) slices of the same five matrices (encoder_split.cu)
   int no_split_encoder;                                 // CNS_NO_SPLIT_ENCODER=1: fp32 mode keeps the FFMA edge kernel (A-B runs)
   alignas(16) float tc_small_host[128 * 2 + 128 + 128 * 4 + 128];   // in_enc / pos_nn.0 weights passed as kernel params
   int tc_tile_n;                                        // edges per tensor-core tile (32 or 64)
   int tc_slots;                                         // tiles in flight per SM of the 32-edge kernel: 4, 5 or 6 (CNS_TC_SLOTS)
+  int split_f16;                                        // slices of the fp32-tolerance kernels: 1 = two f16 (inference default), 0 = two bf16 (training: fp32's range)
   int no_split_gemm;                                    // CNS_NO_SPLIT_GEMM=1: backward GEMMs stay on the fp32 FFMA kernel (A-B runs)
   int no_edge_subtract;                                 // CNS_NO_EDGE_SUBTRACT=1: cached target side always re-sums the visible keypoints (A-B runs)
   int no_edge_cache;                                    // CNS_NO_EDGE_CACHE=1: target caches keep no per-keypoint logits / values (A-B runs)

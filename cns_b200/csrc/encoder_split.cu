@@ -1,8 +1,9 @@
 // fp32-accurate encoder edge kernel on tcgen05 (CNS_PREC_FP32): the keypoint->cluster attention chain of
-// cns/models/graph_vs.py:195-214 with BOTH operands of every 128x128 GEMM split into two bf16 slices
-// (v = hi + lo carries 16 mantissa bits at fp32's exponent range, so nothing needs scaling) and the three
+// cns/models/graph_vs.py:195-214 with BOTH operands of every 128x128 GEMM split into two 16-bit slices
+// (F16S = false: bf16, v = hi + lo carries 16 mantissa bits at fp32's exponent range - training;
+//  F16S = true: f16, 22 mantissa bits at f16's range - inference; tc_common.cuh split_pair) and the three
 // slice products hi*hi, hi*lo, lo*hi accumulated in one fp32 TMEM tile.  Measured against the fp64 oracle the
-// cluster features come out at ~1e-5 (the dropped lo*lo term is 2^-18 relative), an order of magnitude inside
+// cluster features come out at ~1e-5 with bf16 slices (the dropped lo*lo term is 2^-18 relative), an order of magnitude inside
 // the 1e-4 budget of the fp32 mode, at 3 tensor-core passes instead of one FFMA pass per weight.
 //
 // Same algebra, tile walk and online segment softmax as encoder_tc.cu (see the notes there):
@@ -47,6 +48,7 @@ static_assert(SP_ACC_COLS + SP_TMEM_SLICES * 64 <= 512, "tensor memory budget");
 // image order in global memory: [hi0 hi1 hi2 hi3 hi4 lo4 | lo0 lo1 lo2 lo3]
 __host__ __device__ __forceinline__ int sp_image_slot(int w, int lo) { return lo ? (w == 4 ? 5 : 6 + w) : w; }
 
+template <bool F16S>
 __global__ void sp_pack_weights_kernel(const float* __restrict__ chain, unsigned char* __restrict__ img) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= SP_NW * 128 * 128) return;
@@ -54,11 +56,11 @@ __global__ void sp_pack_weights_kernel(const float* __restrict__ chain, unsigned
   const int k = rem / 128, o = rem % 128;          // chain[w][k][o] = W_w[o][k]
   float v = chain[idx];
   if (w == 4) v *= 1.4426950408889634f;            // logits in log2 units (softmax with ex2)
-  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  unsigned short hi, lo;
+  split_scalar<F16S>(v, hi, lo);
   const uint32_t off = sw128_off(128, o, k);
-  *reinterpret_cast<unsigned short*>(img + (size_t)sp_image_slot(w, 0) * SP_W_BYTES + off) = __bfloat16_as_ushort(hi);
-  *reinterpret_cast<unsigned short*>(img + (size_t)sp_image_slot(w, 1) * SP_W_BYTES + off) = __bfloat16_as_ushort(lo);
+  *reinterpret_cast<unsigned short*>(img + (size_t)sp_image_slot(w, 0) * SP_W_BYTES + off) = hi;
+  *reinterpret_cast<unsigned short*>(img + (size_t)sp_image_slot(w, 1) * SP_W_BYTES + off) = lo;
 }
 
 struct SpSmallW {          // kernel parameter space: per channel k {in_enc.w[k][0..1], in_enc.b[k], pos_nn.0.b[k]}, pos_nn.0.w[k][0..3]
@@ -72,15 +74,8 @@ struct SpArgs {
   int tiles_per_chunk;
 };
 
-// (a, b) -> packed bf16 heads and tails: a = hi.a + lo.a to 16 mantissa bits
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);   // exact
-  __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
-  lo = *reinterpret_cast<uint32_t*>(&l);
-}
-
+// F16S: slice format of both operands (tc_common.cuh, split_pair)
+template <bool F16S>
 __global__ void __launch_bounds__(128 * SP_SUB * SP_SLOTS, 1)
 enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant__ SpSmallW sw) {
   constexpr int TN = SP_TN, SLOTS = SP_SLOTS, TS = SP_TS;
@@ -153,7 +148,7 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
 
   // instruction descriptor: D = f32 (bit 4), A / B = bf16 (1 at bits 7 / 10), N >> 3 at bit 17, M >> 4 at bit 24;
   // bit 16 = B is MN-major
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t idesc = (1u << 4) | split_fmt_bits<F16S>() | ((uint32_t)(TN >> 3) << 17) | ((128u >> 4) << 24);
   const uint32_t idesc_mn = idesc | (1u << 16);
 
   const int s = warp >> 3;                       // MMA slot
@@ -341,8 +336,8 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
             xv[h2] = fmaxf(x, 0.f);
             hv[h2] = fmaxf(hp, 0.f);
           }
-          split2(xv[0], xv[1], xo[q], xt[q]);
-          split2(hv[0], hv[1], ho[q], ht[q]);
+          split_pair<F16S>(xv[0], xv[1], xo[q], xt[q]);
+          split_pair<F16S>(hv[0], hv[1], ho[q], ht[q]);
         }
         const uint32_t off = sw128_off(TN, row, k0);
         *reinterpret_cast<uint4*>(xh + off) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
@@ -388,7 +383,7 @@ enc_edge_split_kernel(const __grid_constant__ SpArgs args, const __grid_constant
             }
             v[h2] = fmaxf(acc[q + h2] + adb, 0.f);
           }
-          split2(v[0], v[1], pk[q / 2], pt[q / 2]);
+          split_pair<F16S>(v[0], v[1], pk[q / 2], pt[q / 2]);
         }
         const uint32_t off = u_off + (((uint32_t)(sub * (TS / 8) + cg) ^ u_xor) << 4);
         *reinterpret_cast<uint4*>(xh + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -472,7 +467,8 @@ int split_piece_edges(int64_t n_e01, const cns_handle* h) {
 int split_pack_weights(cns_handle* h, cudaStream_t s) {
   if (!h->tc_w_split) CNS_CUDA_CHECK(cudaMalloc(&h->tc_w_split, (size_t)2 * SP_NW * SP_W_BYTES));
   const int total = SP_NW * 128 * 128;
-  sp_pack_weights_kernel<<<ceil_div(total, 256), 256, 0, s>>>(h->pk.tc_chain, h->tc_w_split);
+  if (h->split_f16) sp_pack_weights_kernel<true><<<ceil_div(total, 256), 256, 0, s>>>(h->pk.tc_chain, h->tc_w_split);
+  else sp_pack_weights_kernel<false><<<ceil_div(total, 256), 256, 0, s>>>(h->pk.tc_chain, h->tc_w_split);
   CNS_LAUNCH_CHECK();
   return CNS_OK;
 }
@@ -482,7 +478,8 @@ int enc_edge_split(const EncEdgeArgs& a, const cns_handle* h, cudaStream_t s) {
   CNS_REQUIRE(h->tc_w_split != nullptr, "split weight image missing");
   static unsigned long long configured = 0;
   if (first_use_on_device(configured)) {
-    CNS_CUDA_CHECK(cudaFuncSetAttribute(enc_edge_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM_BYTES));
+    CNS_CUDA_CHECK(cudaFuncSetAttribute(enc_edge_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM_BYTES));
+    CNS_CUDA_CHECK(cudaFuncSetAttribute(enc_edge_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM_BYTES));
   }
   SpArgs ta;
   ta.e = a;
@@ -493,7 +490,8 @@ int enc_edge_split(const EncEdgeArgs& a, const cns_handle* h, cudaStream_t s) {
   ta.tiles_per_chunk = tpc;
   static_assert(sizeof(SpSmallW) == sizeof(h->tc_small_host), "first-layer weight table");
   const SpSmallW* sw = reinterpret_cast<const SpSmallW*>(h->tc_small_host);
-  enc_edge_split_kernel<<<grid, 128 * SP_SUB * SP_SLOTS, SP_SMEM_BYTES, s>>>(ta, *sw);
+  if (h->split_f16) enc_edge_split_kernel<true><<<grid, 128 * SP_SUB * SP_SLOTS, SP_SMEM_BYTES, s>>>(ta, *sw);
+  else enc_edge_split_kernel<false><<<grid, 128 * SP_SUB * SP_SLOTS, SP_SMEM_BYTES, s>>>(ta, *sw);
   CNS_LAUNCH_CHECK();
   return CNS_OK;
 }

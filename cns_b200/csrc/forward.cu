@@ -181,7 +181,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
   // mantissa on BOTH the edge-level and the recurrent cluster-level layers the hidden state drifts past
   // the 2e-2 budget after a few frames, so bf16 mode keeps them in fp32 (measured).
   const bool tc = h->precision == CNS_PREC_F16;
-  // fp32 mode: the same GEMMs with bf16 (hi, lo) operand splits (three tensor-core products, ~1e-5 of fp64); bf16 mode takes
+  // fp32 mode: the same GEMMs with (hi, lo) operand splits (three tensor-core products, ~1e-5 of fp64); bf16 mode takes
   // them too (its cluster level has to stay at fp32 accuracy, see above - on the tensor cores instead of the FFMA kernel)
   const bool tc2 = (h->precision == CNS_PREC_FP32 && !h->no_split_encoder) || (h->precision == CNS_PREC_BF16 && !h->no_split_gemm);
   const int tci = (h->precision == CNS_PREC_BF16) ? 0 : 1;
@@ -291,7 +291,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
     GemmTcArgs ga{};
     ga.m = C; ga.k1 = 2 * H; ga.k2 = 0; ga.n_out = H; ga.x1 = f.pq; ga.w_img = tc2 ? pk.tc2_out : pk.tc_out[tci];
     ga.bias = h->P(P_OUT_B); ga.row_mask = b->cluster_mask; ga.relu = 1; ga.y = f.x_clu;
-    if (tc2) { RUN(gemm_tc_split(ga, s)); } else { RUN(gemm_tc(ga, tci == 0, s)); }
+    if (tc2) { RUN(gemm_tc_split(ga, h->split_f16 != 0, s)); } else { RUN(gemm_tc(ga, tci == 0, s)); }
   }
 
   // ---- backbone ---------------------------------------------------------------------------
@@ -303,7 +303,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
       ga.m = C; ga.k1 = H; ga.k2 = x2 ? H : 0; ga.n_out = n_out; ga.x1 = x1; ga.x2 = x2; ga.w_img = tc2 ? img2 : img[tci];
       ga.k_img = k_img;
       ga.bias = bias; ga.pos = f.pos_clu; ga.wp = wp; ga.relu = 0; ga.y = f.pq;
-      return tc2 ? gemm_tc_split(ga, s) : gemm_tc(ga, tci == 0, s);
+      return tc2 ? gemm_tc_split(ga, h->split_f16 != 0, s) : gemm_tc(ga, tci == 0, s);
     }
     LinearArgs la{};
     la.m = C; la.k1 = H; la.k2 = x2 ? H : 0; la.n_out = n_out;
@@ -336,7 +336,7 @@ int forward_impl(cns_handle* h, const cns_batch* b, const float* hidden_in, floa
       GemmTcArgs ga{};
       ga.m = C; ga.k1 = H; ga.k2 = 0; ga.n_out = H; ga.x1 = gnb; ga.w_img = tc2 ? fc_img2 : fc_img[tci]; ga.bias = h->P(fc_b);
       ga.residual = x; ga.relu = 1; ga.y = y;
-      return tc2 ? gemm_tc_split(ga, s) : gemm_tc(ga, tci == 0, s);
+      return tc2 ? gemm_tc_split(ga, h->split_f16 != 0, s) : gemm_tc(ga, tci == 0, s);
     }
     LinearArgs la{};
     la.m = C; la.k1 = H; la.k2 = 0; la.n_out = H; la.x1 = gnb; la.wt = fc_t; la.bias = h->P(fc_b);
@@ -465,7 +465,7 @@ static int forward_graphed(cns_handle* h, const cns_batch* b, const float* hidde
   key = fnv(key, b, sizeof(*b));
   const void* ptrs[6] = {hidden_in, vel_si_vec, vel_si_norm, hidden_out, vel, workspace};
   key = fnv(key, ptrs, sizeof(ptrs));
-  const long long mode[8] = {h->precision, h->weights_version, h->timing, h->tc_tile_n, h->tc_slots, 0,
+  const long long mode[8] = {h->precision, h->weights_version, h->timing, h->tc_tile_n, h->tc_slots, h->split_f16,
                              h->no_fused_backbone * 2 + h->no_split_encoder + 4 * h->no_tc_cluster_pre, b->target_cache ? b->target_cache->uid : 0};
   key = fnv(key, mode, sizeof(mode));
   if (key == 0) key = 1;

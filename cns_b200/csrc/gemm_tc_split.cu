@@ -1,7 +1,8 @@
 // fp32-accurate tcgen05 GEMM for the batched cluster-level MLPs of the fp32 mode (PointEdgeConv [P|Q] projections,
 // PERConv fc layers, out_enc; cns/models/graph_vs.py:16-31,108,145,229):
 //   Y = act([X1 | X2] W^T + pos Wp + bias + residual) * row_mask
-// Both operands are split into two bf16 slices (hi + lo = 16 mantissa bits at fp32's exponent range) and the three
+// Both operands are split into two 16-bit slices (bf16: hi + lo = 16 mantissa bits at fp32's exponent range; f16: 22 bits at
+// f16's range - template parameter F16S, tc_common.cuh split_pair) and the three
 // products hi*hi, lo*hi, hi*lo accumulate in one fp32 TMEM tile - the same scheme as the encoder edge kernel of this
 // mode (encoder_split.cu); measured against the fp64 oracle the whole forward stays at ~1e-5 (budget 1e-4).
 //
@@ -23,27 +24,21 @@ constexpr uint32_t G2_UNIT = 128 * 128 * 2;                       // one slice o
 constexpr size_t G2_SMEM = 3 * G2_UNIT + 3 * 256 * 4 + 256 + 1024;  // A hi, A lo, W unit, bias / wp rows, barriers, slack
 
 // image: [n / 128][k / 128][slice][128 rows (n) x 128 k, K-major SWIZZLE_128B]
+template <bool F16S>
 __global__ void g2_pack_kernel(const float* __restrict__ wt, int k_dim, int n_out, unsigned char* __restrict__ img) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= k_dim * n_out) return;
   const int k = idx / n_out, n = idx % n_out;
   const float v = wt[idx];
-  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  unsigned short hi, lo;
+  split_scalar<F16S>(v, hi, lo);
   const size_t block = ((size_t)(n / 128) * (k_dim / 128) + (k / 128)) * 2;
   const uint32_t off = sw128_off(128, n % 128, k % 128);
-  *reinterpret_cast<unsigned short*>(img + block * G2_UNIT + off) = __bfloat16_as_ushort(hi);
-  *reinterpret_cast<unsigned short*>(img + (block + 1) * G2_UNIT + off) = __bfloat16_as_ushort(lo);
+  *reinterpret_cast<unsigned short*>(img + block * G2_UNIT + off) = hi;
+  *reinterpret_cast<unsigned short*>(img + (block + 1) * G2_UNIT + off) = lo;
 }
 
-__device__ __forceinline__ void g2_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
-  __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
-  lo = *reinterpret_cast<uint32_t*>(&l);
-}
-
+template <bool F16S>
 __global__ void __launch_bounds__(G2_THREADS, 2)
 gemm_tc_split_kernel(const __grid_constant__ GemmTcArgs p) {
   extern __shared__ unsigned char smem_raw[];
@@ -84,7 +79,7 @@ gemm_tc_split_kernel(const __grid_constant__ GemmTcArgs p) {
 
   for (int h = 0; h < KH; ++h) {
     if (warp < 8) {
-      // ---- A half h: fp32 rows -> (hi, lo) bf16 SWIZZLE_128B images.  The previous half's MMAs have drained. ----
+      // ---- A half h: fp32 rows -> (hi, lo) SWIZZLE_128B images.  The previous half's MMAs have drained. ----
       if (h > 0) { mbar_wait(smem_u32(&bars[2]), (uint32_t)((h - 1) & 1)); tc_fence_after(); }
       for (int q = tid; q < 128 * 16; q += 256) {
         const int row = q >> 4, k = (q & 15) * 8;
@@ -97,8 +92,8 @@ gemm_tc_split_kernel(const __grid_constant__ GemmTcArgs p) {
           hi4 = *reinterpret_cast<const float4*>(src + 4);
         }
         uint32_t hh[4], ll[4];
-        g2_split2(lo4.x, lo4.y, hh[0], ll[0]); g2_split2(lo4.z, lo4.w, hh[1], ll[1]);
-        g2_split2(hi4.x, hi4.y, hh[2], ll[2]); g2_split2(hi4.z, hi4.w, hh[3], ll[3]);
+        split_pair<F16S>(lo4.x, lo4.y, hh[0], ll[0]); split_pair<F16S>(lo4.z, lo4.w, hh[1], ll[1]);
+        split_pair<F16S>(hi4.x, hi4.y, hh[2], ll[2]); split_pair<F16S>(hi4.z, hi4.w, hh[3], ll[3]);
         const uint32_t off = sw128_off(128, row, k);
         *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
         *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
@@ -109,7 +104,7 @@ gemm_tc_split_kernel(const __grid_constant__ GemmTcArgs p) {
     __syncthreads();
     tc_fence_after();
     if (warp == 8 && lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | split_fmt_bits<F16S>() | ((128u >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), wb = smem_u32(w_s);
       for (int c = 0; c < NC; ++c) {
         const uint32_t d = tmem_base + (uint32_t)(c * 128);
@@ -185,24 +180,27 @@ gemm_tc_split_kernel(const __grid_constant__ GemmTcArgs p) {
 
 }  // namespace
 
-int gemm_tc_split(const GemmTcArgs& a, cudaStream_t s) {
+int gemm_tc_split(const GemmTcArgs& a, bool f16_slices, cudaStream_t s) {
   if (a.m == 0) return CNS_OK;
   CNS_REQUIRE(a.n_out % 128 == 0 && a.n_out <= 512, "gemm_tc_split: n_out must be 128..512, multiple of 128");
   CNS_REQUIRE((a.k1 == 128 || a.k1 == 256) && (a.k2 == 0 || a.k2 == 128) && a.k1 + a.k2 <= 256, "gemm_tc_split: K must be 128 or 256");
   CNS_REQUIRE(a.w_img != nullptr, "gemm_tc_split: weight image missing");
   static unsigned long long configured = 0;
   if (first_use_on_device(configured)) {
-    CNS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
+    CNS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
+    CNS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
   }
   const dim3 grid((unsigned)ceil_div(a.m, 128), (unsigned)ceil_div(a.n_out, 256));
-  gemm_tc_split_kernel<<<grid, G2_THREADS, G2_SMEM, s>>>(a);
+  if (f16_slices) gemm_tc_split_kernel<true><<<grid, G2_THREADS, G2_SMEM, s>>>(a);
+  else gemm_tc_split_kernel<false><<<grid, G2_THREADS, G2_SMEM, s>>>(a);
   CNS_LAUNCH_CHECK();
   return CNS_OK;
 }
 
-int gemm_tc_split_pack(const float* wt, int k_dim, int n_out, unsigned char* img, cudaStream_t s) {
+int gemm_tc_split_pack(const float* wt, int k_dim, int n_out, unsigned char* img, bool f16_slices, cudaStream_t s) {
   const int total = k_dim * n_out;
-  g2_pack_kernel<<<ceil_div(total, 256), 256, 0, s>>>(wt, k_dim, n_out, img);
+  if (f16_slices) g2_pack_kernel<true><<<ceil_div(total, 256), 256, 0, s>>>(wt, k_dim, n_out, img);
+  else g2_pack_kernel<false><<<ceil_div(total, 256), 256, 0, s>>>(wt, k_dim, n_out, img);
   CNS_LAUNCH_CHECK();
   return CNS_OK;
 }

@@ -205,7 +205,7 @@ int repack(cns_handle* h, cudaStream_t s) {
       for (int i = 0; i < 7; ++i) { *split_dst[i] = q; q += (size_t)items[i].k * items[i].n * 2 * 2; }
     }
     for (int i = 0; i < 7; ++i)
-      if ((rc = gemm_tc_split_pack(items[i].wt, items[i].k, items[i].n, *split_dst[i], s)) != CNS_OK) return rc;
+      if ((rc = gemm_tc_split_pack(items[i].wt, items[i].k, items[i].n, *split_dst[i], h->split_f16 != 0, s)) != CNS_OK) return rc;
   }
   if ((rc = bf_pack_vec(h, s)) != CNS_OK) return rc;
   h->weights_loaded = true;
@@ -255,6 +255,7 @@ int cns_create(cns_handle** out, int device) {
   h->no_edge_cache = getenv("CNS_NO_EDGE_CACHE") ? 1 : 0;
   h->no_edge_subtract = getenv("CNS_NO_EDGE_SUBTRACT") ? 1 : 0;
   h->no_split_gemm = getenv("CNS_NO_SPLIT_GEMM") ? 1 : 0;
+  h->split_f16 = getenv("CNS_SPLIT_BF16") ? 0 : 1;
   h->no_split_encoder = getenv("CNS_NO_SPLIT_ENCODER") ? 1 : 0;
   h->tc_slots = getenv("CNS_TC_SLOTS") ? atoi(getenv("CNS_TC_SLOTS")) : 5;
   h->use_graphs = getenv("CNS_NO_GRAPHS") ? 0 : 1;
@@ -387,6 +388,11 @@ int cns_set_option(cns_handle* h, const char* name, long long value) {
   CNS_REQUIRE(h != nullptr && name != nullptr, "NULL argument");
   if (!strcmp(name, "cuda_graphs")) { h->use_graphs = value != 0; if (!value) graph_cache_clear(h); return CNS_OK; }
   if (!strcmp(name, "target_edge_cache")) { h->no_edge_cache = value == 0; return CNS_OK; }   // read by cns_target_cache_create
+  if (!strcmp(name, "split_slices_f16")) {
+    CNS_REQUIRE(!h->weights_loaded || (value != 0) == (h->split_f16 != 0), "split_slices_f16: set it before the weights are loaded");
+    h->split_f16 = value != 0;
+    return CNS_OK;
+  }
   if (!strcmp(name, "tc_slots")) { CNS_REQUIRE(value >= 4 && value <= 6, "tc_slots must be 4..6"); h->tc_slots = (int)value; return CNS_OK; }
   set_error("cns_set_option: unknown option '%s'", name);
   return CNS_ERR_INVALID_ARGUMENT;

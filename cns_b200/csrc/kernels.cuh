@@ -68,7 +68,7 @@ struct EncEdgeArgs {
 int enc_edge_fp32(const EncEdgeArgs& a, cudaStream_t s);
 int enc_edge_tc(const EncEdgeArgs& a, int precision, const cns_handle* h, cudaStream_t s);
 int tc_pack_weights(cns_handle* h, cudaStream_t s);
-int enc_edge_split(const EncEdgeArgs& a, const cns_handle* h, cudaStream_t s);   // fp32-accurate: bf16 (hi, lo) operand split on tcgen05
+int enc_edge_split(const EncEdgeArgs& a, const cns_handle* h, cudaStream_t s);   // fp32-accurate: (hi, lo) operand split on tcgen05 (slices: h->split_f16)
 int split_pack_weights(cns_handle* h, cudaStream_t s);
 int split_piece_edges(int64_t n_e01, const cns_handle* h);
 void tc_chunking(int64_t n_e01, int tile_n, int slots, int sm_count, int sides, int* grid, int* tiles_per_chunk);
@@ -134,9 +134,10 @@ struct GemmTcArgs {
 };
 int gemm_tc(const GemmTcArgs& a, bool bf16, cudaStream_t s);
 int gemm_tc_pack(const float* wt, int k_dim, int n_out, unsigned char* img_bf16, unsigned char* img_f16, cudaStream_t s);
-// the same GEMM at fp32 accuracy: bf16 (hi, lo) operand split, three products (gemm_tc_split.cu); w_img from gemm_tc_split_pack
-int gemm_tc_split(const GemmTcArgs& a, cudaStream_t s);
-int gemm_tc_split_pack(const float* wt, int k_dim, int n_out, unsigned char* img, cudaStream_t s);
+// the same GEMM at fp32 accuracy: (hi, lo) operand split, three products (gemm_tc_split.cu); w_img from gemm_tc_split_pack
+// with the same slice format (f16_slices: two f16 slices instead of two bf16 ones, tc_common.cuh split_pair)
+int gemm_tc_split(const GemmTcArgs& a, bool f16_slices, cudaStream_t s);
+int gemm_tc_split_pack(const float* wt, int k_dim, int n_out, unsigned char* img, bool f16_slices, cudaStream_t s);
 
 enum EdgeConvMode { EC_PLAIN = 0, EC_GATES = 1, EC_CANDIDATE = 2 };
 struct EdgeConvArgs {

@@ -184,4 +184,41 @@ __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
   return r;
 }
 
+// Operand split of the fp32-tolerance kernels: v = hi + lo with both slices 16-bit tensor-core operands.
+//   F16S = false: two bf16 slices = 16 mantissa bits at fp32's exponent range (training: gradients and activations of any
+//                 magnitude);
+//   F16S = true : two f16 slices = 22 mantissa bits while |lo| stays a normal f16 (|v| >= 0.25) and an absolute 2^-25
+//                 below that (f16 subnormals) - ~30x closer to fp32 for O(1) operands; |v| must stay below 65504 like in
+//                 the f16 mode (an overflow turns into NaN outputs, never into a silently wrong number).
+template <bool F16S>
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  if (F16S) {
+    __half2 h = __floats2half2_rn(a, b);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    const float2 hf = __half22float2(h);
+    __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);    // the differences are exact in fp32
+    lo = *reinterpret_cast<uint32_t*>(&l);
+  } else {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);   // exact
+    __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+  }
+}
+template <bool F16S>
+__device__ __forceinline__ void split_scalar(float v, unsigned short& hi, unsigned short& lo) {
+  if (F16S) {
+    const __half h = __float2half_rn(v);
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+  }
+}
+// tcgen05 instruction-descriptor format bits of the slices (A at bit 7, B at bit 10): f16 = 0, bf16 = 1
+template <bool F16S> __device__ __forceinline__ constexpr uint32_t split_fmt_bits() { return F16S ? 0u : ((1u << 7) | (1u << 10)); }
+
 }  // namespace cns

@@ -221,6 +221,10 @@ class GraphVS(nn.Module):
         if ent is None:
             h = _lib.Handle(torch.device("cuda", idx))
             h.set_precision("fp32" if training else self.precision)
+            if training:
+                # operand slices of the fp32-tolerance kernels: bf16 pairs keep fp32's exponent range for activations of
+                # weights in the middle of training; inference handles use f16 pairs (closer to fp32, f16's range)
+                h.set_option("split_slices_f16", 0)
             ent = [h, None]
             self._handles[key] = ent
         if ent[1] != version:
