@@ -15,3 +15,11 @@ def test_randomised_forward_soak():
     res = fuzz_forward.run(n_rounds=8)
     for prec, (ok, worst, detail) in res.items():
         assert ok, "%s: %s (worst case %s)" % (prec, worst, detail)
+
+
+def test_randomised_clustering_soak():
+    """Device graph construction == host (scikit-learn) construction bit for bit over random target point sets, including
+    degenerate ones (lines, near-duplicates, tight blobs) that end in the KMeans(4) fallback: scripts/fuzz_clustering.py."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import fuzz_clustering
+    assert fuzz_clustering.run(n_sets=60, verbose=False) == 0
