@@ -116,7 +116,7 @@ struct cns_handle {
   alignas(16) float tc_small_host[128 * 2 + 128 + 128 * 4 + 128];   // in_enc / pos_nn.0 weights passed as kernel params
   int tc_tile_n;                                        // edges per tensor-core tile (32 or 64)
   int tc_slots;                                         // tiles in flight per SM of the 32-edge kernel: 4, 5 or 6 (CNS_TC_SLOTS)
-  int split_f16;                                        // slices of the fp32-tolerance kernels: 1 = two f16 (inference default), 0 = two bf16 (training: fp32's range)
+  int split_f16;                                        // slices of the fp32-tolerance kernels: 1 = two f16 (default), 0 = two bf16 (fp32's exponent range, 16 mantissa bits)
   int no_split_gemm;                                    // CNS_NO_SPLIT_GEMM=1: backward GEMMs stay on the fp32 FFMA kernel (A-B runs)
   int no_edge_subtract;                                 // CNS_NO_EDGE_SUBTRACT=1: cached target side always re-sums the visible keypoints (A-B runs)
   int no_edge_cache;                                    // CNS_NO_EDGE_CACHE=1: target caches keep no per-keypoint logits / values (A-B runs)

@@ -1,7 +1,7 @@
 // fp32-accurate encoder edge kernel on tcgen05 (CNS_PREC_FP32): the keypoint->cluster attention chain of
 // cns/models/graph_vs.py:195-214 with BOTH operands of every 128x128 GEMM split into two 16-bit slices
-// (F16S = false: bf16, v = hi + lo carries 16 mantissa bits at fp32's exponent range - training;
-//  F16S = true: f16, 22 mantissa bits at f16's range - inference; tc_common.cuh split_pair) and the three
+// (F16S = true: f16, 22 mantissa bits at f16's range - the default; F16S = false: bf16, v = hi + lo carries 16 mantissa
+//  bits at fp32's exponent range; tc_common.cuh split_pair) and the three
 // slice products hi*hi, hi*lo, lo*hi accumulated in one fp32 TMEM tile.  Measured against the fp64 oracle the
 // cluster features come out at ~1e-5 with bf16 slices (the dropped lo*lo term is 2^-18 relative), an order of magnitude inside
 // the 1e-4 budget of the fp32 mode, at 3 tensor-core passes instead of one FFMA pass per weight.

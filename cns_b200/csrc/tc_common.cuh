@@ -185,11 +185,11 @@ __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
 }
 
 // Operand split of the fp32-tolerance kernels: v = hi + lo with both slices 16-bit tensor-core operands.
-//   F16S = false: two bf16 slices = 16 mantissa bits at fp32's exponent range (training: gradients and activations of any
-//                 magnitude);
 //   F16S = true : two f16 slices = 22 mantissa bits while |lo| stays a normal f16 (|v| >= 0.25) and an absolute 2^-25
 //                 below that (f16 subnormals) - ~30x closer to fp32 for O(1) operands; |v| must stay below 65504 like in
-//                 the f16 mode (an overflow turns into NaN outputs, never into a silently wrong number).
+//                 the f16 mode (an overflow turns into NaN outputs, never into a silently wrong number).  The default.
+//   F16S = false: two bf16 slices = 16 mantissa bits at fp32's exponent range (CNS_SPLIT_BF16=1 / cns_set_option
+//                 "split_slices_f16" 0: for weights whose activations leave f16's range).
 template <bool F16S>
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
   if (F16S) {

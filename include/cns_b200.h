@@ -78,9 +78,9 @@ int cns_set_tc_tile(cns_handle* h, int tile_n /* 32 or 64: edges per tensor-core
  * "tc_slots" 4..6 - edge tiles in flight per SM; "target_edge_cache" 0/1 - whether cns_target_cache_create keeps the
  * per-keypoint target-side logits / values (default 1; caches created while it is 0 recompute the target side per frame);
  * "split_slices_f16" 0/1 - operand slices of the fp32-tolerance kernels (CNS_PREC_FP32 and the training forward): 1 (default)
- * = two f16 slices per operand (22 mantissa bits, operands must stay below 65504 in magnitude or the outputs turn NaN),
- * 0 = two bf16 slices (16 mantissa bits at fp32's exponent range; CNS_SPLIT_BF16=1 in the environment); set it before the
- * weights are loaded. */
+ * = two f16 slices per operand (22 mantissa bits; activations and weights must stay below 65504 in magnitude or the outputs
+ * turn NaN), 0 = two bf16 slices (16 mantissa bits at fp32's exponent range: ~1e-5 instead of ~1e-6 of fp64 on the outputs;
+ * CNS_SPLIT_BF16=1 in the environment); set it before the weights are loaded. */
 int cns_set_option(cns_handle* h, const char* name, long long value);
 /* "graph_replays", "graph_captures", "edge_cache_forwards" (forwards enqueued with the target side taken from a
  * cns_target_cache's per-keypoint cache), "kernel_launches" (library-wide host-side count); -1 for an unknown name */

@@ -23,3 +23,13 @@ def test_randomised_clustering_soak():
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
     import fuzz_clustering
     assert fuzz_clustering.run(n_sets=60, verbose=False) == 0
+
+
+def test_randomised_backward_soak():
+    """Parameter gradients vs fp64 autograd over random small ragged training batches (1..8 graphs of 4..512 keypoints,
+    1..3 recurrent frames, up to 60 % missing keypoints), bar as in test_gpu_backward.py: scripts/fuzz_backward.py.
+    (Seeds 5000..5009; over 40 seeds two batches sit on a ReLU / max kink of the network - scripts/kink_scan.py - where
+    fp32 and fp64 legitimately take different sides; DESIGN.md section 4, precision policy.)"""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import fuzz_backward
+    assert fuzz_backward.run(n_rounds=10, verbose=False) == 0
