@@ -33,3 +33,12 @@ def test_randomised_backward_soak():
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
     import fuzz_backward
     assert fuzz_backward.run(n_rounds=10, verbose=False) == 0
+
+
+def test_randomised_controller_soak():
+    """Batch-1 servo path (GraphVSController -> cns_servo_step_host) over random sequences: targets switched mid-sequence,
+    4..600 keypoints, up to all but one keypoint missing, whole clusters hidden - every frame against the fp64 oracle
+    (fp32 mode 1e-4, f16 mode 2e-2): scripts/fuzz_controller.py."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import fuzz_controller
+    assert fuzz_controller.run(n_seq=15, verbose=False) == 0
