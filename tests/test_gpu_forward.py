@@ -666,3 +666,26 @@ def test_target_edge_cache_matches_recomputed_target_side(state_dict, precision)
         assert rel(cached[0], ov) < TOL[precision] and rel(cached[2], hid_o) < TOL[precision]
         for s, v in zip(scenes, cached.vel.cpu().numpy()):
             s.step(v * 2)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16"])
+def test_graphs_with_more_than_128_clusters(state_dict, precision):
+    """Clusters given as Voronoi cells of 129 / 200 exemplar keypoints (GraphGenerator.from_exemplars): more cluster rows
+    per graph than a whole-graph tile of the fused backbone holds (128), next to an ordinary graph - the batch takes the
+    per-layer cluster kernels; two recurrent frames against the oracle."""
+    rng = np.random.default_rng(41)
+    np.random.seed(41)
+    scenes = [synth.Scene(rng, 120)]
+    for n, k in ((600, 129), (900, 200)):
+        pts, tar = synth.sample_points(rng, n), synth.sample_target_pose(rng)
+        gen = GraphGenerator.from_exemplars(synth.project_norm(tar, pts), rng.choice(n, size=k, replace=False))
+        assert gen.num_clusters == k
+        scenes.append(synth.Scene(rng, n, generator=gen, points=pts, tar_wcT=tar))
+    net = ckpt.load_model(os.path.join(ROOT, "checkpoints", "cns.pth"), "cuda:0", precision=precision)
+    hg = ho = None
+    for _ in range(2):
+        batch = Batch.from_data_list([s.frame(0.1) for s in scenes])
+        pred, ho = _check(net, batch, hg, ho, state_dict, tol=TOL[precision])
+        hg = pred[2]
+        for s in scenes:
+            s.step(synth.pbvs_straight(s.cur_wcT, s.tar_wcT) * 2)
