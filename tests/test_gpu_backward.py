@@ -204,3 +204,64 @@ def test_gradients_are_bit_identical_from_run_to_run(state_dict):
             grads.append({n: p.grad.detach().clone() for n, p in net.named_parameters()})
         bad = [n for n in grads[0] if not torch.equal(grads[0][n], grads[1][n])]
         assert not bad, (n_graphs, n_pts, bad)
+
+
+def test_window_with_scenes_restarting_one_by_one(state_dict):
+    """TBPTTStepper carries the hidden state per scene: when ONE scene of the batch restarts inside a window (here with a
+    different target, hence another cluster count) only its cluster rows start from zero, the other scenes keep theirs and
+    the gradient still flows through them.  Loss and parameter gradients against the oracle doing the same row surgery;
+    `hidden_reset="batch"` reproduces the reference's literal rule (whole state dropped, train_gvs_short_seq.py:28)."""
+    rng = np.random.default_rng(77)
+    np.random.seed(77)
+    scenes = [synth.Scene(rng, n) for n in (40, 120, 64)]
+    windows = []
+    for t in range(4):
+        if t == 2:
+            scenes[1] = synth.Scene(rng, 90)                     # scene 1 restarts on a new target
+        fr = [s.frame(0.15, with_labels=True) for s in scenes]
+        if t == 0:
+            for f in fr:
+                f.start_new_scene()
+        if t == 2:
+            fr[1].start_new_scene()
+        windows.append(Batch.from_data_list(fr))
+        for s in scenes:
+            s.step(synth.pbvs_straight(s.cur_wcT, s.tar_wcT) * 2)
+    assert windows[1].num_clusters.tolist() != windows[2].num_clusters.tolist()
+
+    def oracle(rule):
+        W = {k: v.double().clone().requires_grad_(True) for k, v in state_dict.items()}
+        hid, counts, loss = None, None, 0
+        for bt in windows:
+            fresh = bt.new_scene.reshape(-1).bool()
+            if hid is not None and bool(fresh.any()):
+                if rule == "batch" or bool(fresh.all()):
+                    hid = None
+                else:
+                    parts, o = [], 0
+                    for g, c_new in enumerate(bt.num_clusters.tolist()):
+                        c_old = int(counts[g])
+                        parts.append(torch.zeros(c_new, 128, dtype=torch.float64) if fresh[g] else hid[o:o + c_old])
+                        o += c_old
+                    hid = torch.cat(parts)
+            vec, nrm, hid = cns_oracle.forward(W, bt, hid, dtype=torch.float64)
+            counts = bt.num_clusters.clone()
+            loss = loss + cns_oracle.objectives((vec, nrm), bt.vel_si)[2]
+        loss.backward()
+        return float(loss.detach()), {k: v.grad for k, v in W.items()}
+
+    for rule in ("scene", "batch"):
+        loss_ref, gref = oracle(rule)
+        net = GraphVS(2, 2, 128).to("cuda:0")
+        net.load_state_dict(state_dict)
+        net.train()
+        stepper = TBPTTStepper(net, fused=False, hidden_reset=rule)
+        loss, _ = stepper.window_loss([b.to("cuda:0") for b in windows])
+        loss.backward()
+        assert abs(float(loss) - loss_ref) < 1e-5 * max(1.0, abs(loss_ref)), rule
+        scale = max(float(g.abs().max()) for g in gref.values())
+        for name, p in net.named_parameters():
+            err = float((p.grad.double().cpu() - gref[name]).abs().max())
+            assert err <= 1e-4 * float(gref[name].abs().max()) + 2e-6 * scale, (rule, name, err)
+    # the two rules really differ on this window
+    assert abs(oracle("scene")[0] - oracle("batch")[0]) > 1e-6
