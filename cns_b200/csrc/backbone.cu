@@ -232,25 +232,15 @@ int graphnorm_relu(const GraphNormArgs& a, cudaStream_t s) {
 // velocity post-processing  vel = vec/(|vec|+1e-7) * (1+elu(norm)), vel[:3] *= tPo_norm
 // (graph_vs.py:254-270, functions.py:26-38).
 // A CTA of 8 warps owns 8 graphs: warp w pools graph w (a lane owns 4 channels, rows are read as whole 512-byte
-// lines), then the 256 threads run the first layer of both heads for all 8 graphs at once - one weight load feeds
-// 8 FMAs (one CTA per graph re-read the two 64 KB head matrices from L2 for every graph: 134 MB per 1024 graphs).
+// lines), then the 256 threads run the first layer of both heads for all 8 graphs at once - one weight load (from L2)
+// feeds 8 FMAs (one CTA per graph re-read the two 64 KB head matrices from L2 for every graph: 134 MB per 1024 graphs).
 // A graph whose clusters are all masked yields x_scene = 0 (PyG would drop the row).
 // =============================================================================================
 constexpr int PH_G = 8;          // graphs per CTA
 
-__global__ void __launch_bounds__(256)
+// 72 registers x 256 threads + 13.5 KB: fits beside a resident encoder CTA (640 threads x 72 registers, 207 KB)
+__global__ void __maxnreg__(72)
 pool_head_kernel(PoolHeadArgs p) {
-  // both head matrices (2 x 64 KB) arrive by two 1-D TMA bulk copies while the warps pool their graphs
-  extern __shared__ __align__(128) unsigned char ph_smem[];
-  float* w_s = reinterpret_cast<float*>(ph_smem);
-  __shared__ __align__(8) uint64_t w_bar;
-  if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&w_bar), 1);
-    fence_mbar_init();
-    mbar_expect_tx(smem_u32(&w_bar), 2 * H * H * sizeof(float));
-    bulk_g2s(smem_u32(w_s), p.vec0_t, H * H * sizeof(float), smem_u32(&w_bar));
-    bulk_g2s(smem_u32(w_s + H * H), p.nrm0_t, H * H * sizeof(float), smem_u32(&w_bar));
-  }
   __shared__ __align__(16) float xs[PH_G][H];
   __shared__ __align__(16) float hid[2][PH_G][H];
   __shared__ float outv[PH_G][8];
@@ -313,19 +303,34 @@ pool_head_kernel(PoolHeadArgs p) {
   // ---- first layers of both heads: thread = (head, output channel), all 8 graphs per weight load ---------
   {
     const int o = tid & (H - 1), hd = tid >> 7;
-    const float* __restrict__ wt = w_s + hd * (H * H);
+    const float* __restrict__ wt = hd ? p.nrm0_t : p.vec0_t;
     const float b = hd ? p.nrm0_b[o] : p.vec0_b[o];
-    mbar_wait(smem_u32(&w_bar), 0);
     float acc[PH_G];
 #pragma unroll
     for (int g = 0; g < PH_G; ++g) acc[g] = b;
-#pragma unroll 4
-    for (int k = 0; k < H; k += 4) {
-      const float w0 = wt[k * H + o], w1 = wt[(k + 1) * H + o], w2 = wt[(k + 2) * H + o], w3 = wt[(k + 3) * H + o];
+    // the weights come straight from L2 (a warp reads 128 consecutive bytes per k), 16 loads in flight per thread: the
+    // kernel needs no large shared-memory block, so its CTAs fit beside the resident encoder / backbone CTAs of a
+    // neighbouring forward instead of waiting for a free SM (staged through 128 KB of shared memory it held 128 SMs
+    // for 17 us per step)
+    float wn[16];                               // the next round's weights, loaded while this round's FMAs run
 #pragma unroll
-      for (int g = 0; g < PH_G; ++g) {
-        const float4 x = *reinterpret_cast<const float4*>(&xs[g][k]);      // broadcast read
-        acc[g] = fmaf(x.w, w3, fmaf(x.z, w2, fmaf(x.y, w1, fmaf(x.x, w0, acc[g]))));
+    for (int i = 0; i < 16; ++i) wn[i] = __ldg(wt + i * H + o);
+#pragma unroll 1
+    for (int k0 = 0; k0 < H; k0 += 16) {
+      float w[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = wn[i];
+      if (k0 + 16 < H) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) wn[i] = __ldg(wt + (k0 + 16 + i) * H + o);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+#pragma unroll
+        for (int g = 0; g < PH_G; ++g) {
+          const float4 x = *reinterpret_cast<const float4*>(&xs[g][k0 + i]);      // broadcast read
+          acc[g] = fmaf(x.w, w[i + 3], fmaf(x.z, w[i + 2], fmaf(x.y, w[i + 1], fmaf(x.x, w[i], acc[g]))));
+        }
       }
     }
 #pragma unroll
@@ -374,11 +379,7 @@ pool_head_kernel(PoolHeadArgs p) {
 
 int pool_head(const PoolHeadArgs& a, cudaStream_t s) {
   if (a.n_graphs == 0) return CNS_OK;
-  static unsigned long long configured = 0;
-  constexpr int PH_SMEM = 2 * H * H * (int)sizeof(float);
-  if (first_use_on_device(configured))
-    CNS_CUDA_CHECK(cudaFuncSetAttribute(pool_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
-  pool_head_kernel<<<(unsigned)ceil_div(a.n_graphs, PH_G), 256, PH_SMEM, s>>>(a);
+  pool_head_kernel<<<(unsigned)ceil_div(a.n_graphs, PH_G), 256, 0, s>>>(a);
   CNS_LAUNCH_CHECK();
   return CNS_OK;
 }
