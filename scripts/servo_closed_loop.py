@@ -3,7 +3,7 @@
 (cns_b200.stop_policy.BatchedPixelStop, the reference's stop rule: waiting_time 0.8 s, conduct_thresh 0.01,
 cns/benchmark/benchmark.py:220).  Reports how many scenes stopped, the pose error at the stop and the frame rate.
 
-    python scripts/servo_closed_loop.py [B=256] [N=512] [precision=f16] [max_frames=500]
+    python scripts/servo_closed_loop.py [B=256] [N=512] [precision=f16] [max_frames=500] [cache]
 """
 import json
 import os
@@ -18,7 +18,8 @@ import torch
 from cns_b200 import BatchedPixelStop, GraphVS, ckpt, sim_device, synth
 
 
-def run(B=256, N=512, precision="f16", max_frames=500, layouts=32, missing=0.1, gain=2.0, seed=11, device="cuda:0"):
+def run(B=256, N=512, precision="f16", max_frames=500, layouts=32, missing=0.1, gain=2.0, seed=11, device="cuda:0",
+        cache=False):
     rng = np.random.default_rng(seed)
     np.random.seed(seed)
     env = sim_device.DeviceSceneBatch(1, rng, device=device, max_points=8, missing=(missing, missing))
@@ -35,14 +36,16 @@ def run(B=256, N=512, precision="f16", max_frames=500, layouts=32, missing=0.1, 
     active = torch.ones(B, dtype=torch.bool, device=device)
     stop_frame = np.full(B, -1)
     ang0, mm0 = sim_device.pose_error(env.cur_wcT, env.tar_wcT)
-    hidden = None
+    hidden, tcache = None, None
     torch.cuda.synchronize()
     t0 = time.time()
     frames = 0
     with torch.no_grad():
         for k in range(max_frames):
             batch = env.observe()
-            vec, nrm, hidden = net(batch, hidden)
+            if cache and tcache is None:      # per-target terms (and, in f16 mode, per-keypoint target-side logits / values) once
+                tcache = net.build_target_cache(batch)
+            vec, nrm, hidden = net(batch, hidden, target_cache=tcache)
             vel = net.postprocess((vec, nrm), batch)
             stop = stop_rule(batch.pos_cur, batch.pos_tar, batch.node_mask, k * synth.DT)
             newly = stop & (stop_frame < 0)
@@ -58,7 +61,8 @@ def run(B=256, N=512, precision="f16", max_frames=500, layouts=32, missing=0.1, 
     ang, mm = ang.cpu().numpy(), mm.cpu().numpy()
     done = stop_frame >= 0
     q = lambda a: [float(np.percentile(a, p)) for p in (50, 90, 100)] if len(a) else None
-    return {"scenes": B, "keypoints": N, "precision": precision, "missing": missing, "gain": gain, "frames_run": frames,
+    return {"scenes": B, "keypoints": N, "precision": precision, "target_cache": bool(cache), "missing": missing, "gain": gain,
+            "frames_run": frames,
             "stopped": int(done.sum()), "stop_frame_p50_p90_max": q(stop_frame[done]),
             "initial_rot_deg_p50_p90_max": q(ang0.cpu().numpy()), "initial_trans_mm_p50_p90_max": q(mm0.cpu().numpy()),
             "final_rot_deg_p50_p90_max": q(ang[done]), "final_trans_mm_p50_p90_max": q(mm[done]),
@@ -71,4 +75,4 @@ if __name__ == "__main__":
     N = int(a[1]) if len(a) > 1 else 512
     prec = a[2] if len(a) > 2 else "f16"
     mf = int(a[3]) if len(a) > 3 else 500
-    print(json.dumps(run(B, N, prec, mf)))
+    print(json.dumps(run(B, N, prec, mf, cache=len(a) > 4 and a[4] == "cache")))
