@@ -246,3 +246,40 @@ def test_degenerate_similarity_rule_matches_sklearn():
         assert labels is not None and np.array_equal(labels, ref), (X.shape, labels, ref)
     _, labels = _prepare_similarity(np.random.default_rng(0).random((30, 2)))
     assert labels is None
+
+
+def test_tbptt_hidden_rows_follow_scenes_that_restart_one_by_one():
+    """TBPTTStepper._carry_hidden (host logic, no kernels): with `hidden_reset="scene"` the rows of restarted scenes are
+    replaced by zeros - spliced in at the scene's NEW cluster count - while the other scenes keep their rows in order;
+    the reference's literal rule (`"batch"`, train_gvs_short_seq.py:28) drops the whole state; a state whose row count
+    does not match the frame is never reused."""
+    from types import SimpleNamespace
+    from cns_b200.train import TBPTTStepper
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w, self.b = torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(1))
+
+        def get_parameter_groups(self):
+            return [self.w], [self.b]
+
+    frame = lambda counts, fresh: SimpleNamespace(num_clusters=torch.tensor(counts), new_scene=torch.tensor(fresh))
+    old_counts = [2, 3, 1]
+    hidden = torch.arange(6, dtype=torch.float32).reshape(6, 1).repeat(1, 128) + 1      # rows 1..6
+    for rule in ("scene", "batch"):
+        st = TBPTTStepper(Tiny(), fused=False, hidden_reset=rule)
+        assert st._carry_hidden(frame(old_counts, [True] * 3)) is None                     # no state yet
+        st.hidden, st._counts = hidden.clone(), torch.tensor(old_counts)
+        same = st._carry_hidden(frame(old_counts, [False] * 3))
+        assert same is st.hidden                                                            # nothing restarted
+        got = st._carry_hidden(frame([2, 4, 1], [False, True, False]))                      # scene 1 is back with 4 clusters
+        if rule == "batch":
+            assert got is None
+        else:
+            assert got.shape == (7, 128)
+            assert got[:, 0].tolist() == [1, 2, 0, 0, 0, 0, 6]
+        assert st._carry_hidden(frame([2, 3, 1], [True, True, True])) is None               # everything restarted
+        # a cluster count changed WITHOUT a restart flag: the rows cannot be matched, the state is dropped
+        assert st._carry_hidden(frame([2, 4, 1], [True, False, False])) is None
+        assert st._carry_hidden(frame([2, 2, 1], [False, False, False])) is None
