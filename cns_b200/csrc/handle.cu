@@ -288,6 +288,8 @@ int cns_create(cns_handle** out, int device) {
 
 int cns_destroy(cns_handle* h) {
   if (!h) return CNS_OK;
+  int prev_device = -1;
+  cudaGetDevice(&prev_device);                // the caller's current device is restored on the way out
   cudaSetDevice(h->device);
   if (h->ev[0]) for (int i = 0; i < 2 * 256; ++i) cudaEventDestroy(h->ev[i]);
   cudaFree(h->raw);
@@ -308,6 +310,7 @@ int cns_destroy(cns_handle* h) {
   if (h->stage_dev) cudaFree(h->stage_dev);
   if (h->servo_hid) cudaFree(h->servo_hid);
   delete h;
+  if (prev_device >= 0) cudaSetDevice(prev_device);
   return CNS_OK;
 }
 
