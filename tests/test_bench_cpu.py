@@ -24,3 +24,16 @@ def test_reference_arm_line_has_the_contract_keys():
     e2e = line["e2e"]
     assert e2e["value"] == line["value"] and e2e["unit"] == line["unit"]
     assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """Launched like the driver launches N > 1 (one process per GPU): rank 0 alone runs the CPU arm and prints the line, the
+    other ranks exit 0 without work."""
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--graphs", "16", "--points", "64"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{") and '"impl": "reference"' in l]
+    assert len(lines) == 1
+    assert json.loads(lines[0])["n_gpus"] == 2
